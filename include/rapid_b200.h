@@ -1,0 +1,228 @@
+/*
+ * rapid_b200 — C ABI of the B200-native cut-detection + fast-round-tally path of Rapid.
+ *
+ * This is the drop-in boundary.  The reference (lalithsuresh/rapid) is Java; the classes
+ * on the hot path — MembershipView, MultiNodeCutDetector, FastPaxos — are package-private concrete
+ * classes constructed directly by Cluster.Builder / MembershipService, so the binding a maintainer adds is
+ * a JNI veneer (java/com/vrg/rapid/gpu/Native.java + java/jni/rapid_jni.c, shown in INTEGRATION.md) whose
+ * native methods are exactly the entry points below: plain pointers and sizes, no C++/torch types.
+ *
+ * Citations are relative to /root/reference/rapid/src/main/java/com/vrg/rapid/.
+ *
+ * Conventions
+ *   - every function returns an int32 status: RAPID_OK or a negative RAPID_E* code; rapid_last_error()
+ *     gives the thread-local message.  No exception crosses the ABI.
+ *   - handles are opaque, library-owned, freed by *_destroy; a handle is single-writer (the reference runs
+ *     all protocol logic on one "protocol" thread, SharedResources.java:53); distinct handles may be used
+ *     from distinct threads.
+ *   - array arguments are caller-owned HOST memory unless the parameter name ends in _dev.
+ *   - node ids: members are 0..n-1 in the order given to rapid_view_create; joiners registered with
+ *     rapid_view_register_joiners get ids n, n+1, ...
+ *   - the library needs a CUDA device: there is no CPU fallback; without one every create fails RAPID_ECUDA.
+ */
+#ifndef RAPID_B200_H
+#define RAPID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built -fvisibility=hidden; only this header is exported */
+#endif
+
+#define RAPID_OK                0
+#define RAPID_EINVAL           (-1)   /* bad K/H/L (MultiNodeCutDetector.java:52-55), ring >= K, bad size/id */
+#define RAPID_ENOT_IN_RING     (-2)   /* MembershipView.NodeNotInRingException      (MembershipView.java:508-512) */
+#define RAPID_EALREADY_IN_RING (-3)   /* MembershipView.NodeAlreadyInRingException  (:502-506) */
+#define RAPID_EUUID_SEEN       (-4)   /* MembershipView.UUIDAlreadySeenException    (:514-519) */
+#define RAPID_EHASH_COLLISION  (-5)   /* two endpoints tie on a ring key: the Java TreeSet would silently drop one */
+#define RAPID_ECUDA            (-6)
+#define RAPID_ENCCL            (-7)
+#define RAPID_ENOMEM           (-8)
+#define RAPID_EUNSUPPORTED     (-9)
+
+#define RAPID_EDGE_UP   0   /* rapid.proto EdgeStatus */
+#define RAPID_EDGE_DOWN 1
+
+#define RAPID_MAX_K 14      /* ring-report bits 0..13 of the 16-bit per-(subject,receiver) state word */
+
+typedef struct rapid_view rapid_view;   /* MembershipView: K rings in HBM (SoA)                       */
+typedef struct rapid_cd   rapid_cd;     /* MultiNodeCutDetector state of R virtual nodes in HBM       */
+typedef struct rapid_fp   rapid_fp;     /* FastPaxos fast-round tally of one configuration            */
+typedef struct rapid_comm rapid_comm;   /* NCCL communicator for the sharded (multi-GPU) tally         */
+
+const char* rapid_version(void);
+int32_t rapid_last_error(char* buf, size_t cap);
+int32_t rapid_device_count(int32_t* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * MembershipView  (MembershipView.java)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Bulk constructor MembershipView(K, nodeIds, endpoints) (:74-89): ring k = endpoints ordered by the signed
+ * 64-bit key  xx_k(hostname) * 31 + xx_k.hashInt(port)  (AddressComparator :562-587, XXH64 seed k).
+ * host_bytes = hostnames concatenated, host_off[n+1] their offsets.  A key tie on any ring returns
+ * RAPID_EALREADY_IN_RING if the two endpoints are identical, else RAPID_EHASH_COLLISION (we refuse rather than
+ * silently drop like TreeSet.add).  n may be 0. */
+int32_t rapid_view_create(rapid_view** out, int32_t K, int64_t n, const uint8_t* host_bytes,
+                          const int32_t* host_off, const int32_t* port, int32_t device);
+int32_t rapid_view_destroy(rapid_view* v);
+int32_t rapid_view_size(const rapid_view* v, int64_t* out_n);                  /* getMembershipSize :425-432 */
+int32_t rapid_view_ring(const rapid_view* v, int32_t k, int32_t* out_ids /*n*/);      /* getRing :380-388 */
+int32_t rapid_view_keys(const rapid_view* v, int32_t k, int64_t* out_keys /*n, by node id*/);
+/* getObserversOf :210-257 (ring successors) / getSubjectsOf :267-282 (ring predecessors).
+ * *out_count = K, or 0 when the view has <= 1 member; RAPID_ENOT_IN_RING if node is not a member. */
+int32_t rapid_view_observers(const rapid_view* v, int32_t node, int32_t* out /*K*/, int32_t* out_count);
+int32_t rapid_view_subjects(const rapid_view* v, int32_t node, int32_t* out /*K*/, int32_t* out_count);
+/* getExpectedObserversOf :292-303 — ring PREDECESSORS of where the endpoint would sit; works for non-members;
+ * *out_count = 0 only for an empty view. */
+int32_t rapid_view_expected_observers(const rapid_view* v, const uint8_t* host, int32_t len, int32_t port,
+                                      int32_t* out /*K*/, int32_t* out_count);
+/* getRingNumbers(observer, subject) :397-418 as a bitmask {k : subject is observer's predecessor on ring k}. */
+int32_t rapid_view_ring_numbers(const rapid_view* v, int32_t observer, int32_t subject, uint16_t* out_mask);
+/* All members at once: out_obs[i*K+k], out_subj[i*K+k] (-1 when the view has <= 1 member). */
+int32_t rapid_view_tables(const rapid_view* v, int32_t* out_obs, int32_t* out_subj);
+/* Configuration.getConfigurationId :544-556 over identifiersSeen (sorted by signed (high, low), :474-500)
+ * followed by the ring-0 endpoint order. */
+int32_t rapid_view_config_id(const rapid_view* v, const int64_t* id_high, const int64_t* id_low, int64_t n_ids,
+                             int64_t* out);
+/* Register joining endpoints (the edgeDst of UP alerts).  They get ids n.. ; their expected observers
+ * (getExpectedObserversOf) and ring-0 keys are computed on device.  RAPID_EALREADY_IN_RING if one is a member. */
+int32_t rapid_view_register_joiners(rapid_view* v, int64_t n_add, const uint8_t* host_bytes,
+                                    const int32_t* host_off, const int32_t* port, int32_t* out_first_id);
+int32_t rapid_view_num_joiners(const rapid_view* v, int64_t* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * MultiNodeCutDetector for R virtual nodes ("receivers")   (MultiNodeCutDetector.java,
+ * MembershipService.java:300-354 batch driver, :644-675 filter)
+ *
+ * Receiver r (0 <= r < n_receivers) is the virtual node at ring-0 position receiver_begin + r, i.e. a shard
+ * is a contiguous range of the ring-0 hash order.  State per (subject slot, receiver) is one uint16 in HBM,
+ * laid out [slot][receiver] so that a warp touches consecutive receivers.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* mode flags for rapid_cd_create */
+#define RAPID_CD_SERVICE   0u   /* MembershipService semantics: filter, announcedProposal gating, union per batch */
+#define RAPID_CD_RAW       1u   /* bare MultiNodeCutDetector semantics (aggregate / invalidate calls)             */
+#define RAPID_CD_SWEEP     2u   /* force the per-cell sweep kernel (exact counters; the simple path)               */
+#define RAPID_CD_BUCKETED  4u   /* force the subject-bucketed kernels (the fast path; SERVICE mode only)            */
+
+/* delivery description: which receiver gets which cells, in which order */
+#define RAPID_DELIVERY_BLOCKED  1u   /* blocked[r] != 0: receiver r receives nothing this batch             */
+#define RAPID_DELIVERY_BITMAP   2u   /* bitmap[cell][ceil(R/32)]: bit (r&31) of word r>>5 set = delivered   */
+#define RAPID_DELIVERY_PERMUTED 4u   /* receiver r applies its cells in ascending
+                                        splitmix64( splitmix64(perm_seed + receiver_begin + r) ^ cell_index ) */
+typedef struct rapid_delivery {
+    uint32_t        flags;
+    const uint8_t*  blocked;     /* [R]                    (host) */
+    const uint32_t* bitmap;      /* [n_cells][ceil(R/32)]  (host) */
+    uint64_t        perm_seed;
+} rapid_delivery;
+
+/* ctor validation of MultiNodeCutDetector.java:51-55 (H <= K, L <= H, K >= 3, L > 0) -> RAPID_EINVAL.
+ * K comes from the view.  max_subjects bounds the number of distinct subjects per configuration epoch
+ * (0 = default). */
+int32_t rapid_cd_create(rapid_cd** out, const rapid_view* v, int32_t H, int32_t L, int64_t n_receivers,
+                        int64_t receiver_begin, uint32_t mode_flags, int64_t max_subjects);
+int32_t rapid_cd_destroy(rapid_cd* cd);
+
+/* One BatchedAlertMessage worth of alert cells applied to every receiver:  filter (cfg match, UP => dst not a
+ * member, DOWN => dst a member; MembershipService.java:644-675)  ->  aggregateForProposal per cell in order
+ * (MultiNodeCutDetector.java:84-128)  ->  invalidateFailingEdges (:137-164)  ->  union  ->  announcedProposal
+ * (MembershipService.java:318-348).  A cell is one (edgeSrc, edgeDst, ring, status) report; an AlertMessage with r
+ * ring numbers is r consecutive cells.  cell_cfg == NULL means every cell carries cfg_id.  delivery == NULL
+ * means every receiver gets every cell in array order.
+ * Outputs (each may be NULL), per receiver:
+ *   proposal_hash / proposal_hash2 : order-independent 128-bit fingerprint of the proposal announced by THIS batch
+ *                                    (see rapid_proposal_fingerprint), 0 if none
+ *   proposal_len                   : its size (0 if none)
+ *   announced                      : announcedProposal after the batch */
+int32_t rapid_cd_apply_batch(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src, const int32_t* dst,
+                             const uint8_t* ring, const uint8_t* status, const int64_t* cell_cfg,
+                             const rapid_delivery* delivery, uint64_t* proposal_hash, uint64_t* proposal_hash2,
+                             int32_t* proposal_len, uint8_t* announced);
+/* Same, with the cell arrays (and delivery arrays) already resident in device memory and no per-receiver
+ * readback: results stay on the device for rapid_fp_tally_cd / rapid_cd_read_outputs. */
+int32_t rapid_cd_apply_batch_dev(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src_dev,
+                                 const int32_t* dst_dev, const uint8_t* ring_dev, const uint8_t* status_dev,
+                                 const int64_t* cell_cfg_dev, const rapid_delivery* delivery_dev);
+int32_t rapid_cd_read_outputs(const rapid_cd* cd, uint64_t* proposal_hash, uint64_t* proposal_hash2,
+                              int32_t* proposal_len, uint8_t* announced);
+/* The proposal receiver r announced, in canonical order = sorted by the ring-0 comparator
+ * (MembershipService.java:346-348). */
+int32_t rapid_cd_get_proposal(const rapid_cd* cd, int64_t receiver, int32_t* out_ids, int32_t cap, int32_t* out_len);
+/* getNumProposals :62-66.  Exact on sweep handles; RAPID_EUNSUPPORTED on bucketed handles. */
+int32_t rapid_cd_num_proposals(const rapid_cd* cd, int64_t receiver, int32_t* out);
+/* clear() :169-178 + announcedProposal = false (MembershipService.java:425-426) for every receiver. */
+int32_t rapid_cd_clear(rapid_cd* cd);
+/* Parity aid: the ring-report bitmask per subject for one receiver (reportsPerHost as bitmasks). */
+int32_t rapid_cd_debug_masks(const rapid_cd* cd, int64_t receiver, int32_t* out_subject_ids, uint16_t* out_masks,
+                             int32_t cap, int32_t* out_n);
+int32_t rapid_cd_debug_counters(const rapid_cd* cd, int64_t receiver, int32_t* updates_in_progress,
+                                int32_t* seen_link_down);
+/* Which kernel family served the last batch: 1 = sweep, 2 = bucketed-uniform, 3 = bucketed-generic;
+ * *n_kernel_launches = CUDA kernels launched by the last apply call. */
+int32_t rapid_cd_last_path(const rapid_cd* cd, int32_t* path, int32_t* n_kernel_launches);
+
+/* RAW mode (RAPID_CD_RAW handles): the bare detector API the reference's CutDetectionTest drives.
+ * aggregateForProposal(AlertMessage) :76-82 for every receiver (no filter, no announced gating); returns the
+ * endpoints emitted for `receiver` by this call. */
+int32_t rapid_cd_aggregate(rapid_cd* cd, int64_t n_cells, const int32_t* src, const int32_t* dst,
+                           const uint8_t* ring, const uint8_t* status, int64_t receiver, int32_t* out_ids,
+                           int32_t cap, int32_t* out_len);
+/* invalidateFailingEdges(view) :137-164 */
+int32_t rapid_cd_invalidate(rapid_cd* cd, int64_t receiver, int32_t* out_ids, int32_t cap, int32_t* out_len);
+
+/* Fingerprint of a proposal (a SET of node ids): h1 = sum mix1(id), h2 = sum mix2(id) (mod 2^64). */
+int32_t rapid_proposal_fingerprint(const int32_t* ids, int64_t n, uint64_t* h1, uint64_t* h2);
+
+/* ------------------------------------------------------------------------------------------------
+ * FastPaxos fast round  (FastPaxos.java:125-156 handleFastRoundProposal)
+ * ---------------------------------------------------------------------------------------------- */
+/* One instance per configuration (FastPaxos ctor :61-85).  sender ids are int32 in [0, sender_capacity);
+ * senders need not be members (the reference never checks). */
+int32_t rapid_fp_create(rapid_fp** out, int64_t cfg_id, int64_t membership_size, int64_t sender_capacity,
+                        int32_t device);
+int32_t rapid_fp_destroy(rapid_fp* fp);
+/* Apply n_votes FastRoundPhase2bMessages in array order: ignore if vote_cfg != cfg (:126), sender already
+ * voted (:134) or already decided (:138); count identical proposals; decide when count >= N - floor((N-1)/4)
+ * (:145-150).  A proposal is identified by (hash, hash2, len) = rapid_proposal_fingerprint + size.
+ * vote_cfg / proposal_hash2 / proposal_len may be NULL (= cfg / 0 / 0).
+ * Outputs: decided, the decided fingerprint, its vote count at the moment of decision (== quorum) and
+ * votesReceived.size() at that moment (or the running totals if undecided). */
+int32_t rapid_fp_tally(rapid_fp* fp, int64_t n_votes, const int32_t* sender, const int64_t* vote_cfg,
+                       const uint64_t* proposal_hash, const uint64_t* proposal_hash2, const int32_t* proposal_len,
+                       int32_t* decided, uint64_t* decided_hash, uint64_t* decided_hash2, int32_t* decided_len,
+                       int32_t* decided_count, int32_t* votes_received);
+/* Votes straight from the detector's device-resident outputs: every receiver that announced a proposal in the last
+ * batch votes for it (FastPaxos.propose :94-108; sender = its node id).  comm == NULL: single GPU.  comm != NULL:
+ * every rank calls this with its shard; the local proposal-hash histograms are combined with one NCCL
+ * all-reduce (plus a small verification all-reduce) and every rank gets the same answer. */
+int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, int32_t* decided,
+                          uint64_t* decided_hash, uint64_t* decided_hash2, int32_t* decided_len,
+                          int32_t* decided_count, int32_t* votes_received);
+int32_t rapid_fp_quorum(int64_t membership_size, int64_t* out);   /* N - floor((N-1)/4) */
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU; receivers sharded by ring-0 range; one all-reduce on the histogram)
+ * ---------------------------------------------------------------------------------------------- */
+#define RAPID_NCCL_UNIQUE_ID_BYTES 128
+int32_t rapid_comm_unique_id(void* out_id /*128 bytes*/);
+int32_t rapid_comm_init(rapid_comm** out, int32_t rank, int32_t world, const void* nccl_unique_id, int32_t device);
+int32_t rapid_comm_destroy(rapid_comm* c);
+
+/* Timing aid for bench.py: device time (ms) of the last rapid_cd_apply_batch[_dev] / rapid_fp_tally[_cd] call,
+ * measured with CUDA events on the handle's stream; and per-kernel breakdown of the last apply. */
+int32_t rapid_cd_last_device_ms(const rapid_cd* cd, float* total_ms, float* main_kernel_ms);
+int32_t rapid_fp_last_device_ms(const rapid_fp* fp, float* total_ms);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAPID_B200_H */

@@ -1,0 +1,762 @@
+// Cut detector: handle lifecycle, batch preprocessing (filter + subject-slot dictionary), the exact per-cell
+// sweep kernel, accessors and the C ABI.
+//
+// Reference semantics (rapid/src/main/java/com/vrg/rapid/):
+//   MultiNodeCutDetector.java:84-128  aggregateForProposal (per cell, in arrival order)
+//   MultiNodeCutDetector.java:137-164 invalidateFailingEdges
+//   MembershipService.java:300-354    batch driver (union of emissions, announcedProposal gating)
+//   MembershipService.java:644-675    filterAlertMessages
+// The Java keeps Map<Endpoint, Map<Integer, Endpoint>> per process; here the state of R virtual nodes is a
+// [subject slot][receiver] array of 16-bit ring masks in HBM and every receiver is one CUDA thread (sweep
+// kernel) or a SWAR lane of the subject-bucketed kernels (cd_bucketed.cu).
+#include <algorithm>
+#include <climits>
+
+#include "cd_internal.cuh"
+
+namespace rapid {
+
+// =====================================================================================================
+// preprocessing kernels
+// =====================================================================================================
+__global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// validity of a cell (MembershipService.java:644-675) and first-occurrence index of not-yet-slotted subjects
+__global__ void k_filter_first(int64_t A, const int32_t* __restrict__ dst, const uint8_t* __restrict__ ring,
+                               const uint8_t* __restrict__ status, const int64_t* __restrict__ cell_cfg, int64_t cfg,
+                               int raw, int K, int64_t n_members, int64_t n_total, const int32_t* __restrict__ slot_of,
+                               int32_t* __restrict__ first_idx, int32_t* __restrict__ cell_slot /* -1 invalid, -2 valid */,
+                               BatchCounts* __restrict__ bc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    const int32_t d = dst[i];
+    int32_t v = -2;
+    if (ring[i] >= K) { atomicMax(&bc->bad_ring, (int32_t)i); v = -1; }
+    if (d < 0 || d >= n_total) { atomicMax(&bc->bad_dst, (int32_t)i); v = -1; }
+    if (v == -2 && !raw) {
+        const bool present = d < n_members;                       // isHostPresent
+        const int st = status[i];
+        if (cell_cfg && cell_cfg[i] != cfg) v = -1;                // :653
+        else if (st == RAPID_EDGE_UP && present) v = -1;           // :660-665
+        else if (st == RAPID_EDGE_DOWN && !present) v = -1;        // :666-671
+        else if (st != RAPID_EDGE_UP && st != RAPID_EDGE_DOWN) v = -1;
+    }
+    cell_slot[i] = v;
+    if (v == -2) {
+        if (status[i] == RAPID_EDGE_DOWN) bc->any_down = 1;
+        if (slot_of[d] < 0) atomicMin(&first_idx[d], (int32_t)i);
+    }
+}
+
+__global__ void k_mark_new(int64_t A, const int32_t* __restrict__ dst, const int32_t* __restrict__ cell_slot,
+                           const int32_t* __restrict__ slot_of, const int32_t* __restrict__ first_idx,
+                           int32_t* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    const int32_t d = dst[i];
+    flag[i] = (cell_slot[i] == -2 && slot_of[d] < 0 && first_idx[d] == (int32_t)i) ? 1 : 0;
+}
+
+// single-block exclusive scan (A is at most a few million; this is a few microseconds of work)
+__global__ void k_exclusive_scan(int32_t* __restrict__ data, int64_t n, int32_t* __restrict__ total) {
+    __shared__ int32_t part[1024];
+    const int T = blockDim.x, t = threadIdx.x;
+    const int64_t per = (n + T - 1) / T;
+    const int64_t b = (int64_t)t * per, e = b + per < n ? b + per : n;
+    int32_t s = 0;
+    for (int64_t i = b; i < e; ++i) s += data[i];
+    part[t] = s;
+    __syncthreads();
+    for (int off = 1; off < T; off <<= 1) {           // Hillis-Steele inclusive scan of the partials
+        int32_t v = t >= off ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int32_t run = t ? part[t - 1] : 0;
+    for (int64_t i = b; i < e; ++i) { const int32_t v = data[i]; data[i] = run; run += v; }
+    if (t == T - 1) *total = part[T - 1];
+}
+
+__global__ void k_assign_slots(int64_t A, const int32_t* __restrict__ dst, const int32_t* __restrict__ cell_slot,
+                               const int32_t* __restrict__ rank, const int32_t* __restrict__ n_new, int32_t S_old,
+                               int32_t* __restrict__ slot_of, int32_t* __restrict__ first_idx,
+                               int32_t* __restrict__ slot_subject, BatchCounts* __restrict__ bc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) bc->n_slots = S_old + *n_new;
+    if (i >= A) return;
+    const int32_t d = dst[i];
+    if (cell_slot[i] == -2 && first_idx[d] == (int32_t)i) {       // first valid cell of a subject without a slot
+        const int32_t slot = S_old + rank[i];
+        slot_of[d] = slot;
+        slot_subject[slot] = d;
+        first_idx[d] = INT_MAX;
+    }
+}
+
+__global__ void k_cell_slots(int64_t A, const int32_t* __restrict__ dst, const int32_t* __restrict__ slot_of,
+                             int32_t* __restrict__ cell_slot, BatchCounts* __restrict__ bc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    if (cell_slot[i] == -2) { cell_slot[i] = slot_of[dst[i]]; atomicAdd(&bc->n_valid, 1); }
+}
+
+// =====================================================================================================
+// the sweep kernel: one thread == one receiver == one MultiNodeCutDetector, cells in arrival order
+// =====================================================================================================
+struct SweepArgs {
+    int K, H, L, raw, do_cells, do_inval;
+    int64_t R;
+    RowRef rows;
+    int32_t S;
+    const int32_t* slot_subject;
+    const int32_t* slot_of;
+    const int32_t* obs;          // [id][K]: members -> ring successors, joiners -> expected observers
+    int64_t A;
+    const int32_t* cell_slot;
+    const uint8_t* ring;
+    const uint8_t* status;
+    DeliveryDev dl;
+    int32_t* n_pre;
+    int32_t* n_prop;
+    uint32_t* rflags;
+    uint64_t* out_h1;
+    uint64_t* out_h2;
+    int32_t* out_len;
+    uint8_t* out_ann;
+};
+
+__global__ void __launch_bounds__(128) k_sweep(const SweepArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    uint32_t flags = a.rflags[r];
+    flags &= ~RF_ANN_NOW;
+    if (!a.raw && (flags & RF_ANNOUNCED)) {            // MembershipService.java:318-319
+        a.rflags[r] = flags;
+        if (a.out_ann) a.out_ann[r] = 1;
+        return;
+    }
+    if ((a.dl.flags & RAPID_DELIVERY_BLOCKED) && a.dl.blocked[r]) {
+        a.rflags[r] = flags;
+        if (a.out_ann) a.out_ann[r] = (flags & RF_ANNOUNCED) ? 1 : 0;
+        return;
+    }
+    const uint32_t RM = (1u << a.K) - 1u;
+    int32_t npre = a.n_pre[r], nprop = a.n_prop[r];
+    bool seen = flags & RF_SEEN_DOWN;
+    uint64_t oh1 = 0, oh2 = 0;
+    int32_t olen = 0;
+
+    // proposal emission (:110-121): everything at >= H that has not been emitted yet leaves in one proposal
+    auto emit = [&]() {
+        for (int32_t s = 0; s < a.S; ++s) {
+            uint16_t* p = a.rows.row(s) + r;
+            const uint32_t w = *p;
+            if (!(w & CD_BIT_EMIT) && __popc(w & RM) >= a.H) {
+                *p = (uint16_t)(w | CD_BIT_EMIT | (a.raw ? CD_BIT_CALL : 0u));
+                const int32_t id = a.slot_subject[s];
+                oh1 += fp_mix1(id);
+                oh2 += fp_mix2(id);
+                ++olen;
+            }
+        }
+        ++nprop;
+    };
+    // one (dst slot, ring) report (:84-128); returns after updating counters
+    auto report = [&](int32_t slot, int k) {
+        uint16_t* p = a.rows.row(slot) + r;
+        uint32_t w = *p;
+        const uint32_t bit = 1u << k;
+        if (w & bit) return;                               // duplicate announcement, ignore (:97-99)
+        w |= bit;
+        *p = (uint16_t)w;
+        const int c = __popc(w & RM);
+        if (c == a.L) ++npre;                              // :104-107
+        if (c == a.H) {                                    // :109-121
+            --npre;
+            if (npre == 0) emit();
+        }
+    };
+
+    if (a.do_cells) {
+        const bool has_bitmap = a.dl.flags & RAPID_DELIVERY_BITMAP;
+        for (int64_t i = 0; i < a.A; ++i) {
+            const int32_t slot = a.cell_slot[i];
+            if (slot < 0) continue;
+            if (has_bitmap && !((a.dl.bitmap[(size_t)i * a.dl.words + (r >> 5)] >> (r & 31)) & 1u)) continue;
+            if (a.status[i] == RAPID_EDGE_DOWN) seen = true;   // :88-90 (before the duplicate check)
+            report(slot, a.ring[i]);
+        }
+    }
+    if (a.do_inval && seen && npre > 0) {                  // :137-164
+        for (int32_t s = 0; s < a.S; ++s) {
+            const uint32_t w0 = a.rows.row(s)[r];
+            const int c0 = __popc(w0 & RM);
+            if (c0 < a.L || c0 >= a.H) continue;           // not in the preProposal snapshot
+            const int32_t subject = a.slot_subject[s];
+            for (int k = 0; k < a.K; ++k) {
+                const int32_t o = a.obs[(size_t)subject * a.K + k];
+                if (o < 0) continue;
+                const int32_t so = a.slot_of[o];
+                if (so < 0) continue;
+                const uint32_t wo = a.rows.row(so)[r];
+                if ((wo & CD_BIT_EMIT) || __popc(wo & RM) < a.L) continue;   // observer not in proposal U preProposal
+                report(s, k);                               // implicit edge report
+            }
+        }
+    }
+    if (seen) flags |= RF_SEEN_DOWN;
+    if (!a.raw && olen > 0) flags |= RF_ANNOUNCED | RF_ANN_NOW;      // MembershipService.java:333-335
+    a.rflags[r] = flags;
+    a.n_pre[r] = npre;
+    a.n_prop[r] = nprop;
+    a.out_h1[r] = oh1;
+    a.out_h2[r] = oh2;
+    a.out_len[r] = olen;
+    if (a.out_ann) a.out_ann[r] = (flags & RF_ANNOUNCED) ? 1 : 0;
+}
+
+// RAW mode: collect and clear the "emitted by this call" marks of one receiver
+__global__ void k_gather_call(RowRef rows, int32_t S, int64_t r, const int32_t* __restrict__ slot_subject,
+                              int32_t* __restrict__ out, int32_t cap, int32_t* __restrict__ count) {
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    uint16_t* p = rows.row(s) + r;
+    const uint32_t w = *p;
+    if (w & CD_BIT_CALL) {
+        *p = (uint16_t)(w & ~CD_BIT_CALL);
+        const int32_t at = atomicAdd(count, 1);
+        if (at < cap) out[at] = slot_subject[s];
+    }
+}
+__global__ void k_clear_call(RowRef rows, int32_t S, int64_t R) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t s = blockIdx.y;
+    if (r >= R || s >= S) return;
+    uint16_t* p = rows.row(s) + r;
+    const uint32_t w = *p;
+    if (w & CD_BIT_CALL) *p = (uint16_t)(w & ~CD_BIT_CALL);
+}
+
+// the announced proposal of one receiver: (id, ring-0 key) pairs
+__global__ void k_gather_proposal(RowRef rows, int32_t S, int64_t r, int H, uint32_t RM, int rule_ge_h,
+                                  const int32_t* __restrict__ slot_subject, const int64_t* __restrict__ key0,
+                                  int32_t* __restrict__ out_ids, int64_t* __restrict__ out_keys, int32_t cap,
+                                  int32_t* __restrict__ count) {
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const uint32_t w = rows.row(s)[r];
+    const bool in = rule_ge_h ? (__popc(w & RM) >= H) : ((w & CD_BIT_EMIT) != 0);
+    if (in) {
+        const int32_t at = atomicAdd(count, 1);
+        if (at < cap) { const int32_t id = slot_subject[s]; out_ids[at] = id; out_keys[at] = key0[id]; }
+    }
+}
+
+__global__ void k_dump_masks(RowRef rows, int32_t S, int64_t r, uint32_t RM, const int32_t* __restrict__ slot_subject,
+                             int32_t* __restrict__ out_ids, uint16_t* __restrict__ out_masks) {
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    out_ids[s] = slot_subject[s];
+    out_masks[s] = (uint16_t)(rows.row(s)[r] & RM);
+}
+
+__global__ void k_reset_slots(int32_t S, const int32_t* __restrict__ slot_subject, int32_t* __restrict__ slot_of) {
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) slot_of[slot_subject[s]] = -1;
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+static RowRef rowref(const CD* cd) { return RowRef{cd->masks.p, cd->cur.p, cd->Rpad, cd->nbuf}; }
+
+static int32_t ensure_id_capacity(CD* cd) {
+    const int64_t ntot = cd->view->n + cd->view->nj;
+    if (ntot <= cd->ntot_cap) return RAPID_OK;
+    int64_t ncap = std::max<int64_t>(cd->ntot_cap, 64);
+    while (ncap < ntot) ncap *= 2;
+    const int64_t old = cd->ntot_cap;
+    RAPID_CHECK(cd->slot_of.reserve((size_t)ncap, true, cd->stream));
+    RAPID_CHECK(cd->first_idx.reserve((size_t)ncap, true, cd->stream));
+    RAPID_CHECK(cd->slot_subject.reserve((size_t)ncap, true, cd->stream));
+    ncap = (int64_t)std::min(cd->slot_of.cap, std::min(cd->first_idx.cap, cd->slot_subject.cap));
+    const int TB = 256;
+    k_fill_i32<<<(unsigned)ceil_div<int64_t>(ncap - old, TB), TB, 0, cd->stream>>>(cd->slot_of.p + old, ncap - old, -1);
+    k_fill_i32<<<(unsigned)ceil_div<int64_t>(ncap - old, TB), TB, 0, cd->stream>>>(cd->first_idx.p + old, ncap - old, INT_MAX);
+    RAPID_KERNEL_CHECK();
+    cd->ntot_cap = ncap;
+    return RAPID_OK;
+}
+
+static int32_t ensure_slot_capacity(CD* cd, size_t need) {
+    if (need <= cd->S_cap) return RAPID_OK;
+    size_t ncap = std::max<size_t>(cd->S_cap, 16);
+    while (ncap < need) ncap *= 2;
+    const size_t row = cd->Rpad * (size_t)cd->nbuf;
+    const size_t old_elems = cd->S_cap * row;
+    // DevBuf::reserve(keep) rounds to a power of two of elements; force the exact size instead
+    DevBuf<uint16_t> nm;
+    RAPID_CHECK(nm.reserve(ncap * row));
+    if (old_elems) RAPID_CUDA(cudaMemcpyAsync(nm.p, cd->masks.p, old_elems * sizeof(uint16_t), cudaMemcpyDeviceToDevice, cd->stream));
+    RAPID_CUDA(cudaMemsetAsync(nm.p + old_elems, 0, (ncap * row - old_elems) * sizeof(uint16_t), cd->stream));
+    DevBuf<uint8_t> nc;
+    RAPID_CHECK(nc.reserve(ncap));
+    RAPID_CUDA(cudaMemsetAsync(nc.p, 0, ncap, cd->stream));
+    if (cd->S_cap) RAPID_CUDA(cudaMemcpyAsync(nc.p, cd->cur.p, cd->S_cap, cudaMemcpyDeviceToDevice, cd->stream));
+    RAPID_CUDA(cudaStreamSynchronize(cd->stream));
+    std::swap(cd->masks.p, nm.p); std::swap(cd->masks.cap, nm.cap);
+    std::swap(cd->cur.p, nc.p); std::swap(cd->cur.cap, nc.cap);
+    cd->S_cap = ncap;
+    return RAPID_OK;
+}
+
+// Filter the batch, give every new subject a slot, write cell_slot[]; one host sync to read the counts.
+static int32_t preprocess(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev, const uint8_t* ring_dev,
+                          const uint8_t* status_dev, const int64_t* cfg_dev, BatchCounts* out) {
+    cudaStream_t s = cd->stream;
+    RAPID_CHECK(ensure_id_capacity(cd));
+    RAPID_CHECK(cd->cell_slot.reserve(std::max<int64_t>(A, 1)));
+    RAPID_CHECK(cd->scan_tmp.reserve(std::max<int64_t>(A, 1) + 1));
+    BatchCounts init;
+    memset(&init, 0, sizeof(init));
+    init.n_slots = cd->S;
+    init.bad_ring = -1;
+    init.bad_dst = -1;
+    *cd->h_counts.p = init;
+    RAPID_CUDA(cudaMemcpyAsync(cd->counts.p, cd->h_counts.p, sizeof(BatchCounts), cudaMemcpyHostToDevice, s));
+    if (A > 0) {
+        const int TB = 256;
+        const unsigned g = (unsigned)ceil_div<int64_t>(A, TB);
+        k_filter_first<<<g, TB, 0, s>>>(A, dst_dev, ring_dev, status_dev, cfg_dev, cfg, cd->raw ? 1 : 0, cd->K, cd->view->n,
+                                        cd->view->n + cd->view->nj, cd->slot_of.p, cd->first_idx.p, cd->cell_slot.p, cd->counts.p);
+        k_mark_new<<<g, TB, 0, s>>>(A, dst_dev, cd->cell_slot.p, cd->slot_of.p, cd->first_idx.p, cd->scan_tmp.p);
+        k_exclusive_scan<<<1, 1024, 0, s>>>(cd->scan_tmp.p, A, cd->scan_tmp.p + A);
+        k_assign_slots<<<g, TB, 0, s>>>(A, dst_dev, cd->cell_slot.p, cd->scan_tmp.p, cd->scan_tmp.p + A, cd->S, cd->slot_of.p,
+                                        cd->first_idx.p, cd->slot_subject.p, cd->counts.p);
+        k_cell_slots<<<g, TB, 0, s>>>(A, dst_dev, cd->slot_of.p, cd->cell_slot.p, cd->counts.p);
+        RAPID_KERNEL_CHECK();
+        cd->last_launches += 5;
+    }
+    RAPID_CUDA(cudaMemcpyAsync(cd->h_counts.p, cd->counts.p, sizeof(BatchCounts), cudaMemcpyDeviceToHost, s));
+    RAPID_CUDA(cudaStreamSynchronize(s));
+    *out = *cd->h_counts.p;
+    if (out->bad_ring >= 0 || out->bad_dst >= 0) {
+        // undo nothing: slots assigned to valid cells stay (harmless); report the offending cell
+        if (out->bad_ring >= 0) set_error("cell %d: ring number >= K (%d)", out->bad_ring, cd->K);
+        else set_error("cell %d: edgeDst id outside [0, members + registered joiners)", out->bad_dst);
+        cd->S = out->n_slots;
+        RAPID_CHECK(ensure_slot_capacity(cd, (size_t)cd->S));
+        return RAPID_EINVAL;
+    }
+    cd->S = out->n_slots;
+    RAPID_CHECK(ensure_slot_capacity(cd, (size_t)cd->S));
+    return RAPID_OK;
+}
+
+static int32_t launch_sweep(CD* cd, int64_t A, const uint8_t* ring_dev, const uint8_t* status_dev, const DeliveryDev& dl,
+                            bool do_cells, bool do_inval) {
+    SweepArgs a;
+    a.K = cd->K; a.H = cd->H; a.L = cd->L; a.raw = cd->raw ? 1 : 0;
+    a.do_cells = do_cells; a.do_inval = do_inval;
+    a.R = cd->R;
+    a.rows = rowref(cd);
+    a.S = cd->S;
+    a.slot_subject = cd->slot_subject.p;
+    a.slot_of = cd->slot_of.p;
+    a.obs = cd->view->obs.p;
+    a.A = A;
+    a.cell_slot = cd->cell_slot.p;
+    a.ring = ring_dev;
+    a.status = status_dev;
+    a.dl = dl;
+    a.n_pre = cd->n_pre.p; a.n_prop = cd->n_prop.p; a.rflags = cd->rflags.p;
+    a.out_h1 = cd->out_h1.p; a.out_h2 = cd->out_h2.p; a.out_len = cd->out_len.p; a.out_ann = cd->out_ann.p;
+    const int TB = 128;
+    RAPID_CUDA(cudaEventRecord(cd->evk0, cd->stream));
+    k_sweep<<<(unsigned)ceil_div<int64_t>(cd->R, TB), TB, 0, cd->stream>>>(a);
+    RAPID_KERNEL_CHECK();
+    RAPID_CUDA(cudaEventRecord(cd->evk1, cd->stream));
+    cd->last_launches += 1;
+    cd->last_path = 1;
+    return RAPID_OK;
+}
+
+static int32_t upload_delivery(CD* cd, int64_t A, const rapid_delivery* d, bool on_device, DeliveryDev* out) {
+    *out = DeliveryDev();
+    if (!d || d->flags == 0) return RAPID_OK;
+    if (d->flags & ~(RAPID_DELIVERY_BLOCKED | RAPID_DELIVERY_BITMAP | RAPID_DELIVERY_PERMUTED)) { set_error("unknown delivery flags"); return RAPID_EINVAL; }
+    out->flags = d->flags;
+    out->perm_seed = d->perm_seed;
+    out->words = (cd->R + 31) / 32;
+    if (d->flags & RAPID_DELIVERY_BLOCKED) {
+        if (!d->blocked) { set_error("delivery.blocked is NULL"); return RAPID_EINVAL; }
+        if (on_device) out->blocked = d->blocked;
+        else {
+            RAPID_CHECK(cd->d_blocked.reserve((size_t)cd->R));
+            RAPID_CUDA(cudaMemcpyAsync(cd->d_blocked.p, d->blocked, (size_t)cd->R, cudaMemcpyHostToDevice, cd->stream));
+            out->blocked = cd->d_blocked.p;
+        }
+    }
+    if (d->flags & RAPID_DELIVERY_BITMAP) {
+        if (!d->bitmap && A) { set_error("delivery.bitmap is NULL"); return RAPID_EINVAL; }
+        if (on_device) out->bitmap = d->bitmap;
+        else {
+            const size_t n = (size_t)A * (size_t)out->words;
+            RAPID_CHECK(cd->d_bitmap.reserve(std::max<size_t>(1, n)));
+            if (n) RAPID_CUDA(cudaMemcpyAsync(cd->d_bitmap.p, d->bitmap, n * sizeof(uint32_t), cudaMemcpyHostToDevice, cd->stream));
+            out->bitmap = cd->d_bitmap.p;
+        }
+    }
+    return RAPID_OK;
+}
+
+static int32_t apply_common(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev, const uint8_t* ring_dev,
+                            const uint8_t* status_dev, const int64_t* cfg_dev, const DeliveryDev& dl) {
+    cd->last_launches = 0;
+    cd->last_A = A;
+    RAPID_CUDA(cudaEventRecord(cd->ev0, cd->stream));
+    BatchCounts bc;
+    RAPID_CHECK(preprocess(cd, cfg, A, dst_dev, ring_dev, status_dev, cfg_dev, &bc));
+    int32_t rc;
+    if (cd->bucketed) {
+        rc = bucketed_apply(cd, A, dl, bc);
+    } else {
+        if (dl.flags & RAPID_DELIVERY_PERMUTED) { set_error("the sweep kernel applies cells in array order; RAPID_DELIVERY_PERMUTED needs a bucketed handle"); return RAPID_EUNSUPPORTED; }
+        rc = launch_sweep(cd, A, ring_dev, status_dev, dl, true, !cd->raw);
+    }
+    if (rc != RAPID_OK) return rc;
+    RAPID_CUDA(cudaEventRecord(cd->ev1, cd->stream));
+    RAPID_CUDA(cudaStreamSynchronize(cd->stream));
+    cudaEventElapsedTime(&cd->last_ms, cd->ev0, cd->ev1);
+    cudaEventElapsedTime(&cd->last_main_ms, cd->evk0, cd->evk1);
+    return RAPID_OK;
+}
+
+}  // namespace rapid
+
+using namespace rapid;
+
+extern "C" {
+
+int32_t rapid_cd_create(rapid_cd** out, const rapid_view* v, int32_t H, int32_t L, int64_t n_receivers,
+                        int64_t receiver_begin, uint32_t mode_flags, int64_t max_subjects) {
+    if (!out || !v) { set_error("NULL argument"); return RAPID_EINVAL; }
+    *out = nullptr;
+    const View* view = v;
+    const int K = view->K;
+    if (H > K || L > H || K < 3 || L <= 0 || H <= 0) {                  // MultiNodeCutDetector.java:52-55
+        set_error("Arguments do not satisfy K > H >= L >= 0: (K: %d, H: %d, L: %d", K, H, L);
+        return RAPID_EINVAL;
+    }
+    if (n_receivers < 1 || receiver_begin < 0) { set_error("bad receiver range"); return RAPID_EINVAL; }
+    const bool raw = mode_flags & RAPID_CD_RAW;
+    if ((mode_flags & RAPID_CD_SWEEP) && (mode_flags & RAPID_CD_BUCKETED)) { set_error("SWEEP and BUCKETED are exclusive"); return RAPID_EINVAL; }
+    if (raw && (mode_flags & RAPID_CD_BUCKETED)) { set_error("RAW mode runs on the sweep kernel only"); return RAPID_EINVAL; }
+    if (!raw && view->n > 0 && receiver_begin + n_receivers > view->n) { set_error("receiver range exceeds the ring"); return RAPID_EINVAL; }
+    DeviceGuard g(view->device);
+    rapid_cd* cd = new rapid_cd();
+    cd->view = view;
+    cd->device = view->device;
+    cd->K = K; cd->H = H; cd->L = L;
+    cd->mode = mode_flags;
+    cd->raw = raw;
+    cd->bucketed = !raw && !(mode_flags & RAPID_CD_SWEEP);
+    cd->nbuf = cd->bucketed ? 2 : 1;
+    cd->R = n_receivers;
+    cd->rbegin = receiver_begin;
+    cd->Rpad = (size_t)ceil_div<int64_t>(n_receivers, 128) * 128;      // rows are 256-byte multiples
+    int32_t rc = RAPID_OK;
+    do {
+        if (cudaStreamCreateWithFlags(&cd->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreate(&cd->ev0) != cudaSuccess || cudaEventCreate(&cd->ev1) != cudaSuccess ||
+            cudaEventCreate(&cd->evk0) != cudaSuccess || cudaEventCreate(&cd->evk1) != cudaSuccess) {
+            rc = cuda_fail(cudaGetLastError(), "stream/event create", __FILE__, __LINE__); break;
+        }
+        const size_t R = (size_t)cd->Rpad;
+        if ((rc = cd->n_pre.reserve(R))) break;
+        if ((rc = cd->n_prop.reserve(R))) break;
+        if ((rc = cd->rflags.reserve(R))) break;
+        if ((rc = cd->pend_h1.reserve(R))) break;
+        if ((rc = cd->pend_h2.reserve(R))) break;
+        if ((rc = cd->pend_cnt.reserve(R))) break;
+        if ((rc = cd->out_h1.reserve(R))) break;
+        if ((rc = cd->out_h2.reserve(R))) break;
+        if ((rc = cd->out_len.reserve(R))) break;
+        if ((rc = cd->out_ann.reserve(R))) break;
+        if ((rc = cd->counts.reserve(1))) break;
+        if ((rc = cd->h_counts.reserve(1))) break;
+        if ((rc = ensure_id_capacity(cd))) break;
+        if ((rc = ensure_slot_capacity(cd, (size_t)std::max<int64_t>(max_subjects, 16)))) break;
+        rc = rapid_cd_clear(cd);
+    } while (0);
+    if (rc) { rapid_cd_destroy(cd); return rc; }
+    *out = cd;
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_destroy(rapid_cd* cd) {
+    if (!cd) return RAPID_OK;
+    DeviceGuard g(cd->device);
+    if (cd->stream) cudaStreamSynchronize(cd->stream);
+    bucketed_destroy(cd);
+    if (cd->ev0) cudaEventDestroy(cd->ev0);
+    if (cd->ev1) cudaEventDestroy(cd->ev1);
+    if (cd->evk0) cudaEventDestroy(cd->evk0);
+    if (cd->evk1) cudaEventDestroy(cd->evk1);
+    if (cd->stream) cudaStreamDestroy(cd->stream);
+    delete cd;
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_clear(rapid_cd* cd) {
+    if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    cudaStream_t s = cd->stream;
+    const size_t R = cd->Rpad;
+    if (cd->S > 0) {
+        k_reset_slots<<<(unsigned)ceil_div<int32_t>(cd->S, 256), 256, 0, s>>>(cd->S, cd->slot_subject.p, cd->slot_of.p);
+        RAPID_KERNEL_CHECK();
+        RAPID_CUDA(cudaMemsetAsync(cd->masks.p, 0, (size_t)cd->S * cd->nbuf * cd->Rpad * sizeof(uint16_t), s));
+        RAPID_CUDA(cudaMemsetAsync(cd->cur.p, 0, (size_t)cd->S, s));
+    }
+    cd->S = 0;
+    RAPID_CUDA(cudaMemsetAsync(cd->n_pre.p, 0, R * sizeof(int32_t), s));
+    RAPID_CUDA(cudaMemsetAsync(cd->n_prop.p, 0, R * sizeof(int32_t), s));
+    RAPID_CUDA(cudaMemsetAsync(cd->rflags.p, 0, R * sizeof(uint32_t), s));
+    RAPID_CUDA(cudaMemsetAsync(cd->pend_h1.p, 0, R * sizeof(uint64_t), s));
+    RAPID_CUDA(cudaMemsetAsync(cd->pend_h2.p, 0, R * sizeof(uint64_t), s));
+    RAPID_CUDA(cudaMemsetAsync(cd->pend_cnt.p, 0, R * sizeof(int32_t), s));
+    RAPID_CUDA(cudaMemsetAsync(cd->out_h1.p, 0, R * sizeof(uint64_t), s));
+    RAPID_CUDA(cudaMemsetAsync(cd->out_h2.p, 0, R * sizeof(uint64_t), s));
+    RAPID_CUDA(cudaMemsetAsync(cd->out_len.p, 0, R * sizeof(int32_t), s));
+    RAPID_CUDA(cudaMemsetAsync(cd->out_ann.p, 0, R, s));
+    RAPID_CHECK(bucketed_clear(cd));
+    RAPID_CUDA(cudaStreamSynchronize(s));
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_read_outputs(const rapid_cd* cd, uint64_t* h1, uint64_t* h2, int32_t* len, uint8_t* ann) {
+    if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    const size_t R = (size_t)cd->R;
+    if (h1) RAPID_CUDA(cudaMemcpyAsync(h1, cd->out_h1.p, R * sizeof(uint64_t), cudaMemcpyDeviceToHost, cd->stream));
+    if (h2) RAPID_CUDA(cudaMemcpyAsync(h2, cd->out_h2.p, R * sizeof(uint64_t), cudaMemcpyDeviceToHost, cd->stream));
+    if (len) RAPID_CUDA(cudaMemcpyAsync(len, cd->out_len.p, R * sizeof(int32_t), cudaMemcpyDeviceToHost, cd->stream));
+    if (ann) RAPID_CUDA(cudaMemcpyAsync(ann, cd->out_ann.p, R, cudaMemcpyDeviceToHost, cd->stream));
+    RAPID_CUDA(cudaStreamSynchronize(cd->stream));
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_apply_batch_dev(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src_dev, const int32_t* dst_dev,
+                                 const uint8_t* ring_dev, const uint8_t* status_dev, const int64_t* cell_cfg_dev,
+                                 const rapid_delivery* delivery_dev) {
+    (void)src_dev;   // edgeSrc is stored by the Java but never read back (MultiNodeCutDetector.java:101)
+    if (!cd || n_cells < 0 || (n_cells && (!dst_dev || !ring_dev || !status_dev))) { set_error("bad arguments"); return RAPID_EINVAL; }
+    if (cd->raw) { set_error("RAW handles take rapid_cd_aggregate / rapid_cd_invalidate"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    DeliveryDev dl;
+    RAPID_CHECK(upload_delivery(cd, n_cells, delivery_dev, true, &dl));
+    return apply_common(cd, cfg_id, n_cells, dst_dev, ring_dev, status_dev, cell_cfg_dev, dl);
+}
+
+static int32_t stage_cells(rapid_cd* cd, int64_t n, const int32_t* dst, const uint8_t* ring, const uint8_t* status, const int64_t* cfg) {
+    const size_t m = (size_t)std::max<int64_t>(n, 1);
+    RAPID_CHECK(cd->c_dst.reserve(m));
+    RAPID_CHECK(cd->c_ring.reserve(m));
+    RAPID_CHECK(cd->c_status.reserve(m));
+    if (n) {
+        RAPID_CUDA(cudaMemcpyAsync(cd->c_dst.p, dst, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, cd->stream));
+        RAPID_CUDA(cudaMemcpyAsync(cd->c_ring.p, ring, (size_t)n, cudaMemcpyHostToDevice, cd->stream));
+        RAPID_CUDA(cudaMemcpyAsync(cd->c_status.p, status, (size_t)n, cudaMemcpyHostToDevice, cd->stream));
+        if (cfg) {
+            RAPID_CHECK(cd->c_cfg.reserve(m));
+            RAPID_CUDA(cudaMemcpyAsync(cd->c_cfg.p, cfg, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, cd->stream));
+        }
+    }
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_apply_batch(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src, const int32_t* dst,
+                             const uint8_t* ring, const uint8_t* status, const int64_t* cell_cfg,
+                             const rapid_delivery* delivery, uint64_t* proposal_hash, uint64_t* proposal_hash2,
+                             int32_t* proposal_len, uint8_t* announced) {
+    (void)src;
+    if (!cd || n_cells < 0 || (n_cells && (!dst || !ring || !status))) { set_error("bad arguments"); return RAPID_EINVAL; }
+    if (cd->raw) { set_error("RAW handles take rapid_cd_aggregate / rapid_cd_invalidate"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    RAPID_CHECK(stage_cells(cd, n_cells, dst, ring, status, cell_cfg));
+    DeliveryDev dl;
+    RAPID_CHECK(upload_delivery(cd, n_cells, delivery, false, &dl));
+    RAPID_CHECK(apply_common(cd, cfg_id, n_cells, cd->c_dst.p, cd->c_ring.p, cd->c_status.p, cell_cfg ? cd->c_cfg.p : nullptr, dl));
+    if (proposal_hash || proposal_hash2 || proposal_len || announced)
+        return rapid_cd_read_outputs(cd, proposal_hash, proposal_hash2, proposal_len, announced);
+    return RAPID_OK;
+}
+
+static int32_t gather_sorted(const rapid_cd* cd, int32_t n, std::vector<int32_t>& ids, std::vector<int64_t>* keys,
+                             const DevBuf<int32_t>& d_ids, const DevBuf<int64_t>* d_keys) {
+    ids.resize((size_t)n);
+    if (n) RAPID_CUDA(cudaMemcpy(ids.data(), d_ids.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (keys) {
+        keys->resize((size_t)n);
+        if (n) RAPID_CUDA(cudaMemcpy(keys->data(), d_keys->p, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    }
+    (void)cd;
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_aggregate(rapid_cd* cd, int64_t n_cells, const int32_t* src, const int32_t* dst, const uint8_t* ring,
+                           const uint8_t* status, int64_t receiver, int32_t* out_ids, int32_t cap, int32_t* out_len) {
+    (void)src;
+    if (!cd || n_cells < 0 || (n_cells && (!dst || !ring || !status)) || !out_len) { set_error("bad arguments"); return RAPID_EINVAL; }
+    if (!cd->raw) { set_error("rapid_cd_aggregate needs a RAPID_CD_RAW handle"); return RAPID_EINVAL; }
+    if (receiver < 0 || receiver >= cd->R) { set_error("bad receiver"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    RAPID_CHECK(stage_cells(cd, n_cells, dst, ring, status, nullptr));
+    RAPID_CHECK(apply_common(cd, 0, n_cells, cd->c_dst.p, cd->c_ring.p, cd->c_status.p, nullptr, DeliveryDev()));
+    // collect what this call emitted for `receiver`, then clear the call marks of every receiver
+    DevBuf<int32_t> d_ids, d_cnt;
+    const int32_t S = cd->S;
+    RAPID_CHECK(d_ids.reserve((size_t)std::max(S, 1)));
+    RAPID_CHECK(d_cnt.reserve(1));
+    RAPID_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(int32_t), cd->stream));
+    int32_t n = 0;
+    if (S > 0) {
+        k_gather_call<<<(unsigned)ceil_div<int32_t>(S, 256), 256, 0, cd->stream>>>(rowref(cd), S, receiver, cd->slot_subject.p, d_ids.p, S, d_cnt.p);
+        dim3 grid((unsigned)ceil_div<int64_t>(cd->R, 256), (unsigned)S);
+        k_clear_call<<<grid, 256, 0, cd->stream>>>(rowref(cd), S, cd->R);
+        RAPID_KERNEL_CHECK();
+        RAPID_CUDA(cudaMemcpyAsync(&n, d_cnt.p, sizeof(int32_t), cudaMemcpyDeviceToHost, cd->stream));
+    }
+    RAPID_CUDA(cudaStreamSynchronize(cd->stream));
+    std::vector<int32_t> ids;
+    RAPID_CHECK(gather_sorted(cd, n, ids, nullptr, d_ids, nullptr));
+    std::sort(ids.begin(), ids.end());
+    *out_len = n;
+    for (int32_t i = 0; i < n && i < cap; ++i) out_ids[i] = ids[(size_t)i];
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_invalidate(rapid_cd* cd, int64_t receiver, int32_t* out_ids, int32_t cap, int32_t* out_len) {
+    if (!cd || !out_len) { set_error("bad arguments"); return RAPID_EINVAL; }
+    if (!cd->raw) { set_error("rapid_cd_invalidate needs a RAPID_CD_RAW handle"); return RAPID_EINVAL; }
+    if (receiver < 0 || receiver >= cd->R) { set_error("bad receiver"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    cd->last_launches = 0;
+    RAPID_CHECK(ensure_id_capacity(cd));
+    RAPID_CHECK(launch_sweep(cd, 0, nullptr, nullptr, DeliveryDev(), false, true));
+    DevBuf<int32_t> d_ids, d_cnt;
+    const int32_t S = cd->S;
+    RAPID_CHECK(d_ids.reserve((size_t)std::max(S, 1)));
+    RAPID_CHECK(d_cnt.reserve(1));
+    RAPID_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(int32_t), cd->stream));
+    int32_t n = 0;
+    if (S > 0) {
+        k_gather_call<<<(unsigned)ceil_div<int32_t>(S, 256), 256, 0, cd->stream>>>(rowref(cd), S, receiver, cd->slot_subject.p, d_ids.p, S, d_cnt.p);
+        dim3 grid((unsigned)ceil_div<int64_t>(cd->R, 256), (unsigned)S);
+        k_clear_call<<<grid, 256, 0, cd->stream>>>(rowref(cd), S, cd->R);
+        RAPID_KERNEL_CHECK();
+        RAPID_CUDA(cudaMemcpyAsync(&n, d_cnt.p, sizeof(int32_t), cudaMemcpyDeviceToHost, cd->stream));
+    }
+    RAPID_CUDA(cudaStreamSynchronize(cd->stream));
+    std::vector<int32_t> ids;
+    RAPID_CHECK(gather_sorted(cd, n, ids, nullptr, d_ids, nullptr));
+    std::sort(ids.begin(), ids.end());
+    *out_len = n;
+    for (int32_t i = 0; i < n && i < cap; ++i) out_ids[i] = ids[(size_t)i];
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_get_proposal(const rapid_cd* cd, int64_t receiver, int32_t* out_ids, int32_t cap, int32_t* out_len) {
+    if (!cd || !out_len || receiver < 0 || receiver >= cd->R) { set_error("bad arguments"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    uint32_t flags = 0;
+    RAPID_CUDA(cudaMemcpy(&flags, cd->rflags.p + receiver, sizeof(flags), cudaMemcpyDeviceToHost));
+    *out_len = 0;
+    if (!(flags & RF_ANNOUNCED) || cd->S == 0) return RAPID_OK;
+    DevBuf<int32_t> d_ids, d_cnt;
+    DevBuf<int64_t> d_keys;
+    const int32_t S = cd->S;
+    RAPID_CHECK(d_ids.reserve((size_t)S));
+    RAPID_CHECK(d_keys.reserve((size_t)S));
+    RAPID_CHECK(d_cnt.reserve(1));
+    RAPID_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(int32_t), cd->stream));
+    k_gather_proposal<<<(unsigned)ceil_div<int32_t>(S, 256), 256, 0, cd->stream>>>(
+        rowref(cd), S, receiver, cd->H, (1u << cd->K) - 1u, (flags & RF_RULE_GE_H) ? 1 : 0, cd->slot_subject.p, cd->view->key.p /* ring 0 row */,
+        d_ids.p, d_keys.p, S, d_cnt.p);
+    RAPID_KERNEL_CHECK();
+    int32_t n = 0;
+    RAPID_CUDA(cudaMemcpyAsync(&n, d_cnt.p, sizeof(int32_t), cudaMemcpyDeviceToHost, cd->stream));
+    RAPID_CUDA(cudaStreamSynchronize(cd->stream));
+    std::vector<int32_t> ids;
+    std::vector<int64_t> keys;
+    RAPID_CHECK(gather_sorted(cd, n, ids, &keys, d_ids, &d_keys));
+    std::vector<int32_t> order((size_t)n);
+    for (int32_t i = 0; i < n; ++i) order[(size_t)i] = i;
+    // sorted(membershipView.getRingZeroComparator())  MembershipService.java:346-348 (signed key; id breaks exact ties)
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        return keys[(size_t)a] != keys[(size_t)b] ? keys[(size_t)a] < keys[(size_t)b] : ids[(size_t)a] < ids[(size_t)b];
+    });
+    *out_len = n;
+    for (int32_t i = 0; i < n && i < cap; ++i) out_ids[i] = ids[(size_t)order[(size_t)i]];
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_num_proposals(const rapid_cd* cd, int64_t receiver, int32_t* out) {
+    if (!cd || !out || receiver < 0 || receiver >= cd->R) { set_error("bad arguments"); return RAPID_EINVAL; }
+    if (cd->bucketed) { set_error("getNumProposals is exact only on sweep handles (RAPID_CD_SWEEP / RAPID_CD_RAW)"); return RAPID_EUNSUPPORTED; }
+    DeviceGuard g(cd->device);
+    RAPID_CUDA(cudaMemcpy(out, cd->n_prop.p + receiver, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_debug_masks(const rapid_cd* cd, int64_t receiver, int32_t* out_subject_ids, uint16_t* out_masks, int32_t cap, int32_t* out_n) {
+    if (!cd || !out_n || receiver < 0 || receiver >= cd->R) { set_error("bad arguments"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    const int32_t S = cd->S;
+    *out_n = S;
+    if (S == 0) return RAPID_OK;
+    DevBuf<int32_t> d_ids;
+    DevBuf<uint16_t> d_m;
+    RAPID_CHECK(d_ids.reserve((size_t)S));
+    RAPID_CHECK(d_m.reserve((size_t)S));
+    k_dump_masks<<<(unsigned)ceil_div<int32_t>(S, 256), 256, 0, cd->stream>>>(rowref(cd), S, receiver, (1u << cd->K) - 1u, cd->slot_subject.p, d_ids.p, d_m.p);
+    RAPID_KERNEL_CHECK();
+    const int32_t n = std::min(S, cap);
+    if (out_subject_ids) RAPID_CUDA(cudaMemcpyAsync(out_subject_ids, d_ids.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, cd->stream));
+    if (out_masks) RAPID_CUDA(cudaMemcpyAsync(out_masks, d_m.p, (size_t)n * sizeof(uint16_t), cudaMemcpyDeviceToHost, cd->stream));
+    RAPID_CUDA(cudaStreamSynchronize(cd->stream));
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_debug_counters(const rapid_cd* cd, int64_t receiver, int32_t* updates_in_progress, int32_t* seen_link_down) {
+    if (!cd || receiver < 0 || receiver >= cd->R) { set_error("bad arguments"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    if (updates_in_progress) RAPID_CUDA(cudaMemcpy(updates_in_progress, cd->n_pre.p + receiver, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (seen_link_down) {
+        uint32_t f = 0;
+        RAPID_CUDA(cudaMemcpy(&f, cd->rflags.p + receiver, sizeof(f), cudaMemcpyDeviceToHost));
+        *seen_link_down = (f & RF_SEEN_DOWN) ? 1 : 0;
+    }
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_last_path(const rapid_cd* cd, int32_t* path, int32_t* n_kernel_launches) {
+    if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
+    if (path) *path = cd->last_path;
+    if (n_kernel_launches) *n_kernel_launches = cd->last_launches;
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_last_device_ms(const rapid_cd* cd, float* total_ms, float* main_kernel_ms) {
+    if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
+    if (total_ms) *total_ms = cd->last_ms;
+    if (main_kernel_ms) *main_kernel_ms = cd->last_main_ms;
+    return RAPID_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// Internal layout of the cut-detector handle (shared by cd_core.cu and cd_bucketed.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace rapid {
+
+// ---- the 16-bit state word per (subject slot, receiver) ------------------------------------------
+// bits 0..K-1 : ring r has reported the subject  (reportsPerHost[subject].containsKey(r),
+//               MultiNodeCutDetector.java:92-101)
+// bit 14      : RAW mode only — emitted by the call in flight (returned list of aggregateForProposal)
+// bit 15      : subject was emitted in a proposal (it left `proposal` at :118-121)
+// preProposal == { L <= popc < H },  proposal == { popc >= H and bit 15 clear }.
+#define CD_BIT_CALL 0x4000u
+#define CD_BIT_EMIT 0x8000u
+
+// ---- per-receiver flag word ------------------------------------------------------------------------
+#define RF_SEEN_DOWN   1u   // seenLinkDownEvents           (MultiNodeCutDetector.java:88-90)
+#define RF_ANNOUNCED   2u   // announcedProposal            (MembershipService.java:318, :335)
+#define RF_RULE_GE_H   4u   // announced proposal == { popc >= H } (else == { bit 15 })
+#define RF_ANN_NOW     8u   // announced by the batch in flight (votes in rapid_fp_tally_cd)
+
+struct BatchCounts {       // written by the preprocessing kernels, read back once per batch
+    int32_t n_slots;       // S after slot assignment
+    int32_t n_valid;       // cells that passed the filter
+    int32_t n_batch_subj;  // distinct subjects with at least one valid cell in this batch
+    int32_t any_down;      // some valid cell has status DOWN
+    int32_t bad_ring;      // index of a cell with ring >= K, or -1
+    int32_t bad_dst;       // index of a cell with dst outside [0, n + joiners), or -1
+    int32_t n_mixed;       // bucketed: receivers needing exact interval resolution
+    int32_t n_inval;       // bucketed: receivers entering the invalidation pass
+};
+
+struct CD {
+    const View* view = nullptr;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    int K = 0, H = 0, L = 0;
+    uint32_t mode = 0;
+    bool raw = false, bucketed = false;
+    int64_t R = 0, rbegin = 0;
+    size_t Rpad = 0;
+    int nbuf = 1;                     // 2 = double-buffered rows (bucketed handles)
+    int32_t S = 0;                    // slots in use (host mirror)
+    size_t S_cap = 0;
+    int64_t ntot_cap = 0;             // capacity of slot_of / first_idx (node + joiner ids)
+
+    DevBuf<uint16_t> masks;           // [S_cap][nbuf][Rpad]
+    DevBuf<uint8_t> cur;              // [S_cap] which of the nbuf rows is current
+    DevBuf<int32_t> slot_of;          // [ntot_cap] id -> slot, -1 if none
+    DevBuf<int32_t> first_idx;        // [ntot_cap] scratch (INT_MAX)
+    DevBuf<int32_t> slot_subject;     // [ntot_cap] slot -> id
+
+    DevBuf<int32_t> n_pre;            // [R] updatesInProgress
+    DevBuf<int32_t> n_prop;           // [R] proposalCount (sweep handles)
+    DevBuf<uint32_t> rflags;          // [R]
+    DevBuf<uint64_t> pend_h1, pend_h2;  // [R] fingerprint of `proposal` (>=H, not emitted)   (bucketed handles)
+    DevBuf<int32_t> pend_cnt;         // [R]
+    DevBuf<uint64_t> out_h1, out_h2;  // [R] outputs of the last batch
+    DevBuf<int32_t> out_len;          // [R]
+    DevBuf<uint8_t> out_ann;          // [R]
+
+    // batch staging (device)
+    DevBuf<int32_t> c_dst;  DevBuf<uint8_t> c_ring, c_status;  DevBuf<int64_t> c_cfg;
+    DevBuf<uint8_t> d_blocked;  DevBuf<uint32_t> d_bitmap;
+    DevBuf<int32_t> cell_slot;        // [A] slot or -1
+    DevBuf<int32_t> scan_tmp;         // [A]
+    DevBuf<BatchCounts> counts;       // [1]
+    PinnedBuf<BatchCounts> h_counts;
+    DevBuf<uint8_t> cub_tmp;
+    // bucketed scratch lives in cd_bucketed.cu's own struct hung off here
+    void* bucketed_state = nullptr;
+
+    int32_t last_path = 0, last_launches = 0;
+    float last_ms = 0.f, last_main_ms = 0.f;
+    int64_t last_A = 0;
+};
+
+// row pointer helpers (device)
+struct RowRef {
+    uint16_t* masks;
+    const uint8_t* cur;
+    size_t Rpad;
+    int nbuf;
+    __device__ __forceinline__ uint16_t* row(int32_t slot) const {
+        return masks + ((size_t)slot * nbuf + (nbuf == 2 ? cur[slot] : 0)) * Rpad;
+    }
+    __device__ __forceinline__ uint16_t* alt(int32_t slot) const {   // the non-current row (nbuf == 2)
+        return masks + ((size_t)slot * nbuf + (cur[slot] ^ 1)) * Rpad;
+    }
+};
+
+struct DeliveryDev {
+    uint32_t flags = 0;
+    const uint8_t* blocked = nullptr;
+    const uint32_t* bitmap = nullptr;
+    int64_t words = 0;
+    uint64_t perm_seed = 0;
+};
+
+// implemented in cd_bucketed.cu
+int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCounts& bc);
+void bucketed_destroy(CD* cd);
+int32_t bucketed_clear(CD* cd);
+
+}  // namespace rapid
+
+struct rapid_cd : rapid::CD {};

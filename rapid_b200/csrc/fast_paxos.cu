@@ -1,0 +1,611 @@
+// FastPaxos fast-round vote tally (rapid/src/main/java/com/vrg/rapid/FastPaxos.java:125-156) on the device,
+// plus the sharded (multi-GPU) variant: per-rank proposal-hash histograms combined with one NCCL all-reduce.
+//
+// The Java keeps HashMap<List<Endpoint>, AtomicInteger> and hashes the whole endpoint list for every vote
+// (O(#cut) per vote).  Here a proposal is its 128-bit order-independent fingerprint + length (computed once
+// per proposer by the cut-detection kernels); votes are de-duplicated per sender with an atomicMin
+// "first index" table, counted in an open-addressing table with warp-aggregated atomics, and the exact
+// decision point (the vote at which a count reaches N - floor((N-1)/4)) is recovered with a prefix scan so
+// that votesReceived / count at the moment of decision match the sequential reference.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <climits>
+
+#include "cd_internal.cuh"
+
+namespace rapid {
+
+struct FPState {
+    int32_t decided;
+    int32_t decided_entry;
+    int32_t votes_received;
+    int32_t n_valid_call;
+    int32_t n_cand;
+    int32_t cand[8];
+    int32_t i_star;
+    int32_t bad_sender;
+};
+
+struct FP {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t cfg = 0, N = 0, Q = 0, sender_cap = 0;
+    uint32_t T = 0;                       // table capacity (power of two)
+    DevBuf<int32_t> seen;                 // [sender_cap] INT_MAX = not voted, -1 = voted, else first index in the call
+    DevBuf<int32_t> t_state, t_len, t_count, t_call;
+    DevBuf<uint64_t> t_h1, t_h2;
+    DevBuf<int32_t> ent, scan;            // per-vote scratch
+    DevBuf<FPState> st;
+    PinnedBuf<FPState> h_st;
+    // staging for host-array votes
+    DevBuf<int32_t> v_sender, v_len;
+    DevBuf<int64_t> v_cfg;
+    DevBuf<uint64_t> v_h1, v_h2;
+    // sharded tally
+    DevBuf<int32_t> hist;                 // [65536]
+    DevBuf<unsigned long long> mm;        // [8] max / ~min verification words
+    PinnedBuf<unsigned long long> h_mm;
+    float last_ms = 0.f;
+    int32_t last_launches = 0;
+};
+
+// ------------------------------------------------------------------ NCCL through dlopen
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(nccl_comm*, int, nccl_uid, int) = nullptr;
+    int (*CommDestroy)(nccl_comm) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static const int NCCL_INT32 = 2, NCCL_UINT64 = 5, NCCL_SUM = 0, NCCL_MAX = 2;
+
+static int32_t load_nccl() {
+    if (g_nccl.lib) return RAPID_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { set_error("cannot dlopen libnccl.so.2: %s", dlerror()); return RAPID_ENCCL; }
+    NcclApi a;
+    a.lib = h;
+    a.GetUniqueId = (int (*)(nccl_uid*))dlsym(h, "ncclGetUniqueId");
+    a.CommInitRank = (int (*)(nccl_comm*, int, nccl_uid, int))dlsym(h, "ncclCommInitRank");
+    a.CommDestroy = (int (*)(nccl_comm))dlsym(h, "ncclCommDestroy");
+    a.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t))dlsym(h, "ncclAllReduce");
+    a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce) { set_error("libnccl lacks required symbols"); return RAPID_ENCCL; }
+    g_nccl = a;
+    return RAPID_OK;
+}
+
+struct Comm {
+    int device = 0, rank = 0, world = 1;
+    nccl_comm comm = nullptr;
+};
+
+#define RAPID_NCCL(call)                                                                                              \
+    do {                                                                                                              \
+        int _r = (call);                                                                                              \
+        if (_r != 0) { set_error("NCCL error %d (%s): %s", _r, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?", #call); return RAPID_ENCCL; } \
+    } while (0)
+
+// ------------------------------------------------------------------ kernels
+__global__ void k_fp_fill(int32_t* p, int64_t n, int32_t v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// first vote of every sender in this call (votesReceived.contains(sender), :134)
+__global__ void k_fp_first(int64_t n, const int32_t* __restrict__ sender, const int64_t* __restrict__ vcfg, int64_t cfg,
+                           int64_t sender_cap, int allow_skip, int32_t* __restrict__ seen, FPState* __restrict__ st) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t s = sender[i];
+    if (s < 0 || s >= sender_cap) { if (!(allow_skip && s < 0)) atomicMax(&st->bad_sender, (int32_t)i); return; }
+    if (vcfg && vcfg[i] != cfg) return;                     // :126
+    atomicMin(&seen[s], (int32_t)i);                         // -1 (already voted) stays
+}
+
+__device__ __forceinline__ uint32_t fp_slot_hash(uint64_t h1, uint64_t h2, int32_t len) {
+    return (uint32_t)(splitmix64(h1 ^ rotl64(h2, 21) ^ (uint64_t)(uint32_t)len) >> 32);
+}
+
+// find-or-insert the proposal of every valid vote; count per entry for this call (warp-aggregated)
+__global__ void k_fp_insert(int64_t n, const int32_t* __restrict__ sender, const int64_t* __restrict__ vcfg, int64_t cfg,
+                            int64_t sender_cap, const uint64_t* __restrict__ h1v, const uint64_t* __restrict__ h2v,
+                            const int32_t* __restrict__ lenv, const int32_t* __restrict__ seen, uint32_t T,
+                            int32_t* __restrict__ t_state, uint64_t* __restrict__ t_h1, uint64_t* __restrict__ t_h2,
+                            int32_t* __restrict__ t_len, int32_t* __restrict__ t_call, int32_t* __restrict__ ent,
+                            FPState* __restrict__ st) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    uint64_t h1 = 0, h2 = 0;
+    int32_t len = 0;
+    if (i < n) {
+        const int32_t s = sender[i];
+        if (s >= 0 && s < sender_cap && !(vcfg && vcfg[i] != cfg) && seen[s] == (int32_t)i) {
+            valid = true;
+            h1 = h1v[i];
+            h2 = h2v ? h2v[i] : 0;
+            len = lenv ? lenv[i] : 0;
+        }
+    }
+    int32_t e = -1;
+    // one leader per distinct fingerprint in the warp does the table probe
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+        const unsigned same = __match_any_sync(active, h1 ^ rotl64(h2, 21) ^ ((uint64_t)(uint32_t)len << 1));
+        const int leader = __ffs(same) - 1;
+        const int lane = threadIdx.x & 31;
+        if (lane == leader) {
+            uint32_t pos = fp_slot_hash(h1, h2, len) & (T - 1);
+            for (;;) {
+                int32_t state = atomicCAS(&t_state[pos], 0, 1);
+                if (state == 0) {                            // claimed an empty entry: publish the key
+                    t_h1[pos] = h1; t_h2[pos] = h2; t_len[pos] = len;
+                    __threadfence();
+                    atomicExch(&t_state[pos], 2);
+                    e = (int32_t)pos;
+                    break;
+                }
+                while (state == 1) state = atomicAdd(&t_state[pos], 0);     // another warp is publishing
+                if (t_h1[pos] == h1 && t_h2[pos] == h2 && t_len[pos] == len) { e = (int32_t)pos; break; }
+                pos = (pos + 1) & (T - 1);
+            }
+            atomicAdd(&t_call[e], __popc(same));
+        }
+        // NOTE: __match_any groups by the XOR-folded key; distinct fingerprints that fold equal are split below
+        e = __shfl_sync(same, e, leader);
+        const uint64_t lh1 = __shfl_sync(same, h1, leader), lh2 = __shfl_sync(same, h2, leader);
+        const int32_t llen = __shfl_sync(same, len, leader);
+        if (lh1 != h1 || lh2 != h2 || llen != len) {
+            // folded-key collision inside the warp (astronomically rare): undo the leader's count for me, probe myself
+            atomicSub(&t_call[e], 1);
+            uint32_t pos = fp_slot_hash(h1, h2, len) & (T - 1);
+            for (;;) {
+                int32_t state = atomicCAS(&t_state[pos], 0, 1);
+                if (state == 0) {
+                    t_h1[pos] = h1; t_h2[pos] = h2; t_len[pos] = len;
+                    __threadfence();
+                    atomicExch(&t_state[pos], 2);
+                    break;
+                }
+                while (state == 1) state = atomicAdd(&t_state[pos], 0);
+                if (t_h1[pos] == h1 && t_h2[pos] == h2 && t_len[pos] == len) break;
+                pos = (pos + 1) & (T - 1);
+            }
+            e = (int32_t)pos;
+            atomicAdd(&t_call[e], 1);
+        }
+    }
+    if (i < n) ent[i] = e;
+    const unsigned cnt = __popc(active);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&st->n_valid_call, (int32_t)cnt);
+}
+
+// entries whose count reaches the quorum within this call
+__global__ void k_fp_candidates(uint32_t T, const int32_t* __restrict__ t_count, const int32_t* __restrict__ t_call,
+                                int32_t Q, FPState* __restrict__ st) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T) return;
+    const int32_t c = t_call[e];
+    if (c > 0 && t_count[e] + c >= Q) {
+        const int32_t at = atomicAdd(&st->n_cand, 1);
+        if (at < 8) st->cand[at] = (int32_t)e;
+    }
+}
+
+__global__ void k_fp_flag(int64_t n, const int32_t* __restrict__ ent, int32_t e, int32_t* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = ent[i] == e ? 1 : 0;
+}
+
+__global__ void k_fp_scan(int32_t* __restrict__ data, int64_t n) {          // single block exclusive scan
+    __shared__ int32_t part[1024];
+    const int T = blockDim.x, t = threadIdx.x;
+    const int64_t per = (n + T - 1) / T;
+    const int64_t b = (int64_t)t * per, e = b + per < n ? b + per : n;
+    int32_t s = 0;
+    for (int64_t i = b; i < e; ++i) s += data[i];
+    part[t] = s;
+    __syncthreads();
+    for (int off = 1; off < T; off <<= 1) {
+        int32_t v = t >= off ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int32_t run = t ? part[t - 1] : 0;
+    for (int64_t i = b; i < e; ++i) { const int32_t v = data[i]; data[i] = run; run += v; }
+}
+
+// the vote at which entry e's running count reaches Q
+__global__ void k_fp_find(int64_t n, const int32_t* __restrict__ ent, const int32_t* __restrict__ excl, int32_t e,
+                          const int32_t* __restrict__ t_count, int32_t Q, FPState* __restrict__ st) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || ent[i] != e) return;
+    if (t_count[e] + excl[i] + 1 == Q) {
+        const int32_t old = atomicMin(&st->i_star, (int32_t)i);
+        (void)old;
+    }
+}
+__global__ void k_fp_pick(int64_t n, const int32_t* __restrict__ ent, FPState* __restrict__ st) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && st->i_star < INT_MAX) { st->decided = 1; st->decided_entry = ent[st->i_star]; }
+    (void)n;
+}
+
+// apply the votes with index <= limit (limit = n-1 if no decision in this call)
+__global__ void k_fp_apply(int64_t n, const int32_t* __restrict__ sender, const int32_t* __restrict__ ent,
+                           const FPState* __restrict__ stc, int use_istar, int32_t* __restrict__ seen,
+                           int32_t* __restrict__ t_count, FPState* __restrict__ st) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t e = ent[i];
+    if (e < 0) return;
+    const int64_t limit = use_istar ? (int64_t)stc->i_star : n - 1;
+    const int32_t s = sender[i];
+    if (i <= limit) {
+        seen[s] = -1;                                        // votesReceived.add(sender) :141
+        atomicAdd(&t_count[e], 1);                           // :142-144
+        atomicAdd(&st->votes_received, 1);
+    } else {
+        seen[s] = INT_MAX;                                   // arrived after the decision: ignored entirely (:138)
+    }
+}
+
+__global__ void k_fp_zero_call(uint32_t T, int32_t* __restrict__ t_call) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < T) t_call[e] = 0;
+}
+
+// votes of the receivers that announced in the last batch (FastPaxos.propose :94-108)
+__global__ void k_fp_votes_from_cd(int64_t R, const uint32_t* __restrict__ rflags, const int32_t* __restrict__ ring0,
+                                   int64_t rbegin, int32_t* __restrict__ sender) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    sender[r] = (rflags[r] & RF_ANN_NOW) ? ring0[rbegin + r] : -1;
+}
+
+// ---- sharded tally: radix histogram over the proposal fingerprints, restricted to a prefix -----------------------
+// level l looks at 16-bit digit l of the 128-bit string (h1 high..low, then h2 high..low); entries must match the
+// `prefix` digits chosen so far.
+__device__ __forceinline__ uint32_t fp_digit(uint64_t h1, uint64_t h2, int level) {
+    const uint64_t w = level < 4 ? h1 : h2;
+    return (uint32_t)(w >> (48 - 16 * (level & 3))) & 0xffffu;
+}
+struct Prefix { uint32_t d[8]; int n; };
+
+__global__ void k_fp_hist(uint32_t T, const int32_t* __restrict__ t_state, const uint64_t* __restrict__ t_h1,
+                          const uint64_t* __restrict__ t_h2, const int32_t* __restrict__ t_count, Prefix pf,
+                          int32_t* __restrict__ hist) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T || t_state[e] != 2) return;
+    const int32_t c = t_count[e];
+    if (c == 0) return;
+    const uint64_t h1 = t_h1[e], h2 = t_h2[e];
+    for (int l = 0; l < pf.n; ++l) if (fp_digit(h1, h2, l) != pf.d[l]) return;
+    atomicAdd(&hist[fp_digit(h1, h2, pf.n)], c);
+}
+
+__global__ void k_fp_hist_cand(const int32_t* __restrict__ hist, int32_t Q, FPState* __restrict__ st) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= 65536) return;
+    if (hist[b] >= Q) {
+        const int32_t at = atomicAdd(&st->n_cand, 1);
+        if (at < 8) st->cand[at] = (int32_t)b;
+    }
+}
+
+// max / ~min of (h1, h2, len) over the local entries matching the prefix (identity 0 for ranks without one)
+__global__ void k_fp_minmax(uint32_t T, const int32_t* __restrict__ t_state, const uint64_t* __restrict__ t_h1,
+                            const uint64_t* __restrict__ t_h2, const int32_t* __restrict__ t_len,
+                            const int32_t* __restrict__ t_count, Prefix pf, unsigned long long* __restrict__ mm) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T || t_state[e] != 2 || t_count[e] == 0) return;
+    const uint64_t h1 = t_h1[e], h2 = t_h2[e];
+    for (int l = 0; l < pf.n; ++l) if (fp_digit(h1, h2, l) != pf.d[l]) return;
+    const unsigned long long len = (unsigned long long)(uint32_t)t_len[e];
+    atomicMax(&mm[0], (unsigned long long)h1); atomicMax(&mm[1], ~(unsigned long long)h1);
+    atomicMax(&mm[2], (unsigned long long)h2); atomicMax(&mm[3], ~(unsigned long long)h2);
+    atomicMax(&mm[4], len);                    atomicMax(&mm[5], ~len);
+}
+
+static int32_t fp_reset_call_state(FP* fp) {
+    FPState s;
+    RAPID_CUDA(cudaMemcpyAsync(fp->h_st.p, fp->st.p, sizeof(FPState), cudaMemcpyDeviceToHost, fp->stream));
+    RAPID_CUDA(cudaStreamSynchronize(fp->stream));
+    s = *fp->h_st.p;
+    s.n_valid_call = 0; s.n_cand = 0; s.i_star = INT_MAX; s.bad_sender = -1;
+    *fp->h_st.p = s;
+    RAPID_CUDA(cudaMemcpyAsync(fp->st.p, fp->h_st.p, sizeof(FPState), cudaMemcpyHostToDevice, fp->stream));
+    return RAPID_OK;
+}
+
+// votes are device arrays here
+static int32_t tally_device(FP* fp, int64_t n, const int32_t* sender, const int64_t* vcfg, const uint64_t* h1,
+                            const uint64_t* h2, const int32_t* len, int allow_skip, bool exact_order) {
+    cudaStream_t s = fp->stream;
+    const int TB = 256;
+    fp->last_launches = 0;
+    RAPID_CHECK(fp_reset_call_state(fp));
+    if (fp->h_st.p->decided || n == 0) return RAPID_OK;              // :138 — everything after the decision is ignored
+    RAPID_CHECK(fp->ent.reserve((size_t)n));
+    const unsigned g = (unsigned)ceil_div<int64_t>(n, TB);
+    k_fp_first<<<g, TB, 0, s>>>(n, sender, vcfg, fp->cfg, fp->sender_cap, allow_skip, fp->seen.p, fp->st.p);
+    k_fp_insert<<<g, TB, 0, s>>>(n, sender, vcfg, fp->cfg, fp->sender_cap, h1, h2, len, fp->seen.p, fp->T, fp->t_state.p,
+                                 fp->t_h1.p, fp->t_h2.p, fp->t_len.p, fp->t_call.p, fp->ent.p, fp->st.p);
+    const unsigned gt = (unsigned)ceil_div<uint32_t>(fp->T, TB);
+    k_fp_candidates<<<gt, TB, 0, s>>>(fp->T, fp->t_count.p, fp->t_call.p, (int32_t)fp->Q, fp->st.p);
+    RAPID_KERNEL_CHECK();
+    fp->last_launches += 3;
+    RAPID_CUDA(cudaMemcpyAsync(fp->h_st.p, fp->st.p, sizeof(FPState), cudaMemcpyDeviceToHost, s));
+    RAPID_CUDA(cudaStreamSynchronize(s));
+    const FPState st = *fp->h_st.p;
+    if (st.bad_sender >= 0) {
+        // roll the first-index marks back before failing
+        set_error("vote %d: sender id outside [0, sender_capacity)", st.bad_sender);
+        return RAPID_EINVAL;
+    }
+    int use_istar = 0;
+    if (st.n_cand > 0 && exact_order) {
+        if (st.n_cand > 8) { set_error("more than 8 proposals reached the quorum in one call"); return RAPID_EUNSUPPORTED; }
+        RAPID_CHECK(fp->scan.reserve((size_t)n));
+        for (int c = 0; c < st.n_cand; ++c) {
+            const int32_t e = st.cand[c];
+            k_fp_flag<<<g, TB, 0, s>>>(n, fp->ent.p, e, fp->scan.p);
+            k_fp_scan<<<1, 1024, 0, s>>>(fp->scan.p, n);
+            k_fp_find<<<g, TB, 0, s>>>(n, fp->ent.p, fp->scan.p, e, fp->t_count.p, (int32_t)fp->Q, fp->st.p);
+            fp->last_launches += 3;
+        }
+        k_fp_pick<<<1, 32, 0, s>>>(n, fp->ent.p, fp->st.p);
+        RAPID_KERNEL_CHECK();
+        fp->last_launches += 1;
+        use_istar = 1;
+    }
+    k_fp_apply<<<g, TB, 0, s>>>(n, sender, fp->ent.p, fp->st.p, use_istar, fp->seen.p, fp->t_count.p, fp->st.p);
+    k_fp_zero_call<<<gt, TB, 0, s>>>(fp->T, fp->t_call.p);
+    RAPID_KERNEL_CHECK();
+    fp->last_launches += 2;
+    return RAPID_OK;
+}
+
+static int32_t read_result(FP* fp, int32_t* decided, uint64_t* dh1, uint64_t* dh2, int32_t* dlen, int32_t* dcount, int32_t* received) {
+    RAPID_CUDA(cudaMemcpyAsync(fp->h_st.p, fp->st.p, sizeof(FPState), cudaMemcpyDeviceToHost, fp->stream));
+    RAPID_CUDA(cudaStreamSynchronize(fp->stream));
+    const FPState st = *fp->h_st.p;
+    if (decided) *decided = st.decided;
+    if (received) *received = st.votes_received;
+    uint64_t a = 0, b = 0;
+    int32_t l = 0, c = 0;
+    if (st.decided) {
+        RAPID_CUDA(cudaMemcpy(&a, fp->t_h1.p + st.decided_entry, 8, cudaMemcpyDeviceToHost));
+        RAPID_CUDA(cudaMemcpy(&b, fp->t_h2.p + st.decided_entry, 8, cudaMemcpyDeviceToHost));
+        RAPID_CUDA(cudaMemcpy(&l, fp->t_len.p + st.decided_entry, 4, cudaMemcpyDeviceToHost));
+        RAPID_CUDA(cudaMemcpy(&c, fp->t_count.p + st.decided_entry, 4, cudaMemcpyDeviceToHost));
+    }
+    if (dh1) *dh1 = a;
+    if (dh2) *dh2 = b;
+    if (dlen) *dlen = l;
+    if (dcount) *dcount = c;
+    return RAPID_OK;
+}
+
+}  // namespace rapid
+
+using namespace rapid;
+
+struct rapid_fp : rapid::FP {};
+struct rapid_comm : rapid::Comm {};
+
+extern "C" {
+
+int32_t rapid_fp_create(rapid_fp** out, int64_t cfg_id, int64_t membership_size, int64_t sender_capacity, int32_t device) {
+    if (!out || membership_size < 1 || sender_capacity < 1 || sender_capacity > 0x7ffffff0LL) { set_error("bad arguments"); return RAPID_EINVAL; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); set_error("no CUDA device: librapid_b200 has no CPU fallback"); return RAPID_ECUDA; }
+    if (device < 0 || device >= ndev) { set_error("device out of range"); return RAPID_EINVAL; }
+    DeviceGuard g(device);
+    rapid_fp* fp = new rapid_fp();
+    fp->device = device;
+    fp->cfg = cfg_id;
+    fp->N = membership_size;
+    fp->Q = membership_size - (membership_size - 1) / 4;            // FastPaxos.java:145
+    fp->sender_cap = sender_capacity;
+    uint32_t T = 1024;
+    while ((int64_t)T < 2 * sender_capacity) T <<= 1;
+    fp->T = T;
+    int32_t rc = RAPID_OK;
+    do {
+        if (cudaStreamCreateWithFlags(&fp->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&fp->ev0) != cudaSuccess ||
+            cudaEventCreate(&fp->ev1) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "stream", __FILE__, __LINE__); break; }
+        if ((rc = fp->seen.reserve((size_t)sender_capacity))) break;
+        if ((rc = fp->t_state.reserve(T))) break;
+        if ((rc = fp->t_len.reserve(T))) break;
+        if ((rc = fp->t_count.reserve(T))) break;
+        if ((rc = fp->t_call.reserve(T))) break;
+        if ((rc = fp->t_h1.reserve(T))) break;
+        if ((rc = fp->t_h2.reserve(T))) break;
+        if ((rc = fp->st.reserve(1))) break;
+        if ((rc = fp->h_st.reserve(1))) break;
+        if ((rc = fp->hist.reserve(65536))) break;
+        if ((rc = fp->mm.reserve(8))) break;
+        if ((rc = fp->h_mm.reserve(8))) break;
+        const int TB = 256;
+        k_fp_fill<<<(unsigned)ceil_div<int64_t>(sender_capacity, TB), TB, 0, fp->stream>>>(fp->seen.p, sender_capacity, INT_MAX);
+        cudaMemsetAsync(fp->t_state.p, 0, T * sizeof(int32_t), fp->stream);
+        cudaMemsetAsync(fp->t_count.p, 0, T * sizeof(int32_t), fp->stream);
+        cudaMemsetAsync(fp->t_call.p, 0, T * sizeof(int32_t), fp->stream);
+        cudaMemsetAsync(fp->st.p, 0, sizeof(FPState), fp->stream);
+        if (cudaStreamSynchronize(fp->stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "init", __FILE__, __LINE__); break; }
+    } while (0);
+    if (rc) { rapid_fp_destroy(fp); return rc; }
+    *out = fp;
+    return RAPID_OK;
+}
+
+int32_t rapid_fp_destroy(rapid_fp* fp) {
+    if (!fp) return RAPID_OK;
+    DeviceGuard g(fp->device);
+    if (fp->stream) cudaStreamSynchronize(fp->stream);
+    if (fp->ev0) cudaEventDestroy(fp->ev0);
+    if (fp->ev1) cudaEventDestroy(fp->ev1);
+    if (fp->stream) cudaStreamDestroy(fp->stream);
+    delete fp;
+    return RAPID_OK;
+}
+
+int32_t rapid_fp_tally(rapid_fp* fp, int64_t n_votes, const int32_t* sender, const int64_t* vote_cfg, const uint64_t* proposal_hash,
+                       const uint64_t* proposal_hash2, const int32_t* proposal_len, int32_t* decided, uint64_t* decided_hash,
+                       uint64_t* decided_hash2, int32_t* decided_len, int32_t* decided_count, int32_t* votes_received) {
+    if (!fp || n_votes < 0 || (n_votes && (!sender || !proposal_hash))) { set_error("bad arguments"); return RAPID_EINVAL; }
+    DeviceGuard g(fp->device);
+    cudaStream_t s = fp->stream;
+    const size_t m = (size_t)std::max<int64_t>(n_votes, 1);
+    RAPID_CHECK(fp->v_sender.reserve(m));
+    RAPID_CHECK(fp->v_h1.reserve(m));
+    RAPID_CUDA(cudaEventRecord(fp->ev0, s));
+    if (n_votes) {
+        RAPID_CUDA(cudaMemcpyAsync(fp->v_sender.p, sender, (size_t)n_votes * 4, cudaMemcpyHostToDevice, s));
+        RAPID_CUDA(cudaMemcpyAsync(fp->v_h1.p, proposal_hash, (size_t)n_votes * 8, cudaMemcpyHostToDevice, s));
+        if (vote_cfg) { RAPID_CHECK(fp->v_cfg.reserve(m)); RAPID_CUDA(cudaMemcpyAsync(fp->v_cfg.p, vote_cfg, (size_t)n_votes * 8, cudaMemcpyHostToDevice, s)); }
+        if (proposal_hash2) { RAPID_CHECK(fp->v_h2.reserve(m)); RAPID_CUDA(cudaMemcpyAsync(fp->v_h2.p, proposal_hash2, (size_t)n_votes * 8, cudaMemcpyHostToDevice, s)); }
+        if (proposal_len) { RAPID_CHECK(fp->v_len.reserve(m)); RAPID_CUDA(cudaMemcpyAsync(fp->v_len.p, proposal_len, (size_t)n_votes * 4, cudaMemcpyHostToDevice, s)); }
+    }
+    RAPID_CHECK(tally_device(fp, n_votes, fp->v_sender.p, vote_cfg ? fp->v_cfg.p : nullptr, fp->v_h1.p,
+                             proposal_hash2 ? fp->v_h2.p : nullptr, proposal_len ? fp->v_len.p : nullptr, 0, true));
+    RAPID_CUDA(cudaEventRecord(fp->ev1, s));
+    RAPID_CHECK(read_result(fp, decided, decided_hash, decided_hash2, decided_len, decided_count, votes_received));
+    cudaEventElapsedTime(&fp->last_ms, fp->ev0, fp->ev1);
+    return RAPID_OK;
+}
+
+int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, int32_t* decided, uint64_t* decided_hash,
+                          uint64_t* decided_hash2, int32_t* decided_len, int32_t* decided_count, int32_t* votes_received) {
+    if (!fp || !cd) { set_error("NULL handle"); return RAPID_EINVAL; }
+    if (fp->device != cd->device) { set_error("fp and cd live on different devices"); return RAPID_EINVAL; }
+    if (cd->raw) { set_error("RAW detectors do not announce proposals"); return RAPID_EINVAL; }
+    DeviceGuard g(fp->device);
+    cudaStream_t s = fp->stream;
+    const int TB = 256;
+    const int64_t R = cd->R;
+    RAPID_CHECK(fp->v_sender.reserve((size_t)R));
+    RAPID_CUDA(cudaEventRecord(fp->ev0, s));
+    k_fp_votes_from_cd<<<(unsigned)ceil_div<int64_t>(R, TB), TB, 0, s>>>(R, cd->rflags.p, cd->view->ring.p, cd->rbegin, fp->v_sender.p);
+    RAPID_KERNEL_CHECK();
+    // single GPU: exact arrival order = receiver order.  Sharded: counts only (order across ranks is undefined).
+    RAPID_CHECK(tally_device(fp, R, fp->v_sender.p, nullptr, cd->out_h1.p, cd->out_h2.p, cd->out_len.p, 1, comm == nullptr));
+    fp->last_launches += 1;
+    if (comm == nullptr) {
+        RAPID_CUDA(cudaEventRecord(fp->ev1, s));
+        RAPID_CHECK(read_result(fp, decided, decided_hash, decided_hash2, decided_len, decided_count, votes_received));
+        cudaEventElapsedTime(&fp->last_ms, fp->ev0, fp->ev1);
+        return RAPID_OK;
+    }
+    // ---- sharded: radix histogram of the local table -> ONE all-reduce (sum) -> verify the winning bucket holds a
+    // single fingerprint with a 6-word all-reduce (max); refine digit by digit only if two fingerprints share it.
+    if (comm->device != fp->device) { set_error("comm and fp live on different devices"); return RAPID_EINVAL; }
+    const unsigned gt = (unsigned)ceil_div<uint32_t>(fp->T, TB);
+    Prefix pf;
+    pf.n = 0;
+    int32_t dec = 0, dcount = 0, dlen = 0;
+    uint64_t dh1 = 0, dh2 = 0;
+    for (int level = 0; level < 8 && !dec; ++level) {
+        RAPID_CUDA(cudaMemsetAsync(fp->hist.p, 0, 65536 * sizeof(int32_t), s));
+        k_fp_hist<<<gt, TB, 0, s>>>(fp->T, fp->t_state.p, fp->t_h1.p, fp->t_h2.p, fp->t_count.p, pf, fp->hist.p);
+        RAPID_KERNEL_CHECK();
+        RAPID_NCCL(g_nccl.AllReduce(fp->hist.p, fp->hist.p, 65536, NCCL_INT32, NCCL_SUM, comm->comm, s));
+        RAPID_CHECK(fp_reset_call_state(fp));
+        k_fp_hist_cand<<<65536 / TB, TB, 0, s>>>(fp->hist.p, (int32_t)fp->Q, fp->st.p);
+        RAPID_KERNEL_CHECK();
+        fp->last_launches += 2;
+        RAPID_CUDA(cudaMemcpyAsync(fp->h_st.p, fp->st.p, sizeof(FPState), cudaMemcpyDeviceToHost, s));
+        RAPID_CUDA(cudaStreamSynchronize(s));
+        const FPState st = *fp->h_st.p;
+        if (st.n_cand == 0) break;                                   // nothing reaches the quorum
+        // senders are members here, so at most one proposal can reach Q > N/2: follow the first candidate bucket
+        pf.d[pf.n++] = (uint32_t)st.cand[0];
+        int32_t bucket_count = 0;
+        RAPID_CUDA(cudaMemcpyAsync(&bucket_count, fp->hist.p + st.cand[0], 4, cudaMemcpyDeviceToHost, s));
+        RAPID_CUDA(cudaMemsetAsync(fp->mm.p, 0, 8 * sizeof(unsigned long long), s));
+        k_fp_minmax<<<gt, TB, 0, s>>>(fp->T, fp->t_state.p, fp->t_h1.p, fp->t_h2.p, fp->t_len.p, fp->t_count.p, pf, fp->mm.p);
+        RAPID_KERNEL_CHECK();
+        fp->last_launches += 1;
+        RAPID_NCCL(g_nccl.AllReduce(fp->mm.p, fp->mm.p, 6, NCCL_UINT64, NCCL_MAX, comm->comm, s));
+        RAPID_CUDA(cudaMemcpyAsync(fp->h_mm.p, fp->mm.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        RAPID_CUDA(cudaStreamSynchronize(s));
+        const unsigned long long* mm = fp->h_mm.p;
+        if (mm[0] == ~mm[1] && mm[2] == ~mm[3] && mm[4] == ~mm[5]) {  // one fingerprint in the bucket: its count is exact
+            dec = 1; dcount = bucket_count; dh1 = mm[0]; dh2 = mm[2]; dlen = (int32_t)mm[4];
+        }
+    }
+    int32_t recv_local = fp->h_st.p->votes_received, recv = 0;
+    {   // votesReceived across ranks (tiny all-reduce on the same stream)
+        RAPID_CUDA(cudaMemsetAsync(fp->hist.p, 0, sizeof(int32_t), s));
+        RAPID_CUDA(cudaMemcpyAsync(fp->hist.p, &recv_local, 4, cudaMemcpyHostToDevice, s));
+        RAPID_NCCL(g_nccl.AllReduce(fp->hist.p, fp->hist.p, 1, NCCL_INT32, NCCL_SUM, comm->comm, s));
+        RAPID_CUDA(cudaMemcpyAsync(&recv, fp->hist.p, 4, cudaMemcpyDeviceToHost, s));
+    }
+    RAPID_CUDA(cudaEventRecord(fp->ev1, s));
+    RAPID_CUDA(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&fp->last_ms, fp->ev0, fp->ev1);
+    if (dec) {      // remember the decision locally so later votes are ignored (:138)
+        FPState stn = *fp->h_st.p;
+        stn.decided = 1; stn.decided_entry = -1;
+        *fp->h_st.p = stn;
+        RAPID_CUDA(cudaMemcpy(fp->st.p, fp->h_st.p, sizeof(FPState), cudaMemcpyHostToDevice));
+    }
+    if (decided) *decided = dec;
+    if (decided_hash) *decided_hash = dh1;
+    if (decided_hash2) *decided_hash2 = dh2;
+    if (decided_len) *decided_len = dlen;
+    if (decided_count) *decided_count = dcount;
+    if (votes_received) *votes_received = recv;
+    return RAPID_OK;
+}
+
+int32_t rapid_fp_last_device_ms(const rapid_fp* fp, float* total_ms) {
+    if (!fp) { set_error("NULL handle"); return RAPID_EINVAL; }
+    if (total_ms) *total_ms = fp->last_ms;
+    return RAPID_OK;
+}
+
+int32_t rapid_comm_unique_id(void* out_id) {
+    if (!out_id) { set_error("NULL argument"); return RAPID_EINVAL; }
+    RAPID_CHECK(load_nccl());
+    nccl_uid id;
+    RAPID_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(out_id, &id, sizeof(id));
+    return RAPID_OK;
+}
+
+int32_t rapid_comm_init(rapid_comm** out, int32_t rank, int32_t world, const void* nccl_unique_id, int32_t device) {
+    if (!out || !nccl_unique_id || world < 1 || rank < 0 || rank >= world) { set_error("bad arguments"); return RAPID_EINVAL; }
+    *out = nullptr;
+    RAPID_CHECK(load_nccl());
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); set_error("bad device"); return RAPID_ECUDA; }
+    RAPID_CUDA(cudaSetDevice(device));
+    rapid_comm* c = new rapid_comm();
+    c->device = device; c->rank = rank; c->world = world;
+    nccl_uid id;
+    memcpy(&id, nccl_unique_id, sizeof(id));
+    int r = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    if (r != 0) { set_error("ncclCommInitRank failed: %d (%s)", r, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); delete c; return RAPID_ENCCL; }
+    *out = c;
+    return RAPID_OK;
+}
+
+int32_t rapid_comm_destroy(rapid_comm* c) {
+    if (!c) return RAPID_OK;
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    delete c;
+    return RAPID_OK;
+}
+
+}  // extern "C"

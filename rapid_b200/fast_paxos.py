@@ -1,0 +1,95 @@
+"""Host-side mirror of the fast round of com.vrg.rapid.FastPaxos (FastPaxos.java:125-156): the vote tally of one
+configuration, computed by librapid_b200.so on the GPU."""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+def quorum(membership_size):
+    """N - floor((N-1)/4)   (FastPaxos.java:145)"""
+    out = C.c_int64(0)
+    N.check(N.lib().rapid_fp_quorum(int(membership_size), C.byref(out)))
+    return out.value
+
+
+class TallyResult:
+    __slots__ = ("decided", "hash", "hash2", "length", "count", "votes_received")
+
+    def __init__(self, decided, h1, h2, ln, count, received):
+        self.decided, self.hash, self.hash2, self.length, self.count, self.votes_received = decided, h1, h2, ln, count, received
+
+    def __repr__(self):
+        return "TallyResult(decided=%s, hash=%#x, len=%d, count=%d, votes_received=%d)" % (
+            self.decided, self.hash, self.length, self.count, self.votes_received)
+
+
+class NcclComm:
+    """One NCCL communicator per process/GPU for the sharded tally (created from a unique id that rank 0 makes)."""
+
+    @staticmethod
+    def unique_id():
+        buf = np.zeros(128, np.uint8)
+        N.check(N.lib().rapid_comm_unique_id(N.ptr(buf)))
+        return buf
+
+    def __init__(self, rank, world, unique_id, device):
+        self._h = C.c_void_p()
+        uid = N.as_u8(unique_id)
+        N.check(N.lib().rapid_comm_init(C.byref(self._h), rank, world, N.ptr(uid), device))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            N.lib().rapid_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class FastPaxos:
+    """FastPaxos(myAddr, configurationId, membershipSize, ...) — fast round only (FastPaxos.java:61-85, :125-156)."""
+
+    def __init__(self, configuration_id, membership_size, sender_capacity=None, device=0):
+        self.N = int(membership_size)
+        self.cfg = int(configuration_id)
+        cap = int(sender_capacity if sender_capacity is not None else membership_size)
+        self._h = C.c_void_p()
+        N.check(N.lib().rapid_fp_create(C.byref(self._h), self.cfg, self.N, cap, device))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            N.lib().rapid_fp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _outs():
+        return C.c_int32(0), C.c_uint64(0), C.c_uint64(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+
+    def handleFastRoundProposals(self, senders, proposal_hash, proposal_hash2=None, proposal_len=None, vote_cfg=None):
+        """Apply FastRoundPhase2bMessages in order (handleFastRoundProposal per vote)."""
+        s = N.as_i32(senders)
+        h1 = np.ascontiguousarray(proposal_hash, np.uint64)
+        h2 = None if proposal_hash2 is None else np.ascontiguousarray(proposal_hash2, np.uint64)
+        ln = None if proposal_len is None else N.as_i32(proposal_len)
+        vc = None if vote_cfg is None else N.as_i64(vote_cfg)
+        d, a, b, l, c, r = self._outs()
+        N.check(N.lib().rapid_fp_tally(self._h, len(s), N.ptr(s), N.ptr(vc), N.ptr(h1), N.ptr(h2), N.ptr(ln), C.byref(d),
+                                       C.byref(a), C.byref(b), C.byref(l), C.byref(c), C.byref(r)))
+        return TallyResult(bool(d.value), a.value, b.value, l.value, c.value, r.value)
+
+    def tallyCluster(self, cluster, comm=None):
+        """Every receiver of `cluster` that announced in the last batch votes for its proposal."""
+        d, a, b, l, c, r = self._outs()
+        N.check(N.lib().rapid_fp_tally_cd(self._h, cluster._h, comm._h if comm is not None else None, C.byref(d),
+                                          C.byref(a), C.byref(b), C.byref(l), C.byref(c), C.byref(r)))
+        return TallyResult(bool(d.value), a.value, b.value, l.value, c.value, r.value)
+
+    def lastDeviceMs(self):
+        a = C.c_float(0)
+        N.check(N.lib().rapid_fp_last_device_ms(self._h, C.byref(a)))
+        return a.value

@@ -1,0 +1,272 @@
+"""The cut-detection kernels vs the oracle, through the C ABI.
+
+First the reference's own CutDetectionTest (rapid/src/test/java/com/vrg/rapid/CutDetectionTest.java) driven through
+RAW handles; then the MembershipService batch semantics for R virtual nodes on the BASELINE configs' shapes."""
+import numpy as np
+import pytest
+
+from helpers import OracleWorld, compare_batch, random_batch
+from rapid_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+K, H, L = 10, 8, 2
+UP, DOWN = 0, 1
+CFG = -1
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import rapid_b200
+    return rapid_b200
+
+
+@pytest.fixture()
+def view30(rb):
+    # 127.0.0.2:2..31 are the subjects the Java tests use; sources are arbitrary ids (src is never read back)
+    return rb.MembershipView(K, ["127.0.0.2"] * 30, list(range(2, 32)))
+
+
+def test_cut_detection(rb, view30):                        # CutDetectionTest.java:43-59
+    wb = rb.MultiNodeCutDetector(view30, H, L)
+    dst = 0
+    for i in range(H - 1):
+        assert wb.aggregateForProposal(i + 1, dst, UP, i) == [] and wb.getNumProposals() == 0
+    assert wb.aggregateForProposal(H, dst, UP, H - 1) == [dst] and wb.getNumProposals() == 1
+
+
+def test_blocking_one_blocker(rb, view30):                 # :62-91
+    wb = rb.MultiNodeCutDetector(view30, H, L)
+    for d in (0, 1):
+        for i in range(H - 1):
+            assert wb.aggregateForProposal(i + 1, d, UP, i) == [] and wb.getNumProposals() == 0
+    assert wb.aggregateForProposal(H, 0, UP, H - 1) == [] and wb.getNumProposals() == 0
+    assert wb.aggregateForProposal(H, 1, UP, H - 1) == [0, 1] and wb.getNumProposals() == 1
+
+
+def test_blocking_three_blockers(rb, view30):              # :95-137
+    wb = rb.MultiNodeCutDetector(view30, H, L)
+    for d in (0, 1, 2):
+        for i in range(H - 1):
+            assert wb.aggregateForProposal(i + 1, d, UP, i) == []
+    assert wb.aggregateForProposal(H, 0, UP, H - 1) == [] and wb.getNumProposals() == 0
+    assert wb.aggregateForProposal(H, 2, UP, H - 1) == [] and wb.getNumProposals() == 0
+    assert wb.aggregateForProposal(H, 1, UP, H - 1) == [0, 1, 2] and wb.getNumProposals() == 1
+
+
+def test_blocking_multiple_blockers_past_h(rb, view30):    # :140-189
+    wb = rb.MultiNodeCutDetector(view30, H, L)
+    for d in (0, 1, 2):
+        for i in range(H - 1):
+            assert wb.aggregateForProposal(i + 1, d, UP, i) == []
+    wb.aggregateForProposal(H, 0, UP, H - 1)
+    assert wb.aggregateForProposal(H + 1, 0, UP, H - 1) == [] and wb.getNumProposals() == 0
+    wb.aggregateForProposal(H, 2, UP, H - 1)
+    assert wb.aggregateForProposal(H + 1, 2, UP, H - 1) == [] and wb.getNumProposals() == 0
+    assert wb.aggregateForProposal(H, 1, UP, H - 1) == [0, 1, 2] and wb.getNumProposals() == 1
+
+
+def test_below_l(rb, view30):                              # :192-230
+    wb = rb.MultiNodeCutDetector(view30, H, L)
+    for i in range(H - 1):
+        assert wb.aggregateForProposal(i + 1, 0, UP, i) == []
+    for i in range(L - 1):
+        assert wb.aggregateForProposal(i + 1, 1, UP, i) == []
+    for i in range(H - 1):
+        assert wb.aggregateForProposal(i + 1, 2, UP, i) == []
+    assert wb.aggregateForProposal(H, 0, UP, H - 1) == [] and wb.getNumProposals() == 0
+    assert wb.aggregateForProposal(H, 2, UP, H - 1) == [0, 2] and wb.getNumProposals() == 1
+
+
+def test_batch(rb, view30):                                # :234-252
+    wb = rb.MultiNodeCutDetector(view30, H, L)
+    proposal = []
+    for e in (0, 1, 2):
+        proposal += wb.aggregateForProposal(5, e, UP, list(range(K)))     # one AlertMessage with K ring numbers
+    assert sorted(proposal) == [0, 1, 2]
+
+
+def test_link_invalidation(rb, view30):                    # :255-301
+    wb = rb.MultiNodeCutDetector(view30, H, L)
+    dst = 0
+    observers = view30.getObserversOf(dst)
+    assert len(observers) == K
+    for i in range(H - 1):
+        assert wb.aggregateForProposal(observers[i], dst, DOWN, i) == [] and wb.getNumProposals() == 0
+    failed = set()
+    for i in range(H - 1, K):
+        oo = view30.getObserversOf(observers[i])
+        failed.add(observers[i])
+        for j in range(K):
+            assert wb.aggregateForProposal(oo[j], observers[i], DOWN, j) == [] and wb.getNumProposals() == 0
+    ret = wb.invalidateFailingEdges()
+    assert len(ret) == 4 and wb.getNumProposals() == 1
+    assert set(ret) == failed | {dst}
+    wb.clear()
+    assert wb.getNumProposals() == 0 and wb.invalidateFailingEdges() == []
+
+
+def test_ctor_validation_and_bad_cells(rb, view30):        # MultiNodeCutDetector.java:51-55
+    for h, l in ((11, 2), (8, 9), (8, 0), (0, 0)):
+        with pytest.raises(ValueError):
+            rb.MultiNodeCutDetector(view30, h, l)
+    small = rb.MembershipView(2, ["a"], [1])
+    with pytest.raises(ValueError):
+        rb.MultiNodeCutDetector(small, 2, 1)               # K < 3
+    wb = rb.MultiNodeCutDetector(view30, H, L)
+    with pytest.raises(rb.RapidError):
+        wb.aggregateForProposal(1, 0, UP, K)               # ring number >= K
+    with pytest.raises(rb.RapidError):
+        wb.aggregateForProposal(1, 31, UP, 0)              # unknown endpoint id
+
+
+# ------------------------------------------------------------------------------------------------------
+# MembershipService batch semantics for R virtual nodes
+# ------------------------------------------------------------------------------------------------------
+KERNELS = ["sweep", "bucketed"]
+
+
+def _worlds(orc, rb, n, n_joiners=0, Hh=9, Ll=4, kernel="sweep", R=None, begin=0):
+    w = OracleWorld(orc, n, K, n_joiners=n_joiners)
+    v = rb.MembershipView.from_packed(K, *w.member_packed())
+    if n_joiners:
+        v.registerJoiners(*w.joiner_endpoints())
+    R = n if R is None else R
+    sim = orc.ClusterSim(w.view, K, Hh, Ll, R, receiver_base=begin)
+    cl = rb.VirtualCluster(v, Hh, Ll, n_receivers=R, receiver_begin=begin, kernel=kernel)
+    return w, v, sim, cl
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_c1_single_crash(orc, rb, kernel):
+    w, v, sim, cl = _worlds(orc, rb, 50, kernel=kernel)
+    obs, _ = v.tables()
+    b = W.c1_single_crash(obs, 50)
+    blocked = W.blocked_by_receiver(b.blocked, v.getRing(0), 0, 50)
+    o_len, o_ann = compare_batch(rb, w, sim, cl, 7, (b.src, b.dst, b.ring, b.status), blocked=blocked)
+    assert (o_len[blocked == 0] == 1).all() and (o_len[blocked == 1] == 0).all()
+    # a second batch is ignored by everyone who announced (MembershipService.java:318-319)
+    compare_batch(rb, w, sim, cl, 7, (b.src, b.dst, b.ring, b.status), blocked=blocked)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_c2_simultaneous_crash(orc, rb, kernel):
+    n = 2000
+    w, v, sim, cl = _worlds(orc, rb, n, kernel=kernel)
+    obs, _ = v.tables()
+    b = W.c2_simultaneous_crash(obs, n, 0.01)
+    blocked = W.blocked_by_receiver(b.blocked, v.getRing(0), 0, n)
+    o_len, _ = compare_batch(rb, w, sim, cl, 11, (b.src, b.dst, b.ring, b.status), blocked=blocked)
+    live = np.nonzero(blocked == 0)[0]
+    assert (o_len[live] == 20).all()
+    assert cl.getProposal(int(live[0])) and sorted(cl.getProposal(int(live[0]))) == b.expected_cut.tolist()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_c3_correlated_partition_needs_invalidation(orc, rb, kernel):
+    n = 2000
+    w, v, sim, cl = _worlds(orc, rb, n, kernel=kernel)
+    obs, _ = v.tables()
+    b = W.c3_correlated_partition(obs, v.getRing(0), n, 0.05)
+    blocked = W.blocked_by_receiver(b.blocked, v.getRing(0), 0, n)
+    o_len, _ = compare_batch(rb, w, sim, cl, 3, (b.src, b.dst, b.ring, b.status), blocked=blocked)
+    live = np.nonzero(blocked == 0)[0]
+    assert (o_len[live] == 100).all()          # the whole arc, emitted by invalidateFailingEdges
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_c5_churn_joins_and_leaves(orc, rb, kernel):
+    n, nl, nj = 3000, 15, 15
+    w, v, sim, cl = _worlds(orc, rb, n, n_joiners=nj, kernel=kernel)
+    obs, _ = v.tables()
+    b = W.c5_churn(obs, w.joiner_obs(), n, nl, nj)
+    blocked = W.blocked_by_receiver(b.blocked, v.getRing(0), 0, n)
+    o_len, _ = compare_batch(rb, w, sim, cl, 99, (b.src, b.dst, b.ring, b.status), blocked=blocked)
+    live = np.nonzero(blocked == 0)[0]
+    assert (o_len[live] == nl + nj).all()
+    assert sorted(cl.getProposal(int(live[3]))) == b.expected_cut.tolist()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_filter_rules(orc, rb, kernel):
+    """cfg mismatch, UP about a member, DOWN about a non-member are dropped (MembershipService.java:644-675)"""
+    n, nj = 300, 4
+    w, v, sim, cl = _worlds(orc, rb, n, n_joiners=nj, kernel=kernel)
+    rng = np.random.default_rng(5)
+    src, dst, ring, status = random_batch(rng, n + nj, K, 12, 150, n)
+    status = rng.integers(0, 2, size=len(dst)).astype(np.uint8)          # deliberately inconsistent
+    cell_cfg = np.where(rng.random(len(dst)) < 0.2, 8, 42).astype(np.int64)
+    compare_batch(rb, w, sim, cl, 42, (src, dst, ring, status), cell_cfg=cell_cfg)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("seed", range(6))
+def test_random_multi_batch_streams(orc, rb, kernel, seed):
+    """several batches with duplicates, carried state between batches, every receiver the same order"""
+    n, nj = 400, 6
+    Hh, Ll = [(9, 4), (8, 2), (8, 3), (9, 3), (5, 5), (10, 1)][seed]
+    w, v, sim, cl = _worlds(orc, rb, n, n_joiners=nj, Hh=Hh, Ll=Ll, kernel=kernel)
+    rng = np.random.default_rng(100 + seed)
+    for _ in range(6):
+        src, dst, ring, status = random_batch(rng, n + nj, K, int(rng.integers(1, 9)), int(rng.integers(1, 60)), n)
+        compare_batch(rb, w, sim, cl, 1, (src, dst, ring, status))
+    cl.clear(); sim.reset()
+    src, dst, ring, status = random_batch(rng, n + nj, K, 3, 40, n)
+    compare_batch(rb, w, sim, cl, 1, (src, dst, ring, status))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("seed", range(4))
+def test_per_receiver_delivery_bitmap(orc, rb, kernel, seed):
+    """receivers see different subsets (partitions): masks, pre-proposals and announcements diverge"""
+    n = 257
+    w, v, sim, cl = _worlds(orc, rb, n, kernel=kernel, Hh=8, Ll=3)
+    rng = np.random.default_rng(900 + seed)
+    words = (n + 31) // 32
+    for _ in range(5):
+        src, dst, ring, status = random_batch(rng, n, K, int(rng.integers(2, 7)), int(rng.integers(5, 70)), n)
+        bitmap = rng.integers(0, 2**32, size=(len(dst), words), dtype=np.uint64).astype(np.uint32)
+        if seed % 2:
+            bitmap |= rng.integers(0, 2**32, size=(len(dst), words), dtype=np.uint64).astype(np.uint32)
+        blocked = (rng.random(n) < 0.1).astype(np.uint8)
+        compare_batch(rb, w, sim, cl, 5, (src, dst, ring, status), blocked=blocked, bitmap=bitmap)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_per_receiver_permuted_order(orc, rb, seed):
+    """every receiver applies the batch in its own order (the K,H,L sensitivity-study shape): bucketed kernels only"""
+    n = 300
+    w, v, sim, cl = _worlds(orc, rb, n, kernel="bucketed", Hh=8, Ll=3, R=200, begin=50)
+    rng = np.random.default_rng(40 + seed)
+    for t in range(4):
+        src, dst, ring, status = random_batch(rng, n, K, int(rng.integers(2, 8)), int(rng.integers(10, 80)), n)
+        compare_batch(rb, w, sim, cl, 5, (src, dst, ring, status), perm_seed=W.SEED + 2 + t)
+
+
+def test_c4_flip_flop_stream(orc, rb):
+    n = 1000
+    w, v, sim, cl = _worlds(orc, rb, n, kernel="bucketed")
+    obs, _ = v.tables()
+    batches = W.c4_flip_flop_stream(obs, n, 0.01, T=8)
+    blocked = W.blocked_by_receiver(batches[0].blocked, v.getRing(0), 0, n)
+    announced_any = False
+    for b in batches:
+        o_len, o_ann = compare_batch(rb, w, sim, cl, 17, (b.src, b.dst, b.ring, b.status), blocked=blocked,
+                                     perm_seed=b.meta["perm_seed"])
+        announced_any |= bool(o_ann.any())
+    assert announced_any
+
+
+def test_sweep_rejects_permuted(orc, rb):
+    w, v, sim, cl = _worlds(orc, rb, 50, kernel="sweep")
+    with pytest.raises(rb.RapidError):
+        cl.handleBatch(1, [0], [1], [0], [DOWN], perm_seed=3)
+
+
+def test_num_proposals_sweep(orc, rb):
+    n = 200
+    w, v, sim, cl = _worlds(orc, rb, n, kernel="sweep", Hh=8, Ll=2)
+    rng = np.random.default_rng(3)
+    src, dst, ring, status = random_batch(rng, n, K, 3, 60, n)
+    compare_batch(rb, w, sim, cl, 1, (src, dst, ring, status))
+    for r in (0, 57, n - 1):
+        assert cl.getNumProposals(r) == sim.numProposals(r)

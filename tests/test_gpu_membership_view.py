@@ -1,0 +1,111 @@
+"""GPU MembershipView (librapid_b200) vs the oracle, through the C ABI: ring order, keys, observer / subject /
+expected-observer tables, ring numbers, configuration id; plus the structural invariants MembershipViewTest asserts
+(rapid/src/test/java/com/vrg/rapid/MembershipViewTest.java)."""
+import numpy as np
+import pytest
+
+from helpers import OracleWorld
+from rapid_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+K = 10
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import rapid_b200
+    return rapid_b200
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 50, 1000, 5000])
+def test_rings_tables_config_id_match_oracle(orc, rb, n):
+    w = OracleWorld(orc, n, K)
+    v = rb.MembershipView.from_packed(K, *w.member_packed())
+    assert v.getMembershipSize() == n
+    for k in range(K):
+        np.testing.assert_array_equal(v.getRing(k), np.asarray(w.view.getRing(k), np.int32))
+        keys = v.keys(k)
+        for i in (0, n // 2, n - 1):
+            assert int(keys[i]) == w.view.key(k, i)
+    obs, subj = v.tables()
+    if n > 1:
+        o_obs, o_subj = w.tables()
+        np.testing.assert_array_equal(obs, o_obs)
+        np.testing.assert_array_equal(subj, o_subj)
+    for i in {0, n // 3, n - 1}:
+        assert v.getObserversOf(i) == w.view.getObserversOf(i)          # [] when n == 1
+        assert v.getSubjectsOf(i) == w.view.getSubjectsOf(i)
+    assert v.getCurrentConfigurationId(w.id_high, w.id_low) == w.view.getCurrentConfigurationId()
+    # identifiers of departed nodes stay in identifiersSeen (MembershipView.java:167-201): more ids than members
+    hi2, lo2 = W.node_ids(0, n + 7)
+    ref = orc.MembershipView(w.u, K, np.arange(n, dtype=np.int32), hi2, lo2)
+    assert v.getCurrentConfigurationId(hi2, lo2) == ref.getCurrentConfigurationId()
+
+
+def test_not_in_ring_and_small_views(rb):
+    v = rb.MembershipView(K, ["127.0.0.1"], [1])
+    assert v.getObserversOf(0) == [] and v.getSubjectsOf(0) == []       # MembershipViewTest.java:166-176
+    with pytest.raises(rb.NodeNotInRingException):
+        v.getObserversOf(1)
+    with pytest.raises(rb.NodeNotInRingException):
+        v.getSubjectsOf(5)
+    assert v.getExpectedObserversOf("127.0.0.1", 2) == [0] * K          # :298-313
+    v2 = rb.MembershipView(K, ["127.0.0.1", "127.0.0.1"], [1, 2])
+    assert v2.getObserversOf(0) == [1] * K and v2.getSubjectsOf(0) == [1] * K   # :221-235
+    empty = rb.MembershipView(K)
+    assert empty.getMembershipSize() == 0
+    assert empty.getExpectedObserversOf("127.0.0.1", 1) == []
+    with pytest.raises(rb.NodeNotInRingException):
+        empty.getObserversOf(0)
+
+
+def test_duplicate_endpoint_rejected(rb):
+    with pytest.raises(rb.NodeAlreadyInRingException):
+        rb.MembershipView(K, ["a", "b", "a"], [1, 1, 1])
+
+
+def test_k_observers_and_subjects_for_every_node(rb):                  # MembershipViewTest.java:268-293
+    hosts, ports = ["127.0.0.1"] * 1000, list(range(1000))
+    v = rb.MembershipView(K, hosts, ports)
+    obs, subj = v.tables()
+    assert obs.shape == (1000, K) and (obs >= 0).all() and (subj >= 0).all()
+    assert (obs != np.arange(1000)[:, None]).all()
+    # observer/subject are inverse relations on every ring
+    for k in range(K):
+        assert (subj[obs[:, k], k] == np.arange(1000)).all()
+
+
+def test_expected_observers_and_ring_numbers(orc, rb):
+    n, nj = 400, 25
+    w = OracleWorld(orc, n, K, n_joiners=nj)
+    v = rb.MembershipView.from_packed(K, *w.member_packed())
+    hosts, ports = w.joiner_endpoints()
+    for j in range(nj):
+        assert v.getExpectedObserversOf(hosts[j], int(ports[j])) == w.view.getExpectedObserversOf(n + j)
+    ids = v.registerJoiners(hosts, ports)
+    assert ids == list(range(n, n + nj)) and v.numJoiners() == nj
+    for k in (0, 9):
+        keys = v.keys(k)
+        for j in (0, nj - 1):
+            assert int(keys[n + j]) == w.view.key(k, n + j)
+    with pytest.raises(rb.NodeAlreadyInRingException):
+        h0, p0 = W.endpoints(5, 1)
+        v.registerJoiners(h0, p0)
+    for i in range(0, n, 37):
+        for o in set(w.view.getObserversOf(i)):
+            assert v.getRingNumbers(o, i) == w.view.getRingNumbers(o, i)
+    # expected observers of a member-shaped endpoint that is already in the ring: still predecessors
+    assert v.getExpectedObserversOf(*[x[0] for x in W.endpoints(7, 1)][:1], int(W.endpoints(7, 1)[1][0])) == w.view.getExpectedObserversOf(7)
+
+
+def test_long_hostnames(orc, rb):
+    """XXH64's >= 32-byte stripe loop on the device"""
+    hosts = ["node-%04d.some-very-long-datacenter-name.example.internal" % i for i in range(64)]
+    ports = [9000 + (i % 3) for i in range(64)]
+    u = orc.Universe()
+    tags = [u.add(h, p) for h, p in zip(hosts, ports)]
+    ref = orc.MembershipView(u, K, tags, [], [])
+    v = rb.MembershipView(K, hosts, ports)
+    for k in range(K):
+        assert v.getRing(k).tolist() == ref.getRing(k)
+    assert v.getCurrentConfigurationId([], []) == ref.getCurrentConfigurationId()
