@@ -134,13 +134,10 @@ __global__ void __launch_bounds__(128) k_sweep(const SweepArgs a) {
     if (r >= a.R) return;
     uint32_t flags = a.rflags[r];
     flags &= ~RF_ANN_NOW;
-    if (!a.raw && (flags & RF_ANNOUNCED)) {            // MembershipService.java:318-319
+    if ((!a.raw && (flags & RF_ANNOUNCED)) ||                         // MembershipService.java:318-319
+        ((a.dl.flags & RAPID_DELIVERY_BLOCKED) && a.dl.blocked[r])) {  // nothing delivered to this receiver
         a.rflags[r] = flags;
-        if (a.out_ann) a.out_ann[r] = 1;
-        return;
-    }
-    if ((a.dl.flags & RAPID_DELIVERY_BLOCKED) && a.dl.blocked[r]) {
-        a.rflags[r] = flags;
+        a.out_h1[r] = 0; a.out_h2[r] = 0; a.out_len[r] = 0;
         if (a.out_ann) a.out_ann[r] = (flags & RF_ANNOUNCED) ? 1 : 0;
         return;
     }

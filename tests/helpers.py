@@ -61,6 +61,8 @@ def compare_batch(rb, orc_world, sim, cluster, cfg, batch_arrays, blocked=None, 
     Returns (oracle out_len, oracle announced)."""
     src, dst, ring, status = batch_arrays
     A = len(dst)
+    if cfg is None:     # the oracle filters against the view's real configuration id (MembershipService.java:653)
+        cfg = orc_world.view.getCurrentConfigurationId()
     cfgs = np.full(A, cfg, np.int64) if cell_cfg is None else np.asarray(cell_cfg, np.int64)
     o_len, o_ann, o_ids, o_off = sim.apply_batch(src, dst, ring, status, cfgs, blocked=blocked, bitmap=bitmap,
                                                  perm_seed=perm_seed, threads=4)

@@ -142,10 +142,10 @@ def test_c1_single_crash(orc, rb, kernel):
     obs, _ = v.tables()
     b = W.c1_single_crash(obs, 50)
     blocked = W.blocked_by_receiver(b.blocked, v.getRing(0), 0, 50)
-    o_len, o_ann = compare_batch(rb, w, sim, cl, 7, (b.src, b.dst, b.ring, b.status), blocked=blocked)
+    o_len, o_ann = compare_batch(rb, w, sim, cl, None, (b.src, b.dst, b.ring, b.status), blocked=blocked)
     assert (o_len[blocked == 0] == 1).all() and (o_len[blocked == 1] == 0).all()
     # a second batch is ignored by everyone who announced (MembershipService.java:318-319)
-    compare_batch(rb, w, sim, cl, 7, (b.src, b.dst, b.ring, b.status), blocked=blocked)
+    compare_batch(rb, w, sim, cl, None, (b.src, b.dst, b.ring, b.status), blocked=blocked)
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -155,7 +155,7 @@ def test_c2_simultaneous_crash(orc, rb, kernel):
     obs, _ = v.tables()
     b = W.c2_simultaneous_crash(obs, n, 0.01)
     blocked = W.blocked_by_receiver(b.blocked, v.getRing(0), 0, n)
-    o_len, _ = compare_batch(rb, w, sim, cl, 11, (b.src, b.dst, b.ring, b.status), blocked=blocked)
+    o_len, _ = compare_batch(rb, w, sim, cl, None, (b.src, b.dst, b.ring, b.status), blocked=blocked)
     live = np.nonzero(blocked == 0)[0]
     assert (o_len[live] == 20).all()
     assert cl.getProposal(int(live[0])) and sorted(cl.getProposal(int(live[0]))) == b.expected_cut.tolist()
@@ -168,7 +168,7 @@ def test_c3_correlated_partition_needs_invalidation(orc, rb, kernel):
     obs, _ = v.tables()
     b = W.c3_correlated_partition(obs, v.getRing(0), n, 0.05)
     blocked = W.blocked_by_receiver(b.blocked, v.getRing(0), 0, n)
-    o_len, _ = compare_batch(rb, w, sim, cl, 3, (b.src, b.dst, b.ring, b.status), blocked=blocked)
+    o_len, _ = compare_batch(rb, w, sim, cl, None, (b.src, b.dst, b.ring, b.status), blocked=blocked)
     live = np.nonzero(blocked == 0)[0]
     assert (o_len[live] == 100).all()          # the whole arc, emitted by invalidateFailingEdges
 
@@ -180,7 +180,7 @@ def test_c5_churn_joins_and_leaves(orc, rb, kernel):
     obs, _ = v.tables()
     b = W.c5_churn(obs, w.joiner_obs(), n, nl, nj)
     blocked = W.blocked_by_receiver(b.blocked, v.getRing(0), 0, n)
-    o_len, _ = compare_batch(rb, w, sim, cl, 99, (b.src, b.dst, b.ring, b.status), blocked=blocked)
+    o_len, _ = compare_batch(rb, w, sim, cl, None, (b.src, b.dst, b.ring, b.status), blocked=blocked)
     live = np.nonzero(blocked == 0)[0]
     assert (o_len[live] == nl + nj).all()
     assert sorted(cl.getProposal(int(live[3]))) == b.expected_cut.tolist()
@@ -194,8 +194,9 @@ def test_filter_rules(orc, rb, kernel):
     rng = np.random.default_rng(5)
     src, dst, ring, status = random_batch(rng, n + nj, K, 12, 150, n)
     status = rng.integers(0, 2, size=len(dst)).astype(np.uint8)          # deliberately inconsistent
-    cell_cfg = np.where(rng.random(len(dst)) < 0.2, 8, 42).astype(np.int64)
-    compare_batch(rb, w, sim, cl, 42, (src, dst, ring, status), cell_cfg=cell_cfg)
+    cfg = w.view.getCurrentConfigurationId()
+    cell_cfg = np.where(rng.random(len(dst)) < 0.2, cfg + 1, cfg).astype(np.int64)
+    compare_batch(rb, w, sim, cl, cfg, (src, dst, ring, status), cell_cfg=cell_cfg)
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -208,10 +209,10 @@ def test_random_multi_batch_streams(orc, rb, kernel, seed):
     rng = np.random.default_rng(100 + seed)
     for _ in range(6):
         src, dst, ring, status = random_batch(rng, n + nj, K, int(rng.integers(1, 9)), int(rng.integers(1, 60)), n)
-        compare_batch(rb, w, sim, cl, 1, (src, dst, ring, status))
+        compare_batch(rb, w, sim, cl, None, (src, dst, ring, status))
     cl.clear(); sim.reset()
     src, dst, ring, status = random_batch(rng, n + nj, K, 3, 40, n)
-    compare_batch(rb, w, sim, cl, 1, (src, dst, ring, status))
+    compare_batch(rb, w, sim, cl, None, (src, dst, ring, status))
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -228,7 +229,7 @@ def test_per_receiver_delivery_bitmap(orc, rb, kernel, seed):
         if seed % 2:
             bitmap |= rng.integers(0, 2**32, size=(len(dst), words), dtype=np.uint64).astype(np.uint32)
         blocked = (rng.random(n) < 0.1).astype(np.uint8)
-        compare_batch(rb, w, sim, cl, 5, (src, dst, ring, status), blocked=blocked, bitmap=bitmap)
+        compare_batch(rb, w, sim, cl, None, (src, dst, ring, status), blocked=blocked, bitmap=bitmap)
 
 
 @pytest.mark.parametrize("seed", range(4))
@@ -239,7 +240,7 @@ def test_per_receiver_permuted_order(orc, rb, seed):
     rng = np.random.default_rng(40 + seed)
     for t in range(4):
         src, dst, ring, status = random_batch(rng, n, K, int(rng.integers(2, 8)), int(rng.integers(10, 80)), n)
-        compare_batch(rb, w, sim, cl, 5, (src, dst, ring, status), perm_seed=W.SEED + 2 + t)
+        compare_batch(rb, w, sim, cl, None, (src, dst, ring, status), perm_seed=W.SEED + 2 + t)
 
 
 def test_c4_flip_flop_stream(orc, rb):
@@ -250,7 +251,7 @@ def test_c4_flip_flop_stream(orc, rb):
     blocked = W.blocked_by_receiver(batches[0].blocked, v.getRing(0), 0, n)
     announced_any = False
     for b in batches:
-        o_len, o_ann = compare_batch(rb, w, sim, cl, 17, (b.src, b.dst, b.ring, b.status), blocked=blocked,
+        o_len, o_ann = compare_batch(rb, w, sim, cl, None, (b.src, b.dst, b.ring, b.status), blocked=blocked,
                                      perm_seed=b.meta["perm_seed"])
         announced_any |= bool(o_ann.any())
     assert announced_any
@@ -267,6 +268,6 @@ def test_num_proposals_sweep(orc, rb):
     w, v, sim, cl = _worlds(orc, rb, n, kernel="sweep", Hh=8, Ll=2)
     rng = np.random.default_rng(3)
     src, dst, ring, status = random_batch(rng, n, K, 3, 60, n)
-    compare_batch(rb, w, sim, cl, 1, (src, dst, ring, status))
+    compare_batch(rb, w, sim, cl, None, (src, dst, ring, status))
     for r in (0, 57, n - 1):
         assert cl.getNumProposals(r) == sim.numProposals(r)
