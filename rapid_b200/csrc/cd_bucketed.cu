@@ -1,7 +1,961 @@
-// placeholder until the subject-bucketed kernels land
+// The subject-bucketed cut-detection kernels (the fast path of rapid_cd_apply_batch on SERVICE handles).
+//
+// Reference semantics: MultiNodeCutDetector.java:84-128 applied per cell in arrival order, then :137-164, driven
+// by MembershipService.java:300-354.  The Java walks the batch once per process and probes a hash map per cell.
+// Here the batch is regrouped BY SUBJECT once (radix sort of the cell indices by subject slot), and every receiver's
+// 16-bit ring mask for a subject is read ONCE, updated in a register and written ONCE:
+//
+//   traffic = 4 bytes x (#subjects in the batch) x (#receivers)          (SURVEY.md §8d "4·S·R")
+//
+// instead of 4 bytes x #cells x #receivers for a per-cell sweep.  What makes that legal is that the sequential
+// rule "emit when updatesInProgress returns to 0" only depends on, per subject, the two moments at which its
+// report count crosses L and H (t_L, t_H): a proposal is emitted at t_H(s) iff no other subject s' has
+// t_L(s') <= t_H(s) < t_H(s') (SURVEY.md §7 "key reformulation").  Each (subject, receiver) visit yields
+// (t_L, t_H); per receiver we keep a handful of order-independent reductions of them and classify:
+//     all pre-proposals resolved  -> everything at >= H is emitted              (EMIT_ALL)
+//     an unresolved one starts before the first H-crossing -> nothing emitted   (NOEMIT)
+//     otherwise                                                                  (MIXED: exact interval analysis
+//                                                                                 for that receiver only)
+// followed by the implicit-invalidation pass over the (few) subjects left in the unstable band.
+//
+// "Moments" are cell indices for uniform delivery and the receiver's own permutation keys for PERMUTED delivery,
+// so a per-receiver order needs no per-receiver sort.
+//
+// Kernels: k_apply_uniform (SWAR: 8 receivers per thread, 128-bit loads/stores, fresh-subject fast path),
+// k_apply_generic (one receiver per thread: bitmap / permuted delivery), k_finalize1, k_resolve_mixed, k_flip,
+// k_inval_pairs, k_finalize2.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+
 #include "cd_internal.cuh"
+
 namespace rapid {
-int32_t bucketed_apply(CD*, int64_t, const DeliveryDev&, const BatchCounts&) { set_error("bucketed kernels not built"); return RAPID_EUNSUPPORTED; }
-void bucketed_destroy(CD*) {}
-int32_t bucketed_clear(CD*) { return RAPID_OK; }
+
+constexpr int TILE_R = 1024;          // receivers per tile (uniform kernel: 128 threads x 8 receivers)
+constexpr int UNI_THREADS = 128;
+constexpr int GEN_THREADS = 256;
+constexpr int STAGE = 32;             // batch subjects staged in shared memory at a time
+constexpr int MAXK = RAPID_MAX_K;
+constexpr uint32_t T32_NONE = 0xFFFFFFFFu;
+constexpr uint64_t T64_NONE = ~0ULL;
+constexpr int MIXED_BLOCKS = 64;
+constexpr uint32_t RF_K3 = 16u;       // receiver enters the invalidation pass of the batch in flight
+constexpr uint32_t RF_ACTIVE = 32u;   // receiver processed the batch in flight
+
+// partial-accumulator flags
+constexpr uint32_t PF_SEEN = 1u;      // a valid DOWN cell was delivered
+constexpr uint32_t PF_NEGINF = 2u;    // a subject already in the unstable band stayed there (its t_L is "before the batch")
+
+struct SubjDesc {                     // 48 bytes, one per subject of the batch
+    int32_t slot;
+    uint16_t bmask;                   // rings reported in this batch
+    uint8_t nr;                       // number of distinct rings
+    uint8_t any_down;
+    uint32_t tLf, tHf;                // for a fresh subject (no earlier reports): moment of the L-th / H-th distinct ring, 0 if none
+    uint32_t seg_begin, seg_len;      // its cells in the slot-sorted arrays
+    uint64_t mix1, mix2;              // fp_mix1 / fp_mix2 of the subject id
+    uint64_t pad_;
+};
+struct SubjWalk {                     // first-occurrence ring sequence in arrival order (uniform delivery)
+    uint8_t ring[16];
+    uint32_t time[16];
+};
+
+struct Partials {                     // [n_chunks][Rpad] structure of arrays
+    uint4* cnt;                       // x = nL | nH << 16, y = touched_pre | nUn << 16, z = flags, w = 0
+    uint64_t* minTH;
+    uint64_t* minTLun;
+    uint64_t* h1;
+    uint64_t* h2;
+};
+
+struct Bucketed {
+    DevBuf<uint32_t> key_in, key_out;
+    DevBuf<int32_t> val_in, val_out;          // val_out = cell indices sorted by slot
+    DevBuf<int32_t> head;                     // head flags -> exclusive scan
+    DevBuf<SubjDesc> desc;
+    DevBuf<SubjWalk> walk;
+    DevBuf<uint8_t> s_ring, s_status;         // per sorted cell
+    DevBuf<uint4> p_cnt;
+    DevBuf<uint64_t> p_minTH, p_minTLun, p_h1, p_h2;
+    DevBuf<int32_t> mixed_list;
+    DevBuf<int32_t> k3_res;
+    DevBuf<unsigned long long> k3_h1, k3_h2;
+    DevBuf<int2> pre_pairs;
+    DevBuf<int32_t> pre_count;
+    DevBuf<int32_t> in_list;                  // [slot][n_tiles]
+    size_t in_list_slots = 0;
+    DevBuf<uint64_t> iv_tL, iv_tH;            // [MIXED_BLOCKS][Sb]
+    DevBuf<uint32_t> iv_fl;
+    int n_tiles = 0;
+    size_t part_cap = 0;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// batch regrouping
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_sort_keys(int64_t A, const int32_t* __restrict__ cell_slot, uint32_t* __restrict__ key, int32_t* __restrict__ val) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    const int32_t s = cell_slot[i];
+    key[i] = s < 0 ? 0xFFFFFFFFu : (uint32_t)s;
+    val[i] = (int32_t)i;
 }
+
+__global__ void k_heads(int32_t n_valid, const uint32_t* __restrict__ key, int32_t* __restrict__ head) {
+    const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_valid) return;
+    head[j] = (j == 0 || key[j] != key[j - 1]) ? 1 : 0;
+}
+
+__global__ void k_scan_i32(int32_t* __restrict__ data, int64_t n) {
+    __shared__ int32_t part[1024];
+    const int T = blockDim.x, t = threadIdx.x;
+    const int64_t per = (n + T - 1) / T;
+    const int64_t b = (int64_t)t * per, e = b + per < n ? b + per : n;
+    int32_t s = 0;
+    for (int64_t i = b; i < e; ++i) s += data[i];
+    part[t] = s;
+    __syncthreads();
+    for (int off = 1; off < T; off <<= 1) {
+        int32_t v = t >= off ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int32_t run = t ? part[t - 1] : 0;
+    for (int64_t i = b; i < e; ++i) { const int32_t v = data[i]; data[i] = run; run += v; }
+}
+
+// one thread per segment head: walk the subject's cells in arrival order
+__global__ void k_build_desc(int32_t n_valid, const uint32_t* __restrict__ key, const int32_t* __restrict__ sidx,
+                             const int32_t* __restrict__ head_excl, const uint8_t* __restrict__ ring,
+                             const uint8_t* __restrict__ status, const int32_t* __restrict__ slot_subject, int L, int H,
+                             SubjDesc* __restrict__ desc, SubjWalk* __restrict__ walk, uint8_t* __restrict__ s_ring,
+                             uint8_t* __restrict__ s_status) {
+    const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_valid) return;
+    const int32_t ci = sidx[j];
+    s_ring[j] = ring[ci];
+    s_status[j] = status[ci];
+    const bool is_head = (j == 0 || key[j] != key[j - 1]);
+    if (!is_head) return;
+    const int32_t b = head_excl[j];
+    SubjDesc d;
+    SubjWalk w;
+    d.slot = (int32_t)key[j];
+    d.bmask = 0; d.nr = 0; d.any_down = 0; d.tLf = 0; d.tHf = 0;
+    d.seg_begin = (uint32_t)j;
+    int32_t e = j;
+    while (e < n_valid && key[e] == key[j]) {
+        const int32_t c = sidx[e];
+        const int k = ring[c];
+        if (status[c] == RAPID_EDGE_DOWN) d.any_down = 1;
+        if (!((d.bmask >> k) & 1)) {
+            d.bmask |= (uint16_t)(1u << k);
+            w.ring[d.nr] = (uint8_t)k;
+            w.time[d.nr] = (uint32_t)c + 1u;           // moments are 1-based cell indices (0 = "before the batch")
+            ++d.nr;
+            if (d.nr == L) d.tLf = (uint32_t)c + 1u;
+            if (d.nr == H) d.tHf = (uint32_t)c + 1u;
+        }
+        ++e;
+    }
+    for (int q = d.nr; q < 16; ++q) { w.ring[q] = 0; w.time[q] = 0; }
+    d.seg_len = (uint32_t)(e - j);
+    d.mix1 = fp_mix1(slot_subject[d.slot]);
+    d.mix2 = fp_mix2(slot_subject[d.slot]);
+    d.pad_ = 0;
+    desc[b] = d;
+    walk[b] = w;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// the (subject, receiver) visit, uniform delivery: old 16-bit state -> crossings and moments
+// ------------------------------------------------------------------------------------------------------------------
+struct Visit {
+    int c0, c1;
+    bool crossL, crossH;
+    uint32_t tL, tH;
+};
+
+__device__ __forceinline__ Visit visit_uniform(uint32_t ur, const SubjDesc& d, const SubjWalk& w, int L, int H) {
+    Visit v;
+    v.tL = 0; v.tH = 0;
+    if (ur == 0) {                                      // fresh subject: the descriptor already knows the answer
+        v.c0 = 0; v.c1 = d.nr;
+        v.tL = d.tLf; v.tH = d.tHf;
+    } else {
+        int c = __popc(ur);
+        v.c0 = c;
+        const int nr = d.nr;
+        for (int q = 0; q < nr; ++q) {
+            const int k = w.ring[q];
+            const bool isnew = !((ur >> k) & 1u);
+            c += isnew;
+            if (isnew && c == L) v.tL = w.time[q];
+            if (isnew && c == H) v.tH = w.time[q];
+        }
+        v.c1 = c;
+    }
+    v.crossL = v.c0 < L && v.c1 >= L;
+    v.crossH = v.c0 < H && v.c1 >= H;
+    return v;
+}
+
+struct Acc {
+    uint32_t nL = 0, nH = 0, tp = 0, nUn = 0, flags = 0;
+    uint32_t minTH = T32_NONE, minTLun = T32_NONE;
+    uint64_t h1 = 0, h2 = 0;
+};
+
+__device__ __forceinline__ bool accumulate(Acc& a, const Visit& v, const SubjDesc& d, int L, int H) {
+    if (v.c0 >= L && v.c0 < H) a.tp++;
+    if (v.crossL) a.nL++;
+    if (v.crossH) { a.nH++; a.minTH = min(a.minTH, v.tH); a.h1 += d.mix1; a.h2 += d.mix2; }
+    if (v.c1 >= L && v.c1 < H) {                        // still in the unstable band after the batch
+        if (v.crossL) { a.nUn++; a.minTLun = min(a.minTLun, v.tL); }
+        else a.flags |= PF_NEGINF;
+        return true;
+    }
+    return false;
+}
+
+struct ApplyArgs {
+    uint16_t* masks;
+    const uint8_t* cur;
+    size_t Rpad;
+    int K, H, L;
+    int64_t R, rbegin;
+    const uint32_t* rflags;
+    DeliveryDev dl;
+    int Sb, chunk;
+    const SubjDesc* desc;
+    const SubjWalk* walk;
+    const int32_t* slot_subject;
+    const int32_t* sidx;          // sorted cell indices
+    const uint8_t* s_ring;
+    const uint8_t* s_status;
+    Partials part;
+    int n_tiles;
+    int32_t* in_list;
+    int2* pre_pairs;
+    int32_t* pre_count;
+    int32_t pre_cap;
+};
+
+__device__ __forceinline__ void note_unresolved(const ApplyArgs& a, int tile, int32_t slot) {
+    int32_t* f = a.in_list + (size_t)slot * a.n_tiles + tile;
+    if (atomicExch(f, 1) == 0) {
+        const int32_t at = atomicAdd(a.pre_count, 1);
+        if (at < a.pre_cap) a.pre_pairs[at] = make_int2(tile, slot);
+    }
+}
+
+// ---- uniform delivery: every active receiver gets every valid cell in array order -------------------------------------
+__global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a) {
+    __shared__ SubjDesc sd[STAGE];
+    __shared__ SubjWalk sw[STAGE];
+    __shared__ const uint16_t* s_src[STAGE];
+    __shared__ uint16_t* s_dst[STAGE];
+    __shared__ int s_unres[STAGE];
+    // per-receiver exception accumulators (receivers whose state differs from their 7 neighbours)
+    __shared__ uint32_t e_nLH[TILE_R], e_tpUn[TILE_R], e_fl[TILE_R], e_minTH[TILE_R], e_minTLun[TILE_R];
+    __shared__ uint64_t e_h1[TILE_R], e_h2[TILE_R];
+
+    const int tile = blockIdx.x, chunk = blockIdx.y, t = threadIdx.x;
+    const int s0 = chunk * a.chunk, s1 = min(a.Sb, s0 + a.chunk);
+    const int64_t r0 = (int64_t)tile * TILE_R + (int64_t)t * 8;
+    const uint32_t RM = (1u << a.K) - 1u;
+    const int L = a.L, H = a.H;
+
+    uint32_t act = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int64_t r = r0 + j;
+        if (r < a.R) {
+            const bool on = !(a.rflags[r] & RF_ANNOUNCED) && !((a.dl.flags & RAPID_DELIVERY_BLOCKED) && a.dl.blocked[r]);
+            act |= (on ? 1u : 0u) << j;
+        }
+        const int li = t * 8 + j;
+        e_nLH[li] = 0; e_tpUn[li] = 0; e_fl[li] = 0; e_minTH[li] = T32_NONE; e_minTLun[li] = T32_NONE; e_h1[li] = 0; e_h2[li] = 0;
+    }
+    Acc com;                                              // applies to all 8 receivers of this thread (act == 0xFF only)
+
+    for (int base = s0; base < s1; base += STAGE) {
+        const int n = min(STAGE, s1 - base);
+        __syncthreads();
+        if (t < n) {
+            const SubjDesc d = a.desc[base + t];
+            sd[t] = d;
+            sw[t] = a.walk[base + t];
+            const uint8_t c = a.cur[d.slot];
+            s_src[t] = a.masks + ((size_t)d.slot * 2 + c) * a.Rpad;
+            s_dst[t] = a.masks + ((size_t)d.slot * 2 + (c ^ 1)) * a.Rpad;
+            s_unres[t] = 0;
+        }
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += 4) {
+            uint4 W[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u < n) W[u] = *reinterpret_cast<const uint4*>(s_src[i0 + u] + r0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u;
+                if (i >= n) break;
+                const SubjDesc& d = sd[i];
+                uint4 w = W[u];
+                bool unres = false;
+                const bool uniform = act == 0xFFu && w.x == w.y && w.y == w.z && w.z == w.w && (w.x >> 16) == (w.x & 0xFFFFu);
+                if (uniform) {
+                    const uint32_t st = w.x & 0xFFFFu;
+                    const Visit v = visit_uniform(st & RM, d, sw[i], L, H);
+                    unres = accumulate(com, v, d, L, H);
+                    const uint32_t nw = (st | d.bmask) * 0x10001u;
+                    w = make_uint4(nw, nw, nw, nw);
+                } else if (act) {
+                    uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (!((act >> j) & 1u)) continue;
+                        const uint32_t st = (words[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+                        const Visit v = visit_uniform(st & RM, d, sw[i], L, H);
+                        Acc ex;
+                        const bool un = accumulate(ex, v, d, L, H);
+                        unres |= un;
+                        const int li = t * 8 + j;
+                        e_nLH[li] += ex.nL | (ex.nH << 16);
+                        e_tpUn[li] += ex.tp | (ex.nUn << 16);
+                        e_fl[li] |= ex.flags;
+                        e_minTH[li] = min(e_minTH[li], ex.minTH);
+                        e_minTLun[li] = min(e_minTLun[li], ex.minTLun);
+                        e_h1[li] += ex.h1; e_h2[li] += ex.h2;
+                        words[j >> 1] |= (uint32_t)d.bmask << ((j & 1) * 16);
+                    }
+                    w = make_uint4(words[0], words[1], words[2], words[3]);
+                }
+                *reinterpret_cast<uint4*>(s_dst[i] + r0) = w;       // the non-current row becomes the new state
+                if (__any_sync(0xffffffffu, unres) && (t & 31) == 0) s_unres[i] = 1;
+            }
+        }
+        __syncthreads();
+        if (t < n && s_unres[t]) note_unresolved(a, tile, sd[t].slot);
+    }
+    // partials for this (chunk, tile)
+    const size_t pbase = (size_t)chunk * a.Rpad + (size_t)r0;
+    const bool use_com = act == 0xFFu;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int li = t * 8 + j;
+        uint32_t nLH = e_nLH[li], tpUn = e_tpUn[li], fl = e_fl[li], mTH = e_minTH[li], mTL = e_minTLun[li];
+        uint64_t h1 = e_h1[li], h2 = e_h2[li];
+        if (use_com) {
+            nLH += com.nL | (com.nH << 16); tpUn += com.tp | (com.nUn << 16); fl |= com.flags;
+            mTH = min(mTH, com.minTH); mTL = min(mTL, com.minTLun); h1 += com.h1; h2 += com.h2;
+        }
+        a.part.cnt[pbase + j] = make_uint4(nLH, tpUn, fl, 0u);
+        a.part.minTH[pbase + j] = mTH == T32_NONE ? T64_NONE : (uint64_t)mTH;
+        a.part.minTLun[pbase + j] = mTL == T32_NONE ? T64_NONE : (uint64_t)mTL;
+        a.part.h1[pbase + j] = h1;
+        a.part.h2[pbase + j] = h2;
+    }
+}
+
+// ---- generic delivery (per-receiver subset and/or per-receiver order): one receiver per thread -------------------
+struct GVisit {
+    int c0, c1;
+    bool crossL, crossH, seen_down;
+    uint64_t tL, tH;
+    uint32_t have;        // rings delivered to this receiver in this batch
+};
+
+// moments of a subject's cells as seen by one receiver; `rs` is the receiver's permutation seed
+__device__ __forceinline__ GVisit visit_generic(uint32_t ur, const SubjDesc& d, const int32_t* __restrict__ sidx,
+                                                const uint8_t* __restrict__ s_ring, const uint8_t* __restrict__ s_status,
+                                                const DeliveryDev& dl, int64_t r, uint64_t rs, int L, int H) {
+    uint64_t tmin[MAXK];
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k) tmin[k] = 0;
+    GVisit v;
+    v.have = 0; v.seen_down = false; v.tL = 0; v.tH = 0;
+    const bool has_bitmap = dl.flags & RAPID_DELIVERY_BITMAP, permuted = dl.flags & RAPID_DELIVERY_PERMUTED;
+    const uint32_t e = d.seg_begin + d.seg_len;
+    for (uint32_t j = d.seg_begin; j < e; ++j) {
+        const int32_t ci = sidx[j];
+        if (has_bitmap && !((dl.bitmap[(size_t)ci * dl.words + (r >> 5)] >> (r & 31)) & 1u)) continue;
+        if (s_status[j] == RAPID_EDGE_DOWN) v.seen_down = true;
+        const int k = s_ring[j];
+        const uint64_t tm = permuted ? splitmix64(rs ^ (uint64_t)ci) : (uint64_t)ci + 1ull;
+        const bool had = (v.have >> k) & 1u;
+#pragma unroll
+        for (int kk = 0; kk < MAXK; ++kk)
+            if (kk == k && (!had || tm < tmin[kk])) tmin[kk] = tm;
+        v.have |= 1u << k;
+    }
+    const uint32_t fresh = v.have & ~ur;
+    v.c0 = __popc(ur);
+    v.c1 = v.c0 + __popc(fresh);
+    v.crossL = v.c0 < L && v.c1 >= L;
+    v.crossH = v.c0 < H && v.c1 >= H;
+    if (v.crossL || v.crossH) {
+        const int wantL = L - v.c0 - 1, wantH = H - v.c0 - 1;       // rank (0-based) among the new rings' first moments
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) {
+            if (!((fresh >> k) & 1u)) continue;
+            int rank = 0;
+#pragma unroll
+            for (int q = 0; q < MAXK; ++q) rank += (((fresh >> q) & 1u) && tmin[q] < tmin[k]) ? 1 : 0;
+            if (rank == wantL) v.tL = tmin[k];
+            if (rank == wantH) v.tH = tmin[k];
+        }
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(GEN_THREADS) k_apply_generic(const ApplyArgs a) {
+    __shared__ SubjDesc sd[STAGE];
+    __shared__ const uint16_t* s_src[STAGE];
+    __shared__ uint16_t* s_dst[STAGE];
+    __shared__ int s_unres[STAGE];
+    const int t = threadIdx.x, chunk = blockIdx.y;
+    const int64_t r = (int64_t)blockIdx.x * GEN_THREADS + t;
+    const int tile = (int)(((int64_t)blockIdx.x * GEN_THREADS) / TILE_R);
+    const int s0 = chunk * a.chunk, s1 = min(a.Sb, s0 + a.chunk);
+    const uint32_t RM = (1u << a.K) - 1u;
+    const int L = a.L, H = a.H;
+    const bool in_range = r < a.R;
+    const bool active = in_range && !(a.rflags[r] & RF_ANNOUNCED) && !((a.dl.flags & RAPID_DELIVERY_BLOCKED) && a.dl.blocked[r]);
+    const uint64_t rs = splitmix64(a.dl.perm_seed + (uint64_t)(a.rbegin + r));
+    uint32_t nL = 0, nH = 0, tp = 0, nUn = 0, fl = 0;
+    uint64_t minTH = T64_NONE, minTLun = T64_NONE, h1 = 0, h2 = 0;
+    bool haveTH = false, haveTL = false;
+    for (int base = s0; base < s1; base += STAGE) {
+        const int n = min(STAGE, s1 - base);
+        __syncthreads();
+        if (t < n) {
+            const SubjDesc d = a.desc[base + t];
+            sd[t] = d;
+            const uint8_t c = a.cur[d.slot];
+            s_src[t] = a.masks + ((size_t)d.slot * 2 + c) * a.Rpad;
+            s_dst[t] = a.masks + ((size_t)d.slot * 2 + (c ^ 1)) * a.Rpad;
+            s_unres[t] = 0;
+        }
+        __syncthreads();
+        for (int i = 0; i < n; ++i) {
+            const SubjDesc& d = sd[i];
+            bool unres = false;
+            if (r < (int64_t)a.Rpad) {
+                uint32_t st = s_src[i][r];
+                if (active) {
+                    const GVisit v = visit_generic(st & RM, d, a.sidx, a.s_ring, a.s_status, a.dl, r, rs, L, H);
+                    if (v.seen_down) fl |= PF_SEEN;
+                    if (v.c0 >= L && v.c0 < H) tp++;
+                    if (v.crossL) nL++;
+                    if (v.crossH) {
+                        nH++;
+                        if (!haveTH || v.tH < minTH) { minTH = v.tH; haveTH = true; }
+                        h1 += d.mix1; h2 += d.mix2;
+                    }
+                    if (v.c1 >= L && v.c1 < H) {
+                        unres = true;
+                        if (v.crossL) { nUn++; if (!haveTL || v.tL < minTLun) { minTLun = v.tL; haveTL = true; } }
+                        else fl |= PF_NEGINF;
+                    }
+                    st |= v.have;
+                }
+                s_dst[i][r] = (uint16_t)st;
+            }
+            if (__any_sync(0xffffffffu, unres) && (t & 31) == 0) s_unres[i] = 1;
+        }
+        __syncthreads();
+        if (t < n && s_unres[t]) note_unresolved(a, tile, sd[t].slot);   // a 256-receiver block lies inside one tile
+    }
+    if (r < (int64_t)a.Rpad) {
+        const size_t p = (size_t)chunk * a.Rpad + (size_t)r;
+        a.part.cnt[p] = make_uint4(nL | (nH << 16), tp | (nUn << 16), fl, 0u);
+        a.part.minTH[p] = minTH;
+        a.part.minTLun[p] = minTLun;
+        a.part.h1[p] = h1;
+        a.part.h2[p] = h2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// finalize 1: combine the chunk partials of every receiver, classify, keep the scalars
+// ------------------------------------------------------------------------------------------------------------------
+struct FinArgs {
+    int64_t R;
+    size_t Rpad;
+    int n_chunks;
+    Partials part;
+    DeliveryDev dl;
+    int any_down_uniform;        // uniform delivery: the batch holds a valid DOWN cell
+    int uniform;
+    int32_t* n_pre;
+    uint32_t* rflags;
+    uint64_t* pend_h1;
+    uint64_t* pend_h2;
+    int32_t* pend_cnt;
+    uint64_t* out_h1;
+    uint64_t* out_h2;
+    int32_t* out_len;
+    int32_t* mixed_list;
+    BatchCounts* bc;
+};
+
+__global__ void k_finalize1(const FinArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    uint32_t flags = a.rflags[r] & ~(RF_ANN_NOW | RF_K3 | RF_ACTIVE);
+    a.out_h1[r] = 0; a.out_h2[r] = 0; a.out_len[r] = 0;
+    const bool active = !(flags & RF_ANNOUNCED) && !((a.dl.flags & RAPID_DELIVERY_BLOCKED) && a.dl.blocked[r]);
+    if (!active) { a.rflags[r] = flags; return; }
+    flags |= RF_ACTIVE;
+    uint32_t nL = 0, nH = 0, tp = 0, nUn = 0, fl = 0;
+    uint64_t minTH = T64_NONE, minTLun = T64_NONE, h1 = 0, h2 = 0;
+    bool haveTH = false, haveTL = false;
+    for (int c = 0; c < a.n_chunks; ++c) {
+        const size_t p = (size_t)c * a.Rpad + (size_t)r;
+        const uint4 q = a.part.cnt[p];
+        const uint32_t cH = q.x >> 16, cUn = q.y >> 16;
+        nL += q.x & 0xFFFFu; nH += cH; tp += q.y & 0xFFFFu; nUn += cUn; fl |= q.z;
+        if (cH) { const uint64_t v = a.part.minTH[p]; if (!haveTH || v < minTH) { minTH = v; haveTH = true; } }
+        if (cUn) { const uint64_t v = a.part.minTLun[p]; if (!haveTL || v < minTLun) { minTLun = v; haveTL = true; } }
+        h1 += a.part.h1[p]; h2 += a.part.h2[p];
+    }
+    if (a.uniform ? a.any_down_uniform : (fl & PF_SEEN)) flags |= RF_SEEN_DOWN;
+    const int32_t npre_old = a.n_pre[r];
+    const int32_t npre_new = npre_old + (int32_t)nL - (int32_t)nH;
+    uint64_t ph1 = a.pend_h1[r] + h1, ph2 = a.pend_h2[r] + h2;
+    int32_t pc = a.pend_cnt[r] + (int32_t)nH;
+    const int32_t untouched_pre = npre_old - (int32_t)tp;
+    if (nH > 0 && npre_new == 0) {
+        // EMIT_ALL: the last H-crossing of the batch leaves updatesInProgress == 0, so every subject at >= H has
+        // left in some proposal of this batch (MultiNodeCutDetector.java:110-121); the union is what is announced.
+        a.out_h1[r] = ph1; a.out_h2[r] = ph2; a.out_len[r] = pc;
+        ph1 = 0; ph2 = 0; pc = 0;
+        flags |= RF_ANNOUNCED | RF_ANN_NOW | RF_RULE_GE_H;
+    } else if (nH > 0 && !(untouched_pre > 0 || (fl & PF_NEGINF) || (haveTL && minTLun < minTH))) {
+        // MIXED: some proposals may have been emitted before the unresolved subjects entered the band
+        const int32_t at = atomicAdd(&a.bc->n_mixed, 1);
+        a.mixed_list[at] = (int32_t)r;
+    }
+    if (npre_new > 0 && (flags & RF_SEEN_DOWN)) flags |= RF_K3;
+    a.n_pre[r] = npre_new;
+    a.pend_h1[r] = ph1; a.pend_h2[r] = ph2; a.pend_cnt[r] = pc;
+    a.rflags[r] = flags;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// MIXED receivers: exact interval analysis (one block per receiver)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t IV_HAS = 1u, IV_NEGINF = 2u, IV_FINITE = 4u, IV_CARRIED = 8u;
+
+struct MixArgs {
+    ApplyArgs ap;
+    int32_t S;
+    const int32_t* touch;
+    int32_t serial;
+    const int32_t* mixed_list;
+    const BatchCounts* bc;
+    uint64_t* iv_tL;
+    uint64_t* iv_tH;
+    uint32_t* iv_fl;
+    uint32_t* rflags;
+    uint64_t* pend_h1;
+    uint64_t* pend_h2;
+    int32_t* pend_cnt;
+    uint64_t* out_h1;
+    uint64_t* out_h2;
+    int32_t* out_len;
+};
+
+__device__ __forceinline__ uint64_t block_min_u64(uint64_t v, uint64_t* sm) {
+    for (int o = 16; o > 0; o >>= 1) { const uint64_t x = __shfl_down_sync(0xffffffffu, v, o); v = x < v ? x : v; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint64_t m = sm[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = sm[w] < m ? sm[w] : m;
+    return m;
+}
+
+__global__ void __launch_bounds__(256) k_resolve_mixed(const MixArgs m) {
+    __shared__ uint64_t red[8];
+    __shared__ unsigned long long s_h1, s_h2;
+    __shared__ int s_cnt;
+    const ApplyArgs& a = m.ap;
+    const uint32_t RM = (1u << a.K) - 1u;
+    const int L = a.L, H = a.H, t = threadIdx.x;
+    const int n_mixed = m.bc->n_mixed;
+    uint64_t* tLs = m.iv_tL + (size_t)blockIdx.x * a.Sb;
+    uint64_t* tHs = m.iv_tH + (size_t)blockIdx.x * a.Sb;
+    uint32_t* fls = m.iv_fl + (size_t)blockIdx.x * a.Sb;
+    for (int mi = blockIdx.x; mi < n_mixed; mi += gridDim.x) {
+        const int64_t r = m.mixed_list[mi];
+        const uint64_t rs = splitmix64(a.dl.perm_seed + (uint64_t)(a.rbegin + r));
+        // intervals [tL, tH) of the batch's subjects, recomputed from the OLD rows
+        uint64_t tinf = T64_NONE;          // earliest start of an interval that never closes
+        bool inf_neg = false;
+        for (int b = t; b < a.Sb; b += blockDim.x) {
+            const SubjDesc d = a.desc[b];
+            const uint32_t st = (a.masks + ((size_t)d.slot * 2 + a.cur[d.slot]) * a.Rpad)[r];
+            const GVisit v = visit_generic(st & RM, d, a.sidx, a.s_ring, a.s_status, a.dl, r, rs, L, H);
+            uint32_t f = 0;
+            const bool starts_in = v.c0 >= L && v.c0 < H;
+            if (starts_in || v.crossL) {
+                f |= IV_HAS;
+                if (starts_in) f |= IV_NEGINF;
+                if (v.crossH) f |= IV_FINITE;
+            } else if (v.crossH) f |= IV_HAS | IV_FINITE;          // (L == H cannot reach here: band is empty)
+            if (v.c0 >= H && !(st & CD_BIT_EMIT)) f |= IV_CARRIED;
+            tLs[b] = v.tL; tHs[b] = v.tH; fls[b] = f;
+            if ((f & IV_HAS) && !(f & IV_FINITE)) {
+                if (f & IV_NEGINF) inf_neg = true; else tinf = v.tL < tinf ? v.tL : tinf;
+            }
+        }
+        __syncthreads();
+        int any_neg = __syncthreads_or(inf_neg ? 1 : 0);
+        uint64_t aa = block_min_u64(tinf, red);
+        bool emit = !any_neg;
+        // grow the never-closing component leftwards until nothing that closes after `aa` starts before it
+        while (emit) {
+            uint64_t cand = aa;
+            bool neg = false;
+            for (int b = t; b < a.Sb; b += blockDim.x) {
+                const uint32_t f = fls[b];
+                if (!(f & IV_HAS) || !(f & IV_FINITE)) continue;
+                if (tHs[b] > aa) { if (f & IV_NEGINF) neg = true; else cand = tLs[b] < cand ? tLs[b] : cand; }
+            }
+            any_neg = __syncthreads_or(neg ? 1 : 0);
+            if (any_neg) { emit = false; break; }
+            const uint64_t na = block_min_u64(cand, red);
+            if (na == aa) break;
+            aa = na;
+        }
+        // e* = latest closing moment before the component; everything closed by then was emitted
+        uint64_t estar = 0;
+        bool have_e = false;
+        if (emit) {
+            uint64_t best = 0; bool hb = false;
+            for (int b = t; b < a.Sb; b += blockDim.x) {
+                const uint32_t f = fls[b];
+                if ((f & IV_HAS) && (f & IV_FINITE) && tHs[b] < aa && (!hb || tHs[b] > best)) { best = tHs[b]; hb = true; }
+            }
+            // block max via min of complement
+            const uint64_t mm = block_min_u64(hb ? ~best : T64_NONE, red);
+            int anyb = __syncthreads_or(hb ? 1 : 0);
+            have_e = anyb != 0;
+            estar = ~mm;
+        }
+        if (t == 0) { s_h1 = 0; s_h2 = 0; s_cnt = 0; }
+        __syncthreads();
+        if (have_e) {
+            unsigned long long h1 = 0, h2 = 0; int cnt = 0;
+            for (int b = t; b < a.Sb; b += blockDim.x) {
+                const uint32_t f = fls[b];
+                const bool em = ((f & IV_HAS) && (f & IV_FINITE) && tHs[b] <= estar) || (f & IV_CARRIED);
+                if (em) {
+                    const SubjDesc d = a.desc[b];
+                    uint16_t* p = a.masks + ((size_t)d.slot * 2 + (a.cur[d.slot] ^ 1)) * a.Rpad + r;   // the new row
+                    *p = (uint16_t)(*p | CD_BIT_EMIT);
+                    const int32_t id = a.slot_subject[d.slot];
+                    h1 += fp_mix1(id); h2 += fp_mix2(id); ++cnt;
+                }
+            }
+            // subjects at >= H from earlier batches that this batch did not touch leave with the first proposal too
+            for (int32_t s = t; s < m.S; s += blockDim.x) {
+                if (m.touch[s] == m.serial) continue;
+                uint16_t* p = a.masks + ((size_t)s * 2 + a.cur[s]) * a.Rpad + r;
+                const uint32_t w = *p;
+                if (!(w & CD_BIT_EMIT) && __popc(w & RM) >= H) {
+                    *p = (uint16_t)(w | CD_BIT_EMIT);
+                    const int32_t id = a.slot_subject[s];
+                    h1 += fp_mix1(id); h2 += fp_mix2(id); ++cnt;
+                }
+            }
+            atomicAdd(&s_h1, h1); atomicAdd(&s_h2, h2); atomicAdd(&s_cnt, cnt);
+        }
+        __syncthreads();
+        if (t == 0 && have_e) {
+            m.out_h1[r] = s_h1; m.out_h2[r] = s_h2; m.out_len[r] = s_cnt;
+            m.pend_h1[r] -= s_h1; m.pend_h2[r] -= s_h2; m.pend_cnt[r] -= s_cnt;
+            m.rflags[r] = (m.rflags[r] | RF_ANNOUNCED | RF_ANN_NOW) & ~RF_RULE_GE_H;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_flip(int Sb, const SubjDesc* __restrict__ desc, uint8_t* __restrict__ cur) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < Sb) cur[desc[b].slot] ^= 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// invalidateFailingEdges (MultiNodeCutDetector.java:137-164) over the (tile, subject) pairs known to hold an
+// unstable subject: implicit reports from observers that are themselves in proposal U preProposal.
+// ------------------------------------------------------------------------------------------------------------------
+struct InvArgs {
+    uint16_t* masks;
+    const uint8_t* cur;
+    size_t Rpad;
+    int K, H, L;
+    int64_t R;
+    const uint32_t* rflags;
+    const int2* pre_pairs;
+    const int32_t* pre_count;
+    int32_t pre_cap;
+    const int32_t* slot_subject;
+    const int32_t* slot_of;
+    const int32_t* obs;
+    int32_t* k3_res;
+    unsigned long long* k3_h1;
+    unsigned long long* k3_h2;
+};
+
+__global__ void __launch_bounds__(256) k_inval_pairs(const InvArgs a) {
+    __shared__ int32_t so[MAXK];
+    const uint32_t RM = (1u << a.K) - 1u;
+    const int n = min(*a.pre_count, a.pre_cap);
+    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+        const int2 pr = a.pre_pairs[e];
+        const int32_t slot = pr.y, subject = a.slot_subject[slot];
+        __syncthreads();
+        if (threadIdx.x < a.K) {
+            const int32_t o = a.obs[(size_t)subject * a.K + threadIdx.x];
+            so[threadIdx.x] = o < 0 ? -1 : a.slot_of[o];
+        }
+        __syncthreads();
+        uint16_t* row = a.masks + ((size_t)slot * 2 + a.cur[slot]) * a.Rpad;
+        for (int q = 0; q < TILE_R / 256; ++q) {
+            const int64_t r = (int64_t)pr.x * TILE_R + q * 256 + threadIdx.x;
+            if (r >= a.R || !(a.rflags[r] & RF_K3)) continue;
+            const uint32_t w = row[r];
+            const int c = __popc(w & RM);
+            if (c < a.L || c >= a.H) continue;                      // not in this receiver's preProposal
+            uint32_t implicit = 0;
+            for (int k = 0; k < a.K; ++k) {
+                if ((w >> k) & 1u) continue;
+                const int32_t s2 = so[k];
+                if (s2 < 0) continue;
+                const uint32_t wo = (a.masks + ((size_t)s2 * 2 + a.cur[s2]) * a.Rpad)[r];
+                if (!(wo & CD_BIT_EMIT) && __popc(wo & RM) >= a.L) implicit |= 1u << k;   // observer in proposal U preProposal
+            }
+            if (!implicit) continue;
+            const uint32_t nw = w | implicit;
+            row[r] = (uint16_t)nw;
+            if (__popc(nw & RM) >= a.H) {                            // moved preProposal -> proposal
+                atomicAdd(&a.k3_res[r], 1);
+                atomicAdd(&a.k3_h1[r], (unsigned long long)fp_mix1(subject));
+                atomicAdd(&a.k3_h2[r], (unsigned long long)fp_mix2(subject));
+            }
+        }
+    }
+}
+
+struct Fin2Args {
+    int64_t R;
+    int32_t* n_pre;
+    uint32_t* rflags;
+    uint64_t* pend_h1;
+    uint64_t* pend_h2;
+    int32_t* pend_cnt;
+    uint64_t* out_h1;
+    uint64_t* out_h2;
+    int32_t* out_len;
+    uint8_t* out_ann;
+    int32_t* k3_res;
+    unsigned long long* k3_h1;
+    unsigned long long* k3_h2;
+};
+
+__global__ void k_finalize2(const Fin2Args a) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    uint32_t flags = a.rflags[r];
+    if (flags & RF_K3) {
+        const int32_t res = a.k3_res[r];
+        if (res > 0) {
+            const int32_t npre = a.n_pre[r] - res;
+            uint64_t ph1 = a.pend_h1[r] + a.k3_h1[r], ph2 = a.pend_h2[r] + a.k3_h2[r];
+            int32_t pc = a.pend_cnt[r] + res;
+            if (npre == 0) {
+                // the last unstable subject resolved inside invalidateFailingEdges: proposal (all of it) is emitted
+                a.out_h1[r] += ph1; a.out_h2[r] += ph2; a.out_len[r] += pc;
+                ph1 = 0; ph2 = 0; pc = 0;
+                flags |= RF_ANNOUNCED | RF_ANN_NOW | RF_RULE_GE_H;
+            }
+            a.n_pre[r] = npre;
+            a.pend_h1[r] = ph1; a.pend_h2[r] = ph2; a.pend_cnt[r] = pc;
+            a.k3_res[r] = 0; a.k3_h1[r] = 0; a.k3_h2[r] = 0;
+        }
+    }
+    flags &= ~RF_K3;
+    a.rflags[r] = flags;
+    a.out_ann[r] = (flags & RF_ANNOUNCED) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------------------------
+static Bucketed* state(CD* cd) {
+    if (!cd->bucketed_state) cd->bucketed_state = new Bucketed();
+    return static_cast<Bucketed*>(cd->bucketed_state);
+}
+
+void bucketed_destroy(CD* cd) {
+    if (cd->bucketed_state) { delete static_cast<Bucketed*>(cd->bucketed_state); cd->bucketed_state = nullptr; }
+}
+
+int32_t bucketed_clear(CD* cd) {
+    if (!cd->bucketed) return RAPID_OK;
+    Bucketed* b = state(cd);
+    b->n_tiles = (int)(cd->Rpad / TILE_R);
+    RAPID_CHECK(b->pre_count.reserve(1));
+    RAPID_CUDA(cudaMemsetAsync(b->pre_count.p, 0, sizeof(int32_t), cd->stream));
+    if (b->in_list.p && b->in_list_slots)
+        RAPID_CUDA(cudaMemsetAsync(b->in_list.p, 0, b->in_list_slots * (size_t)b->n_tiles * sizeof(int32_t), cd->stream));
+    RAPID_CHECK(b->k3_res.reserve(cd->Rpad));
+    RAPID_CHECK(b->k3_h1.reserve(cd->Rpad));
+    RAPID_CHECK(b->k3_h2.reserve(cd->Rpad));
+    RAPID_CUDA(cudaMemsetAsync(b->k3_res.p, 0, cd->Rpad * sizeof(int32_t), cd->stream));
+    RAPID_CUDA(cudaMemsetAsync(b->k3_h1.p, 0, cd->Rpad * sizeof(unsigned long long), cd->stream));
+    RAPID_CUDA(cudaMemsetAsync(b->k3_h2.p, 0, cd->Rpad * sizeof(unsigned long long), cd->stream));
+    return RAPID_OK;
+}
+
+static int32_t ensure_pre_capacity(CD* cd, Bucketed* b) {
+    const size_t slots = cd->S_cap;
+    if (slots <= b->in_list_slots) return RAPID_OK;
+    const size_t n_old = b->in_list_slots * (size_t)b->n_tiles, n_new = slots * (size_t)b->n_tiles;
+    DevBuf<int32_t> nl;
+    RAPID_CHECK(nl.reserve(n_new));
+    RAPID_CUDA(cudaMemsetAsync(nl.p, 0, n_new * sizeof(int32_t), cd->stream));
+    if (n_old) RAPID_CUDA(cudaMemcpyAsync(nl.p, b->in_list.p, n_old * sizeof(int32_t), cudaMemcpyDeviceToDevice, cd->stream));
+    DevBuf<int2> np;
+    RAPID_CHECK(np.reserve(n_new));
+    if (n_old) RAPID_CUDA(cudaMemcpyAsync(np.p, b->pre_pairs.p, n_old * sizeof(int2), cudaMemcpyDeviceToDevice, cd->stream));
+    RAPID_CUDA(cudaStreamSynchronize(cd->stream));
+    std::swap(b->in_list.p, nl.p); std::swap(b->in_list.cap, nl.cap);
+    std::swap(b->pre_pairs.p, np.p); std::swap(b->pre_pairs.cap, np.cap);
+    b->in_list_slots = slots;
+    return RAPID_OK;
+}
+
+int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCounts& bc) {
+    Bucketed* b = state(cd);
+    cudaStream_t s = cd->stream;
+    const int TB = 256;
+    const int Sb = bc.n_batch_subj;
+    const int32_t n_valid = bc.n_valid;
+    const bool uniform = !(dl.flags & (RAPID_DELIVERY_BITMAP | RAPID_DELIVERY_PERMUTED));
+    b->n_tiles = (int)(cd->Rpad / TILE_R);
+    RAPID_CHECK(ensure_pre_capacity(cd, b));
+
+    int n_chunks = 1, chunk = std::max(Sb, 1);
+    if (Sb > 0) {
+        // ---- regroup the batch by subject ---------------------------------------------------------------------------
+        RAPID_CHECK(b->key_in.reserve((size_t)A)); RAPID_CHECK(b->key_out.reserve((size_t)A));
+        RAPID_CHECK(b->val_in.reserve((size_t)A)); RAPID_CHECK(b->val_out.reserve((size_t)A));
+        RAPID_CHECK(b->head.reserve((size_t)A));
+        RAPID_CHECK(b->s_ring.reserve((size_t)A)); RAPID_CHECK(b->s_status.reserve((size_t)A));
+        RAPID_CHECK(b->desc.reserve((size_t)Sb)); RAPID_CHECK(b->walk.reserve((size_t)Sb));
+        const unsigned ga = (unsigned)ceil_div<int64_t>(A, TB);
+        k_sort_keys<<<ga, TB, 0, s>>>(A, cd->cell_slot.p, b->key_in.p, b->val_in.p);
+        size_t tmp_bytes = 0;
+        RAPID_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, b->key_in.p, b->key_out.p, b->val_in.p, b->val_out.p, (int)A, 0, 32, s));
+        RAPID_CHECK(cd->cub_tmp.reserve(std::max<size_t>(tmp_bytes, 1)));
+        RAPID_CUDA(cub::DeviceRadixSort::SortPairs(cd->cub_tmp.p, tmp_bytes, b->key_in.p, b->key_out.p, b->val_in.p, b->val_out.p, (int)A, 0, 32, s));
+        const unsigned gv = (unsigned)ceil_div<int32_t>(n_valid, TB);
+        k_heads<<<gv, TB, 0, s>>>(n_valid, b->key_out.p, b->head.p);
+        k_scan_i32<<<1, 1024, 0, s>>>(b->head.p, n_valid);
+        k_build_desc<<<gv, TB, 0, s>>>(n_valid, b->key_out.p, b->val_out.p, b->head.p, cd->cur_ring_dev, cd->cur_status_dev,
+                                       cd->slot_subject.p, cd->L, cd->H, b->desc.p, b->walk.p, b->s_ring.p, b->s_status.p);
+        RAPID_KERNEL_CHECK();
+        cd->last_launches += 6;   // sort keys, radix sort (counted once), heads, scan, descriptors
+        // ---- grid: tiles x subject chunks, a few waves of 148 SMs -----------------------------------------------------
+        const int rblocks = uniform ? b->n_tiles : (int)(cd->Rpad / GEN_THREADS);
+        const int target = 148 * 8;
+        n_chunks = std::max(1, std::min(Sb, ceil_div(target, rblocks)));
+        chunk = ceil_div(Sb, n_chunks);
+        n_chunks = ceil_div(Sb, chunk);
+    }
+    const size_t pn = (size_t)n_chunks * cd->Rpad;
+    RAPID_CHECK(b->p_cnt.reserve(pn)); RAPID_CHECK(b->p_minTH.reserve(pn)); RAPID_CHECK(b->p_minTLun.reserve(pn));
+    RAPID_CHECK(b->p_h1.reserve(pn)); RAPID_CHECK(b->p_h2.reserve(pn));
+    RAPID_CHECK(b->mixed_list.reserve(cd->Rpad));
+    Partials part{b->p_cnt.p, b->p_minTH.p, b->p_minTLun.p, b->p_h1.p, b->p_h2.p};
+
+    ApplyArgs ap;
+    ap.masks = cd->masks.p; ap.cur = cd->cur.p; ap.Rpad = cd->Rpad;
+    ap.K = cd->K; ap.H = cd->H; ap.L = cd->L; ap.R = cd->R; ap.rbegin = cd->rbegin;
+    ap.rflags = cd->rflags.p; ap.dl = dl; ap.Sb = Sb; ap.chunk = chunk;
+    ap.desc = b->desc.p; ap.walk = b->walk.p; ap.slot_subject = cd->slot_subject.p;
+    ap.sidx = b->val_out.p; ap.s_ring = b->s_ring.p; ap.s_status = b->s_status.p;
+    ap.part = part; ap.n_tiles = b->n_tiles; ap.in_list = b->in_list.p; ap.pre_pairs = b->pre_pairs.p;
+    ap.pre_count = b->pre_count.p; ap.pre_cap = (int32_t)std::min<size_t>(b->in_list_slots * (size_t)b->n_tiles, 0x7fffffff);
+
+    RAPID_CUDA(cudaEventRecord(cd->evk0, s));
+    if (Sb > 0) {
+        if (uniform) {
+            dim3 grid((unsigned)b->n_tiles, (unsigned)n_chunks);
+            k_apply_uniform<<<grid, UNI_THREADS, 0, s>>>(ap);
+            cd->last_path = 2;
+        } else {
+            dim3 grid((unsigned)(cd->Rpad / GEN_THREADS), (unsigned)n_chunks);
+            k_apply_generic<<<grid, GEN_THREADS, 0, s>>>(ap);
+            cd->last_path = 3;
+        }
+        RAPID_KERNEL_CHECK();
+        cd->last_launches += 1;
+    } else {
+        RAPID_CUDA(cudaMemsetAsync(b->p_cnt.p, 0, pn * sizeof(uint4), s));
+        RAPID_CUDA(cudaMemsetAsync(b->p_h1.p, 0, pn * sizeof(uint64_t), s));
+        RAPID_CUDA(cudaMemsetAsync(b->p_h2.p, 0, pn * sizeof(uint64_t), s));
+        cd->last_path = uniform ? 2 : 3;
+    }
+    RAPID_CUDA(cudaEventRecord(cd->evk1, s));
+
+    FinArgs fa;
+    fa.R = cd->R; fa.Rpad = cd->Rpad; fa.n_chunks = n_chunks; fa.part = part; fa.dl = dl;
+    fa.any_down_uniform = bc.any_down; fa.uniform = uniform ? 1 : 0;
+    fa.n_pre = cd->n_pre.p; fa.rflags = cd->rflags.p; fa.pend_h1 = cd->pend_h1.p; fa.pend_h2 = cd->pend_h2.p;
+    fa.pend_cnt = cd->pend_cnt.p; fa.out_h1 = cd->out_h1.p; fa.out_h2 = cd->out_h2.p; fa.out_len = cd->out_len.p;
+    fa.mixed_list = b->mixed_list.p; fa.bc = cd->counts.p;
+    const unsigned gr = (unsigned)ceil_div<int64_t>(cd->R, TB);
+    k_finalize1<<<gr, TB, 0, s>>>(fa);
+    RAPID_KERNEL_CHECK();
+    cd->last_launches += 1;
+
+    if (Sb > 0) {
+        RAPID_CHECK(b->iv_tL.reserve((size_t)MIXED_BLOCKS * Sb)); RAPID_CHECK(b->iv_tH.reserve((size_t)MIXED_BLOCKS * Sb));
+        RAPID_CHECK(b->iv_fl.reserve((size_t)MIXED_BLOCKS * Sb));
+        MixArgs ma;
+        ma.ap = ap; ma.S = cd->S; ma.touch = cd->touch.p; ma.serial = cd->batch_serial; ma.mixed_list = b->mixed_list.p;
+        ma.bc = cd->counts.p; ma.iv_tL = b->iv_tL.p; ma.iv_tH = b->iv_tH.p; ma.iv_fl = b->iv_fl.p; ma.rflags = cd->rflags.p;
+        ma.pend_h1 = cd->pend_h1.p; ma.pend_h2 = cd->pend_h2.p; ma.pend_cnt = cd->pend_cnt.p;
+        ma.out_h1 = cd->out_h1.p; ma.out_h2 = cd->out_h2.p; ma.out_len = cd->out_len.p;
+        k_resolve_mixed<<<MIXED_BLOCKS, 256, 0, s>>>(ma);
+        k_flip<<<(unsigned)ceil_div(Sb, TB), TB, 0, s>>>(Sb, b->desc.p, cd->cur.p);
+        RAPID_KERNEL_CHECK();
+        cd->last_launches += 2;
+    }
+    InvArgs ia;
+    ia.masks = cd->masks.p; ia.cur = cd->cur.p; ia.Rpad = cd->Rpad; ia.K = cd->K; ia.H = cd->H; ia.L = cd->L; ia.R = cd->R;
+    ia.rflags = cd->rflags.p; ia.pre_pairs = b->pre_pairs.p; ia.pre_count = b->pre_count.p; ia.pre_cap = ap.pre_cap;
+    ia.slot_subject = cd->slot_subject.p; ia.slot_of = cd->slot_of.p; ia.obs = cd->view->obs.p;
+    ia.k3_res = b->k3_res.p; ia.k3_h1 = b->k3_h1.p; ia.k3_h2 = b->k3_h2.p;
+    k_inval_pairs<<<148 * 4, 256, 0, s>>>(ia);
+    Fin2Args f2;
+    f2.R = cd->R; f2.n_pre = cd->n_pre.p; f2.rflags = cd->rflags.p; f2.pend_h1 = cd->pend_h1.p; f2.pend_h2 = cd->pend_h2.p;
+    f2.pend_cnt = cd->pend_cnt.p; f2.out_h1 = cd->out_h1.p; f2.out_h2 = cd->out_h2.p; f2.out_len = cd->out_len.p;
+    f2.out_ann = cd->out_ann.p; f2.k3_res = b->k3_res.p; f2.k3_h1 = b->k3_h1.p; f2.k3_h2 = b->k3_h2.p;
+    k_finalize2<<<gr, TB, 0, s>>>(f2);
+    RAPID_KERNEL_CHECK();
+    cd->last_launches += 2;
+    return RAPID_OK;
+}
+
+}  // namespace rapid

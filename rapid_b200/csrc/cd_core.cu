@@ -98,10 +98,16 @@ __global__ void k_assign_slots(int64_t A, const int32_t* __restrict__ dst, const
 }
 
 __global__ void k_cell_slots(int64_t A, const int32_t* __restrict__ dst, const int32_t* __restrict__ slot_of,
-                             int32_t* __restrict__ cell_slot, BatchCounts* __restrict__ bc) {
+                             int32_t* __restrict__ cell_slot, int32_t* __restrict__ touch, int32_t serial,
+                             BatchCounts* __restrict__ bc) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A) return;
-    if (cell_slot[i] == -2) { cell_slot[i] = slot_of[dst[i]]; atomicAdd(&bc->n_valid, 1); }
+    if (cell_slot[i] == -2) {
+        const int32_t slot = slot_of[dst[i]];
+        cell_slot[i] = slot;
+        atomicAdd(&bc->n_valid, 1);
+        if (atomicExch(&touch[slot], serial) != serial) atomicAdd(&bc->n_batch_subj, 1);   // first cell of this subject in the batch
+    }
 }
 
 // =====================================================================================================
@@ -280,10 +286,12 @@ static int32_t ensure_id_capacity(CD* cd) {
     RAPID_CHECK(cd->slot_of.reserve((size_t)ncap, true, cd->stream));
     RAPID_CHECK(cd->first_idx.reserve((size_t)ncap, true, cd->stream));
     RAPID_CHECK(cd->slot_subject.reserve((size_t)ncap, true, cd->stream));
-    ncap = (int64_t)std::min(cd->slot_of.cap, std::min(cd->first_idx.cap, cd->slot_subject.cap));
+    RAPID_CHECK(cd->touch.reserve((size_t)ncap, true, cd->stream));
+    ncap = (int64_t)std::min(std::min(cd->slot_of.cap, cd->touch.cap), std::min(cd->first_idx.cap, cd->slot_subject.cap));
     const int TB = 256;
     k_fill_i32<<<(unsigned)ceil_div<int64_t>(ncap - old, TB), TB, 0, cd->stream>>>(cd->slot_of.p + old, ncap - old, -1);
     k_fill_i32<<<(unsigned)ceil_div<int64_t>(ncap - old, TB), TB, 0, cd->stream>>>(cd->first_idx.p + old, ncap - old, INT_MAX);
+    k_fill_i32<<<(unsigned)ceil_div<int64_t>(ncap - old, TB), TB, 0, cd->stream>>>(cd->touch.p + old, ncap - old, 0);
     RAPID_KERNEL_CHECK();
     cd->ntot_cap = ncap;
     return RAPID_OK;
@@ -334,7 +342,7 @@ static int32_t preprocess(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev
         k_exclusive_scan<<<1, 1024, 0, s>>>(cd->scan_tmp.p, A, cd->scan_tmp.p + A);
         k_assign_slots<<<g, TB, 0, s>>>(A, dst_dev, cd->cell_slot.p, cd->scan_tmp.p, cd->scan_tmp.p + A, cd->S, cd->slot_of.p,
                                         cd->first_idx.p, cd->slot_subject.p, cd->counts.p);
-        k_cell_slots<<<g, TB, 0, s>>>(A, dst_dev, cd->slot_of.p, cd->cell_slot.p, cd->counts.p);
+        k_cell_slots<<<g, TB, 0, s>>>(A, dst_dev, cd->slot_of.p, cd->cell_slot.p, cd->touch.p, ++cd->batch_serial, cd->counts.p);
         RAPID_KERNEL_CHECK();
         cd->last_launches += 5;
     }
@@ -419,6 +427,8 @@ static int32_t apply_common(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_d
     BatchCounts bc;
     RAPID_CHECK(preprocess(cd, cfg, A, dst_dev, ring_dev, status_dev, cfg_dev, &bc));
     int32_t rc;
+    cd->cur_ring_dev = ring_dev;
+    cd->cur_status_dev = status_dev;
     if (cd->bucketed) {
         rc = bucketed_apply(cd, A, dl, bc);
     } else {
@@ -465,7 +475,9 @@ int32_t rapid_cd_create(rapid_cd** out, const rapid_view* v, int32_t H, int32_t 
     cd->nbuf = cd->bucketed ? 2 : 1;
     cd->R = n_receivers;
     cd->rbegin = receiver_begin;
-    cd->Rpad = (size_t)ceil_div<int64_t>(n_receivers, 128) * 128;      // rows are 256-byte multiples
+    // rows are 256-byte multiples; bucketed handles pad to whole 1024-receiver tiles so every uint4 access is in-bounds
+    const int64_t pad = cd->bucketed ? 1024 : 128;
+    cd->Rpad = (size_t)ceil_div<int64_t>(n_receivers, pad) * pad;
     int32_t rc = RAPID_OK;
     do {
         if (cudaStreamCreateWithFlags(&cd->stream, cudaStreamNonBlocking) != cudaSuccess ||

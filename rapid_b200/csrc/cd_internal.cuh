@@ -51,6 +51,8 @@ struct CD {
     DevBuf<int32_t> slot_of;          // [ntot_cap] id -> slot, -1 if none
     DevBuf<int32_t> first_idx;        // [ntot_cap] scratch (INT_MAX)
     DevBuf<int32_t> slot_subject;     // [ntot_cap] slot -> id
+    DevBuf<int32_t> touch;            // [ntot_cap] slot -> serial of the last batch that had a valid cell for it
+    int32_t batch_serial = 0;
 
     DevBuf<int32_t> n_pre;            // [R] updatesInProgress
     DevBuf<int32_t> n_prop;           // [R] proposalCount (sweep handles)
@@ -64,6 +66,8 @@ struct CD {
     // batch staging (device)
     DevBuf<int32_t> c_dst;  DevBuf<uint8_t> c_ring, c_status;  DevBuf<int64_t> c_cfg;
     DevBuf<uint8_t> d_blocked;  DevBuf<uint32_t> d_bitmap;
+    const uint8_t* cur_ring_dev = nullptr;    // ring / status arrays of the batch in flight (device)
+    const uint8_t* cur_status_dev = nullptr;
     DevBuf<int32_t> cell_slot;        // [A] slot or -1
     DevBuf<int32_t> scan_tmp;         // [A]
     DevBuf<BatchCounts> counts;       // [1]
