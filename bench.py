@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py — alert cells / second to a converged, quorum-decided cut (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nodes n] [--workload c5|c2|c3]
+
+One "step" = one pass of the hot path over one synthetic alert batch:
+    filter -> per-receiver cut detection (subject-bucketed kernel) -> implicit invalidation -> per-node proposal
+    fingerprints -> fast-round vote tally [-> NCCL histogram all-reduce when sharded] -> decision on the host.
+Default workload (N=1): BASELINE config 5 — 1,000,000 virtual nodes, K=10, H=9, L=4, a 1 % churn batch (5,000 crashes
++ 5,000 joins, ~10^5 alert cells) — on however many GPUs --gpus names; receivers are sharded by ring-0 range, the
+cluster size stays fixed ("scaling": "strong").
+
+`value`  : device time only, cell arrays resident in HBM when the timed region starts (CUDA events on the library's
+           streams, summed over the calls of a step, max over ranks).  The epoch reset between steps (clear() / new
+           FastPaxos, the reference's decideViewChange) is outside the timed region.
+`e2e`    : the same through the host-facing C ABI: host arrays in, H2D copies, epoch reset, kernels, decision read
+           back — wall clock.
+--impl reference : the reference's own CPU path.  The reference is Java and cannot be built or run in this image (no
+           JDK), so this times oracle/'s literal C++ restatement of it (kind "port") on all host cores, on a bounded
+           sample of the same workload, extrapolated linearly (see `sample`).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K, H, L = 10, 9, 4          # Cluster.java:72-74
+METRIC = "alert_cells_per_sec_to_converged_cut"
+UNIT = "cells/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--nodes", type=int, default=1_000_000)
+    p.add_argument("--workload", default="c5", choices=["c5", "c2", "c3"])
+    p.add_argument("--kernel", default="auto", choices=["auto", "bucketed", "sweep"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=20.0, help="budget for the CPU baseline sample")
+    return p.parse_args()
+
+
+def workload_name(args, A, S):
+    n = args.nodes
+    if args.workload == "c5":
+        return "C5 %d-node K=10 H=9 L=4, 1%% churn batch (%d DOWN + %d UP subjects, %d cells)" % (n, n // 200, n // 200, A)
+    if args.workload == "c2":
+        return "C2 %d-node K=10 H=9 L=4, 1%% simultaneous crash (%d subjects, %d cells)" % (n, S, A)
+    return "C3 %d-node K=10 H=9 L=4, 5%% correlated one-way partition (%d subjects, %d cells)" % (n, S, A)
+
+
+def make_batch(args, W, obs, joiner_obs, ring0):
+    n = args.nodes
+    if args.workload == "c5":
+        return W.c5_churn(obs, joiner_obs, n, n // 200, n // 200)
+    if args.workload == "c2":
+        return W.c2_simultaneous_crash(obs, n, 0.01)
+    return W.c3_correlated_partition(obs, ring0, n, 0.05)
+
+
+def n_joiners(args):
+    return args.nodes // 200 if args.workload == "c5" else 0
+
+
+# --------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.rows, self.proc, self.dev = [], None, device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle): cpu_baseline at N=1 and --impl reference
+# --------------------------------------------------------------------------------------------------------------
+def cpu_sample(args, threads, budget_s):
+    """Time the literal C++ restatement on a bounded sample of the workload; returns a dict (value = cells/s for the
+    WHOLE cluster, extrapolated linearly from the sample)."""
+    from oracle import oracle_py as orc
+    from rapid_b200 import workloads as W
+    n, nj = args.nodes, n_joiners(args)
+    t0 = time.time()
+    hb, off, ports = W.packed_endpoints(0, n + nj)
+    u = orc.Universe()
+    tags = u.add_bulk(hb, off, ports)
+    hi, lo = W.node_ids(0, n)
+    view = orc.MembershipView(u, K, tags[:n], hi, lo)
+    cfg = view.getCurrentConfigurationId()
+    obs = lambda ids: view.tables(ids)[0]
+    joiner_obs = np.asarray([view.getExpectedObserversOf(n + j) for j in range(nj)], np.int32).reshape(nj, K)
+    ring0 = np.asarray(view.getRing(0), np.int32) if args.workload == "c3" else None
+    b = make_batch(args, W, obs, joiner_obs, ring0)
+    A = len(b)
+    setup_s = time.time() - t0
+    cfgs = np.full(A, cfg, np.int64)
+    # apply: R_s receivers x the full batch; grow the sample until it costs ~budget/2
+    Rs = threads * 2
+    while True:
+        sim = orc.ClusterSim(view, K, H, L, Rs)
+        o_len, o_ann, o_ids, o_off = sim.apply_batch(b.src, b.dst, b.ring, b.status, cfgs, threads=threads)
+        t_apply = sim.last_seconds
+        if t_apply > budget_s / 4 or Rs >= 64 * threads:
+            break
+        Rs *= 4
+    assert (o_len == len(b.expected_cut)).all(), "oracle did not converge to the expected cut"
+    live = int(n - int(b.blocked.sum()))
+    apply_whole = t_apply * live / Rs
+    # tally: `threads` nodes x V_s of the `live` identical votes
+    prop = o_ids[o_off[0]: o_off[1]]
+    Vs = 64
+    while True:
+        senders = np.arange(Vs, dtype=np.int32)
+        nd, dec, rec, t_tally = orc.sim_tally(u, cfg, n, threads, senders, np.full(Vs, cfg, np.int64),
+                                              np.zeros(Vs, np.int32), np.array([0, len(prop)], np.int32), prop, threads=threads)
+        if t_tally > budget_s / 4 or Vs >= live:
+            break
+        Vs = min(live, Vs * 4)
+    tally_whole = t_tally * (live / threads) * (live / Vs)
+    whole = apply_whole + tally_whole
+    return {
+        "value": A / whole, "unit": UNIT, "cores": threads, "kind": "port",
+        "apply_only_value": A / apply_whole,
+        "sample": ("literal C++ restatement of MultiNodeCutDetector/MembershipService batch handler/FastPaxos tally "
+                   "(oracle/, g++ -O2; the Java reference cannot run here: no JDK).  apply: %d of %d live virtual nodes x "
+                   "the full %d-cell batch on %d threads = %.3f s; tally: %d nodes x %d of %d votes (each vote re-hashes "
+                   "the %d-endpoint proposal list like List.hashCode) = %.3f s; both extrapolated linearly to all %d "
+                   "nodes and votes (whole job %.3g s, of which tally %.3g s)"
+                   % (Rs, live, A, threads, t_apply, threads, Vs, live, len(prop), t_tally, live, whole, tally_whole)),
+        "setup_s": round(setup_s, 1),
+    }, A
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle_py as orc
+    orc.build()
+    threads = max(1, orc.hardware_threads())
+    W_ = args.warmup
+    vals = []
+    t_start = time.time()
+    per = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + W_)))
+    for i in range(W_ + args.steps):
+        d, A = cpu_sample(args, threads, per)
+        if i >= W_:
+            vals.append(d)
+        if time.time() - t_start > 240 and len(vals) >= 1:
+            break
+    v = float(np.mean([x["value"] for x in vals]))
+    d = vals[-1]
+    d["value"] = v
+    S = n_joiners(args) * 2 if args.workload == "c5" else 0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": W_, "ms_per_step": 1e3 * A / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u16", "data": "synthetic",
+        "config": {"workload": workload_name(args, A, S), "nodes": args.nodes, "cells": A, "K": K, "H": H, "L": L},
+        "cpu_baseline": d,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import rapid_b200 as rb
+    from rapid_b200 import _native as N
+    from rapid_b200 import workloads as W
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log("note: WORLD_SIZE=%d but --gpus %d; using WORLD_SIZE" % (world, args.gpus))
+    G = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (librapid_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if G > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n, nj = args.nodes, n_joiners(args)
+    t0 = time.time()
+    hb, off, ports = W.packed_endpoints(0, n + nj)
+    view = rb.MembershipView.from_packed(K, hb[: off[n]], off[: n + 1], ports[:n], device=local)
+    if nj:
+        jh = hb[off[n]: off[n + nj]]
+        first = C.c_int32(0)
+        N.check(N.lib().rapid_view_register_joiners(view._h, nj, N.ptr(np.ascontiguousarray(jh)),
+                                                    N.ptr(np.ascontiguousarray(off[n:] - off[n])),
+                                                    N.ptr(np.ascontiguousarray(ports[n:])), C.byref(first)))
+        assert first.value == n
+    obs, _ = view.tables()
+    ring0 = view.getRing(0)
+    joiner_obs = view.joinerTables() if nj else np.zeros((0, K), np.int32)
+    b = make_batch(args, W, obs, joiner_obs, ring0)
+    A = len(b)
+    S = len(np.unique(b.dst))
+    hi, lo = W.node_ids(0, n)
+    cfg = view.getCurrentConfigurationId(hi, lo)
+    begin = rank * n // G
+    R = (rank + 1) * n // G - begin
+    blocked = W.blocked_by_receiver(b.blocked, ring0, begin, R)
+    cl = rb.VirtualCluster(view, H, L, n_receivers=R, receiver_begin=begin, kernel=args.kernel, max_subjects=S + 64)
+    fp = rb.FastPaxos(cfg, n, sender_capacity=n)
+    comm = None
+    if G > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.from_numpy(rb.NcclComm.unique_id()))
+        dist.broadcast(uid, 0)
+        comm = rb.NcclComm(rank, G, uid.cpu().numpy(), local)
+    want = rb.proposal_fingerprint(b.expected_cut)
+    log("[rank %d] setup %.1fs: n=%d receivers=[%d,%d) cells=%d subjects=%d" % (rank, time.time() - t0, n, begin, begin + R, A, S))
+
+    # device-resident inputs (torch only holds the memory)
+    d_dst = torch.from_numpy(b.dst).cuda()
+    d_ring = torch.from_numpy(b.ring).cuda()
+    d_status = torch.from_numpy(b.status).cuda()
+    d_blocked = torch.from_numpy(blocked).cuda()
+    dl = N.Delivery()
+    dl.flags = N.DELIVERY_BLOCKED
+    dl.blocked = d_blocked.data_ptr()
+    lib = N.lib()
+
+    def step_device():
+        cl.clear()
+        fp.reset(cfg)
+        N.check(lib.rapid_cd_apply_batch_dev(cl._h, cfg, A, None, d_dst.data_ptr(), d_ring.data_ptr(),
+                                             d_status.data_ptr(), None, C.byref(dl)))
+        res = fp.tallyCluster(cl, comm)
+        tot, main = cl.lastDeviceMs()
+        return res, tot + fp.lastDeviceMs(), main, cl.lastPath()[1] + fp.lastLaunches()
+
+    def step_host():
+        cl.clear()
+        fp.reset(cfg)
+        cl.handleBatch(cfg, None, b.dst, b.ring, b.status, blocked=blocked, read_outputs=False)
+        return fp.tallyCluster(cl, comm)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if G > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        res, _, _, _ = step_device()
+    assert res.decided and (res.hash, res.hash2, res.length) == (want[0], want[1], len(b.expected_cut)), \
+        "decision differs from the expected cut: %r" % (res,)
+
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    dev_ms, main_ms, launches = 0.0, 0.0, 0
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        res, ms, mk, nl = step_device()
+        dev_ms += ms; main_ms += mk; launches += nl
+    barrier()
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    # end-to-end through the host-facing ABI (host arrays, H2D, reset, kernels, decision back)
+    for _ in range(2):
+        step_host()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step_host()
+    barrier()
+    e2e_ms = (time.perf_counter() - e0) * 1e3 / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    assert res.decided and res.hash == want[0]
+
+    t = torch.tensor([dev_ms, main_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if G > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, main_ms, e2e_ms, wall_ms = [float(x) for x in t.cpu()]
+    ms_per_step = dev_ms / args.steps
+    main_per = main_ms / args.steps
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        fresh = True   # every step starts a new epoch: all subjects are new, their state is written, never read
+        alg = (2 if fresh else 4) * S * R + 5 * R + 40 * R      # mask bytes + flags/blocked read + per-receiver partial
+        achieved = alg / (main_per * 1e-3) / 1e9 if main_per > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": A / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": G, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+            "config": {"workload": workload_name(args, A, S), "nodes": n, "cells": A, "alert_messages": b.n_messages(),
+                       "subjects": S, "K": K, "H": H, "L": L, "receivers_per_gpu": R,
+                       "parallelism": "virtual nodes sharded by ring-0 range x%d; one NCCL histogram all-reduce" % G,
+                       "l2": "per-step state %.1f GB per GPU >> 126 MB L2 (inputs larger than L2, no flush)" % (2 * S * R / 1e9),
+                       "timing": "CUDA events on the library streams per call, summed per step, max over ranks; "
+                                 "epoch reset between steps excluded",
+                       "kernel_path": {1: "sweep", 2: "bucketed-uniform", 3: "bucketed-generic"}.get(cl.lastPath()[0])},
+            "wall_ms_per_step_incl_reset": wall_ms / args.steps,
+            "clocks": clk,
+            "e2e": {"value": A / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(A * 6 + R), "d2h_bytes_per_step": 64 + 36},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_apply_uniform", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(alg), "kernel_ms": main_per,
+                         "kernel_share_of_step": main_per / ms_per_step if ms_per_step else None},
+        }
+    if G > 1:
+        dist.barrier()
+    if rank == 0:
+        if not args.no_cpu_baseline and G == 1:
+            try:
+                from oracle import oracle_py as orc
+                orc.build()
+                d, _ = cpu_sample(args, max(1, orc.hardware_threads()), args.cpu_seconds)
+                line["cpu_baseline"] = d
+            except Exception as e:       # the baseline is a reported extra; never lose the GPU line over it
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        print(json.dumps(line), flush=True)
+    if G > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

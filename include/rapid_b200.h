@@ -94,6 +94,8 @@ int32_t rapid_view_config_id(const rapid_view* v, const int64_t* id_high, const 
 int32_t rapid_view_register_joiners(rapid_view* v, int64_t n_add, const uint8_t* host_bytes,
                                     const int32_t* host_off, const int32_t* port, int32_t* out_first_id);
 int32_t rapid_view_num_joiners(const rapid_view* v, int64_t* out);
+/* expected observers of every registered joiner: out[j*K+k] for joiner id n + j. */
+int32_t rapid_view_joiner_tables(const rapid_view* v, int32_t* out);
 
 /* ------------------------------------------------------------------------------------------------
  * MultiNodeCutDetector for R virtual nodes ("receivers")   (MultiNodeCutDetector.java,
@@ -166,6 +168,10 @@ int32_t rapid_cd_debug_counters(const rapid_cd* cd, int64_t receiver, int32_t* u
 /* Which kernel family served the last batch: 1 = sweep, 2 = bucketed-uniform, 3 = bucketed-generic;
  * *n_kernel_launches = CUDA kernels launched by the last apply call. */
 int32_t rapid_cd_last_path(const rapid_cd* cd, int32_t* path, int32_t* n_kernel_launches);
+/* Bucketed handles, last batch: receivers that needed the exact interval analysis, (tile, subject) pairs on the
+ * invalidation work list, distinct subjects and valid cells of the batch. */
+int32_t rapid_cd_debug_stats(const rapid_cd* cd, int32_t* n_mixed, int32_t* n_inval_pairs, int32_t* n_batch_subjects,
+                             int32_t* n_valid_cells);
 
 /* RAW mode (RAPID_CD_RAW handles): the bare detector API the reference's CutDetectionTest drives.
  * aggregateForProposal(AlertMessage) :76-82 for every receiver (no filter, no announced gating); returns the
@@ -187,6 +193,8 @@ int32_t rapid_proposal_fingerprint(const int32_t* ids, int64_t n, uint64_t* h1, 
 int32_t rapid_fp_create(rapid_fp** out, int64_t cfg_id, int64_t membership_size, int64_t sender_capacity,
                         int32_t device);
 int32_t rapid_fp_destroy(rapid_fp* fp);
+/* Start over for the next configuration (the new FastPaxos of MembershipService.java:427-429) on the same buffers. */
+int32_t rapid_fp_reset(rapid_fp* fp, int64_t cfg_id, int64_t membership_size);
 /* Apply n_votes FastRoundPhase2bMessages in array order: ignore if vote_cfg != cfg (:126), sender already
  * voted (:134) or already decided (:138); count identical proposals; decide when count >= N - floor((N-1)/4)
  * (:145-150).  A proposal is identified by (hash, hash2, len) = rapid_proposal_fingerprint + size.
@@ -218,6 +226,7 @@ int32_t rapid_comm_destroy(rapid_comm* c);
  * measured with CUDA events on the handle's stream; and per-kernel breakdown of the last apply. */
 int32_t rapid_cd_last_device_ms(const rapid_cd* cd, float* total_ms, float* main_kernel_ms);
 int32_t rapid_fp_last_device_ms(const rapid_fp* fp, float* total_ms);
+int32_t rapid_fp_last_launches(const rapid_fp* fp, int32_t* n_kernel_launches);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -118,12 +118,20 @@ public:
     MembershipView(int K, const std::vector<NodeId>& nodeIds,                /* :74-89 */
                    const std::vector<Endpoint>& endpoints) : K_(K) {
         init();
+        // Same result as `set.addAll(endpoints)` on a TreeSet (first of two comparator-equal endpoints wins, the
+        // other is silently dropped), built bottom-up: stable-sort by the memoised key, then append with an end
+        // hint.  Construction is outside every timed region; only its result matters.
         for (int k = 0; k < K_; ++k) {
-            for (const Endpoint& e : endpoints) {
-                rings_[k].insert(e);          // TreeSet.addAll: a comparator tie silently drops e
-                allNodes_.insert(e);
-            }
+            std::vector<std::pair<int64_t, const Endpoint*>> order;
+            order.reserve(endpoints.size());
+            for (const Endpoint& e : endpoints) order.emplace_back(cmps_[k].hashOf(e), &e);
+            std::stable_sort(order.begin(), order.end(),
+                             [](const std::pair<int64_t, const Endpoint*>& a, const std::pair<int64_t, const Endpoint*>& b) {
+                                 return a.first < b.first;
+                             });
+            for (const auto& kv : order) rings_[k].emplace_hint(rings_[k].end(), *kv.second);
         }
+        for (const Endpoint& e : endpoints) allNodes_.insert(e);
         for (const NodeId& id : nodeIds) identifiersSeen_.insert(id);
     }
 

@@ -68,6 +68,8 @@ SIGNATURES = {
     "rapid_view_config_id": [_vp, _p, _p, _i64, _p],
     "rapid_view_register_joiners": [_vp, _i64, _p, _p, _p, _p],
     "rapid_view_num_joiners": [_vp, _p],
+    "rapid_view_joiner_tables": [_vp, _p],
+    "rapid_cd_debug_stats": [_vp, _p, _p, _p, _p],
     "rapid_cd_create": [_pp, _vp, _i32, _i32, _i64, _i64, _u32, _i64],
     "rapid_cd_destroy": [_vp],
     "rapid_cd_apply_batch": [_vp, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
@@ -84,6 +86,7 @@ SIGNATURES = {
     "rapid_proposal_fingerprint": [_p, _i64, _p, _p],
     "rapid_fp_create": [_pp, _i64, _i64, _i64, _i32],
     "rapid_fp_destroy": [_vp],
+    "rapid_fp_reset": [_vp, _i64, _i64],
     "rapid_fp_tally": [_vp, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "rapid_fp_tally_cd": [_vp, _vp, _vp, _p, _p, _p, _p, _p, _p],
     "rapid_fp_quorum": [_i64, _p],
@@ -92,6 +95,7 @@ SIGNATURES = {
     "rapid_comm_destroy": [_vp],
     "rapid_cd_last_device_ms": [_vp, _p, _p],
     "rapid_fp_last_device_ms": [_vp, _p],
+    "rapid_fp_last_launches": [_vp, _p],
 }
 
 

@@ -243,6 +243,7 @@ struct ApplyArgs {
     int2* pre_pairs;
     int32_t* pre_count;
     int32_t pre_cap;
+    int32_t S_before;             // slots >= S_before were assigned by this batch: their state is known-zero (never read)
 };
 
 __device__ __forceinline__ void note_unresolved(const ApplyArgs& a, int tile, int32_t slot) {
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
             sd[t] = d;
             sw[t] = a.walk[base + t];
             const uint8_t c = a.cur[d.slot];
-            s_src[t] = a.masks + ((size_t)d.slot * 2 + c) * a.Rpad;
+            s_src[t] = d.slot >= a.S_before ? nullptr : a.masks + ((size_t)d.slot * 2 + c) * a.Rpad;
             s_dst[t] = a.masks + ((size_t)d.slot * 2 + (c ^ 1)) * a.Rpad;
             s_unres[t] = 0;
         }
@@ -300,7 +301,8 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
             uint4 W[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (i0 + u < n) W[u] = *reinterpret_cast<const uint4*>(s_src[i0 + u] + r0);
+                if (i0 + u < n)
+                    W[u] = s_src[i0 + u] ? *reinterpret_cast<const uint4*>(s_src[i0 + u] + r0) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = i0 + u;
@@ -438,7 +440,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_apply_generic(const ApplyArgs a
             const SubjDesc d = a.desc[base + t];
             sd[t] = d;
             const uint8_t c = a.cur[d.slot];
-            s_src[t] = a.masks + ((size_t)d.slot * 2 + c) * a.Rpad;
+            s_src[t] = d.slot >= a.S_before ? nullptr : a.masks + ((size_t)d.slot * 2 + c) * a.Rpad;
             s_dst[t] = a.masks + ((size_t)d.slot * 2 + (c ^ 1)) * a.Rpad;
             s_unres[t] = 0;
         }
@@ -447,7 +449,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_apply_generic(const ApplyArgs a
             const SubjDesc& d = sd[i];
             bool unres = false;
             if (r < (int64_t)a.Rpad) {
-                uint32_t st = s_src[i][r];
+                uint32_t st = s_src[i] ? s_src[i][r] : 0u;
                 if (active) {
                     const GVisit v = visit_generic(st & RM, d, a.sidx, a.s_ring, a.s_status, a.dl, r, rs, L, H);
                     if (v.seen_down) fl |= PF_SEEN;
@@ -601,7 +603,7 @@ __global__ void __launch_bounds__(256) k_resolve_mixed(const MixArgs m) {
         bool inf_neg = false;
         for (int b = t; b < a.Sb; b += blockDim.x) {
             const SubjDesc d = a.desc[b];
-            const uint32_t st = (a.masks + ((size_t)d.slot * 2 + a.cur[d.slot]) * a.Rpad)[r];
+            const uint32_t st = d.slot >= a.S_before ? 0u : (a.masks + ((size_t)d.slot * 2 + a.cur[d.slot]) * a.Rpad)[r];
             const GVisit v = visit_generic(st & RM, d, a.sidx, a.s_ring, a.s_status, a.dl, r, rs, L, H);
             uint32_t f = 0;
             const bool starts_in = v.c0 >= L && v.c0 < H;
@@ -809,6 +811,14 @@ void bucketed_destroy(CD* cd) {
     if (cd->bucketed_state) { delete static_cast<Bucketed*>(cd->bucketed_state); cd->bucketed_state = nullptr; }
 }
 
+int32_t bucketed_pair_count(const CD* cd) {
+    if (!cd->bucketed_state) return 0;
+    const Bucketed* b = static_cast<const Bucketed*>(cd->bucketed_state);
+    int32_t n = 0;
+    if (b->pre_count.p) cudaMemcpy(&n, b->pre_count.p, sizeof(n), cudaMemcpyDeviceToHost);
+    return n;
+}
+
 int32_t bucketed_clear(CD* cd) {
     if (!cd->bucketed) return RAPID_OK;
     Bucketed* b = state(cd);
@@ -895,6 +905,7 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
     ap.desc = b->desc.p; ap.walk = b->walk.p; ap.slot_subject = cd->slot_subject.p;
     ap.sidx = b->val_out.p; ap.s_ring = b->s_ring.p; ap.s_status = b->s_status.p;
     ap.part = part; ap.n_tiles = b->n_tiles; ap.in_list = b->in_list.p; ap.pre_pairs = b->pre_pairs.p;
+    ap.S_before = cd->S_before;
     ap.pre_count = b->pre_count.p; ap.pre_cap = (int32_t)std::min<size_t>(b->in_list_slots * (size_t)b->n_tiles, 0x7fffffff);
 
     RAPID_CUDA(cudaEventRecord(cd->evk0, s));

@@ -329,6 +329,7 @@ static int32_t preprocess(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev
     BatchCounts init;
     memset(&init, 0, sizeof(init));
     init.n_slots = cd->S;
+    cd->S_before = cd->S;
     init.bad_ring = -1;
     init.bad_dst = -1;
     *cd->h_counts.p = init;
@@ -529,7 +530,10 @@ int32_t rapid_cd_clear(rapid_cd* cd) {
     if (cd->S > 0) {
         k_reset_slots<<<(unsigned)ceil_div<int32_t>(cd->S, 256), 256, 0, s>>>(cd->S, cd->slot_subject.p, cd->slot_of.p);
         RAPID_KERNEL_CHECK();
-        RAPID_CUDA(cudaMemsetAsync(cd->masks.p, 0, (size_t)cd->S * cd->nbuf * cd->Rpad * sizeof(uint16_t), s));
+        // Bucketed handles never read the state of a slot before the batch that assigns it has written it
+        // (ApplyArgs::S_before), so clear() is O(#slots) there; the sweep kernel reads in place and needs zeros.
+        if (!cd->bucketed)
+            RAPID_CUDA(cudaMemsetAsync(cd->masks.p, 0, (size_t)cd->S * cd->nbuf * cd->Rpad * sizeof(uint16_t), s));
         RAPID_CUDA(cudaMemsetAsync(cd->cur.p, 0, (size_t)cd->S, s));
     }
     cd->S = 0;
@@ -751,6 +755,19 @@ int32_t rapid_cd_debug_counters(const rapid_cd* cd, int64_t receiver, int32_t* u
         RAPID_CUDA(cudaMemcpy(&f, cd->rflags.p + receiver, sizeof(f), cudaMemcpyDeviceToHost));
         *seen_link_down = (f & RF_SEEN_DOWN) ? 1 : 0;
     }
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_debug_stats(const rapid_cd* cd, int32_t* n_mixed, int32_t* n_inval_pairs, int32_t* n_batch_subjects,
+                             int32_t* n_valid_cells) {
+    if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    BatchCounts bc;
+    RAPID_CUDA(cudaMemcpy(&bc, cd->counts.p, sizeof(bc), cudaMemcpyDeviceToHost));
+    if (n_mixed) *n_mixed = bc.n_mixed;
+    if (n_batch_subjects) *n_batch_subjects = bc.n_batch_subj;
+    if (n_valid_cells) *n_valid_cells = bc.n_valid;
+    if (n_inval_pairs) *n_inval_pairs = bucketed_pair_count(cd);
     return RAPID_OK;
 }
 

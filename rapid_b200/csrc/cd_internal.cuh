@@ -43,6 +43,7 @@ struct CD {
     size_t Rpad = 0;
     int nbuf = 1;                     // 2 = double-buffered rows (bucketed handles)
     int32_t S = 0;                    // slots in use (host mirror)
+    int32_t S_before = 0;             // S when the batch in flight started
     size_t S_cap = 0;
     int64_t ntot_cap = 0;             // capacity of slot_of / first_idx (node + joiner ids)
 
@@ -107,6 +108,7 @@ struct DeliveryDev {
 int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCounts& bc);
 void bucketed_destroy(CD* cd);
 int32_t bucketed_clear(CD* cd);
+int32_t bucketed_pair_count(const CD* cd);
 
 }  // namespace rapid
 

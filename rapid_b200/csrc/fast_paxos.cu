@@ -449,6 +449,25 @@ int32_t rapid_fp_create(rapid_fp** out, int64_t cfg_id, int64_t membership_size,
     return RAPID_OK;
 }
 
+// A new FastPaxos instance for the next configuration (MembershipService.java:427-429) on the same buffers.
+int32_t rapid_fp_reset(rapid_fp* fp, int64_t cfg_id, int64_t membership_size) {
+    if (!fp || membership_size < 1) { set_error("bad arguments"); return RAPID_EINVAL; }
+    DeviceGuard g(fp->device);
+    cudaStream_t s = fp->stream;
+    fp->cfg = cfg_id;
+    fp->N = membership_size;
+    fp->Q = membership_size - (membership_size - 1) / 4;
+    const int TB = 256;
+    k_fp_fill<<<(unsigned)ceil_div<int64_t>(fp->sender_cap, TB), TB, 0, s>>>(fp->seen.p, fp->sender_cap, INT_MAX);
+    RAPID_KERNEL_CHECK();
+    RAPID_CUDA(cudaMemsetAsync(fp->t_state.p, 0, fp->T * sizeof(int32_t), s));
+    RAPID_CUDA(cudaMemsetAsync(fp->t_count.p, 0, fp->T * sizeof(int32_t), s));
+    RAPID_CUDA(cudaMemsetAsync(fp->t_call.p, 0, fp->T * sizeof(int32_t), s));
+    RAPID_CUDA(cudaMemsetAsync(fp->st.p, 0, sizeof(FPState), s));
+    RAPID_CUDA(cudaStreamSynchronize(s));
+    return RAPID_OK;
+}
+
 int32_t rapid_fp_destroy(rapid_fp* fp) {
     if (!fp) return RAPID_OK;
     DeviceGuard g(fp->device);
@@ -572,6 +591,12 @@ int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, in
 int32_t rapid_fp_last_device_ms(const rapid_fp* fp, float* total_ms) {
     if (!fp) { set_error("NULL handle"); return RAPID_EINVAL; }
     if (total_ms) *total_ms = fp->last_ms;
+    return RAPID_OK;
+}
+
+int32_t rapid_fp_last_launches(const rapid_fp* fp, int32_t* n_kernel_launches) {
+    if (!fp || !n_kernel_launches) { set_error("NULL argument"); return RAPID_EINVAL; }
+    *n_kernel_launches = fp->last_launches;
     return RAPID_OK;
 }
 

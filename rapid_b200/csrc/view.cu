@@ -369,6 +369,13 @@ int32_t rapid_view_tables(const rapid_view* v, int32_t* out_obs, int32_t* out_su
     return RAPID_OK;
 }
 
+int32_t rapid_view_joiner_tables(const rapid_view* v, int32_t* out) {
+    if (!v || (!out && v->nj)) { set_error("NULL argument"); return RAPID_EINVAL; }
+    DeviceGuard g(v->device);
+    if (v->nj) RAPID_CUDA(cudaMemcpy(out, v->obs.p + (size_t)v->n * v->K, (size_t)v->nj * v->K * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return RAPID_OK;
+}
+
 int32_t rapid_view_ring_numbers(const rapid_view* v, int32_t observer, int32_t subject, uint16_t* out_mask) {
     if (!v || !out_mask) { set_error("NULL argument"); return RAPID_EINVAL; }
     int32_t row[RAPID_MAX_K], cnt = 0;

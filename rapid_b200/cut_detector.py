@@ -196,6 +196,12 @@ class VirtualCluster:
         N.check(N.lib().rapid_cd_debug_counters(self._h, int(receiver), C.byref(a), C.byref(b)))
         return a.value, bool(b.value)
 
+    def debugStats(self):
+        """(receivers resolved by exact interval analysis, invalidation work-list pairs, batch subjects, valid cells)"""
+        a, b, c, d = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        N.check(N.lib().rapid_cd_debug_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
     def lastPath(self):
         a, b = C.c_int32(0), C.c_int32(0)
         N.check(N.lib().rapid_cd_last_path(self._h, C.byref(a), C.byref(b)))

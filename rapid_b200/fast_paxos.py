@@ -89,6 +89,18 @@ class FastPaxos:
                                           C.byref(a), C.byref(b), C.byref(l), C.byref(c), C.byref(r)))
         return TallyResult(bool(d.value), a.value, b.value, l.value, c.value, r.value)
 
+    def reset(self, configuration_id, membership_size=None):
+        """the new FastPaxos instance of the next configuration (MembershipService.java:427-429)"""
+        self.cfg = int(configuration_id)
+        if membership_size is not None:
+            self.N = int(membership_size)
+        N.check(N.lib().rapid_fp_reset(self._h, self.cfg, self.N))
+
+    def lastLaunches(self):
+        a = C.c_int32(0)
+        N.check(N.lib().rapid_fp_last_launches(self._h, C.byref(a)))
+        return a.value
+
     def lastDeviceMs(self):
         a = C.c_float(0)
         N.check(N.lib().rapid_fp_last_device_ms(self._h, C.byref(a)))

@@ -112,6 +112,13 @@ class MembershipView:
         N.check(N.lib().rapid_view_register_joiners(self._h, len(port), N.ptr(hb), N.ptr(off), N.ptr(port), C.byref(first)))
         return list(range(first.value, first.value + len(port)))
 
+    def joinerTables(self):
+        """expected observers [n_joiners][K] of the registered joiners"""
+        nj = self.numJoiners()
+        out = np.empty((max(nj, 1), self.K), np.int32)
+        N.check(N.lib().rapid_view_joiner_tables(self._h, N.ptr(out)))
+        return out[:nj]
+
     def numJoiners(self):
         out = C.c_int64(0)
         N.check(N.lib().rapid_view_num_joiners(self._h, C.byref(out)))

@@ -91,14 +91,21 @@ def _mk(src, dst, ring, status):
             "status": np.asarray(status, np.uint8)}
 
 
-def crash_cells(obs, failed, silent=None):
+def _rows(obs, ids):
+    """observer rows of `ids`: obs is a full [n][K] table or a callable ids -> [len(ids)][K]"""
+    ids = np.asarray(ids, np.int32)
+    return np.asarray(obs(ids) if callable(obs) else obs[ids], np.int32)
+
+
+def crash_cells(obs, failed, n, silent=None):
     """DOWN reports (obs_k(s), s, k) for every failed s from every observer that is not itself silent."""
     failed = np.asarray(failed, np.int32)
-    K = obs.shape[1]
-    src = obs[failed].reshape(-1)
+    rows = _rows(obs, failed)
+    K = rows.shape[1]
+    src = rows.reshape(-1)
     dst = np.repeat(failed, K)
     ring = np.tile(np.arange(K, dtype=np.uint8), len(failed))
-    mute = np.zeros(obs.shape[0], bool)
+    mute = np.zeros(n, bool)
     mute[failed if silent is None else silent] = True
     keep = ~mute[src]
     return _mk(src[keep], dst[keep], ring[keep], np.full(int(keep.sum()), DOWN, np.uint8))
@@ -107,7 +114,7 @@ def crash_cells(obs, failed, silent=None):
 def c1_single_crash(obs, n=50, seed=SEED):
     """C1: one crashed node, its K observer reports, one batch."""
     failed = pick_smallest(n, 1, seed)
-    cells = shuffle_cells(crash_cells(obs, failed), seed + 1)
+    cells = shuffle_cells(crash_cells(obs, failed, n), seed + 1)
     blocked = np.zeros(n, np.uint8)
     blocked[failed] = 1
     return Batch(**cells, blocked=blocked, expected_cut=failed, meta={"config": "C1", "failed": failed})
@@ -116,7 +123,7 @@ def c1_single_crash(obs, n=50, seed=SEED):
 def c2_simultaneous_crash(obs, n, frac=0.01, seed=SEED):
     """C2: floor(frac*n) simultaneous crashes; failed nodes send nothing, receive nothing, cast no vote."""
     failed = pick_smallest(n, int(frac * n), seed)
-    cells = shuffle_cells(crash_cells(obs, failed), seed + 1)
+    cells = shuffle_cells(crash_cells(obs, failed, n), seed + 1)
     blocked = np.zeros(n, np.uint8)
     blocked[failed] = 1
     return Batch(**cells, blocked=blocked, expected_cut=failed, meta={"config": "C2", "failed": failed})
@@ -128,7 +135,7 @@ def c3_correlated_partition(obs, ring0, n, frac=0.05, seed=SEED):
     count = int(frac * n)
     start = int(splitmix64(np.uint64(seed))) % n
     arc = np.sort(np.asarray(ring0)[(start + np.arange(count)) % n].astype(np.int32))
-    cells = shuffle_cells(crash_cells(obs, arc), seed + 1)
+    cells = shuffle_cells(crash_cells(obs, arc, n), seed + 1)
     blocked = np.zeros(n, np.uint8)
     blocked[arc] = 1
     return Batch(**cells, blocked=blocked, expected_cut=arc, meta={"config": "C3", "failed": arc, "arc_start": start})
@@ -138,8 +145,8 @@ def c5_churn(obs, joiner_obs, n, n_leave, n_join, seed=SEED):
     """C5: n_leave crashes (as C2) + n_join joins in one batch.  Joiner j has id n + j; its UP reports come from its K
     expected observers (ring predecessors, `joiner_obs[j]`), except those that crashed."""
     failed = pick_smallest(n, n_leave, seed)
-    down = crash_cells(obs, failed)
-    K = obs.shape[1]
+    down = crash_cells(obs, failed, n)
+    K = np.asarray(joiner_obs).shape[1]
     jid = n + np.arange(n_join, dtype=np.int32)
     src = np.asarray(joiner_obs, np.int32)[:n_join].reshape(-1)
     dst = np.repeat(jid, K)
@@ -161,7 +168,7 @@ def c4_flip_flop_stream(obs, n, frac=0.01, T=8, seed=SEED):
     batch re-sends each earlier cell with probability 1/4 (the StaticFailureDetector behaviour: duplicates).
     Returns a list of T Batches; receivers apply each in their own permuted order (perm seed = seed + 2 + batch)."""
     failed = pick_smallest(n, int(frac * n), seed)
-    base = crash_cells(obs, failed)
+    base = crash_cells(obs, failed, n)
     phase = (splitmix64(np.uint64(seed) ^ base["dst"].astype(np.uint64) ^ (base["ring"].astype(np.uint64) << np.uint64(32)))
              % np.uint64(T)).astype(np.int64)
     blocked = np.zeros(n, np.uint8)

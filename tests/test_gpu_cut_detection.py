@@ -271,3 +271,28 @@ def test_num_proposals_sweep(orc, rb):
     compare_batch(rb, w, sim, cl, None, (src, dst, ring, status))
     for r in (0, 57, n - 1):
         assert cl.getNumProposals(r) == sim.numProposals(r)
+
+
+@pytest.mark.parametrize("permuted", [False, True])
+def test_mixed_receivers_take_the_interval_analysis(orc, rb, permuted):
+    """a proposal is emitted early in the batch, then another subject enters the unstable band and stays there:
+    neither "everything resolved" nor "nothing emitted" — the exact interval analysis must run and agree."""
+    n = 300
+    w, v, sim, cl = _worlds(orc, rb, n, kernel="bucketed", Hh=8, Ll=3)
+    rng = np.random.default_rng(77)
+    seen_mixed = 0
+    for trial in range(12):
+        cl.clear(); sim.reset()
+        a, bsub, c = (int(x) for x in rng.choice(n, size=3, replace=False))
+        cells = [(a, k) for k in range(8)] + [(bsub, k) for k in range(int(rng.integers(3, 7)))]
+        if trial % 2:
+            cells = [(c, k) for k in range(9)] + cells              # two emission points before the blocker
+        if trial % 3 == 0:
+            rng.shuffle(cells)
+        dst = np.array([x[0] for x in cells], np.int32)
+        ring = np.array([x[1] for x in cells], np.uint8)
+        src = np.zeros(len(cells), np.int32)
+        status = np.full(len(cells), DOWN, np.uint8)
+        compare_batch(rb, w, sim, cl, None, (src, dst, ring, status), perm_seed=(1234 + trial) if permuted else None)
+        seen_mixed += cl.debugStats()[0]
+    assert seen_mixed > 0
