@@ -255,19 +255,31 @@ __device__ __forceinline__ void note_unresolved(const ApplyArgs& a, int tile, in
 }
 
 // ---- uniform delivery: every active receiver gets every valid cell in array order -------------------------------------
+// One thread owns 8 consecutive receivers (one 128-bit load + one 128-bit store per subject).  The common case is
+// that all of a thread's ACTIVE receivers hold the same state for the subject (they saw the same history): the
+// visit is computed once, merged into the new word with a SWAR mask, and accumulated in registers ("com").  Only
+// when active neighbours disagree (partitions) do we fall back to a per-receiver visit whose accumulators live in
+// the thread's own slice of the global partial arrays.
+__device__ __forceinline__ void part_store(const Partials& p, size_t at, uint32_t nLH, uint32_t tpUn, uint32_t fl,
+                                           uint32_t mTH, uint32_t mTL, uint64_t h1, uint64_t h2) {
+    p.cnt[at] = make_uint4(nLH, tpUn, fl, 0u);
+    p.minTH[at] = mTH == T32_NONE ? T64_NONE : (uint64_t)mTH;
+    p.minTLun[at] = mTL == T32_NONE ? T64_NONE : (uint64_t)mTL;
+    p.h1[at] = h1;
+    p.h2[at] = h2;
+}
+
 __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a) {
     __shared__ SubjDesc sd[STAGE];
     __shared__ SubjWalk sw[STAGE];
     __shared__ const uint16_t* s_src[STAGE];
     __shared__ uint16_t* s_dst[STAGE];
     __shared__ int s_unres[STAGE];
-    // per-receiver exception accumulators (receivers whose state differs from their 7 neighbours)
-    __shared__ uint32_t e_nLH[TILE_R], e_tpUn[TILE_R], e_fl[TILE_R], e_minTH[TILE_R], e_minTLun[TILE_R];
-    __shared__ uint64_t e_h1[TILE_R], e_h2[TILE_R];
 
     const int tile = blockIdx.x, chunk = blockIdx.y, t = threadIdx.x;
     const int s0 = chunk * a.chunk, s1 = min(a.Sb, s0 + a.chunk);
     const int64_t r0 = (int64_t)tile * TILE_R + (int64_t)t * 8;
+    const size_t pbase = (size_t)chunk * a.Rpad + (size_t)r0;
     const uint32_t RM = (1u << a.K) - 1u;
     const int L = a.L, H = a.H;
 
@@ -279,10 +291,15 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
             const bool on = !(a.rflags[r] & RF_ANNOUNCED) && !((a.dl.flags & RAPID_DELIVERY_BLOCKED) && a.dl.blocked[r]);
             act |= (on ? 1u : 0u) << j;
         }
-        const int li = t * 8 + j;
-        e_nLH[li] = 0; e_tpUn[li] = 0; e_fl[li] = 0; e_minTH[li] = T32_NONE; e_minTLun[li] = T32_NONE; e_h1[li] = 0; e_h2[li] = 0;
     }
-    Acc com;                                              // applies to all 8 receivers of this thread (act == 0xFF only)
+    // SWAR masks: 0xFFFF per active half-word
+    uint32_t am[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) am[q] = (((act >> (2 * q)) & 1u) ? 0x0000FFFFu : 0u) | (((act >> (2 * q + 1)) & 1u) ? 0xFFFF0000u : 0u);
+    const int fa = act ? __ffs(act) - 1 : 0;              // first active receiver of this thread
+    const int fsel = fa >> 1, fsh = (fa & 1) * 16;
+    Acc com;                                              // shared by all ACTIVE receivers of this thread
+    bool had_exc = false;                                 // the thread's global partial slots hold per-receiver extras
 
     for (int base = s0; base < s1; base += STAGE) {
         const int n = min(STAGE, s1 - base);
@@ -310,33 +327,44 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                 const SubjDesc& d = sd[i];
                 uint4 w = W[u];
                 bool unres = false;
-                const bool uniform = act == 0xFFu && w.x == w.y && w.y == w.z && w.z == w.w && (w.x >> 16) == (w.x & 0xFFFFu);
-                if (uniform) {
-                    const uint32_t st = w.x & 0xFFFFu;
-                    const Visit v = visit_uniform(st & RM, d, sw[i], L, H);
-                    unres = accumulate(com, v, d, L, H);
-                    const uint32_t nw = (st | d.bmask) * 0x10001u;
-                    w = make_uint4(nw, nw, nw, nw);
-                } else if (act) {
-                    uint32_t words[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (!((act >> j) & 1u)) continue;
-                        const uint32_t st = (words[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+                if (act) {
+                    const uint32_t wsel = fsel == 0 ? w.x : fsel == 1 ? w.y : fsel == 2 ? w.z : w.w;
+                    const uint32_t st = (wsel >> fsh) & 0xFFFFu;
+                    const uint32_t rep = st * 0x10001u;
+                    const uint32_t diff = ((w.x ^ rep) & am[0]) | ((w.y ^ rep) & am[1]) | ((w.z ^ rep) & am[2]) | ((w.w ^ rep) & am[3]);
+                    if (diff == 0) {                       // all active receivers of the thread agree
                         const Visit v = visit_uniform(st & RM, d, sw[i], L, H);
-                        Acc ex;
-                        const bool un = accumulate(ex, v, d, L, H);
-                        unres |= un;
-                        const int li = t * 8 + j;
-                        e_nLH[li] += ex.nL | (ex.nH << 16);
-                        e_tpUn[li] += ex.tp | (ex.nUn << 16);
-                        e_fl[li] |= ex.flags;
-                        e_minTH[li] = min(e_minTH[li], ex.minTH);
-                        e_minTLun[li] = min(e_minTLun[li], ex.minTLun);
-                        e_h1[li] += ex.h1; e_h2[li] += ex.h2;
-                        words[j >> 1] |= (uint32_t)d.bmask << ((j & 1) * 16);
+                        unres = accumulate(com, v, d, L, H);
+                        const uint32_t nw = (st | d.bmask) * 0x10001u;
+                        w.x = (w.x & ~am[0]) | (nw & am[0]);
+                        w.y = (w.y & ~am[1]) | (nw & am[1]);
+                        w.z = (w.z & ~am[2]) | (nw & am[2]);
+                        w.w = (w.w & ~am[3]) | (nw & am[3]);
+                    } else {
+                        if (!had_exc) {
+                            had_exc = true;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) part_store(a.part, pbase + j, 0u, 0u, 0u, T32_NONE, T32_NONE, 0ull, 0ull);
+                        }
+                        uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (!((act >> j) & 1u)) continue;
+                            const uint32_t sj = (words[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+                            const Visit v = visit_uniform(sj & RM, d, sw[i], L, H);
+                            Acc ex;
+                            unres |= accumulate(ex, v, d, L, H);
+                            const size_t at = pbase + j;
+                            uint4 c = a.part.cnt[at];
+                            c.x += ex.nL | (ex.nH << 16); c.y += ex.tp | (ex.nUn << 16); c.z |= ex.flags;
+                            a.part.cnt[at] = c;
+                            if (ex.minTH != T32_NONE) { const uint64_t o = a.part.minTH[at]; if ((uint64_t)ex.minTH < o) a.part.minTH[at] = ex.minTH; }
+                            if (ex.minTLun != T32_NONE) { const uint64_t o = a.part.minTLun[at]; if ((uint64_t)ex.minTLun < o) a.part.minTLun[at] = ex.minTLun; }
+                            if (ex.nH) { a.part.h1[at] += ex.h1; a.part.h2[at] += ex.h2; }
+                            words[j >> 1] |= (uint32_t)d.bmask << ((j & 1) * 16);
+                        }
+                        w = make_uint4(words[0], words[1], words[2], words[3]);
                     }
-                    w = make_uint4(words[0], words[1], words[2], words[3]);
                 }
                 *reinterpret_cast<uint4*>(s_dst[i] + r0) = w;       // the non-current row becomes the new state
                 if (__any_sync(0xffffffffu, unres) && (t & 31) == 0) s_unres[i] = 1;
@@ -345,23 +373,22 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
         __syncthreads();
         if (t < n && s_unres[t]) note_unresolved(a, tile, sd[t].slot);
     }
-    // partials for this (chunk, tile)
-    const size_t pbase = (size_t)chunk * a.Rpad + (size_t)r0;
-    const bool use_com = act == 0xFFu;
+    // partials of this (chunk, tile): com applies to every active receiver; extras (if any) are already in place
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int li = t * 8 + j;
-        uint32_t nLH = e_nLH[li], tpUn = e_tpUn[li], fl = e_fl[li], mTH = e_minTH[li], mTL = e_minTLun[li];
-        uint64_t h1 = e_h1[li], h2 = e_h2[li];
-        if (use_com) {
-            nLH += com.nL | (com.nH << 16); tpUn += com.tp | (com.nUn << 16); fl |= com.flags;
-            mTH = min(mTH, com.minTH); mTL = min(mTL, com.minTLun); h1 += com.h1; h2 += com.h2;
+        const size_t at = pbase + j;
+        const bool on = (act >> j) & 1u;
+        if (!had_exc) {
+            if (on) part_store(a.part, at, com.nL | (com.nH << 16), com.tp | (com.nUn << 16), com.flags, com.minTH, com.minTLun, com.h1, com.h2);
+            else part_store(a.part, at, 0u, 0u, 0u, T32_NONE, T32_NONE, 0ull, 0ull);
+        } else if (on) {
+            uint4 c = a.part.cnt[at];
+            c.x += com.nL | (com.nH << 16); c.y += com.tp | (com.nUn << 16); c.z |= com.flags;
+            a.part.cnt[at] = c;
+            if (com.minTH != T32_NONE) { const uint64_t o = a.part.minTH[at]; if ((uint64_t)com.minTH < o) a.part.minTH[at] = com.minTH; }
+            if (com.minTLun != T32_NONE) { const uint64_t o = a.part.minTLun[at]; if ((uint64_t)com.minTLun < o) a.part.minTLun[at] = com.minTLun; }
+            a.part.h1[at] += com.h1; a.part.h2[at] += com.h2;
         }
-        a.part.cnt[pbase + j] = make_uint4(nLH, tpUn, fl, 0u);
-        a.part.minTH[pbase + j] = mTH == T32_NONE ? T64_NONE : (uint64_t)mTH;
-        a.part.minTLun[pbase + j] = mTL == T32_NONE ? T64_NONE : (uint64_t)mTL;
-        a.part.h1[pbase + j] = h1;
-        a.part.h2[pbase + j] = h2;
     }
 }
 
