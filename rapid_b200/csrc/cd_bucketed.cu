@@ -29,6 +29,7 @@
 #include <algorithm>
 
 #include "cd_internal.cuh"
+#include "scan.cuh"
 
 namespace rapid {
 
@@ -269,12 +270,23 @@ __device__ __forceinline__ void part_store(const Partials& p, size_t at, uint32_
     p.h2[at] = h2;
 }
 
+// Subjects whose slot was assigned by this very batch ("fresh") have known-zero state for EVERY receiver: nothing is
+// read, the new word is the batch's ring mask under the thread's activity mask, and their contribution to the
+// per-receiver accumulators is the same for every active receiver — it is reduced once per stage by warp 0 and added
+// at the end.  Only carried subjects (reports from earlier batches) take the load / compare / visit path.
+struct StageAcc {
+    uint32_t nLH, tpUn, fl, minTH, minTLun;
+    uint64_t h1, h2;
+};
+
 __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a) {
     __shared__ SubjDesc sd[STAGE];
     __shared__ SubjWalk sw[STAGE];
     __shared__ const uint16_t* s_src[STAGE];
     __shared__ uint16_t* s_dst[STAGE];
+    __shared__ uint32_t s_nw[STAGE];          // (batch ring mask) replicated in both half-words
     __shared__ int s_unres[STAGE];
+    __shared__ StageAcc s_facc;               // fresh-subject accumulators of this block's chunk (same for every receiver)
 
     const int tile = blockIdx.x, chunk = blockIdx.y, t = threadIdx.x;
     const int s0 = chunk * a.chunk, s1 = min(a.Sb, s0 + a.chunk);
@@ -296,82 +308,116 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
     uint32_t am[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) am[q] = (((act >> (2 * q)) & 1u) ? 0x0000FFFFu : 0u) | (((act >> (2 * q + 1)) & 1u) ? 0xFFFF0000u : 0u);
-    const int fa = act ? __ffs(act) - 1 : 0;              // first active receiver of this thread
-    const int fsel = fa >> 1, fsh = (fa & 1) * 16;
-    Acc com;                                              // shared by all ACTIVE receivers of this thread
+    if (t == 0) { s_facc.nLH = 0; s_facc.tpUn = 0; s_facc.fl = 0; s_facc.minTH = T32_NONE; s_facc.minTLun = T32_NONE; s_facc.h1 = 0; s_facc.h2 = 0; }
+    const int block_active = __syncthreads_or(act != 0);
+    Acc com;                                              // carried subjects: shared by all ACTIVE receivers of this thread
     bool had_exc = false;                                 // the thread's global partial slots hold per-receiver extras
 
     for (int base = s0; base < s1; base += STAGE) {
         const int n = min(STAGE, s1 - base);
         __syncthreads();
-        if (t < n) {
-            const SubjDesc d = a.desc[base + t];
-            sd[t] = d;
-            sw[t] = a.walk[base + t];
-            const uint8_t c = a.cur[d.slot];
-            s_src[t] = d.slot >= a.S_before ? nullptr : a.masks + ((size_t)d.slot * 2 + c) * a.Rpad;
-            s_dst[t] = a.masks + ((size_t)d.slot * 2 + (c ^ 1)) * a.Rpad;
-            s_unres[t] = 0;
-        }
-        __syncthreads();
-        for (int i0 = 0; i0 < n; i0 += 4) {
-            uint4 W[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i0 + u < n)
-                    W[u] = s_src[i0 + u] ? *reinterpret_cast<const uint4*>(s_src[i0 + u] + r0) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u;
-                if (i >= n) break;
-                const SubjDesc& d = sd[i];
-                uint4 w = W[u];
-                bool unres = false;
-                if (act) {
-                    const uint32_t wsel = fsel == 0 ? w.x : fsel == 1 ? w.y : fsel == 2 ? w.z : w.w;
-                    const uint32_t st = (wsel >> fsh) & 0xFFFFu;
-                    const uint32_t rep = st * 0x10001u;
-                    const uint32_t diff = ((w.x ^ rep) & am[0]) | ((w.y ^ rep) & am[1]) | ((w.z ^ rep) & am[2]) | ((w.w ^ rep) & am[3]);
-                    if (diff == 0) {                       // all active receivers of the thread agree
-                        const Visit v = visit_uniform(st & RM, d, sw[i], L, H);
-                        unres = accumulate(com, v, d, L, H);
-                        const uint32_t nw = (st | d.bmask) * 0x10001u;
-                        w.x = (w.x & ~am[0]) | (nw & am[0]);
-                        w.y = (w.y & ~am[1]) | (nw & am[1]);
-                        w.z = (w.z & ~am[2]) | (nw & am[2]);
-                        w.w = (w.w & ~am[3]) | (nw & am[3]);
-                    } else {
-                        if (!had_exc) {
-                            had_exc = true;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) part_store(a.part, pbase + j, 0u, 0u, 0u, T32_NONE, T32_NONE, 0ull, 0ull);
-                        }
-                        uint32_t words[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (!((act >> j) & 1u)) continue;
-                            const uint32_t sj = (words[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-                            const Visit v = visit_uniform(sj & RM, d, sw[i], L, H);
-                            Acc ex;
-                            unres |= accumulate(ex, v, d, L, H);
-                            const size_t at = pbase + j;
-                            uint4 c = a.part.cnt[at];
-                            c.x += ex.nL | (ex.nH << 16); c.y += ex.tp | (ex.nUn << 16); c.z |= ex.flags;
-                            a.part.cnt[at] = c;
-                            if (ex.minTH != T32_NONE) { const uint64_t o = a.part.minTH[at]; if ((uint64_t)ex.minTH < o) a.part.minTH[at] = ex.minTH; }
-                            if (ex.minTLun != T32_NONE) { const uint64_t o = a.part.minTLun[at]; if ((uint64_t)ex.minTLun < o) a.part.minTLun[at] = ex.minTLun; }
-                            if (ex.nH) { a.part.h1[at] += ex.h1; a.part.h2[at] += ex.h2; }
-                            words[j >> 1] |= (uint32_t)d.bmask << ((j & 1) * 16);
-                        }
-                        w = make_uint4(words[0], words[1], words[2], words[3]);
-                    }
+        if (t < 32) {                                     // warp 0 stages the descriptors (STAGE == 32)
+            uint32_t nLH = 0, tpUn = 0, mTH = T32_NONE, mTL = T32_NONE;
+            uint64_t h1 = 0, h2 = 0;
+            if (t < n) {
+                const SubjDesc d = a.desc[base + t];
+                sd[t] = d;
+                const uint8_t c = a.cur[d.slot];
+                const bool fresh = d.slot >= a.S_before;
+                s_src[t] = fresh ? nullptr : a.masks + ((size_t)d.slot * 2 + c) * a.Rpad;
+                s_dst[t] = a.masks + ((size_t)d.slot * 2 + (c ^ 1)) * a.Rpad;
+                s_nw[t] = (uint32_t)d.bmask * 0x10001u;
+                int un = 0;
+                if (fresh) {
+                    const int nr = d.nr;
+                    if (nr >= L) nLH += 1u;
+                    if (nr >= H) { nLH += 1u << 16; mTH = d.tHf; h1 = d.mix1; h2 = d.mix2; }
+                    else if (nr >= L) { tpUn += 1u << 16; mTL = d.tLf; un = block_active; }
+                } else {
+                    sw[t] = a.walk[base + t];
                 }
-                *reinterpret_cast<uint4*>(s_dst[i] + r0) = w;       // the non-current row becomes the new state
-                if (__any_sync(0xffffffffu, unres) && (t & 31) == 0) s_unres[i] = 1;
+                s_unres[t] = un;
+            }
+            // warp reduction of the fresh subjects' contribution
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                nLH += __shfl_down_sync(0xffffffffu, nLH, o);
+                tpUn += __shfl_down_sync(0xffffffffu, tpUn, o);
+                mTH = min(mTH, __shfl_down_sync(0xffffffffu, mTH, o));
+                mTL = min(mTL, __shfl_down_sync(0xffffffffu, mTL, o));
+                h1 += __shfl_down_sync(0xffffffffu, h1, o);
+                h2 += __shfl_down_sync(0xffffffffu, h2, o);
+            }
+            if (t == 0) {
+                s_facc.nLH += nLH; s_facc.tpUn += tpUn; s_facc.minTH = min(s_facc.minTH, mTH);
+                s_facc.minTLun = min(s_facc.minTLun, mTL); s_facc.h1 += h1; s_facc.h2 += h2;
             }
         }
         __syncthreads();
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            const uint16_t* src = s_src[i];
+            uint16_t* dst = s_dst[i];
+            const uint32_t nwb = s_nw[i];
+            if (src == nullptr) {                          // fresh subject: write-only
+                *reinterpret_cast<uint4*>(dst + r0) = make_uint4(nwb & am[0], nwb & am[1], nwb & am[2], nwb & am[3]);
+                continue;
+            }
+            uint4 w = *reinterpret_cast<const uint4*>(src + r0);
+            bool unres = false;
+            if (act) {
+                const SubjDesc& d = sd[i];
+                // all active half-words equal  <=>  AND over them == OR over them
+                const uint32_t andw = (w.x | ~am[0]) & (w.y | ~am[1]) & (w.z | ~am[2]) & (w.w | ~am[3]);
+                const uint32_t orw = (w.x & am[0]) | (w.y & am[1]) | (w.z & am[2]) | (w.w & am[3]);
+                const uint32_t andv = andw & (andw >> 16) & 0xFFFFu, st = (orw | (orw >> 16)) & 0xFFFFu;
+                if (andv == st) {
+                    const Visit v = visit_uniform(st & RM, d, sw[i], L, H);
+                    unres = accumulate(com, v, d, L, H);
+                    const uint32_t nw = st * 0x10001u | nwb;
+                    w.x = (w.x & ~am[0]) | (nw & am[0]);
+                    w.y = (w.y & ~am[1]) | (nw & am[1]);
+                    w.z = (w.z & ~am[2]) | (nw & am[2]);
+                    w.w = (w.w & ~am[3]) | (nw & am[3]);
+                } else {
+                    if (!had_exc) {
+                        had_exc = true;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) part_store(a.part, pbase + j, 0u, 0u, 0u, T32_NONE, T32_NONE, 0ull, 0ull);
+                    }
+                    uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (!((act >> j) & 1u)) continue;
+                        const uint32_t sj = (words[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+                        const Visit v = visit_uniform(sj & RM, d, sw[i], L, H);
+                        Acc ex;
+                        unres |= accumulate(ex, v, d, L, H);
+                        const size_t at = pbase + j;
+                        uint4 c = a.part.cnt[at];
+                        c.x += ex.nL | (ex.nH << 16); c.y += ex.tp | (ex.nUn << 16); c.z |= ex.flags;
+                        a.part.cnt[at] = c;
+                        if (ex.minTH != T32_NONE) { const uint64_t o = a.part.minTH[at]; if ((uint64_t)ex.minTH < o) a.part.minTH[at] = ex.minTH; }
+                        if (ex.minTLun != T32_NONE) { const uint64_t o = a.part.minTLun[at]; if ((uint64_t)ex.minTLun < o) a.part.minTLun[at] = ex.minTLun; }
+                        if (ex.nH) { a.part.h1[at] += ex.h1; a.part.h2[at] += ex.h2; }
+                        words[j >> 1] |= (uint32_t)d.bmask << ((j & 1) * 16);
+                    }
+                    w = make_uint4(words[0], words[1], words[2], words[3]);
+                }
+            }
+            *reinterpret_cast<uint4*>(dst + r0) = w;       // the non-current row becomes the new state
+            if (__any_sync(0xffffffffu, unres) && (t & 31) == 0) s_unres[i] = 1;
+        }
+        __syncthreads();
         if (t < n && s_unres[t]) note_unresolved(a, tile, sd[t].slot);
+    }
+    __syncthreads();
+    // fold the block-wide fresh-subject accumulators into the thread's
+    {
+        const StageAcc f = s_facc;
+        com.nL += f.nLH & 0xFFFFu; com.nH += f.nLH >> 16; com.nUn += f.tpUn >> 16;
+        com.minTH = min(com.minTH, f.minTH); com.minTLun = min(com.minTLun, f.minTLun);
+        com.h1 += f.h1; com.h2 += f.h2;
     }
     // partials of this (chunk, tile): com applies to every active receiver; extras (if any) are already in place
 #pragma unroll
@@ -907,7 +953,7 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
         RAPID_CUDA(cub::DeviceRadixSort::SortPairs(cd->cub_tmp.p, tmp_bytes, b->key_in.p, b->key_out.p, b->val_in.p, b->val_out.p, (int)A, 0, 32, s));
         const unsigned gv = (unsigned)ceil_div<int32_t>(n_valid, TB);
         k_heads<<<gv, TB, 0, s>>>(n_valid, b->key_out.p, b->head.p);
-        k_scan_i32<<<1, 1024, 0, s>>>(b->head.p, n_valid);
+        RAPID_CHECK(exclusive_scan_i32(b->head.p, n_valid, cd->scan_sums, nullptr, s, nullptr));
         k_build_desc<<<gv, TB, 0, s>>>(n_valid, b->key_out.p, b->val_out.p, b->head.p, cd->cur_ring_dev, cd->cur_status_dev,
                                        cd->slot_subject.p, cd->L, cd->H, b->desc.p, b->walk.p, b->s_ring.p, b->s_status.p);
         RAPID_KERNEL_CHECK();

@@ -13,6 +13,7 @@
 #include <climits>
 
 #include "cd_internal.cuh"
+#include "scan.cuh"
 
 namespace rapid {
 
@@ -340,7 +341,7 @@ static int32_t preprocess(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev
         k_filter_first<<<g, TB, 0, s>>>(A, dst_dev, ring_dev, status_dev, cfg_dev, cfg, cd->raw ? 1 : 0, cd->K, cd->view->n,
                                         cd->view->n + cd->view->nj, cd->slot_of.p, cd->first_idx.p, cd->cell_slot.p, cd->counts.p);
         k_mark_new<<<g, TB, 0, s>>>(A, dst_dev, cd->cell_slot.p, cd->slot_of.p, cd->first_idx.p, cd->scan_tmp.p);
-        k_exclusive_scan<<<1, 1024, 0, s>>>(cd->scan_tmp.p, A, cd->scan_tmp.p + A);
+        RAPID_CHECK(exclusive_scan_i32(cd->scan_tmp.p, A, cd->scan_sums, cd->scan_tmp.p + A, s, nullptr));
         k_assign_slots<<<g, TB, 0, s>>>(A, dst_dev, cd->cell_slot.p, cd->scan_tmp.p, cd->scan_tmp.p + A, cd->S, cd->slot_of.p,
                                         cd->first_idx.p, cd->slot_subject.p, cd->counts.p);
         k_cell_slots<<<g, TB, 0, s>>>(A, dst_dev, cd->slot_of.p, cd->cell_slot.p, cd->touch.p, ++cd->batch_serial, cd->counts.p);

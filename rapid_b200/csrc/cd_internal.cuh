@@ -71,6 +71,7 @@ struct CD {
     const uint8_t* cur_status_dev = nullptr;
     DevBuf<int32_t> cell_slot;        // [A] slot or -1
     DevBuf<int32_t> scan_tmp;         // [A]
+    DevBuf<int32_t> scan_sums;        // tile totals of the prefix sums
     DevBuf<BatchCounts> counts;       // [1]
     PinnedBuf<BatchCounts> h_counts;
     DevBuf<uint8_t> cub_tmp;

@@ -13,6 +13,7 @@
 #include <climits>
 
 #include "cd_internal.cuh"
+#include "scan.cuh"
 
 namespace rapid {
 
@@ -36,7 +37,7 @@ struct FP {
     DevBuf<int32_t> seen;                 // [sender_cap] INT_MAX = not voted, -1 = voted, else first index in the call
     DevBuf<int32_t> t_state, t_len, t_count, t_call;
     DevBuf<uint64_t> t_h1, t_h2;
-    DevBuf<int32_t> ent, scan;            // per-vote scratch
+    DevBuf<int32_t> ent, scan, scan_sums; // per-vote scratch
     DevBuf<FPState> st;
     PinnedBuf<FPState> h_st;
     // staging for host-array votes
@@ -243,19 +244,42 @@ __global__ void k_fp_pick(int64_t n, const int32_t* __restrict__ ent, FPState* _
 __global__ void k_fp_apply(int64_t n, const int32_t* __restrict__ sender, const int32_t* __restrict__ ent,
                            const FPState* __restrict__ stc, int use_istar, int32_t* __restrict__ seen,
                            int32_t* __restrict__ t_count, FPState* __restrict__ st) {
+    // counts are aggregated warp -> block (a handful of distinct proposals per block) -> one global atomic per
+    // (block, proposal): a million votes for one proposal would otherwise serialise on a single L2 address
+    __shared__ int32_t s_key[16], s_val[16], s_recv;
+    if (threadIdx.x < 16) { s_key[threadIdx.x] = -1; s_val[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) s_recv = 0;
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int32_t e = ent[i];
-    if (e < 0) return;
     const int64_t limit = use_istar ? (int64_t)stc->i_star : n - 1;
-    const int32_t s = sender[i];
-    if (i <= limit) {
-        seen[s] = -1;                                        // votesReceived.add(sender) :141
-        atomicAdd(&t_count[e], 1);                           // :142-144
-        atomicAdd(&st->votes_received, 1);
-    } else {
-        seen[s] = INT_MAX;                                   // arrived after the decision: ignored entirely (:138)
+    int32_t e = -1;
+    bool counted = false;
+    if (i < n) {
+        e = ent[i];
+        if (e >= 0) {
+            const int32_t s = sender[i];
+            if (i <= limit) { seen[s] = -1; counted = true; }    // votesReceived.add(sender) :141
+            else seen[s] = INT_MAX;                              // arrived after the decision: ignored entirely (:138)
+        }
     }
+    const unsigned m = __ballot_sync(0xffffffffu, counted);
+    if (counted) {
+        const unsigned same = __match_any_sync(m, e);
+        if ((int)(threadIdx.x & 31) == __ffs(same) - 1) {
+            const int c = __popc(same);
+            int slot = -1;
+            for (int q = 0; q < 16; ++q) {
+                const int32_t k = atomicCAS(&s_key[q], -1, e);
+                if (k == -1 || k == e) { slot = q; break; }
+            }
+            if (slot >= 0) atomicAdd(&s_val[slot], c);
+            else atomicAdd(&t_count[e], c);                      // more than 16 distinct proposals in one block
+        }
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_recv, __popc(m));
+    __syncthreads();
+    if (threadIdx.x < 16 && s_key[threadIdx.x] >= 0) atomicAdd(&t_count[s_key[threadIdx.x]], s_val[threadIdx.x]);   // :142-144
+    if (threadIdx.x == 0 && s_recv) atomicAdd(&st->votes_received, s_recv);
 }
 
 __global__ void k_fp_zero_call(uint32_t T, int32_t* __restrict__ t_call) {
@@ -358,7 +382,7 @@ static int32_t tally_device(FP* fp, int64_t n, const int32_t* sender, const int6
         for (int c = 0; c < st.n_cand; ++c) {
             const int32_t e = st.cand[c];
             k_fp_flag<<<g, TB, 0, s>>>(n, fp->ent.p, e, fp->scan.p);
-            k_fp_scan<<<1, 1024, 0, s>>>(fp->scan.p, n);
+            RAPID_CHECK(exclusive_scan_i32(fp->scan.p, n, fp->scan_sums, nullptr, s, nullptr));
             k_fp_find<<<g, TB, 0, s>>>(n, fp->ent.p, fp->scan.p, e, fp->t_count.p, (int32_t)fp->Q, fp->st.p);
             fp->last_launches += 3;
         }
