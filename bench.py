@@ -219,7 +219,7 @@ def run_reference(args):
         "cpu_baseline": d,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -267,7 +267,7 @@ def run_ours(args):
     R = (rank + 1) * n // G - begin
     blocked = W.blocked_by_receiver(b.blocked, ring0, begin, R)
     cl = rb.VirtualCluster(view, H, L, n_receivers=R, receiver_begin=begin, kernel=args.kernel, max_subjects=S + 64)
-    fp = rb.FastPaxos(cfg, n, sender_capacity=n)
+    fp = rb.FastPaxos(cfg, n, sender_capacity=n, device=local)
     comm = None
     if G > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -382,13 +382,28 @@ def run_ours(args):
                 line["cpu_baseline"] = d
             except Exception as e:       # the baseline is a reported extra; never lose the GPU line over it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if G > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """the ONE JSON line, on the real stdout"""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
     args = parse()
+    # Libraries print to stdout behind our back (NCCL's "NCCL version ..." banner): keep the real stdout for the JSON
+    # line only and point fd 1 at stderr for everything else.
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -91,6 +91,7 @@ struct Bucketed {
     DevBuf<uint32_t> iv_fl;
     int n_tiles = 0;
     size_t part_cap = 0;
+    int slots_uniform = 0, slots_generic = 0;   // resident blocks of the apply kernels on this device
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -960,10 +961,27 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
         cd->last_launches += 6;   // sort keys, radix sort (counted once), heads, scan, descriptors
         // ---- grid: tiles x subject chunks, a few waves of 148 SMs -----------------------------------------------------
         const int rblocks = uniform ? b->n_tiles : (int)(cd->Rpad / GEN_THREADS);
-        const int target = 148 * 8;
-        n_chunks = std::max(1, std::min(Sb, ceil_div(target, rblocks)));
-        chunk = ceil_div(Sb, n_chunks);
-        n_chunks = ceil_div(Sb, chunk);
+        // Pick the number of subject chunks so that (tiles x chunks) blocks fill whole waves of resident blocks:
+        // a bandwidth-bound grid whose last wave is mostly empty pays almost a full wave for it.  More chunks also
+        // mean more per-receiver partials (48 B each), so cap them at ~8 % of the mask traffic.
+        if (b->slots_uniform == 0) {
+            int dev = 0, sms = 148, per_u = 8, per_g = 4;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_u, k_apply_uniform, UNI_THREADS, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_g, k_apply_generic, GEN_THREADS, 0);
+            b->slots_uniform = sms * std::max(per_u, 1);
+            b->slots_generic = sms * std::max(per_g, 1);
+        }
+        const int slots = uniform ? b->slots_uniform : b->slots_generic;
+        const int cmax = std::max(1, std::min(Sb, std::max(Sb / 300, ceil_div(slots, rblocks))));
+        double best = -1.0;
+        for (int c = 1; c <= cmax; ++c) {
+            const int ch = ceil_div(Sb, c), cc = ceil_div(Sb, ch);
+            const double w = (double)rblocks * cc / slots;
+            const double eff = w / std::ceil(w) + 1e-4 * std::min(w, 8.0);     // tie-break: a few more waves
+            if (eff > best) { best = eff; n_chunks = cc; chunk = ch; }
+        }
     }
     const size_t pn = (size_t)n_chunks * cd->Rpad;
     RAPID_CHECK(b->p_cnt.reserve(pn)); RAPID_CHECK(b->p_minTH.reserve(pn)); RAPID_CHECK(b->p_minTLun.reserve(pn));
