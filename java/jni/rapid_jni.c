@@ -1,0 +1,245 @@
+/*
+ * JNI glue between com.vrg.rapid.gpu.Native and librapid_b200.so (include/rapid_b200.h).
+ *
+ * NOT compiled in this repository's build image: there is no JDK (no jni.h).  Where one exists:
+ *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../include rapid_jni.c \
+ *       -L../../rapid_b200 -lrapid_b200 -o librapid_jni.so
+ * Every native is a thin pass-through: pin / copy the Java arrays, call the C entry point, release.  Handles travel
+ * as jlong.  No JNI exception is raised here: the Java side checks the status code and asks lastError().
+ */
+#include <jni.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "rapid_b200.h"
+
+#define H(type, h) ((type*)(intptr_t)(h))
+#define BUF(env, b) ((b) ? (*(env))->GetDirectBufferAddress((env), (b)) : NULL)
+
+JNIEXPORT jstring JNICALL Java_com_vrg_rapid_gpu_Native_lastError(JNIEnv* env, jclass c) {
+    char buf[512];
+    rapid_last_error(buf, sizeof(buf));
+    return (*env)->NewStringUTF(env, buf);
+}
+
+/* ---------------------------------------------------------------- MembershipView */
+JNIEXPORT jlong JNICALL Java_com_vrg_rapid_gpu_Native_viewCreate(JNIEnv* env, jclass c, jint k, jlong n, jbyteArray hostBytes,
+                                                                 jintArray hostOff, jintArray port, jint device) {
+    jbyte* hb = (*env)->GetByteArrayElements(env, hostBytes, NULL);
+    jint* ho = (*env)->GetIntArrayElements(env, hostOff, NULL);
+    jint* po = (*env)->GetIntArrayElements(env, port, NULL);
+    rapid_view* v = NULL;
+    const int32_t rc = rapid_view_create(&v, k, n, (const uint8_t*)hb, (const int32_t*)ho, (const int32_t*)po, device);
+    (*env)->ReleaseByteArrayElements(env, hostBytes, hb, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, hostOff, ho, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, port, po, JNI_ABORT);
+    return rc == RAPID_OK ? (jlong)(intptr_t)v : 0;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_viewDestroy(JNIEnv* env, jclass c, jlong view) {
+    return rapid_view_destroy(H(rapid_view, view));
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_viewRing(JNIEnv* env, jclass c, jlong view, jint ring, jintArray out) {
+    jint* o = (*env)->GetIntArrayElements(env, out, NULL);
+    const int32_t rc = rapid_view_ring(H(rapid_view, view), ring, (int32_t*)o);
+    (*env)->ReleaseIntArrayElements(env, out, o, 0);
+    return rc;
+}
+
+static jint row_call(JNIEnv* env, jlong view, jint node, jintArray out, int observers) {
+    jint* o = (*env)->GetIntArrayElements(env, out, NULL);
+    int32_t cnt = 0;
+    const int32_t rc = observers ? rapid_view_observers(H(rapid_view, view), node, (int32_t*)o, &cnt)
+                                 : rapid_view_subjects(H(rapid_view, view), node, (int32_t*)o, &cnt);
+    (*env)->ReleaseIntArrayElements(env, out, o, 0);
+    return rc == RAPID_OK ? cnt : rc;        /* RAPID_ENOT_IN_RING -> NodeNotInRingException on the Java side */
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_viewObservers(JNIEnv* env, jclass c, jlong view, jint node, jintArray out) {
+    return row_call(env, view, node, out, 1);
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_viewSubjects(JNIEnv* env, jclass c, jlong view, jint node, jintArray out) {
+    return row_call(env, view, node, out, 0);
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_viewExpectedObservers(JNIEnv* env, jclass c, jlong view, jbyteArray host,
+                                                                           jint port, jintArray out) {
+    const jsize len = (*env)->GetArrayLength(env, host);
+    jbyte* h = (*env)->GetByteArrayElements(env, host, NULL);
+    jint* o = (*env)->GetIntArrayElements(env, out, NULL);
+    int32_t cnt = 0;
+    const int32_t rc = rapid_view_expected_observers(H(rapid_view, view), (const uint8_t*)h, len, port, (int32_t*)o, &cnt);
+    (*env)->ReleaseByteArrayElements(env, host, h, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, out, o, 0);
+    return rc == RAPID_OK ? cnt : rc;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_viewRingNumbers(JNIEnv* env, jclass c, jlong view, jint observer, jint subject) {
+    uint16_t m = 0;
+    const int32_t rc = rapid_view_ring_numbers(H(rapid_view, view), observer, subject, &m);
+    return rc == RAPID_OK ? (jint)m : rc;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_viewConfigId(JNIEnv* env, jclass c, jlong view, jlongArray hi, jlongArray lo,
+                                                                  jlongArray out1) {
+    const jsize n = (*env)->GetArrayLength(env, hi);
+    jlong* h = (*env)->GetLongArrayElements(env, hi, NULL);
+    jlong* l = (*env)->GetLongArrayElements(env, lo, NULL);
+    int64_t id = 0;
+    const int32_t rc = rapid_view_config_id(H(rapid_view, view), (const int64_t*)h, (const int64_t*)l, n, &id);
+    (*env)->ReleaseLongArrayElements(env, hi, h, JNI_ABORT);
+    (*env)->ReleaseLongArrayElements(env, lo, l, JNI_ABORT);
+    const jlong v = id;
+    (*env)->SetLongArrayRegion(env, out1, 0, 1, &v);
+    return rc;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_viewRegisterJoiners(JNIEnv* env, jclass c, jlong view, jbyteArray hostBytes,
+                                                                         jintArray hostOff, jintArray port) {
+    const jsize n = (*env)->GetArrayLength(env, port);
+    jbyte* hb = (*env)->GetByteArrayElements(env, hostBytes, NULL);
+    jint* ho = (*env)->GetIntArrayElements(env, hostOff, NULL);
+    jint* po = (*env)->GetIntArrayElements(env, port, NULL);
+    int32_t first = 0;
+    const int32_t rc = rapid_view_register_joiners(H(rapid_view, view), n, (const uint8_t*)hb, (const int32_t*)ho,
+                                                   (const int32_t*)po, &first);
+    (*env)->ReleaseByteArrayElements(env, hostBytes, hb, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, hostOff, ho, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, port, po, JNI_ABORT);
+    return rc == RAPID_OK ? first : rc;
+}
+
+/* ---------------------------------------------------------------- cut detector */
+JNIEXPORT jlong JNICALL Java_com_vrg_rapid_gpu_Native_cdCreate(JNIEnv* env, jclass c, jlong view, jint h, jint l, jlong receivers,
+                                                               jlong begin, jint flags, jlong maxSubjects) {
+    rapid_cd* cd = NULL;
+    const int32_t rc = rapid_cd_create(&cd, H(rapid_view, view), h, l, receivers, begin, (uint32_t)flags, maxSubjects);
+    return rc == RAPID_OK ? (jlong)(intptr_t)cd : 0;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_cdDestroy(JNIEnv* env, jclass c, jlong cd) {
+    return rapid_cd_destroy(H(rapid_cd, cd));
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_cdApplyBatch(JNIEnv* env, jclass c, jlong cd, jlong cfg, jlong n, jobject dst,
+                                                                  jobject ring, jobject status, jobject cellCfg, jint dflags,
+                                                                  jobject blocked, jobject bitmap, jlong permSeed, jobject oh,
+                                                                  jobject oh2, jobject olen, jobject oann) {
+    rapid_delivery d;
+    d.flags = (uint32_t)dflags;
+    d.blocked = (const uint8_t*)BUF(env, blocked);
+    d.bitmap = (const uint32_t*)BUF(env, bitmap);
+    d.perm_seed = (uint64_t)permSeed;
+    return rapid_cd_apply_batch(H(rapid_cd, cd), cfg, n, NULL, (const int32_t*)BUF(env, dst), (const uint8_t*)BUF(env, ring),
+                                (const uint8_t*)BUF(env, status), (const int64_t*)BUF(env, cellCfg), dflags ? &d : NULL,
+                                (uint64_t*)BUF(env, oh), (uint64_t*)BUF(env, oh2), (int32_t*)BUF(env, olen), (uint8_t*)BUF(env, oann));
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_cdGetProposal(JNIEnv* env, jclass c, jlong cd, jlong receiver, jintArray out) {
+    const jsize cap = (*env)->GetArrayLength(env, out);
+    jint* o = (*env)->GetIntArrayElements(env, out, NULL);
+    int32_t len = 0;
+    const int32_t rc = rapid_cd_get_proposal(H(rapid_cd, cd), receiver, (int32_t*)o, cap, &len);
+    (*env)->ReleaseIntArrayElements(env, out, o, 0);
+    return rc == RAPID_OK ? len : rc;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_cdAggregate(JNIEnv* env, jclass c, jlong cd, jintArray dst, jbyteArray ring,
+                                                                 jbyteArray status, jlong receiver, jintArray out) {
+    const jsize n = (*env)->GetArrayLength(env, dst), cap = (*env)->GetArrayLength(env, out);
+    jint* d = (*env)->GetIntArrayElements(env, dst, NULL);
+    jbyte* r = (*env)->GetByteArrayElements(env, ring, NULL);
+    jbyte* s = (*env)->GetByteArrayElements(env, status, NULL);
+    jint* o = (*env)->GetIntArrayElements(env, out, NULL);
+    int32_t len = 0;
+    const int32_t rc = rapid_cd_aggregate(H(rapid_cd, cd), n, NULL, (const int32_t*)d, (const uint8_t*)r, (const uint8_t*)s,
+                                          receiver, (int32_t*)o, cap, &len);
+    (*env)->ReleaseIntArrayElements(env, dst, d, JNI_ABORT);
+    (*env)->ReleaseByteArrayElements(env, ring, r, JNI_ABORT);
+    (*env)->ReleaseByteArrayElements(env, status, s, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, out, o, 0);
+    return rc == RAPID_OK ? len : rc;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_cdInvalidate(JNIEnv* env, jclass c, jlong cd, jlong receiver, jintArray out) {
+    const jsize cap = (*env)->GetArrayLength(env, out);
+    jint* o = (*env)->GetIntArrayElements(env, out, NULL);
+    int32_t len = 0;
+    const int32_t rc = rapid_cd_invalidate(H(rapid_cd, cd), receiver, (int32_t*)o, cap, &len);
+    (*env)->ReleaseIntArrayElements(env, out, o, 0);
+    return rc == RAPID_OK ? len : rc;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_cdNumProposals(JNIEnv* env, jclass c, jlong cd, jlong receiver) {
+    int32_t n = 0;
+    const int32_t rc = rapid_cd_num_proposals(H(rapid_cd, cd), receiver, &n);
+    return rc == RAPID_OK ? n : rc;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_cdClear(JNIEnv* env, jclass c, jlong cd) {
+    return rapid_cd_clear(H(rapid_cd, cd));
+}
+
+/* ---------------------------------------------------------------- FastPaxos fast round */
+JNIEXPORT jlong JNICALL Java_com_vrg_rapid_gpu_Native_fpCreate(JNIEnv* env, jclass c, jlong cfg, jlong size, jlong cap, jint device) {
+    rapid_fp* fp = NULL;
+    const int32_t rc = rapid_fp_create(&fp, cfg, size, cap, device);
+    return rc == RAPID_OK ? (jlong)(intptr_t)fp : 0;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_fpDestroy(JNIEnv* env, jclass c, jlong fp) {
+    return rapid_fp_destroy(H(rapid_fp, fp));
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_fpReset(JNIEnv* env, jclass c, jlong fp, jlong cfg, jlong size) {
+    return rapid_fp_reset(H(rapid_fp, fp), cfg, size);
+}
+
+static void put_result(JNIEnv* env, jlongArray out6, int32_t decided, uint64_t h1, uint64_t h2, int32_t len, int32_t count, int32_t recv) {
+    const jlong v[6] = {decided, (jlong)h1, (jlong)h2, len, count, recv};
+    (*env)->SetLongArrayRegion(env, out6, 0, 6, v);
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_fpTally(JNIEnv* env, jclass c, jlong fp, jintArray sender, jlongArray voteCfg,
+                                                             jlongArray hash, jlongArray hash2, jintArray len, jlongArray out6) {
+    const jsize n = (*env)->GetArrayLength(env, sender);
+    jint* s = (*env)->GetIntArrayElements(env, sender, NULL);
+    jlong* vc = voteCfg ? (*env)->GetLongArrayElements(env, voteCfg, NULL) : NULL;
+    jlong* h1 = (*env)->GetLongArrayElements(env, hash, NULL);
+    jlong* h2 = hash2 ? (*env)->GetLongArrayElements(env, hash2, NULL) : NULL;
+    jint* ln = len ? (*env)->GetIntArrayElements(env, len, NULL) : NULL;
+    int32_t decided = 0, dlen = 0, dcount = 0, recv = 0;
+    uint64_t a = 0, b = 0;
+    const int32_t rc = rapid_fp_tally(H(rapid_fp, fp), n, (const int32_t*)s, (const int64_t*)vc, (const uint64_t*)h1,
+                                      (const uint64_t*)h2, (const int32_t*)ln, &decided, &a, &b, &dlen, &dcount, &recv);
+    (*env)->ReleaseIntArrayElements(env, sender, s, JNI_ABORT);
+    if (vc) (*env)->ReleaseLongArrayElements(env, voteCfg, vc, JNI_ABORT);
+    (*env)->ReleaseLongArrayElements(env, hash, h1, JNI_ABORT);
+    if (h2) (*env)->ReleaseLongArrayElements(env, hash2, h2, JNI_ABORT);
+    if (ln) (*env)->ReleaseIntArrayElements(env, len, ln, JNI_ABORT);
+    put_result(env, out6, decided, a, b, dlen, dcount, recv);
+    return rc;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_fpTallyCd(JNIEnv* env, jclass c, jlong fp, jlong cd, jlong comm, jlongArray out6) {
+    int32_t decided = 0, dlen = 0, dcount = 0, recv = 0;
+    uint64_t a = 0, b = 0;
+    const int32_t rc = rapid_fp_tally_cd(H(rapid_fp, fp), H(rapid_cd, cd), H(rapid_comm, comm), &decided, &a, &b, &dlen, &dcount, &recv);
+    put_result(env, out6, decided, a, b, dlen, dcount, recv);
+    return rc;
+}
+
+JNIEXPORT jlongArray JNICALL Java_com_vrg_rapid_gpu_Native_proposalFingerprint(JNIEnv* env, jclass c, jintArray ids) {
+    const jsize n = (*env)->GetArrayLength(env, ids);
+    jint* p = (*env)->GetIntArrayElements(env, ids, NULL);
+    uint64_t h1 = 0, h2 = 0;
+    rapid_proposal_fingerprint((const int32_t*)p, n, &h1, &h2);
+    (*env)->ReleaseIntArrayElements(env, ids, p, JNI_ABORT);
+    jlongArray out = (*env)->NewLongArray(env, 2);
+    const jlong v[2] = {(jlong)h1, (jlong)h2};
+    (*env)->SetLongArrayRegion(env, out, 0, 2, v);
+    return out;
+}

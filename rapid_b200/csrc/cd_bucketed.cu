@@ -978,8 +978,13 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
         double best = -1.0;
         for (int c = 1; c <= cmax; ++c) {
             const int ch = ceil_div(Sb, c), cc = ceil_div(Sb, ch);
+            // cost model (fitted to measurements on B200): a bandwidth-bound wave needs about half of the resident
+            // slots busy to saturate HBM, so a tail wave of fraction f costs max(f, 0.5) of a full wave; every extra
+            // chunk costs ~1 % (block prologue / per-receiver partials).
             const double w = (double)rblocks * cc / slots;
-            const double eff = w / std::ceil(w) + 1e-4 * std::min(w, 8.0);     // tie-break: a few more waves
+            const double f = w - std::floor(w);
+            const double t = std::floor(w) + (f > 0 ? std::max(f, 0.5) : 0.0);
+            const double eff = w / t - 0.01 * cc;
             if (eff > best) { best = eff; n_chunks = cc; chunk = ch; }
         }
     }

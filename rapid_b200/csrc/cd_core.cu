@@ -300,8 +300,8 @@ static int32_t ensure_id_capacity(CD* cd) {
 
 static int32_t ensure_slot_capacity(CD* cd, size_t need) {
     if (need <= cd->S_cap) return RAPID_OK;
-    size_t ncap = std::max<size_t>(cd->S_cap, 16);
-    while (ncap < need) ncap *= 2;
+    size_t ncap = need;                       // first allocation: exactly what was asked for (max_subjects)
+    if (cd->S_cap) { ncap = cd->S_cap; while (ncap < need) ncap *= 2; }
     const size_t row = cd->Rpad * (size_t)cd->nbuf;
     const size_t old_elems = cd->S_cap * row;
     // DevBuf::reserve(keep) rounds to a power of two of elements; force the exact size instead
