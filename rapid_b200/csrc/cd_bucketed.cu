@@ -40,9 +40,12 @@ constexpr int STAGE = 32;             // batch subjects staged in shared memory 
 constexpr int MAXK = RAPID_MAX_K;
 constexpr uint32_t T32_NONE = 0xFFFFFFFFu;
 constexpr uint64_t T64_NONE = ~0ULL;
-constexpr int MIXED_BLOCKS = 64;
 constexpr uint32_t RF_K3 = 16u;       // receiver enters the invalidation pass of the batch in flight
 constexpr uint32_t RF_ACTIVE = 32u;   // receiver processed the batch in flight
+constexpr uint32_t RF_MIXED_EMIT = 64u;   // announced a proposal found by the interval analysis: "emitted" == t_H <= estar[r]
+
+// per-receiver state of the interval analysis (MIXED receivers)
+constexpr uint32_t MX_ON = 1u, MX_NEG = 2u, MX_HAS_E = 4u, MX_DONE = 8u;
 
 // partial-accumulator flags
 constexpr uint32_t PF_SEEN = 1u;      // a valid DOWN cell was delivered
@@ -80,15 +83,21 @@ struct Bucketed {
     DevBuf<uint8_t> s_ring, s_status;         // per sorted cell
     DevBuf<uint4> p_cnt;
     DevBuf<uint64_t> p_minTH, p_minTLun, p_h1, p_h2;
-    DevBuf<int32_t> mixed_list;
+    DevBuf<uint32_t> mx_fl;                   // [Rpad] MX_* flags
+    DevBuf<uint64_t> mx_a, mx_cand, mx_emax;  // [Rpad] start of the never-closing component / its next candidate / e* candidate
+    DevBuf<uint64_t> mx_p1, mx_p2;            // [Rpad] fingerprint of `proposal` before the batch
+    DevBuf<int32_t> mx_pc;
+    DevBuf<unsigned long long> mx_e1, mx_e2;  // [Rpad] fingerprint of the batch subjects emitted explicitly
+    DevBuf<int32_t> mx_ec;
+    DevBuf<uint64_t> estar;                   // [Rpad] last explicit emission moment of RF_MIXED_EMIT receivers
+    DevBuf<int32_t> mx_changed;               // [1]
+    DevBuf<int32_t> batch_index;              // [slot] -> index of the subject in the batch in flight
     DevBuf<int32_t> k3_res;
     DevBuf<unsigned long long> k3_h1, k3_h2;
     DevBuf<int2> pre_pairs;
     DevBuf<int32_t> pre_count;
     DevBuf<int32_t> in_list;                  // [slot][n_tiles]
     size_t in_list_slots = 0;
-    DevBuf<uint64_t> iv_tL, iv_tH;            // [MIXED_BLOCKS][Sb]
-    DevBuf<uint32_t> iv_fl;
     int n_tiles = 0;
     size_t part_cap = 0;
     int slots_uniform = 0, slots_generic = 0;   // resident blocks of the apply kernels on this device
@@ -135,7 +144,7 @@ __global__ void k_build_desc(int32_t n_valid, const uint32_t* __restrict__ key, 
                              const int32_t* __restrict__ head_excl, const uint8_t* __restrict__ ring,
                              const uint8_t* __restrict__ status, const int32_t* __restrict__ slot_subject, int L, int H,
                              SubjDesc* __restrict__ desc, SubjWalk* __restrict__ walk, uint8_t* __restrict__ s_ring,
-                             uint8_t* __restrict__ s_status) {
+                             uint8_t* __restrict__ s_status, int32_t* __restrict__ batch_index) {
     const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_valid) return;
     const int32_t ci = sidx[j];
@@ -171,6 +180,7 @@ __global__ void k_build_desc(int32_t n_valid, const uint32_t* __restrict__ key, 
     d.pad_ = 0;
     desc[b] = d;
     walk[b] = w;
+    batch_index[d.slot] = b;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -577,13 +587,20 @@ struct FinArgs {
     uint64_t* out_h1;
     uint64_t* out_h2;
     int32_t* out_len;
-    int32_t* mixed_list;
+    uint32_t* mx_fl;
+    uint64_t* mx_a;
+    uint64_t* mx_cand;
+    uint64_t* mx_emax;
+    uint64_t* mx_p1;
+    uint64_t* mx_p2;
+    int32_t* mx_pc;
     BatchCounts* bc;
 };
 
 __global__ void k_finalize1(const FinArgs a) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.R) return;
+    a.mx_fl[r] = 0;
     uint32_t flags = a.rflags[r] & ~(RF_ANN_NOW | RF_K3 | RF_ACTIVE);
     a.out_h1[r] = 0; a.out_h2[r] = 0; a.out_len[r] = 0;
     const bool active = !(flags & RF_ANNOUNCED) && !((a.dl.flags & RAPID_DELIVERY_BLOCKED) && a.dl.blocked[r]);
@@ -615,8 +632,11 @@ __global__ void k_finalize1(const FinArgs a) {
         flags |= RF_ANNOUNCED | RF_ANN_NOW | RF_RULE_GE_H;
     } else if (nH > 0 && !(untouched_pre > 0 || (fl & PF_NEGINF) || (haveTL && minTLun < minTH))) {
         // MIXED: some proposals may have been emitted before the unresolved subjects entered the band
-        const int32_t at = atomicAdd(&a.bc->n_mixed, 1);
-        a.mixed_list[at] = (int32_t)r;
+        // (haveTL holds here: npre_new > 0 and every unresolved subject entered the band inside the batch)
+        atomicAdd(&a.bc->n_mixed, 1);
+        a.mx_fl[r] = MX_ON;
+        a.mx_a[r] = minTLun; a.mx_cand[r] = T64_NONE; a.mx_emax[r] = 0;
+        a.mx_p1[r] = a.pend_h1[r]; a.mx_p2[r] = a.pend_h2[r]; a.mx_pc[r] = a.pend_cnt[r];
     }
     if (npre_new > 0 && (flags & RF_SEEN_DOWN)) flags |= RF_K3;
     a.n_pre[r] = npre_new;
@@ -625,20 +645,128 @@ __global__ void k_finalize1(const FinArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// MIXED receivers: exact interval analysis (one block per receiver)
+// MIXED receivers: exact interval analysis as data-parallel passes over (batch subjects x receivers).
+//
+// For one receiver the batch's subjects give intervals [t_L, t_H) (t_L = "before the batch" if the subject started
+// inside the band, t_H = never if it does not reach H).  A proposal is emitted at t_H(s) iff no other interval covers
+// it.  Let a = start of the connected component of intervals that contains the never-closing ones: everything closing
+// after `a` is covered, and e* = the latest closing moment before `a` is the last explicit emission; what left is
+// {t_H <= e*} plus whatever was pending before the batch.  `a` is found as a fixpoint: a <- min{t_L : t_H > a},
+// starting from the earliest never-closing start (k_finalize1).  One FIX pass recomputes every flagged receiver's
+// intervals from the PRE-batch rows (nothing is stored per (subject, receiver)); uniform delivery typically makes
+// every receiver MIXED in the same way, so the passes are shaped like the apply kernels, not like a rare fallback.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t IV_HAS = 1u, IV_NEGINF = 2u, IV_FINITE = 4u, IV_CARRIED = 8u;
-
 struct MixArgs {
     ApplyArgs ap;
-    int32_t S;
-    const int32_t* touch;
-    int32_t serial;
-    const int32_t* mixed_list;
-    const BatchCounts* bc;
-    uint64_t* iv_tL;
-    uint64_t* iv_tH;
-    uint32_t* iv_fl;
+    uint32_t* mx_fl;
+    uint64_t* mx_a;
+    uint64_t* mx_cand;
+    uint64_t* mx_emax;
+    uint64_t* estar;
+    unsigned long long* mx_e1;
+    unsigned long long* mx_e2;
+    int32_t* mx_ec;
+    int uniform;
+};
+
+struct IVisit { int c0; bool crossL, crossH; uint64_t tL, tH; };
+
+__device__ __forceinline__ IVisit interval_visit(const ApplyArgs& a, int uniform, uint32_t ur, const SubjDesc& d, const SubjWalk* w,
+                                                 int64_t r, uint64_t rs) {
+    IVisit o;
+    if (uniform) {
+        const Visit v = visit_uniform(ur, d, *w, a.L, a.H);
+        o.c0 = v.c0; o.crossL = v.crossL; o.crossH = v.crossH; o.tL = v.tL; o.tH = v.tH;
+    } else {
+        const GVisit v = visit_generic(ur, d, a.sidx, a.s_ring, a.s_status, a.dl, r, rs, a.L, a.H);
+        o.c0 = v.c0; o.crossL = v.crossL; o.crossH = v.crossH; o.tL = v.tL; o.tH = v.tH;
+    }
+    return o;
+}
+
+template <int MODE>      // 0: FIX pass (next candidate for `a`, e* candidate)   1: SUM pass (fingerprint of {t_H <= e*})
+__global__ void __launch_bounds__(GEN_THREADS) k_mixed_pass(const MixArgs m) {
+    __shared__ SubjDesc sd[STAGE];
+    __shared__ SubjWalk sw[STAGE];
+    __shared__ const uint16_t* s_old[STAGE];
+    const ApplyArgs& a = m.ap;
+    const int t = threadIdx.x, chunk = blockIdx.y;
+    const int64_t r = (int64_t)blockIdx.x * GEN_THREADS + t;
+    const uint32_t RM = (1u << a.K) - 1u;
+    const int L = a.L, H = a.H;
+    const uint32_t fl = r < a.R ? m.mx_fl[r] : 0u;
+    const bool on = MODE == 0 ? ((fl & MX_ON) && !(fl & MX_DONE)) : ((fl & MX_DONE) && (fl & MX_HAS_E));
+    if (!__syncthreads_or(on ? 1 : 0)) return;
+    const uint64_t ref = on ? (MODE == 0 ? m.mx_a[r] : m.estar[r]) : 0ull;
+    const uint64_t rs = splitmix64(a.dl.perm_seed + (uint64_t)(a.rbegin + r));
+    const int s0 = chunk * a.chunk, s1 = min(a.Sb, s0 + a.chunk);
+    uint64_t cand = T64_NONE, emax = 0, h1 = 0, h2 = 0;
+    bool neg = false, has_e = false;
+    int cnt = 0;
+    for (int base = s0; base < s1; base += STAGE) {
+        const int n = min(STAGE, s1 - base);
+        __syncthreads();
+        if (t < n) {
+            const SubjDesc d = a.desc[base + t];
+            sd[t] = d;
+            const bool fresh = d.slot >= a.S_before;
+            s_old[t] = fresh ? nullptr : a.masks + ((size_t)d.slot * 2 + a.cur[d.slot]) * a.Rpad;   // pre-batch row (not flipped yet)
+            if (!fresh && m.uniform) sw[t] = a.walk[base + t];
+        }
+        __syncthreads();
+        if (!on) continue;
+        for (int i = 0; i < n; ++i) {
+            const SubjDesc& d = sd[i];
+            const uint32_t st = s_old[i] ? s_old[i][r] : 0u;
+            const IVisit v = interval_visit(a, m.uniform, st & RM, d, &sw[i], r, rs);
+            if (MODE == 0) {
+                if (!v.crossH) continue;                                  // never closes, or never in the band
+                const bool starts_in = v.c0 >= L && v.c0 < H;
+                if (v.tH > ref) { if (starts_in) neg = true; else if (v.tL < cand) cand = v.tL; }
+                else if (!has_e || v.tH > emax) { emax = v.tH; has_e = true; }
+            } else {
+                if (v.crossH && v.tH <= ref) { h1 += d.mix1; h2 += d.mix2; ++cnt; }
+            }
+        }
+    }
+    if (!on) return;
+    if (MODE == 0) {
+        if (neg) atomicOr(&m.mx_fl[r], MX_NEG);
+        if (cand != T64_NONE) atomicMin((unsigned long long*)&m.mx_cand[r], (unsigned long long)cand);
+        if (has_e) { atomicMax((unsigned long long*)&m.mx_emax[r], (unsigned long long)emax); atomicOr(&m.mx_fl[r], MX_HAS_E); }
+    } else if (cnt) {
+        atomicAdd(&m.mx_e1[r], (unsigned long long)h1); atomicAdd(&m.mx_e2[r], (unsigned long long)h2); atomicAdd(&m.mx_ec[r], cnt);
+    }
+}
+
+__global__ void k_mixed_update(int64_t R, uint32_t* __restrict__ mx_fl, uint64_t* __restrict__ mx_a, uint64_t* __restrict__ mx_cand,
+                               uint64_t* __restrict__ mx_emax, uint64_t* __restrict__ estar, int32_t* __restrict__ changed) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const uint32_t fl = mx_fl[r];
+    if (!(fl & MX_ON) || (fl & MX_DONE)) return;
+    if (fl & MX_NEG) { mx_fl[r] = 0; return; }              // covered since before the batch: nothing was emitted
+    const uint64_t c = mx_cand[r];
+    if (c < mx_a[r]) {                                       // the component grows leftwards: another pass
+        mx_a[r] = c; mx_cand[r] = T64_NONE; mx_emax[r] = 0; mx_fl[r] = fl & ~MX_HAS_E;
+        atomicAdd(changed, 1);
+    } else if (fl & MX_HAS_E) {
+        estar[r] = mx_emax[r];
+        mx_fl[r] = fl | MX_DONE;
+    } else {
+        mx_fl[r] = 0;                                        // no closing moment before the component: nothing emitted
+    }
+}
+
+struct MixCommitArgs {
+    int64_t R;
+    const uint32_t* mx_fl;
+    const uint64_t* mx_p1;
+    const uint64_t* mx_p2;
+    const int32_t* mx_pc;
+    unsigned long long* mx_e1;
+    unsigned long long* mx_e2;
+    int32_t* mx_ec;
     uint32_t* rflags;
     uint64_t* pend_h1;
     uint64_t* pend_h2;
@@ -648,119 +776,60 @@ struct MixArgs {
     int32_t* out_len;
 };
 
-__device__ __forceinline__ uint64_t block_min_u64(uint64_t v, uint64_t* sm) {
-    for (int o = 16; o > 0; o >>= 1) { const uint64_t x = __shfl_down_sync(0xffffffffu, v, o); v = x < v ? x : v; }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
-    __syncthreads();
-    uint64_t m = sm[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = sm[w] < m ? sm[w] : m;
-    return m;
+__global__ void k_mixed_commit(const MixCommitArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    const uint32_t fl = a.mx_fl[r];
+    if (!((fl & MX_DONE) && (fl & MX_HAS_E))) return;
+    // what left explicitly = everything pending before the batch + the batch subjects that closed by e*
+    const uint64_t o1 = a.mx_p1[r] + a.mx_e1[r], o2 = a.mx_p2[r] + a.mx_e2[r];
+    const int32_t oc = a.mx_pc[r] + a.mx_ec[r];
+    a.out_h1[r] = o1; a.out_h2[r] = o2; a.out_len[r] = oc;
+    a.pend_h1[r] -= o1; a.pend_h2[r] -= o2; a.pend_cnt[r] -= oc;
+    a.mx_e1[r] = 0; a.mx_e2[r] = 0; a.mx_ec[r] = 0;
+    a.rflags[r] = (a.rflags[r] | RF_ANNOUNCED | RF_ANN_NOW | RF_MIXED_EMIT) & ~RF_RULE_GE_H;
 }
 
-__global__ void __launch_bounds__(256) k_resolve_mixed(const MixArgs m) {
-    __shared__ uint64_t red[8];
-    __shared__ unsigned long long s_h1, s_h2;
-    __shared__ int s_cnt;
-    const ApplyArgs& a = m.ap;
+// Did subject slot `s` leave in an explicit proposal of the batch in flight, for an RF_MIXED_EMIT receiver?  Rows have been
+// flipped: the pre-batch row is the non-current one.
+struct EmitCtx {
+    ApplyArgs ap;
+    const int32_t* touch;
+    const int32_t* batch_index;
+    int32_t serial;
+    const uint64_t* estar;
+    int uniform;
+};
+
+__device__ __forceinline__ bool emitted_in_batch(const EmitCtx& e, int32_t s, int64_t r, uint32_t w_new, uint64_t rs) {
+    const ApplyArgs& a = e.ap;
     const uint32_t RM = (1u << a.K) - 1u;
-    const int L = a.L, H = a.H, t = threadIdx.x;
-    const int n_mixed = m.bc->n_mixed;
-    uint64_t* tLs = m.iv_tL + (size_t)blockIdx.x * a.Sb;
-    uint64_t* tHs = m.iv_tH + (size_t)blockIdx.x * a.Sb;
-    uint32_t* fls = m.iv_fl + (size_t)blockIdx.x * a.Sb;
-    for (int mi = blockIdx.x; mi < n_mixed; mi += gridDim.x) {
-        const int64_t r = m.mixed_list[mi];
-        const uint64_t rs = splitmix64(a.dl.perm_seed + (uint64_t)(a.rbegin + r));
-        // intervals [tL, tH) of the batch's subjects, recomputed from the OLD rows
-        uint64_t tinf = T64_NONE;          // earliest start of an interval that never closes
-        bool inf_neg = false;
-        for (int b = t; b < a.Sb; b += blockDim.x) {
-            const SubjDesc d = a.desc[b];
-            const uint32_t st = d.slot >= a.S_before ? 0u : (a.masks + ((size_t)d.slot * 2 + a.cur[d.slot]) * a.Rpad)[r];
-            const GVisit v = visit_generic(st & RM, d, a.sidx, a.s_ring, a.s_status, a.dl, r, rs, L, H);
-            uint32_t f = 0;
-            const bool starts_in = v.c0 >= L && v.c0 < H;
-            if (starts_in || v.crossL) {
-                f |= IV_HAS;
-                if (starts_in) f |= IV_NEGINF;
-                if (v.crossH) f |= IV_FINITE;
-            } else if (v.crossH) f |= IV_HAS | IV_FINITE;          // (L == H cannot reach here: band is empty)
-            if (v.c0 >= H && !(st & CD_BIT_EMIT)) f |= IV_CARRIED;
-            tLs[b] = v.tL; tHs[b] = v.tH; fls[b] = f;
-            if ((f & IV_HAS) && !(f & IV_FINITE)) {
-                if (f & IV_NEGINF) inf_neg = true; else tinf = v.tL < tinf ? v.tL : tinf;
-            }
-        }
-        __syncthreads();
-        int any_neg = __syncthreads_or(inf_neg ? 1 : 0);
-        uint64_t aa = block_min_u64(tinf, red);
-        bool emit = !any_neg;
-        // grow the never-closing component leftwards until nothing that closes after `aa` starts before it
-        while (emit) {
-            uint64_t cand = aa;
-            bool neg = false;
-            for (int b = t; b < a.Sb; b += blockDim.x) {
-                const uint32_t f = fls[b];
-                if (!(f & IV_HAS) || !(f & IV_FINITE)) continue;
-                if (tHs[b] > aa) { if (f & IV_NEGINF) neg = true; else cand = tLs[b] < cand ? tLs[b] : cand; }
-            }
-            any_neg = __syncthreads_or(neg ? 1 : 0);
-            if (any_neg) { emit = false; break; }
-            const uint64_t na = block_min_u64(cand, red);
-            if (na == aa) break;
-            aa = na;
-        }
-        // e* = latest closing moment before the component; everything closed by then was emitted
-        uint64_t estar = 0;
-        bool have_e = false;
-        if (emit) {
-            uint64_t best = 0; bool hb = false;
-            for (int b = t; b < a.Sb; b += blockDim.x) {
-                const uint32_t f = fls[b];
-                if ((f & IV_HAS) && (f & IV_FINITE) && tHs[b] < aa && (!hb || tHs[b] > best)) { best = tHs[b]; hb = true; }
-            }
-            // block max via min of complement
-            const uint64_t mm = block_min_u64(hb ? ~best : T64_NONE, red);
-            int anyb = __syncthreads_or(hb ? 1 : 0);
-            have_e = anyb != 0;
-            estar = ~mm;
-        }
-        if (t == 0) { s_h1 = 0; s_h2 = 0; s_cnt = 0; }
-        __syncthreads();
-        if (have_e) {
-            unsigned long long h1 = 0, h2 = 0; int cnt = 0;
-            for (int b = t; b < a.Sb; b += blockDim.x) {
-                const uint32_t f = fls[b];
-                const bool em = ((f & IV_HAS) && (f & IV_FINITE) && tHs[b] <= estar) || (f & IV_CARRIED);
-                if (em) {
-                    const SubjDesc d = a.desc[b];
-                    uint16_t* p = a.masks + ((size_t)d.slot * 2 + (a.cur[d.slot] ^ 1)) * a.Rpad + r;   // the new row
-                    *p = (uint16_t)(*p | CD_BIT_EMIT);
-                    const int32_t id = a.slot_subject[d.slot];
-                    h1 += fp_mix1(id); h2 += fp_mix2(id); ++cnt;
-                }
-            }
-            // subjects at >= H from earlier batches that this batch did not touch leave with the first proposal too
-            for (int32_t s = t; s < m.S; s += blockDim.x) {
-                if (m.touch[s] == m.serial) continue;
-                uint16_t* p = a.masks + ((size_t)s * 2 + a.cur[s]) * a.Rpad + r;
-                const uint32_t w = *p;
-                if (!(w & CD_BIT_EMIT) && __popc(w & RM) >= H) {
-                    *p = (uint16_t)(w | CD_BIT_EMIT);
-                    const int32_t id = a.slot_subject[s];
-                    h1 += fp_mix1(id); h2 += fp_mix2(id); ++cnt;
-                }
-            }
-            atomicAdd(&s_h1, h1); atomicAdd(&s_h2, h2); atomicAdd(&s_cnt, cnt);
-        }
-        __syncthreads();
-        if (t == 0 && have_e) {
-            m.out_h1[r] = s_h1; m.out_h2[r] = s_h2; m.out_len[r] = s_cnt;
-            m.pend_h1[r] -= s_h1; m.pend_h2[r] -= s_h2; m.pend_cnt[r] -= s_cnt;
-            m.rflags[r] = (m.rflags[r] | RF_ANNOUNCED | RF_ANN_NOW) & ~RF_RULE_GE_H;
-        }
-        __syncthreads();
+    if (e.touch[s] != e.serial) return __popc(w_new & RM) >= a.H;         // untouched and at >= H: it was pending, it left first
+    const int b = e.batch_index[s];
+    const SubjDesc d = a.desc[b];
+    const uint32_t old = s >= a.S_before ? 0u : (a.masks + ((size_t)s * 2 + (a.cur[s] ^ 1)) * a.Rpad)[r];
+    if (__popc(old & RM) >= a.H) return true;                              // pending before the batch
+    const SubjWalk* w = e.uniform ? &a.walk[b] : nullptr;
+    SubjWalk wl;
+    if (e.uniform) { wl = *w; }
+    const IVisit v = interval_visit(a, e.uniform, old & RM, d, &wl, r, rs);
+    return v.crossH && v.tH <= e.estar[r];
+}
+
+// RF_MIXED_EMIT receivers whose invalidation pass did not emit announce only the explicit part: give it bit 15 so that
+// rapid_cd_get_proposal can list it later (the pre-batch rows are gone by then).
+__global__ void __launch_bounds__(GEN_THREADS) k_mixed_mark(const EmitCtx e, int32_t S, int slots_per_block, const uint32_t* __restrict__ rflags) {
+    const ApplyArgs& a = e.ap;
+    const int64_t r = (int64_t)blockIdx.x * GEN_THREADS + threadIdx.x;
+    if (r >= a.R) return;
+    const uint32_t f = rflags[r];
+    if (!(f & RF_MIXED_EMIT) || !(f & RF_ANN_NOW) || (f & RF_RULE_GE_H)) return;
+    const uint64_t rs = splitmix64(a.dl.perm_seed + (uint64_t)(a.rbegin + r));
+    const int32_t s0 = blockIdx.y * slots_per_block, s1 = min(S, s0 + slots_per_block);
+    for (int32_t s = s0; s < s1; ++s) {
+        uint16_t* p = a.masks + ((size_t)s * 2 + a.cur[s]) * a.Rpad + r;
+        const uint32_t w = *p;
+        if (!(w & CD_BIT_EMIT) && emitted_in_batch(e, s, r, w, rs)) *p = (uint16_t)(w | CD_BIT_EMIT);
     }
 }
 
@@ -789,6 +858,8 @@ struct InvArgs {
     int32_t* k3_res;
     unsigned long long* k3_h1;
     unsigned long long* k3_h2;
+    int mixed;                 // some receiver announced through the interval analysis in this batch
+    EmitCtx ec;                // (valid when mixed)
 };
 
 __global__ void __launch_bounds__(256) k_inval_pairs(const InvArgs a) {
@@ -807,7 +878,11 @@ __global__ void __launch_bounds__(256) k_inval_pairs(const InvArgs a) {
         uint16_t* row = a.masks + ((size_t)slot * 2 + a.cur[slot]) * a.Rpad;
         for (int q = 0; q < TILE_R / 256; ++q) {
             const int64_t r = (int64_t)pr.x * TILE_R + q * 256 + threadIdx.x;
-            if (r >= a.R || !(a.rflags[r] & RF_K3)) continue;
+            if (r >= a.R) continue;
+            const uint32_t rf = a.rflags[r];
+            if (!(rf & RF_K3)) continue;
+            const bool mx = a.mixed && (rf & RF_MIXED_EMIT);
+            const uint64_t rs = mx ? splitmix64(a.ec.ap.dl.perm_seed + (uint64_t)(a.ec.ap.rbegin + r)) : 0ull;
             const uint32_t w = row[r];
             const int c = __popc(w & RM);
             if (c < a.L || c >= a.H) continue;                      // not in this receiver's preProposal
@@ -817,16 +892,36 @@ __global__ void __launch_bounds__(256) k_inval_pairs(const InvArgs a) {
                 const int32_t s2 = so[k];
                 if (s2 < 0) continue;
                 const uint32_t wo = (a.masks + ((size_t)s2 * 2 + a.cur[s2]) * a.Rpad)[r];
-                if (!(wo & CD_BIT_EMIT) && __popc(wo & RM) >= a.L) implicit |= 1u << k;   // observer in proposal U preProposal
+                if ((wo & CD_BIT_EMIT) || __popc(wo & RM) < a.L) continue;            // observer not in proposal U preProposal
+                // a receiver that already announced explicit proposals in this batch: those subjects left `proposal`.
+                // (bit 14 = raised to >= H by this very pass, i.e. it was in the band at entry, not pending)
+                if (mx && !(wo & CD_BIT_CALL) && emitted_in_batch(a.ec, s2, r, wo, rs)) continue;
+                implicit |= 1u << k;
             }
             if (!implicit) continue;
-            const uint32_t nw = w | implicit;
+            uint32_t nw = w | implicit;
+            const bool raised = __popc(nw & RM) >= a.H;
+            if (raised && a.mixed) nw |= CD_BIT_CALL;                // transient marker, cleared by k_inval_unmark
             row[r] = (uint16_t)nw;
-            if (__popc(nw & RM) >= a.H) {                            // moved preProposal -> proposal
+            if (raised) {                                            // moved preProposal -> proposal
                 atomicAdd(&a.k3_res[r], 1);
                 atomicAdd(&a.k3_h1[r], (unsigned long long)fp_mix1(subject));
                 atomicAdd(&a.k3_h2[r], (unsigned long long)fp_mix2(subject));
             }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_inval_unmark(const InvArgs a) {
+    const int n = min(*a.pre_count, a.pre_cap);
+    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+        const int2 pr = a.pre_pairs[e];
+        uint16_t* row = a.masks + ((size_t)pr.y * 2 + a.cur[pr.y]) * a.Rpad;
+        for (int q = 0; q < TILE_R / 256; ++q) {
+            const int64_t r = (int64_t)pr.x * TILE_R + q * 256 + threadIdx.x;
+            if (r >= a.R) continue;
+            const uint32_t w = row[r];
+            if (w & CD_BIT_CALL) row[r] = (uint16_t)(w & ~CD_BIT_CALL);
         }
     }
 }
@@ -845,6 +940,7 @@ struct Fin2Args {
     int32_t* k3_res;
     unsigned long long* k3_h1;
     unsigned long long* k3_h2;
+    BatchCounts* bc;
 };
 
 __global__ void k_finalize2(const Fin2Args a) {
@@ -869,6 +965,7 @@ __global__ void k_finalize2(const Fin2Args a) {
         }
     }
     flags &= ~RF_K3;
+    if ((flags & RF_MIXED_EMIT) && (flags & RF_ANN_NOW) && !(flags & RF_RULE_GE_H)) atomicAdd(&a.bc->n_inval, 1);   // needs bit-15 marks
     a.rflags[r] = flags;
     a.out_ann[r] = (flags & RF_ANNOUNCED) ? 1 : 0;
 }
@@ -946,6 +1043,7 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
         RAPID_CHECK(b->head.reserve((size_t)A));
         RAPID_CHECK(b->s_ring.reserve((size_t)A)); RAPID_CHECK(b->s_status.reserve((size_t)A));
         RAPID_CHECK(b->desc.reserve((size_t)Sb)); RAPID_CHECK(b->walk.reserve((size_t)Sb));
+        RAPID_CHECK(b->batch_index.reserve(std::max<size_t>(cd->S_cap, 1)));
         const unsigned ga = (unsigned)ceil_div<int64_t>(A, TB);
         k_sort_keys<<<ga, TB, 0, s>>>(A, cd->cell_slot.p, b->key_in.p, b->val_in.p);
         size_t tmp_bytes = 0;
@@ -956,7 +1054,7 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
         k_heads<<<gv, TB, 0, s>>>(n_valid, b->key_out.p, b->head.p);
         RAPID_CHECK(exclusive_scan_i32(b->head.p, n_valid, cd->scan_sums, nullptr, s, nullptr));
         k_build_desc<<<gv, TB, 0, s>>>(n_valid, b->key_out.p, b->val_out.p, b->head.p, cd->cur_ring_dev, cd->cur_status_dev,
-                                       cd->slot_subject.p, cd->L, cd->H, b->desc.p, b->walk.p, b->s_ring.p, b->s_status.p);
+                                       cd->slot_subject.p, cd->L, cd->H, b->desc.p, b->walk.p, b->s_ring.p, b->s_status.p, b->batch_index.p);
         RAPID_KERNEL_CHECK();
         cd->last_launches += 6;   // sort keys, radix sort (counted once), heads, scan, descriptors
         // ---- grid: tiles x subject chunks, a few waves of 148 SMs -----------------------------------------------------
@@ -991,7 +1089,15 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
     const size_t pn = (size_t)n_chunks * cd->Rpad;
     RAPID_CHECK(b->p_cnt.reserve(pn)); RAPID_CHECK(b->p_minTH.reserve(pn)); RAPID_CHECK(b->p_minTLun.reserve(pn));
     RAPID_CHECK(b->p_h1.reserve(pn)); RAPID_CHECK(b->p_h2.reserve(pn));
-    RAPID_CHECK(b->mixed_list.reserve(cd->Rpad));
+    RAPID_CHECK(b->mx_fl.reserve(cd->Rpad)); RAPID_CHECK(b->mx_a.reserve(cd->Rpad)); RAPID_CHECK(b->mx_cand.reserve(cd->Rpad));
+    RAPID_CHECK(b->mx_emax.reserve(cd->Rpad)); RAPID_CHECK(b->mx_p1.reserve(cd->Rpad)); RAPID_CHECK(b->mx_p2.reserve(cd->Rpad));
+    RAPID_CHECK(b->mx_pc.reserve(cd->Rpad)); RAPID_CHECK(b->estar.reserve(cd->Rpad)); RAPID_CHECK(b->mx_changed.reserve(1));
+    if (!b->mx_e1.p) {
+        RAPID_CHECK(b->mx_e1.reserve(cd->Rpad)); RAPID_CHECK(b->mx_e2.reserve(cd->Rpad)); RAPID_CHECK(b->mx_ec.reserve(cd->Rpad));
+        RAPID_CUDA(cudaMemsetAsync(b->mx_e1.p, 0, cd->Rpad * sizeof(unsigned long long), s));
+        RAPID_CUDA(cudaMemsetAsync(b->mx_e2.p, 0, cd->Rpad * sizeof(unsigned long long), s));
+        RAPID_CUDA(cudaMemsetAsync(b->mx_ec.p, 0, cd->Rpad * sizeof(int32_t), s));
+    }
     Partials part{b->p_cnt.p, b->p_minTH.p, b->p_minTLun.p, b->p_h1.p, b->p_h2.p};
 
     ApplyArgs ap;
@@ -1030,38 +1136,84 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
     fa.any_down_uniform = bc.any_down; fa.uniform = uniform ? 1 : 0;
     fa.n_pre = cd->n_pre.p; fa.rflags = cd->rflags.p; fa.pend_h1 = cd->pend_h1.p; fa.pend_h2 = cd->pend_h2.p;
     fa.pend_cnt = cd->pend_cnt.p; fa.out_h1 = cd->out_h1.p; fa.out_h2 = cd->out_h2.p; fa.out_len = cd->out_len.p;
-    fa.mixed_list = b->mixed_list.p; fa.bc = cd->counts.p;
+    fa.mx_fl = b->mx_fl.p; fa.mx_a = b->mx_a.p; fa.mx_cand = b->mx_cand.p; fa.mx_emax = b->mx_emax.p;
+    fa.mx_p1 = b->mx_p1.p; fa.mx_p2 = b->mx_p2.p; fa.mx_pc = b->mx_pc.p; fa.bc = cd->counts.p;
     const unsigned gr = (unsigned)ceil_div<int64_t>(cd->R, TB);
     k_finalize1<<<gr, TB, 0, s>>>(fa);
     RAPID_KERNEL_CHECK();
     cd->last_launches += 1;
 
-    if (Sb > 0) {
-        RAPID_CHECK(b->iv_tL.reserve((size_t)MIXED_BLOCKS * Sb)); RAPID_CHECK(b->iv_tH.reserve((size_t)MIXED_BLOCKS * Sb));
-        RAPID_CHECK(b->iv_fl.reserve((size_t)MIXED_BLOCKS * Sb));
+    // ---- receivers needing the exact interval analysis (one small readback tells whether there are any) ----------------
+    RAPID_CUDA(cudaMemcpyAsync(cd->h_counts.p, cd->counts.p, sizeof(BatchCounts), cudaMemcpyDeviceToHost, s));
+    RAPID_CUDA(cudaStreamSynchronize(s));
+    const int n_mixed = cd->h_counts.p->n_mixed;
+    EmitCtx ectx;
+    ectx.ap = ap; ectx.touch = cd->touch.p; ectx.batch_index = b->batch_index.p; ectx.serial = cd->batch_serial;
+    ectx.estar = b->estar.p; ectx.uniform = uniform ? 1 : 0;
+    if (n_mixed > 0 && Sb > 0) {
         MixArgs ma;
-        ma.ap = ap; ma.S = cd->S; ma.touch = cd->touch.p; ma.serial = cd->batch_serial; ma.mixed_list = b->mixed_list.p;
-        ma.bc = cd->counts.p; ma.iv_tL = b->iv_tL.p; ma.iv_tH = b->iv_tH.p; ma.iv_fl = b->iv_fl.p; ma.rflags = cd->rflags.p;
-        ma.pend_h1 = cd->pend_h1.p; ma.pend_h2 = cd->pend_h2.p; ma.pend_cnt = cd->pend_cnt.p;
-        ma.out_h1 = cd->out_h1.p; ma.out_h2 = cd->out_h2.p; ma.out_len = cd->out_len.p;
-        k_resolve_mixed<<<MIXED_BLOCKS, 256, 0, s>>>(ma);
-        k_flip<<<(unsigned)ceil_div(Sb, TB), TB, 0, s>>>(Sb, b->desc.p, cd->cur.p);
+        ma.ap = ap; ma.mx_fl = b->mx_fl.p; ma.mx_a = b->mx_a.p; ma.mx_cand = b->mx_cand.p; ma.mx_emax = b->mx_emax.p;
+        ma.estar = b->estar.p; ma.mx_e1 = b->mx_e1.p; ma.mx_e2 = b->mx_e2.p; ma.mx_ec = b->mx_ec.p; ma.uniform = uniform ? 1 : 0;
+        const int rblocks = (int)(cd->Rpad / GEN_THREADS);
+        int mchunks = std::max(1, std::min(ceil_div(Sb, STAGE), ceil_div(2 * std::max(b->slots_generic, 148), rblocks)));
+        ma.ap.chunk = ceil_div(Sb, mchunks);
+        mchunks = ceil_div(Sb, ma.ap.chunk);
+        dim3 mgrid((unsigned)rblocks, (unsigned)mchunks);
+        for (int iter = 0; iter <= Sb + 1; ++iter) {
+            RAPID_CUDA(cudaMemsetAsync(b->mx_changed.p, 0, sizeof(int32_t), s));
+            k_mixed_pass<0><<<mgrid, GEN_THREADS, 0, s>>>(ma);
+            k_mixed_update<<<gr, TB, 0, s>>>(cd->R, b->mx_fl.p, b->mx_a.p, b->mx_cand.p, b->mx_emax.p, b->estar.p, b->mx_changed.p);
+            RAPID_KERNEL_CHECK();
+            cd->last_launches += 2;
+            int32_t changed = 0;
+            RAPID_CUDA(cudaMemcpyAsync(&changed, b->mx_changed.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            RAPID_CUDA(cudaStreamSynchronize(s));
+            if (changed == 0) break;
+        }
+        k_mixed_pass<1><<<mgrid, GEN_THREADS, 0, s>>>(ma);
+        MixCommitArgs mc;
+        mc.R = cd->R; mc.mx_fl = b->mx_fl.p; mc.mx_p1 = b->mx_p1.p; mc.mx_p2 = b->mx_p2.p; mc.mx_pc = b->mx_pc.p;
+        mc.mx_e1 = b->mx_e1.p; mc.mx_e2 = b->mx_e2.p; mc.mx_ec = b->mx_ec.p; mc.rflags = cd->rflags.p;
+        mc.pend_h1 = cd->pend_h1.p; mc.pend_h2 = cd->pend_h2.p; mc.pend_cnt = cd->pend_cnt.p;
+        mc.out_h1 = cd->out_h1.p; mc.out_h2 = cd->out_h2.p; mc.out_len = cd->out_len.p;
+        k_mixed_commit<<<gr, TB, 0, s>>>(mc);
         RAPID_KERNEL_CHECK();
         cd->last_launches += 2;
+    }
+    if (Sb > 0) {
+        k_flip<<<(unsigned)ceil_div(Sb, TB), TB, 0, s>>>(Sb, b->desc.p, cd->cur.p);
+        RAPID_KERNEL_CHECK();
+        cd->last_launches += 1;
+        ectx.ap.cur = cd->cur.p;
     }
     InvArgs ia;
     ia.masks = cd->masks.p; ia.cur = cd->cur.p; ia.Rpad = cd->Rpad; ia.K = cd->K; ia.H = cd->H; ia.L = cd->L; ia.R = cd->R;
     ia.rflags = cd->rflags.p; ia.pre_pairs = b->pre_pairs.p; ia.pre_count = b->pre_count.p; ia.pre_cap = ap.pre_cap;
     ia.slot_subject = cd->slot_subject.p; ia.slot_of = cd->slot_of.p; ia.obs = cd->view->obs.p;
     ia.k3_res = b->k3_res.p; ia.k3_h1 = b->k3_h1.p; ia.k3_h2 = b->k3_h2.p;
+    ia.mixed = n_mixed > 0 ? 1 : 0; ia.ec = ectx;
     k_inval_pairs<<<148 * 4, 256, 0, s>>>(ia);
     Fin2Args f2;
     f2.R = cd->R; f2.n_pre = cd->n_pre.p; f2.rflags = cd->rflags.p; f2.pend_h1 = cd->pend_h1.p; f2.pend_h2 = cd->pend_h2.p;
     f2.pend_cnt = cd->pend_cnt.p; f2.out_h1 = cd->out_h1.p; f2.out_h2 = cd->out_h2.p; f2.out_len = cd->out_len.p;
-    f2.out_ann = cd->out_ann.p; f2.k3_res = b->k3_res.p; f2.k3_h1 = b->k3_h1.p; f2.k3_h2 = b->k3_h2.p;
+    f2.out_ann = cd->out_ann.p; f2.k3_res = b->k3_res.p; f2.k3_h1 = b->k3_h1.p; f2.k3_h2 = b->k3_h2.p; f2.bc = cd->counts.p;
     k_finalize2<<<gr, TB, 0, s>>>(f2);
     RAPID_KERNEL_CHECK();
     cd->last_launches += 2;
+    if (n_mixed > 0) {
+        k_inval_unmark<<<148 * 4, 256, 0, s>>>(ia);
+        RAPID_CUDA(cudaMemcpyAsync(cd->h_counts.p, cd->counts.p, sizeof(BatchCounts), cudaMemcpyDeviceToHost, s));
+        RAPID_CUDA(cudaStreamSynchronize(s));
+        cd->last_launches += 1;
+        if (cd->h_counts.p->n_inval > 0 && cd->S > 0) {
+            // receivers that announce only the explicit part: persist it as bit 15 while the pre-batch rows still exist
+            const int spb = 64;
+            dim3 kgrid((unsigned)(cd->Rpad / GEN_THREADS), (unsigned)ceil_div(cd->S, spb));
+            k_mixed_mark<<<kgrid, GEN_THREADS, 0, s>>>(ectx, cd->S, spb, cd->rflags.p);
+            RAPID_KERNEL_CHECK();
+            cd->last_launches += 1;
+        }
+    }
     return RAPID_OK;
 }
 

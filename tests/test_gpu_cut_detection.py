@@ -296,3 +296,40 @@ def test_mixed_receivers_take_the_interval_analysis(orc, rb, permuted):
         compare_batch(rb, w, sim, cl, None, (src, dst, ring, status), perm_seed=(1234 + trial) if permuted else None)
         seen_mixed += cl.debugStats()[0]
     assert seen_mixed > 0
+
+
+@pytest.mark.parametrize("permuted", [False, True])
+def test_interval_analysis_then_invalidation(orc, rb, permuted):
+    """explicit proposals early in the batch, then subjects stuck in the band whose observers are partly the subjects that
+    already left: the implicit pass must not count edges from observers that are no longer in proposal U preProposal"""
+    n = 40
+    rng = np.random.default_rng(2024)
+    total_mixed = 0
+    for trial in range(30):
+        Hh, Ll = [(9, 4), (8, 3), (7, 2)][trial % 3]
+        w, v, sim, cl = _worlds(orc, rb, n, kernel="bucketed", Hh=Hh, Ll=Ll)
+        obs, _ = v.tables()
+        s = int(rng.integers(0, n))
+        o = list(dict.fromkeys(obs[s].tolist()))                         # distinct observers of s
+        rng.shuffle(o)
+        early = o[: int(rng.integers(1, 4))]                             # leave explicitly, first
+        band = o[len(early): len(early) + int(rng.integers(0, 4))]       # stay in the unstable band
+        cells = []
+        for e in early:
+            cells += [(e, k) for k in rng.permutation(K)[: int(rng.integers(Hh, K + 1))]]
+        if trial % 4 == 0:
+            rng.shuffle(cells)
+        late = [(s, k) for k in rng.permutation(K)[: int(rng.integers(Ll, Hh))]]
+        for bnode in band:
+            late += [(bnode, k) for k in rng.permutation(K)[: int(rng.integers(Ll, Hh))]]
+        rng.shuffle(late)
+        cells += late
+        dst = np.array([c[0] for c in cells], np.int32)
+        ring = np.array([c[1] for c in cells], np.uint8)
+        compare_batch(rb, w, sim, cl, None, (np.zeros(len(cells), np.int32), dst, ring, np.full(len(cells), DOWN, np.uint8)),
+                      perm_seed=(99 + trial) if permuted else None)
+        total_mixed += cl.debugStats()[0]
+        # a follow-up batch: announced receivers ignore it, the others carry their state
+        src2, dst2, ring2, st2 = random_batch(rng, n, K, 4, 30, n)
+        compare_batch(rb, w, sim, cl, None, (src2, dst2, ring2, st2), perm_seed=(7 + trial) if permuted else None)
+    assert total_mixed > 0
