@@ -288,6 +288,8 @@ def run_ours(args):
     dl.blocked = d_blocked.data_ptr()
     lib = N.lib()
 
+    phases = [0.0, 0.0, 0.0]     # apply call, its dominant kernel, tally call (device ms, summed)
+
     def step_device():
         cl.clear()
         fp.reset(cfg)
@@ -295,6 +297,7 @@ def run_ours(args):
                                              d_status.data_ptr(), None, C.byref(dl)))
         res = fp.tallyCluster(cl, comm)
         tot, main = cl.lastDeviceMs()
+        phases[0] += tot; phases[1] += main; phases[2] += fp.lastDeviceMs()
         return res, tot + fp.lastDeviceMs(), main, cl.lastPath()[1] + fp.lastLaunches()
 
     def step_host():
@@ -318,6 +321,7 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     barrier()
+    phases[:] = [0.0, 0.0, 0.0]
     dev_ms, main_ms, launches = 0.0, 0.0, 0
     w0 = time.perf_counter()
     for _ in range(args.steps):
@@ -325,6 +329,8 @@ def run_ours(args):
         dev_ms += ms; main_ms += mk; launches += nl
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
+    log("[rank %d] per step: apply %.3f ms (dominant kernel %.3f ms), tally %.3f ms" % (
+        rank, phases[0] / args.steps, phases[1] / args.steps, phases[2] / args.steps))
     # end-to-end through the host-facing ABI (host arrays, H2D, reset, kernels, decision back)
     for _ in range(2):
         step_host()

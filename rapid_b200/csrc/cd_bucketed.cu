@@ -1076,13 +1076,14 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
         double best = -1.0;
         for (int c = 1; c <= cmax; ++c) {
             const int ch = ceil_div(Sb, c), cc = ceil_div(Sb, ch);
-            // cost model (fitted to measurements on B200): a bandwidth-bound wave needs about half of the resident
-            // slots busy to saturate HBM, so a tail wave of fraction f costs max(f, 0.5) of a full wave; every extra
-            // chunk costs ~1 % (block prologue / per-receiver partials).
+            // cost model fitted to measurements on B200 (977 tiles: 1 chunk 0.92, 2 chunks 0.94 of peak; 489 tiles x 3
+            // chunks = 1.24 waves: 0.79)
             const double w = (double)rblocks * cc / slots;
             const double f = w - std::floor(w);
-            const double t = std::floor(w) + (f > 0 ? std::max(f, 0.5) : 0.0);
-            const double eff = w / t - 0.01 * cc;
+            double eff;
+            if (w <= 1.0) eff = 0.85 + 0.15 * w;                                   // one partial wave: a little less occupancy
+            else eff = w / (std::floor(w) + (f > 0 ? std::max(f, 0.6) : 0.0));     // tail wave: needs ~60 % of the slots to saturate HBM
+            eff -= 0.005 * cc;                                                     // per-chunk prologue / partials
             if (eff > best) { best = eff; n_chunks = cc; chunk = ch; }
         }
     }
@@ -1192,7 +1193,7 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
     ia.slot_subject = cd->slot_subject.p; ia.slot_of = cd->slot_of.p; ia.obs = cd->view->obs.p;
     ia.k3_res = b->k3_res.p; ia.k3_h1 = b->k3_h1.p; ia.k3_h2 = b->k3_h2.p;
     ia.mixed = n_mixed > 0 ? 1 : 0; ia.ec = ectx;
-    k_inval_pairs<<<148 * 4, 256, 0, s>>>(ia);
+    k_inval_pairs<<<148 * 16, 256, 0, s>>>(ia);
     Fin2Args f2;
     f2.R = cd->R; f2.n_pre = cd->n_pre.p; f2.rflags = cd->rflags.p; f2.pend_h1 = cd->pend_h1.p; f2.pend_h2 = cd->pend_h2.p;
     f2.pend_cnt = cd->pend_cnt.p; f2.out_h1 = cd->out_h1.p; f2.out_h2 = cd->out_h2.p; f2.out_len = cd->out_len.p;

@@ -28,8 +28,11 @@ struct FPState {
     int32_t bad_sender;
 };
 
+struct FPResult;
 struct FP {
     int device = 0;
+    bool decided_host = false;            // host mirror of FPState::decided
+    DevBuf<unsigned char> d_res_raw;      // FPResult on the device
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t cfg = 0, N = 0, Q = 0, sender_cap = 0;
@@ -48,6 +51,7 @@ struct FP {
     DevBuf<int32_t> hist;                 // [65536]
     DevBuf<unsigned long long> mm;        // [8] max / ~min verification words
     PinnedBuf<unsigned long long> h_mm;
+    PinnedBuf<unsigned char> h_res_raw;
     float last_ms = 0.f;
     int32_t last_launches = 0;
 };
@@ -123,6 +127,9 @@ __global__ void k_fp_insert(int64_t n, const int32_t* __restrict__ sender, const
                             int32_t* __restrict__ t_state, uint64_t* __restrict__ t_h1, uint64_t* __restrict__ t_h2,
                             int32_t* __restrict__ t_len, int32_t* __restrict__ t_call, int32_t* __restrict__ ent,
                             FPState* __restrict__ st) {
+    __shared__ int32_t s_key[16], s_val[16];
+    if (threadIdx.x < 16) { s_key[threadIdx.x] = -1; s_val[threadIdx.x] = 0; }
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false;
     uint64_t h1 = 0, h2 = 0;
@@ -146,7 +153,8 @@ __global__ void k_fp_insert(int64_t n, const int32_t* __restrict__ sender, const
         if (lane == leader) {
             uint32_t pos = fp_slot_hash(h1, h2, len) & (T - 1);
             for (;;) {
-                int32_t state = atomicCAS(&t_state[pos], 0, 1);
+                int32_t state = *(volatile int32_t*)&t_state[pos];         // published entries need no atomic
+                if (state == 0) state = atomicCAS(&t_state[pos], 0, 1);
                 if (state == 0) {                            // claimed an empty entry: publish the key
                     t_h1[pos] = h1; t_h2[pos] = h2; t_len[pos] = len;
                     __threadfence();
@@ -155,10 +163,20 @@ __global__ void k_fp_insert(int64_t n, const int32_t* __restrict__ sender, const
                     break;
                 }
                 while (state == 1) state = atomicAdd(&t_state[pos], 0);     // another warp is publishing
+                __threadfence();
                 if (t_h1[pos] == h1 && t_h2[pos] == h2 && t_len[pos] == len) { e = (int32_t)pos; break; }
                 pos = (pos + 1) & (T - 1);
             }
-            atomicAdd(&t_call[e], __popc(same));
+            {   // warp -> block aggregation of the per-call count (a handful of distinct proposals per block)
+                const int c = __popc(same);
+                int slot = -1;
+                for (int q = 0; q < 16; ++q) {
+                    const int32_t k = atomicCAS(&s_key[q], -1, e);
+                    if (k == -1 || k == e) { slot = q; break; }
+                }
+                if (slot >= 0) atomicAdd(&s_val[slot], c);
+                else atomicAdd(&t_call[e], c);
+            }
         }
         // NOTE: __match_any groups by the XOR-folded key; distinct fingerprints that fold equal are split below
         e = __shfl_sync(same, e, leader);
@@ -187,6 +205,8 @@ __global__ void k_fp_insert(int64_t n, const int32_t* __restrict__ sender, const
     if (i < n) ent[i] = e;
     const unsigned cnt = __popc(active);
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&st->n_valid_call, (int32_t)cnt);
+    __syncthreads();
+    if (threadIdx.x < 16 && s_key[threadIdx.x] >= 0) atomicAdd(&t_call[s_key[threadIdx.x]], s_val[threadIdx.x]);
 }
 
 // entries whose count reaches the quorum within this call
@@ -339,14 +359,29 @@ __global__ void k_fp_minmax(uint32_t T, const int32_t* __restrict__ t_state, con
     atomicMax(&mm[4], len);                    atomicMax(&mm[5], ~len);
 }
 
-static int32_t fp_reset_call_state(FP* fp) {
-    FPState s;
-    RAPID_CUDA(cudaMemcpyAsync(fp->h_st.p, fp->st.p, sizeof(FPState), cudaMemcpyDeviceToHost, fp->stream));
-    RAPID_CUDA(cudaStreamSynchronize(fp->stream));
-    s = *fp->h_st.p;
-    s.n_valid_call = 0; s.n_cand = 0; s.i_star = INT_MAX; s.bad_sender = -1;
-    *fp->h_st.p = s;
-    RAPID_CUDA(cudaMemcpyAsync(fp->st.p, fp->h_st.p, sizeof(FPState), cudaMemcpyHostToDevice, fp->stream));
+__global__ void k_fp_begin(FPState* st) {
+    st->n_valid_call = 0; st->n_cand = 0; st->i_star = INT_MAX; st->bad_sender = -1;
+}
+
+struct FPResult {
+    int32_t decided, len, count, received;
+    uint64_t h1, h2;
+};
+
+__global__ void k_fp_result(const FPState* __restrict__ st, const uint64_t* __restrict__ t_h1, const uint64_t* __restrict__ t_h2,
+                            const int32_t* __restrict__ t_len, const int32_t* __restrict__ t_count, FPResult* __restrict__ out) {
+    FPResult r;
+    r.decided = st->decided; r.received = st->votes_received; r.len = 0; r.count = 0; r.h1 = 0; r.h2 = 0;
+    if (r.decided && st->decided_entry >= 0) {
+        const int32_t e = st->decided_entry;
+        r.h1 = t_h1[e]; r.h2 = t_h2[e]; r.len = t_len[e]; r.count = t_count[e];
+    }
+    *out = r;
+}
+
+static int32_t fp_reset_call_state(FP* fp) {        // per-call fields only; no host round trip
+    k_fp_begin<<<1, 1, 0, fp->stream>>>(fp->st.p);
+    RAPID_KERNEL_CHECK();
     return RAPID_OK;
 }
 
@@ -357,7 +392,7 @@ static int32_t tally_device(FP* fp, int64_t n, const int32_t* sender, const int6
     const int TB = 256;
     fp->last_launches = 0;
     RAPID_CHECK(fp_reset_call_state(fp));
-    if (fp->h_st.p->decided || n == 0) return RAPID_OK;              // :138 — everything after the decision is ignored
+    if (fp->decided_host || n == 0) return RAPID_OK;                 // :138 — everything after the decision is ignored
     RAPID_CHECK(fp->ent.reserve((size_t)n));
     const unsigned g = (unsigned)ceil_div<int64_t>(n, TB);
     k_fp_first<<<g, TB, 0, s>>>(n, sender, vcfg, fp->cfg, fp->sender_cap, allow_skip, fp->seen.p, fp->st.p);
@@ -399,23 +434,18 @@ static int32_t tally_device(FP* fp, int64_t n, const int32_t* sender, const int6
 }
 
 static int32_t read_result(FP* fp, int32_t* decided, uint64_t* dh1, uint64_t* dh2, int32_t* dlen, int32_t* dcount, int32_t* received) {
-    RAPID_CUDA(cudaMemcpyAsync(fp->h_st.p, fp->st.p, sizeof(FPState), cudaMemcpyDeviceToHost, fp->stream));
+    k_fp_result<<<1, 1, 0, fp->stream>>>(fp->st.p, fp->t_h1.p, fp->t_h2.p, fp->t_len.p, fp->t_count.p, (FPResult*)fp->d_res_raw.p);
+    RAPID_KERNEL_CHECK();
+    RAPID_CUDA(cudaMemcpyAsync(fp->h_res_raw.p, (FPResult*)fp->d_res_raw.p, sizeof(FPResult), cudaMemcpyDeviceToHost, fp->stream));
     RAPID_CUDA(cudaStreamSynchronize(fp->stream));
-    const FPState st = *fp->h_st.p;
-    if (decided) *decided = st.decided;
-    if (received) *received = st.votes_received;
-    uint64_t a = 0, b = 0;
-    int32_t l = 0, c = 0;
-    if (st.decided) {
-        RAPID_CUDA(cudaMemcpy(&a, fp->t_h1.p + st.decided_entry, 8, cudaMemcpyDeviceToHost));
-        RAPID_CUDA(cudaMemcpy(&b, fp->t_h2.p + st.decided_entry, 8, cudaMemcpyDeviceToHost));
-        RAPID_CUDA(cudaMemcpy(&l, fp->t_len.p + st.decided_entry, 4, cudaMemcpyDeviceToHost));
-        RAPID_CUDA(cudaMemcpy(&c, fp->t_count.p + st.decided_entry, 4, cudaMemcpyDeviceToHost));
-    }
-    if (dh1) *dh1 = a;
-    if (dh2) *dh2 = b;
-    if (dlen) *dlen = l;
-    if (dcount) *dcount = c;
+    const FPResult r = *(const FPResult*)fp->h_res_raw.p;
+    fp->decided_host = r.decided != 0;
+    if (decided) *decided = r.decided;
+    if (received) *received = r.received;
+    if (dh1) *dh1 = r.h1;
+    if (dh2) *dh2 = r.h2;
+    if (dlen) *dlen = r.len;
+    if (dcount) *dcount = r.count;
     return RAPID_OK;
 }
 
@@ -460,6 +490,8 @@ int32_t rapid_fp_create(rapid_fp** out, int64_t cfg_id, int64_t membership_size,
         if ((rc = fp->hist.reserve(65536))) break;
         if ((rc = fp->mm.reserve(8))) break;
         if ((rc = fp->h_mm.reserve(8))) break;
+        if ((rc = fp->d_res_raw.reserve(64))) break;
+        if ((rc = fp->h_res_raw.reserve(64))) break;
         const int TB = 256;
         k_fp_fill<<<(unsigned)ceil_div<int64_t>(sender_capacity, TB), TB, 0, fp->stream>>>(fp->seen.p, sender_capacity, INT_MAX);
         cudaMemsetAsync(fp->t_state.p, 0, T * sizeof(int32_t), fp->stream);
@@ -481,6 +513,7 @@ int32_t rapid_fp_reset(rapid_fp* fp, int64_t cfg_id, int64_t membership_size) {
     fp->cfg = cfg_id;
     fp->N = membership_size;
     fp->Q = membership_size - (membership_size - 1) / 4;
+    fp->decided_host = false;
     const int TB = 256;
     k_fp_fill<<<(unsigned)ceil_div<int64_t>(fp->sender_cap, TB), TB, 0, s>>>(fp->seen.p, fp->sender_cap, INT_MAX);
     RAPID_KERNEL_CHECK();
@@ -602,6 +635,7 @@ int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, in
         stn.decided = 1; stn.decided_entry = -1;
         *fp->h_st.p = stn;
         RAPID_CUDA(cudaMemcpy(fp->st.p, fp->h_st.p, sizeof(FPState), cudaMemcpyHostToDevice));
+        fp->decided_host = true;
     }
     if (decided) *decided = dec;
     if (decided_hash) *decided_hash = dh1;
