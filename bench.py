@@ -133,61 +133,71 @@ def measured_hbm_peak():
 # --------------------------------------------------------------------------------------------------------------
 # CPU legs (oracle): cpu_baseline at N=1 and --impl reference
 # --------------------------------------------------------------------------------------------------------------
-def cpu_sample(args, threads, budget_s):
-    """Time the literal C++ restatement on a bounded sample of the workload; returns a dict (value = cells/s for the
-    WHOLE cluster, extrapolated linearly from the sample)."""
-    from oracle import oracle_py as orc
-    from rapid_b200 import workloads as W
-    n, nj = args.nodes, n_joiners(args)
-    t0 = time.time()
-    hb, off, ports = W.packed_endpoints(0, n + nj)
-    u = orc.Universe()
-    tags = u.add_bulk(hb, off, ports)
-    hi, lo = W.node_ids(0, n)
-    view = orc.MembershipView(u, K, tags[:n], hi, lo)
-    cfg = view.getCurrentConfigurationId()
-    obs = lambda ids: view.tables(ids)[0]
-    joiner_obs = np.asarray([view.getExpectedObserversOf(n + j) for j in range(nj)], np.int32).reshape(nj, K)
-    ring0 = np.asarray(view.getRing(0), np.int32) if args.workload == "c3" else None
-    b = make_batch(args, W, obs, joiner_obs, ring0)
-    A = len(b)
-    setup_s = time.time() - t0
-    cfgs = np.full(A, cfg, np.int64)
-    # apply: R_s receivers x the full batch; grow the sample until it costs ~budget/2
-    Rs = threads * 2
-    while True:
-        sim = orc.ClusterSim(view, K, H, L, Rs)
-        o_len, o_ann, o_ids, o_off = sim.apply_batch(b.src, b.dst, b.ring, b.status, cfgs, threads=threads)
-        t_apply = sim.last_seconds
-        if t_apply > budget_s / 4 or Rs >= 64 * threads:
-            break
-        Rs *= 4
-    assert (o_len == len(b.expected_cut)).all(), "oracle did not converge to the expected cut"
-    live = int(n - int(b.blocked.sum()))
-    apply_whole = t_apply * live / Rs
-    # tally: `threads` nodes x V_s of the `live` identical votes
-    prop = o_ids[o_off[0]: o_off[1]]
-    Vs = 64
-    while True:
-        senders = np.arange(Vs, dtype=np.int32)
-        nd, dec, rec, t_tally = orc.sim_tally(u, cfg, n, threads, senders, np.full(Vs, cfg, np.int64),
-                                              np.zeros(Vs, np.int32), np.array([0, len(prop)], np.int32), prop, threads=threads)
-        if t_tally > budget_s / 4 or Vs >= live:
-            break
-        Vs = min(live, Vs * 4)
-    tally_whole = t_tally * (live / threads) * (live / Vs)
-    whole = apply_whole + tally_whole
-    return {
-        "value": A / whole, "unit": UNIT, "cores": threads, "kind": "port",
-        "apply_only_value": A / apply_whole,
-        "sample": ("literal C++ restatement of MultiNodeCutDetector/MembershipService batch handler/FastPaxos tally "
-                   "(oracle/, g++ -O2; the Java reference cannot run here: no JDK).  apply: %d of %d live virtual nodes x "
-                   "the full %d-cell batch on %d threads = %.3f s; tally: %d nodes x %d of %d votes (each vote re-hashes "
-                   "the %d-endpoint proposal list like List.hashCode) = %.3f s; both extrapolated linearly to all %d "
-                   "nodes and votes (whole job %.3g s, of which tally %.3g s)"
-                   % (Rs, live, A, threads, t_apply, threads, Vs, live, len(prop), t_tally, live, whole, tally_whole)),
-        "setup_s": round(setup_s, 1),
-    }, A
+class CpuProblem:
+    """The workload inside the oracle (built once; construction is outside every timed region)."""
+
+    def __init__(self, args):
+        from oracle import oracle_py as orc
+        from rapid_b200 import workloads as W
+        self.orc, self.args = orc, args
+        n, nj = args.nodes, n_joiners(args)
+        t0 = time.time()
+        hb, off, ports = W.packed_endpoints(0, n + nj)
+        self.u = orc.Universe()
+        tags = self.u.add_bulk(hb, off, ports)
+        hi, lo = W.node_ids(0, n)
+        self.view = orc.MembershipView(self.u, K, tags[:n], hi, lo)
+        self.cfg = self.view.getCurrentConfigurationId()
+        obs = lambda ids: self.view.tables(ids)[0]
+        joiner_obs = np.asarray([self.view.getExpectedObserversOf(n + j) for j in range(nj)], np.int32).reshape(nj, K)
+        ring0 = np.asarray(self.view.getRing(0), np.int32) if args.workload == "c3" else None
+        self.b = make_batch(args, W, obs, joiner_obs, ring0)
+        self.A = len(self.b)
+        self.cfgs = np.full(self.A, self.cfg, np.int64)
+        self.live = int(n - int(self.b.blocked.sum()))
+        self.setup_s = time.time() - t0
+        self.Rs, self.Vs = None, None       # sample sizes, fixed by the first measurement
+
+    def measure(self, threads, budget_s):
+        """Time the literal C++ restatement on a bounded sample; value = cells/s for the WHOLE cluster (extrapolated)."""
+        orc, b, n = self.orc, self.b, self.args.nodes
+        # apply: R_s receivers x the full batch (sample grown until it costs ~budget/4)
+        Rs = self.Rs or threads * 2
+        while True:
+            sim = orc.ClusterSim(self.view, K, H, L, Rs)
+            o_len, o_ann, o_ids, o_off = sim.apply_batch(b.src, b.dst, b.ring, b.status, self.cfgs, threads=threads)
+            t_apply = sim.last_seconds
+            if self.Rs or t_apply > budget_s / 4 or Rs >= 64 * threads:
+                break
+            Rs *= 4
+        self.Rs = Rs
+        assert (o_len == len(b.expected_cut)).all(), "oracle did not converge to the expected cut"
+        apply_whole = t_apply * self.live / Rs
+        # tally: `threads` FastPaxos instances x V_s of the `live` identical votes
+        prop = o_ids[o_off[0]: o_off[1]]
+        Vs = self.Vs or 64
+        while True:
+            senders = np.arange(Vs, dtype=np.int32)
+            nd, dec, rec, t_tally = orc.sim_tally(self.u, self.cfg, n, threads, senders, np.full(Vs, self.cfg, np.int64),
+                                                  np.zeros(Vs, np.int32), np.array([0, len(prop)], np.int32), prop, threads=threads)
+            if self.Vs or t_tally > budget_s / 4 or Vs >= self.live:
+                break
+            Vs = min(self.live, Vs * 4)
+        self.Vs = Vs
+        tally_whole = t_tally * (self.live / threads) * (self.live / Vs)
+        whole = apply_whole + tally_whole
+        return {
+            "value": self.A / whole, "unit": UNIT, "cores": threads, "kind": "port",
+            "apply_only_value": self.A / apply_whole,
+            "sample": ("literal C++ restatement of MultiNodeCutDetector / MembershipService batch handler / FastPaxos tally "
+                       "(oracle/, g++ -O2; the Java reference cannot run here: no JDK).  apply: %d of %d live virtual nodes x "
+                       "the full %d-cell batch on %d threads = %.3f s; tally: %d nodes x %d of %d votes (each vote re-hashes "
+                       "the %d-endpoint proposal list like List.hashCode) = %.3f s; both extrapolated linearly to all %d "
+                       "nodes and votes (whole job %.3g s, of which tally %.3g s)"
+                       % (Rs, self.live, self.A, threads, t_apply, threads, Vs, self.live, len(prop), t_tally, self.live,
+                          whole, tally_whole)),
+            "setup_s": round(self.setup_s, 1),
+        }
 
 
 def run_reference(args):
@@ -197,25 +207,28 @@ def run_reference(args):
     from oracle import oracle_py as orc
     orc.build()
     threads = max(1, orc.hardware_threads())
-    W_ = args.warmup
+    prob = CpuProblem(args)
+    log("[reference] setup %.1fs (n=%d, cells=%d), %d threads" % (prob.setup_s, args.nodes, prob.A, threads))
+    n_iter = args.warmup + args.steps
+    per = max(1.0, min(args.cpu_seconds, 150.0 / max(1, n_iter)))      # the whole run stays within a few minutes
     vals = []
     t_start = time.time()
-    per = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + W_)))
-    for i in range(W_ + args.steps):
-        d, A = cpu_sample(args, threads, per)
-        if i >= W_:
+    for i in range(n_iter):
+        d = prob.measure(threads, per)
+        if i >= args.warmup:
             vals.append(d)
-        if time.time() - t_start > 240 and len(vals) >= 1:
+        if time.time() - t_start > 200 and vals:
             break
     v = float(np.mean([x["value"] for x in vals]))
-    d = vals[-1]
+    d = dict(vals[-1])
     d["value"] = v
-    S = n_joiners(args) * 2 if args.workload == "c5" else 0
+    A = prob.A
+    S = len(np.unique(prob.b.dst))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
-        "warmup": W_, "ms_per_step": 1e3 * A / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": 1e3 * A / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u16", "data": "synthetic",
-        "config": {"workload": workload_name(args, A, S), "nodes": args.nodes, "cells": A, "K": K, "H": H, "L": L},
+        "config": {"workload": workload_name(args, A, S), "nodes": args.nodes, "cells": A, "subjects": S, "K": K, "H": H, "L": L},
         "cpu_baseline": d,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -384,8 +397,7 @@ def run_ours(args):
             try:
                 from oracle import oracle_py as orc
                 orc.build()
-                d, _ = cpu_sample(args, max(1, orc.hardware_threads()), args.cpu_seconds)
-                line["cpu_baseline"] = d
+                line["cpu_baseline"] = CpuProblem(args).measure(max(1, orc.hardware_threads()), args.cpu_seconds)
             except Exception as e:       # the baseline is a reported extra; never lose the GPU line over it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
         emit(line)
