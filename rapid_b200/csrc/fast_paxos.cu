@@ -48,7 +48,8 @@ struct FP {
     DevBuf<int64_t> v_cfg;
     DevBuf<uint64_t> v_h1, v_h2;
     // sharded tally
-    DevBuf<int32_t> hist;                 // [65536]
+    DevBuf<int32_t> hist;                 // [65536] (refinement path)
+    DevBuf<unsigned long long> sumbuf;    // [(4096 + 1) * 8] the single all-reduce buffer
     DevBuf<unsigned long long> mm;        // [8] max / ~min verification words
     PinnedBuf<unsigned long long> h_mm;
     PinnedBuf<unsigned char> h_res_raw;
@@ -379,6 +380,72 @@ __global__ void k_fp_result(const FPState* __restrict__ st, const uint64_t* __re
     *out = r;
 }
 
+// ---- sharded tally, the single all-reduce: per 12-bit bucket of the fingerprint, SUMS of (count, h1 hi/lo, h2 hi/lo, len,
+// check hi/lo) weighted by the vote counts.  After ncclAllReduce(sum) a bucket that reached the quorum and holds ONE
+// proposal gives it back by exact division, and the independent check word proves there was only one (two different
+// proposals averaging to integers would have to collide on a 64-bit mix as well).
+constexpr int SUM_BUCKETS = 4096, SUM_WORDS = 8;
+
+__device__ __forceinline__ uint64_t fp_check_word(uint64_t h1, uint64_t h2, uint64_t len) {
+    return splitmix64(h1 ^ rotl64(h2, 17) ^ (len * 0x9E3779B97F4A7C15ULL));
+}
+
+__global__ void k_fp_hist_sum(uint32_t T, const int32_t* __restrict__ t_state, const uint64_t* __restrict__ t_h1,
+                              const uint64_t* __restrict__ t_h2, const int32_t* __restrict__ t_len,
+                              const int32_t* __restrict__ t_count, const FPState* __restrict__ st,
+                              unsigned long long* __restrict__ buf) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) buf[(size_t)SUM_BUCKETS * SUM_WORDS] = (unsigned long long)st->votes_received;
+    if (e >= T || t_state[e] != 2) return;
+    const unsigned long long c = (unsigned long long)t_count[e];
+    if (c == 0) return;
+    const uint64_t h1 = t_h1[e], h2 = t_h2[e], len = (uint64_t)(uint32_t)t_len[e], m = fp_check_word(h1, h2, len);
+    unsigned long long* b = buf + (size_t)(h1 >> 52) * SUM_WORDS;
+    atomicAdd(b + 0, c);
+    atomicAdd(b + 1, c * (h1 >> 32)); atomicAdd(b + 2, c * (h1 & 0xFFFFFFFFull));
+    atomicAdd(b + 3, c * (h2 >> 32)); atomicAdd(b + 4, c * (h2 & 0xFFFFFFFFull));
+    atomicAdd(b + 5, c * len);
+    atomicAdd(b + 6, c * (m >> 32)); atomicAdd(b + 7, c * (m & 0xFFFFFFFFull));
+}
+
+struct FPSumResult {
+    FPResult r;
+    int32_t ambiguous;       // a bucket reached the quorum but holds more than one proposal
+    int32_t pad;
+};
+
+__global__ void k_fp_decide_sum_impl(const unsigned long long* __restrict__ buf, unsigned long long Q, FPSumResult* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= SUM_BUCKETS) return;
+    const unsigned long long* w = buf + (size_t)b * SUM_WORDS;
+    const unsigned long long c = w[0];
+    if (c < Q || c == 0) return;
+    bool ok = true;
+    for (int q = 1; q < SUM_WORDS; ++q) ok = ok && (w[q] % c == 0);
+    uint64_t h1 = 0, h2 = 0, len = 0;
+    if (ok) {
+        const uint64_t a1 = w[1] / c, a2 = w[2] / c, b1 = w[3] / c, b2 = w[4] / c;
+        len = w[5] / c;
+        ok = a1 <= 0xFFFFFFFFull && a2 <= 0xFFFFFFFFull && b1 <= 0xFFFFFFFFull && b2 <= 0xFFFFFFFFull && len <= 0x7FFFFFFFull;
+        h1 = (a1 << 32) | a2; h2 = (b1 << 32) | b2;
+        if (ok) {
+            const uint64_t m = fp_check_word(h1, h2, len);
+            ok = (w[6] / c == (m >> 32)) && (w[7] / c == (m & 0xFFFFFFFFull)) && ((h1 >> 52) == (uint64_t)b);
+        }
+    }
+    if (ok) {
+        out->r.decided = 1; out->r.h1 = h1; out->r.h2 = h2; out->r.len = (int32_t)len; out->r.count = (int32_t)c;
+    } else {
+        out->ambiguous = 1;
+    }
+}
+
+__global__ void k_fp_sum_begin(const unsigned long long* __restrict__ buf, FPSumResult* __restrict__ out) {
+    out->r.decided = 0; out->r.len = 0; out->r.count = 0; out->r.h1 = 0; out->r.h2 = 0;
+    out->r.received = (int32_t)buf[(size_t)SUM_BUCKETS * SUM_WORDS];
+    out->ambiguous = 0; out->pad = 0;
+}
+
 static int32_t fp_reset_call_state(FP* fp) {        // per-call fields only; no host round trip
     k_fp_begin<<<1, 1, 0, fp->stream>>>(fp->st.p);
     RAPID_KERNEL_CHECK();
@@ -388,6 +455,7 @@ static int32_t fp_reset_call_state(FP* fp) {        // per-call fields only; no 
 // votes are device arrays here
 static int32_t tally_device(FP* fp, int64_t n, const int32_t* sender, const int64_t* vcfg, const uint64_t* h1,
                             const uint64_t* h2, const int32_t* len, int allow_skip, bool exact_order) {
+    // exact_order == false (sharded tally): senders are this rank's own members, counts only -> no mid-call readback
     cudaStream_t s = fp->stream;
     const int TB = 256;
     fp->last_launches = 0;
@@ -402,6 +470,13 @@ static int32_t tally_device(FP* fp, int64_t n, const int32_t* sender, const int6
     k_fp_candidates<<<gt, TB, 0, s>>>(fp->T, fp->t_count.p, fp->t_call.p, (int32_t)fp->Q, fp->st.p);
     RAPID_KERNEL_CHECK();
     fp->last_launches += 3;
+    if (!exact_order) {
+        k_fp_apply<<<g, TB, 0, s>>>(n, sender, fp->ent.p, fp->st.p, 0, fp->seen.p, fp->t_count.p, fp->st.p);
+        k_fp_zero_call<<<gt, TB, 0, s>>>(fp->T, fp->t_call.p);
+        RAPID_KERNEL_CHECK();
+        fp->last_launches += 2;
+        return RAPID_OK;
+    }
     RAPID_CUDA(cudaMemcpyAsync(fp->h_st.p, fp->st.p, sizeof(FPState), cudaMemcpyDeviceToHost, s));
     RAPID_CUDA(cudaStreamSynchronize(s));
     const FPState st = *fp->h_st.p;
@@ -490,8 +565,8 @@ int32_t rapid_fp_create(rapid_fp** out, int64_t cfg_id, int64_t membership_size,
         if ((rc = fp->hist.reserve(65536))) break;
         if ((rc = fp->mm.reserve(8))) break;
         if ((rc = fp->h_mm.reserve(8))) break;
-        if ((rc = fp->d_res_raw.reserve(64))) break;
-        if ((rc = fp->h_res_raw.reserve(64))) break;
+        if ((rc = fp->d_res_raw.reserve(128))) break;
+        if ((rc = fp->h_res_raw.reserve(128))) break;
         const int TB = 256;
         k_fp_fill<<<(unsigned)ceil_div<int64_t>(sender_capacity, TB), TB, 0, fp->stream>>>(fp->seen.p, sender_capacity, INT_MAX);
         cudaMemsetAsync(fp->t_state.p, 0, T * sizeof(int32_t), fp->stream);
@@ -587,6 +662,43 @@ int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, in
     // single fingerprint with a 6-word all-reduce (max); refine digit by digit only if two fingerprints share it.
     if (comm->device != fp->device) { set_error("comm and fp live on different devices"); return RAPID_EINVAL; }
     const unsigned gt = (unsigned)ceil_div<uint32_t>(fp->T, TB);
+    {   // the common case: ONE all-reduce, one readback
+        const size_t words = (size_t)(SUM_BUCKETS + 1) * SUM_WORDS;
+        RAPID_CHECK(fp->sumbuf.reserve(words));
+        RAPID_CUDA(cudaMemsetAsync(fp->sumbuf.p, 0, words * sizeof(unsigned long long), s));
+        k_fp_hist_sum<<<gt, TB, 0, s>>>(fp->T, fp->t_state.p, fp->t_h1.p, fp->t_h2.p, fp->t_len.p, fp->t_count.p, fp->st.p, fp->sumbuf.p);
+        RAPID_KERNEL_CHECK();
+        RAPID_NCCL(g_nccl.AllReduce(fp->sumbuf.p, fp->sumbuf.p, words, NCCL_UINT64, NCCL_SUM, comm->comm, s));
+        FPSumResult* dres = (FPSumResult*)fp->d_res_raw.p;
+        k_fp_sum_begin<<<1, 1, 0, s>>>(fp->sumbuf.p, dres);
+        k_fp_decide_sum_impl<<<SUM_BUCKETS / TB, TB, 0, s>>>(fp->sumbuf.p, (unsigned long long)fp->Q, dres);
+        RAPID_KERNEL_CHECK();
+        fp->last_launches += 3;
+        RAPID_CUDA(cudaMemcpyAsync(fp->h_res_raw.p, dres, sizeof(FPSumResult), cudaMemcpyDeviceToHost, s));
+        RAPID_CUDA(cudaEventRecord(fp->ev1, s));
+        RAPID_CUDA(cudaStreamSynchronize(s));
+        const FPSumResult res = *(const FPSumResult*)fp->h_res_raw.p;
+        if (!res.ambiguous) {
+            cudaEventElapsedTime(&fp->last_ms, fp->ev0, fp->ev1);
+            if (res.r.decided) {      // remember the decision locally so later votes are ignored (:138)
+                FPState stn;
+                memset(&stn, 0, sizeof(stn));
+                stn.decided = 1; stn.decided_entry = -1; stn.votes_received = res.r.received; stn.i_star = INT_MAX; stn.bad_sender = -1;
+                *fp->h_st.p = stn;
+                RAPID_CUDA(cudaMemcpyAsync(fp->st.p, fp->h_st.p, sizeof(FPState), cudaMemcpyHostToDevice, s));
+                RAPID_CUDA(cudaStreamSynchronize(s));
+                fp->decided_host = true;
+            }
+            if (decided) *decided = res.r.decided;
+            if (decided_hash) *decided_hash = res.r.h1;
+            if (decided_hash2) *decided_hash2 = res.r.h2;
+            if (decided_len) *decided_len = res.r.len;
+            if (decided_count) *decided_count = res.r.count;
+            if (votes_received) *votes_received = res.r.received;
+            return RAPID_OK;
+        }
+        // two proposals share a quorum-sized bucket: fall through to the digit-by-digit refinement
+    }
     Prefix pf;
     pf.n = 0;
     int32_t dec = 0, dcount = 0, dlen = 0;

@@ -62,7 +62,6 @@ WORKER = textwrap.dedent("""
         w = S.verification_words(h1s, h2s, lens, bucket).view(np.int64).copy()
         # max over uint64 via two int64 halves is overkill here: gloo has no uint64; compare as (hi32, lo32) pairs
         t = torch.from_numpy(np.stack([(w.view(np.uint64) >> np.uint64(32)).astype(np.int64), (w.view(np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.int64)], 1))
-        key = t[:, 0] * (1 << 32) // (1 << 32)                       # keep simple: gather and take max in numpy
         gathered = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(gathered, t)
         allw = np.stack([(g[:, 0].numpy().astype(np.uint64) << np.uint64(32)) | g[:, 1].numpy().astype(np.uint64) for g in gathered])
@@ -72,6 +71,11 @@ WORKER = textwrap.dedent("""
     assert decided and (dh1, dh2, dlen) == (want[0], want[1], len(b.expected_cut)), (decided, dh1, want)
     live = n - int(b.blocked.sum())
     assert dcount == live - 1                                         # everyone but the dissenter
+    # the single-all-reduce protocol the library uses first: count-weighted sums, exact division, check word
+    sb = torch.from_numpy(S.sum_buffer_of(h1s, h2s, lens, len(h1s)).view(np.int64).copy())
+    dist.all_reduce(sb)                                               # int64 sums wrap exactly like the device's uint64
+    d2 = S.decide_sum(sb.numpy().view(np.uint64), Q)
+    assert d2[0] and not d2[6] and (d2[1], d2[2], d2[3], d2[4], d2[5]) == (want[0], want[1], len(b.expected_cut), live - 1, live), d2
     # single-instance reference: one literal FastPaxosTally over all votes decides the same cut
     if rank == 0:
         fp = orc.FastPaxosTally(u, cfg, n)
