@@ -51,21 +51,6 @@ constexpr uint32_t MX_ON = 1u, MX_NEG = 2u, MX_HAS_E = 4u, MX_DONE = 8u;
 constexpr uint32_t PF_SEEN = 1u;      // a valid DOWN cell was delivered
 constexpr uint32_t PF_NEGINF = 2u;    // a subject already in the unstable band stayed there (its t_L is "before the batch")
 
-struct SubjDesc {                     // 48 bytes, one per subject of the batch
-    int32_t slot;
-    uint16_t bmask;                   // rings reported in this batch
-    uint8_t nr;                       // number of distinct rings
-    uint8_t any_down;
-    uint32_t tLf, tHf;                // for a fresh subject (no earlier reports): moment of the L-th / H-th distinct ring, 0 if none
-    uint32_t seg_begin, seg_len;      // its cells in the slot-sorted arrays
-    uint64_t mix1, mix2;              // fp_mix1 / fp_mix2 of the subject id
-    uint64_t pad_;
-};
-struct SubjWalk {                     // first-occurrence ring sequence in arrival order (uniform delivery)
-    uint8_t ring[16];
-    uint32_t time[16];
-};
-
 struct Partials {                     // [n_chunks][Rpad] structure of arrays
     uint4* cnt;                       // x = nL | nH << 16, y = touched_pre | nUn << 16, z = flags, w = 0
     uint64_t* minTH;
@@ -75,9 +60,8 @@ struct Partials {                     // [n_chunks][Rpad] structure of arrays
 };
 
 struct Bucketed {
-    DevBuf<uint32_t> key_in, key_out;
-    DevBuf<int32_t> val_in, val_out;          // val_out = cell indices sorted by slot
-    DevBuf<int32_t> head;                     // head flags -> exclusive scan
+    DevBuf<int32_t> sidx;                     // cell indices grouped by subject (arrival order inside a subject)
+    DevBuf<int32_t> seg_cnt, seg_pos;         // [slot] scratch of the prepare kernel (seg_cnt all zero between batches)
     DevBuf<SubjDesc> desc;
     DevBuf<SubjWalk> walk;
     DevBuf<uint8_t> s_ring, s_status;         // per sorted cell
@@ -982,6 +966,23 @@ void bucketed_destroy(CD* cd) {
     if (cd->bucketed_state) { delete static_cast<Bucketed*>(cd->bucketed_state); cd->bucketed_state = nullptr; }
 }
 
+int32_t bucketed_prep_buffers(CD* cd, int64_t A, PrepOut* po) {
+    Bucketed* b = state(cd);
+    const size_t a = (size_t)std::max<int64_t>(A, 1);
+    RAPID_CHECK(b->desc.reserve(a)); RAPID_CHECK(b->walk.reserve(a));
+    RAPID_CHECK(b->sidx.reserve(a)); RAPID_CHECK(b->s_ring.reserve(a)); RAPID_CHECK(b->s_status.reserve(a));
+    const size_t slots = (size_t)std::min<int64_t>((int64_t)cd->S + A, std::max<int64_t>(cd->ntot_cap, 1));
+    RAPID_CHECK(b->batch_index.reserve(slots));
+    RAPID_CHECK(b->seg_pos.reserve(slots));
+    if (slots > b->seg_cnt.cap) {
+        RAPID_CHECK(b->seg_cnt.reserve(slots));
+        RAPID_CUDA(cudaMemsetAsync(b->seg_cnt.p, 0, b->seg_cnt.cap * sizeof(int32_t), cd->stream));
+    }
+    po->desc = b->desc.p; po->walk = b->walk.p; po->sidx = b->sidx.p; po->s_ring = b->s_ring.p; po->s_status = b->s_status.p;
+    po->batch_index = b->batch_index.p; po->seg_cnt = b->seg_cnt.p; po->seg_pos = b->seg_pos.p;
+    return RAPID_OK;
+}
+
 int32_t bucketed_pair_count(const CD* cd) {
     if (!cd->bucketed_state) return 0;
     const Bucketed* b = static_cast<const Bucketed*>(cd->bucketed_state);
@@ -1037,26 +1038,6 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
 
     int n_chunks = 1, chunk = std::max(Sb, 1);
     if (Sb > 0) {
-        // ---- regroup the batch by subject ---------------------------------------------------------------------------
-        RAPID_CHECK(b->key_in.reserve((size_t)A)); RAPID_CHECK(b->key_out.reserve((size_t)A));
-        RAPID_CHECK(b->val_in.reserve((size_t)A)); RAPID_CHECK(b->val_out.reserve((size_t)A));
-        RAPID_CHECK(b->head.reserve((size_t)A));
-        RAPID_CHECK(b->s_ring.reserve((size_t)A)); RAPID_CHECK(b->s_status.reserve((size_t)A));
-        RAPID_CHECK(b->desc.reserve((size_t)Sb)); RAPID_CHECK(b->walk.reserve((size_t)Sb));
-        RAPID_CHECK(b->batch_index.reserve(std::max<size_t>(cd->S_cap, 1)));
-        const unsigned ga = (unsigned)ceil_div<int64_t>(A, TB);
-        k_sort_keys<<<ga, TB, 0, s>>>(A, cd->cell_slot.p, b->key_in.p, b->val_in.p);
-        size_t tmp_bytes = 0;
-        RAPID_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, b->key_in.p, b->key_out.p, b->val_in.p, b->val_out.p, (int)A, 0, 32, s));
-        RAPID_CHECK(cd->cub_tmp.reserve(std::max<size_t>(tmp_bytes, 1)));
-        RAPID_CUDA(cub::DeviceRadixSort::SortPairs(cd->cub_tmp.p, tmp_bytes, b->key_in.p, b->key_out.p, b->val_in.p, b->val_out.p, (int)A, 0, 32, s));
-        const unsigned gv = (unsigned)ceil_div<int32_t>(n_valid, TB);
-        k_heads<<<gv, TB, 0, s>>>(n_valid, b->key_out.p, b->head.p);
-        RAPID_CHECK(exclusive_scan_i32(b->head.p, n_valid, cd->scan_sums, nullptr, s, nullptr));
-        k_build_desc<<<gv, TB, 0, s>>>(n_valid, b->key_out.p, b->val_out.p, b->head.p, cd->cur_ring_dev, cd->cur_status_dev,
-                                       cd->slot_subject.p, cd->L, cd->H, b->desc.p, b->walk.p, b->s_ring.p, b->s_status.p, b->batch_index.p);
-        RAPID_KERNEL_CHECK();
-        cd->last_launches += 6;   // sort keys, radix sort (counted once), heads, scan, descriptors
         // ---- grid: tiles x subject chunks, a few waves of 148 SMs -----------------------------------------------------
         const int rblocks = uniform ? b->n_tiles : (int)(cd->Rpad / GEN_THREADS);
         // Pick the number of subject chunks so that (tiles x chunks) blocks fill whole waves of resident blocks:
@@ -1106,7 +1087,7 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
     ap.K = cd->K; ap.H = cd->H; ap.L = cd->L; ap.R = cd->R; ap.rbegin = cd->rbegin;
     ap.rflags = cd->rflags.p; ap.dl = dl; ap.Sb = Sb; ap.chunk = chunk;
     ap.desc = b->desc.p; ap.walk = b->walk.p; ap.slot_subject = cd->slot_subject.p;
-    ap.sidx = b->val_out.p; ap.s_ring = b->s_ring.p; ap.s_status = b->s_status.p;
+    ap.sidx = b->sidx.p; ap.s_ring = b->s_ring.p; ap.s_status = b->s_status.p;
     ap.part = part; ap.n_tiles = b->n_tiles; ap.in_list = b->in_list.p; ap.pre_pairs = b->pre_pairs.p;
     ap.S_before = cd->S_before;
     ap.pre_count = b->pre_count.p; ap.pre_cap = (int32_t)std::min<size_t>(b->in_list_slots * (size_t)b->n_tiles, 0x7fffffff);

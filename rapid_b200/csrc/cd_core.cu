@@ -336,17 +336,12 @@ static int32_t preprocess(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev
     *cd->h_counts.p = init;
     RAPID_CUDA(cudaMemcpyAsync(cd->counts.p, cd->h_counts.p, sizeof(BatchCounts), cudaMemcpyHostToDevice, s));
     if (A > 0) {
-        const int TB = 256;
-        const unsigned g = (unsigned)ceil_div<int64_t>(A, TB);
-        k_filter_first<<<g, TB, 0, s>>>(A, dst_dev, ring_dev, status_dev, cfg_dev, cfg, cd->raw ? 1 : 0, cd->K, cd->view->n,
-                                        cd->view->n + cd->view->nj, cd->slot_of.p, cd->first_idx.p, cd->cell_slot.p, cd->counts.p);
-        k_mark_new<<<g, TB, 0, s>>>(A, dst_dev, cd->cell_slot.p, cd->slot_of.p, cd->first_idx.p, cd->scan_tmp.p);
-        RAPID_CHECK(exclusive_scan_i32(cd->scan_tmp.p, A, cd->scan_sums, cd->scan_tmp.p + A, s, nullptr));
-        k_assign_slots<<<g, TB, 0, s>>>(A, dst_dev, cd->cell_slot.p, cd->scan_tmp.p, cd->scan_tmp.p + A, cd->S, cd->slot_of.p,
-                                        cd->first_idx.p, cd->slot_subject.p, cd->counts.p);
-        k_cell_slots<<<g, TB, 0, s>>>(A, dst_dev, cd->slot_of.p, cd->cell_slot.p, cd->touch.p, ++cd->batch_serial, cd->counts.p);
-        RAPID_KERNEL_CHECK();
-        cd->last_launches += 5;
+        PrepOut po;
+        const bool regroup = cd->bucketed;
+        if (regroup) RAPID_CHECK(bucketed_prep_buffers(cd, A, &po));
+        RAPID_CHECK(prepare_batch(cd, cfg, A, dst_dev, ring_dev, status_dev, cfg_dev, regroup ? &po : nullptr));
+    } else {
+        ++cd->batch_serial;
     }
     RAPID_CUDA(cudaMemcpyAsync(cd->h_counts.p, cd->counts.p, sizeof(BatchCounts), cudaMemcpyDeviceToHost, s));
     RAPID_CUDA(cudaStreamSynchronize(s));

@@ -54,6 +54,7 @@ struct CD {
     DevBuf<int32_t> slot_subject;     // [ntot_cap] slot -> id
     DevBuf<int32_t> touch;            // [ntot_cap] slot -> serial of the last batch that had a valid cell for it
     int32_t batch_serial = 0;
+    int prep_grid_max = 0;            // co-resident blocks of the cooperative prepare kernel
 
     DevBuf<int32_t> n_pre;            // [R] updatesInProgress
     DevBuf<int32_t> n_prop;           // [R] proposalCount (sweep handles)
@@ -105,7 +106,39 @@ struct DeliveryDev {
     uint64_t perm_seed = 0;
 };
 
+// ---- the batch regrouped by subject (built by cd_prepare.cu, consumed by cd_bucketed.cu) -------------------------
+struct SubjDesc {                     // 48 bytes, one per subject of the batch
+    int32_t slot;
+    uint16_t bmask;                   // rings reported in this batch
+    uint8_t nr;                       // number of distinct rings
+    uint8_t any_down;
+    uint32_t tLf, tHf;                // for a fresh subject (no earlier reports): moment of the L-th / H-th distinct ring, 0 if none
+    uint32_t seg_begin, seg_len;      // its cells in the slot-sorted arrays
+    uint64_t mix1, mix2;              // fp_mix1 / fp_mix2 of the subject id
+    uint64_t pad_;
+};
+struct SubjWalk {                     // first-occurrence ring sequence in arrival order (uniform delivery)
+    uint8_t ring[16];
+    uint32_t time[16];
+};
+
+struct PrepOut {                      // where the prepare kernel writes the regrouped batch
+    SubjDesc* desc;
+    SubjWalk* walk;
+    int32_t* sidx;                    // cell indices grouped by subject, ascending within a subject
+    uint8_t* s_ring;
+    uint8_t* s_status;
+    int32_t* batch_index;             // [slot] -> index of the subject in the batch
+    int32_t* seg_cnt;                 // [slot] scratch, all zero between batches
+    int32_t* seg_pos;                 // [slot] scratch
+};
+
+// implemented in cd_prepare.cu: filter + slot dictionary (+ regrouping by subject when po != nullptr) in ONE cooperative launch
+int32_t prepare_batch(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev, const uint8_t* ring_dev, const uint8_t* status_dev,
+                      const int64_t* cfg_dev, const PrepOut* po);
 // implemented in cd_bucketed.cu
+int32_t bucketed_prep_buffers(CD* cd, int64_t A, PrepOut* po);
+
 int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCounts& bc);
 void bucketed_destroy(CD* cd);
 int32_t bucketed_clear(CD* cd);
