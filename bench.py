@@ -367,7 +367,7 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         fresh = True   # every step starts a new epoch: all subjects are new, their state is written, never read
-        alg = (2 if fresh else 4) * S * R + 5 * R + 40 * R      # mask bytes + flags/blocked read + per-receiver partial
+        alg = (2 if fresh else 4) * S * R + 5 * R      # mask bytes written + rflags/blocked read (fresh subjects: no per-receiver partials)
         achieved = alg / (main_per * 1e-3) / 1e9 if main_per > 0 else 0.0
         line = {
             "metric": METRIC, "value": A / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": G, "steps": args.steps,

@@ -10,7 +10,7 @@ def launches(path):
         lines = [l for l in f if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
     names = [x["Kernel Name"] for x in rows]
-    last = [i for i, n in enumerate(names) if "k_filter_first" in n][-1]
+    last = [i for i, n in enumerate(names) if "k_prepare" in n or "k_filter_first" in n][-1]
     # one step = clear()/reset kernels are outside; from k_filter_first to the end of the tally
     seg = rows[last:]
     tot = sum(float(x["Metric Value"]) for x in seg)

@@ -51,12 +51,20 @@ constexpr uint32_t MX_ON = 1u, MX_NEG = 2u, MX_HAS_E = 4u, MX_DONE = 8u;
 constexpr uint32_t PF_SEEN = 1u;      // a valid DOWN cell was delivered
 constexpr uint32_t PF_NEGINF = 2u;    // a subject already in the unstable band stayed there (its t_L is "before the batch")
 
+struct ChunkAcc {                     // what the FRESH subjects of a chunk contribute to EVERY active receiver
+    uint32_t nLH, tpUn, fl, minTH, minTLun, pad_;
+    uint64_t h1, h2;
+};
+
 struct Partials {                     // [n_chunks][Rpad] structure of arrays
     uint4* cnt;                       // x = nL | nH << 16, y = touched_pre | nUn << 16, z = flags, w = 0
     uint64_t* minTH;
     uint64_t* minTLun;
     uint64_t* h1;
     uint64_t* h2;
+    int32_t* flag;                    // [n_chunks][n_tiles] 1 = the per-receiver partials of this (chunk, tile) were written
+    ChunkAcc* chunk;                  // [n_chunks] used for (chunk, tile) pairs whose flag is 0
+    int n_tiles;
 };
 
 struct Bucketed {
@@ -65,6 +73,8 @@ struct Bucketed {
     DevBuf<SubjDesc> desc;
     DevBuf<SubjWalk> walk;
     DevBuf<uint8_t> s_ring, s_status;         // per sorted cell
+    DevBuf<int32_t> p_flag;
+    DevBuf<ChunkAcc> p_chunk;
     DevBuf<uint4> p_cnt;
     DevBuf<uint64_t> p_minTH, p_minTLun, p_h1, p_h2;
     DevBuf<uint32_t> mx_fl;                   // [Rpad] MX_* flags
@@ -307,6 +317,7 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
     const int block_active = __syncthreads_or(act != 0);
     Acc com;                                              // carried subjects: shared by all ACTIVE receivers of this thread
     bool had_exc = false;                                 // the thread's global partial slots hold per-receiver extras
+    bool carried = false;                                 // this thread visited a carried subject (com is not just zeros)
 
     for (int base = s0; base < s1; base += STAGE) {
         const int n = min(STAGE, s1 - base);
@@ -366,6 +377,7 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                 const uint32_t andw = (w.x | ~am[0]) & (w.y | ~am[1]) & (w.z | ~am[2]) & (w.w | ~am[3]);
                 const uint32_t orw = (w.x & am[0]) | (w.y & am[1]) | (w.z & am[2]) | (w.w & am[3]);
                 const uint32_t andv = andw & (andw >> 16) & 0xFFFFu, st = (orw | (orw >> 16)) & 0xFFFFu;
+                carried = true;
                 if (andv == st) {
                     const Visit v = visit_uniform(st & RM, d, sw[i], L, H);
                     unres = accumulate(com, v, d, L, H);
@@ -406,15 +418,19 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
         __syncthreads();
         if (t < n && s_unres[t]) note_unresolved(a, tile, sd[t].slot);
     }
-    __syncthreads();
-    // fold the block-wide fresh-subject accumulators into the thread's
-    {
-        const StageAcc f = s_facc;
-        com.nL += f.nLH & 0xFFFFu; com.nH += f.nLH >> 16; com.nUn += f.tpUn >> 16;
-        com.minTH = min(com.minTH, f.minTH); com.minTLun = min(com.minTLun, f.minTLun);
-        com.h1 += f.h1; com.h2 += f.h2;
+    // Fresh subjects contribute the same to every active receiver: that goes to ONE record per chunk.  Per-receiver
+    // partials are only written by blocks in which some thread met a carried subject; k_finalize1 adds the two.
+    const int need = __syncthreads_or((carried || had_exc) ? 1 : 0);
+    if (t == 0) {
+        a.part.flag[(size_t)chunk * a.part.n_tiles + tile] = need;
+        if (tile == 0) {
+            const StageAcc f = s_facc;
+            ChunkAcc c;
+            c.nLH = f.nLH; c.tpUn = f.tpUn; c.fl = f.fl; c.minTH = f.minTH; c.minTLun = f.minTLun; c.pad_ = 0; c.h1 = f.h1; c.h2 = f.h2;
+            a.part.chunk[chunk] = c;
+        }
     }
-    // partials of this (chunk, tile): com applies to every active receiver; extras (if any) are already in place
+    if (!need) return;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const size_t at = pbase + j;
@@ -542,6 +558,14 @@ __global__ void __launch_bounds__(GEN_THREADS) k_apply_generic(const ApplyArgs a
         __syncthreads();
         if (t < n && s_unres[t]) note_unresolved(a, tile, sd[t].slot);   // a 256-receiver block lies inside one tile
     }
+    if (t == 0) {
+        if ((blockIdx.x * GEN_THREADS) % TILE_R == 0) a.part.flag[(size_t)chunk * a.part.n_tiles + tile] = 1;
+        if (blockIdx.x == 0) {
+            ChunkAcc c;
+            c.nLH = 0; c.tpUn = 0; c.fl = 0; c.minTH = T32_NONE; c.minTLun = T32_NONE; c.pad_ = 0; c.h1 = 0; c.h2 = 0;
+            a.part.chunk[chunk] = c;
+        }
+    }
     if (r < (int64_t)a.Rpad) {
         const size_t p = (size_t)chunk * a.Rpad + (size_t)r;
         a.part.cnt[p] = make_uint4(nL | (nH << 16), tp | (nUn << 16), fl, 0u);
@@ -593,7 +617,17 @@ __global__ void k_finalize1(const FinArgs a) {
     uint32_t nL = 0, nH = 0, tp = 0, nUn = 0, fl = 0;
     uint64_t minTH = T64_NONE, minTLun = T64_NONE, h1 = 0, h2 = 0;
     bool haveTH = false, haveTL = false;
+    const int tile = (int)(r / TILE_R);
     for (int c = 0; c < a.n_chunks; ++c) {
+        {   // fresh subjects of the chunk: the same for every active receiver
+            const ChunkAcc k = a.part.chunk[c];
+            const uint32_t cH = k.nLH >> 16, cUn = k.tpUn >> 16;
+            nL += k.nLH & 0xFFFFu; nH += cH; nUn += cUn; fl |= k.fl;
+            if (cH && (!haveTH || (uint64_t)k.minTH < minTH)) { minTH = k.minTH; haveTH = true; }
+            if (cUn && (!haveTL || (uint64_t)k.minTLun < minTLun)) { minTLun = k.minTLun; haveTL = true; }
+            h1 += k.h1; h2 += k.h2;
+        }
+        if (!a.part.flag[(size_t)c * a.part.n_tiles + tile]) continue;
         const size_t p = (size_t)c * a.Rpad + (size_t)r;
         const uint4 q = a.part.cnt[p];
         const uint32_t cH = q.x >> 16, cUn = q.y >> 16;
@@ -1080,7 +1114,9 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
         RAPID_CUDA(cudaMemsetAsync(b->mx_e2.p, 0, cd->Rpad * sizeof(unsigned long long), s));
         RAPID_CUDA(cudaMemsetAsync(b->mx_ec.p, 0, cd->Rpad * sizeof(int32_t), s));
     }
-    Partials part{b->p_cnt.p, b->p_minTH.p, b->p_minTLun.p, b->p_h1.p, b->p_h2.p};
+    RAPID_CHECK(b->p_flag.reserve((size_t)n_chunks * std::max(b->n_tiles, 1)));
+    RAPID_CHECK(b->p_chunk.reserve((size_t)n_chunks));
+    Partials part{b->p_cnt.p, b->p_minTH.p, b->p_minTLun.p, b->p_h1.p, b->p_h2.p, b->p_flag.p, b->p_chunk.p, b->n_tiles};
 
     ApplyArgs ap;
     ap.masks = cd->masks.p; ap.cur = cd->cur.p; ap.Rpad = cd->Rpad;
@@ -1106,9 +1142,8 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
         RAPID_KERNEL_CHECK();
         cd->last_launches += 1;
     } else {
-        RAPID_CUDA(cudaMemsetAsync(b->p_cnt.p, 0, pn * sizeof(uint4), s));
-        RAPID_CUDA(cudaMemsetAsync(b->p_h1.p, 0, pn * sizeof(uint64_t), s));
-        RAPID_CUDA(cudaMemsetAsync(b->p_h2.p, 0, pn * sizeof(uint64_t), s));
+        RAPID_CUDA(cudaMemsetAsync(b->p_flag.p, 0, (size_t)n_chunks * std::max(b->n_tiles, 1) * sizeof(int32_t), s));
+        RAPID_CUDA(cudaMemsetAsync(b->p_chunk.p, 0, (size_t)n_chunks * sizeof(ChunkAcc), s));
         cd->last_path = uniform ? 2 : 3;
     }
     RAPID_CUDA(cudaEventRecord(cd->evk1, s));

@@ -127,7 +127,7 @@ __global__ void k_fp_insert(int64_t n, const int32_t* __restrict__ sender, const
                             const int32_t* __restrict__ lenv, const int32_t* __restrict__ seen, uint32_t T,
                             int32_t* __restrict__ t_state, uint64_t* __restrict__ t_h1, uint64_t* __restrict__ t_h2,
                             int32_t* __restrict__ t_len, int32_t* __restrict__ t_call, int32_t* __restrict__ ent,
-                            FPState* __restrict__ st) {
+                            FPState* __restrict__ st, int unique_senders) {
     __shared__ int32_t s_key[16], s_val[16];
     if (threadIdx.x < 16) { s_key[threadIdx.x] = -1; s_val[threadIdx.x] = 0; }
     __syncthreads();
@@ -137,7 +137,9 @@ __global__ void k_fp_insert(int64_t n, const int32_t* __restrict__ sender, const
     int32_t len = 0;
     if (i < n) {
         const int32_t s = sender[i];
-        if (s >= 0 && s < sender_cap && !(vcfg && vcfg[i] != cfg) && seen[s] == (int32_t)i) {
+        // unique_senders: every sender appears at most once in this call (votes of a detector's own receivers), so the
+        // first-vote pass was skipped and "has not voted yet" is all there is to check
+        if (s >= 0 && s < sender_cap && !(vcfg && vcfg[i] != cfg) && (unique_senders ? seen[s] != -1 : seen[s] == (int32_t)i)) {
             valid = true;
             h1 = h1v[i];
             h2 = h2v ? h2v[i] : 0;
@@ -454,7 +456,7 @@ static int32_t fp_reset_call_state(FP* fp) {        // per-call fields only; no 
 
 // votes are device arrays here
 static int32_t tally_device(FP* fp, int64_t n, const int32_t* sender, const int64_t* vcfg, const uint64_t* h1,
-                            const uint64_t* h2, const int32_t* len, int allow_skip, bool exact_order) {
+                            const uint64_t* h2, const int32_t* len, int allow_skip, bool exact_order, bool unique_senders = false) {
     // exact_order == false (sharded tally): senders are this rank's own members, counts only -> no mid-call readback
     cudaStream_t s = fp->stream;
     const int TB = 256;
@@ -463,13 +465,16 @@ static int32_t tally_device(FP* fp, int64_t n, const int32_t* sender, const int6
     if (fp->decided_host || n == 0) return RAPID_OK;                 // :138 — everything after the decision is ignored
     RAPID_CHECK(fp->ent.reserve((size_t)n));
     const unsigned g = (unsigned)ceil_div<int64_t>(n, TB);
-    k_fp_first<<<g, TB, 0, s>>>(n, sender, vcfg, fp->cfg, fp->sender_cap, allow_skip, fp->seen.p, fp->st.p);
+    if (!unique_senders) {
+        k_fp_first<<<g, TB, 0, s>>>(n, sender, vcfg, fp->cfg, fp->sender_cap, allow_skip, fp->seen.p, fp->st.p);
+        fp->last_launches += 1;
+    }
     k_fp_insert<<<g, TB, 0, s>>>(n, sender, vcfg, fp->cfg, fp->sender_cap, h1, h2, len, fp->seen.p, fp->T, fp->t_state.p,
-                                 fp->t_h1.p, fp->t_h2.p, fp->t_len.p, fp->t_call.p, fp->ent.p, fp->st.p);
+                                 fp->t_h1.p, fp->t_h2.p, fp->t_len.p, fp->t_call.p, fp->ent.p, fp->st.p, unique_senders ? 1 : 0);
     const unsigned gt = (unsigned)ceil_div<uint32_t>(fp->T, TB);
     k_fp_candidates<<<gt, TB, 0, s>>>(fp->T, fp->t_count.p, fp->t_call.p, (int32_t)fp->Q, fp->st.p);
     RAPID_KERNEL_CHECK();
-    fp->last_launches += 3;
+    fp->last_launches += 2;
     if (!exact_order) {
         k_fp_apply<<<g, TB, 0, s>>>(n, sender, fp->ent.p, fp->st.p, 0, fp->seen.p, fp->t_count.p, fp->st.p);
         k_fp_zero_call<<<gt, TB, 0, s>>>(fp->T, fp->t_call.p);
@@ -650,7 +655,7 @@ int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, in
     k_fp_votes_from_cd<<<(unsigned)ceil_div<int64_t>(R, TB), TB, 0, s>>>(R, cd->rflags.p, cd->view->ring.p, cd->rbegin, fp->v_sender.p);
     RAPID_KERNEL_CHECK();
     // single GPU: exact arrival order = receiver order.  Sharded: counts only (order across ranks is undefined).
-    RAPID_CHECK(tally_device(fp, R, fp->v_sender.p, nullptr, cd->out_h1.p, cd->out_h2.p, cd->out_len.p, 1, comm == nullptr));
+    RAPID_CHECK(tally_device(fp, R, fp->v_sender.p, nullptr, cd->out_h1.p, cd->out_h2.p, cd->out_len.p, 1, comm == nullptr, true));
     fp->last_launches += 1;
     if (comm == nullptr) {
         RAPID_CUDA(cudaEventRecord(fp->ev1, s));
