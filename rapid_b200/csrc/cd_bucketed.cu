@@ -1025,20 +1025,40 @@ int32_t bucketed_pair_count(const CD* cd) {
     return n;
 }
 
+__global__ void k_clear_pairs(const int2* __restrict__ pairs, int32_t* __restrict__ count, int32_t cap, int32_t* __restrict__ in_list,
+                              int n_tiles) {
+    const int n = min(*count, cap);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int2 pr = pairs[e];
+        in_list[(size_t)pr.y * n_tiles + pr.x] = 0;
+    }
+}
+__global__ void k_zero_i32(int32_t* p) { *p = 0; }
+
 int32_t bucketed_clear(CD* cd) {
     if (!cd->bucketed) return RAPID_OK;
     Bucketed* b = state(cd);
     b->n_tiles = (int)(cd->Rpad / TILE_R);
-    RAPID_CHECK(b->pre_count.reserve(1));
-    RAPID_CUDA(cudaMemsetAsync(b->pre_count.p, 0, sizeof(int32_t), cd->stream));
-    if (b->in_list.p && b->in_list_slots)
-        RAPID_CUDA(cudaMemsetAsync(b->in_list.p, 0, b->in_list_slots * (size_t)b->n_tiles * sizeof(int32_t), cd->stream));
-    RAPID_CHECK(b->k3_res.reserve(cd->Rpad));
-    RAPID_CHECK(b->k3_h1.reserve(cd->Rpad));
-    RAPID_CHECK(b->k3_h2.reserve(cd->Rpad));
-    RAPID_CUDA(cudaMemsetAsync(b->k3_res.p, 0, cd->Rpad * sizeof(int32_t), cd->stream));
-    RAPID_CUDA(cudaMemsetAsync(b->k3_h1.p, 0, cd->Rpad * sizeof(unsigned long long), cd->stream));
-    RAPID_CUDA(cudaMemsetAsync(b->k3_h2.p, 0, cd->Rpad * sizeof(unsigned long long), cd->stream));
+    cudaStream_t s = cd->stream;
+    if (!b->pre_count.p) {
+        RAPID_CHECK(b->pre_count.reserve(1));
+        RAPID_CUDA(cudaMemsetAsync(b->pre_count.p, 0, sizeof(int32_t), s));
+    }
+    if (b->in_list.p && b->in_list_slots) {
+        // undo only the (tile, subject) pairs that were noted: O(#pairs), not O(slots x tiles)
+        const int32_t cap = (int32_t)std::min<size_t>(b->in_list_slots * (size_t)b->n_tiles, 0x7fffffff);
+        k_clear_pairs<<<64, 256, 0, s>>>(b->pre_pairs.p, b->pre_count.p, cap, b->in_list.p, b->n_tiles);
+        k_zero_i32<<<1, 1, 0, s>>>(b->pre_count.p);
+        RAPID_KERNEL_CHECK();
+    }
+    if (!b->k3_res.p) {      // zero once: k_finalize2 leaves them zero after every batch
+        RAPID_CHECK(b->k3_res.reserve(cd->Rpad));
+        RAPID_CHECK(b->k3_h1.reserve(cd->Rpad));
+        RAPID_CHECK(b->k3_h2.reserve(cd->Rpad));
+        RAPID_CUDA(cudaMemsetAsync(b->k3_res.p, 0, cd->Rpad * sizeof(int32_t), s));
+        RAPID_CUDA(cudaMemsetAsync(b->k3_h1.p, 0, cd->Rpad * sizeof(unsigned long long), s));
+        RAPID_CUDA(cudaMemsetAsync(b->k3_h2.p, 0, cd->Rpad * sizeof(unsigned long long), s));
+    }
     return RAPID_OK;
 }
 

@@ -268,9 +268,22 @@ __global__ void k_dump_masks(RowRef rows, int32_t S, int64_t r, uint32_t RM, con
     out_masks[s] = (uint16_t)(rows.row(s)[r] & RM);
 }
 
-__global__ void k_reset_slots(int32_t S, const int32_t* __restrict__ slot_subject, int32_t* __restrict__ slot_of) {
+__global__ void k_reset_slots(int32_t S, const int32_t* __restrict__ slot_subject, int32_t* __restrict__ slot_of,
+                              uint8_t* __restrict__ cur) {
     const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < S) slot_of[slot_subject[s]] = -1;
+    if (s < S) { slot_of[slot_subject[s]] = -1; cur[s] = 0; }
+}
+
+// clear() of every receiver's detector scalars in one launch (MultiNodeCutDetector.java:169-178 + announcedProposal = false)
+__global__ void k_clear_receivers(int64_t R, int32_t* __restrict__ n_pre, int32_t* __restrict__ n_prop, uint32_t* __restrict__ rflags,
+                                  uint64_t* __restrict__ pend_h1, uint64_t* __restrict__ pend_h2, int32_t* __restrict__ pend_cnt,
+                                  uint64_t* __restrict__ out_h1, uint64_t* __restrict__ out_h2, int32_t* __restrict__ out_len,
+                                  uint8_t* __restrict__ out_ann) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    n_pre[r] = 0; n_prop[r] = 0; rflags[r] = 0u;
+    pend_h1[r] = 0; pend_h2[r] = 0; pend_cnt[r] = 0;
+    out_h1[r] = 0; out_h2[r] = 0; out_len[r] = 0; out_ann[r] = 0;
 }
 
 // =====================================================================================================
@@ -396,12 +409,7 @@ static int32_t upload_delivery(CD* cd, int64_t A, const rapid_delivery* d, bool 
     out->words = (cd->R + 31) / 32;
     if (d->flags & RAPID_DELIVERY_BLOCKED) {
         if (!d->blocked) { set_error("delivery.blocked is NULL"); return RAPID_EINVAL; }
-        if (on_device) out->blocked = d->blocked;
-        else {
-            RAPID_CHECK(cd->d_blocked.reserve((size_t)cd->R));
-            RAPID_CUDA(cudaMemcpyAsync(cd->d_blocked.p, d->blocked, (size_t)cd->R, cudaMemcpyHostToDevice, cd->stream));
-            out->blocked = cd->d_blocked.p;
-        }
+        if (on_device) out->blocked = d->blocked;      // host arrays: the caller puts it in the staging blob
     }
     if (d->flags & RAPID_DELIVERY_BITMAP) {
         if (!d->bitmap && A) { set_error("delivery.bitmap is NULL"); return RAPID_EINVAL; }
@@ -524,33 +532,28 @@ int32_t rapid_cd_clear(rapid_cd* cd) {
     cudaStream_t s = cd->stream;
     const size_t R = cd->Rpad;
     if (cd->S > 0) {
-        k_reset_slots<<<(unsigned)ceil_div<int32_t>(cd->S, 256), 256, 0, s>>>(cd->S, cd->slot_subject.p, cd->slot_of.p);
+        k_reset_slots<<<(unsigned)ceil_div<int32_t>(cd->S, 256), 256, 0, s>>>(cd->S, cd->slot_subject.p, cd->slot_of.p, cd->cur.p);
         RAPID_KERNEL_CHECK();
         // Bucketed handles never read the state of a slot before the batch that assigns it has written it
         // (ApplyArgs::S_before), so clear() is O(#slots) there; the sweep kernel reads in place and needs zeros.
         if (!cd->bucketed)
             RAPID_CUDA(cudaMemsetAsync(cd->masks.p, 0, (size_t)cd->S * cd->nbuf * cd->Rpad * sizeof(uint16_t), s));
-        RAPID_CUDA(cudaMemsetAsync(cd->cur.p, 0, (size_t)cd->S, s));
     }
     cd->S = 0;
-    RAPID_CUDA(cudaMemsetAsync(cd->n_pre.p, 0, R * sizeof(int32_t), s));
-    RAPID_CUDA(cudaMemsetAsync(cd->n_prop.p, 0, R * sizeof(int32_t), s));
-    RAPID_CUDA(cudaMemsetAsync(cd->rflags.p, 0, R * sizeof(uint32_t), s));
-    RAPID_CUDA(cudaMemsetAsync(cd->pend_h1.p, 0, R * sizeof(uint64_t), s));
-    RAPID_CUDA(cudaMemsetAsync(cd->pend_h2.p, 0, R * sizeof(uint64_t), s));
-    RAPID_CUDA(cudaMemsetAsync(cd->pend_cnt.p, 0, R * sizeof(int32_t), s));
-    RAPID_CUDA(cudaMemsetAsync(cd->out_h1.p, 0, R * sizeof(uint64_t), s));
-    RAPID_CUDA(cudaMemsetAsync(cd->out_h2.p, 0, R * sizeof(uint64_t), s));
-    RAPID_CUDA(cudaMemsetAsync(cd->out_len.p, 0, R * sizeof(int32_t), s));
-    RAPID_CUDA(cudaMemsetAsync(cd->out_ann.p, 0, R, s));
+    k_clear_receivers<<<(unsigned)ceil_div<size_t>(R, 256), 256, 0, s>>>((int64_t)R, cd->n_pre.p, cd->n_prop.p, cd->rflags.p, cd->pend_h1.p,
+                                                                        cd->pend_h2.p, cd->pend_cnt.p, cd->out_h1.p, cd->out_h2.p,
+                                                                        cd->out_len.p, cd->out_ann.p);
+    RAPID_KERNEL_CHECK();
     RAPID_CHECK(bucketed_clear(cd));
-    RAPID_CUDA(cudaStreamSynchronize(s));
+    // no synchronisation: everything that follows runs on the same stream (the tally reads the detector's outputs only
+    // after rapid_cd_apply_batch, which synchronises)
     return RAPID_OK;
 }
 
 int32_t rapid_cd_read_outputs(const rapid_cd* cd, uint64_t* h1, uint64_t* h2, int32_t* len, uint8_t* ann) {
     if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
     DeviceGuard g(cd->device);
+    cudaStreamSynchronize(cd->stream);   // clear() and the apply calls are asynchronous on the handle's stream
     const size_t R = (size_t)cd->R;
     if (h1) RAPID_CUDA(cudaMemcpyAsync(h1, cd->out_h1.p, R * sizeof(uint64_t), cudaMemcpyDeviceToHost, cd->stream));
     if (h2) RAPID_CUDA(cudaMemcpyAsync(h2, cd->out_h2.p, R * sizeof(uint64_t), cudaMemcpyDeviceToHost, cd->stream));
@@ -572,20 +575,28 @@ int32_t rapid_cd_apply_batch_dev(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, 
     return apply_common(cd, cfg_id, n_cells, dst_dev, ring_dev, status_dev, cell_cfg_dev, dl);
 }
 
-static int32_t stage_cells(rapid_cd* cd, int64_t n, const int32_t* dst, const uint8_t* ring, const uint8_t* status, const int64_t* cfg) {
-    const size_t m = (size_t)std::max<int64_t>(n, 1);
-    RAPID_CHECK(cd->c_dst.reserve(m));
-    RAPID_CHECK(cd->c_ring.reserve(m));
-    RAPID_CHECK(cd->c_status.reserve(m));
-    if (n) {
-        RAPID_CUDA(cudaMemcpyAsync(cd->c_dst.p, dst, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, cd->stream));
-        RAPID_CUDA(cudaMemcpyAsync(cd->c_ring.p, ring, (size_t)n, cudaMemcpyHostToDevice, cd->stream));
-        RAPID_CUDA(cudaMemcpyAsync(cd->c_status.p, status, (size_t)n, cudaMemcpyHostToDevice, cd->stream));
-        if (cfg) {
-            RAPID_CHECK(cd->c_cfg.reserve(m));
-            RAPID_CUDA(cudaMemcpyAsync(cd->c_cfg.p, cfg, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, cd->stream));
-        }
-    }
+// Host arrays -> one pinned blob -> ONE host-to-device copy.  Layout: [cfg int64 x n]? [dst int32 x n] [ring u8 x n]
+// [status u8 x n] [blocked u8 x R]?  (8-byte things first so every section is naturally aligned)
+struct Staged { const int32_t* dst; const uint8_t* ring; const uint8_t* status; const int64_t* cfg; const uint8_t* blocked; };
+
+static int32_t stage_cells(rapid_cd* cd, int64_t n, const int32_t* dst, const uint8_t* ring, const uint8_t* status, const int64_t* cfg,
+                           const uint8_t* blocked, Staged* out) {
+    const size_t un = (size_t)n, R = (size_t)cd->R;
+    const size_t o_cfg = 0, o_dst = o_cfg + (cfg ? 8 * un : 0), o_ring = o_dst + 4 * un, o_status = o_ring + un;
+    const size_t o_blk = (o_status + un + 7) & ~(size_t)7, total = o_blk + (blocked ? R : 0);
+    RAPID_CHECK(cd->h_stage.reserve(std::max<size_t>(total, 8)));
+    RAPID_CHECK(cd->d_stage.reserve(std::max<size_t>(total, 8)));
+    uint8_t* h = cd->h_stage.p;
+    if (cfg) memcpy(h + o_cfg, cfg, 8 * un);
+    if (un) { memcpy(h + o_dst, dst, 4 * un); memcpy(h + o_ring, ring, un); memcpy(h + o_status, status, un); }
+    if (blocked) memcpy(h + o_blk, blocked, R);
+    if (total) RAPID_CUDA(cudaMemcpyAsync(cd->d_stage.p, h, total, cudaMemcpyHostToDevice, cd->stream));
+    const uint8_t* d = cd->d_stage.p;
+    out->cfg = cfg ? (const int64_t*)(d + o_cfg) : nullptr;
+    out->dst = (const int32_t*)(d + o_dst);
+    out->ring = d + o_ring;
+    out->status = d + o_status;
+    out->blocked = blocked ? d + o_blk : nullptr;
     return RAPID_OK;
 }
 
@@ -597,10 +608,14 @@ int32_t rapid_cd_apply_batch(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, cons
     if (!cd || n_cells < 0 || (n_cells && (!dst || !ring || !status))) { set_error("bad arguments"); return RAPID_EINVAL; }
     if (cd->raw) { set_error("RAW handles take rapid_cd_aggregate / rapid_cd_invalidate"); return RAPID_EINVAL; }
     DeviceGuard g(cd->device);
-    RAPID_CHECK(stage_cells(cd, n_cells, dst, ring, status, cell_cfg));
+    Staged st;
+    const bool has_blocked = delivery && (delivery->flags & RAPID_DELIVERY_BLOCKED);
+    if (has_blocked && !delivery->blocked) { set_error("delivery.blocked is NULL"); return RAPID_EINVAL; }
+    RAPID_CHECK(stage_cells(cd, n_cells, dst, ring, status, cell_cfg, has_blocked ? delivery->blocked : nullptr, &st));
     DeliveryDev dl;
     RAPID_CHECK(upload_delivery(cd, n_cells, delivery, false, &dl));
-    RAPID_CHECK(apply_common(cd, cfg_id, n_cells, cd->c_dst.p, cd->c_ring.p, cd->c_status.p, cell_cfg ? cd->c_cfg.p : nullptr, dl));
+    if (has_blocked) dl.blocked = st.blocked;          // travelled in the staging blob
+    RAPID_CHECK(apply_common(cd, cfg_id, n_cells, st.dst, st.ring, st.status, st.cfg, dl));
     if (proposal_hash || proposal_hash2 || proposal_len || announced)
         return rapid_cd_read_outputs(cd, proposal_hash, proposal_hash2, proposal_len, announced);
     return RAPID_OK;
@@ -625,8 +640,9 @@ int32_t rapid_cd_aggregate(rapid_cd* cd, int64_t n_cells, const int32_t* src, co
     if (!cd->raw) { set_error("rapid_cd_aggregate needs a RAPID_CD_RAW handle"); return RAPID_EINVAL; }
     if (receiver < 0 || receiver >= cd->R) { set_error("bad receiver"); return RAPID_EINVAL; }
     DeviceGuard g(cd->device);
-    RAPID_CHECK(stage_cells(cd, n_cells, dst, ring, status, nullptr));
-    RAPID_CHECK(apply_common(cd, 0, n_cells, cd->c_dst.p, cd->c_ring.p, cd->c_status.p, nullptr, DeliveryDev()));
+    Staged st;
+    RAPID_CHECK(stage_cells(cd, n_cells, dst, ring, status, nullptr, nullptr, &st));
+    RAPID_CHECK(apply_common(cd, 0, n_cells, st.dst, st.ring, st.status, nullptr, DeliveryDev()));
     // collect what this call emitted for `receiver`, then clear the call marks of every receiver
     DevBuf<int32_t> d_ids, d_cnt;
     const int32_t S = cd->S;
@@ -683,6 +699,7 @@ int32_t rapid_cd_invalidate(rapid_cd* cd, int64_t receiver, int32_t* out_ids, in
 int32_t rapid_cd_get_proposal(const rapid_cd* cd, int64_t receiver, int32_t* out_ids, int32_t cap, int32_t* out_len) {
     if (!cd || !out_len || receiver < 0 || receiver >= cd->R) { set_error("bad arguments"); return RAPID_EINVAL; }
     DeviceGuard g(cd->device);
+    cudaStreamSynchronize(cd->stream);   // clear() and the apply calls are asynchronous on the handle's stream
     uint32_t flags = 0;
     RAPID_CUDA(cudaMemcpy(&flags, cd->rflags.p + receiver, sizeof(flags), cudaMemcpyDeviceToHost));
     *out_len = 0;
@@ -719,6 +736,7 @@ int32_t rapid_cd_num_proposals(const rapid_cd* cd, int64_t receiver, int32_t* ou
     if (!cd || !out || receiver < 0 || receiver >= cd->R) { set_error("bad arguments"); return RAPID_EINVAL; }
     if (cd->bucketed) { set_error("getNumProposals is exact only on sweep handles (RAPID_CD_SWEEP / RAPID_CD_RAW)"); return RAPID_EUNSUPPORTED; }
     DeviceGuard g(cd->device);
+    cudaStreamSynchronize(cd->stream);   // clear() and the apply calls are asynchronous on the handle's stream
     RAPID_CUDA(cudaMemcpy(out, cd->n_prop.p + receiver, sizeof(int32_t), cudaMemcpyDeviceToHost));
     return RAPID_OK;
 }
@@ -726,6 +744,7 @@ int32_t rapid_cd_num_proposals(const rapid_cd* cd, int64_t receiver, int32_t* ou
 int32_t rapid_cd_debug_masks(const rapid_cd* cd, int64_t receiver, int32_t* out_subject_ids, uint16_t* out_masks, int32_t cap, int32_t* out_n) {
     if (!cd || !out_n || receiver < 0 || receiver >= cd->R) { set_error("bad arguments"); return RAPID_EINVAL; }
     DeviceGuard g(cd->device);
+    cudaStreamSynchronize(cd->stream);   // clear() and the apply calls are asynchronous on the handle's stream
     const int32_t S = cd->S;
     *out_n = S;
     if (S == 0) return RAPID_OK;
@@ -745,6 +764,7 @@ int32_t rapid_cd_debug_masks(const rapid_cd* cd, int64_t receiver, int32_t* out_
 int32_t rapid_cd_debug_counters(const rapid_cd* cd, int64_t receiver, int32_t* updates_in_progress, int32_t* seen_link_down) {
     if (!cd || receiver < 0 || receiver >= cd->R) { set_error("bad arguments"); return RAPID_EINVAL; }
     DeviceGuard g(cd->device);
+    cudaStreamSynchronize(cd->stream);   // clear() and the apply calls are asynchronous on the handle's stream
     if (updates_in_progress) RAPID_CUDA(cudaMemcpy(updates_in_progress, cd->n_pre.p + receiver, sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (seen_link_down) {
         uint32_t f = 0;
@@ -758,6 +778,7 @@ int32_t rapid_cd_debug_stats(const rapid_cd* cd, int32_t* n_mixed, int32_t* n_in
                              int32_t* n_valid_cells) {
     if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
     DeviceGuard g(cd->device);
+    cudaStreamSynchronize(cd->stream);   // clear() and the apply calls are asynchronous on the handle's stream
     BatchCounts bc;
     RAPID_CUDA(cudaMemcpy(&bc, cd->counts.p, sizeof(bc), cudaMemcpyDeviceToHost));
     if (n_mixed) *n_mixed = bc.n_mixed;

@@ -68,6 +68,7 @@ struct CD {
     // batch staging (device)
     DevBuf<int32_t> c_dst;  DevBuf<uint8_t> c_ring, c_status;  DevBuf<int64_t> c_cfg;
     DevBuf<uint8_t> d_blocked;  DevBuf<uint32_t> d_bitmap;
+    PinnedBuf<uint8_t> h_stage;  DevBuf<uint8_t> d_stage;   // host-array path: one pinned blob, one H2D copy
     const uint8_t* cur_ring_dev = nullptr;    // ring / status arrays of the batch in flight (device)
     const uint8_t* cur_status_dev = nullptr;
     DevBuf<int32_t> cell_slot;        // [A] slot or -1

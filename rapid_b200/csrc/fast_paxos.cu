@@ -101,9 +101,21 @@ struct Comm {
     } while (0)
 
 // ------------------------------------------------------------------ kernels
+// a new FastPaxos instance on the same buffers, one launch
+__global__ void k_fp_reset(int64_t sender_cap, int32_t* __restrict__ seen, uint32_t T, int32_t* __restrict__ t_state,
+                           int32_t* __restrict__ t_count, int32_t* __restrict__ t_call, FPState* __restrict__ st);
+
 __global__ void k_fp_fill(int32_t* p, int64_t n, int32_t v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
+}
+
+__global__ void k_fp_reset(int64_t sender_cap, int32_t* __restrict__ seen, uint32_t T, int32_t* __restrict__ t_state,
+                           int32_t* __restrict__ t_count, int32_t* __restrict__ t_call, FPState* __restrict__ st) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < sender_cap) seen[i] = INT_MAX;
+    if (i < (int64_t)T) { t_state[i] = 0; t_count[i] = 0; t_call[i] = 0; }
+    if (i == 0) { st->decided = 0; st->decided_entry = 0; st->votes_received = 0; st->n_valid_call = 0; st->n_cand = 0; st->i_star = INT_MAX; st->bad_sender = -1; }
 }
 
 // first vote of every sender in this call (votesReceived.contains(sender), :134)
@@ -595,14 +607,10 @@ int32_t rapid_fp_reset(rapid_fp* fp, int64_t cfg_id, int64_t membership_size) {
     fp->Q = membership_size - (membership_size - 1) / 4;
     fp->decided_host = false;
     const int TB = 256;
-    k_fp_fill<<<(unsigned)ceil_div<int64_t>(fp->sender_cap, TB), TB, 0, s>>>(fp->seen.p, fp->sender_cap, INT_MAX);
+    const int64_t m = std::max<int64_t>(fp->sender_cap, (int64_t)fp->T);
+    k_fp_reset<<<(unsigned)ceil_div<int64_t>(m, TB), TB, 0, s>>>(fp->sender_cap, fp->seen.p, fp->T, fp->t_state.p, fp->t_count.p, fp->t_call.p, fp->st.p);
     RAPID_KERNEL_CHECK();
-    RAPID_CUDA(cudaMemsetAsync(fp->t_state.p, 0, fp->T * sizeof(int32_t), s));
-    RAPID_CUDA(cudaMemsetAsync(fp->t_count.p, 0, fp->T * sizeof(int32_t), s));
-    RAPID_CUDA(cudaMemsetAsync(fp->t_call.p, 0, fp->T * sizeof(int32_t), s));
-    RAPID_CUDA(cudaMemsetAsync(fp->st.p, 0, sizeof(FPState), s));
-    RAPID_CUDA(cudaStreamSynchronize(s));
-    return RAPID_OK;
+    return RAPID_OK;      // asynchronous: everything that follows runs on the same stream
 }
 
 int32_t rapid_fp_destroy(rapid_fp* fp) {
