@@ -2,7 +2,7 @@
 //
 // Reference semantics: MultiNodeCutDetector.java:84-128 applied per cell in arrival order, then :137-164, driven
 // by MembershipService.java:300-354.  The Java walks the batch once per process and probes a hash map per cell.
-// Here the batch is regrouped BY SUBJECT once (radix sort of the cell indices by subject slot), and every receiver's
+// Here the batch is regrouped BY SUBJECT once (counting sort by subject slot inside cd_prepare.cu), and every receiver's
 // 16-bit ring mask for a subject is read ONCE, updated in a register and written ONCE:
 //
 //   traffic = 4 bytes x (#subjects in the batch) x (#receivers)          (SURVEY.md §8d "4·S·R")
@@ -21,15 +21,12 @@
 // "Moments" are cell indices for uniform delivery and the receiver's own permutation keys for PERMUTED delivery,
 // so a per-receiver order needs no per-receiver sort.
 //
-// Kernels: k_apply_uniform (SWAR: 8 receivers per thread, 128-bit loads/stores, fresh-subject fast path),
-// k_apply_generic (one receiver per thread: bitmap / permuted delivery), k_finalize1, k_resolve_mixed, k_flip,
-// k_inval_pairs, k_finalize2.
-#include <cub/cub.cuh>
-
+// Kernels: k_apply_uniform (SWAR: 8 receivers per thread, 128-bit loads/stores, write-only fresh-subject path),
+// k_apply_generic (one receiver per thread: bitmap / permuted delivery), k_finalize1, k_mixed_pass / k_mixed_update /
+// k_mixed_commit / k_mixed_mark (interval analysis), k_flip, k_inval_pairs, k_finalize2.
 #include <algorithm>
 
 #include "cd_internal.cuh"
-#include "scan.cuh"
 
 namespace rapid {
 
@@ -96,86 +93,6 @@ struct Bucketed {
     size_t part_cap = 0;
     int slots_uniform = 0, slots_generic = 0;   // resident blocks of the apply kernels on this device
 };
-
-// ------------------------------------------------------------------------------------------------------------------
-// batch regrouping
-// ------------------------------------------------------------------------------------------------------------------
-__global__ void k_sort_keys(int64_t A, const int32_t* __restrict__ cell_slot, uint32_t* __restrict__ key, int32_t* __restrict__ val) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A) return;
-    const int32_t s = cell_slot[i];
-    key[i] = s < 0 ? 0xFFFFFFFFu : (uint32_t)s;
-    val[i] = (int32_t)i;
-}
-
-__global__ void k_heads(int32_t n_valid, const uint32_t* __restrict__ key, int32_t* __restrict__ head) {
-    const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_valid) return;
-    head[j] = (j == 0 || key[j] != key[j - 1]) ? 1 : 0;
-}
-
-__global__ void k_scan_i32(int32_t* __restrict__ data, int64_t n) {
-    __shared__ int32_t part[1024];
-    const int T = blockDim.x, t = threadIdx.x;
-    const int64_t per = (n + T - 1) / T;
-    const int64_t b = (int64_t)t * per, e = b + per < n ? b + per : n;
-    int32_t s = 0;
-    for (int64_t i = b; i < e; ++i) s += data[i];
-    part[t] = s;
-    __syncthreads();
-    for (int off = 1; off < T; off <<= 1) {
-        int32_t v = t >= off ? part[t - off] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    int32_t run = t ? part[t - 1] : 0;
-    for (int64_t i = b; i < e; ++i) { const int32_t v = data[i]; data[i] = run; run += v; }
-}
-
-// one thread per segment head: walk the subject's cells in arrival order
-__global__ void k_build_desc(int32_t n_valid, const uint32_t* __restrict__ key, const int32_t* __restrict__ sidx,
-                             const int32_t* __restrict__ head_excl, const uint8_t* __restrict__ ring,
-                             const uint8_t* __restrict__ status, const int32_t* __restrict__ slot_subject, int L, int H,
-                             SubjDesc* __restrict__ desc, SubjWalk* __restrict__ walk, uint8_t* __restrict__ s_ring,
-                             uint8_t* __restrict__ s_status, int32_t* __restrict__ batch_index) {
-    const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_valid) return;
-    const int32_t ci = sidx[j];
-    s_ring[j] = ring[ci];
-    s_status[j] = status[ci];
-    const bool is_head = (j == 0 || key[j] != key[j - 1]);
-    if (!is_head) return;
-    const int32_t b = head_excl[j];
-    SubjDesc d;
-    SubjWalk w;
-    d.slot = (int32_t)key[j];
-    d.bmask = 0; d.nr = 0; d.any_down = 0; d.tLf = 0; d.tHf = 0;
-    d.seg_begin = (uint32_t)j;
-    int32_t e = j;
-    while (e < n_valid && key[e] == key[j]) {
-        const int32_t c = sidx[e];
-        const int k = ring[c];
-        if (status[c] == RAPID_EDGE_DOWN) d.any_down = 1;
-        if (!((d.bmask >> k) & 1)) {
-            d.bmask |= (uint16_t)(1u << k);
-            w.ring[d.nr] = (uint8_t)k;
-            w.time[d.nr] = (uint32_t)c + 1u;           // moments are 1-based cell indices (0 = "before the batch")
-            ++d.nr;
-            if (d.nr == L) d.tLf = (uint32_t)c + 1u;
-            if (d.nr == H) d.tHf = (uint32_t)c + 1u;
-        }
-        ++e;
-    }
-    for (int q = d.nr; q < 16; ++q) { w.ring[q] = 0; w.time[q] = 0; }
-    d.seg_len = (uint32_t)(e - j);
-    d.mix1 = fp_mix1(slot_subject[d.slot]);
-    d.mix2 = fp_mix2(slot_subject[d.slot]);
-    d.pad_ = 0;
-    desc[b] = d;
-    walk[b] = w;
-    batch_index[d.slot] = b;
-}
 
 // ------------------------------------------------------------------------------------------------------------------
 // the (subject, receiver) visit, uniform delivery: old 16-bit state -> crossings and moments

@@ -1,5 +1,5 @@
-// Cut detector: handle lifecycle, batch preprocessing (filter + subject-slot dictionary), the exact per-cell
-// sweep kernel, accessors and the C ABI.
+// Cut detector: handle lifecycle, the exact per-cell sweep kernel, accessors and the C ABI.  (Batch preparation — filter,
+// subject-slot dictionary, regrouping — is cd_prepare.cu; the subject-bucketed kernels are cd_bucketed.cu.)
 //
 // Reference semantics (rapid/src/main/java/com/vrg/rapid/):
 //   MultiNodeCutDetector.java:84-128  aggregateForProposal (per cell, in arrival order)
@@ -13,7 +13,6 @@
 #include <climits>
 
 #include "cd_internal.cuh"
-#include "scan.cuh"
 
 namespace rapid {
 
@@ -23,92 +22,6 @@ namespace rapid {
 __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
-}
-
-// validity of a cell (MembershipService.java:644-675) and first-occurrence index of not-yet-slotted subjects
-__global__ void k_filter_first(int64_t A, const int32_t* __restrict__ dst, const uint8_t* __restrict__ ring,
-                               const uint8_t* __restrict__ status, const int64_t* __restrict__ cell_cfg, int64_t cfg,
-                               int raw, int K, int64_t n_members, int64_t n_total, const int32_t* __restrict__ slot_of,
-                               int32_t* __restrict__ first_idx, int32_t* __restrict__ cell_slot /* -1 invalid, -2 valid */,
-                               BatchCounts* __restrict__ bc) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A) return;
-    const int32_t d = dst[i];
-    int32_t v = -2;
-    if (ring[i] >= K) { atomicMax(&bc->bad_ring, (int32_t)i); v = -1; }
-    if (d < 0 || d >= n_total) { atomicMax(&bc->bad_dst, (int32_t)i); v = -1; }
-    if (v == -2 && !raw) {
-        const bool present = d < n_members;                       // isHostPresent
-        const int st = status[i];
-        if (cell_cfg && cell_cfg[i] != cfg) v = -1;                // :653
-        else if (st == RAPID_EDGE_UP && present) v = -1;           // :660-665
-        else if (st == RAPID_EDGE_DOWN && !present) v = -1;        // :666-671
-        else if (st != RAPID_EDGE_UP && st != RAPID_EDGE_DOWN) v = -1;
-    }
-    cell_slot[i] = v;
-    if (v == -2) {
-        if (status[i] == RAPID_EDGE_DOWN) bc->any_down = 1;
-        if (slot_of[d] < 0) atomicMin(&first_idx[d], (int32_t)i);
-    }
-}
-
-__global__ void k_mark_new(int64_t A, const int32_t* __restrict__ dst, const int32_t* __restrict__ cell_slot,
-                           const int32_t* __restrict__ slot_of, const int32_t* __restrict__ first_idx,
-                           int32_t* __restrict__ flag) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A) return;
-    const int32_t d = dst[i];
-    flag[i] = (cell_slot[i] == -2 && slot_of[d] < 0 && first_idx[d] == (int32_t)i) ? 1 : 0;
-}
-
-// single-block exclusive scan (A is at most a few million; this is a few microseconds of work)
-__global__ void k_exclusive_scan(int32_t* __restrict__ data, int64_t n, int32_t* __restrict__ total) {
-    __shared__ int32_t part[1024];
-    const int T = blockDim.x, t = threadIdx.x;
-    const int64_t per = (n + T - 1) / T;
-    const int64_t b = (int64_t)t * per, e = b + per < n ? b + per : n;
-    int32_t s = 0;
-    for (int64_t i = b; i < e; ++i) s += data[i];
-    part[t] = s;
-    __syncthreads();
-    for (int off = 1; off < T; off <<= 1) {           // Hillis-Steele inclusive scan of the partials
-        int32_t v = t >= off ? part[t - off] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    int32_t run = t ? part[t - 1] : 0;
-    for (int64_t i = b; i < e; ++i) { const int32_t v = data[i]; data[i] = run; run += v; }
-    if (t == T - 1) *total = part[T - 1];
-}
-
-__global__ void k_assign_slots(int64_t A, const int32_t* __restrict__ dst, const int32_t* __restrict__ cell_slot,
-                               const int32_t* __restrict__ rank, const int32_t* __restrict__ n_new, int32_t S_old,
-                               int32_t* __restrict__ slot_of, int32_t* __restrict__ first_idx,
-                               int32_t* __restrict__ slot_subject, BatchCounts* __restrict__ bc) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) bc->n_slots = S_old + *n_new;
-    if (i >= A) return;
-    const int32_t d = dst[i];
-    if (cell_slot[i] == -2 && first_idx[d] == (int32_t)i) {       // first valid cell of a subject without a slot
-        const int32_t slot = S_old + rank[i];
-        slot_of[d] = slot;
-        slot_subject[slot] = d;
-        first_idx[d] = INT_MAX;
-    }
-}
-
-__global__ void k_cell_slots(int64_t A, const int32_t* __restrict__ dst, const int32_t* __restrict__ slot_of,
-                             int32_t* __restrict__ cell_slot, int32_t* __restrict__ touch, int32_t serial,
-                             BatchCounts* __restrict__ bc) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A) return;
-    if (cell_slot[i] == -2) {
-        const int32_t slot = slot_of[dst[i]];
-        cell_slot[i] = slot;
-        atomicAdd(&bc->n_valid, 1);
-        if (atomicExch(&touch[slot], serial) != serial) atomicAdd(&bc->n_batch_subj, 1);   // first cell of this subject in the batch
-    }
 }
 
 // =====================================================================================================
@@ -339,7 +252,6 @@ static int32_t preprocess(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev
     cudaStream_t s = cd->stream;
     RAPID_CHECK(ensure_id_capacity(cd));
     RAPID_CHECK(cd->cell_slot.reserve(std::max<int64_t>(A, 1)));
-    RAPID_CHECK(cd->scan_tmp.reserve(std::max<int64_t>(A, 1) + 1));
     BatchCounts init;
     memset(&init, 0, sizeof(init));
     init.n_slots = cd->S;
