@@ -94,6 +94,12 @@ int32_t rapid_view_config_id(const rapid_view* v, const int64_t* id_high, const 
 int32_t rapid_view_register_joiners(rapid_view* v, int64_t n_add, const uint8_t* host_bytes,
                                     const int32_t* host_off, const int32_t* port, int32_t* out_first_id);
 int32_t rapid_view_num_joiners(const rapid_view* v, int64_t* out);
+/* decideViewChange (MembershipService.java:385-444) on the view: every cut id that is a member is removed (ringDelete
+ * :167-201), every other one must be a registered joiner and is added (ringAdd :123-160); the K rings are rebuilt on the
+ * device.  Ids are renumbered densely (surviving members in order, then the admitted joiners; joiners not in the cut are
+ * dropped); out_old_to_new[n + joiners] receives the mapping (-1 = gone) and may be NULL.  Detector handles created on
+ * the old view must be destroyed and recreated. */
+int32_t rapid_view_apply_cut(rapid_view* v, const int32_t* cut_ids, int64_t n_cut, int32_t* out_old_to_new);
 /* expected observers of every registered joiner: out[j*K+k] for joiner id n + j. */
 int32_t rapid_view_joiner_tables(const rapid_view* v, int32_t* out);
 

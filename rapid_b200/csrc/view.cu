@@ -432,6 +432,50 @@ int32_t rapid_view_register_joiners(rapid_view* v, int64_t n_add, const uint8_t*
     return RAPID_OK;
 }
 
+// decideViewChange (MembershipService.java:385-444): every node of the decided cut that is a member leaves (ringDelete,
+// MembershipView.java:167-201), every other one — a registered joiner — is added (ringAdd, :123-160).  The K rings are
+// rebuilt on the device from the surviving endpoints (hash + radix sort + tables); ids are renumbered densely: surviving
+// members keep their relative order, the admitted joiners follow in id order, joiners not in the cut are dropped.
+int32_t rapid_view_apply_cut(rapid_view* v, const int32_t* cut_ids, int64_t n_cut, int32_t* out_old_to_new) {
+    if (!v || n_cut < 0 || (n_cut && !cut_ids)) { set_error("bad arguments"); return RAPID_EINVAL; }
+    DeviceGuard g(v->device);
+    const int64_t tot = v->n + v->nj;
+    std::vector<uint8_t> in_cut((size_t)tot, 0);
+    for (int64_t i = 0; i < n_cut; ++i) {
+        const int32_t id = cut_ids[i];
+        if (id < 0 || id >= tot) { set_error("cut id %d outside [0, members + joiners)", id); return RAPID_EINVAL; }
+        if (in_cut[(size_t)id]) {
+            set_error("cut names node %d twice", id);
+            return id < v->n ? RAPID_ENOT_IN_RING : RAPID_EALREADY_IN_RING;      // second ringDelete / ringAdd would throw
+        }
+        in_cut[(size_t)id] = 1;
+    }
+    std::vector<uint8_t> hb;
+    std::vector<int32_t> off(1, 0), port;
+    std::vector<int32_t> map((size_t)tot, -1);
+    hb.reserve(v->h_host_bytes.size());
+    int32_t next = 0;
+    for (int64_t id = 0; id < tot; ++id) {
+        const bool keep = id < v->n ? !in_cut[(size_t)id] : in_cut[(size_t)id];
+        if (!keep) continue;
+        const int32_t o = v->h_host_off[(size_t)id], len = v->h_host_off[(size_t)id + 1] - o;
+        hb.insert(hb.end(), v->h_host_bytes.begin() + o, v->h_host_bytes.begin() + o + len);
+        off.push_back(off.back() + len);
+        port.push_back(v->h_port[(size_t)id]);
+        map[(size_t)id] = next++;
+    }
+    // swap in the new endpoint list and rebuild
+    v->h_host_bytes.clear(); v->h_host_off.clear(); v->h_port.clear();
+    v->n = 0; v->nj = 0;
+    static const uint8_t dummy = 0;
+    static const int32_t zero_off[1] = {0};
+    RAPID_CHECK(upload_endpoints(v, next, next ? hb.data() : &dummy, next ? off.data() : zero_off, port.data()));
+    v->n = next;
+    RAPID_CHECK(build_rings(v));
+    if (out_old_to_new) memcpy(out_old_to_new, map.data(), (size_t)tot * sizeof(int32_t));
+    return RAPID_OK;
+}
+
 int32_t rapid_view_expected_observers(const rapid_view* cv, const uint8_t* host, int32_t len, int32_t port, int32_t* out,
                                       int32_t* out_count) {
     rapid_view* v = const_cast<rapid_view*>(cv);   // uses scratch space past the registered endpoints; logically const

@@ -112,6 +112,16 @@ class MembershipView:
         N.check(N.lib().rapid_view_register_joiners(self._h, len(port), N.ptr(hb), N.ptr(off), N.ptr(port), C.byref(first)))
         return list(range(first.value, first.value + len(port)))
 
+    def applyCut(self, cut_ids):
+        """decideViewChange (MembershipService.java:385-444): members in the cut leave, registered joiners in it are added;
+        rings rebuilt on the device.  Returns old id -> new id (-1 = gone); detector handles on the old view are stale."""
+        ids = N.as_i32(cut_ids)
+        tot = self.n + self.numJoiners()
+        mapping = np.empty(max(tot, 1), np.int32)
+        N.check(N.lib().rapid_view_apply_cut(self._h, N.ptr(ids), len(ids), N.ptr(mapping)))
+        self.n = self.getMembershipSize()
+        return mapping[:tot]
+
     def joinerTables(self):
         """expected observers [n_joiners][K] of the registered joiners"""
         nj = self.numJoiners()

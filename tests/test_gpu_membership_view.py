@@ -109,3 +109,42 @@ def test_long_hostnames(orc, rb):
     for k in range(K):
         assert v.getRing(k).tolist() == ref.getRing(k)
     assert v.getCurrentConfigurationId([], []) == ref.getCurrentConfigurationId()
+
+
+def test_apply_cut_matches_ring_delete_and_add(orc, rb):
+    """decideViewChange on the device view == ringDelete / ringAdd on the oracle view (MembershipService.java:385-444)"""
+    n, nj = 300, 12
+    w = OracleWorld(orc, n, K, n_joiners=nj)
+    v = rb.MembershipView.from_packed(K, *w.member_packed())
+    v.registerJoiners(*w.joiner_endpoints())
+    rng = np.random.default_rng(8)
+    leave = sorted(rng.choice(n, size=9, replace=False).tolist())
+    join = [n + j for j in sorted(rng.choice(nj, size=5, replace=False).tolist())]
+    mapping = v.applyCut(leave + join)
+    # the same decision applied to the oracle view
+    hi, lo = W.node_ids(n, nj)
+    for x in leave:
+        w.view.ringDelete(x)
+    for x in join:
+        w.view.ringAdd(x, (int(hi[x - n]), int(lo[x - n])))
+    assert v.getMembershipSize() == w.view.getMembershipSize() == n - 9 + 5
+    inv = {int(new): old for old, new in enumerate(mapping.tolist()) if new >= 0}
+    for k in range(K):
+        assert [inv[i] for i in v.getRing(k).tolist()] == w.view.getRing(k)
+    for old in (0, 17, join[0]):
+        if mapping[old] >= 0:
+            assert [inv[i] for i in v.getObserversOf(int(mapping[old]))] == w.view.getObserversOf(old)
+            assert [inv[i] for i in v.getSubjectsOf(int(mapping[old]))] == w.view.getSubjectsOf(old)
+    assert all(mapping[x] == -1 for x in leave) and all(mapping[x] >= 0 for x in join)
+    # identifiersSeen keeps the ids of the departed (MembershipView.java:167-201): same configuration id
+    ids_hi = np.concatenate([w.id_high, hi[[x - n for x in join]]])
+    ids_lo = np.concatenate([w.id_low, lo[[x - n for x in join]]])
+    assert v.getCurrentConfigurationId(ids_hi, ids_lo) == w.view.getCurrentConfigurationId()
+    with pytest.raises(rb.RapidError):
+        v.applyCut([0, 0])
+    # a detector on the new view works
+    cl = rb.VirtualCluster(v, 9, 4)
+    obs, _ = v.tables()
+    b = W.c2_simultaneous_crash(obs, v.n, 0.01)
+    res = cl.handleBatch(5, b.src, b.dst, b.ring, b.status)
+    assert set(res.proposal_len.tolist()) == {len(b.expected_cut)}
