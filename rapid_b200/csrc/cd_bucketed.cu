@@ -35,6 +35,7 @@ constexpr int UNI_THREADS = 128;
 constexpr int GEN_THREADS = 256;
 constexpr int STAGE = 32;             // batch subjects staged in shared memory at a time
 constexpr int MAXK = RAPID_MAX_K;
+constexpr int SMALL_SEG = 4;          // generic visit: subjects with at most this many cells in the batch stay in registers
 constexpr uint32_t T32_NONE = 0xFFFFFFFFu;
 constexpr uint64_t T64_NONE = ~0ULL;
 constexpr uint32_t RF_K3 = 16u;       // receiver enters the invalidation pass of the batch in flight
@@ -378,12 +379,59 @@ struct GVisit {
 __device__ __forceinline__ GVisit visit_generic(uint32_t ur, const SubjDesc& d, const int32_t* __restrict__ sidx,
                                                 const uint8_t* __restrict__ s_ring, const uint8_t* __restrict__ s_status,
                                                 const DeliveryDev& dl, int64_t r, uint64_t rs, int L, int H) {
-    uint64_t tmin[MAXK];
-#pragma unroll
-    for (int k = 0; k < MAXK; ++k) tmin[k] = 0;
     GVisit v;
     v.have = 0; v.seen_down = false; v.tL = 0; v.tH = 0;
     const bool has_bitmap = dl.flags & RAPID_DELIVERY_BITMAP, permuted = dl.flags & RAPID_DELIVERY_PERMUTED;
+    if (d.seg_len <= SMALL_SEG) {
+        // Few cells (the common case: ~1-3 reports of a subject per batch): work on the cells themselves instead of a
+        // per-ring table — first occurrence of each not-yet-reported ring, then its rank by moment, all in registers.
+        uint64_t tm[SMALL_SEG];
+        int rk[SMALL_SEG];
+        bool ok[SMALL_SEG];
+#pragma unroll
+        for (int j = 0; j < SMALL_SEG; ++j) {
+            ok[j] = false; tm[j] = 0; rk[j] = 0;
+            if (j < (int)d.seg_len) {
+                const int32_t ci = sidx[d.seg_begin + j];
+                if (!has_bitmap || ((dl.bitmap[(size_t)ci * dl.words + (r >> 5)] >> (r & 31)) & 1u)) {
+                    ok[j] = true;
+                    rk[j] = s_ring[d.seg_begin + j];
+                    tm[j] = permuted ? splitmix64(rs ^ (uint64_t)ci) : (uint64_t)ci + 1ull;
+                    if (s_status[d.seg_begin + j] == RAPID_EDGE_DOWN) v.seen_down = true;
+                    v.have |= 1u << rk[j];
+                }
+            }
+        }
+        const uint32_t fresh = v.have & ~ur;
+        v.c0 = __popc(ur);
+        v.c1 = v.c0 + __popc(fresh);
+        v.crossL = v.c0 < L && v.c1 >= L;
+        v.crossH = v.c0 < H && v.c1 >= H;
+        if (v.crossL || v.crossH) {
+            const int wantL = L - v.c0 - 1, wantH = H - v.c0 - 1;
+            bool first[SMALL_SEG];
+#pragma unroll
+            for (int j = 0; j < SMALL_SEG; ++j) {             // first report of a ring this receiver had not counted yet
+                first[j] = ok[j] && !((ur >> rk[j]) & 1u);
+#pragma unroll
+                for (int i = 0; i < SMALL_SEG; ++i)
+                    if (i != j && ok[i] && rk[i] == rk[j] && tm[i] < tm[j]) first[j] = false;
+            }
+#pragma unroll
+            for (int j = 0; j < SMALL_SEG; ++j) {
+                if (!first[j]) continue;
+                int rank = 0;
+#pragma unroll
+                for (int i = 0; i < SMALL_SEG; ++i) rank += (first[i] && tm[i] < tm[j]) ? 1 : 0;
+                if (rank == wantL) v.tL = tm[j];
+                if (rank == wantH) v.tH = tm[j];
+            }
+        }
+        return v;
+    }
+    uint64_t tmin[MAXK];
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k) tmin[k] = 0;
     const uint32_t e = d.seg_begin + d.seg_len;
     for (uint32_t j = d.seg_begin; j < e; ++j) {
         const int32_t ci = sidx[j];
