@@ -465,7 +465,7 @@ __device__ __forceinline__ GVisit visit_generic(uint32_t ur, const SubjDesc& d, 
     return v;
 }
 
-__global__ void __launch_bounds__(GEN_THREADS) k_apply_generic(const ApplyArgs a) {
+__global__ void __launch_bounds__(GEN_THREADS, 4) k_apply_generic(const ApplyArgs a) {
     __shared__ SubjDesc sd[STAGE];
     __shared__ const uint16_t* s_src[STAGE];
     __shared__ uint16_t* s_dst[STAGE];
@@ -494,11 +494,17 @@ __global__ void __launch_bounds__(GEN_THREADS) k_apply_generic(const ApplyArgs a
             s_unres[t] = 0;
         }
         __syncthreads();
+        // the visit is a dependent chain (state word -> cells -> moments): keep 8 state loads in flight per thread
+        uint32_t pre[8];
         for (int i = 0; i < n; ++i) {
+            if ((i & 7) == 0) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) pre[u] = (i + u < n && s_src[i + u]) ? s_src[i + u][r] : 0u;
+            }
             const SubjDesc& d = sd[i];
             bool unres = false;
             if (r < (int64_t)a.Rpad) {
-                uint32_t st = s_src[i] ? s_src[i][r] : 0u;
+                uint32_t st = pre[i & 7];
                 if (active) {
                     const GVisit v = visit_generic(st & RM, d, a.sidx, a.s_ring, a.s_status, a.dl, r, rs, L, H);
                     if (v.seen_down) fl |= PF_SEEN;
