@@ -793,7 +793,9 @@ struct EmitCtx {
 __device__ __forceinline__ bool emitted_in_batch(const EmitCtx& e, int32_t s, int64_t r, uint32_t w_new, uint64_t rs) {
     const ApplyArgs& a = e.ap;
     const uint32_t RM = (1u << a.K) - 1u;
-    if (e.touch[s] != e.serial) return __popc(w_new & RM) >= a.H;         // untouched and at >= H: it was pending, it left first
+    // untouched by the batch: it left (with the first explicit proposal) iff it was pending, i.e. at >= H and NOT raised there by
+    // this batch's invalidation pass (bit 14, cleared by k_inval_unmark once the batch is done)
+    if (e.touch[s] != e.serial) return __popc(w_new & RM) >= a.H && !(w_new & CD_BIT_CALL);
     const int b = e.batch_index[s];
     const SubjDesc d = a.desc[b];
     const uint32_t old = s >= a.S_before ? 0u : (a.masks + ((size_t)s * 2 + (a.cur[s] ^ 1)) * a.Rpad)[r];
@@ -884,7 +886,7 @@ __global__ void __launch_bounds__(256) k_inval_pairs(const InvArgs a) {
                 if ((wo & CD_BIT_EMIT) || __popc(wo & RM) < a.L) continue;            // observer not in proposal U preProposal
                 // a receiver that already announced explicit proposals in this batch: those subjects left `proposal`.
                 // (bit 14 = raised to >= H by this very pass, i.e. it was in the band at entry, not pending)
-                if (mx && !(wo & CD_BIT_CALL) && emitted_in_batch(a.ec, s2, r, wo, rs)) continue;
+                if (mx && emitted_in_batch(a.ec, s2, r, wo, rs)) continue;
                 implicit |= 1u << k;
             }
             if (!implicit) continue;
@@ -1209,10 +1211,8 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
     RAPID_KERNEL_CHECK();
     cd->last_launches += 2;
     if (n_mixed > 0) {
-        k_inval_unmark<<<148 * 4, 256, 0, s>>>(ia);
         RAPID_CUDA(cudaMemcpyAsync(cd->h_counts.p, cd->counts.p, sizeof(BatchCounts), cudaMemcpyDeviceToHost, s));
         RAPID_CUDA(cudaStreamSynchronize(s));
-        cd->last_launches += 1;
         if (cd->h_counts.p->n_inval > 0 && cd->S > 0) {
             // receivers that announce only the explicit part: persist it as bit 15 while the pre-batch rows still exist
             const int spb = 64;
@@ -1221,6 +1221,9 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
             RAPID_KERNEL_CHECK();
             cd->last_launches += 1;
         }
+        k_inval_unmark<<<148 * 4, 256, 0, s>>>(ia);          // only now: the marks above still needed bit 14
+        RAPID_KERNEL_CHECK();
+        cd->last_launches += 1;
     }
     return RAPID_OK;
 }

@@ -136,10 +136,12 @@ __device__ __forceinline__ uint32_t fp_slot_hash(uint64_t h1, uint64_t h2, int32
 // find-or-insert the proposal of every valid vote; count per entry for this call (warp-aggregated)
 __global__ void k_fp_insert(int64_t n, const int32_t* __restrict__ sender, const int64_t* __restrict__ vcfg, int64_t cfg,
                             int64_t sender_cap, const uint64_t* __restrict__ h1v, const uint64_t* __restrict__ h2v,
-                            const int32_t* __restrict__ lenv, const int32_t* __restrict__ seen, uint32_t T,
+                            const int32_t* __restrict__ lenv, int32_t* __restrict__ seen, uint32_t T,
                             int32_t* __restrict__ t_state, uint64_t* __restrict__ t_h1, uint64_t* __restrict__ t_h2,
                             int32_t* __restrict__ t_len, int32_t* __restrict__ t_call, int32_t* __restrict__ ent,
-                            FPState* __restrict__ st, int unique_senders) {
+                            FPState* __restrict__ st, int unique_senders, int direct) {
+    // direct (sharded tally of a detector's own votes): no arrival-order bookkeeping is needed, so the counts go straight
+    // to t_count (the caller passes it as t_call), the senders are marked as having voted and votesReceived grows here
     __shared__ int32_t s_key[16], s_val[16];
     if (threadIdx.x < 16) { s_key[threadIdx.x] = -1; s_val[threadIdx.x] = 0; }
     __syncthreads();
@@ -218,8 +220,9 @@ __global__ void k_fp_insert(int64_t n, const int32_t* __restrict__ sender, const
         }
     }
     if (i < n) ent[i] = e;
+    if (direct && valid) seen[sender[i]] = -1;
     const unsigned cnt = __popc(active);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&st->n_valid_call, (int32_t)cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(direct ? &st->votes_received : &st->n_valid_call, (int32_t)cnt);
     __syncthreads();
     if (threadIdx.x < 16 && s_key[threadIdx.x] >= 0) atomicAdd(&t_call[s_key[threadIdx.x]], s_val[threadIdx.x]);
 }
@@ -481,8 +484,11 @@ static int32_t tally_device(FP* fp, int64_t n, const int32_t* sender, const int6
         k_fp_first<<<g, TB, 0, s>>>(n, sender, vcfg, fp->cfg, fp->sender_cap, allow_skip, fp->seen.p, fp->st.p);
         fp->last_launches += 1;
     }
+    const bool direct = !exact_order && unique_senders;
     k_fp_insert<<<g, TB, 0, s>>>(n, sender, vcfg, fp->cfg, fp->sender_cap, h1, h2, len, fp->seen.p, fp->T, fp->t_state.p,
-                                 fp->t_h1.p, fp->t_h2.p, fp->t_len.p, fp->t_call.p, fp->ent.p, fp->st.p, unique_senders ? 1 : 0);
+                                 fp->t_h1.p, fp->t_h2.p, fp->t_len.p, direct ? fp->t_count.p : fp->t_call.p, fp->ent.p, fp->st.p,
+                                 unique_senders ? 1 : 0, direct ? 1 : 0);
+    if (direct) { RAPID_KERNEL_CHECK(); fp->last_launches += 1; return RAPID_OK; }
     const unsigned gt = (unsigned)ceil_div<uint32_t>(fp->T, TB);
     k_fp_candidates<<<gt, TB, 0, s>>>(fp->T, fp->t_count.p, fp->t_call.p, (int32_t)fp->Q, fp->st.p);
     RAPID_KERNEL_CHECK();

@@ -333,3 +333,100 @@ def test_interval_analysis_then_invalidation(orc, rb, permuted):
         src2, dst2, ring2, st2 = random_batch(rng, n, K, 4, 30, n)
         compare_batch(rb, w, sim, cl, None, (src2, dst2, ring2, st2), perm_seed=(7 + trial) if permuted else None)
     assert total_mixed > 0
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("Kx,Hx,Lx", [(3, 3, 1), (5, 4, 2), (14, 12, 5), (7, 7, 7)])
+def test_other_ring_counts(orc, rb, kernel, Kx, Hx, Lx):
+    """K is a parameter of the view, not a constant of the kernels (K_MIN = 3, up to RAPID_MAX_K = 14)"""
+    n = 150
+    w = OracleWorld(orc, n, Kx)
+    v = rb.MembershipView.from_packed(Kx, *w.member_packed())
+    sim = orc.ClusterSim(w.view, Kx, Hx, Lx, n)
+    cl = rb.VirtualCluster(v, Hx, Lx, kernel=kernel)
+    rng = np.random.default_rng(Kx * 100 + Hx)
+    obs, _ = v.tables()
+    np.testing.assert_array_equal(obs, w.tables()[0])
+    for _ in range(4):
+        src, dst, ring, status = random_batch(rng, n, Kx, int(rng.integers(1, 6)), int(rng.integers(5, 50)), n)
+        compare_batch(rb, w, sim, cl, None, (src, dst, ring, status))
+    b = W.c2_simultaneous_crash(obs, n, 0.02)
+    cl.clear(); sim.reset()
+    compare_batch(rb, w, sim, cl, None, (b.src, b.dst, b.ring, b.status))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_joiners_registered_after_the_detector_exists(orc, rb, kernel):
+    """the id space grows (rapid_view_register_joiners) while a detector is alive: its dictionaries must follow"""
+    n = 120
+    w = OracleWorld(orc, n, K, n_joiners=70)
+    v = rb.MembershipView.from_packed(K, *w.member_packed())
+    sim = orc.ClusterSim(w.view, K, 9, 4, n)
+    cl = rb.VirtualCluster(v, 9, 4, kernel=kernel)
+    hosts, ports = w.joiner_endpoints()
+    rng = np.random.default_rng(1)
+    src, dst, ring, status = random_batch(rng, n, K, 3, 20, n)
+    compare_batch(rb, w, sim, cl, None, (src, dst, ring, status))
+    with pytest.raises(rb.RapidError):
+        cl.handleBatch(1, [0], [n + 3], [0], [UP])                       # not registered yet
+    v.registerJoiners(hosts[:10], ports[:10])
+    v.registerJoiners(hosts[10:], ports[10:])                             # 70 joiners > the initial id capacity slack
+    jo = w.joiner_obs()
+    cells_dst, cells_ring = [], []
+    for j in (0, 9, 10, 69):
+        for k in range(K):
+            cells_dst.append(n + j); cells_ring.append(k)
+    order = rng.permutation(len(cells_dst))
+    dst = np.array(cells_dst, np.int32)[order]; ring = np.array(cells_ring, np.uint8)[order]
+    src = jo[dst - n, ring]
+    compare_batch(rb, w, sim, cl, None, (src, dst, ring, np.full(len(dst), UP, np.uint8)))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_long_segments_and_heavy_duplication(orc, rb, kernel):
+    """hundreds of cells about one subject in one batch (the StaticFailureDetector re-fires every tick)"""
+    n = 90
+    w, v, sim, cl = _worlds(orc, rb, n, kernel=kernel, Hh=9, Ll=4)
+    rng = np.random.default_rng(4)
+    a, b2 = 7, 33
+    dst = np.concatenate([np.full(400, a), np.full(150, b2), rng.integers(0, n, size=60)]).astype(np.int32)
+    ring = rng.integers(0, K, size=len(dst)).astype(np.uint8)
+    order = rng.permutation(len(dst))
+    dst, ring = dst[order], ring[order]
+    src = rng.integers(0, n, size=len(dst)).astype(np.int32)
+    compare_batch(rb, w, sim, cl, None, (src, dst, ring, np.full(len(dst), DOWN, np.uint8)))
+    if kernel == "bucketed":
+        cl.clear(); sim.reset()
+        compare_batch(rb, w, sim, cl, None, (src, dst, ring, np.full(len(dst), DOWN, np.uint8)), perm_seed=5)
+
+
+@pytest.mark.parametrize("permuted", [False, True])
+def test_explicit_part_only_with_carried_band_subject(orc, rb, permuted):
+    """batch 1 leaves X in the unstable band; batch 2 emits A explicitly, then an observer of X enters the band: the
+    invalidation pass raises X (it was NOT pending), nobody's band empties, so exactly the explicit part {A} is announced."""
+    n = 60
+    rng = np.random.default_rng(31)
+    hits = 0
+    for trial in range(20):
+        Hh, Ll = (9, 4) if trial % 2 else (8, 3)
+        w, v, sim, cl = _worlds(orc, rb, n, kernel="bucketed", Hh=Hh, Ll=Ll)
+        obs, _ = v.tables()
+        x = int(rng.integers(0, n))
+        xo = obs[x].tolist()
+        o1 = xo[int(rng.integers(0, K))]
+        rings_x = [k for k in range(K) if xo[k] != o1][: Hh - 1]          # reports that leave X one short, not via o1
+        if len(rings_x) < Ll:
+            continue
+        a = int(rng.choice([i for i in range(n) if i not in (x, o1) and i not in xo]))
+        b1 = [(x, k) for k in rings_x]
+        d1 = np.array([c[0] for c in b1], np.int32); r1 = np.array([c[1] for c in b1], np.uint8)
+        compare_batch(rb, w, sim, cl, None, (np.zeros(len(b1), np.int32), d1, r1, np.full(len(b1), DOWN, np.uint8)),
+                      perm_seed=(3 + trial) if permuted else None)
+        b2 = [(a, k) for k in rng.permutation(K)[:Hh]] + [(o1, k) for k in rng.permutation(K)[: int(rng.integers(Ll, Hh))]]
+        d2 = np.array([c[0] for c in b2], np.int32); r2 = np.array([c[1] for c in b2], np.uint8)
+        o_len, o_ann = compare_batch(rb, w, sim, cl, None, (np.zeros(len(b2), np.int32), d2, r2, np.full(len(b2), DOWN, np.uint8)),
+                                     perm_seed=(40 + trial) if permuted else None)
+        if o_len.max() == 1:
+            hits += 1
+            assert cl.getProposal(0) == [a]
+    assert hits > 0
