@@ -98,3 +98,52 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.lower() or f == "workloads.py", (dp, f)
+
+
+def test_workload_generators_are_deterministic(orc):
+    """the synthetic scenarios are pure functions of (n, seed, ring topology): regenerate the golden cells"""
+    for c in _golden("cut_scenarios.json"):
+        n, nj = c["n"], c["n_joiners"]
+        hb, off, ports = W.packed_endpoints(0, n + nj)
+        u = orc.Universe()
+        tags = u.add_bulk(hb, off, ports)
+        hi, lo = W.node_ids(0, n)
+        v = orc.MembershipView(u, K, tags[:n], hi, lo)
+        obs = lambda ids: v.tables(ids)[0]
+        if c["name"] == "c1":
+            b = W.c1_single_crash(obs, n)
+        elif c["name"] == "c2":
+            b = W.c2_simultaneous_crash(obs, n, 0.01)
+        elif c["name"] == "c3":
+            b = W.c3_correlated_partition(obs, np.asarray(v.getRing(0)), n, 0.05)
+        else:
+            jo = np.asarray([v.getExpectedObserversOf(n + j) for j in range(nj)], np.int32)
+            b = W.c5_churn(obs, jo, n, 3, nj)
+        assert b.dst.tolist() == c["cells"]["dst"] and b.ring.tolist() == c["cells"]["ring"]
+        assert b.src.tolist() == c["cells"]["src"] and b.status.tolist() == c["cells"]["status"]
+        assert b.expected_cut.tolist() == c["expected_cut"]
+        # a full table and a lookup callable give the same batch
+        full_obs, _ = v.tables(np.arange(n, dtype=np.int32))
+        b2 = W.c2_simultaneous_crash(full_obs, n, 0.01)
+        b3 = W.c2_simultaneous_crash(obs, n, 0.01)
+        assert b2.dst.tolist() == b3.dst.tolist() and b2.src.tolist() == b3.src.tolist()
+
+
+def test_c4_stream_shape(orc):
+    n = 500
+    hb, off, ports = W.packed_endpoints(0, n)
+    u = orc.Universe()
+    tags = u.add_bulk(hb, off, ports)
+    v = orc.MembershipView(u, K, tags, *W.node_ids(0, n))
+    obs, _ = v.tables(np.arange(n, dtype=np.int32))
+    bs = W.c4_flip_flop_stream(obs, n, 0.02, T=8)
+    assert len(bs) == 8 and bs[-1].expected_cut is not None and all(b.expected_cut is None for b in bs[:-1])
+    failed = set(bs[-1].expected_cut.tolist())
+    seen = set()
+    for b in bs:
+        assert set(b.dst.tolist()) <= failed and not (set(b.src.tolist()) & failed)
+        seen |= set(zip(b.dst.tolist(), b.ring.tolist()))
+    # every report of every flapping node is sent at least once over the stream
+    want = {(s, k) for s in failed for k in range(K) if int(obs[s, k]) not in failed}
+    assert seen == want
+    assert sum(len(b) for b in bs) > len(want)          # and some are re-sent (duplicates)
