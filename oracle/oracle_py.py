@@ -384,7 +384,9 @@ class ClusterSim:
         bm = None if bitmap is None else np.ascontiguousarray(bitmap, np.uint32)
         out_len = np.zeros(self.R, np.int32)
         out_ann = np.zeros(self.R, np.uint8)
-        cap = max(1, self.R * max(1, len(np.unique(dst)) if A else 1))
+        # a proposal can hold subjects reported in earlier batches too
+        self._subjects = getattr(self, "_subjects", set()) | set(np.unique(dst).tolist())
+        cap = max(1, self.R * max(1, len(self._subjects)))
         out_ids = np.empty(cap, np.int32)
         secs = C.c_double(0.0)
         w = lib().orc_sim_apply_batch(self.h, A, _ptr(src), _ptr(dst), _ptr(ring), _ptr(status), _ptr(cfg),

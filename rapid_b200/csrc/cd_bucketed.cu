@@ -25,6 +25,7 @@
 // k_apply_generic (one receiver per thread: bitmap / permuted delivery), k_finalize1, k_mixed_pass / k_mixed_update /
 // k_mixed_commit / k_mixed_mark (interval analysis), k_flip, k_inval_pairs, k_finalize2.
 #include <algorithm>
+#include <cstdlib>
 
 #include "cd_internal.cuh"
 
@@ -1093,6 +1094,11 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
             else eff = w / (std::floor(w) + (f > 0 ? std::max(f, 0.6) : 0.0));     // tail wave: needs ~60 % of the slots to saturate HBM
             eff -= 0.005 * cc;                                                     // per-chunk prologue / partials
             if (eff > best) { best = eff; n_chunks = cc; chunk = ch; }
+        }
+        if (const char* ov = getenv("RAPID_B200_CHUNKS")) {          // tuning aid: force the number of subject chunks
+            const int c = std::max(1, std::min(Sb, atoi(ov)));
+            chunk = ceil_div(Sb, c);
+            n_chunks = ceil_div(Sb, chunk);
         }
     }
     const size_t pn = (size_t)n_chunks * cd->Rpad;
