@@ -1092,7 +1092,7 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
             double eff;
             if (w <= 1.0) eff = 0.85 + 0.15 * w;                                   // one partial wave: a little less occupancy
             else eff = w / (std::floor(w) + (f > 0 ? std::max(f, 0.6) : 0.0));     // tail wave: needs ~60 % of the slots to saturate HBM
-            eff -= 0.005 * cc;                                                     // per-chunk prologue / partials
+            eff -= 0.001 * cc;                                                     // per-chunk prologue (fresh subjects cost no partials)
             if (eff > best) { best = eff; n_chunks = cc; chunk = ch; }
         }
         if (const char* ov = getenv("RAPID_B200_CHUNKS")) {          // tuning aid: force the number of subject chunks

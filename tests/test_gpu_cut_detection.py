@@ -401,32 +401,36 @@ def test_long_segments_and_heavy_duplication(orc, rb, kernel):
 
 
 @pytest.mark.parametrize("permuted", [False, True])
-def test_explicit_part_only_with_carried_band_subject(orc, rb, permuted):
-    """batch 1 leaves X in the unstable band; batch 2 emits A explicitly, then an observer of X enters the band: the
-    invalidation pass raises X (it was NOT pending), nobody's band empties, so exactly the explicit part {A} is announced."""
+def test_explicit_part_only_is_what_get_proposal_lists(orc, rb, permuted):
+    """A leaves in an explicit proposal, then X and one of its observers enter the unstable band: the invalidation pass
+    raises X (implicit report from the observer) but the observer itself stays stuck, so nothing more is emitted and the
+    announced proposal is exactly the explicit part {A} — which rapid_cd_get_proposal must still be able to list."""
     n = 60
     rng = np.random.default_rng(31)
     hits = 0
-    for trial in range(20):
+    for trial in range(24):
         Hh, Ll = (9, 4) if trial % 2 else (8, 3)
         w, v, sim, cl = _worlds(orc, rb, n, kernel="bucketed", Hh=Hh, Ll=Ll)
         obs, _ = v.tables()
         x = int(rng.integers(0, n))
         xo = obs[x].tolist()
         o1 = xo[int(rng.integers(0, K))]
-        rings_x = [k for k in range(K) if xo[k] != o1][: Hh - 1]          # reports that leave X one short, not via o1
-        if len(rings_x) < Ll:
+        rings_x = [k for k in range(K) if xo[k] != o1][: Hh - 1]          # X ends one short of H, none of it via o1
+        if len(rings_x) < Ll or o1 == x:
             continue
-        a = int(rng.choice([i for i in range(n) if i not in (x, o1) and i not in xo]))
-        b1 = [(x, k) for k in rings_x]
-        d1 = np.array([c[0] for c in b1], np.int32); r1 = np.array([c[1] for c in b1], np.uint8)
-        compare_batch(rb, w, sim, cl, None, (np.zeros(len(b1), np.int32), d1, r1, np.full(len(b1), DOWN, np.uint8)),
-                      perm_seed=(3 + trial) if permuted else None)
-        b2 = [(a, k) for k in rng.permutation(K)[:Hh]] + [(o1, k) for k in rng.permutation(K)[: int(rng.integers(Ll, Hh))]]
-        d2 = np.array([c[0] for c in b2], np.int32); r2 = np.array([c[1] for c in b2], np.uint8)
-        o_len, o_ann = compare_batch(rb, w, sim, cl, None, (np.zeros(len(b2), np.int32), d2, r2, np.full(len(b2), DOWN, np.uint8)),
+        a = int(rng.choice([i for i in range(n) if i not in (x, o1) and i not in xo and i not in obs[o1].tolist()]))
+        first = [(a, int(k)) for k in rng.permutation(K)[:Hh]]
+        late = [(x, k) for k in rings_x] + [(o1, int(k)) for k in rng.permutation(K)[: int(rng.integers(Ll, Hh))]]
+        rng.shuffle(late)
+        cells = first + late
+        dst = np.array([c[0] for c in cells], np.int32); ring = np.array([c[1] for c in cells], np.uint8)
+        o_len, o_ann = compare_batch(rb, w, sim, cl, None, (np.zeros(len(cells), np.int32), dst, ring, np.full(len(cells), DOWN, np.uint8)),
                                      perm_seed=(40 + trial) if permuted else None)
-        if o_len.max() == 1:
+        if o_len.max() == 1 and o_len.min() == 1:
             hits += 1
-            assert cl.getProposal(0) == [a]
+            assert cl.getProposal(0) == [a] and cl.getProposal(n - 1) == [a]
+            assert cl.debugStats()[0] == n                             # every receiver went through the interval analysis
+        # the next batch is ignored by those who announced; the others carry on
+        src2, dst2, ring2, st2 = random_batch(rng, n, K, 3, 25, n)
+        compare_batch(rb, w, sim, cl, None, (src2, dst2, ring2, st2), perm_seed=(90 + trial) if permuted else None)
     assert hits > 0
