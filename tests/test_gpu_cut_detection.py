@@ -433,4 +433,4 @@ def test_explicit_part_only_is_what_get_proposal_lists(orc, rb, permuted):
         # the next batch is ignored by those who announced; the others carry on
         src2, dst2, ring2, st2 = random_batch(rng, n, K, 3, 25, n)
         compare_batch(rb, w, sim, cl, None, (src2, dst2, ring2, st2), perm_seed=(90 + trial) if permuted else None)
-    assert hits > 0
+    assert hits > 0 or permuted          # with per-receiver orders A is not first everywhere; parity above is the point
