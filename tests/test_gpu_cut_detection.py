@@ -434,3 +434,32 @@ def test_explicit_part_only_is_what_get_proposal_lists(orc, rb, permuted):
         src2, dst2, ring2, st2 = random_batch(rng, n, K, 3, 25, n)
         compare_batch(rb, w, sim, cl, None, (src2, dst2, ring2, st2), perm_seed=(90 + trial) if permuted else None)
     assert hits > 0 or permuted          # with per-receiver orders A is not first everywhere; parity above is the point
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_empty_and_fully_filtered_batches(orc, rb, kernel):
+    """empty batch, a batch whose every cell is dropped by the filter, then real work, then an empty batch again"""
+    n = 100
+    w, v, sim, cl = _worlds(orc, rb, n, kernel=kernel)
+    empty = (np.zeros(0, np.int32),) * 2 + (np.zeros(0, np.uint8),) * 2
+    compare_batch(rb, w, sim, cl, None, empty)
+    cfg = w.view.getCurrentConfigurationId()
+    rng = np.random.default_rng(2)
+    src, dst, ring, status = random_batch(rng, n, K, 4, 30, n)
+    compare_batch(rb, w, sim, cl, cfg, (src, dst, ring, status), cell_cfg=np.full(len(dst), cfg + 7, np.int64))   # all stale
+    compare_batch(rb, w, sim, cl, None, (src, dst, ring, np.zeros(len(dst), np.uint8)))                            # UP about members
+    assert cl.debugMasks(0) == {} or all(m == 0 for m in cl.debugMasks(0).values())
+    compare_batch(rb, w, sim, cl, None, (src, dst, ring, status))
+    compare_batch(rb, w, sim, cl, None, empty)
+    blocked_all = np.ones(n, np.uint8)
+    compare_batch(rb, w, sim, cl, None, (src, dst, ring, status), blocked=blocked_all)                            # nobody receives it
+
+
+def test_single_receiver_and_tiny_views(orc, rb):
+    """R = 1 (seam 1 sizes) and a 3-node view through the bucketed kernels"""
+    for n in (3, 4, 11):
+        w, v, sim, cl = _worlds(orc, rb, n, kernel="bucketed", R=1, begin=n - 1)
+        rng = np.random.default_rng(n)
+        for _ in range(3):
+            src, dst, ring, status = random_batch(rng, n, K, min(n, 3), 25, n)
+            compare_batch(rb, w, sim, cl, None, (src, dst, ring, status))

@@ -110,3 +110,28 @@ def test_tally_from_cluster(orc, rb):
         want = rb.proposal_fingerprint(b.expected_cut)
         assert r.decided and (r.hash, r.hash2, r.length) == (want[0], want[1], 20)
         assert r.count == rb.quorum(n) and r.votes_received == rb.quorum(n)   # 1980 voters, decision at the 1501st
+
+
+def test_empty_calls_and_reset(rb):
+    fp = rb.FastPaxos(CFG, 9, sender_capacity=16)
+    r = fp.handleFastRoundProposals([], [])
+    assert not r.decided and r.votes_received == 0
+    h = rb.proposal_fingerprint([3, 4])
+    r = fp.handleFastRoundProposals(list(range(7)), [h[0]] * 7, [h[1]] * 7, [2] * 7)       # quorum of 9 is 7
+    assert r.decided and r.count == 7
+    fp.reset(CFG + 1)
+    r = fp.handleFastRoundProposals(list(range(6)), [h[0]] * 6, [h[1]] * 6, [2] * 6, vote_cfg=[CFG + 1] * 6)
+    assert not r.decided and r.votes_received == 6
+    r = fp.handleFastRoundProposals([6], [h[0]], [h[1]], [2], vote_cfg=[CFG])                # stale configuration id
+    assert not r.decided and r.votes_received == 6
+    r = fp.handleFastRoundProposals([6], [h[0]], [h[1]], [2], vote_cfg=[CFG + 1])
+    assert r.decided and r.votes_received == 7 and (r.hash, r.hash2, r.length) == (h[0], h[1], 2)
+
+
+def test_many_distinct_proposals_never_decide(rb):
+    """every voter proposes something else (the conflict regime of the K,H,L sensitivity study): table growth, no decision"""
+    n = 3000
+    fp = rb.FastPaxos(CFG, n)
+    hs = np.array([rb.proposal_fingerprint([i, i + 1]) for i in range(n)], dtype=np.uint64)
+    r = fp.handleFastRoundProposals(np.arange(n), hs[:, 0], hs[:, 1], np.full(n, 2))
+    assert not r.decided and r.votes_received == n
