@@ -463,3 +463,36 @@ def test_single_receiver_and_tiny_views(orc, rb):
         for _ in range(3):
             src, dst, ring, status = random_batch(rng, n, K, min(n, 3), 25, n)
             compare_batch(rb, w, sim, cl, None, (src, dst, ring, status))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_all_delivery_modes_combined(orc, rb, seed):
+    """random K/H/L, joiners, several batches, and blocked + per-receiver subsets + per-receiver orders all at once"""
+    rng = np.random.default_rng(7000 + seed)
+    Kx = int(rng.integers(3, 15))
+    Hx = int(rng.integers(1, Kx + 1))
+    Lx = int(rng.integers(1, Hx + 1))
+    n, nj = int(rng.integers(20, 200)), int(rng.integers(0, 6))
+    R = int(rng.integers(1, n + 1))
+    begin = int(rng.integers(0, n - R + 1))
+    w = OracleWorld(orc, n, Kx, n_joiners=nj)
+    v = rb.MembershipView.from_packed(Kx, *w.member_packed())
+    if nj:
+        v.registerJoiners(*w.joiner_endpoints())
+    sim = orc.ClusterSim(w.view, Kx, Hx, Lx, R, receiver_base=begin)
+    cl = rb.VirtualCluster(v, Hx, Lx, n_receivers=R, receiver_begin=begin, kernel="bucketed")
+    words = (R + 31) // 32
+    for t in range(int(rng.integers(2, 7))):
+        src, dst, ring, status = random_batch(rng, n + nj, Kx, int(rng.integers(1, 8)), int(rng.integers(1, 70)), n)
+        kw = {}
+        if rng.random() < 0.6:
+            kw["blocked"] = (rng.random(R) < 0.15).astype(np.uint8)
+        if rng.random() < 0.6:
+            bm = rng.integers(0, 2**32, size=(len(dst), words), dtype=np.uint64).astype(np.uint32)
+            bm |= rng.integers(0, 2**32, size=(len(dst), words), dtype=np.uint64).astype(np.uint32)
+            kw["bitmap"] = bm
+        if rng.random() < 0.6:
+            kw["perm_seed"] = int(rng.integers(0, 2**62))
+        compare_batch(rb, w, sim, cl, None, (src, dst, ring, status), **kw)
+        if rng.random() < 0.15:
+            cl.clear(); sim.reset()
