@@ -16,6 +16,7 @@
 #include <thread>
 
 #include "rapid_oracle.hpp"
+#include "paxos_oracle.hpp"
 
 using namespace oracle;
 
@@ -431,6 +432,98 @@ int32_t orc_sim_tally(orc_universe* u, int64_t cfg, int32_t membership_size, int
         if (decided_pid[(size_t)i] >= 0) ++nd;
     }
     return nd;
+}
+
+/* ---------------- classic Paxos (Paxos.java) — one literal instance per node ---------------- */
+struct orc_px {
+    orc_universe* u;
+    std::unique_ptr<ClassicPaxos> px;
+};
+static Value value_of(const orc_universe* u, const int32_t* tags, int32_t n) {
+    Value v;
+    v.reserve((size_t)(n > 0 ? n : 0));
+    for (int32_t i = 0; i < n; ++i) v.push_back(u->eps[(size_t)tags[i]]);
+    return v;
+}
+orc_px* orc_px_create(orc_universe* u, int32_t my_tag, int32_t my_hash, int64_t cfg, int32_t N) {
+    orc_px* p = new orc_px();
+    p->u = u;
+    p->px.reset(new ClassicPaxos(u->eps[(size_t)my_tag], my_hash, cfg, N));
+    return p;
+}
+void orc_px_destroy(orc_px* p) { delete p; }
+/* out_rank[2] = crnd */
+int32_t orc_px_start_phase1a(orc_px* p, int32_t round, int32_t* out_rank) {
+    Phase1aMessage m;
+    if (!p->px->startPhase1a(round, &m)) return 0;
+    out_rank[0] = m.rank.round; out_rank[1] = m.rank.nodeIndex;
+    return 1;
+}
+/* reply: out_ranks[4] = rnd, vrnd; out_tags/out_len = vval */
+int32_t orc_px_phase1a(orc_px* p, int32_t sender, int64_t cfg, int32_t round, int32_t node, int32_t* out_ranks,
+                       int32_t* out_tags, int32_t cap, int32_t* out_len) {
+    Phase1aMessage m;
+    m.sender = p->u->eps[(size_t)sender]; m.configurationId = cfg; m.rank.round = round; m.rank.nodeIndex = node;
+    Phase1bMessage r;
+    if (!p->px->handlePhase1aMessage(m, &r)) return 0;
+    out_ranks[0] = r.rnd.round; out_ranks[1] = r.rnd.nodeIndex; out_ranks[2] = r.vrnd.round; out_ranks[3] = r.vrnd.nodeIndex;
+    *out_len = emit_tags(p->u, r.vval, out_tags, cap);
+    return 1;
+}
+/* ranks[4] = rnd, vrnd.  returns 1 iff a Phase2aMessage (rnd = out_rank, vval = out_tags) is broadcast */
+int32_t orc_px_phase1b(orc_px* p, int32_t sender, int64_t cfg, const int32_t* ranks, const int32_t* tags, int32_t n,
+                       int32_t* out_rank, int32_t* out_tags, int32_t cap, int32_t* out_len) {
+    Phase1bMessage m;
+    m.sender = p->u->eps[(size_t)sender]; m.configurationId = cfg;
+    m.rnd.round = ranks[0]; m.rnd.nodeIndex = ranks[1]; m.vrnd.round = ranks[2]; m.vrnd.nodeIndex = ranks[3];
+    m.vval = value_of(p->u, tags, n);
+    Phase2aMessage o;
+    if (!p->px->handlePhase1bMessage(m, &o)) return 0;
+    out_rank[0] = o.rnd.round; out_rank[1] = o.rnd.nodeIndex;
+    *out_len = emit_tags(p->u, o.vval, out_tags, cap);
+    return 1;
+}
+/* returns 1 iff a Phase2bMessage (same rnd, same value) is broadcast */
+int32_t orc_px_phase2a(orc_px* p, int32_t sender, int64_t cfg, int32_t round, int32_t node, const int32_t* tags, int32_t n) {
+    Phase2aMessage m;
+    m.sender = p->u->eps[(size_t)sender]; m.configurationId = cfg; m.rnd.round = round; m.rnd.nodeIndex = node;
+    m.vval = value_of(p->u, tags, n);
+    Phase2bMessage o;
+    return p->px->handlePhase2aMessage(m, &o) ? 1 : 0;
+}
+/* returns 1 iff this message made the node decide */
+int32_t orc_px_phase2b(orc_px* p, int32_t sender, int64_t cfg, int32_t round, int32_t node, const int32_t* tags, int32_t n) {
+    Phase2bMessage m;
+    m.sender = p->u->eps[(size_t)sender]; m.configurationId = cfg; m.rnd.round = round; m.rnd.nodeIndex = node;
+    m.endpoints = value_of(p->u, tags, n);
+    return p->px->handlePhase2bMessage(m) ? 1 : 0;
+}
+void orc_px_register_fast_round_vote(orc_px* p, const int32_t* tags, int32_t n) {
+    p->px->registerFastRoundVote(value_of(p->u, tags, n));
+}
+int32_t orc_px_decided(orc_px* p) { return p->px->decided() ? 1 : 0; }
+int32_t orc_px_decision(orc_px* p, int32_t* out, int32_t cap) { return emit_tags(p->u, p->px->decision(), out, cap); }
+int32_t orc_px_vval(orc_px* p, int32_t* out, int32_t cap) { return emit_tags(p->u, p->px->vval(), out, cap); }
+int32_t orc_px_cval(orc_px* p, int32_t* out, int32_t cap) { return emit_tags(p->u, p->px->cval(), out, cap); }
+/* out[6] = rnd, vrnd, crnd */
+void orc_px_ranks(orc_px* p, int32_t* out) {
+    const Rank a = p->px->rnd(), b = p->px->vrnd(), c = p->px->crnd();
+    out[0] = a.round; out[1] = a.nodeIndex; out[2] = b.round; out[3] = b.nodeIndex; out[4] = c.round; out[5] = c.nodeIndex;
+}
+/* selectProposalUsingCoordinatorRule over n messages: vrnd[2n], vval of message i = tags[off[i]..off[i+1]).
+ * returns the chosen value's length (tags to out), -1 if the list was empty (IllegalArgumentException). */
+int32_t orc_px_coordinator_rule(orc_px* p, int32_t n, const int32_t* vrnd, const int32_t* off, const int32_t* tags,
+                                int32_t* out, int32_t cap) {
+    std::vector<Phase1bMessage> msgs((size_t)n);
+    for (int32_t i = 0; i < n; ++i) {
+        msgs[(size_t)i].vrnd.round = vrnd[2 * i]; msgs[(size_t)i].vrnd.nodeIndex = vrnd[2 * i + 1];
+        msgs[(size_t)i].vval = value_of(p->u, tags + off[i], off[i + 1] - off[i]);
+    }
+    try {
+        return emit_tags(p->u, p->px->selectProposalUsingCoordinatorRule(msgs), out, cap);
+    } catch (const std::invalid_argument&) {
+        return -1;
+    }
 }
 
 int32_t orc_hardware_threads(void) { return (int32_t)std::thread::hardware_concurrency(); }

@@ -99,6 +99,20 @@ def lib():
         "orc_sim_num_proposals": (i32, [vp, i64]),
         "orc_sim_updates_in_progress": (i32, [vp, i64]),
         "orc_sim_tally": (i32, [vp, i64, i32, i32, i64, p, p, p, p, p, i32, p, p, p]),
+        "orc_px_create": (vp, [vp, i32, i32, i64, i32]),
+        "orc_px_destroy": (None, [vp]),
+        "orc_px_start_phase1a": (i32, [vp, i32, p]),
+        "orc_px_phase1a": (i32, [vp, i32, i64, i32, i32, p, p, i32, p]),
+        "orc_px_phase1b": (i32, [vp, i32, i64, p, p, i32, p, p, i32, p]),
+        "orc_px_phase2a": (i32, [vp, i32, i64, i32, i32, p, i32]),
+        "orc_px_phase2b": (i32, [vp, i32, i64, i32, i32, p, i32]),
+        "orc_px_register_fast_round_vote": (None, [vp, p, i32]),
+        "orc_px_decided": (i32, [vp]),
+        "orc_px_decision": (i32, [vp, p, i32]),
+        "orc_px_vval": (i32, [vp, p, i32]),
+        "orc_px_cval": (i32, [vp, p, i32]),
+        "orc_px_ranks": (None, [vp, p]),
+        "orc_px_coordinator_rule": (i32, [vp, i32, p, p, p, p, i32]),
         "orc_hardware_threads": (i32, []),
     }
     for name, (res, args) in sig.items():
@@ -351,6 +365,103 @@ class FastPaxosTally:
         out = np.empty(len(self.u) + 1, np.int32)
         n = lib().orc_fp_decision(self.h, _ptr(out), len(out))
         return out[:n].tolist()
+
+
+class ClassicPaxos:
+    """Paxos.java restated (oracle/paxos_oracle.hpp).  Values are lists of endpoint tags; ranks are (round, nodeIndex).
+    Handlers return the outgoing message (or None) instead of handing it to a broadcaster."""
+
+    CAP = 4096
+
+    def __init__(self, universe: Universe, my_tag: int, my_hash: int, configuration_id: int, N: int):
+        self.u, self.me, self.cfg, self.N = universe, my_tag, configuration_id, N
+        self.h = lib().orc_px_create(universe.h, my_tag, my_hash, configuration_id, N)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_px_destroy(self.h)
+            self.h = None
+
+    @staticmethod
+    def _tags(v):
+        return _i32(v if len(v) else [0])
+
+    def startPhase1a(self, round_):
+        """-> Phase1aMessage dict broadcast to all, or None (Paxos.java:98-113)"""
+        rk = np.zeros(2, np.int32)
+        if not lib().orc_px_start_phase1a(self.h, round_, _ptr(rk)):
+            return None
+        return {"sender": self.me, "cfg": self.cfg, "rank": (int(rk[0]), int(rk[1]))}
+
+    def handlePhase1aMessage(self, m):
+        """-> Phase1bMessage dict sent to m['sender'], or None (:120-151)"""
+        rk, out, n = np.zeros(4, np.int32), np.empty(self.CAP, np.int32), C.c_int32(0)
+        if not lib().orc_px_phase1a(self.h, m["sender"], m["cfg"], m["rank"][0], m["rank"][1], _ptr(rk), _ptr(out),
+                                    self.CAP, C.addressof(n)):
+            return None
+        return {"sender": self.me, "cfg": self.cfg, "rnd": (int(rk[0]), int(rk[1])), "vrnd": (int(rk[2]), int(rk[3])),
+                "vval": out[:n.value].tolist()}
+
+    def handlePhase1bMessage(self, m):
+        """-> Phase2aMessage dict broadcast to all, or None (:159-191)"""
+        rk = _i32([m["rnd"][0], m["rnd"][1], m["vrnd"][0], m["vrnd"][1]])
+        t = self._tags(m["vval"])
+        ork, out, n = np.zeros(2, np.int32), np.empty(self.CAP, np.int32), C.c_int32(0)
+        if not lib().orc_px_phase1b(self.h, m["sender"], m["cfg"], _ptr(rk), _ptr(t), len(m["vval"]), _ptr(ork), _ptr(out),
+                                    self.CAP, C.addressof(n)):
+            return None
+        return {"sender": self.me, "cfg": self.cfg, "rnd": (int(ork[0]), int(ork[1])), "vval": out[:n.value].tolist()}
+
+    def handlePhase2aMessage(self, m):
+        """-> Phase2bMessage dict broadcast to all, or None (:198-216)"""
+        t = self._tags(m["vval"])
+        if not lib().orc_px_phase2a(self.h, m["sender"], m["cfg"], m["rnd"][0], m["rnd"][1], _ptr(t), len(m["vval"])):
+            return None
+        return {"sender": self.me, "cfg": self.cfg, "rnd": m["rnd"], "endpoints": list(m["vval"])}
+
+    def handlePhase2bMessage(self, m):
+        """-> True iff this message made the node decide (:223-236)"""
+        t = self._tags(m["endpoints"])
+        return bool(lib().orc_px_phase2b(self.h, m["sender"], m["cfg"], m["rnd"][0], m["rnd"][1], _ptr(t), len(m["endpoints"])))
+
+    def registerFastRoundVote(self, vote):
+        t = self._tags(vote)
+        lib().orc_px_register_fast_round_vote(self.h, _ptr(t), len(vote))
+
+    def selectProposalUsingCoordinatorRule(self, msgs):
+        """msgs: list of dicts with 'vrnd' and 'vval' (:271-328).  Raises ValueError on an empty list."""
+        vr = _i32([x for m in msgs for x in m["vrnd"]] or [0])
+        off = np.zeros(len(msgs) + 1, np.int32)
+        off[1:] = np.cumsum([len(m["vval"]) for m in msgs]) if msgs else []
+        tags = _i32([t for m in msgs for t in m["vval"]] or [0])
+        out = np.empty(self.CAP, np.int32)
+        n = lib().orc_px_coordinator_rule(self.h, len(msgs), _ptr(vr), _ptr(off), _ptr(tags), _ptr(out), self.CAP)
+        if n < 0:
+            raise ValueError("phase1bMessages was empty")
+        return out[:n].tolist()
+
+    def _list(self, fn):
+        out = np.empty(self.CAP, np.int32)
+        return out[:fn(self.h, _ptr(out), self.CAP)].tolist()
+
+    def decided(self):
+        return bool(lib().orc_px_decided(self.h))
+
+    def decision(self):
+        return self._list(lib().orc_px_decision)
+
+    def vval(self):
+        return self._list(lib().orc_px_vval)
+
+    def cval(self):
+        return self._list(lib().orc_px_cval)
+
+    def ranks(self):
+        """-> {'rnd': (r, i), 'vrnd': (r, i), 'crnd': (r, i)}"""
+        o = np.zeros(6, np.int32)
+        lib().orc_px_ranks(self.h, _ptr(o))
+        o = o.tolist()
+        return {"rnd": (o[0], o[1]), "vrnd": (o[2], o[3]), "crnd": (o[4], o[5])}
 
 
 class ClusterSim:
