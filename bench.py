@@ -90,20 +90,28 @@ class Clocks:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index):
-        self.rows, self.proc, self.dev = [], None, device_index
+        self.rows, self.proc, self.dev, self.t_begin = [], None, device_index, 0.0
+        self.first = threading.Event()
 
     def start(self):
+        """Start ONE polling nvidia-smi and wait until it delivers its first row: its start-up (NVML init over every GPU of
+        the box) must not overlap the timed region, or it slows the rank that shares the GPU with it."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            self.first.wait(10.0)
         except OSError:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+            self.first.set()
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -112,7 +120,8 @@ class Clocks:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        timed = [r for t, r in self.rows if t >= self.t_begin]
+        for r in (timed if timed else [r for _, r in self.rows]):
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -339,15 +348,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()             # polls from here on; samples taken from the start of the timed region are reported
     for _ in range(max(3, args.warmup)):
         res, _, _, _ = step_device()
     assert emulated or (res.decided and (res.hash, res.hash2, res.length) == (want[0], want[1], len(b.expected_cut))), \
         "decision differs from the expected cut: %r" % (res,)
 
-    clocks = Clocks(local)
-    if rank == 0:
-        clocks.start()
     barrier()
+    clocks.mark_begin()
     phases[:] = [0.0, 0.0, 0.0]
     dev_ms, main_ms, launches = 0.0, 0.0, 0
     w0 = time.perf_counter()

@@ -53,6 +53,8 @@ typedef struct rapid_view rapid_view;   /* MembershipView: K rings in HBM (SoA) 
 typedef struct rapid_cd   rapid_cd;     /* MultiNodeCutDetector state of R virtual nodes in HBM       */
 typedef struct rapid_fp   rapid_fp;     /* FastPaxos fast-round tally of one configuration            */
 typedef struct rapid_comm rapid_comm;   /* NCCL communicator for the sharded (multi-GPU) tally         */
+typedef struct rapid_px   rapid_px;     /* classic-Paxos tallies of one node (coordinator + learner)   */
+typedef struct rapid_pxa  rapid_pxa;    /* classic-Paxos acceptor state of R virtual nodes in HBM      */
 
 const char* rapid_version(void);
 int32_t rapid_last_error(char* buf, size_t cap);
@@ -219,6 +221,75 @@ int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, in
                           uint64_t* decided_hash, uint64_t* decided_hash2, int32_t* decided_len,
                           int32_t* decided_count, int32_t* votes_received);
 int32_t rapid_fp_quorum(int64_t membership_size, int64_t* out);   /* N - floor((N-1)/4) */
+
+/* ------------------------------------------------------------------------------------------------
+ * Classic-Paxos fallback  (Paxos.java)
+ * A value (List<Endpoint>) is identified by an opaque (hash, hash2, len) triple the caller chooses (for the canonical
+ * fast-round proposals: rapid_proposal_fingerprint + size); len == 0 is the empty list.  A Rank (rapid.proto:133-137)
+ * is the pair (round, node_index), ordered by signed round then signed node_index (compareRanks :333-339).
+ * All arrays are host memory, one element per message, in ARRIVAL order.
+ * ---------------------------------------------------------------------------------------------- */
+/* One node's tallies (Paxos ctor :76-90): the coordinator's Phase1b list and the learner's Phase2b sets, on the device.
+ * message_capacity bounds the Phase1b messages kept plus the distinct (rnd, sender) Phase2b pairs. */
+int32_t rapid_px_create(rapid_px** out, int64_t cfg_id, int64_t membership_size, int64_t message_capacity, int32_t device);
+int32_t rapid_px_destroy(rapid_px* px);
+/* startPhase1a :98-113: *started = 0 if crnd.round > round, else crnd = (round, node_index) and *started = 1.
+ * node_index stands for myAddr.hashCode() (:102). */
+int32_t rapid_px_start_phase1a(rapid_px* px, int32_t round, int32_t node_index, int32_t* started);
+/* selectProposalUsingCoordinatorRule :271-328 over n Phase1bMessages (stateless; N = the handle's membership size):
+ * *chosen_index = index of the message whose vval is the chosen value, -1 if the chosen value is the empty list.
+ * n == 0 is RAPID_EINVAL (the reference throws IllegalArgumentException :274). */
+int32_t rapid_px_coordinator_rule(rapid_px* px, int64_t n, const int32_t* vrnd_round, const int32_t* vrnd_node,
+                                  const uint64_t* vval_hash, const uint64_t* vval_hash2, const int32_t* vval_len,
+                                  int64_t* chosen_index);
+/* handlePhase1bMessage :159-191 for n messages: ignore if msg_cfg != cfg (:160) or rnd != crnd (:165); append; once more
+ * than N/2 messages are held, the coordinator rule runs at every arrival and the first non-empty result becomes cval
+ * (a Phase2aMessage{rnd = crnd, vval = cval} is broadcast, once).  msg_cfg / vval_hash2 may be NULL (= cfg / 0).
+ * Outputs: *proposed = 1 iff THIS call picked cval; then *trigger_index = index (in this call's arrays) of the message at
+ * which it happened and cval_* = the value.  *n_messages = phase1bMessages.size() after the call. */
+int32_t rapid_px_phase1b(rapid_px* px, int64_t n, const int64_t* msg_cfg, const int32_t* rnd_round, const int32_t* rnd_node,
+                         const int32_t* vrnd_round, const int32_t* vrnd_node, const uint64_t* vval_hash,
+                         const uint64_t* vval_hash2, const int32_t* vval_len, int32_t* proposed, int64_t* trigger_index,
+                         uint64_t* cval_hash, uint64_t* cval_hash2, int32_t* cval_len, int64_t* n_messages);
+/* handlePhase2bMessage :223-236 for n messages: ignore if msg_cfg != cfg; acceptResponses[rnd].put(sender, msg); the
+ * node decides at the first arrival that leaves more than N/2 distinct senders in that message's round, on THAT message's
+ * value (:231-235).  Outputs: *decided = 1 iff the node has decided (now or earlier); if THIS call decided,
+ * *decided_index = index of the deciding message (else -1); decided_* = the decision. */
+int32_t rapid_px_phase2b(rapid_px* px, int64_t n, const int64_t* msg_cfg, const int32_t* rnd_round, const int32_t* rnd_node,
+                         const int32_t* sender, const uint64_t* hash, const uint64_t* hash2, const int32_t* len,
+                         int32_t* decided, int64_t* decided_index, uint64_t* decided_hash, uint64_t* decided_hash2,
+                         int32_t* decided_len);
+int32_t rapid_px_last_device_ms(const rapid_px* px, float* total_ms);
+
+/* Acceptor state (rnd, vrnd, vval :63-65) of n_acceptors virtual nodes, resident in HBM; acceptor r is node
+ * acceptor_begin + r (its `sender` id in the messages it emits). */
+int32_t rapid_pxa_create(rapid_pxa** out, int64_t cfg_id, int64_t n_acceptors, int64_t acceptor_begin, int32_t device);
+int32_t rapid_pxa_destroy(rapid_pxa* a);
+/* registerFastRoundVote :244-257 for the listed acceptors (local indexes): skipped where rnd.round > 1, else
+ * rnd = vrnd = (1, 1), vval = the vote. */
+int32_t rapid_pxa_register_fast_round_votes(rapid_pxa* a, int64_t n, const int64_t* acceptor, const uint64_t* hash,
+                                            const uint64_t* hash2, const int32_t* len);
+/* Same, straight from a detector's device-resident outputs: every receiver that announced a proposal in the last batch
+ * registers it (FastPaxos.propose :94-98).  The detector's receivers must be this handle's acceptors (same count). */
+int32_t rapid_pxa_register_fast_round_votes_cd(rapid_pxa* a, const rapid_cd* cd);
+/* handlePhase1aMessage :120-151 of every acceptor for ONE broadcast Phase1aMessage: acceptors with rnd < rank adopt it
+ * and answer Phase1bMessage{rnd = rank, vrnd, vval}.  The answers stay on the device; *n_replies = how many. */
+int32_t rapid_pxa_phase1a(rapid_pxa* a, int64_t msg_cfg, int32_t round, int32_t node_index, int64_t* n_replies);
+/* handlePhase2aMessage :198-216 of every acceptor for ONE broadcast Phase2aMessage: acceptors with rnd <= msg.rnd and
+ * vrnd != msg.rnd accept (rnd = vrnd = msg.rnd, vval = msg.vval) and broadcast Phase2bMessage.  *n_accepted = how many. */
+int32_t rapid_pxa_phase2a(rapid_pxa* a, int64_t msg_cfg, int32_t round, int32_t node_index, uint64_t hash, uint64_t hash2,
+                          int32_t len, int64_t* n_accepted);
+/* Deliver the device-resident answers of the last rapid_pxa_phase1a / rapid_pxa_phase2a to a coordinator / learner,
+ * in acceptor order (perm_seed == 0) or in ascending splitmix64(perm_seed ^ sender) order.  Outputs as in
+ * rapid_px_phase1b / rapid_px_phase2b; trigger_index / decided_index are positions in that arrival order. */
+int32_t rapid_px_phase1b_from_acceptors(rapid_px* px, const rapid_pxa* a, uint64_t perm_seed, int32_t* proposed,
+                                        int64_t* trigger_index, uint64_t* cval_hash, uint64_t* cval_hash2,
+                                        int32_t* cval_len, int64_t* n_messages);
+int32_t rapid_px_phase2b_from_acceptors(rapid_px* px, const rapid_pxa* a, uint64_t perm_seed, int32_t* decided,
+                                        int64_t* decided_index, uint64_t* decided_hash, uint64_t* decided_hash2,
+                                        int32_t* decided_len);
+/* State of one acceptor: ranks[4] = rnd.round, rnd.node_index, vrnd.round, vrnd.node_index; its vval triple. */
+int32_t rapid_pxa_read(const rapid_pxa* a, int64_t acceptor, int32_t* ranks, uint64_t* hash, uint64_t* hash2, int32_t* len);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU; receivers sharded by ring-0 range; one all-reduce on the histogram)

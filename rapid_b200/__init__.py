@@ -9,7 +9,8 @@ from ._native import (RapidError, NodeNotInRingException, NodeAlreadyInRingExcep
 from .membership_view import MembershipView
 from .cut_detector import MultiNodeCutDetector, VirtualCluster, proposal_fingerprint, UP, DOWN
 from .fast_paxos import FastPaxos, NcclComm, quorum
+from .classic_paxos import Paxos, PaxosAcceptors
 
-__all__ = ["MembershipView", "MultiNodeCutDetector", "VirtualCluster", "FastPaxos", "NcclComm", "quorum",
+__all__ = ["MembershipView", "MultiNodeCutDetector", "VirtualCluster", "FastPaxos", "NcclComm", "quorum", "Paxos", "PaxosAcceptors",
            "proposal_fingerprint", "UP", "DOWN", "RapidError", "NodeNotInRingException",
            "NodeAlreadyInRingException", "UUIDAlreadySeenException", "HashCollisionError"]

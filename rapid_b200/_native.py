@@ -97,6 +97,22 @@ SIGNATURES = {
     "rapid_cd_last_device_ms": [_vp, _p, _p],
     "rapid_fp_last_device_ms": [_vp, _p],
     "rapid_fp_last_launches": [_vp, _p],
+    "rapid_px_create": [_pp, _i64, _i64, _i64, _i32],
+    "rapid_px_destroy": [_vp],
+    "rapid_px_start_phase1a": [_vp, _i32, _i32, _p],
+    "rapid_px_coordinator_rule": [_vp, _i64, _p, _p, _p, _p, _p, _p],
+    "rapid_px_phase1b": [_vp, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "rapid_px_phase2b": [_vp, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "rapid_px_last_device_ms": [_vp, _p],
+    "rapid_pxa_create": [_pp, _i64, _i64, _i64, _i32],
+    "rapid_pxa_destroy": [_vp],
+    "rapid_pxa_register_fast_round_votes": [_vp, _i64, _p, _p, _p, _p],
+    "rapid_pxa_register_fast_round_votes_cd": [_vp, _vp],
+    "rapid_pxa_phase1a": [_vp, _i64, _i32, _i32, _p],
+    "rapid_pxa_phase2a": [_vp, _i64, _i32, _i32, _u64, _u64, _i32, _p],
+    "rapid_px_phase1b_from_acceptors": [_vp, _vp, _u64, _p, _p, _p, _p, _p, _p],
+    "rapid_px_phase2b_from_acceptors": [_vp, _vp, _u64, _p, _p, _p, _p, _p],
+    "rapid_pxa_read": [_vp, _i64, _p, _p, _p, _p],
 }
 
 
