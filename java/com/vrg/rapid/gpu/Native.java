@@ -54,4 +54,25 @@ public final class Native {
     public static native int fpTallyCd(long fp, long cd, long comm, long[] out6);
 
     public static native long[] proposalFingerprint(int[] ids);
+
+    // ---- classic Paxos fallback (Paxos.java) ----
+    public static native long pxCreate(long cfgId, long membershipSize, long messageCapacity, int device);
+    public static native int pxDestroy(long px);
+    /** startPhase1a: returns 1 if crnd moved to (round, nodeIndex), 0 if ignored, <0 status */
+    public static native int pxStartPhase1a(long px, int round, int nodeIndex);
+    /** selectProposalUsingCoordinatorRule: index of the message whose vval is chosen, -1 = empty list, <-1 status-2 */
+    public static native long pxCoordinatorRule(long px, int[] vrndRound, int[] vrndNode, long[] hash, long[] hash2, int[] len);
+    /** handlePhase1bMessage over a batch; out6 = {proposed, triggerIndex, cvalHash, cvalHash2, cvalLen, nMessages} */
+    public static native int pxPhase1b(long px, long[] msgCfg, int[] rndRound, int[] rndNode, int[] vrndRound, int[] vrndNode,
+                                       long[] hash, long[] hash2, int[] len, long[] out6);
+    /** handlePhase2bMessage over a batch; out5 = {decided, decidedIndex, hash, hash2, len} */
+    public static native int pxPhase2b(long px, long[] msgCfg, int[] rndRound, int[] rndNode, int[] sender, long[] hash,
+                                       long[] hash2, int[] len, long[] out5);
+    public static native long pxaCreate(long cfgId, long nAcceptors, long acceptorBegin, int device);
+    public static native int pxaDestroy(long pxa);
+    public static native int pxaRegisterFastRoundVotesCd(long pxa, long cd);
+    public static native long pxaPhase1a(long pxa, long msgCfg, int round, int nodeIndex);            // replies or <0
+    public static native long pxaPhase2a(long pxa, long msgCfg, int round, int nodeIndex, long hash, long hash2, int len);
+    public static native int pxPhase1bFromAcceptors(long px, long pxa, long permSeed, long[] out6);
+    public static native int pxPhase2bFromAcceptors(long px, long pxa, long permSeed, long[] out5);
 }

@@ -243,3 +243,137 @@ JNIEXPORT jlongArray JNICALL Java_com_vrg_rapid_gpu_Native_proposalFingerprint(J
     (*env)->SetLongArrayRegion(env, out, 0, 2, v);
     return out;
 }
+
+/* ---------------------------------------------------------------- classic Paxos fallback (Paxos.java) */
+JNIEXPORT jlong JNICALL Java_com_vrg_rapid_gpu_Native_pxCreate(JNIEnv* env, jclass c, jlong cfg, jlong size, jlong cap, jint device) {
+    rapid_px* px = NULL;
+    const int32_t rc = rapid_px_create(&px, cfg, size, cap, device);
+    return rc == RAPID_OK ? (jlong)(intptr_t)px : 0;
+}
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_pxDestroy(JNIEnv* env, jclass c, jlong px) { return rapid_px_destroy(H(rapid_px, px)); }
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_pxStartPhase1a(JNIEnv* env, jclass c, jlong px, jint round, jint nodeIndex) {
+    int32_t started = 0;
+    const int32_t rc = rapid_px_start_phase1a(H(rapid_px, px), round, nodeIndex, &started);
+    return rc == RAPID_OK ? started : rc;
+}
+
+/* Paxos.selectProposalUsingCoordinatorRule (Paxos.java:271-328) */
+JNIEXPORT jlong JNICALL Java_com_vrg_rapid_gpu_Native_pxCoordinatorRule(JNIEnv* env, jclass c, jlong px, jintArray vrRound, jintArray vrNode,
+                                                                        jlongArray hash, jlongArray hash2, jintArray len) {
+    const jsize n = (*env)->GetArrayLength(env, len);
+    jint* r0 = (*env)->GetIntArrayElements(env, vrRound, NULL);
+    jint* r1 = (*env)->GetIntArrayElements(env, vrNode, NULL);
+    jlong* h1 = (*env)->GetLongArrayElements(env, hash, NULL);
+    jlong* h2 = hash2 ? (*env)->GetLongArrayElements(env, hash2, NULL) : NULL;
+    jint* ln = (*env)->GetIntArrayElements(env, len, NULL);
+    int64_t chosen = -1;
+    const int32_t rc = rapid_px_coordinator_rule(H(rapid_px, px), n, (const int32_t*)r0, (const int32_t*)r1, (const uint64_t*)h1,
+                                                 (const uint64_t*)h2, (const int32_t*)ln, &chosen);
+    (*env)->ReleaseIntArrayElements(env, vrRound, r0, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, vrNode, r1, JNI_ABORT);
+    (*env)->ReleaseLongArrayElements(env, hash, h1, JNI_ABORT);
+    if (h2) (*env)->ReleaseLongArrayElements(env, hash2, h2, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, len, ln, JNI_ABORT);
+    return rc == RAPID_OK ? (jlong)chosen : (jlong)rc - 2;
+}
+
+/* Paxos.handlePhase1bMessage (Paxos.java:159-191) for a batch */
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_pxPhase1b(JNIEnv* env, jclass c, jlong px, jlongArray msgCfg, jintArray rndRound,
+                                                               jintArray rndNode, jintArray vrRound, jintArray vrNode, jlongArray hash,
+                                                               jlongArray hash2, jintArray len, jlongArray out6) {
+    const jsize n = (*env)->GetArrayLength(env, len);
+    jlong* mc = msgCfg ? (*env)->GetLongArrayElements(env, msgCfg, NULL) : NULL;
+    jint* a0 = (*env)->GetIntArrayElements(env, rndRound, NULL);
+    jint* a1 = (*env)->GetIntArrayElements(env, rndNode, NULL);
+    jint* b0 = (*env)->GetIntArrayElements(env, vrRound, NULL);
+    jint* b1 = (*env)->GetIntArrayElements(env, vrNode, NULL);
+    jlong* h1 = (*env)->GetLongArrayElements(env, hash, NULL);
+    jlong* h2 = hash2 ? (*env)->GetLongArrayElements(env, hash2, NULL) : NULL;
+    jint* ln = (*env)->GetIntArrayElements(env, len, NULL);
+    int32_t proposed = 0, clen = 0;
+    int64_t trigger = -1, total = 0;
+    uint64_t ca = 0, cb = 0;
+    const int32_t rc = rapid_px_phase1b(H(rapid_px, px), n, (const int64_t*)mc, (const int32_t*)a0, (const int32_t*)a1, (const int32_t*)b0,
+                                        (const int32_t*)b1, (const uint64_t*)h1, (const uint64_t*)h2, (const int32_t*)ln, &proposed,
+                                        &trigger, &ca, &cb, &clen, &total);
+    if (mc) (*env)->ReleaseLongArrayElements(env, msgCfg, mc, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, rndRound, a0, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, rndNode, a1, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, vrRound, b0, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, vrNode, b1, JNI_ABORT);
+    (*env)->ReleaseLongArrayElements(env, hash, h1, JNI_ABORT);
+    if (h2) (*env)->ReleaseLongArrayElements(env, hash2, h2, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, len, ln, JNI_ABORT);
+    const jlong v[6] = {proposed, (jlong)trigger, (jlong)ca, (jlong)cb, clen, (jlong)total};
+    (*env)->SetLongArrayRegion(env, out6, 0, 6, v);
+    return rc;
+}
+
+/* Paxos.handlePhase2bMessage (Paxos.java:223-236) for a batch */
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_pxPhase2b(JNIEnv* env, jclass c, jlong px, jlongArray msgCfg, jintArray rndRound,
+                                                               jintArray rndNode, jintArray sender, jlongArray hash, jlongArray hash2,
+                                                               jintArray len, jlongArray out5) {
+    const jsize n = (*env)->GetArrayLength(env, len);
+    jlong* mc = msgCfg ? (*env)->GetLongArrayElements(env, msgCfg, NULL) : NULL;
+    jint* a0 = (*env)->GetIntArrayElements(env, rndRound, NULL);
+    jint* a1 = (*env)->GetIntArrayElements(env, rndNode, NULL);
+    jint* s = (*env)->GetIntArrayElements(env, sender, NULL);
+    jlong* h1 = (*env)->GetLongArrayElements(env, hash, NULL);
+    jlong* h2 = hash2 ? (*env)->GetLongArrayElements(env, hash2, NULL) : NULL;
+    jint* ln = (*env)->GetIntArrayElements(env, len, NULL);
+    int32_t decided = 0, dlen = 0;
+    int64_t at = -1;
+    uint64_t da = 0, db = 0;
+    const int32_t rc = rapid_px_phase2b(H(rapid_px, px), n, (const int64_t*)mc, (const int32_t*)a0, (const int32_t*)a1, (const int32_t*)s,
+                                        (const uint64_t*)h1, (const uint64_t*)h2, (const int32_t*)ln, &decided, &at, &da, &db, &dlen);
+    if (mc) (*env)->ReleaseLongArrayElements(env, msgCfg, mc, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, rndRound, a0, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, rndNode, a1, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, sender, s, JNI_ABORT);
+    (*env)->ReleaseLongArrayElements(env, hash, h1, JNI_ABORT);
+    if (h2) (*env)->ReleaseLongArrayElements(env, hash2, h2, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, len, ln, JNI_ABORT);
+    const jlong v[5] = {decided, (jlong)at, (jlong)da, (jlong)db, dlen};
+    (*env)->SetLongArrayRegion(env, out5, 0, 5, v);
+    return rc;
+}
+
+JNIEXPORT jlong JNICALL Java_com_vrg_rapid_gpu_Native_pxaCreate(JNIEnv* env, jclass c, jlong cfg, jlong n, jlong begin, jint device) {
+    rapid_pxa* a = NULL;
+    const int32_t rc = rapid_pxa_create(&a, cfg, n, begin, device);
+    return rc == RAPID_OK ? (jlong)(intptr_t)a : 0;
+}
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_pxaDestroy(JNIEnv* env, jclass c, jlong a) { return rapid_pxa_destroy(H(rapid_pxa, a)); }
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_pxaRegisterFastRoundVotesCd(JNIEnv* env, jclass c, jlong a, jlong cd) {
+    return rapid_pxa_register_fast_round_votes_cd(H(rapid_pxa, a), H(rapid_cd, cd));
+}
+JNIEXPORT jlong JNICALL Java_com_vrg_rapid_gpu_Native_pxaPhase1a(JNIEnv* env, jclass c, jlong a, jlong cfg, jint round, jint node) {
+    int64_t n = 0;
+    const int32_t rc = rapid_pxa_phase1a(H(rapid_pxa, a), cfg, round, node, &n);
+    return rc == RAPID_OK ? (jlong)n : (jlong)rc;
+}
+JNIEXPORT jlong JNICALL Java_com_vrg_rapid_gpu_Native_pxaPhase2a(JNIEnv* env, jclass c, jlong a, jlong cfg, jint round, jint node, jlong h1,
+                                                                 jlong h2, jint len) {
+    int64_t n = 0;
+    const int32_t rc = rapid_pxa_phase2a(H(rapid_pxa, a), cfg, round, node, (uint64_t)h1, (uint64_t)h2, len, &n);
+    return rc == RAPID_OK ? (jlong)n : (jlong)rc;
+}
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_pxPhase1bFromAcceptors(JNIEnv* env, jclass c, jlong px, jlong a, jlong seed, jlongArray out6) {
+    int32_t proposed = 0, clen = 0;
+    int64_t trigger = -1, total = 0;
+    uint64_t ca = 0, cb = 0;
+    const int32_t rc = rapid_px_phase1b_from_acceptors(H(rapid_px, px), H(rapid_pxa, a), (uint64_t)seed, &proposed, &trigger, &ca, &cb, &clen, &total);
+    const jlong v[6] = {proposed, (jlong)trigger, (jlong)ca, (jlong)cb, clen, (jlong)total};
+    (*env)->SetLongArrayRegion(env, out6, 0, 6, v);
+    return rc;
+}
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_pxPhase2bFromAcceptors(JNIEnv* env, jclass c, jlong px, jlong a, jlong seed, jlongArray out5) {
+    int32_t decided = 0, dlen = 0;
+    int64_t at = -1;
+    uint64_t da = 0, db = 0;
+    const int32_t rc = rapid_px_phase2b_from_acceptors(H(rapid_px, px), H(rapid_pxa, a), (uint64_t)seed, &decided, &at, &da, &db, &dlen);
+    const jlong v[5] = {decided, (jlong)at, (jlong)da, (jlong)db, dlen};
+    (*env)->SetLongArrayRegion(env, out5, 0, 5, v);
+    return rc;
+}

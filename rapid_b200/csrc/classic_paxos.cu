@@ -66,6 +66,26 @@ __device__ int32_t px_find_or_insert(const PxTable t, uint64_t a, uint64_t b, in
     return -1;
 }
 
+// Warp-aggregated find-or-insert: one probe per distinct key per warp (a million messages typically carry a handful of
+// values, and without this every thread of the first wave fights over the same entry).  EVERY thread of the warp must call
+// it; `valid` says whether this lane has a key.  *is_new is set on one lane per newly inserted key.
+__device__ int32_t px_find_or_insert_warp(const PxTable t, bool valid, uint64_t a, uint64_t b, int32_t c, bool* is_new) {
+    *is_new = false;
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return -1;
+    const unsigned same = __match_any_sync(active, a ^ rotl64(b, 21) ^ ((uint64_t)(uint32_t)c << 1));
+    const int leader = __ffs(same) - 1;
+    int32_t e = -1;
+    bool nw = false;
+    if ((int)(threadIdx.x & 31) == leader) e = px_find_or_insert(t, a, b, c, &nw);
+    e = __shfl_sync(same, e, leader);
+    const uint64_t la = __shfl_sync(same, a, leader), lb = __shfl_sync(same, b, leader);
+    const int32_t lc = __shfl_sync(same, c, leader);
+    if (la != a || lb != b || lc != c) e = px_find_or_insert(t, a, b, c, &nw);      // folded keys collided: probe for myself
+    *is_new = nw;
+    return e;
+}
+
 __device__ __forceinline__ int32_t warp_min(int32_t v) { return __reduce_min_sync(0xffffffffu, v); }
 __device__ __forceinline__ long long warp_max64(long long v) {
     for (int o = 16; o > 0; o >>= 1) { const long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
@@ -99,12 +119,13 @@ __global__ void k_px_rule_collect(int64_t m, const int64_t* __restrict__ vr, con
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool col = false;
     int32_t fc = INT_MAX;
+    const bool want = i < m && vr[i] == sc->max_rank && len[i] > 0;
+    bool nw;
+    const int32_t e = px_find_or_insert_warp(t, want, want ? h1[i] : 0, want ? h2[i] : 0, want ? len[i] : 0, &nw);
     if (i < m) {
         idx[i] = (int32_t)i;
         uint32_t k = t.T;
-        if (vr[i] == sc->max_rank && len[i] > 0) {
-            bool nw;
-            const int32_t e = px_find_or_insert(t, h1[i], h2[i], len[i], &nw);
+        if (want) {
             if (e < 0) atomicExch(&sc->overflow, 1);
             else {
                 if (nw) atomicAdd(&sc->distinct, 1);
@@ -223,13 +244,14 @@ __global__ void k_px2b_rounds(int64_t n, const int64_t* __restrict__ rnd, int64_
                               PxTable t, const int32_t* __restrict__ t_val, uint32_t* __restrict__ key, int32_t* __restrict__ idx,
                               PxScal* __restrict__ sc) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t e = i < n ? slot[i] : -1;
+    const bool first = e >= 0 && t_val[e] == (int32_t)i;
+    bool nw;
+    const int32_t r = px_find_or_insert_warp(t, first, first ? (uint64_t)(rnd ? rnd[i] : rnd_const) : 0, 0, 1, &nw);   // c = 1: a round counter
     if (i >= n) return;
     idx[i] = (int32_t)i;
     uint32_t k = t.T;
-    const int32_t e = slot[i];
-    if (e >= 0 && t_val[e] == (int32_t)i) {
-        bool nw;
-        const int32_t r = px_find_or_insert(t, (uint64_t)(rnd ? rnd[i] : rnd_const), 0, 1, &nw);   // c = 1: a round counter
+    if (first) {
         if (r < 0) atomicExch(&sc->overflow, 1);
         else { if (nw) atomicAdd(&sc->inserted, 1); k = (uint32_t)r; }
     }

@@ -13,6 +13,12 @@ pytestmark = pytest.mark.gpu
 M64 = (1 << 64) - 1
 
 
+@pytest.fixture(scope="module")
+def rb():
+    import rapid_b200
+    return rapid_b200
+
+
 def splitmix64(x):
     x = (x + 0x9E3779B97F4A7C15) & M64
     x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M64
