@@ -55,6 +55,7 @@ typedef struct rapid_fp   rapid_fp;     /* FastPaxos fast-round tally of one con
 typedef struct rapid_comm rapid_comm;   /* NCCL communicator for the sharded (multi-GPU) tally         */
 typedef struct rapid_px   rapid_px;     /* classic-Paxos tallies of one node (coordinator + learner)   */
 typedef struct rapid_pxa  rapid_pxa;    /* classic-Paxos acceptor state of R virtual nodes in HBM      */
+typedef struct rapid_wire rapid_wire;   /* protobuf wire-format decoder bound to a view's dictionary    */
 
 const char* rapid_version(void);
 int32_t rapid_last_error(char* buf, size_t cap);
@@ -233,6 +234,8 @@ int32_t rapid_fp_quorum(int64_t membership_size, int64_t* out);   /* N - floor((
  * message_capacity bounds the Phase1b messages kept plus the distinct (rnd, sender) Phase2b pairs. */
 int32_t rapid_px_create(rapid_px** out, int64_t cfg_id, int64_t membership_size, int64_t message_capacity, int32_t device);
 int32_t rapid_px_destroy(rapid_px* px);
+/* Start over for the next configuration (the new Paxos of FastPaxos.java:86 / MembershipService.java:427-429). */
+int32_t rapid_px_reset(rapid_px* px, int64_t cfg_id, int64_t membership_size);
 /* startPhase1a :98-113: *started = 0 if crnd.round > round, else crnd = (round, node_index) and *started = 1.
  * node_index stands for myAddr.hashCode() (:102). */
 int32_t rapid_px_start_phase1a(rapid_px* px, int32_t round, int32_t node_index, int32_t* started);
@@ -265,6 +268,7 @@ int32_t rapid_px_last_device_ms(const rapid_px* px, float* total_ms);
  * acceptor_begin + r (its `sender` id in the messages it emits). */
 int32_t rapid_pxa_create(rapid_pxa** out, int64_t cfg_id, int64_t n_acceptors, int64_t acceptor_begin, int32_t device);
 int32_t rapid_pxa_destroy(rapid_pxa* a);
+int32_t rapid_pxa_reset(rapid_pxa* a, int64_t cfg_id);      /* rnd = vrnd = (0, 0), vval = [] (:82-85) for every acceptor */
 /* registerFastRoundVote :244-257 for the listed acceptors (local indexes): skipped where rnd.round > 1, else
  * rnd = vrnd = (1, 1), vval = the vote. */
 int32_t rapid_pxa_register_fast_round_votes(rapid_pxa* a, int64_t n, const int64_t* acceptor, const uint64_t* hash,
@@ -290,6 +294,44 @@ int32_t rapid_px_phase2b_from_acceptors(rapid_px* px, const rapid_pxa* a, uint64
                                         int32_t* decided_len);
 /* State of one acceptor: ranks[4] = rnd.round, rnd.node_index, vrnd.round, vrnd.node_index; its vval triple. */
 int32_t rapid_pxa_read(const rapid_pxa* a, int64_t acceptor, int32_t* ranks, uint64_t* hash, uint64_t* hash2, int32_t* len);
+
+/* ------------------------------------------------------------------------------------------------
+ * Wire-format ingest  (rapid.proto) — the step BEFORE the path: serialized protobuf bytes, as
+ * they arrive at IMessagingServer / MembershipService.handleMessage(RapidRequest) (MembershipService.java:174),
+ * straight into the cell SoA and the Endpoint -> id dictionary, on the device.
+ * ---------------------------------------------------------------------------------------------- */
+#define RAPID_WIRE_REQUEST 1u   /* the bytes are a RapidRequest (rapid.proto:21-35) whose content is the message */
+/* A decoder owns the Endpoint{hostname, port} -> int32 id table of `v` (rebuilt when the view changes). */
+int32_t rapid_wire_create(rapid_wire** out, rapid_view* v);
+int32_t rapid_wire_destroy(rapid_wire* w);
+/* One serialized BatchedAlertMessage (rapid.proto:95-99): every AlertMessage (:101-110) becomes one cell per ring
+ * number (MultiNodeCutDetector.java:79-80), in message order then ring order.  Endpoints map to ids; the edgeDst of
+ * an UP alert that is not in the dictionary yet is REGISTERED as a joiner (rapid_view_register_joiners) in order of
+ * first appearance; a DOWN alert about an unknown endpoint is dropped (MembershipService.java:660-664 would filter
+ * it); an unknown edgeSrc becomes -1 (the detector never reads it).  Malformed bytes -> RAPID_EINVAL
+ * (InvalidProtocolBufferException).  Unknown fields are skipped; packed and unpacked ringNumber are both accepted.
+ * Outputs (each may be NULL): number of AlertMessages, cells produced, messages dropped, joiners registered, and
+ * the id of BatchedAlertMessage.sender (-1 if unknown / absent). */
+int32_t rapid_wire_decode_alerts(rapid_wire* w, const uint8_t* bytes, int64_t len, uint32_t flags, int64_t* n_messages,
+                                 int64_t* n_cells, int64_t* n_dropped, int64_t* n_new_joiners, int32_t* sender_id);
+/* The cells of the last decode, resident on the device (valid until the next decode on this handle): pass them to
+ * rapid_cd_apply_batch_dev.  cfg carries each cell's AlertMessage.configurationId. */
+int32_t rapid_wire_cells_dev(const rapid_wire* w, const int32_t** src, const int32_t** dst, const uint8_t** ring,
+                             const uint8_t** status, const int64_t** cfg);
+/* Host copies of the same (arrays of n_cells; each may be NULL). */
+int32_t rapid_wire_read_cells(const rapid_wire* w, int32_t* src, int32_t* dst, uint8_t* ring, uint8_t* status, int64_t* cfg);
+/* Per AlertMessage of the last decode (arrays of n_messages; each may be NULL): edgeDst id (-1 if dropped), edgeStatus,
+ * number of ring numbers, NodeId (extractJoinerUuidAndMetadata, MembershipService.java:677-685; has_node_id = 0 if the
+ * field is absent) and the byte range of the Metadata submessage inside the input buffer (len 0 if absent). */
+int32_t rapid_wire_read_messages(const rapid_wire* w, int32_t* dst, uint8_t* status, int32_t* n_rings, int64_t* node_high,
+                                 int64_t* node_low, uint8_t* has_node_id, int64_t* meta_off, int32_t* meta_len);
+/* n serialized FastRoundPhase2bMessages (rapid.proto:105-110), message i = bytes[off[i] .. off[i+1]):
+ * sender id (-1 if unknown), configurationId, and the proposal as rapid_proposal_fingerprint + size.  A proposal
+ * naming an endpoint that is not in the dictionary cannot be identified: RAPID_ENOT_IN_RING. */
+int32_t rapid_wire_decode_votes(rapid_wire* w, const uint8_t* bytes, const int64_t* off, int64_t n, uint32_t flags,
+                                int32_t* sender, int64_t* vote_cfg, uint64_t* proposal_hash, uint64_t* proposal_hash2,
+                                int32_t* proposal_len);
+int32_t rapid_wire_last_device_ms(const rapid_wire* w, float* total_ms);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU; receivers sharded by ring-0 range; one all-reduce on the histogram)

@@ -10,7 +10,8 @@ from .membership_view import MembershipView
 from .cut_detector import MultiNodeCutDetector, VirtualCluster, proposal_fingerprint, UP, DOWN
 from .fast_paxos import FastPaxos, NcclComm, quorum
 from .classic_paxos import Paxos, PaxosAcceptors
+from .wire import WireDecoder
 
-__all__ = ["MembershipView", "MultiNodeCutDetector", "VirtualCluster", "FastPaxos", "NcclComm", "quorum", "Paxos", "PaxosAcceptors",
+__all__ = ["MembershipView", "MultiNodeCutDetector", "VirtualCluster", "FastPaxos", "NcclComm", "quorum", "Paxos", "PaxosAcceptors", "WireDecoder",
            "proposal_fingerprint", "UP", "DOWN", "RapidError", "NodeNotInRingException",
            "NodeAlreadyInRingException", "UUIDAlreadySeenException", "HashCollisionError"]

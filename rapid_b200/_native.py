@@ -16,6 +16,7 @@ EINVAL, ENOT_IN_RING, EALREADY_IN_RING, EUUID_SEEN, EHASH_COLLISION, ECUDA, ENCC
 
 CD_SERVICE, CD_RAW, CD_SWEEP, CD_BUCKETED = 0, 1, 2, 4
 DELIVERY_BLOCKED, DELIVERY_BITMAP, DELIVERY_PERMUTED = 1, 2, 4
+WIRE_REQUEST = 1
 EDGE_UP, EDGE_DOWN = 0, 1
 MAX_K = 14
 
@@ -99,6 +100,16 @@ SIGNATURES = {
     "rapid_fp_last_launches": [_vp, _p],
     "rapid_px_create": [_pp, _i64, _i64, _i64, _i32],
     "rapid_px_destroy": [_vp],
+    "rapid_px_reset": [_vp, _i64, _i64],
+    "rapid_pxa_reset": [_vp, _i64],
+    "rapid_wire_create": [_pp, _vp],
+    "rapid_wire_destroy": [_vp],
+    "rapid_wire_decode_alerts": [_vp, _p, _i64, _u32, _p, _p, _p, _p, _p],
+    "rapid_wire_cells_dev": [_vp, _p, _p, _p, _p, _p],
+    "rapid_wire_read_cells": [_vp, _p, _p, _p, _p, _p],
+    "rapid_wire_read_messages": [_vp, _p, _p, _p, _p, _p, _p, _p, _p],
+    "rapid_wire_decode_votes": [_vp, _p, _p, _i64, _u32, _p, _p, _p, _p, _p],
+    "rapid_wire_last_device_ms": [_vp, _p],
     "rapid_px_start_phase1a": [_vp, _i32, _i32, _p],
     "rapid_px_coordinator_rule": [_vp, _i64, _p, _p, _p, _p, _p, _p],
     "rapid_px_phase1b": [_vp, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],

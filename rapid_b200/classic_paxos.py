@@ -65,6 +65,12 @@ class Paxos:
         except Exception:
             pass
 
+    def reset(self, configuration_id, membership_size=None):
+        """the Paxos of the next configuration (FastPaxos.java:86) on the same buffers"""
+        self.cfg = int(configuration_id)
+        self.N = int(self.N if membership_size is None else membership_size)
+        N.check(N.lib().rapid_px_reset(self._h, self.cfg, self.N))
+
     def startPhase1a(self, round_, node_index):
         """:98-113 — node_index stands for myAddr.hashCode().  -> True iff a Phase1aMessage(rank) goes out"""
         out = C.c_int32(0)
@@ -160,6 +166,10 @@ class PaxosAcceptors:
             self.close()
         except Exception:
             pass
+
+    def reset(self, configuration_id):
+        self.cfg = int(configuration_id)
+        N.check(N.lib().rapid_pxa_reset(self._h, self.cfg))
 
     def registerFastRoundVotes(self, acceptor, value_hash, value_len, value_hash2=None):
         """:244-257 for the listed acceptors"""

@@ -585,6 +585,14 @@ static int32_t px_arrival_order(PX* px, const PXA* a, uint64_t perm_seed, const 
     return RAPID_OK;
 }
 
+static int32_t px_clear_tables(PX* px) {
+    RAPID_CUDA(cudaMemsetAsync(px->t_state.p, 0, (size_t)px->T * sizeof(int32_t), px->stream));
+    const int64_t words = (int64_t)px->T / 2;                 // t_val = INT_MAX everywhere
+    k_px_fill64<<<grid_for(words), TB, 0, px->stream>>>(words, (uint64_t*)px->t_val.p, ((uint64_t)(uint32_t)INT_MAX << 32) | (uint32_t)INT_MAX);
+    RAPID_KERNEL_CHECK();
+    return RAPID_OK;
+}
+
 }  // namespace rapid
 
 using namespace rapid;
@@ -613,17 +621,24 @@ int32_t rapid_px_create(rapid_px** out, int64_t cfg_id, int64_t membership_size,
         if ((rc = px->t_state.reserve(T)) || (rc = px->t_c.reserve(T)) || (rc = px->t_val.reserve(T)) || (rc = px->t_a.reserve(T)) ||
             (rc = px->t_b.reserve(T))) break;
         if ((rc = px->sc.reserve(1)) || (rc = px->h_sc.reserve(1))) break;
-        cudaMemsetAsync(px->t_state.p, 0, (size_t)T * sizeof(int32_t), px->stream);
         cudaMemsetAsync(px->sc.p, 0, sizeof(PxScal), px->stream);
-        {   // t_val = INT_MAX everywhere
-            const int64_t words = (int64_t)T / 2;
-            k_px_fill64<<<grid_for(words), TB, 0, px->stream>>>(words, (uint64_t*)px->t_val.p, ((uint64_t)(uint32_t)INT_MAX << 32) | (uint32_t)INT_MAX);
-        }
+        if ((rc = px_clear_tables(px))) break;
         if (cudaStreamSynchronize(px->stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "init", __FILE__, __LINE__); break; }
     } while (0);
     if (rc) { rapid_px_destroy(px); return rc; }
     *out = px;
     return RAPID_OK;
+}
+
+// The Paxos instance of the next configuration (FastPaxos ctor :86, MembershipService.java:427-429) on the same buffers.
+int32_t rapid_px_reset(rapid_px* px, int64_t cfg_id, int64_t membership_size) {
+    if (!px || membership_size < 1) { set_error("bad arguments"); return RAPID_EINVAL; }
+    DeviceGuard g(px->device);
+    px->cfg = cfg_id; px->N = membership_size;
+    px->crnd = pack_rank(0, 0); px->have_cval = false; px->cval_h1 = px->cval_h2 = 0; px->cval_len = 0;
+    px->n_msgs = 0; px->first_nonempty = -1;
+    px->decided = false; px->dec_h1 = px->dec_h2 = 0; px->dec_len = 0; px->pairs = 0;
+    return px_clear_tables(px);                               // asynchronous: ordered before the next call on the stream
 }
 
 int32_t rapid_px_destroy(rapid_px* px) {
@@ -750,6 +765,16 @@ int32_t rapid_pxa_create(rapid_pxa** out, int64_t cfg_id, int64_t n_acceptors, i
     } while (0);
     if (rc) { rapid_pxa_destroy(a); return rc; }
     *out = a;
+    return RAPID_OK;
+}
+
+// every acceptor back to rnd = vrnd = (0, 0), vval = [] (Paxos ctor :82-85) for the next configuration
+int32_t rapid_pxa_reset(rapid_pxa* a, int64_t cfg_id) {
+    if (!a) { set_error("NULL handle"); return RAPID_EINVAL; }
+    DeviceGuard g(a->device);
+    a->cfg = cfg_id; a->last_kind = 0; a->n_out = 0;
+    k_pxa_init<<<grid_for(a->R), TB, 0, a->stream>>>(a->R, a->rnd.p, a->vrnd.p, a->h1.p, a->h2.p, a->len.p);
+    RAPID_KERNEL_CHECK();
     return RAPID_OK;
 }
 

@@ -170,6 +170,7 @@ struct View {
     int K = 0;
     int64_t n = 0;          // members
     int64_t nj = 0;         // registered joiners (ids n .. n+nj-1)
+    uint64_t epoch = 1;     // bumped whenever the endpoint -> id dictionary changes (joiners registered, cut applied)
     cudaStream_t stream = nullptr;
     // endpoints (members then joiners)
     DevBuf<uint8_t> host_bytes;   size_t host_bytes_len = 0;

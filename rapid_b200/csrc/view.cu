@@ -429,6 +429,7 @@ int32_t rapid_view_register_joiners(rapid_view* v, int64_t n_add, const uint8_t*
     }
     if (rc != RAPID_OK) { pop_endpoints(v, n_add); return rc; }
     v->nj += n_add;
+    ++v->epoch;
     return RAPID_OK;
 }
 
@@ -471,6 +472,7 @@ int32_t rapid_view_apply_cut(rapid_view* v, const int32_t* cut_ids, int64_t n_cu
     static const int32_t zero_off[1] = {0};
     RAPID_CHECK(upload_endpoints(v, next, next ? hb.data() : &dummy, next ? off.data() : zero_off, port.data()));
     v->n = next;
+    ++v->epoch;
     RAPID_CHECK(build_rings(v));
     if (out_old_to_new) memcpy(out_old_to_new, map.data(), (size_t)tot * sizeof(int32_t));
     return RAPID_OK;
