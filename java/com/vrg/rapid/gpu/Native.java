@@ -75,4 +75,12 @@ public final class Native {
     public static native long pxaPhase2a(long pxa, long msgCfg, int round, int nodeIndex, long hash, long hash2, int len);
     public static native int pxPhase1bFromAcceptors(long px, long pxa, long permSeed, long[] out6);
     public static native int pxPhase2bFromAcceptors(long px, long pxa, long permSeed, long[] out5);
+
+    // ---- wire-format ingest (rapid.proto bytes -> cells on the device) ----
+    public static native long wireCreate(long view);
+    public static native int wireDestroy(long wire);
+    /** bytes = BatchedAlertMessage.toByteArray() (or the RapidRequest, asRequest); out5 = {nMessages, nCells, nDropped, nNewJoiners, senderId} */
+    public static native int wireDecodeAlerts(long wire, ByteBuffer bytes, int len, boolean asRequest, long[] out5);
+    /** apply the cells of the last decode to a detector without leaving the device (rapid_wire_cells_dev + rapid_cd_apply_batch_dev) */
+    public static native int wireApplyToDetector(long wire, long cd, long cfgId, long nCells);
 }

@@ -377,3 +377,31 @@ JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_pxPhase2bFromAcceptors(JNIE
     (*env)->SetLongArrayRegion(env, out5, 0, 5, v);
     return rc;
 }
+
+/* ---------------------------------------------------------------- wire-format ingest (rapid.proto) */
+JNIEXPORT jlong JNICALL Java_com_vrg_rapid_gpu_Native_wireCreate(JNIEnv* env, jclass c, jlong view) {
+    rapid_wire* w = NULL;
+    const int32_t rc = rapid_wire_create(&w, H(rapid_view, view));
+    return rc == RAPID_OK ? (jlong)(intptr_t)w : 0;
+}
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_wireDestroy(JNIEnv* env, jclass c, jlong w) { return rapid_wire_destroy(H(rapid_wire, w)); }
+
+/* what the gRPC server hands to MembershipService.handleMessage (MembershipService.java:174), still serialized */
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_wireDecodeAlerts(JNIEnv* env, jclass c, jlong w, jobject bytes, jint len,
+                                                                      jboolean asRequest, jlongArray out5) {
+    int64_t nm = 0, nc = 0, nd = 0, nj = 0;
+    int32_t sender = -1;
+    const int32_t rc = rapid_wire_decode_alerts(H(rapid_wire, w), (const uint8_t*)BUF(env, bytes), len, asRequest ? RAPID_WIRE_REQUEST : 0,
+                                                &nm, &nc, &nd, &nj, &sender);
+    const jlong v[5] = {(jlong)nm, (jlong)nc, (jlong)nd, (jlong)nj, sender};
+    (*env)->SetLongArrayRegion(env, out5, 0, 5, v);
+    return rc;
+}
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_wireApplyToDetector(JNIEnv* env, jclass c, jlong w, jlong cd, jlong cfg, jlong nCells) {
+    const int32_t *src, *dst;
+    const uint8_t *ring, *status;
+    const int64_t* cell_cfg;
+    int32_t rc = rapid_wire_cells_dev(H(rapid_wire, w), &src, &dst, &ring, &status, &cell_cfg);
+    if (rc != RAPID_OK) return rc;
+    return rapid_cd_apply_batch_dev(H(rapid_cd, cd), cfg, nCells, src, dst, ring, status, cell_cfg, NULL);
+}
