@@ -56,6 +56,7 @@ typedef struct rapid_comm rapid_comm;   /* NCCL communicator for the sharded (mu
 typedef struct rapid_px   rapid_px;     /* classic-Paxos tallies of one node (coordinator + learner)   */
 typedef struct rapid_pxa  rapid_pxa;    /* classic-Paxos acceptor state of R virtual nodes in HBM      */
 typedef struct rapid_wire rapid_wire;   /* protobuf wire-format decoder bound to a view's dictionary    */
+typedef struct rapid_fdet rapid_fdet;   /* the K edge failure detectors of every virtual node            */
 
 const char* rapid_version(void);
 int32_t rapid_last_error(char* buf, size_t cap);
@@ -332,6 +333,39 @@ int32_t rapid_wire_decode_votes(rapid_wire* w, const uint8_t* bytes, const int64
                                 int32_t* sender, int64_t* vote_cfg, uint64_t* proposal_hash, uint64_t* proposal_hash2,
                                 int32_t* proposal_len);
 int32_t rapid_wire_last_device_ms(const rapid_wire* w, float* total_ms);
+
+/* ------------------------------------------------------------------------------------------------
+ * Alert generation  (SURVEY.md §8 f4): PingPongFailureDetector.java:38-121 — one detector per entry of
+ * getSubjectsOf(node), i.e. K per member (MembershipService.java:697-707) — and the AlertMessage a notifier
+ * raises (edgeFailureNotification, MembershipService.java:472-495: DOWN, every ring number of the edge).
+ * The network is a scenario: per-node flags and optional per-detector probe failures.
+ * ---------------------------------------------------------------------------------------------- */
+#define RAPID_FD_CRASHED         1u   /* answers no probe and runs no detector                               */
+#define RAPID_FD_INGRESS_BLOCKED 2u   /* probes TO the node fail                                             */
+#define RAPID_FD_EGRESS_BLOCKED  4u   /* probes FROM the node fail                                           */
+#define RAPID_FD_BOOTSTRAPPING   8u   /* answers NodeStatus.BOOTSTRAPPING (tolerated bootstrap_threshold times, :45, :97-104) */
+/* failure_threshold = FAILURE_THRESHOLD (10, :41), bootstrap_threshold = BOOTSTRAP_COUNT_THRESHOLD (30, :45). */
+int32_t rapid_fdet_create(rapid_fdet** out, const rapid_view* v, int32_t failure_threshold, int32_t bootstrap_threshold);
+int32_t rapid_fdet_destroy(rapid_fdet* fd);
+/* New configuration: cancelFailureDetectorJobs + createFailureDetectorsForCurrentConfiguration (MembershipService.java:433-434). */
+int32_t rapid_fdet_reset(rapid_fdet* fd);
+/* One failure-detector interval of every live node: run() (:75-85) of its K detectors in ring order — notify if
+ * failureCount >= threshold and not yet notified, else probe and count a failure (:120-123).  node_flags[n]: RAPID_FD_* of
+ * every member; edge_fail[n * K] (may be NULL): non-zero = the probe of that node's k-th detector fails regardless.
+ * The notifications of this interval become AlertMessages{edgeSrc = node, edgeDst = subject, DOWN, cfg_id, all ring numbers
+ * of the edge} and their cells, ordered by node id, then detector, then ring number; they stay on the device. */
+int32_t rapid_fdet_tick(rapid_fdet* fd, const uint8_t* node_flags, const uint8_t* edge_fail, int64_t cfg_id, int64_t* n_alerts,
+                        int64_t* n_cells);
+int32_t rapid_fdet_tick_dev(rapid_fdet* fd, const uint8_t* node_flags_dev, const uint8_t* edge_fail_dev, int64_t cfg_id,
+                            int64_t* n_alerts, int64_t* n_cells);
+/* Cells of the last tick on the device (for rapid_cd_apply_batch_dev) / on the host; alerts as (observer, subject, ring bitmask). */
+int32_t rapid_fdet_cells_dev(const rapid_fdet* fd, const int32_t** src, const int32_t** dst, const uint8_t** ring,
+                             const uint8_t** status, const int64_t** cfg);
+int32_t rapid_fdet_read_cells(const rapid_fdet* fd, int32_t* src, int32_t* dst, uint8_t* ring, uint8_t* status, int64_t* cfg);
+int32_t rapid_fdet_read_alerts(const rapid_fdet* fd, int32_t* observer, int32_t* subject, uint16_t* ring_mask);
+/* failureCount / notified of node's k-th detector */
+int32_t rapid_fdet_state(const rapid_fdet* fd, int64_t node, int32_t k, int32_t* failure_count, int32_t* notified);
+int32_t rapid_fdet_last_device_ms(const rapid_fdet* fd, float* total_ms);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU; receivers sharded by ring-0 range; one all-reduce on the histogram)

@@ -17,6 +17,7 @@
 
 #include "rapid_oracle.hpp"
 #include "paxos_oracle.hpp"
+#include "fd_oracle.hpp"
 
 using namespace oracle;
 
@@ -525,6 +526,71 @@ int32_t orc_px_coordinator_rule(orc_px* p, int32_t n, const int32_t* vrnd, const
         return -1;
     }
 }
+
+/* ---------------- alert generation: one FdNode (K PingPongFailureDetectors) per member ----------------
+ * node_flags[tag]: bit0 crashed (answers no probe, runs no detector), bit1 ingress blocked (probes TO it fail),
+ * bit2 egress blocked (probes FROM it fail), bit3 bootstrapping (answers BOOTSTRAPPING).
+ * edge_fail[tag * K + k] != 0: the probe of `tag`'s k-th detector fails regardless. */
+struct orc_fdsim {
+    orc_view* view;
+    int K;
+    std::vector<int32_t> members;                 // tags, in the order the nodes are ticked
+    std::vector<std::unique_ptr<FdNode>> nodes;
+};
+orc_fdsim* orc_fdsim_create(orc_view* v, int32_t K, const int32_t* member_tags, int64_t n) {
+    orc_fdsim* s = new orc_fdsim();
+    s->view = v; s->K = K;
+    for (int64_t i = 0; i < n; ++i) {
+        s->members.push_back(member_tags[i]);
+        s->nodes.emplace_back(new FdNode(v->v.get(), v->u->eps[(size_t)member_tags[i]]));
+    }
+    return s;
+}
+void orc_fdsim_destroy(orc_fdsim* s) { delete s; }
+/* one interval for every live node, nodes in member order.  Outputs (capacity cap alerts / cap_rings ring numbers):
+ * observer tag, subject tag, ring_off[n_alerts + 1], rings.  Returns the number of alerts (may exceed cap: truncated). */
+int64_t orc_fdsim_tick(orc_fdsim* s, const uint8_t* node_flags, const uint8_t* edge_fail, int64_t cfg, int32_t* observer,
+                       int32_t* subject, int32_t* ring_off, int32_t* rings, int64_t cap, int64_t cap_rings) {
+    std::vector<AlertMessage> out;
+    for (size_t i = 0; i < s->nodes.size(); ++i) {
+        const int32_t me = s->members[i];
+        if (node_flags[me] & 1) continue;                                   // a crashed process runs nothing
+        size_t k = 0;
+        // the callback sees the detectors in creation order: k counts the probes of this tick
+        const std::vector<PingPongFailureDetector>& fds = s->nodes[i]->detectors();
+        std::vector<int> probing;                                           // detector indexes that will probe this tick
+        for (size_t j = 0; j < fds.size(); ++j)
+            if (!(fds[j].failureCount() >= PingPongFailureDetector::FAILURE_THRESHOLD && !fds[j].notified())) probing.push_back((int)j);
+        s->nodes[i]->tick(
+            [&](const Endpoint&, const Endpoint& subj) -> ProbeOutcome {
+                const int j = probing[k++];
+                const int32_t st = s->view->u->tagOf(subj);
+                if (edge_fail && edge_fail[(size_t)me * (size_t)s->K + (size_t)j]) return PROBE_FAILED;
+                if ((node_flags[me] & 4) || (node_flags[st] & 3)) return PROBE_FAILED;
+                if (node_flags[st] & 8) return PROBE_BOOTSTRAPPING;
+                return PROBE_OK;
+            },
+            cfg, &out);
+    }
+    int64_t n = 0, nr = 0;
+    if (ring_off && cap > 0) ring_off[0] = 0;
+    for (const AlertMessage& m : out) {
+        if (n < cap) {
+            observer[n] = s->view->u->tagOf(m.edgeSrc);
+            subject[n] = s->view->u->tagOf(m.edgeDst);
+            for (int32_t r : m.ringNumber) { if (nr < cap_rings) rings[nr] = r; ++nr; }
+            ring_off[n + 1] = (int32_t)nr;
+        }
+        ++n;
+    }
+    return n;
+}
+/* state of node i's k-th detector: out[0] = failureCount, out[1] = notified */
+void orc_fdsim_state(orc_fdsim* s, int64_t i, int32_t k, int32_t* out) {
+    const PingPongFailureDetector& fd = s->nodes[(size_t)i]->detectors()[(size_t)k];
+    out[0] = fd.failureCount(); out[1] = fd.notified() ? 1 : 0;
+}
+int32_t orc_fdsim_num_detectors(orc_fdsim* s, int64_t i) { return (int32_t)s->nodes[(size_t)i]->detectors().size(); }
 
 int32_t orc_hardware_threads(void) { return (int32_t)std::thread::hardware_concurrency(); }
 

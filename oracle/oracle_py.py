@@ -113,6 +113,11 @@ def lib():
         "orc_px_cval": (i32, [vp, p, i32]),
         "orc_px_ranks": (None, [vp, p]),
         "orc_px_coordinator_rule": (i32, [vp, i32, p, p, p, p, i32]),
+        "orc_fdsim_create": (vp, [vp, i32, p, i64]),
+        "orc_fdsim_destroy": (None, [vp]),
+        "orc_fdsim_tick": (i64, [vp, p, p, i64, p, p, p, p, i64, i64]),
+        "orc_fdsim_state": (None, [vp, i64, i32, p]),
+        "orc_fdsim_num_detectors": (i32, [vp, i64]),
         "orc_hardware_threads": (i32, []),
     }
     for name, (res, args) in sig.items():
@@ -462,6 +467,42 @@ class ClassicPaxos:
         lib().orc_px_ranks(self.h, _ptr(o))
         o = o.tolist()
         return {"rnd": (o[0], o[1]), "vrnd": (o[2], o[3]), "crnd": (o[4], o[5])}
+
+
+FD_CRASHED, FD_INGRESS_BLOCKED, FD_EGRESS_BLOCKED, FD_BOOTSTRAPPING = 1, 2, 4, 8
+
+
+class FdSim:
+    """Alert generation restated (oracle/fd_oracle.hpp): one FdNode — K PingPongFailureDetectors, in getSubjectsOf order —
+    per member; tick() = one failure-detector interval of every live node, in member order."""
+
+    def __init__(self, view: MembershipView, K, member_tags):
+        self.view, self.K = view, K
+        self.members = _i32(member_tags)
+        self.h = lib().orc_fdsim_create(view.h, K, _ptr(self.members), len(self.members))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_fdsim_destroy(self.h)
+            self.h = None
+
+    def tick(self, node_flags, cfg, edge_fail=None):
+        """-> list of (observer tag, subject tag, [ring numbers]) in the order the notifiers fired"""
+        nf = np.ascontiguousarray(node_flags, np.uint8)
+        ef = None if edge_fail is None else np.ascontiguousarray(edge_fail, np.uint8)
+        cap = len(self.members) * self.K + 1
+        obs, sub = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        off, rings = np.zeros(cap + 1, np.int32), np.zeros(cap * self.K, np.int32)
+        n = lib().orc_fdsim_tick(self.h, _ptr(nf), _ptr(ef), cfg, _ptr(obs), _ptr(sub), _ptr(off), _ptr(rings), cap, cap * self.K)
+        return [(int(obs[i]), int(sub[i]), rings[off[i]: off[i + 1]].tolist()) for i in range(n)]
+
+    def state(self, i, k):
+        out = np.zeros(2, np.int32)
+        lib().orc_fdsim_state(self.h, i, k, _ptr(out))
+        return int(out[0]), bool(out[1])
+
+    def numDetectors(self, i):
+        return lib().orc_fdsim_num_detectors(self.h, i)
 
 
 class ClusterSim:

@@ -11,7 +11,8 @@ from .cut_detector import MultiNodeCutDetector, VirtualCluster, proposal_fingerp
 from .fast_paxos import FastPaxos, NcclComm, quorum
 from .classic_paxos import Paxos, PaxosAcceptors
 from .wire import WireDecoder
+from .failure_detector import EdgeFailureDetectors
 
-__all__ = ["MembershipView", "MultiNodeCutDetector", "VirtualCluster", "FastPaxos", "NcclComm", "quorum", "Paxos", "PaxosAcceptors", "WireDecoder",
+__all__ = ["MembershipView", "MultiNodeCutDetector", "VirtualCluster", "FastPaxos", "NcclComm", "quorum", "Paxos", "PaxosAcceptors", "WireDecoder", "EdgeFailureDetectors",
            "proposal_fingerprint", "UP", "DOWN", "RapidError", "NodeNotInRingException",
            "NodeAlreadyInRingException", "UUIDAlreadySeenException", "HashCollisionError"]

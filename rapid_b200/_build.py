@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librapid_b200.so")
-SOURCES = ["api.cu", "view.cu", "cd_core.cu", "cd_prepare.cu", "cd_bucketed.cu", "fast_paxos.cu", "classic_paxos.cu", "wire.cu"]
+SOURCES = ["api.cu", "view.cu", "cd_core.cu", "cd_prepare.cu", "cd_bucketed.cu", "fast_paxos.cu", "classic_paxos.cu", "wire.cu", "fd.cu"]
 HEADERS = ["common.cuh", "cd_internal.cuh", "scan.cuh", os.path.join("..", "..", "include", "rapid_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

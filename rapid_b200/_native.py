@@ -110,6 +110,16 @@ SIGNATURES = {
     "rapid_wire_read_messages": [_vp, _p, _p, _p, _p, _p, _p, _p, _p],
     "rapid_wire_decode_votes": [_vp, _p, _p, _i64, _u32, _p, _p, _p, _p, _p],
     "rapid_wire_last_device_ms": [_vp, _p],
+    "rapid_fdet_create": [_pp, _vp, _i32, _i32],
+    "rapid_fdet_destroy": [_vp],
+    "rapid_fdet_reset": [_vp],
+    "rapid_fdet_tick": [_vp, _p, _p, _i64, _p, _p],
+    "rapid_fdet_tick_dev": [_vp, _p, _p, _i64, _p, _p],
+    "rapid_fdet_cells_dev": [_vp, _p, _p, _p, _p, _p],
+    "rapid_fdet_read_cells": [_vp, _p, _p, _p, _p, _p],
+    "rapid_fdet_read_alerts": [_vp, _p, _p, _p],
+    "rapid_fdet_state": [_vp, _i64, _i32, _p, _p],
+    "rapid_fdet_last_device_ms": [_vp, _p],
     "rapid_px_start_phase1a": [_vp, _i32, _i32, _p],
     "rapid_px_coordinator_rule": [_vp, _i64, _p, _p, _p, _p, _p, _p],
     "rapid_px_phase1b": [_vp, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
