@@ -32,12 +32,17 @@ struct PxScal {
     int32_t len, src;                            // src: batch index of the trigger message
 };
 
+// One open-addressing entry = one 32-byte sector: a probe, its key compare and its value update touch a single line.
+struct __align__(32) PxEntry {
+    int32_t state;       // 0 empty, 1 being published, 2 ready
+    int32_t c;
+    uint64_t a, b;
+    int32_t val;         // pairs: earliest arrival of a new pair (INT_MAX fresh, -1 sealed); round counters: distinct senders so far
+    int32_t pad_;
+};
 struct PxTable {
     uint32_t T;
-    int32_t* state;      // 0 empty, 1 being published, 2 ready
-    uint64_t* a;
-    uint64_t* b;
-    int32_t* c;
+    PxEntry* e;
 };
 
 __device__ __forceinline__ uint32_t px_hash(uint64_t a, uint64_t b, int32_t c) {
@@ -49,18 +54,18 @@ __device__ int32_t px_find_or_insert(const PxTable t, uint64_t a, uint64_t b, in
     uint32_t pos = px_hash(a, b, c) & (t.T - 1);
     *is_new = false;
     for (uint32_t probes = 0; probes < t.T; ++probes) {
-        int32_t state = *(volatile int32_t*)&t.state[pos];
-        if (state == 0) state = atomicCAS(&t.state[pos], 0, 1);
+        int32_t state = *(volatile int32_t*)&t.e[pos].state;
+        if (state == 0) state = atomicCAS(&t.e[pos].state, 0, 1);
         if (state == 0) {
-            t.a[pos] = a; t.b[pos] = b; t.c[pos] = c;
+            t.e[pos].a = a; t.e[pos].b = b; t.e[pos].c = c;
             __threadfence();
-            atomicExch(&t.state[pos], 2);
+            atomicExch(&t.e[pos].state, 2);
             *is_new = true;
             return (int32_t)pos;
         }
-        while (state == 1) state = atomicAdd(&t.state[pos], 0);
+        while (state == 1) state = atomicAdd(&t.e[pos].state, 0);
         __threadfence();
-        if (t.a[pos] == a && t.b[pos] == b && t.c[pos] == c) return (int32_t)pos;
+        if (t.e[pos].a == a && t.e[pos].b == b && t.e[pos].c == c) return (int32_t)pos;
         pos = (pos + 1) & (t.T - 1);
     }
     return -1;
@@ -143,7 +148,7 @@ __global__ void k_px_rule_collect(int64_t m, const int64_t* __restrict__ vr, con
 // (need - 1 - prior[key]) of its run; the earliest such arrival index wins.  prior == NULL means 0 everywhere; if
 // prior is given it is advanced by the run length (the per-round sender counts of the learner).
 __global__ void k_px_kth(int64_t m, const uint32_t* __restrict__ skey, const int32_t* __restrict__ sval, uint32_t T,
-                         int32_t* __restrict__ prior, int32_t need, int32_t* __restrict__ out_min) {
+                         const PxEntry* __restrict__ prior, int32_t need, int32_t* __restrict__ out_min) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= m) return;
     const uint32_t k = skey[p];
@@ -151,10 +156,10 @@ __global__ void k_px_kth(int64_t m, const uint32_t* __restrict__ skey, const int
     int64_t lo = 0, hi = p;                                  // first position of k's run (keys are sorted)
     while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (skey[mid] < k) lo = mid + 1; else hi = mid; }
     const int64_t off = p - lo;
-    const int32_t before = prior ? prior[k] : 0;             // read-only here; k_px_kth_advance updates it afterwards
+    const int32_t before = prior ? prior[k].val : 0;             // read-only here; k_px_kth_advance updates it afterwards
     if (before < need && off == (int64_t)(need - 1 - before)) atomicMin(out_min, sval[p]);
 }
-__global__ void k_px_kth_advance(int64_t m, const uint32_t* __restrict__ skey, uint32_t T, int32_t* __restrict__ prior) {
+__global__ void k_px_kth_advance(int64_t m, const uint32_t* __restrict__ skey, uint32_t T, PxEntry* __restrict__ prior) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= m) return;
     const uint32_t k = skey[p];
@@ -162,7 +167,7 @@ __global__ void k_px_kth_advance(int64_t m, const uint32_t* __restrict__ skey, u
     if (p + 1 < m && skey[p + 1] == k) return;               // only the last element of a run
     int64_t lo = 0, hi = p;
     while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (skey[mid] < k) lo = mid + 1; else hi = mid; }
-    prior[k] += (int32_t)(p - lo + 1);
+    prior[k].val += (int32_t)(p - lo + 1);
 }
 
 // :287-326 — put the three cases together
@@ -181,9 +186,12 @@ __global__ void k_px_pack(int64_t n, const int32_t* __restrict__ round, const in
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = pack_rank(round[i], node[i]);
 }
-__global__ void k_px_fill64(int64_t n, uint64_t* p, uint64_t v) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
+__global__ void k_px_table_clear(uint32_t T, PxEntry* __restrict__ e) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    PxEntry z;
+    z.state = 0; z.c = 0; z.a = 0; z.b = 0; z.val = INT_MAX; z.pad_ = 0;
+    e[i] = z;
 }
 
 // phase1b filter (:160-167): keep[i] = cfg matches and rnd == crnd.   rnd == NULL: every message carries rnd_const.
@@ -223,7 +231,7 @@ __global__ void k_px2b_begin(PxScal* sc) { sc->decide_idx = INT_MAX; sc->overflo
 
 // acceptResponses[rnd].put(sender, msg) (:228-230): slot of the (rnd, sender) pair; earliest arrival of a NEW pair wins it
 __global__ void k_px2b_pairs(int64_t n, const int64_t* __restrict__ mcfg, int64_t cfg, const int64_t* __restrict__ rnd,
-                             int64_t rnd_const, const int32_t* __restrict__ sender, PxTable t, int32_t* __restrict__ t_val,
+                             int64_t rnd_const, const int32_t* __restrict__ sender, PxTable t,
                              int32_t* __restrict__ slot, PxScal* __restrict__ sc) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -234,18 +242,18 @@ __global__ void k_px2b_pairs(int64_t n, const int64_t* __restrict__ mcfg, int64_
         if (e < 0) atomicExch(&sc->overflow, 1);
         else {
             if (nw) atomicAdd(&sc->inserted, 1);
-            atomicMin(&t_val[e], (int32_t)i);            // INT_MAX on a fresh entry, -1 once a pair is from an earlier call
+            atomicMin(&t.e[e].val, (int32_t)i);            // INT_MAX on a fresh entry, -1 once a pair is from an earlier call
         }
     }
     slot[i] = e;
 }
 // key[i] = slot of the round's counter if message i is the first of its (rnd, sender) pair, T otherwise
 __global__ void k_px2b_rounds(int64_t n, const int64_t* __restrict__ rnd, int64_t rnd_const, const int32_t* __restrict__ slot,
-                              PxTable t, const int32_t* __restrict__ t_val, uint32_t* __restrict__ key, int32_t* __restrict__ idx,
+                              PxTable t, uint32_t* __restrict__ key, int32_t* __restrict__ idx,
                               PxScal* __restrict__ sc) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int32_t e = i < n ? slot[i] : -1;
-    const bool first = e >= 0 && t_val[e] == (int32_t)i;
+    const bool first = e >= 0 && t.e[e].val == (int32_t)i;
     bool nw;
     const int32_t r = px_find_or_insert_warp(t, first, first ? (uint64_t)(rnd ? rnd[i] : rnd_const) : 0, 0, 1, &nw);   // c = 1: a round counter
     if (i >= n) return;
@@ -258,11 +266,11 @@ __global__ void k_px2b_rounds(int64_t n, const int64_t* __restrict__ rnd, int64_
     key[i] = k;
 }
 // the pairs of this call are "seen" from now on
-__global__ void k_px2b_seal(int64_t n, const int32_t* __restrict__ slot, int32_t* __restrict__ t_val) {
+__global__ void k_px2b_seal(int64_t n, const int32_t* __restrict__ slot, PxEntry* __restrict__ ent) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int32_t e = slot[i];
-    if (e >= 0 && t_val[e] == (int32_t)i) t_val[e] = -1;
+    if (e >= 0 && ent[e].val == (int32_t)i) ent[e].val = -1;
 }
 __global__ void k_px2b_final(const uint64_t* __restrict__ h1, const uint64_t* __restrict__ h2, const int32_t* __restrict__ len,
                              uint64_t h1c, uint64_t h2c, int32_t lenc, PxScal* __restrict__ sc) {
@@ -271,14 +279,14 @@ __global__ void k_px2b_final(const uint64_t* __restrict__ h1, const uint64_t* __
         sc->h1 = h1 ? h1[d] : h1c; sc->h2 = h1 ? (h2 ? h2[d] : 0) : h2c; sc->len = h1 ? len[d] : lenc;
     }
 }
-// a round counter slot's prior count lives in t_val too (c == 1 entries); fresh entries hold INT_MAX -> 0
-__global__ void k_px2b_fix_counters(int64_t m, const uint32_t* __restrict__ skey, uint32_t T, int32_t* __restrict__ t_val) {
+// a round counter's prior count lives in the entry's val too (c == 1 entries); fresh entries hold INT_MAX -> 0
+__global__ void k_px2b_fix_counters(int64_t m, const uint32_t* __restrict__ skey, uint32_t T, PxEntry* __restrict__ ent) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= m) return;
     const uint32_t k = skey[p];
     if (k >= T) return;
     if (p > 0 && skey[p - 1] == k) return;                   // first element of a run
-    if (t_val[k] == INT_MAX) t_val[k] = 0;
+    if (ent[k].val == INT_MAX) ent[k].val = 0;
 }
 
 // ------------------------------------------------------------------ acceptor kernels
@@ -367,12 +375,10 @@ struct PX {
     int32_t dec_len = 0;
     int64_t pairs = 0;                     // entries used in the persistent table
     uint32_t T = 0;                        // persistent (rnd, sender) / round-counter table
-    DevBuf<int32_t> t_state, t_c, t_val;
-    DevBuf<uint64_t> t_a, t_b;
+    DevBuf<PxEntry> tbl;
     // scratch
     uint32_t RT = 0;                       // rule table (cleared per evaluation)
-    DevBuf<int32_t> r_state, r_c;
-    DevBuf<uint64_t> r_a, r_b;
+    DevBuf<PxEntry> rtbl;
     DevBuf<uint32_t> key, skey;
     DevBuf<int32_t> idx, sidx, keep, pos, app_src, slot;
     DevBuf<uint8_t> cub_tmp;
@@ -437,14 +443,13 @@ static int32_t px_rule_device(PX* px, int64_t m, const int64_t* vr, const uint64
     uint32_t RT = 1024;
     while ((int64_t)RT < 2 * m) RT <<= 1;
     if (RT > px->RT) {
-        RAPID_CHECK(px->r_state.reserve(RT)); RAPID_CHECK(px->r_c.reserve(RT));
-        RAPID_CHECK(px->r_a.reserve(RT)); RAPID_CHECK(px->r_b.reserve(RT));
+        RAPID_CHECK(px->rtbl.reserve(RT));
         px->RT = RT;
     }
     RT = px->RT;
     RAPID_CHECK(px_scratch(px, m));
-    RAPID_CUDA(cudaMemsetAsync(px->r_state.p, 0, (size_t)RT * sizeof(int32_t), s));
-    PxTable t{RT, px->r_state.p, px->r_a.p, px->r_b.p, px->r_c.p};
+    k_px_table_clear<<<grid_for(RT), TB, 0, s>>>(RT, px->rtbl.p);
+    PxTable t{RT, px->rtbl.p};
     k_px_rule_begin<<<1, 1, 0, s>>>(px->sc.p);
     k_px_rule_max<<<grid_for(m), TB, 0, s>>>(m, vr, len, px->sc.p);
     k_px_rule_collect<<<grid_for(m), TB, 0, s>>>(m, vr, h1, h2, len, t, px->key.p, px->idx.p, px->sc.p);
@@ -522,16 +527,16 @@ static int32_t px_phase2b_device(PX* px, int64_t n, const int64_t* mcfg, const i
         // worst case this call adds n new (rnd, sender) pairs and n new rounds: refuse before the table degrades
         if (px->pairs + 2 * n > (int64_t)px->T / 4 * 3) { set_error("Phase2b table would exceed message_capacity (%lld)", (long long)px->cap); return RAPID_ENOMEM; }
         RAPID_CHECK(px_scratch(px, n));
-        PxTable t{px->T, px->t_state.p, px->t_a.p, px->t_b.p, px->t_c.p};
+        PxTable t{px->T, px->tbl.p};
         k_px2b_begin<<<1, 1, 0, s>>>(px->sc.p);
-        k_px2b_pairs<<<grid_for(n), TB, 0, s>>>(n, mcfg, px->cfg, rnd, rnd_const, sender, t, px->t_val.p, px->slot.p, px->sc.p);
-        k_px2b_rounds<<<grid_for(n), TB, 0, s>>>(n, rnd, rnd_const, px->slot.p, t, px->t_val.p, px->key.p, px->idx.p, px->sc.p);
+        k_px2b_pairs<<<grid_for(n), TB, 0, s>>>(n, mcfg, px->cfg, rnd, rnd_const, sender, t, px->slot.p, px->sc.p);
+        k_px2b_rounds<<<grid_for(n), TB, 0, s>>>(n, rnd, rnd_const, px->slot.p, t, px->key.p, px->idx.p, px->sc.p);
         RAPID_KERNEL_CHECK();
         RAPID_CHECK(px_sort_pairs(px, n, bits_for(px->T)));
-        k_px2b_fix_counters<<<grid_for(n), TB, 0, s>>>(n, px->skey.p, px->T, px->t_val.p);
-        k_px_kth<<<grid_for(n), TB, 0, s>>>(n, px->skey.p, px->sidx.p, px->T, px->t_val.p, (int32_t)(px->N / 2) + 1, &px->sc.p->decide_idx);
-        k_px_kth_advance<<<grid_for(n), TB, 0, s>>>(n, px->skey.p, px->T, px->t_val.p);
-        k_px2b_seal<<<grid_for(n), TB, 0, s>>>(n, px->slot.p, px->t_val.p);
+        k_px2b_fix_counters<<<grid_for(n), TB, 0, s>>>(n, px->skey.p, px->T, px->tbl.p);
+        k_px_kth<<<grid_for(n), TB, 0, s>>>(n, px->skey.p, px->sidx.p, px->T, px->tbl.p, (int32_t)(px->N / 2) + 1, &px->sc.p->decide_idx);
+        k_px_kth_advance<<<grid_for(n), TB, 0, s>>>(n, px->skey.p, px->T, px->tbl.p);
+        k_px2b_seal<<<grid_for(n), TB, 0, s>>>(n, px->slot.p, px->tbl.p);
         k_px2b_final<<<1, 1, 0, s>>>(h1, h2, len, h1c, h2c, lenc, px->sc.p);
         RAPID_KERNEL_CHECK();
         RAPID_CHECK(px_read_scal(px));
@@ -586,9 +591,7 @@ static int32_t px_arrival_order(PX* px, const PXA* a, uint64_t perm_seed, const 
 }
 
 static int32_t px_clear_tables(PX* px) {
-    RAPID_CUDA(cudaMemsetAsync(px->t_state.p, 0, (size_t)px->T * sizeof(int32_t), px->stream));
-    const int64_t words = (int64_t)px->T / 2;                 // t_val = INT_MAX everywhere
-    k_px_fill64<<<grid_for(words), TB, 0, px->stream>>>(words, (uint64_t*)px->t_val.p, ((uint64_t)(uint32_t)INT_MAX << 32) | (uint32_t)INT_MAX);
+    k_px_table_clear<<<grid_for(px->T), TB, 0, px->stream>>>(px->T, px->tbl.p);
     RAPID_KERNEL_CHECK();
     return RAPID_OK;
 }
@@ -618,8 +621,7 @@ int32_t rapid_px_create(rapid_px** out, int64_t cfg_id, int64_t membership_size,
             cudaEventCreate(&px->ev1) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "stream", __FILE__, __LINE__); break; }
         const size_t cap = (size_t)message_capacity;
         if ((rc = px->L_vr.reserve(cap)) || (rc = px->L_h1.reserve(cap)) || (rc = px->L_h2.reserve(cap)) || (rc = px->L_len.reserve(cap))) break;
-        if ((rc = px->t_state.reserve(T)) || (rc = px->t_c.reserve(T)) || (rc = px->t_val.reserve(T)) || (rc = px->t_a.reserve(T)) ||
-            (rc = px->t_b.reserve(T))) break;
+        if ((rc = px->tbl.reserve(T))) break;
         if ((rc = px->sc.reserve(1)) || (rc = px->h_sc.reserve(1))) break;
         cudaMemsetAsync(px->sc.p, 0, sizeof(PxScal), px->stream);
         if ((rc = px_clear_tables(px))) break;
