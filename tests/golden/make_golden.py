@@ -77,8 +77,52 @@ def cut_scenarios():
         json.dump(cases, f)
 
 
+def paxos_rule_cases():
+    """selectProposalUsingCoordinatorRule (Paxos.java:271-328) on seeded message lists: values are small ints (0 = empty list),
+    the answer is the INDEX of the message whose vval is chosen (-1 = empty)."""
+    import random
+    rng = random.Random(20260922)
+    u = orc.Universe()
+    vals = {0: []}
+    for i in range(1, 6):
+        vals[i] = [u.add("v", 10 * i + j) for j in range(1 + i % 3)]
+    cases = []
+    for _ in range(40):
+        N = rng.choice([4, 5, 6, 9, 16, 33, 100])
+        m = rng.randint(1, 2 * N)
+        ranks = [(rng.randint(0, 2), rng.choice([-3, 0, 1, 7, 2**31 - 1])) for _ in range(rng.randint(1, 3))]
+        msgs = [{"vrnd": rng.choice(ranks), "value": rng.randint(0, rng.randint(1, 5))} for _ in range(m)]
+        px = orc.ClassicPaxos(u, u.add("me", 1), 7, 1, N)
+        chosen = px.selectProposalUsingCoordinatorRule([{"vrnd": x["vrnd"], "vval": vals[x["value"]]} for x in msgs])
+        # the rule returns a value; the fixtures pin the first message carrying it among those the rule could have taken it from
+        cases.append({"N": N, "vrnd": [list(x["vrnd"]) for x in msgs], "value": [x["value"] for x in msgs],
+                      "chosen_value": next((k for k, v in vals.items() if v == chosen), None)})
+    with open(os.path.join(HERE, "paxos_rule_cases.json"), "w") as f:
+        json.dump(cases, f)
+
+
+def failure_detector_stream():
+    """alerts of 14 failure-detector intervals (PingPongFailureDetector.java:75-85) of a 60-node view under a fixed scenario"""
+    n = 60
+    hb, off, ports = W.packed_endpoints(0, n)
+    u = orc.Universe()
+    tags = u.add_bulk(hb, off, ports)
+    hi, lo = W.node_ids(0, n)
+    v = orc.MembershipView(u, K, tags, hi, lo)
+    sim = orc.FdSim(v, K, np.arange(n))
+    flags = np.zeros(n, np.uint8)
+    flags[[4, 17]] = orc.FD_CRASHED
+    flags[30] = orc.FD_INGRESS_BLOCKED
+    flags[41] = orc.FD_EGRESS_BLOCKED
+    out = {"n": n, "K": K, "flags": flags.tolist(), "cfg": 99, "intervals": [sim.tick(flags, 99) for _ in range(14)]}
+    with open(os.path.join(HERE, "failure_detector_stream.json"), "w") as f:
+        json.dump(out, f)
+
+
 if __name__ == "__main__":
     orc.build()
     ring_keys()
     cut_scenarios()
+    paxos_rule_cases()
+    failure_detector_stream()
     print("wrote", os.listdir(HERE))

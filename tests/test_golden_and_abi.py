@@ -62,6 +62,31 @@ def test_oracle_matches_golden_cut_scenarios(orc):
         assert sorted(c["proposal_canonical"]) == c["expected_cut"]
 
 
+def test_oracle_matches_golden_paxos_rule_cases(orc):
+    u = orc.Universe()
+    vals = {0: []}
+    for i in range(1, 6):
+        vals[i] = [u.add("v", 10 * i + j) for j in range(1 + i % 3)]
+    for c in _golden("paxos_rule_cases.json"):
+        px = orc.ClassicPaxos(u, u.add("me", 1), 7, 1, c["N"])
+        msgs = [{"vrnd": tuple(r), "vval": vals[v]} for r, v in zip(c["vrnd"], c["value"])]
+        assert px.selectProposalUsingCoordinatorRule(msgs) == vals[c["chosen_value"]]
+
+
+def test_oracle_matches_golden_failure_detector_stream(orc):
+    g = _golden("failure_detector_stream.json")
+    n, K = g["n"], g["K"]
+    hb, off, ports = W.packed_endpoints(0, n)
+    u = orc.Universe()
+    tags = u.add_bulk(hb, off, ports)
+    hi, lo = W.node_ids(0, n)
+    sim = orc.FdSim(orc.MembershipView(u, K, tags, hi, lo), K, np.arange(n))
+    flags = np.asarray(g["flags"], np.uint8)
+    for want in g["intervals"]:
+        assert [[o, s, r] for o, s, r in sim.tick(flags, g["cfg"])] == want
+    assert sum(len(x) for x in g["intervals"]) > 0
+
+
 def test_library_exports_every_declared_symbol():
     from rapid_b200 import _native, _build
     hdr = open(os.path.join(ROOT, "include", "rapid_b200.h")).read()
