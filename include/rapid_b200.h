@@ -232,7 +232,8 @@ int32_t rapid_fp_quorum(int64_t membership_size, int64_t* out);   /* N - floor((
  * All arrays are host memory, one element per message, in ARRIVAL order.
  * ---------------------------------------------------------------------------------------------- */
 /* One node's tallies (Paxos ctor :76-90): the coordinator's Phase1b list and the learner's Phase2b sets, on the device.
- * message_capacity bounds the Phase1b messages kept plus the distinct (rnd, sender) Phase2b pairs. */
+ * message_capacity sizes the Phase1b list (it grows if exceeded) and bounds the distinct (rnd, sender) Phase2b pairs plus
+ * rounds (RAPID_ENOMEM beyond ~3x message_capacity entries). */
 int32_t rapid_px_create(rapid_px** out, int64_t cfg_id, int64_t membership_size, int64_t message_capacity, int32_t device);
 int32_t rapid_px_destroy(rapid_px* px);
 /* Start over for the next configuration (the new Paxos of FastPaxos.java:86 / MembershipService.java:427-429). */

@@ -475,7 +475,11 @@ static int32_t px_phase1b_device(PX* px, int64_t n, const int64_t* mcfg, const i
     if (proposed) *proposed = 0;
     if (trigger_index) *trigger_index = -1;
     if (n > 0) {
-        if (px->n_msgs + n > px->cap) { set_error("Phase1b list would exceed message_capacity (%lld)", (long long)px->cap); return RAPID_ENOMEM; }
+        {   // the list grows past message_capacity if it must (a batch may be mostly filtered; the bound is only known afterwards)
+            const size_t need = (size_t)(px->n_msgs + n);
+            RAPID_CHECK(px->L_vr.reserve(need, true, s)); RAPID_CHECK(px->L_h1.reserve(need, true, s));
+            RAPID_CHECK(px->L_h2.reserve(need, true, s)); RAPID_CHECK(px->L_len.reserve(need, true, s));
+        }
         RAPID_CHECK(px_scratch(px, n));
         k_px1b_begin<<<1, 1, 0, s>>>(px->sc.p);
         k_px1b_keep<<<grid_for(n), TB, 0, s>>>(n, mcfg, px->cfg, rnd, rnd_const, px->crnd, px->keep.p);

@@ -273,8 +273,9 @@ def test_acceptor_errors(rb):
         px.handlePhase2bFromAcceptors(acc)                     # Phase1b answers pending, not Phase2b
     small = rb.Paxos(CFG, 4, message_capacity=2)
     small.startPhase1a(2, 3)
-    with pytest.raises(rb.RapidError):
-        small.handlePhase1bFromAcceptors(acc)                  # 4 answers > message_capacity
+    assert small.handlePhase1bFromAcceptors(acc).n_messages == 4     # the Phase1b list grows past the initial capacity
+    with pytest.raises(rb.RapidError):                                # ... the Phase2b table does not: refused, not corrupted
+        small.handlePhase2bMessages([(2, 3)] * 500, list(range(500)), [1] * 500, [1] * 500)   # table of 1024 entries, load <= 3/4
 
 
 def test_conflicting_fast_round_falls_back_to_classic_round(orc, rb):
