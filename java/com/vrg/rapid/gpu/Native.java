@@ -83,4 +83,12 @@ public final class Native {
     public static native int wireDecodeAlerts(long wire, ByteBuffer bytes, int len, boolean asRequest, long[] out5);
     /** apply the cells of the last decode to a detector without leaving the device (rapid_wire_cells_dev + rapid_cd_apply_batch_dev) */
     public static native int wireApplyToDetector(long wire, long cd, long cfgId, long nCells);
+
+    // ---- alert generation: the K PingPongFailureDetectors of every virtual node ----
+    public static native long fdetCreate(long view, int failureThreshold, int bootstrapThreshold);
+    public static native int fdetDestroy(long fdet);
+    public static native int fdetReset(long fdet);
+    /** one failure-detector interval; out2 = {nAlerts, nCells}; the cells stay on the device */
+    public static native int fdetTick(long fdet, byte[] nodeFlags, byte[] edgeFail, long cfgId, long[] out2);
+    public static native int fdetApplyToDetector(long fdet, long cd, long cfgId, long nCells);
 }

@@ -405,3 +405,34 @@ JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_wireApplyToDetector(JNIEnv*
     if (rc != RAPID_OK) return rc;
     return rapid_cd_apply_batch_dev(H(rapid_cd, cd), cfg, nCells, src, dst, ring, status, cell_cfg, NULL);
 }
+
+/* ---------------------------------------------------------------- alert generation (PingPongFailureDetector.java) */
+JNIEXPORT jlong JNICALL Java_com_vrg_rapid_gpu_Native_fdetCreate(JNIEnv* env, jclass c, jlong view, jint thr, jint bootThr) {
+    rapid_fdet* fd = NULL;
+    const int32_t rc = rapid_fdet_create(&fd, H(rapid_view, view), thr, bootThr);
+    return rc == RAPID_OK ? (jlong)(intptr_t)fd : 0;
+}
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_fdetDestroy(JNIEnv* env, jclass c, jlong fd) { return rapid_fdet_destroy(H(rapid_fdet, fd)); }
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_fdetReset(JNIEnv* env, jclass c, jlong fd) { return rapid_fdet_reset(H(rapid_fdet, fd)); }
+
+/* what the msbg thread's scheduleAtFixedRate of every detector amounts to (MembershipService.java:697-707), for all virtual nodes */
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_fdetTick(JNIEnv* env, jclass c, jlong fd, jbyteArray nodeFlags, jbyteArray edgeFail,
+                                                              jlong cfg, jlongArray out2) {
+    jbyte* nf = (*env)->GetByteArrayElements(env, nodeFlags, NULL);
+    jbyte* ef = edgeFail ? (*env)->GetByteArrayElements(env, edgeFail, NULL) : NULL;
+    int64_t na = 0, nc = 0;
+    const int32_t rc = rapid_fdet_tick(H(rapid_fdet, fd), (const uint8_t*)nf, (const uint8_t*)ef, cfg, &na, &nc);
+    (*env)->ReleaseByteArrayElements(env, nodeFlags, nf, JNI_ABORT);
+    if (ef) (*env)->ReleaseByteArrayElements(env, edgeFail, ef, JNI_ABORT);
+    const jlong v[2] = {(jlong)na, (jlong)nc};
+    (*env)->SetLongArrayRegion(env, out2, 0, 2, v);
+    return rc;
+}
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_fdetApplyToDetector(JNIEnv* env, jclass c, jlong fd, jlong cd, jlong cfg, jlong nCells) {
+    const int32_t *src, *dst;
+    const uint8_t *ring, *status;
+    const int64_t* cell_cfg;
+    int32_t rc = rapid_fdet_cells_dev(H(rapid_fdet, fd), &src, &dst, &ring, &status, &cell_cfg);
+    if (rc != RAPID_OK) return rc;
+    return rapid_cd_apply_batch_dev(H(rapid_cd, cd), cfg, nCells, src, dst, ring, status, cell_cfg, NULL);
+}
