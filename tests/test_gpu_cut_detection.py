@@ -496,3 +496,32 @@ def test_fuzz_all_delivery_modes_combined(orc, rb, seed):
         compare_batch(rb, w, sim, cl, None, (src, dst, ring, status), **kw)
         if rng.random() < 0.15:
             cl.clear(); sim.reset()
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_fuzz_mid_scale_shards(orc, rb, seed):
+    """the same fuzz at a size where a shard spans several 1024-receiver row tiles and chunks: 2,500-4,000 nodes, a
+    receiver shard that starts mid-tile, several hundred cells per batch over a few dozen subjects, every delivery mode"""
+    rng = np.random.default_rng(9000 + seed)
+    n, nj = int(rng.integers(2500, 4000)), int(rng.integers(0, 20))
+    R = int(rng.integers(1100, n))
+    begin = int(rng.integers(0, n - R + 1))
+    w = OracleWorld(orc, n, K, n_joiners=nj)
+    v = rb.MembershipView.from_packed(K, *w.member_packed())
+    if nj:
+        v.registerJoiners(*w.joiner_endpoints())
+    sim = orc.ClusterSim(w.view, K, 9, 4, R, receiver_base=begin)
+    cl = rb.VirtualCluster(v, 9, 4, n_receivers=R, receiver_begin=begin, kernel="bucketed")
+    words = (R + 31) // 32
+    for t in range(4):
+        src, dst, ring, status = random_batch(rng, n + nj, K, int(rng.integers(5, 40)), int(rng.integers(100, 500)), n)
+        kw = {}
+        if t != 1:
+            kw["blocked"] = (rng.random(R) < 0.1).astype(np.uint8)
+        if t >= 2:
+            bm = rng.integers(0, 2**32, size=(len(dst), words), dtype=np.uint64).astype(np.uint32)
+            bm |= rng.integers(0, 2**32, size=(len(dst), words), dtype=np.uint64).astype(np.uint32)
+            kw["bitmap"] = bm
+        if t % 2 == 1:
+            kw["perm_seed"] = int(rng.integers(1, 2**62))
+        compare_batch(rb, w, sim, cl, None, (src, dst, ring, status), **kw)
