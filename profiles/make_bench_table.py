@@ -1,0 +1,33 @@
+"""profiles/r01_bench_results.md from the bench lines a gpurun call left in gpurun_out/bench_<G>gpu.json."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+rows = []
+for g in (1, 2, 4, 8):
+    p = os.path.join(ROOT, "gpurun_out", "bench_%dgpu.json" % g)
+    if os.path.exists(p):
+        with open(p) as f:
+            txt = f.read().strip().splitlines()
+        if txt:
+            rows.append(json.loads(txt[-1]))
+if not rows:
+    sys.exit("no bench lines")
+base = next((r for r in rows if r["n_gpus"] == 1), None)
+out = ["# Round 1 — measured on B200 (gpurun), BASELINE config 5: 1,000,000 virtual nodes, K=10 H=9 L=4, 1 % churn batch",
+       "# (%d alert cells, %d subjects); `python bench.py --gpus G --steps %d --warmup 3` (torchrun for G > 1)" % (
+           rows[0]["config"]["cells"], rows[0]["config"]["subjects"], rows[0]["steps"]),
+       "# value = cells / device time of (apply + tally), max over ranks; e2e = host arrays -> C ABI -> decision, wall clock", "",
+       "| GPUs | value (cells/s) | ms/step | e2e (cells/s) | dominant kernel ms | roofline frac (of measured %.0f GB/s) | SM MHz (median, reasons) | scaling eff. vs 1 GPU |" % rows[0]["roofline"]["peak"],
+       "|---|---|---|---|---|---|---|---|"]
+for r in rows:
+    eff = "%.2f" % (r["value"] / (base["value"] * r["n_gpus"])) if base else "-"
+    clk = r.get("clocks") or {}
+    out.append("| %d | %.2e | %.3f | %.2e | %.3f | %.3f | %s %s | %s |" % (
+        r["n_gpus"], r["value"], r["ms_per_step"], r["e2e"]["value"], r["roofline"]["kernel_ms"], r["roofline"]["frac"],
+        clk.get("sm_mhz"), clk.get("reasons"), eff))
+out += ["", "The driver's own scaling run at round end is authoritative; these are the lines this repository's last gpurun calls produced."]
+with open(os.path.join(ROOT, "profiles", "r01_bench_results.md"), "w") as f:
+    f.write("\n".join(out) + "\n")
+print("\n".join(out))
