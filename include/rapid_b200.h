@@ -156,6 +156,17 @@ int32_t rapid_cd_apply_batch(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, cons
                              const uint8_t* ring, const uint8_t* status, const int64_t* cell_cfg,
                              const rapid_delivery* delivery, uint64_t* proposal_hash, uint64_t* proposal_hash2,
                              int32_t* proposal_len, uint8_t* announced);
+/* A SEQUENCE of BatchedAlertMessages in one call — one per sender, as the reference's AlertBatcher produces them
+ * (MembershipService.java:613-637): batch b = cells [batch_off[b], batch_off[b+1]), batch_off[0] = 0, batch_off[n_batches] = n_cells.
+ * Every receiver runs handleMessage (:300-354) once per batch, in array order: filter, cells, invalidateFailingEdges, and the
+ * announcedProposal gating BETWEEN batches — a receiver that announces in batch b ignores batches b+1.. (:318-319).  Outputs as
+ * rapid_cd_apply_batch (the proposal is that of the announcing batch), plus announced_in[receiver] = index of the batch in
+ * which it announced during this call (-1: it did not).  RAPID_CD_SWEEP handles only (RAPID_EUNSUPPORTED otherwise);
+ * delivery may carry BLOCKED / BITMAP. */
+int32_t rapid_cd_apply_batches(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src, const int32_t* dst,
+                               const uint8_t* ring, const uint8_t* status, const int64_t* cell_cfg, int64_t n_batches,
+                               const int64_t* batch_off, const rapid_delivery* delivery, uint64_t* proposal_hash,
+                               uint64_t* proposal_hash2, int32_t* proposal_len, uint8_t* announced, int32_t* announced_in);
 /* Same, with the cell arrays (and delivery arrays) already resident in device memory and no per-receiver
  * readback: results stay on the device for rapid_fp_tally_cd / rapid_cd_read_outputs. */
 int32_t rapid_cd_apply_batch_dev(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src_dev,

@@ -47,6 +47,9 @@ struct SweepArgs {
     uint64_t* out_h2;
     int32_t* out_len;
     uint8_t* out_ann;
+    const int64_t* batch_off;    // NULL: the cells are ONE BatchedAlertMessage; else batch b = cells [batch_off[b], batch_off[b+1])
+    int32_t n_batches;
+    int32_t* out_batch;          // with batch_off: index of the batch in which the receiver announced during this call, -1 otherwise
 };
 
 __global__ void __launch_bounds__(128) k_sweep(const SweepArgs a) {
@@ -59,6 +62,7 @@ __global__ void __launch_bounds__(128) k_sweep(const SweepArgs a) {
         a.rflags[r] = flags;
         a.out_h1[r] = 0; a.out_h2[r] = 0; a.out_len[r] = 0;
         if (a.out_ann) a.out_ann[r] = (flags & RF_ANNOUNCED) ? 1 : 0;
+        if (a.out_batch) a.out_batch[r] = -1;
         return;
     }
     const uint32_t RM = (1u << a.K) - 1u;
@@ -98,33 +102,42 @@ __global__ void __launch_bounds__(128) k_sweep(const SweepArgs a) {
         }
     };
 
-    if (a.do_cells) {
-        const bool has_bitmap = a.dl.flags & RAPID_DELIVERY_BITMAP;
-        for (int64_t i = 0; i < a.A; ++i) {
-            const int32_t slot = a.cell_slot[i];
-            if (slot < 0) continue;
-            if (has_bitmap && !((a.dl.bitmap[(size_t)i * a.dl.words + (r >> 5)] >> (r & 31)) & 1u)) continue;
-            if (a.status[i] == RAPID_EDGE_DOWN) seen = true;   // :88-90 (before the duplicate check)
-            report(slot, a.ring[i]);
-        }
-    }
-    if (a.do_inval && seen && npre > 0) {                  // :137-164
-        for (int32_t s = 0; s < a.S; ++s) {
-            const uint32_t w0 = a.rows.row(s)[r];
-            const int c0 = __popc(w0 & RM);
-            if (c0 < a.L || c0 >= a.H) continue;           // not in the preProposal snapshot
-            const int32_t subject = a.slot_subject[s];
-            for (int k = 0; k < a.K; ++k) {
-                const int32_t o = a.obs[(size_t)subject * a.K + k];
-                if (o < 0) continue;
-                const int32_t so = a.slot_of[o];
-                if (so < 0) continue;
-                const uint32_t wo = a.rows.row(so)[r];
-                if ((wo & CD_BIT_EMIT) || __popc(wo & RM) < a.L) continue;   // observer not in proposal U preProposal
-                report(s, k);                               // implicit edge report
+    // MembershipService.handleMessage(BatchedAlertMessage) (:300-354) once per batch, in order: the batch's cells, then
+    // invalidateFailingEdges, then — if anything was emitted — announce and ignore every later batch (:318-319, :333-335)
+    const bool has_bitmap = a.dl.flags & RAPID_DELIVERY_BITMAP;
+    const int32_t nb = a.batch_off ? a.n_batches : 1;
+    int32_t ann_batch = -1;
+    for (int32_t b = 0; b < nb; ++b) {
+        const int64_t i0 = a.batch_off ? a.batch_off[b] : 0, i1 = a.batch_off ? a.batch_off[b + 1] : a.A;
+        if (a.do_cells) {
+            for (int64_t i = i0; i < i1; ++i) {
+                const int32_t slot = a.cell_slot[i];
+                if (slot < 0) continue;
+                if (has_bitmap && !((a.dl.bitmap[(size_t)i * a.dl.words + (r >> 5)] >> (r & 31)) & 1u)) continue;
+                if (a.status[i] == RAPID_EDGE_DOWN) seen = true;   // :88-90 (before the duplicate check)
+                report(slot, a.ring[i]);
             }
         }
+        if (a.do_inval && seen && npre > 0) {                  // :137-164
+            for (int32_t s = 0; s < a.S; ++s) {
+                const uint32_t w0 = a.rows.row(s)[r];
+                const int c0 = __popc(w0 & RM);
+                if (c0 < a.L || c0 >= a.H) continue;           // not in the preProposal snapshot
+                const int32_t subject = a.slot_subject[s];
+                for (int k = 0; k < a.K; ++k) {
+                    const int32_t o = a.obs[(size_t)subject * a.K + k];
+                    if (o < 0) continue;
+                    const int32_t so = a.slot_of[o];
+                    if (so < 0) continue;
+                    const uint32_t wo = a.rows.row(so)[r];
+                    if ((wo & CD_BIT_EMIT) || __popc(wo & RM) < a.L) continue;   // observer not in proposal U preProposal
+                    report(s, k);                               // implicit edge report
+                }
+            }
+        }
+        if (!a.raw && olen > 0) { ann_batch = b; break; }
     }
+    if (a.out_batch) a.out_batch[r] = ann_batch;
     if (seen) flags |= RF_SEEN_DOWN;
     if (!a.raw && olen > 0) flags |= RF_ANNOUNCED | RF_ANN_NOW;      // MembershipService.java:333-335
     a.rflags[r] = flags;
@@ -285,8 +298,10 @@ static int32_t preprocess(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev
 }
 
 static int32_t launch_sweep(CD* cd, int64_t A, const uint8_t* ring_dev, const uint8_t* status_dev, const DeliveryDev& dl,
-                            bool do_cells, bool do_inval) {
+                            bool do_cells, bool do_inval, const int64_t* batch_off_dev = nullptr, int32_t n_batches = 0,
+                            int32_t* out_batch_dev = nullptr) {
     SweepArgs a;
+    a.batch_off = batch_off_dev; a.n_batches = n_batches; a.out_batch = out_batch_dev;
     a.K = cd->K; a.H = cd->H; a.L = cd->L; a.raw = cd->raw ? 1 : 0;
     a.do_cells = do_cells; a.do_inval = do_inval;
     a.R = cd->R;
@@ -337,7 +352,8 @@ static int32_t upload_delivery(CD* cd, int64_t A, const rapid_delivery* d, bool 
 }
 
 static int32_t apply_common(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev, const uint8_t* ring_dev,
-                            const uint8_t* status_dev, const int64_t* cfg_dev, const DeliveryDev& dl) {
+                            const uint8_t* status_dev, const int64_t* cfg_dev, const DeliveryDev& dl,
+                            const int64_t* batch_off_dev = nullptr, int32_t n_batches = 0, int32_t* out_batch_dev = nullptr) {
     cd->last_launches = 0;
     cd->last_A = A;
     RAPID_CUDA(cudaEventRecord(cd->ev0, cd->stream));
@@ -347,10 +363,11 @@ static int32_t apply_common(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_d
     cd->cur_ring_dev = ring_dev;
     cd->cur_status_dev = status_dev;
     if (cd->bucketed) {
+        if (batch_off_dev) { set_error("a sequence of batches needs the per-cell order of a sweep handle (RAPID_CD_SWEEP)"); return RAPID_EUNSUPPORTED; }
         rc = bucketed_apply(cd, A, dl, bc);
     } else {
         if (dl.flags & RAPID_DELIVERY_PERMUTED) { set_error("the sweep kernel applies cells in array order; RAPID_DELIVERY_PERMUTED needs a bucketed handle"); return RAPID_EUNSUPPORTED; }
-        rc = launch_sweep(cd, A, ring_dev, status_dev, dl, true, !cd->raw);
+        rc = launch_sweep(cd, A, ring_dev, status_dev, dl, true, !cd->raw, batch_off_dev, n_batches, out_batch_dev);
     }
     if (rc != RAPID_OK) return rc;
     RAPID_CUDA(cudaEventRecord(cd->ev1, cd->stream));
@@ -528,6 +545,37 @@ int32_t rapid_cd_apply_batch(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, cons
     RAPID_CHECK(upload_delivery(cd, n_cells, delivery, false, &dl));
     if (has_blocked) dl.blocked = st.blocked;          // travelled in the staging blob
     RAPID_CHECK(apply_common(cd, cfg_id, n_cells, st.dst, st.ring, st.status, st.cfg, dl));
+    if (proposal_hash || proposal_hash2 || proposal_len || announced)
+        return rapid_cd_read_outputs(cd, proposal_hash, proposal_hash2, proposal_len, announced);
+    return RAPID_OK;
+}
+
+// A sequence of BatchedAlertMessages — one per sender, as AlertBatcher (MembershipService.java:613-637) produces them —
+// delivered to every receiver in array order, with handleMessage's gating between them.
+int32_t rapid_cd_apply_batches(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src, const int32_t* dst, const uint8_t* ring,
+                               const uint8_t* status, const int64_t* cell_cfg, int64_t n_batches, const int64_t* batch_off,
+                               const rapid_delivery* delivery, uint64_t* proposal_hash, uint64_t* proposal_hash2, int32_t* proposal_len,
+                               uint8_t* announced, int32_t* announced_in) {
+    (void)src;
+    if (!cd || n_cells < 0 || (n_cells && (!dst || !ring || !status)) || n_batches < 0 || n_batches > 0x7ffffff0LL || !batch_off) { set_error("bad arguments"); return RAPID_EINVAL; }
+    if (cd->raw) { set_error("RAW handles take rapid_cd_aggregate / rapid_cd_invalidate"); return RAPID_EINVAL; }
+    if (cd->bucketed) { set_error("a sequence of batches needs the per-cell order of a sweep handle (RAPID_CD_SWEEP)"); return RAPID_EUNSUPPORTED; }
+    if (batch_off[0] != 0 || batch_off[n_batches] != n_cells) { set_error("batch_off must run from 0 to n_cells"); return RAPID_EINVAL; }
+    for (int64_t b = 0; b < n_batches; ++b)
+        if (batch_off[b + 1] < batch_off[b]) { set_error("batch_off must be non-decreasing"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    Staged st;
+    const bool has_blocked = delivery && (delivery->flags & RAPID_DELIVERY_BLOCKED);
+    if (has_blocked && !delivery->blocked) { set_error("delivery.blocked is NULL"); return RAPID_EINVAL; }
+    RAPID_CHECK(stage_cells(cd, n_cells, dst, ring, status, cell_cfg, has_blocked ? delivery->blocked : nullptr, &st));
+    DeliveryDev dl;
+    RAPID_CHECK(upload_delivery(cd, n_cells, delivery, false, &dl));
+    if (has_blocked) dl.blocked = st.blocked;
+    RAPID_CHECK(cd->batch_off.reserve((size_t)n_batches + 1));
+    RAPID_CHECK(cd->out_batch.reserve((size_t)cd->Rpad));
+    RAPID_CUDA(cudaMemcpyAsync(cd->batch_off.p, batch_off, (size_t)(n_batches + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, cd->stream));
+    RAPID_CHECK(apply_common(cd, cfg_id, n_cells, st.dst, st.ring, st.status, st.cfg, dl, cd->batch_off.p, (int32_t)n_batches, cd->out_batch.p));
+    if (announced_in) RAPID_CUDA(cudaMemcpy(announced_in, cd->out_batch.p, (size_t)cd->R * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (proposal_hash || proposal_hash2 || proposal_len || announced)
         return rapid_cd_read_outputs(cd, proposal_hash, proposal_hash2, proposal_len, announced);
     return RAPID_OK;

@@ -62,6 +62,8 @@ struct CD {
     DevBuf<uint64_t> pend_h1, pend_h2;  // [R] fingerprint of `proposal` (>=H, not emitted)   (bucketed handles)
     DevBuf<int32_t> pend_cnt;         // [R]
     DevBuf<uint64_t> out_h1, out_h2;  // [R] outputs of the last batch
+    DevBuf<int64_t> batch_off;        // rapid_cd_apply_batches: batch boundaries
+    DevBuf<int32_t> out_batch;        // [R] ... and the batch in which each receiver announced
     DevBuf<int32_t> out_len;          // [R]
     DevBuf<uint8_t> out_ann;          // [R]
 

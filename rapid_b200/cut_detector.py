@@ -158,6 +158,24 @@ class VirtualCluster:
                                              N.ptr(ln), N.ptr(ann)))
         return AlertBatchResult(h1, h2, ln, ann) if read_outputs else None
 
+    def handleBatches(self, cfg_id, src, dst, ring, status, batch_off, cell_cfg=None, blocked=None, bitmap=None):
+        """A sequence of BatchedAlertMessages (batch b = cells batch_off[b]:batch_off[b+1]) delivered in order, with the
+        announcedProposal gating between them (MembershipService.java:318-319).  Sweep handles only.
+        -> (AlertBatchResult, announced_in): announced_in[r] = index of the batch in which receiver r announced, -1 if none."""
+        dst = N.as_i32(dst)
+        A = len(dst)
+        src = N.as_i32(src) if src is not None else np.zeros(max(A, 1), np.int32)
+        ring, status = N.as_u8(ring), N.as_u8(status)
+        off = N.as_i64(batch_off)
+        cc = None if cell_cfg is None else N.as_i64(cell_cfg)
+        d = self._delivery(blocked, bitmap, None)
+        h1, h2 = np.zeros(self.R, np.uint64), np.zeros(self.R, np.uint64)
+        ln, ann, ain = np.zeros(self.R, np.int32), np.zeros(self.R, np.uint8), np.zeros(self.R, np.int32)
+        N.check(N.lib().rapid_cd_apply_batches(self._h, int(cfg_id), A, N.ptr(src), N.ptr(dst), N.ptr(ring), N.ptr(status), N.ptr(cc),
+                                               len(off) - 1, N.ptr(off), C.byref(d) if d is not None else None, N.ptr(h1), N.ptr(h2),
+                                               N.ptr(ln), N.ptr(ann), N.ptr(ain)))
+        return AlertBatchResult(h1, h2, ln, ann), ain
+
     def readOutputs(self):
         h1 = np.zeros(self.R, np.uint64)
         h2 = np.zeros(self.R, np.uint64)

@@ -525,3 +525,67 @@ def test_fuzz_mid_scale_shards(orc, rb, seed):
         if t % 2 == 1:
             kw["perm_seed"] = int(rng.integers(1, 2**62))
         compare_batch(rb, w, sim, cl, None, (src, dst, ring, status), **kw)
+
+
+def _per_sender(src, dst, ring, status):
+    """group cells into one batch per sender, senders in order of first appearance, cells in their original order"""
+    order, seen = [], {}
+    for i, s in enumerate(src.tolist()):
+        if s not in seen:
+            seen[s] = len(order)
+            order.append([])
+        order[seen[s]].append(i)
+    idx = np.array([i for g in order for i in g], np.int64)
+    off = np.zeros(len(order) + 1, np.int64)
+    off[1:] = np.cumsum([len(g) for g in order])
+    return src[idx], dst[idx], ring[idx], status[idx], off
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_sequence_of_per_sender_batches_matches_sequential_handling(orc, rb, seed):
+    """the reference's AlertBatcher sends one BatchedAlertMessage per observer; a receiver handles them one by one and stops
+    at the first that yields a proposal.  One rapid_cd_apply_batches call == the oracle handling the batches one by one."""
+    rng = np.random.default_rng(12000 + seed)
+    n, nj = int(rng.integers(30, 400)), int(rng.integers(0, 5))
+    Hh, Ll = (9, 4) if seed % 2 else (8, 3)
+    w, v, sim, cl = _worlds(orc, rb, n, n_joiners=nj, Hh=Hh, Ll=Ll, kernel="sweep")
+    cfg = w.view.getCurrentConfigurationId()
+    for call in range(3):
+        src, dst, ring, status = random_batch(rng, n + nj, K, int(rng.integers(1, 6)), int(rng.integers(5, 120)), n)
+        src, dst, ring, status, off = _per_sender(src, dst, ring, status)
+        blocked = (rng.random(n) < 0.1).astype(np.uint8) if call == 1 else None
+        want_len, want_in = np.zeros(n, np.int32), np.full(n, -1, np.int32)
+        want_ids = {}
+        for b in range(len(off) - 1):
+            sl = slice(int(off[b]), int(off[b + 1]))
+            o_len, o_ann, o_ids, o_off = sim.apply_batch(src[sl], dst[sl], ring[sl], status[sl], np.full(sl.stop - sl.start, cfg, np.int64),
+                                                         blocked=blocked, threads=2)
+            for r in np.nonzero(o_len)[0]:
+                assert want_in[r] == -1                                   # a receiver announces once per configuration
+                want_in[r], want_len[r] = b, o_len[r]
+                want_ids[int(r)] = o_ids[o_off[r]: o_off[r + 1]].tolist()
+        res, ain = cl.handleBatches(cfg, src, dst, ring, status, off, blocked=blocked)
+        np.testing.assert_array_equal(ain, want_in)
+        np.testing.assert_array_equal(res.proposal_len, want_len)
+        np.testing.assert_array_equal(res.announced, o_ann)
+        for r, ids in list(want_ids.items())[:6]:
+            assert rb.proposal_fingerprint(ids) == (int(res.proposal_hash[r]), int(res.proposal_hash2[r]))
+            assert cl.getProposal(r) == ids
+
+
+def test_per_sender_batches_can_differ_from_one_merged_batch(orc, rb):
+    """two crashes whose alerts do not interleave: sender by sender the first cut is announced alone; merged, both go together"""
+    n = 60
+    w, v, sim, cl = _worlds(orc, rb, n, kernel="sweep")
+    obs = w.tables()[0]
+    cfg = w.view.getCurrentConfigurationId()
+    cells = [(int(obs[s][r]), s, r, 1) for s in (5, 17) for r in range(K)]          # all of 5's reports, then all of 17's
+    src, dst, ring, status = (np.array(x) for x in zip(*cells))
+    off = np.arange(len(cells) + 1, dtype=np.int64)                                  # worst case: one batch per cell
+    res, ain = cl.handleBatches(cfg, src, dst, ring, status, off)
+    assert set(res.proposal_len.tolist()) == {1} and set(ain.tolist()) == {8}        # the 9th report (H = 9) of node 5, alone
+    merged = rb.VirtualCluster(v, 9, 4, kernel="sweep").handleBatch(cfg, src, dst, ring, status)
+    assert set(merged.proposal_len.tolist()) == {2}
+    bk = rb.VirtualCluster(v, 9, 4, kernel="bucketed")
+    with pytest.raises(rb.RapidError):
+        bk.handleBatches(cfg, src, dst, ring, status, off)
