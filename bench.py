@@ -360,14 +360,20 @@ def run_ours(args):
     clocks.mark_begin()
     phases[:] = [0.0, 0.0, 0.0]
     dev_ms, main_ms, launches = 0.0, 0.0, 0
+    import gc
+    gc.collect()
+    gc.disable()                   # no collector pauses inside the timed loops (one late rank stalls the whole all-reduce)
+    per_step = []
     w0 = time.perf_counter()
     for _ in range(args.steps):
+        t_step = time.perf_counter()
         res, ms, mk, nl = step_device()
         dev_ms += ms; main_ms += mk; launches += nl
+        per_step.append((time.perf_counter() - t_step) * 1e3)
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
-    log("[rank %d] per step: apply %.3f ms (dominant kernel %.3f ms), tally %.3f ms" % (
-        rank, phases[0] / args.steps, phases[1] / args.steps, phases[2] / args.steps))
+    log("[rank %d] per step: apply %.3f ms (dominant kernel %.3f ms), tally %.3f ms; host wall per step median %.3f max %.3f ms" % (
+        rank, phases[0] / args.steps, phases[1] / args.steps, phases[2] / args.steps, float(np.median(per_step)), max(per_step)))
     # end-to-end through the host-facing ABI (host arrays, H2D, reset, kernels, decision back)
     for _ in range(2):
         step_host()
@@ -377,6 +383,7 @@ def run_ours(args):
         res = step_host()
     barrier()
     e2e_ms = (time.perf_counter() - e0) * 1e3 / args.steps
+    gc.enable()
     clk = clocks.stop() if rank == 0 else None
     assert emulated or (res.decided and res.hash == want[0])
 

@@ -2,7 +2,8 @@
 // (PingPongFailureDetector.java:38-121, one per entry of getSubjectsOf(myAddr), MembershipService.java:697-707) and the
 // AlertMessages their notifiers raise (edgeFailureNotification, MembershipService.java:472-495), as cells ready for
 // rapid_cd_apply_batch_dev.  One 32-bit word per detector; one tick = one failure-detector interval of the whole cluster:
-// a single elementwise pass (HBM-bound: 8 B of state + 4 B of subject table per detector), a prefix sum, a scatter.
+// a single elementwise pass (HBM-bound: 4-8 B of state + 4 B of subject table per detector); the few detectors that notify are
+// appended to a list, sorted back into detector order, and expanded into alerts and cells.
 #include <limits.h>
 
 #include <cub/cub.cuh>
@@ -16,70 +17,74 @@ namespace rapid {
 #define FD_NOTIFIED (1u << 23)
 
 struct FdScal {
-    unsigned long long totals;          // (alerts << 32) | cells of the last tick
+    int32_t n_fired;                    // detectors whose notifier fired in this interval
+    int32_t n_cells;                    // ring numbers of their AlertMessages
 };
 
-// One interval: run() of every detector (:75-85).  out[idx] = (1 << 32) | #cells if the notifier fired, else 0.
-__global__ void k_fd_tick(int64_t n, int K, const int32_t* __restrict__ subj, const uint8_t* __restrict__ flags,
+// One interval: run() of every detector (:75-85).  A detector that notifies appends its index to `fired` (rare: the list
+// is sorted afterwards, so the atomics' order does not matter); a quiet interval touches nothing but the state words.
+__global__ void k_fd_tick(uint32_t D, uint32_t K, const int32_t* __restrict__ subj, const uint8_t* __restrict__ flags,
                           const uint8_t* __restrict__ edge_fail, int32_t thr, int32_t boot_thr, uint32_t* __restrict__ st,
-                          unsigned long long* __restrict__ out) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * K) return;
-    const int64_t o = idx / K;
-    unsigned long long res = 0;
+                          uint32_t* __restrict__ fired, FdScal* __restrict__ sc) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= D) return;
+    const uint32_t o = idx / K;                                                  // 32-bit: D < 2^31 is checked at create
     const uint8_t fo = flags[o];
-    if (!(fo & RAPID_FD_CRASHED)) {                                              // a crashed process runs nothing
-        uint32_t w = st[idx];
-        const int32_t s = subj[idx];
-        if ((int32_t)(w & FD_CNT_MASK) >= thr && !(w & FD_NOTIFIED)) {           // hasFailed() && !notified (:76-79)
-            w |= FD_NOTIFIED;
-            int cells = 0;                                                       // getRingNumbers(myAddr, subject) (MembershipView.java:397-418)
-            for (int r = 0; r < K; ++r) cells += subj[o * K + r] == s ? 1 : 0;
-            res = (1ull << 32) | (unsigned long long)cells;
-        } else {                                                                 // probe (:80-84) and its callback
-            const uint8_t fs = flags[s];
-            const bool fail = (edge_fail && edge_fail[idx]) || (fo & RAPID_FD_EGRESS_BLOCKED) || (fs & (RAPID_FD_CRASHED | RAPID_FD_INGRESS_BLOCKED));
-            bool count = fail;
-            if (!fail && (fs & RAPID_FD_BOOTSTRAPPING)) {                        // :97-104
-                uint32_t b = w >> 24;
-                if (b < 255) ++b;
-                w = (w & 0x00ffffffu) | (b << 24);
-                count = (int32_t)b > boot_thr;
-            }
-            if (count && (w & FD_CNT_MASK) < FD_CNT_MASK) w = (w & ~FD_CNT_MASK) | ((w & FD_CNT_MASK) + 1);   // :120-123
-        }
-        st[idx] = w;
+    if (fo & RAPID_FD_CRASHED) return;                                           // a crashed process runs nothing
+    uint32_t w = st[idx];
+    if ((int32_t)(w & FD_CNT_MASK) >= thr && !(w & FD_NOTIFIED)) {               // hasFailed() && !notified (:76-79)
+        st[idx] = w | FD_NOTIFIED;
+        fired[atomicAdd(&sc->n_fired, 1)] = idx;
+        return;
     }
-    out[idx] = res;
+    const uint32_t w0 = w;                                                       // probe (:80-84) and its callback
+    const uint8_t fs = flags[subj[idx]];
+    const bool fail = (edge_fail && edge_fail[idx]) || (fo & RAPID_FD_EGRESS_BLOCKED) || (fs & (RAPID_FD_CRASHED | RAPID_FD_INGRESS_BLOCKED));
+    bool count = fail;
+    if (!fail && (fs & RAPID_FD_BOOTSTRAPPING)) {                                // :97-104
+        uint32_t b = w >> 24;
+        if (b < 255) ++b;
+        w = (w & 0x00ffffffu) | (b << 24);
+        count = (int32_t)b > boot_thr;
+    }
+    if (count && (w & FD_CNT_MASK) < FD_CNT_MASK) w = (w & ~FD_CNT_MASK) | ((w & FD_CNT_MASK) + 1);   // :120-123
+    if (w != w0) st[idx] = w;                                                    // healthy edges write nothing
+}
+
+// number of ring numbers of each fired detector's AlertMessage: getRingNumbers(myAddr, subject) (MembershipView.java:397-418)
+__global__ void k_fd_count(int32_t nf, uint32_t K, const uint32_t* __restrict__ fired_sorted, const int32_t* __restrict__ subj,
+                           int32_t* __restrict__ cnt) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    const uint32_t idx = fired_sorted[i], o = idx / K;
+    const int32_t s = subj[idx];
+    int c = 0;
+    for (uint32_t r = 0; r < K; ++r) c += subj[o * K + r] == s ? 1 : 0;
+    cnt[i] = c;
 }
 
 // alerts and cells of the detectors that fired, in detector order (node, then ring of the detector), rings ascending
-__global__ void k_fd_emit(int64_t n, int K, const int32_t* __restrict__ subj, const unsigned long long* __restrict__ cnt,
-                          const unsigned long long* __restrict__ pos, int64_t cfg, int32_t* __restrict__ a_obs,
+__global__ void k_fd_emit(int32_t nf, uint32_t K, const uint32_t* __restrict__ fired_sorted, const int32_t* __restrict__ subj,
+                          const int32_t* __restrict__ cnt, const int32_t* __restrict__ pos, int64_t cfg, int32_t* __restrict__ a_obs,
                           int32_t* __restrict__ a_subj, uint16_t* __restrict__ a_mask, int32_t* __restrict__ c_src,
                           int32_t* __restrict__ c_dst, uint8_t* __restrict__ c_ring, uint8_t* __restrict__ c_status,
-                          int64_t* __restrict__ c_cfg) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * K) return;
-    if (cnt[idx] == 0) return;
-    const int64_t o = idx / K;
+                          int64_t* __restrict__ c_cfg, FdScal* __restrict__ sc) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    if (i == nf - 1) sc->n_cells = pos[i] + cnt[i];
+    const uint32_t idx = fired_sorted[i], o = idx / K;
     const int32_t s = subj[idx];
-    const uint32_t a = (uint32_t)(pos[idx] >> 32);
-    uint32_t c = (uint32_t)pos[idx];
+    int32_t c = pos[i];
     uint32_t mask = 0;
-    for (int r = 0; r < K; ++r) {
+    for (uint32_t r = 0; r < K; ++r) {
         if (subj[o * K + r] != s) continue;
         mask |= 1u << r;
         c_src[c] = (int32_t)o; c_dst[c] = s; c_ring[c] = (uint8_t)r; c_status[c] = RAPID_EDGE_DOWN; c_cfg[c] = cfg;
         ++c;
     }
-    a_obs[a] = (int32_t)o; a_subj[a] = s; a_mask[a] = (uint16_t)mask;
+    a_obs[i] = (int32_t)o; a_subj[i] = s; a_mask[i] = (uint16_t)mask;
 }
-
-__global__ void k_fd_totals(int64_t D, const unsigned long long* __restrict__ cnt, const unsigned long long* __restrict__ pos,
-                            FdScal* __restrict__ sc) {
-    sc->totals = pos[D - 1] + cnt[D - 1];
-}
+__global__ void k_fd_begin(FdScal* sc) { sc->n_fired = 0; sc->n_cells = 0; }
 
 struct FD {
     const View* view = nullptr;
@@ -91,8 +96,8 @@ struct FD {
     int K = 0;
     int32_t thr = 10, boot_thr = 30;
     uint64_t view_epoch = 0;
-    DevBuf<uint32_t> st;
-    DevBuf<unsigned long long> cnt, pos;
+    DevBuf<uint32_t> st, fired, fired_sorted;
+    DevBuf<int32_t> cnt, pos;
     DevBuf<uint8_t> flags, edge, cub_tmp;
     DevBuf<FdScal> sc;
     PinnedBuf<FdScal> h_sc;
@@ -110,12 +115,17 @@ static int32_t fd_alloc(FD* fd) {
     const View* v = fd->view;
     fd->n = v->n; fd->K = v->K; fd->view_epoch = v->epoch;
     const size_t D = (size_t)std::max<int64_t>(fd->n * fd->K, 1);
-    RAPID_CHECK(fd->st.reserve(D)); RAPID_CHECK(fd->cnt.reserve(D)); RAPID_CHECK(fd->pos.reserve(D));
+    if (fd->n * fd->K > 0x7ffffff0LL) { set_error("more than 2^31 detectors"); return RAPID_EINVAL; }
+    RAPID_CHECK(fd->st.reserve(D)); RAPID_CHECK(fd->fired.reserve(D));      // at most every detector fires in one interval
     RAPID_CHECK(fd->flags.reserve((size_t)std::max<int64_t>(fd->n, 1))); RAPID_CHECK(fd->edge.reserve(D));
-    // at most every detector fires in one tick; a fired detector yields at most K cells
-    RAPID_CHECK(fd->a_obs.reserve(D)); RAPID_CHECK(fd->a_subj.reserve(D)); RAPID_CHECK(fd->a_mask.reserve(D));
     RAPID_CUDA(cudaMemsetAsync(fd->st.p, 0, D * sizeof(uint32_t), fd->stream));
     fd->n_alerts = fd->n_cells = 0;
+    return RAPID_OK;
+}
+
+static int32_t fd_read_scal(FD* fd) {
+    RAPID_CUDA(cudaMemcpyAsync(fd->h_sc.p, fd->sc.p, sizeof(FdScal), cudaMemcpyDeviceToHost, fd->stream));
+    RAPID_CUDA(cudaStreamSynchronize(fd->stream));
     return RAPID_OK;
 }
 
@@ -124,26 +134,31 @@ static int32_t fd_tick_device(FD* fd, const uint8_t* d_flags, const uint8_t* d_e
     const int64_t D = fd->n * fd->K;
     fd->n_alerts = fd->n_cells = 0;
     if (fd->n >= 2 && D > 0) {                               // getSubjectsOf is empty in a one-node view (MembershipView.java:270-272)
-        k_fd_tick<<<grid_for(D), TB, 0, s>>>(fd->n, fd->K, fd->view->subj.p, d_flags, d_edge, fd->thr, fd->boot_thr, fd->st.p, fd->cnt.p);
+        k_fd_begin<<<1, 1, 0, s>>>(fd->sc.p);
+        k_fd_tick<<<grid_for(D), TB, 0, s>>>((uint32_t)D, (uint32_t)fd->K, fd->view->subj.p, d_flags, d_edge, fd->thr, fd->boot_thr, fd->st.p,
+                                             fd->fired.p, fd->sc.p);
         RAPID_KERNEL_CHECK();
-        size_t bytes = 0;
-        RAPID_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, fd->cnt.p, fd->pos.p, (int)D, s));
-        RAPID_CHECK(fd->cub_tmp.reserve(bytes));
-        RAPID_CUDA(cub::DeviceScan::ExclusiveSum(fd->cub_tmp.p, bytes, fd->cnt.p, fd->pos.p, (int)D, s));
-        // the cell buffers are sized exactly (a bound of K cells per detector would be 180 MB per million nodes): one 8-byte readback
-        k_fd_totals<<<1, 1, 0, s>>>(D, fd->cnt.p, fd->pos.p, fd->sc.p);
-        RAPID_KERNEL_CHECK();
-        RAPID_CUDA(cudaMemcpyAsync(fd->h_sc.p, fd->sc.p, sizeof(FdScal), cudaMemcpyDeviceToHost, s));
-        RAPID_CUDA(cudaStreamSynchronize(s));
-        const unsigned long long tot = fd->h_sc.p->totals;
-        fd->n_alerts = (int64_t)(tot >> 32); fd->n_cells = (int64_t)(tot & 0xffffffffull);
-        if (fd->n_alerts > 0) {
-            const size_t C = (size_t)std::max<int64_t>(fd->n_cells, 1);
+        RAPID_CHECK(fd_read_scal(fd));                       // a quiet interval ends here: one kernel, one 8-byte readback
+        const int32_t nf = fd->h_sc.p->n_fired;
+        if (nf > 0) {
+            const size_t F = (size_t)nf, C = F * (size_t)fd->K;      // a fired detector yields at most K cells
+            RAPID_CHECK(fd->fired_sorted.reserve(F)); RAPID_CHECK(fd->cnt.reserve(F)); RAPID_CHECK(fd->pos.reserve(F));
+            RAPID_CHECK(fd->a_obs.reserve(F)); RAPID_CHECK(fd->a_subj.reserve(F)); RAPID_CHECK(fd->a_mask.reserve(F));
             RAPID_CHECK(fd->c_src.reserve(C)); RAPID_CHECK(fd->c_dst.reserve(C)); RAPID_CHECK(fd->c_ring.reserve(C));
             RAPID_CHECK(fd->c_status.reserve(C)); RAPID_CHECK(fd->c_cfg.reserve(C));
-            k_fd_emit<<<grid_for(D), TB, 0, s>>>(fd->n, fd->K, fd->view->subj.p, fd->cnt.p, fd->pos.p, cfg, fd->a_obs.p, fd->a_subj.p, fd->a_mask.p,
-                                                fd->c_src.p, fd->c_dst.p, fd->c_ring.p, fd->c_status.p, fd->c_cfg.p);
+            size_t b1 = 0, b2 = 0;
+            RAPID_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, b1, fd->fired.p, fd->fired_sorted.p, nf, 0, 32, s));
+            RAPID_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b2, fd->cnt.p, fd->pos.p, nf, s));
+            RAPID_CHECK(fd->cub_tmp.reserve(std::max(b1, b2)));
+            RAPID_CUDA(cub::DeviceRadixSort::SortKeys(fd->cub_tmp.p, b1, fd->fired.p, fd->fired_sorted.p, nf, 0, 32, s));
+            k_fd_count<<<grid_for(nf), TB, 0, s>>>(nf, (uint32_t)fd->K, fd->fired_sorted.p, fd->view->subj.p, fd->cnt.p);
             RAPID_KERNEL_CHECK();
+            RAPID_CUDA(cub::DeviceScan::ExclusiveSum(fd->cub_tmp.p, b2, fd->cnt.p, fd->pos.p, nf, s));
+            k_fd_emit<<<grid_for(nf), TB, 0, s>>>(nf, (uint32_t)fd->K, fd->fired_sorted.p, fd->view->subj.p, fd->cnt.p, fd->pos.p, cfg, fd->a_obs.p,
+                                                 fd->a_subj.p, fd->a_mask.p, fd->c_src.p, fd->c_dst.p, fd->c_ring.p, fd->c_status.p, fd->c_cfg.p, fd->sc.p);
+            RAPID_KERNEL_CHECK();
+            RAPID_CHECK(fd_read_scal(fd));
+            fd->n_alerts = nf; fd->n_cells = fd->h_sc.p->n_cells;
         }
     }
     if (n_alerts) *n_alerts = fd->n_alerts;
