@@ -387,6 +387,15 @@ def run_ours(args):
     clk = clocks.stop() if rank == 0 else None
     assert emulated or (res.decided and res.hash == want[0])
 
+    # per-rank breakdown (diagnosis of a late rank: every other rank's wait for it shows up in their tally time)
+    mine = torch.tensor([float(np.median(per_step)), max(per_step), phases[0] / args.steps, phases[2] / args.steps],
+                        dtype=torch.float64, device="cuda")
+    if G > 1:
+        allr = [torch.zeros_like(mine) for _ in range(G)]
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    per_rank = [[round(float(x), 4) for x in r.cpu()] for r in allr]
     t = torch.tensor([dev_ms, main_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
     if G > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -412,6 +421,8 @@ def run_ours(args):
                                  "epoch reset between steps excluded",
                        "kernel_path": {1: "sweep", 2: "bucketed-uniform", 3: "bucketed-generic"}.get(cl.lastPath()[0])},
             "wall_ms_per_step_incl_reset": wall_ms / args.steps,
+            "per_rank_ms": {"host_wall_per_step_median": [r[0] for r in per_rank], "host_wall_per_step_max": [r[1] for r in per_rank],
+                            "apply_device": [r[2] for r in per_rank], "tally_device_incl_allreduce_wait": [r[3] for r in per_rank]},
             "clocks": clk,
             "e2e": {"value": A / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(A * 6 + R), "d2h_bytes_per_step": 64 + 36},
