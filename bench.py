@@ -182,28 +182,42 @@ class CpuProblem:
     def measure(self, threads, budget_s):
         """Time the literal C++ restatement on a bounded sample; value = cells/s for the WHOLE cluster (extrapolated)."""
         orc, b, n = self.orc, self.b, self.args.nodes
-        # apply: R_s receivers x the full batch (sample grown until it costs ~budget/4)
-        Rs = self.Rs or threads * 2
-        while True:
+        # apply: R_s receivers x the full batch.  First measurement: a probe of 2 receivers per thread sizes the sample so that it
+        # costs ~budget/4 (one more run); later measurements reuse the size.
+        def run_apply(Rs):
             sim = orc.ClusterSim(self.view, K, H, L, Rs)
-            o_len, o_ann, o_ids, o_off = sim.apply_batch(b.src, b.dst, b.ring, b.status, self.cfgs, threads=threads)
-            t_apply = sim.last_seconds
-            if self.Rs or t_apply > budget_s / 4 or Rs >= 64 * threads:
-                break
-            Rs *= 4
+            out = sim.apply_batch(b.src, b.dst, b.ring, b.status, self.cfgs, threads=threads)
+            return out, sim.last_seconds
+        if self.Rs:
+            Rs = self.Rs
+            (o_len, o_ann, o_ids, o_off), t_apply = run_apply(Rs)
+        else:
+            Rs = max(1, min(threads * 2, self.live))
+            (o_len, o_ann, o_ids, o_off), t_apply = run_apply(Rs)
+            want = int(Rs * (budget_s / 4) / max(t_apply, 1e-3)) // threads * threads
+            want = max(Rs, min(want, 64 * threads, max(threads, self.live // threads * threads)))
+            if want >= 2 * Rs:
+                Rs = want
+                (o_len, o_ann, o_ids, o_off), t_apply = run_apply(Rs)
         self.Rs = Rs
         assert (o_len == len(b.expected_cut)).all(), "oracle did not converge to the expected cut"
         apply_whole = t_apply * self.live / Rs
         # tally: `threads` FastPaxos instances x V_s of the `live` identical votes
         prop = o_ids[o_off[0]: o_off[1]]
-        Vs = self.Vs or 64
-        while True:
+        def run_tally(Vs):
             senders = np.arange(Vs, dtype=np.int32)
-            nd, dec, rec, t_tally = orc.sim_tally(self.u, self.cfg, n, threads, senders, np.full(Vs, self.cfg, np.int64),
-                                                  np.zeros(Vs, np.int32), np.array([0, len(prop)], np.int32), prop, threads=threads)
-            if self.Vs or t_tally > budget_s / 4 or Vs >= self.live:
-                break
-            Vs = min(self.live, Vs * 4)
+            return orc.sim_tally(self.u, self.cfg, n, threads, senders, np.full(Vs, self.cfg, np.int64), np.zeros(Vs, np.int32),
+                                 np.array([0, len(prop)], np.int32), prop, threads=threads)[3]
+        if self.Vs:
+            Vs = self.Vs
+            t_tally = run_tally(Vs)
+        else:
+            Vs = min(64, self.live)
+            t_tally = run_tally(Vs)
+            want = max(Vs, min(int(Vs * (budget_s / 4) / max(t_tally, 1e-3)), self.live))
+            if want >= 2 * Vs:
+                Vs = want
+                t_tally = run_tally(Vs)
         self.Vs = Vs
         tally_whole = t_tally * (self.live / threads) * (self.live / Vs)
         whole = apply_whole + tally_whole
@@ -356,13 +370,13 @@ def run_ours(args):
     assert emulated or (res.decided and (res.hash, res.hash2, res.length) == (want[0], want[1], len(b.expected_cut))), \
         "decision differs from the expected cut: %r" % (res,)
 
-    barrier()
-    clocks.mark_begin()
-    phases[:] = [0.0, 0.0, 0.0]
-    dev_ms, main_ms, launches = 0.0, 0.0, 0
     import gc
     gc.collect()
     gc.disable()                   # no collector pauses inside the timed loops (one late rank stalls the whole all-reduce)
+    clocks.mark_begin()
+    barrier()                      # nothing rank-specific between the barrier and the first timed step: a rank that starts late
+    phases[:] = [0.0, 0.0, 0.0]    # makes every other rank wait for it inside the first all-reduce
+    dev_ms, main_ms, launches = 0.0, 0.0, 0
     per_step = []
     w0 = time.perf_counter()
     for _ in range(args.steps):
