@@ -112,6 +112,10 @@ def test_no_cpu_fallback_without_a_device():
     assert e.value.code == _native.ECUDA
     with pytest.raises(rb.RapidError):
         rb.FastPaxos(1, 10)
+    for make in (lambda: rb.Paxos(1, 10), lambda: rb.PaxosAcceptors(1, 10)):      # the "next" rows fail just as loudly
+        with pytest.raises(rb.RapidError) as e:
+            make()
+        assert e.value.code == _native.ECUDA
 
 
 def test_product_never_touches_the_oracle():
