@@ -43,6 +43,10 @@ public final class Native {
     public static native int cdInvalidate(long cd, long receiver, int[] outIds);
     public static native int cdNumProposals(long cd, long receiver);
     public static native int cdClear(long cd);
+    /** several BatchedAlertMessages in one call: batch b = cells [batchOff[b], batchOff[b+1]); announcedIn[r] = batch index or -1 */
+    public static native int cdApplyBatches(long cd, long cfgId, int[] dst, byte[] ring, byte[] status, long[] cellCfg, long[] batchOff,
+                                            ByteBuffer outHash, ByteBuffer outHash2, ByteBuffer outLen, ByteBuffer outAnnounced,
+                                            ByteBuffer outAnnouncedIn);
 
     // ---- FastPaxos fast round ----
     public static native long fpCreate(long cfgId, long membershipSize, long senderCapacity, int device);

@@ -436,3 +436,26 @@ JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_fdetApplyToDetector(JNIEnv*
     if (rc != RAPID_OK) return rc;
     return rapid_cd_apply_batch_dev(H(rapid_cd, cd), cfg, nCells, src, dst, ring, status, cell_cfg, NULL);
 }
+
+/* ---------------------------------------------------------------- a drained inbox of BatchedAlertMessages (MembershipService.java:300-354 per batch) */
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_cdApplyBatches(JNIEnv* env, jclass c, jlong cd, jlong cfg, jintArray dst, jbyteArray ring,
+                                                                    jbyteArray status, jlongArray cellCfg, jlongArray batchOff, jobject outHash,
+                                                                    jobject outHash2, jobject outLen, jobject outAnnounced, jobject outAnnouncedIn) {
+    const jsize n = (*env)->GetArrayLength(env, dst);
+    const jsize nb = (*env)->GetArrayLength(env, batchOff) - 1;
+    jint* d = (*env)->GetIntArrayElements(env, dst, NULL);
+    jbyte* r = (*env)->GetByteArrayElements(env, ring, NULL);
+    jbyte* s = (*env)->GetByteArrayElements(env, status, NULL);
+    jlong* cc = cellCfg ? (*env)->GetLongArrayElements(env, cellCfg, NULL) : NULL;
+    jlong* off = (*env)->GetLongArrayElements(env, batchOff, NULL);
+    const int32_t rc = rapid_cd_apply_batches(H(rapid_cd, cd), cfg, n, NULL, (const int32_t*)d, (const uint8_t*)r, (const uint8_t*)s,
+                                              (const int64_t*)cc, nb, (const int64_t*)off, NULL, (uint64_t*)BUF(env, outHash),
+                                              (uint64_t*)BUF(env, outHash2), (int32_t*)BUF(env, outLen), (uint8_t*)BUF(env, outAnnounced),
+                                              (int32_t*)BUF(env, outAnnouncedIn));
+    (*env)->ReleaseIntArrayElements(env, dst, d, JNI_ABORT);
+    (*env)->ReleaseByteArrayElements(env, ring, r, JNI_ABORT);
+    (*env)->ReleaseByteArrayElements(env, status, s, JNI_ABORT);
+    if (cc) (*env)->ReleaseLongArrayElements(env, cellCfg, cc, JNI_ABORT);
+    (*env)->ReleaseLongArrayElements(env, batchOff, off, JNI_ABORT);
+    return rc;
+}
