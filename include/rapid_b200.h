@@ -7,6 +7,10 @@
  * a JNI veneer (java/com/vrg/rapid/gpu/Native.java + java/jni/rapid_jni.c, shown in INTEGRATION.md) whose
  * native methods are exactly the entry points below: plain pointers and sizes, no C++/torch types.
  *
+ * Besides the path itself (view, cut detection, fast-round tally, sharded tally) the header carries the rows SURVEY.md §8f
+ * marks "next": applying a decided cut, the classic-Paxos fallback (rapid_px_*, rapid_pxa_*), wire-format ingest
+ * (rapid_wire_*) and alert generation by the edge failure detectors (rapid_fdet_*).
+ *
  * Citations are relative to /root/reference/rapid/src/main/java/com/vrg/rapid/.
  *
  * Conventions
