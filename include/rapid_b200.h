@@ -151,6 +151,8 @@ int32_t rapid_cd_destroy(rapid_cd* cd);
  * (MembershipService.java:318-348).  A cell is one (edgeSrc, edgeDst, ring, status) report; an AlertMessage with r
  * ring numbers is r consecutive cells.  cell_cfg == NULL means every cell carries cfg_id.  delivery == NULL
  * means every receiver gets every cell in array order.
+ * A cell whose ring number is >= K or whose edgeDst is not a known id is DROPPED, the rest of the batch is applied, and the
+ * call returns RAPID_EINVAL naming the cell (the Java trusts ring numbers: only an `assert`, MultiNodeCutDetector.java:87).
  * Outputs (each may be NULL), per receiver:
  *   proposal_hash / proposal_hash2 : order-independent 128-bit fingerprint of the proposal announced by THIS batch
  *                                    (see rapid_proposal_fingerprint), 0 if none
@@ -176,6 +178,18 @@ int32_t rapid_cd_apply_batches(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, co
 int32_t rapid_cd_apply_batch_dev(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src_dev,
                                  const int32_t* dst_dev, const uint8_t* ring_dev, const uint8_t* status_dev,
                                  const int64_t* cell_cfg_dev, const rapid_delivery* delivery_dev);
+/* Same as rapid_cd_apply_batch_dev, but only ENQUEUES the batch on the handle's stream and returns ("calls are synchronous
+ * unless *_async"): a batch is three kernel launches with no host round trip in between, and rapid_fp_tally_cd
+ * orders itself after it on the device, so a whole step (batch -> proposals -> votes -> decision) costs ONE host
+ * synchronisation — the tally's read-back.  Subject-bucketed handles only.  The batch's status is collected at the next
+ * synchronisation point (rapid_cd_sync, rapid_fp_tally_cd, or any accessor): dropped cells -> RAPID_EINVAL; a batch that needed
+ * more than max_subjects subject slots is NOT applied -> RAPID_ENOMEM (the synchronous entry points grow the handle and replay
+ * instead).  The device arrays must stay valid until then. */
+int32_t rapid_cd_apply_batch_dev_async(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src_dev,
+                                       const int32_t* dst_dev, const uint8_t* ring_dev, const uint8_t* status_dev,
+                                       const int64_t* cell_cfg_dev, const rapid_delivery* delivery_dev);
+/* Wait for everything enqueued on the handle; returns (and clears) the latched status of asynchronous batches. */
+int32_t rapid_cd_sync(rapid_cd* cd);
 int32_t rapid_cd_read_outputs(const rapid_cd* cd, uint64_t* proposal_hash, uint64_t* proposal_hash2,
                               int32_t* proposal_len, uint8_t* announced);
 /* The proposal receiver r announced, in canonical order = sorted by the ring-0 comparator
@@ -190,7 +204,8 @@ int32_t rapid_cd_debug_masks(const rapid_cd* cd, int64_t receiver, int32_t* out_
                              int32_t cap, int32_t* out_n);
 int32_t rapid_cd_debug_counters(const rapid_cd* cd, int64_t receiver, int32_t* updates_in_progress,
                                 int32_t* seen_link_down);
-/* Which kernel family served the last batch: 1 = sweep, 2 = bucketed-uniform, 3 = bucketed-generic;
+/* Which kernel family served the last batch: 1 = sweep, 2 = bucketed-uniform, 3 = bucketed-generic (per-receiver delivery
+ * bitmaps), 4 = bucketed-permuted (every cell to every receiver in its own order: the uniform kernel, moments on demand);
  * *n_kernel_launches = CUDA kernels launched by the last apply call. */
 int32_t rapid_cd_last_path(const rapid_cd* cd, int32_t* path, int32_t* n_kernel_launches);
 /* Bucketed handles, last batch: receivers that needed the exact interval analysis, (tile, subject) pairs on the

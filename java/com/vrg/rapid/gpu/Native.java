@@ -43,6 +43,8 @@ public final class Native {
     public static native int cdInvalidate(long cd, long receiver, int[] outIds);
     public static native int cdNumProposals(long cd, long receiver);
     public static native int cdClear(long cd);
+    /** wait for asynchronous batches (wireApplyToDetector / fdetApplyToDetector with async = true); returns their latched status */
+    public static native int cdSync(long cd);
     /** several BatchedAlertMessages in one call: batch b = cells [batchOff[b], batchOff[b+1]); announcedIn[r] = batch index or -1 */
     public static native int cdApplyBatches(long cd, long cfgId, int[] dst, byte[] ring, byte[] status, long[] cellCfg, long[] batchOff,
                                             ByteBuffer outHash, ByteBuffer outHash2, ByteBuffer outLen, ByteBuffer outAnnounced,
@@ -87,6 +89,8 @@ public final class Native {
     public static native int wireDecodeAlerts(long wire, ByteBuffer bytes, int len, boolean asRequest, long[] out5);
     /** apply the cells of the last decode to a detector without leaving the device (rapid_wire_cells_dev + rapid_cd_apply_batch_dev) */
     public static native int wireApplyToDetector(long wire, long cd, long cfgId, long nCells);
+    /** same, enqueue only (rapid_cd_apply_batch_dev_async): the status comes back from cdSync / fpTallyCd */
+    public static native int wireApplyToDetectorAsync(long wire, long cd, long cfgId, long nCells);
 
     // ---- alert generation: the K PingPongFailureDetectors of every virtual node ----
     public static native long fdetCreate(long view, int failureThreshold, int bootstrapThreshold);

@@ -406,6 +406,16 @@ JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_wireApplyToDetector(JNIEnv*
     return rapid_cd_apply_batch_dev(H(rapid_cd, cd), cfg, nCells, src, dst, ring, status, cell_cfg, NULL);
 }
 
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_wireApplyToDetectorAsync(JNIEnv* env, jclass c, jlong w, jlong cd, jlong cfg, jlong nCells) {
+    const int32_t *src, *dst;
+    const uint8_t *ring, *status;
+    const int64_t* cell_cfg;
+    int32_t rc = rapid_wire_cells_dev(H(rapid_wire, w), &src, &dst, &ring, &status, &cell_cfg);
+    if (rc != RAPID_OK) return rc;
+    return rapid_cd_apply_batch_dev_async(H(rapid_cd, cd), cfg, nCells, src, dst, ring, status, cell_cfg, NULL);
+}
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_cdSync(JNIEnv* env, jclass c, jlong cd) { return rapid_cd_sync(H(rapid_cd, cd)); }
+
 /* ---------------------------------------------------------------- alert generation (PingPongFailureDetector.java) */
 JNIEXPORT jlong JNICALL Java_com_vrg_rapid_gpu_Native_fdetCreate(JNIEnv* env, jclass c, jlong view, jint thr, jint bootThr) {
     rapid_fdet* fd = NULL;

@@ -76,6 +76,8 @@ SIGNATURES = {
     "rapid_cd_destroy": [_vp],
     "rapid_cd_apply_batch": [_vp, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "rapid_cd_apply_batch_dev": [_vp, _i64, _i64, _p, _p, _p, _p, _p, _p],
+    "rapid_cd_apply_batch_dev_async": [_vp, _i64, _i64, _p, _p, _p, _p, _p, _p],
+    "rapid_cd_sync": [_vp],
     "rapid_cd_apply_batches": [_vp, _i64, _i64, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p],
     "rapid_cd_read_outputs": [_vp, _p, _p, _p, _p],
     "rapid_cd_get_proposal": [_vp, _i64, _p, _i32, _p],

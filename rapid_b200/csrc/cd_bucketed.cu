@@ -21,13 +21,24 @@
 // "Moments" are cell indices for uniform delivery and the receiver's own permutation keys for PERMUTED delivery,
 // so a per-receiver order needs no per-receiver sort.
 //
-// Kernels: k_apply_uniform (SWAR: 8 receivers per thread, 128-bit loads/stores, write-only fresh-subject path),
-// k_apply_generic (one receiver per thread: bitmap / permuted delivery), k_finalize1, k_mixed_pass / k_mixed_update /
-// k_mixed_commit / k_mixed_mark (interval analysis), k_flip, k_inval_pairs, k_finalize2.
+// A batch is THREE launches with no host round trip between them (cd_prepare.cu's k_prepare, then the two below); the
+// host learns the outcome from a snapshot of the device counters at its next synchronisation point:
+//   k_apply_uniform<PERM>  SWAR, 8 receivers per thread, 128-bit loads/stores, write-only fresh-subject path.  PERM = every
+//                          receiver gets every cell but in its OWN order (RAPID_DELIVERY_PERMUTED): the new state and all the
+//                          crossing COUNTS do not depend on the order, so the kernel is the uniform one minus the moments;
+//                          the (rare) receivers whose classification needs their own t_L / t_H get them from a second,
+//                          per-receiver pass over the pre-batch rows inside k_resolve.
+//   k_apply_generic        one receiver per thread: per-receiver delivery bitmaps (with or without a permuted order)
+//   k_resolve              cooperative: finalize1 -> [moments on demand] -> [interval analysis to its fixpoint] -> row flip ->
+//                          invalidateFailingEdges over the work list -> finalize2 -> [bit-15 marks] -> counter snapshot.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdlib>
 
 #include "cd_internal.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace rapid {
 
@@ -45,6 +56,7 @@ constexpr uint32_t RF_MIXED_EMIT = 64u;   // announced a proposal found by the i
 
 // per-receiver state of the interval analysis (MIXED receivers)
 constexpr uint32_t MX_ON = 1u, MX_NEG = 2u, MX_HAS_E = 4u, MX_DONE = 8u;
+constexpr uint32_t MX_TIME = 16u;     // PERMUTED delivery: the classification needs this receiver's own min t_H / min t_L
 
 // partial-accumulator flags
 constexpr uint32_t PF_SEEN = 1u;      // a valid DOWN cell was delivered
@@ -76,6 +88,8 @@ struct Bucketed {
     DevBuf<ChunkAcc> p_chunk;
     DevBuf<uint4> p_cnt;
     DevBuf<uint64_t> p_minTH, p_minTLun, p_h1, p_h2;
+    DevBuf<unsigned char> ra_dev;             // the ResolveArgs of the batch in flight (the kernels take a pointer: the struct is
+                                              // too big to pass by value to the out-of-line rare paths without a per-thread copy)
     DevBuf<uint32_t> mx_fl;                   // [Rpad] MX_* flags
     DevBuf<uint64_t> mx_a, mx_cand, mx_emax;  // [Rpad] start of the never-closing component / its next candidate / e* candidate
     DevBuf<uint64_t> mx_p1, mx_p2;            // [Rpad] fingerprint of `proposal` before the batch
@@ -83,17 +97,17 @@ struct Bucketed {
     DevBuf<unsigned long long> mx_e1, mx_e2;  // [Rpad] fingerprint of the batch subjects emitted explicitly
     DevBuf<int32_t> mx_ec;
     DevBuf<uint64_t> estar;                   // [Rpad] last explicit emission moment of RF_MIXED_EMIT receivers
-    DevBuf<int32_t> mx_changed;               // [1]
+    DevBuf<int32_t> mx_changed;               // [4] rotating "the component grew" counters of the fixpoint loop
     DevBuf<int32_t> batch_index;              // [slot] -> index of the subject in the batch in flight
-    DevBuf<int32_t> k3_res;
-    DevBuf<unsigned long long> k3_h1, k3_h2;
-    DevBuf<int2> pre_pairs;
-    DevBuf<int32_t> pre_count;
-    DevBuf<int32_t> in_list;                  // [slot][n_tiles]
-    size_t in_list_slots = 0;
+    // invalidation work list (WorkList)
+    DevBuf<int32_t> wl_slots, wl_count, wl_listed, wl_so_tab;
+    DevBuf<uint8_t> wl_in_tile;               // [slot][n_tiles]
+    DevBuf<uint8_t> has_so;                   // [slot] some observer of the subject has a slot (can get implicit reports)
+    size_t in_list_slots = 0;                 // slots the work-list arrays are sized for
     int n_tiles = 0;
     size_t part_cap = 0;
     int slots_uniform = 0, slots_generic = 0;   // resident blocks of the apply kernels on this device
+    int resolve_grid = 0;                       // co-resident blocks of the cooperative resolve kernel
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -129,6 +143,18 @@ __device__ __forceinline__ Visit visit_uniform(uint32_t ur, const SubjDesc& d, c
     return v;
 }
 
+// PERMUTED delivery (every cell reaches every active receiver, each in its own order): the counts before / after the batch
+// do not depend on the order; the moments are left out (they are computed on demand, k_resolve's moment pass)
+__device__ __forceinline__ Visit visit_counts(uint32_t ur, const SubjDesc& d, uint32_t RM, int L, int H) {
+    Visit v;
+    v.tL = 0; v.tH = 0;
+    v.c0 = __popc(ur);
+    v.c1 = __popc((ur | d.bmask) & RM);
+    v.crossL = v.c0 < L && v.c1 >= L;
+    v.crossH = v.c0 < H && v.c1 >= H;
+    return v;
+}
+
 struct Acc {
     uint32_t nL = 0, nH = 0, tp = 0, nUn = 0, flags = 0;
     uint32_t minTH = T32_NONE, minTLun = T32_NONE;
@@ -155,7 +181,9 @@ struct ApplyArgs {
     int64_t R, rbegin;
     const uint32_t* rflags;
     DeliveryDev dl;
-    int Sb, chunk;
+    const BatchCounts* bc;        // device counters of the batch in flight: the number of batch subjects, the first fresh slot
+                                  // (slots >= S_before were assigned by this batch: known-zero state, never read) and the
+                                  // overflow flag come from HERE — the host never learns them inside a batch
     const SubjDesc* desc;
     const SubjWalk* walk;
     const int32_t* slot_subject;
@@ -164,20 +192,10 @@ struct ApplyArgs {
     const uint8_t* s_status;
     Partials part;
     int n_tiles;
-    int32_t* in_list;
-    int2* pre_pairs;
-    int32_t* pre_count;
-    int32_t pre_cap;
-    int32_t S_before;             // slots >= S_before were assigned by this batch: their state is known-zero (never read)
+    WorkList wl;                  // invalidation work list
 };
 
-__device__ __forceinline__ void note_unresolved(const ApplyArgs& a, int tile, int32_t slot) {
-    int32_t* f = a.in_list + (size_t)slot * a.n_tiles + tile;
-    if (atomicExch(f, 1) == 0) {
-        const int32_t at = atomicAdd(a.pre_count, 1);
-        if (at < a.pre_cap) a.pre_pairs[at] = make_int2(tile, slot);
-    }
-}
+__device__ __forceinline__ void note_unresolved(const ApplyArgs& a, int tile, int32_t slot) { worklist_note(a.wl, tile, slot); }
 
 // ---- uniform delivery: every active receiver gets every valid cell in array order -------------------------------------
 // One thread owns 8 consecutive receivers (one 128-bit load + one 128-bit store per subject).  The common case is
@@ -203,17 +221,22 @@ struct StageAcc {
     uint64_t h1, h2;
 };
 
+template <bool PERM>
 __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a) {
     __shared__ SubjDesc sd[STAGE];
-    __shared__ SubjWalk sw[STAGE];
+    __shared__ SubjWalk sw[PERM ? 1 : STAGE];
     __shared__ const uint16_t* s_src[STAGE];
     __shared__ uint16_t* s_dst[STAGE];
     __shared__ uint32_t s_nw[STAGE];          // (batch ring mask) replicated in both half-words
     __shared__ int s_unres[STAGE];
     __shared__ StageAcc s_facc;               // fresh-subject accumulators of this block's chunk (same for every receiver)
 
+    if (a.bc->overflow) return;               // the batch was rolled back by k_prepare
+    // the number of batch subjects / the first fresh slot are only known on the device
+    const int Sb = a.bc->n_batch_subj, S_before = a.bc->S_before;
+    const int per_chunk = max(1, (Sb + (int)gridDim.y - 1) / (int)gridDim.y);
     const int tile = blockIdx.x, chunk = blockIdx.y, t = threadIdx.x;
-    const int s0 = chunk * a.chunk, s1 = min(a.Sb, s0 + a.chunk);
+    const int s0 = min(Sb, chunk * per_chunk), s1 = min(Sb, s0 + per_chunk);
     const int64_t r0 = (int64_t)tile * TILE_R + (int64_t)t * 8;
     const size_t pbase = (size_t)chunk * a.Rpad + (size_t)r0;
     const uint32_t RM = (1u << a.K) - 1u;
@@ -248,7 +271,7 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                 const SubjDesc d = a.desc[base + t];
                 sd[t] = d;
                 const uint8_t c = a.cur[d.slot];
-                const bool fresh = d.slot >= a.S_before;
+                const bool fresh = d.slot >= S_before;
                 s_src[t] = fresh ? nullptr : a.masks + ((size_t)d.slot * 2 + c) * a.Rpad;
                 s_dst[t] = a.masks + ((size_t)d.slot * 2 + (c ^ 1)) * a.Rpad;
                 s_nw[t] = (uint32_t)d.bmask * 0x10001u;
@@ -258,10 +281,13 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                     if (nr >= L) nLH += 1u;
                     if (nr >= H) { nLH += 1u << 16; mTH = d.tHf; h1 = d.mix1; h2 = d.mix2; }
                     else if (nr >= L) { tpUn += 1u << 16; mTL = d.tLf; un = block_active; }
-                } else {
+                } else if (!PERM) {
                     sw[t] = a.walk[base + t];
                 }
-                s_unres[t] = un;
+                // only subjects with an observer in the dictionary can receive implicit reports: the others never go on
+                // the invalidation work list (has_so is refreshed by k_prepare whenever a subject gets a slot)
+                s_unres[t] = (un && a.wl.has_so[d.slot]) ? 1 : 0;
+                if (!fresh) s_unres[t] = a.wl.has_so[d.slot] ? 0 : -1;       // -1: never list it
             }
             // warp reduction of the fresh subjects' contribution
 #pragma unroll
@@ -298,7 +324,7 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                 const uint32_t andv = andw & (andw >> 16) & 0xFFFFu, st = (orw | (orw >> 16)) & 0xFFFFu;
                 carried = true;
                 if (andv == st) {
-                    const Visit v = visit_uniform(st & RM, d, sw[i], L, H);
+                    const Visit v = PERM ? visit_counts(st & RM, d, RM, L, H) : visit_uniform(st & RM, d, sw[PERM ? 0 : i], L, H);
                     unres = accumulate(com, v, d, L, H);
                     const uint32_t nw = st * 0x10001u | nwb;
                     w.x = (w.x & ~am[0]) | (nw & am[0]);
@@ -316,7 +342,7 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                     for (int j = 0; j < 8; ++j) {
                         if (!((act >> j) & 1u)) continue;
                         const uint32_t sj = (words[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-                        const Visit v = visit_uniform(sj & RM, d, sw[i], L, H);
+                        const Visit v = PERM ? visit_counts(sj & RM, d, RM, L, H) : visit_uniform(sj & RM, d, sw[PERM ? 0 : i], L, H);
                         Acc ex;
                         unres |= accumulate(ex, v, d, L, H);
                         const size_t at = pbase + j;
@@ -332,13 +358,13 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                 }
             }
             *reinterpret_cast<uint4*>(dst + r0) = w;       // the non-current row becomes the new state
-            if (__any_sync(0xffffffffu, unres) && (t & 31) == 0) s_unres[i] = 1;
+            if (__any_sync(0xffffffffu, unres) && (t & 31) == 0 && s_unres[i] == 0) s_unres[i] = 1;
         }
         __syncthreads();
-        if (t < n && s_unres[t]) note_unresolved(a, tile, sd[t].slot);
+        if (t < n && s_unres[t] > 0) note_unresolved(a, tile, sd[t].slot);
     }
     // Fresh subjects contribute the same to every active receiver: that goes to ONE record per chunk.  Per-receiver
-    // partials are only written by blocks in which some thread met a carried subject; k_finalize1 adds the two.
+    // partials are only written by blocks in which some thread met a carried subject; finalize1 adds the two.
     const int need = __syncthreads_or((carried || had_exc) ? 1 : 0);
     if (t == 0) {
         a.part.flag[(size_t)chunk * a.part.n_tiles + tile] = need;
@@ -471,10 +497,13 @@ __global__ void __launch_bounds__(GEN_THREADS, 4) k_apply_generic(const ApplyArg
     __shared__ const uint16_t* s_src[STAGE];
     __shared__ uint16_t* s_dst[STAGE];
     __shared__ int s_unres[STAGE];
+    if (a.bc->overflow) return;               // the batch was rolled back by k_prepare
+    const int Sb = a.bc->n_batch_subj, S_before = a.bc->S_before;
+    const int per_chunk = max(1, (Sb + (int)gridDim.y - 1) / (int)gridDim.y);
     const int t = threadIdx.x, chunk = blockIdx.y;
     const int64_t r = (int64_t)blockIdx.x * GEN_THREADS + t;
     const int tile = (int)(((int64_t)blockIdx.x * GEN_THREADS) / TILE_R);
-    const int s0 = chunk * a.chunk, s1 = min(a.Sb, s0 + a.chunk);
+    const int s0 = min(Sb, chunk * per_chunk), s1 = min(Sb, s0 + per_chunk);
     const uint32_t RM = (1u << a.K) - 1u;
     const int L = a.L, H = a.H;
     const bool in_range = r < a.R;
@@ -490,9 +519,9 @@ __global__ void __launch_bounds__(GEN_THREADS, 4) k_apply_generic(const ApplyArg
             const SubjDesc d = a.desc[base + t];
             sd[t] = d;
             const uint8_t c = a.cur[d.slot];
-            s_src[t] = d.slot >= a.S_before ? nullptr : a.masks + ((size_t)d.slot * 2 + c) * a.Rpad;
+            s_src[t] = d.slot >= S_before ? nullptr : a.masks + ((size_t)d.slot * 2 + c) * a.Rpad;
             s_dst[t] = a.masks + ((size_t)d.slot * 2 + (c ^ 1)) * a.Rpad;
-            s_unres[t] = 0;
+            s_unres[t] = a.wl.has_so[d.slot] ? 0 : -1;          // -1: no observer in the dictionary, never on the work list
         }
         __syncthreads();
         // the visit is a dependent chain (state word -> cells -> moments): keep 8 state loads in flight per thread
@@ -525,10 +554,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 4) k_apply_generic(const ApplyArg
                 }
                 s_dst[i][r] = (uint16_t)st;
             }
-            if (__any_sync(0xffffffffu, unres) && (t & 31) == 0) s_unres[i] = 1;
+            if (__any_sync(0xffffffffu, unres) && (t & 31) == 0 && s_unres[i] == 0) s_unres[i] = 1;
         }
         __syncthreads();
-        if (t < n && s_unres[t]) note_unresolved(a, tile, sd[t].slot);   // a 256-receiver block lies inside one tile
+        if (t < n && s_unres[t] > 0) note_unresolved(a, tile, sd[t].slot);   // a 256-receiver block lies inside one tile
     }
     if (t == 0) {
         if ((blockIdx.x * GEN_THREADS) % TILE_R == 0) a.part.flag[(size_t)chunk * a.part.n_tiles + tile] = 1;
@@ -548,17 +577,26 @@ __global__ void __launch_bounds__(GEN_THREADS, 4) k_apply_generic(const ApplyArg
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// finalize 1: combine the chunk partials of every receiver, classify, keep the scalars
-// ------------------------------------------------------------------------------------------------------------------
-struct FinArgs {
-    int64_t R;
-    size_t Rpad;
-    int n_chunks;
-    Partials part;
-    DeliveryDev dl;
-    int any_down_uniform;        // uniform delivery: the batch holds a valid DOWN cell
-    int uniform;
+// ==================================================================================================================
+// k_resolve: everything after the apply kernel, in ONE cooperative launch (grid-wide barriers instead of host round trips)
+//
+//   finalize1   combine the chunk partials of every receiver, classify (EMIT_ALL / nothing / needs moments / MIXED)
+//   [moments]   PERMUTED delivery only, flagged receivers only: their own min t_H / min t_L from the PRE-batch rows
+//   [mixed]     exact interval analysis to its fixpoint (see below), flagged receivers only
+//   flip        the rows written by the apply kernel become current
+//   inval       invalidateFailingEdges over the (tile, subject) work list
+//   finalize2   emissions of the invalidation pass, announced flags
+//   [marks]     bit 15 for receivers that announced only the explicit part
+//   tail        the last block snapshots the batch counters for the host and resets the per-batch fields
+// ==================================================================================================================
+struct ResolveArgs {
+    ApplyArgs ap;
+    BatchCounts* bc;
+    BatchCounts* snap;
+    int n_chunks;                 // subject chunks of the apply launch (layout of the partials)
+    int uniform;                  // moments are cell indices (no PERMUTED / BITMAP)
+    int counts_only;              // the apply kernel left the moments out (k_apply_uniform<true>)
+    uint8_t* cur_w;
     int32_t* n_pre;
     uint32_t* rflags;
     uint64_t* pend_h1;
@@ -567,6 +605,7 @@ struct FinArgs {
     uint64_t* out_h1;
     uint64_t* out_h2;
     int32_t* out_len;
+    uint8_t* out_ann;
     uint32_t* mx_fl;
     uint64_t* mx_a;
     uint64_t* mx_cand;
@@ -574,64 +613,107 @@ struct FinArgs {
     uint64_t* mx_p1;
     uint64_t* mx_p2;
     int32_t* mx_pc;
-    BatchCounts* bc;
+    uint64_t* estar;
+    unsigned long long* mx_e1;
+    unsigned long long* mx_e2;
+    int32_t* mx_ec;
+    int32_t* mx_changed;          // [4]
+    const int32_t* slot_of;
+    const int32_t* obs;
+    const int32_t* touch;
+    const int32_t* batch_index;
+    int32_t serial;
 };
 
-__global__ void k_finalize1(const FinArgs a) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.R) return;
-    a.mx_fl[r] = 0;
-    uint32_t flags = a.rflags[r] & ~(RF_ANN_NOW | RF_K3 | RF_ACTIVE);
-    a.out_h1[r] = 0; a.out_h2[r] = 0; a.out_len[r] = 0;
-    const bool active = !(flags & RF_ANNOUNCED) && !((a.dl.flags & RAPID_DELIVERY_BLOCKED) && a.dl.blocked[r]);
-    if (!active) { a.rflags[r] = flags; return; }
-    flags |= RF_ACTIVE;
-    uint32_t nL = 0, nH = 0, tp = 0, nUn = 0, fl = 0;
-    uint64_t minTH = T64_NONE, minTLun = T64_NONE, h1 = 0, h2 = 0;
-    bool haveTH = false, haveTL = false;
-    const int tile = (int)(r / TILE_R);
-    for (int c = 0; c < a.n_chunks; ++c) {
-        {   // fresh subjects of the chunk: the same for every active receiver
-            const ChunkAcc k = a.part.chunk[c];
-            const uint32_t cH = k.nLH >> 16, cUn = k.tpUn >> 16;
-            nL += k.nLH & 0xFFFFu; nH += cH; nUn += cUn; fl |= k.fl;
-            if (cH && (!haveTH || (uint64_t)k.minTH < minTH)) { minTH = k.minTH; haveTH = true; }
-            if (cUn && (!haveTL || (uint64_t)k.minTLun < minTLun)) { minTLun = k.minTLun; haveTL = true; }
-            h1 += k.h1; h2 += k.h2;
+__device__ __forceinline__ int32_t block_sum_i32(int32_t v, int32_t* s_red) {      // every thread gets the block total
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int32_t s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += s_red[w];
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// finalize 1: combine the chunk partials of every receiver, classify, keep the scalars
+// ------------------------------------------------------------------------------------------------------------------
+__device__ void phase_finalize1(const ResolveArgs& a, int32_t* s_red) {
+    const ApplyArgs& ap = a.ap;
+    const int any_down = a.bc->any_down;
+    int32_t my_mixed = 0, my_times = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < ap.R; r += (int64_t)gridDim.x * blockDim.x) {
+        a.mx_fl[r] = 0;
+        uint32_t flags = a.rflags[r] & ~(RF_ANN_NOW | RF_K3 | RF_ACTIVE);
+        a.out_h1[r] = 0; a.out_h2[r] = 0; a.out_len[r] = 0;
+        const bool active = !(flags & RF_ANNOUNCED) && !((ap.dl.flags & RAPID_DELIVERY_BLOCKED) && ap.dl.blocked[r]);
+        if (!active) { a.rflags[r] = flags; a.out_ann[r] = (flags & RF_ANNOUNCED) ? 1 : 0; continue; }
+        flags |= RF_ACTIVE;
+        uint32_t nL = 0, nH = 0, tp = 0, nUn = 0, fl = 0;
+        uint64_t minTH = T64_NONE, minTLun = T64_NONE, h1 = 0, h2 = 0;
+        bool haveTH = false, haveTL = false;
+        const int tile = (int)(r / TILE_R);
+        for (int c = 0; c < a.n_chunks; ++c) {
+            {   // fresh subjects of the chunk: the same for every active receiver
+                const ChunkAcc k = ap.part.chunk[c];
+                const uint32_t cH = k.nLH >> 16, cUn = k.tpUn >> 16;
+                nL += k.nLH & 0xFFFFu; nH += cH; nUn += cUn; fl |= k.fl;
+                if (cH && (!haveTH || (uint64_t)k.minTH < minTH)) { minTH = k.minTH; haveTH = true; }
+                if (cUn && (!haveTL || (uint64_t)k.minTLun < minTLun)) { minTLun = k.minTLun; haveTL = true; }
+                h1 += k.h1; h2 += k.h2;
+            }
+            if (!ap.part.flag[(size_t)c * ap.part.n_tiles + tile]) continue;
+            const size_t p = (size_t)c * ap.Rpad + (size_t)r;
+            const uint4 q = ap.part.cnt[p];
+            const uint32_t cH = q.x >> 16, cUn = q.y >> 16;
+            nL += q.x & 0xFFFFu; nH += cH; tp += q.y & 0xFFFFu; nUn += cUn; fl |= q.z;
+            if (cH) { const uint64_t v = ap.part.minTH[p]; if (!haveTH || v < minTH) { minTH = v; haveTH = true; } }
+            if (cUn) { const uint64_t v = ap.part.minTLun[p]; if (!haveTL || v < minTLun) { minTLun = v; haveTL = true; } }
+            h1 += ap.part.h1[p]; h2 += ap.part.h2[p];
         }
-        if (!a.part.flag[(size_t)c * a.part.n_tiles + tile]) continue;
-        const size_t p = (size_t)c * a.Rpad + (size_t)r;
-        const uint4 q = a.part.cnt[p];
-        const uint32_t cH = q.x >> 16, cUn = q.y >> 16;
-        nL += q.x & 0xFFFFu; nH += cH; tp += q.y & 0xFFFFu; nUn += cUn; fl |= q.z;
-        if (cH) { const uint64_t v = a.part.minTH[p]; if (!haveTH || v < minTH) { minTH = v; haveTH = true; } }
-        if (cUn) { const uint64_t v = a.part.minTLun[p]; if (!haveTL || v < minTLun) { minTLun = v; haveTL = true; } }
-        h1 += a.part.h1[p]; h2 += a.part.h2[p];
+        // every valid cell reaches every active receiver unless there is a per-receiver bitmap
+        if ((a.uniform || a.counts_only) ? any_down : (fl & PF_SEEN)) flags |= RF_SEEN_DOWN;
+        const int32_t npre_old = a.n_pre[r];
+        const int32_t npre_new = npre_old + (int32_t)nL - (int32_t)nH;
+        const uint64_t p1_old = a.pend_h1[r], p2_old = a.pend_h2[r];
+        const int32_t pc_old = a.pend_cnt[r];
+        uint64_t ph1 = p1_old + h1, ph2 = p2_old + h2;
+        int32_t pc = pc_old + (int32_t)nH;
+        const int32_t untouched_pre = npre_old - (int32_t)tp;
+        if (nH > 0 && npre_new == 0) {
+            // EMIT_ALL: the last H-crossing of the batch leaves updatesInProgress == 0, so every subject at >= H has
+            // left in some proposal of this batch (MultiNodeCutDetector.java:110-121); the union is what is announced.
+            a.out_h1[r] = ph1; a.out_h2[r] = ph2; a.out_len[r] = pc;
+            ph1 = 0; ph2 = 0; pc = 0;
+            flags |= RF_ANNOUNCED | RF_ANN_NOW | RF_RULE_GE_H;
+        } else if (nH > 0 && untouched_pre <= 0 && !(fl & PF_NEGINF)) {
+            // every unresolved subject entered the band inside this batch: whether an H-crossing came before the first of
+            // them depends on the moments (haveTL holds: npre_new > 0)
+            if (a.counts_only) {
+                // PERMUTED: the moments are this receiver's own — computed on demand from the pre-batch rows
+                ++my_times;
+                a.mx_fl[r] = MX_TIME;
+                a.mx_a[r] = T64_NONE; a.mx_cand[r] = T64_NONE; a.mx_emax[r] = 0;
+                a.mx_p1[r] = p1_old; a.mx_p2[r] = p2_old; a.mx_pc[r] = pc_old;
+            } else if (!(haveTL && minTLun < minTH)) {
+                // MIXED: some proposals may have been emitted before the unresolved subjects entered the band
+                ++my_mixed;
+                a.mx_fl[r] = MX_ON;
+                a.mx_a[r] = minTLun; a.mx_cand[r] = T64_NONE; a.mx_emax[r] = 0;
+                a.mx_p1[r] = p1_old; a.mx_p2[r] = p2_old; a.mx_pc[r] = pc_old;
+            }
+        }
+        if (npre_new > 0 && (flags & RF_SEEN_DOWN)) flags |= RF_K3;
+        a.n_pre[r] = npre_new;
+        a.pend_h1[r] = ph1; a.pend_h2[r] = ph2; a.pend_cnt[r] = pc;
+        a.rflags[r] = flags;
     }
-    if (a.uniform ? a.any_down_uniform : (fl & PF_SEEN)) flags |= RF_SEEN_DOWN;
-    const int32_t npre_old = a.n_pre[r];
-    const int32_t npre_new = npre_old + (int32_t)nL - (int32_t)nH;
-    uint64_t ph1 = a.pend_h1[r] + h1, ph2 = a.pend_h2[r] + h2;
-    int32_t pc = a.pend_cnt[r] + (int32_t)nH;
-    const int32_t untouched_pre = npre_old - (int32_t)tp;
-    if (nH > 0 && npre_new == 0) {
-        // EMIT_ALL: the last H-crossing of the batch leaves updatesInProgress == 0, so every subject at >= H has
-        // left in some proposal of this batch (MultiNodeCutDetector.java:110-121); the union is what is announced.
-        a.out_h1[r] = ph1; a.out_h2[r] = ph2; a.out_len[r] = pc;
-        ph1 = 0; ph2 = 0; pc = 0;
-        flags |= RF_ANNOUNCED | RF_ANN_NOW | RF_RULE_GE_H;
-    } else if (nH > 0 && !(untouched_pre > 0 || (fl & PF_NEGINF) || (haveTL && minTLun < minTH))) {
-        // MIXED: some proposals may have been emitted before the unresolved subjects entered the band
-        // (haveTL holds here: npre_new > 0 and every unresolved subject entered the band inside the batch)
-        atomicAdd(&a.bc->n_mixed, 1);
-        a.mx_fl[r] = MX_ON;
-        a.mx_a[r] = minTLun; a.mx_cand[r] = T64_NONE; a.mx_emax[r] = 0;
-        a.mx_p1[r] = a.pend_h1[r]; a.mx_p2[r] = a.pend_h2[r]; a.mx_pc[r] = a.pend_cnt[r];
+    const int32_t bm = block_sum_i32(my_mixed, s_red), bt = block_sum_i32(my_times, s_red);
+    if (threadIdx.x == 0) {
+        if (bm) atomicAdd(&a.bc->n_mixed, bm);
+        if (bt) atomicAdd(&a.bc->n_times, bt);
     }
-    if (npre_new > 0 && (flags & RF_SEEN_DOWN)) flags |= RF_K3;
-    a.n_pre[r] = npre_new;
-    a.pend_h1[r] = ph1; a.pend_h2[r] = ph2; a.pend_cnt[r] = pc;
-    a.rflags[r] = flags;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -642,275 +724,312 @@ __global__ void k_finalize1(const FinArgs a) {
 // it.  Let a = start of the connected component of intervals that contains the never-closing ones: everything closing
 // after `a` is covered, and e* = the latest closing moment before `a` is the last explicit emission; what left is
 // {t_H <= e*} plus whatever was pending before the batch.  `a` is found as a fixpoint: a <- min{t_L : t_H > a},
-// starting from the earliest never-closing start (k_finalize1).  One FIX pass recomputes every flagged receiver's
+// starting from the earliest never-closing start (finalize1).  One FIX pass recomputes every flagged receiver's
 // intervals from the PRE-batch rows (nothing is stored per (subject, receiver)); uniform delivery typically makes
 // every receiver MIXED in the same way, so the passes are shaped like the apply kernels, not like a rare fallback.
+// The loop runs on the device: pass, grid barrier, update, grid barrier, until no receiver's component grew.
 // ------------------------------------------------------------------------------------------------------------------
-struct MixArgs {
-    ApplyArgs ap;
-    uint32_t* mx_fl;
-    uint64_t* mx_a;
-    uint64_t* mx_cand;
-    uint64_t* mx_emax;
-    uint64_t* estar;
-    unsigned long long* mx_e1;
-    unsigned long long* mx_e2;
-    int32_t* mx_ec;
-    int uniform;
-};
-
-struct IVisit { int c0; bool crossL, crossH; uint64_t tL, tH; };
+struct IVisit { int c0, c1; bool crossL, crossH; uint64_t tL, tH; };
 
 __device__ __forceinline__ IVisit interval_visit(const ApplyArgs& a, int uniform, uint32_t ur, const SubjDesc& d, const SubjWalk* w,
                                                  int64_t r, uint64_t rs) {
     IVisit o;
     if (uniform) {
         const Visit v = visit_uniform(ur, d, *w, a.L, a.H);
-        o.c0 = v.c0; o.crossL = v.crossL; o.crossH = v.crossH; o.tL = v.tL; o.tH = v.tH;
+        o.c0 = v.c0; o.c1 = v.c1; o.crossL = v.crossL; o.crossH = v.crossH; o.tL = v.tL; o.tH = v.tH;
     } else {
         const GVisit v = visit_generic(ur, d, a.sidx, a.s_ring, a.s_status, a.dl, r, rs, a.L, a.H);
-        o.c0 = v.c0; o.crossL = v.crossL; o.crossH = v.crossH; o.tL = v.tL; o.tH = v.tH;
+        o.c0 = v.c0; o.c1 = v.c1; o.crossL = v.crossL; o.crossH = v.crossH; o.tL = v.tL; o.tH = v.tH;
     }
     return o;
 }
 
-template <int MODE>      // 0: FIX pass (next candidate for `a`, e* candidate)   1: SUM pass (fingerprint of {t_H <= e*})
-__global__ void __launch_bounds__(GEN_THREADS) k_mixed_pass(const MixArgs m) {
-    __shared__ SubjDesc sd[STAGE];
-    __shared__ SubjWalk sw[STAGE];
-    __shared__ const uint16_t* s_old[STAGE];
-    const ApplyArgs& a = m.ap;
-    const int t = threadIdx.x, chunk = blockIdx.y;
-    const int64_t r = (int64_t)blockIdx.x * GEN_THREADS + t;
-    const uint32_t RM = (1u << a.K) - 1u;
-    const int L = a.L, H = a.H;
-    const uint32_t fl = r < a.R ? m.mx_fl[r] : 0u;
-    const bool on = MODE == 0 ? ((fl & MX_ON) && !(fl & MX_DONE)) : ((fl & MX_DONE) && (fl & MX_HAS_E));
-    if (!__syncthreads_or(on ? 1 : 0)) return;
-    const uint64_t ref = on ? (MODE == 0 ? m.mx_a[r] : m.estar[r]) : 0ull;
-    const uint64_t rs = splitmix64(a.dl.perm_seed + (uint64_t)(a.rbegin + r));
-    const int s0 = chunk * a.chunk, s1 = min(a.Sb, s0 + a.chunk);
-    uint64_t cand = T64_NONE, emax = 0, h1 = 0, h2 = 0;
-    bool neg = false, has_e = false;
-    int cnt = 0;
-    for (int base = s0; base < s1; base += STAGE) {
-        const int n = min(STAGE, s1 - base);
-        __syncthreads();
-        if (t < n) {
-            const SubjDesc d = a.desc[base + t];
-            sd[t] = d;
-            const bool fresh = d.slot >= a.S_before;
-            s_old[t] = fresh ? nullptr : a.masks + ((size_t)d.slot * 2 + a.cur[d.slot]) * a.Rpad;   // pre-batch row (not flipped yet)
-            if (!fresh && m.uniform) sw[t] = a.walk[base + t];
-        }
-        __syncthreads();
-        if (!on) continue;
-        for (int i = 0; i < n; ++i) {
-            const SubjDesc& d = sd[i];
-            const uint32_t st = s_old[i] ? s_old[i][r] : 0u;
-            const IVisit v = interval_visit(a, m.uniform, st & RM, d, &sw[i], r, rs);
-            if (MODE == 0) {
-                if (!v.crossH) continue;                                  // never closes, or never in the band
-                const bool starts_in = v.c0 >= L && v.c0 < H;
-                if (v.tH > ref) { if (starts_in) neg = true; else if (v.tL < cand) cand = v.tL; }
-                else if (!has_e || v.tH > emax) { emax = v.tH; has_e = true; }
-            } else {
-                if (v.crossH && v.tH <= ref) { h1 += d.mix1; h2 += d.mix2; ++cnt; }
-            }
-        }
-    }
-    if (!on) return;
-    if (MODE == 0) {
-        if (neg) atomicOr(&m.mx_fl[r], MX_NEG);
-        if (cand != T64_NONE) atomicMin((unsigned long long*)&m.mx_cand[r], (unsigned long long)cand);
-        if (has_e) { atomicMax((unsigned long long*)&m.mx_emax[r], (unsigned long long)emax); atomicOr(&m.mx_fl[r], MX_HAS_E); }
-    } else if (cnt) {
-        atomicAdd(&m.mx_e1[r], (unsigned long long)h1); atomicAdd(&m.mx_e2[r], (unsigned long long)h2); atomicAdd(&m.mx_ec[r], cnt);
-    }
-}
-
-__global__ void k_mixed_update(int64_t R, uint32_t* __restrict__ mx_fl, uint64_t* __restrict__ mx_a, uint64_t* __restrict__ mx_cand,
-                               uint64_t* __restrict__ mx_emax, uint64_t* __restrict__ estar, int32_t* __restrict__ changed) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    const uint32_t fl = mx_fl[r];
-    if (!(fl & MX_ON) || (fl & MX_DONE)) return;
-    if (fl & MX_NEG) { mx_fl[r] = 0; return; }              // covered since before the batch: nothing was emitted
-    const uint64_t c = mx_cand[r];
-    if (c < mx_a[r]) {                                       // the component grows leftwards: another pass
-        mx_a[r] = c; mx_cand[r] = T64_NONE; mx_emax[r] = 0; mx_fl[r] = fl & ~MX_HAS_E;
-        atomicAdd(changed, 1);
-    } else if (fl & MX_HAS_E) {
-        estar[r] = mx_emax[r];
-        mx_fl[r] = fl | MX_DONE;
-    } else {
-        mx_fl[r] = 0;                                        // no closing moment before the component: nothing emitted
-    }
-}
-
-struct MixCommitArgs {
-    int64_t R;
-    const uint32_t* mx_fl;
-    const uint64_t* mx_p1;
-    const uint64_t* mx_p2;
-    const int32_t* mx_pc;
-    unsigned long long* mx_e1;
-    unsigned long long* mx_e2;
-    int32_t* mx_ec;
-    uint32_t* rflags;
-    uint64_t* pend_h1;
-    uint64_t* pend_h2;
-    int32_t* pend_cnt;
-    uint64_t* out_h1;
-    uint64_t* out_h2;
-    int32_t* out_len;
+struct PassSmem {
+    SubjDesc sd[STAGE];
+    SubjWalk sw[STAGE];
+    const uint16_t* s_old[STAGE];
 };
 
-__global__ void k_mixed_commit(const MixCommitArgs a) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.R) return;
-    const uint32_t fl = a.mx_fl[r];
-    if (!((fl & MX_DONE) && (fl & MX_HAS_E))) return;
-    // what left explicitly = everything pending before the batch + the batch subjects that closed by e*
-    const uint64_t o1 = a.mx_p1[r] + a.mx_e1[r], o2 = a.mx_p2[r] + a.mx_e2[r];
-    const int32_t oc = a.mx_pc[r] + a.mx_ec[r];
-    a.out_h1[r] = o1; a.out_h2[r] = o2; a.out_len[r] = oc;
-    a.pend_h1[r] -= o1; a.pend_h2[r] -= o2; a.pend_cnt[r] -= oc;
-    a.mx_e1[r] = 0; a.mx_e2[r] = 0; a.mx_ec[r] = 0;
-    a.rflags[r] = (a.rflags[r] | RF_ANNOUNCED | RF_ANN_NOW | RF_MIXED_EMIT) & ~RF_RULE_GE_H;
+// MODE 0: FIX pass (next candidate for `a`, e* candidate)   1: SUM pass (fingerprint of {t_H <= e*})
+// MODE 2: MOMENT pass (min t_H over H-crossers -> mx_cand, min t_L over subjects left in the band -> mx_a)
+template <int MODE>
+__device__ __noinline__ void mixed_pass(const ResolveArgs& m, PassSmem& sm, const int Sb, const int S_before) {
+    const ApplyArgs& a = m.ap;
+    const int t = threadIdx.x;
+    const uint32_t RM = (1u << a.K) - 1u;
+    const int L = a.L, H = a.H;
+    const int rblocks = (int)(a.Rpad / GEN_THREADS);
+    int mchunks = max(1, min((Sb + STAGE - 1) / STAGE, (2 * (int)gridDim.x + rblocks - 1) / rblocks));
+    const int mchunk = max(1, (Sb + mchunks - 1) / mchunks);
+    mchunks = (Sb + mchunk - 1) / mchunk;
+    const int64_t items = (int64_t)rblocks * mchunks;
+    for (int64_t wi = blockIdx.x; wi < items; wi += gridDim.x) {
+        const int rb = (int)(wi % rblocks), chunk = (int)(wi / rblocks);
+        const int64_t r = (int64_t)rb * GEN_THREADS + t;
+        const uint32_t fl = r < a.R ? m.mx_fl[r] : 0u;
+        const bool on = MODE == 0 ? ((fl & MX_ON) && !(fl & MX_DONE)) : MODE == 1 ? ((fl & MX_DONE) && (fl & MX_HAS_E)) : ((fl & MX_TIME) != 0);
+        if (!__syncthreads_or(on ? 1 : 0)) continue;
+        const uint64_t ref = on ? (MODE == 0 ? m.mx_a[r] : MODE == 1 ? m.estar[r] : 0ull) : 0ull;
+        const uint64_t rs = splitmix64(a.dl.perm_seed + (uint64_t)(a.rbegin + r));
+        const int s0 = chunk * mchunk, s1 = min(Sb, s0 + mchunk);
+        uint64_t cand = T64_NONE, emax = 0, h1 = 0, h2 = 0, mTH = T64_NONE, mTL = T64_NONE;
+        bool neg = false, has_e = false;
+        int cnt = 0;
+        for (int base = s0; base < s1; base += STAGE) {
+            const int n = min(STAGE, s1 - base);
+            __syncthreads();
+            if (t < n) {
+                const SubjDesc d = a.desc[base + t];
+                sm.sd[t] = d;
+                const bool fresh = d.slot >= S_before;
+                sm.s_old[t] = fresh ? nullptr : a.masks + ((size_t)d.slot * 2 + a.cur[d.slot]) * a.Rpad;   // pre-batch row (not flipped yet)
+                if (!fresh && m.uniform) sm.sw[t] = a.walk[base + t];
+            }
+            __syncthreads();
+            if (!on) continue;
+            for (int i = 0; i < n; ++i) {
+                const SubjDesc& d = sm.sd[i];
+                const uint32_t st = sm.s_old[i] ? sm.s_old[i][r] : 0u;
+                const IVisit v = interval_visit(a, m.uniform, st & RM, d, &sm.sw[i], r, rs);
+                if (MODE == 0) {
+                    if (!v.crossH) continue;                                  // never closes, or never in the band
+                    const bool starts_in = v.c0 >= L && v.c0 < H;
+                    if (v.tH > ref) { if (starts_in) neg = true; else if (v.tL < cand) cand = v.tL; }
+                    else if (!has_e || v.tH > emax) { emax = v.tH; has_e = true; }
+                } else if (MODE == 1) {
+                    if (v.crossH && v.tH <= ref) { h1 += d.mix1; h2 += d.mix2; ++cnt; }
+                } else {
+                    if (v.crossH && v.tH < mTH) mTH = v.tH;
+                    if (v.crossL && v.c1 < H && v.tL < mTL) mTL = v.tL;
+                }
+            }
+        }
+        if (!on) continue;
+        if (MODE == 0) {
+            if (neg) atomicOr(&m.mx_fl[r], MX_NEG);
+            if (cand != T64_NONE) atomicMin((unsigned long long*)&m.mx_cand[r], (unsigned long long)cand);
+            if (has_e) { atomicMax((unsigned long long*)&m.mx_emax[r], (unsigned long long)emax); atomicOr(&m.mx_fl[r], MX_HAS_E); }
+        } else if (MODE == 1) {
+            if (cnt) { atomicAdd(&m.mx_e1[r], (unsigned long long)h1); atomicAdd(&m.mx_e2[r], (unsigned long long)h2); atomicAdd(&m.mx_ec[r], cnt); }
+        } else {
+            if (mTH != T64_NONE) atomicMin((unsigned long long*)&m.mx_cand[r], (unsigned long long)mTH);
+            if (mTL != T64_NONE) atomicMin((unsigned long long*)&m.mx_a[r], (unsigned long long)mTL);
+        }
+    }
+}
+
+// after the MOMENT pass: an unresolved subject entered the band before the first H-crossing -> nothing was emitted; else MIXED
+__device__ void phase_classify_moments(const ResolveArgs& a, int32_t* s_red) {
+    int32_t my_mixed = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.ap.R; r += (int64_t)gridDim.x * blockDim.x) {
+        if (!(a.mx_fl[r] & MX_TIME)) continue;
+        const uint64_t tl = a.mx_a[r], th = a.mx_cand[r];
+        if (tl < th) { a.mx_fl[r] = 0; continue; }
+        a.mx_fl[r] = MX_ON; a.mx_cand[r] = T64_NONE; a.mx_emax[r] = 0;
+        ++my_mixed;
+    }
+    const int32_t bm = block_sum_i32(my_mixed, s_red);
+    if (threadIdx.x == 0 && bm) atomicAdd(&a.bc->n_mixed, bm);
+}
+
+__device__ void phase_mixed_update(const ResolveArgs& a, int32_t* changed, int32_t* s_red) {
+    int32_t my = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.ap.R; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t fl = a.mx_fl[r];
+        if (!(fl & MX_ON) || (fl & MX_DONE)) continue;
+        if (fl & MX_NEG) { a.mx_fl[r] = 0; continue; }           // covered since before the batch: nothing was emitted
+        const uint64_t c = a.mx_cand[r];
+        if (c < a.mx_a[r]) {                                      // the component grows leftwards: another pass
+            a.mx_a[r] = c; a.mx_cand[r] = T64_NONE; a.mx_emax[r] = 0; a.mx_fl[r] = fl & ~MX_HAS_E;
+            ++my;
+        } else if (fl & MX_HAS_E) {
+            a.estar[r] = a.mx_emax[r];
+            a.mx_fl[r] = fl | MX_DONE;
+        } else {
+            a.mx_fl[r] = 0;                                       // no closing moment before the component: nothing emitted
+        }
+    }
+    const int32_t b = block_sum_i32(my, s_red);
+    if (threadIdx.x == 0 && b) atomicAdd(changed, b);
+}
+
+__device__ void phase_mixed_commit(const ResolveArgs& a) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.ap.R; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t fl = a.mx_fl[r];
+        if (!((fl & MX_DONE) && (fl & MX_HAS_E))) continue;
+        // what left explicitly = everything pending before the batch + the batch subjects that closed by e*
+        const uint64_t o1 = a.mx_p1[r] + a.mx_e1[r], o2 = a.mx_p2[r] + a.mx_e2[r];
+        const int32_t oc = a.mx_pc[r] + a.mx_ec[r];
+        a.out_h1[r] = o1; a.out_h2[r] = o2; a.out_len[r] = oc;
+        a.pend_h1[r] -= o1; a.pend_h2[r] -= o2; a.pend_cnt[r] -= oc;
+        a.mx_e1[r] = 0; a.mx_e2[r] = 0; a.mx_ec[r] = 0;
+        a.rflags[r] = (a.rflags[r] | RF_ANNOUNCED | RF_ANN_NOW | RF_MIXED_EMIT) & ~RF_RULE_GE_H;
+    }
 }
 
 // Did subject slot `s` leave in an explicit proposal of the batch in flight, for an RF_MIXED_EMIT receiver?  Rows have been
 // flipped: the pre-batch row is the non-current one.
-struct EmitCtx {
-    ApplyArgs ap;
-    const int32_t* touch;
-    const int32_t* batch_index;
-    int32_t serial;
-    const uint64_t* estar;
-    int uniform;
-};
-
-__device__ __forceinline__ bool emitted_in_batch(const EmitCtx& e, int32_t s, int64_t r, uint32_t w_new, uint64_t rs) {
+__device__ __noinline__ bool emitted_in_batch(const ResolveArgs& e, int32_t s, int64_t r, uint32_t w_new, uint64_t rs) {
     const ApplyArgs& a = e.ap;
     const uint32_t RM = (1u << a.K) - 1u;
     // untouched by the batch: it left (with the first explicit proposal) iff it was pending, i.e. at >= H and NOT raised there by
-    // this batch's invalidation pass (bit 14, cleared by k_inval_unmark once the batch is done)
+    // this batch's invalidation pass (bit 14, cleared by the unmark phase once the batch is done)
     if (e.touch[s] != e.serial) return __popc(w_new & RM) >= a.H && !(w_new & CD_BIT_CALL);
     const int b = e.batch_index[s];
     const SubjDesc d = a.desc[b];
-    const uint32_t old = s >= a.S_before ? 0u : (a.masks + ((size_t)s * 2 + (a.cur[s] ^ 1)) * a.Rpad)[r];
+    const uint32_t old = s >= a.bc->S_before ? 0u : (a.masks + ((size_t)s * 2 + (a.cur[s] ^ 1)) * a.Rpad)[r];
     if (__popc(old & RM) >= a.H) return true;                              // pending before the batch
-    const SubjWalk* w = e.uniform ? &a.walk[b] : nullptr;
     SubjWalk wl;
-    if (e.uniform) { wl = *w; }
+    if (e.uniform) wl = a.walk[b];
     const IVisit v = interval_visit(a, e.uniform, old & RM, d, &wl, r, rs);
     return v.crossH && v.tH <= e.estar[r];
 }
 
-// RF_MIXED_EMIT receivers whose invalidation pass did not emit announce only the explicit part: give it bit 15 so that
-// rapid_cd_get_proposal can list it later (the pre-batch rows are gone by then).
-__global__ void __launch_bounds__(GEN_THREADS) k_mixed_mark(const EmitCtx e, int32_t S, int slots_per_block, const uint32_t* __restrict__ rflags) {
-    const ApplyArgs& a = e.ap;
-    const int64_t r = (int64_t)blockIdx.x * GEN_THREADS + threadIdx.x;
-    if (r >= a.R) return;
-    const uint32_t f = rflags[r];
-    if (!(f & RF_MIXED_EMIT) || !(f & RF_ANN_NOW) || (f & RF_RULE_GE_H)) return;
-    const uint64_t rs = splitmix64(a.dl.perm_seed + (uint64_t)(a.rbegin + r));
-    const int32_t s0 = blockIdx.y * slots_per_block, s1 = min(S, s0 + slots_per_block);
-    for (int32_t s = s0; s < s1; ++s) {
-        uint16_t* p = a.masks + ((size_t)s * 2 + a.cur[s]) * a.Rpad + r;
-        const uint32_t w = *p;
-        if (!(w & CD_BIT_EMIT) && emitted_in_batch(e, s, r, w, rs)) *p = (uint16_t)(w | CD_BIT_EMIT);
-    }
-}
-
-__global__ void k_flip(int Sb, const SubjDesc* __restrict__ desc, uint8_t* __restrict__ cur) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < Sb) cur[desc[b].slot] ^= 1;
-}
-
 // ------------------------------------------------------------------------------------------------------------------
-// invalidateFailingEdges (MultiNodeCutDetector.java:137-164) over the (tile, subject) pairs known to hold an
-// unstable subject: implicit reports from observers that are themselves in proposal U preProposal.
+// invalidateFailingEdges (MultiNodeCutDetector.java:137-164) + the receiver's closing bookkeeping, per 256-receiver unit.
+// The work list names the subjects that sit in the unstable band of some receiver AND have an observer that is itself a
+// subject; a unit walks the list (skipping subjects not in the band anywhere in its 1024-receiver tile), ORs in the implicit
+// reports from observers that are themselves in proposal U preProposal, and — since everything a receiver needs is now in
+// the thread's registers — finishes the receiver right away: emissions of the pass, announced flags, outputs.
 // ------------------------------------------------------------------------------------------------------------------
-struct InvArgs {
-    uint16_t* masks;
-    const uint8_t* cur;
-    size_t Rpad;
-    int K, H, L;
-    int64_t R;
-    const uint32_t* rflags;
-    const int2* pre_pairs;
-    const int32_t* pre_count;
-    int32_t pre_cap;
-    const int32_t* slot_subject;
-    const int32_t* slot_of;
-    const int32_t* obs;
-    int32_t* k3_res;
-    unsigned long long* k3_h1;
-    unsigned long long* k3_h2;
-    int mixed;                 // some receiver announced through the interval analysis in this batch
-    EmitCtx ec;                // (valid when mixed)
+constexpr int INV_STAGE = 32;
+struct InvSmem {
+    uint16_t* row[INV_STAGE];
+    const uint16_t* orow[INV_STAGE][MAXK];
+    int32_t slot[INV_STAGE];
+    int32_t so[INV_STAGE][MAXK];
+    uint64_t mix1[INV_STAGE], mix2[INV_STAGE];
+    uint8_t flag[INV_STAGE];
 };
 
-__global__ void __launch_bounds__(256) k_inval_pairs(const InvArgs a) {
-    __shared__ int32_t so[MAXK];
+__device__ void phase_inval_finalize2(const ResolveArgs& e, int mixed, InvSmem& sm, int32_t* s_red) {
+    const ApplyArgs& a = e.ap;
     const uint32_t RM = (1u << a.K) - 1u;
-    const int n = min(*a.pre_count, a.pre_cap);
-    for (int e = blockIdx.x; e < n; e += gridDim.x) {
-        const int2 pr = a.pre_pairs[e];
-        const int32_t slot = pr.y, subject = a.slot_subject[slot];
-        __syncthreads();
-        if (threadIdx.x < a.K) {
-            const int32_t o = a.obs[(size_t)subject * a.K + threadIdx.x];
-            so[threadIdx.x] = o < 0 ? -1 : a.slot_of[o];
+    const int t = threadIdx.x;
+    const int n_list = min(*(volatile int32_t*)a.wl.count, a.wl.cap);
+    const int64_t units = (int64_t)(a.Rpad / GEN_THREADS);
+    int32_t my_inval = 0;
+    for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const int64_t r = u * GEN_THREADS + t;
+        const int tile = (int)(r / TILE_R);
+        uint32_t flags = r < a.R ? e.rflags[r] : 0u;
+        const bool k3 = (flags & RF_ACTIVE) && (flags & RF_K3);
+        int32_t res = 0;
+        uint64_t kh1 = 0, kh2 = 0;
+        if (n_list > 0 && __syncthreads_or(k3 ? 1 : 0)) {
+            const bool mx = mixed && (flags & RF_MIXED_EMIT);
+            const uint64_t rs = mx ? splitmix64(a.dl.perm_seed + (uint64_t)(a.rbegin + r)) : 0ull;
+            for (int base = 0; base < n_list; base += INV_STAGE) {
+                const int n = min(INV_STAGE, n_list - base);
+                __syncthreads();
+                if (t < n) {
+                    const int32_t sl = a.wl.slots[base + t];
+                    sm.slot[t] = sl;
+                    sm.flag[t] = a.wl.in_tile[(size_t)sl * a.wl.n_tiles + tile];
+                    sm.row[t] = a.masks + ((size_t)sl * 2 + a.cur[sl]) * a.Rpad;
+                    const int32_t subject = a.slot_subject[sl];
+                    sm.mix1[t] = fp_mix1(subject); sm.mix2[t] = fp_mix2(subject);
+                }
+                for (int q = t; q < n * a.K; q += GEN_THREADS) {
+                    const int i = q / a.K, k = q - i * a.K;
+                    const int32_t s2 = a.wl.so_tab[(size_t)a.wl.slots[base + i] * SO_STRIDE + k];
+                    sm.so[i][k] = s2;
+                    sm.orow[i][k] = s2 < 0 ? nullptr : a.masks + ((size_t)s2 * 2 + a.cur[s2]) * a.Rpad;
+                }
+                __syncthreads();
+                if (!k3) continue;
+                for (int i0 = 0; i0 < n; i0 += 4) {
+                    // four independent row loads in flight, then the (rare) observer rows
+                    uint32_t w4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) w4[j] = (i0 + j < n && sm.flag[i0 + j]) ? sm.row[i0 + j][r] : 0xFFFFu;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = i0 + j;
+                        if (i >= n || !sm.flag[i]) continue;
+                        const uint32_t w = w4[j];
+                        const int c = __popc(w & RM);
+                        if (c < a.L || c >= a.H) continue;                  // not in this receiver's preProposal
+                        uint32_t implicit = 0;
+                        for (int k = 0; k < a.K; ++k) {
+                            if ((w >> k) & 1u) continue;
+                            const uint16_t* orow = sm.orow[i][k];
+                            if (!orow) continue;
+                            const uint32_t wo = orow[r];
+                            if ((wo & CD_BIT_EMIT) || __popc(wo & RM) < a.L) continue;   // observer not in proposal U preProposal
+                            // a receiver that already announced explicit proposals in this batch: those subjects left `proposal`.
+                            // (bit 14 = raised to >= H by this very pass, i.e. it was in the band at entry, not pending)
+                            if (mx && emitted_in_batch(e, sm.so[i][k], r, wo, rs)) continue;
+                            implicit |= 1u << k;
+                        }
+                        if (!implicit) continue;
+                        uint32_t nw = w | implicit;
+                        const bool raised = __popc(nw & RM) >= a.H;
+                        if (raised && mixed) nw |= CD_BIT_CALL;            // transient marker, cleared by the unmark phase
+                        sm.row[i][r] = (uint16_t)nw;
+                        if (raised) { ++res; kh1 += sm.mix1[i]; kh2 += sm.mix2[i]; }   // moved preProposal -> proposal
+                    }
+                }
+            }
         }
-        __syncthreads();
-        uint16_t* row = a.masks + ((size_t)slot * 2 + a.cur[slot]) * a.Rpad;
-        for (int q = 0; q < TILE_R / 256; ++q) {
-            const int64_t r = (int64_t)pr.x * TILE_R + q * 256 + threadIdx.x;
-            if (r >= a.R) continue;
-            const uint32_t rf = a.rflags[r];
-            if (!(rf & RF_K3)) continue;
-            const bool mx = a.mixed && (rf & RF_MIXED_EMIT);
-            const uint64_t rs = mx ? splitmix64(a.ec.ap.dl.perm_seed + (uint64_t)(a.ec.ap.rbegin + r)) : 0ull;
-            const uint32_t w = row[r];
-            const int c = __popc(w & RM);
-            if (c < a.L || c >= a.H) continue;                      // not in this receiver's preProposal
-            uint32_t implicit = 0;
-            for (int k = 0; k < a.K; ++k) {
-                if ((w >> k) & 1u) continue;
-                const int32_t s2 = so[k];
-                if (s2 < 0) continue;
-                const uint32_t wo = (a.masks + ((size_t)s2 * 2 + a.cur[s2]) * a.Rpad)[r];
-                if ((wo & CD_BIT_EMIT) || __popc(wo & RM) < a.L) continue;            // observer not in proposal U preProposal
-                // a receiver that already announced explicit proposals in this batch: those subjects left `proposal`.
-                // (bit 14 = raised to >= H by this very pass, i.e. it was in the band at entry, not pending)
-                if (mx && emitted_in_batch(a.ec, s2, r, wo, rs)) continue;
-                implicit |= 1u << k;
+        if (r >= a.R || !(flags & RF_ACTIVE)) continue;              // inactive receivers were settled by finalize1
+        if (res > 0) {
+            const int32_t npre = e.n_pre[r] - res;
+            uint64_t ph1 = e.pend_h1[r] + kh1, ph2 = e.pend_h2[r] + kh2;
+            int32_t pc = e.pend_cnt[r] + res;
+            if (npre == 0) {
+                // the last unstable subject resolved inside invalidateFailingEdges: proposal (all of it) is emitted
+                e.out_h1[r] += ph1; e.out_h2[r] += ph2; e.out_len[r] += pc;
+                ph1 = 0; ph2 = 0; pc = 0;
+                flags |= RF_ANNOUNCED | RF_ANN_NOW | RF_RULE_GE_H;
             }
-            if (!implicit) continue;
-            uint32_t nw = w | implicit;
-            const bool raised = __popc(nw & RM) >= a.H;
-            if (raised && a.mixed) nw |= CD_BIT_CALL;                // transient marker, cleared by k_inval_unmark
-            row[r] = (uint16_t)nw;
-            if (raised) {                                            // moved preProposal -> proposal
-                atomicAdd(&a.k3_res[r], 1);
-                atomicAdd(&a.k3_h1[r], (unsigned long long)fp_mix1(subject));
-                atomicAdd(&a.k3_h2[r], (unsigned long long)fp_mix2(subject));
-            }
+            e.n_pre[r] = npre;
+            e.pend_h1[r] = ph1; e.pend_h2[r] = ph2; e.pend_cnt[r] = pc;
+        }
+        flags &= ~RF_K3;
+        if ((flags & RF_MIXED_EMIT) && (flags & RF_ANN_NOW) && !(flags & RF_RULE_GE_H)) ++my_inval;   // needs bit-15 marks
+        e.rflags[r] = flags;
+        e.out_ann[r] = (flags & RF_ANNOUNCED) ? 1 : 0;
+    }
+    if (mixed) {
+        const int32_t b = block_sum_i32(my_inval, s_red);
+        if (t == 0 && b) atomicAdd(&e.bc->n_inval, b);
+    }
+}
+
+// RF_MIXED_EMIT receivers whose invalidation pass did not emit announce only the explicit part: give it bit 15 so that
+// rapid_cd_get_proposal can list it later (the pre-batch rows are gone by then).
+__device__ __noinline__ void phase_mixed_mark(const ResolveArgs& e, int32_t S) {
+    const ApplyArgs& a = e.ap;
+    const int spb = 64;
+    const int rblocks = (int)(a.Rpad / GEN_THREADS), sblocks = (S + spb - 1) / spb;
+    const int64_t items = (int64_t)rblocks * sblocks;
+    for (int64_t wi = blockIdx.x; wi < items; wi += gridDim.x) {
+        const int64_t r = (wi % rblocks) * GEN_THREADS + threadIdx.x;
+        if (r >= a.R) continue;
+        const uint32_t f = e.rflags[r];
+        if (!(f & RF_MIXED_EMIT) || !(f & RF_ANN_NOW) || (f & RF_RULE_GE_H)) continue;
+        const uint64_t rs = splitmix64(a.dl.perm_seed + (uint64_t)(a.rbegin + r));
+        const int32_t s0 = (int32_t)(wi / rblocks) * spb, s1 = min(S, s0 + spb);
+        for (int32_t s = s0; s < s1; ++s) {
+            uint16_t* p = a.masks + ((size_t)s * 2 + a.cur[s]) * a.Rpad + r;
+            const uint32_t w = *p;
+            if (!(w & CD_BIT_EMIT) && emitted_in_batch(e, s, r, w, rs)) *p = (uint16_t)(w | CD_BIT_EMIT);
         }
     }
 }
 
-__global__ void __launch_bounds__(256) k_inval_unmark(const InvArgs a) {
-    const int n = min(*a.pre_count, a.pre_cap);
-    for (int e = blockIdx.x; e < n; e += gridDim.x) {
-        const int2 pr = a.pre_pairs[e];
-        uint16_t* row = a.masks + ((size_t)pr.y * 2 + a.cur[pr.y]) * a.Rpad;
-        for (int q = 0; q < TILE_R / 256; ++q) {
-            const int64_t r = (int64_t)pr.x * TILE_R + q * 256 + threadIdx.x;
+__device__ void phase_inval_unmark(const ResolveArgs& e) {
+    const ApplyArgs& a = e.ap;
+    const int n_list = min(*(volatile int32_t*)a.wl.count, a.wl.cap);
+    const int64_t items = (int64_t)n_list * a.wl.n_tiles;
+    for (int64_t p = blockIdx.x; p < items; p += gridDim.x) {
+        const int32_t sl = a.wl.slots[p / a.wl.n_tiles];
+        const int tile = (int)(p % a.wl.n_tiles);
+        if (!a.wl.in_tile[(size_t)sl * a.wl.n_tiles + tile]) continue;
+        uint16_t* row = a.masks + ((size_t)sl * 2 + a.cur[sl]) * a.Rpad;
+        for (int q = 0; q < TILE_R / GEN_THREADS; ++q) {
+            const int64_t r = (int64_t)tile * TILE_R + q * GEN_THREADS + threadIdx.x;
             if (r >= a.R) continue;
             const uint32_t w = row[r];
             if (w & CD_BIT_CALL) row[r] = (uint16_t)(w & ~CD_BIT_CALL);
@@ -918,48 +1037,100 @@ __global__ void __launch_bounds__(256) k_inval_unmark(const InvArgs a) {
     }
 }
 
-struct Fin2Args {
-    int64_t R;
-    int32_t* n_pre;
-    uint32_t* rflags;
-    uint64_t* pend_h1;
-    uint64_t* pend_h2;
-    int32_t* pend_cnt;
-    uint64_t* out_h1;
-    uint64_t* out_h2;
-    int32_t* out_len;
-    uint8_t* out_ann;
-    int32_t* k3_res;
-    unsigned long long* k3_h1;
-    unsigned long long* k3_h2;
-    BatchCounts* bc;
-};
-
-__global__ void k_finalize2(const Fin2Args a) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.R) return;
-    uint32_t flags = a.rflags[r];
-    if (flags & RF_K3) {
-        const int32_t res = a.k3_res[r];
-        if (res > 0) {
-            const int32_t npre = a.n_pre[r] - res;
-            uint64_t ph1 = a.pend_h1[r] + a.k3_h1[r], ph2 = a.pend_h2[r] + a.k3_h2[r];
-            int32_t pc = a.pend_cnt[r] + res;
-            if (npre == 0) {
-                // the last unstable subject resolved inside invalidateFailingEdges: proposal (all of it) is emitted
-                a.out_h1[r] += ph1; a.out_h2[r] += ph2; a.out_len[r] += pc;
-                ph1 = 0; ph2 = 0; pc = 0;
-                flags |= RF_ANNOUNCED | RF_ANN_NOW | RF_RULE_GE_H;
-            }
-            a.n_pre[r] = npre;
-            a.pend_h1[r] = ph1; a.pend_h2[r] = ph2; a.pend_cnt[r] = pc;
-            a.k3_res[r] = 0; a.k3_h1[r] = 0; a.k3_h2[r] = 0;
-        }
+// the last block to get here copies the counters for the host and re-arms the per-batch fields for the next batch
+__device__ void resolve_tail(const ResolveArgs& a, int32_t serial) {
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&a.bc->ticket, 1) == (int)gridDim.x - 1;
     }
-    flags &= ~RF_K3;
-    if ((flags & RF_MIXED_EMIT) && (flags & RF_ANN_NOW) && !(flags & RF_RULE_GE_H)) atomicAdd(&a.bc->n_inval, 1);   // needs bit-15 marks
-    a.rflags[r] = flags;
-    a.out_ann[r] = (flags & RF_ANNOUNCED) ? 1 : 0;
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    volatile BatchCounts* b = a.bc;
+    BatchCounts c;
+    c.n_slots = b->n_slots; c.n_valid = b->n_valid; c.n_batch_subj = b->n_batch_subj; c.any_down = b->any_down;
+    c.bad_ring = b->bad_ring; c.bad_dst = b->bad_dst; c.n_mixed = b->n_mixed; c.n_inval = b->n_inval; c.S_before = b->S_before;
+    c.overflow = b->overflow; c.need_slots = b->need_slots; c.n_times = b->n_times; c.mixed_iters = b->mixed_iters;
+    c.n_pairs = *(volatile int32_t*)a.ap.wl.count; c.ticket = 0; c.serial = serial;
+    // errors stay latched until the host has collected them (an asynchronous caller may have several batches in flight)
+    c.sticky_bad_ring = b->sticky_bad_ring | (c.bad_ring >= 0 ? 1 : 0);
+    c.sticky_bad_dst = b->sticky_bad_dst | (c.bad_dst >= 0 ? 1 : 0);
+    c.sticky_overflow = b->sticky_overflow | (c.overflow ? 1 : 0);
+    b->sticky_bad_ring = c.sticky_bad_ring; b->sticky_bad_dst = c.sticky_bad_dst; b->sticky_overflow = c.sticky_overflow;
+    *a.snap = c;
+    b->n_valid = 0; b->n_batch_subj = 0; b->any_down = 0; b->bad_ring = -1; b->bad_dst = -1; b->n_mixed = 0; b->n_inval = 0;
+    b->overflow = 0; b->need_slots = 0; b->n_times = 0; b->mixed_iters = 0; b->ticket = 0;
+}
+
+// ---- the four launches after the apply kernel (no host round trip between them) ---------------------------------------------
+__global__ void __launch_bounds__(GEN_THREADS) k_finalize1(const ResolveArgs* __restrict__ ga) {
+    const ResolveArgs& a = *ga;
+    __shared__ int32_t s_red[GEN_THREADS / 32];
+    if (a.bc->overflow) return;                                         // rolled back by k_prepare: nothing to resolve
+    phase_finalize1(a, s_red);
+}
+
+// cooperative, ALWAYS launched: with nothing flagged it just flips the rows (a few microseconds)
+__global__ void __launch_bounds__(GEN_THREADS, 2) k_mixed_flip(const ResolveArgs* __restrict__ ga) {
+    const ResolveArgs& a = *ga;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ PassSmem sm;
+    __shared__ int32_t s_red[GEN_THREADS / 32];
+    if (a.bc->overflow) return;
+    const int Sb = a.bc->n_batch_subj, S_before = a.bc->S_before;
+    if (a.counts_only && a.bc->n_times > 0 && Sb > 0) {
+        mixed_pass<2>(a, sm, Sb, S_before);
+        grid.sync();
+        phase_classify_moments(a, s_red);
+        grid.sync();
+    }
+    const int mixed = *(volatile int32_t*)&a.bc->n_mixed > 0 ? 1 : 0;
+    if (mixed && Sb > 0) {
+        int it = 0;
+        for (;; ++it) {
+            mixed_pass<0>(a, sm, Sb, S_before);
+            grid.sync();
+            if (blockIdx.x == 0 && threadIdx.x == 0) a.mx_changed[(it + 2) & 3] = 0;
+            phase_mixed_update(a, &a.mx_changed[it & 3], s_red);
+            grid.sync();
+            if (*(volatile int32_t*)&a.mx_changed[it & 3] == 0 || it > Sb + 1) break;
+        }
+        mixed_pass<1>(a, sm, Sb, S_before);
+        grid.sync();
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            a.mx_changed[0] = 0; a.mx_changed[1] = 0; a.mx_changed[2] = 0; a.mx_changed[3] = 0;
+            a.bc->mixed_iters = it + 1;
+        }
+        phase_mixed_commit(a);
+        grid.sync();
+    }
+    // flip: the rows the apply kernel wrote become current (the interval analysis above still needed the pre-batch rows)
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < Sb; b += gridDim.x * blockDim.x) a.cur_w[a.ap.desc[b].slot] ^= 1;
+}
+
+__global__ void __launch_bounds__(GEN_THREADS, 3) k_inval_finalize2(const ResolveArgs* __restrict__ ga) {
+    const ResolveArgs& a = *ga;
+    __shared__ InvSmem sm;
+    __shared__ int32_t s_red[GEN_THREADS / 32];
+    const int mixed = a.bc->n_mixed > 0 ? 1 : 0;
+    if (!a.bc->overflow) phase_inval_finalize2(a, mixed, sm, s_red);
+    if (!mixed) resolve_tail(a, a.serial);                               // else k_marks closes the batch
+}
+
+// cooperative, ALWAYS launched: returns at once unless some receiver went through the interval analysis
+__global__ void __launch_bounds__(GEN_THREADS, 2) k_marks(const ResolveArgs* __restrict__ ga) {
+    const ResolveArgs& a = *ga;
+    cg::grid_group grid = cg::this_grid();
+    if (a.bc->n_mixed <= 0) return;                                      // (k_inval_finalize2 closed the batch)
+    if (a.bc->n_inval > 0) {
+        // receivers that announce only the explicit part: persist it as bit 15 while the pre-batch rows still exist
+        phase_mixed_mark(a, a.bc->n_slots);
+        grid.sync();
+    }
+    phase_inval_unmark(a);                                              // only now: the marks above still needed bit 14
+    resolve_tail(a, a.serial);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -974,12 +1145,48 @@ void bucketed_destroy(CD* cd) {
     if (cd->bucketed_state) { delete static_cast<Bucketed*>(cd->bucketed_state); cd->bucketed_state = nullptr; }
 }
 
+static WorkList worklist(const Bucketed* b) {
+    WorkList wl;
+    wl.has_so = b->has_so.p; wl.so_tab = b->wl_so_tab.p; wl.in_tile = b->wl_in_tile.p; wl.listed = b->wl_listed.p;
+    wl.slots = b->wl_slots.p; wl.count = b->wl_count.p;
+    wl.cap = (int32_t)std::min<size_t>(b->in_list_slots, 0x7fffffff); wl.n_tiles = b->n_tiles;
+    return wl;
+}
+
+// the work-list arrays follow the handle's slot capacity (they only ever grow, with the contents kept)
+template <typename T>
+static int32_t grow_keep(DevBuf<T>& buf, size_t n_old, size_t n_new, cudaStream_t s) {
+    DevBuf<T> nb;
+    RAPID_CHECK(nb.reserve(std::max<size_t>(n_new, 1)));
+    RAPID_CUDA(cudaMemsetAsync(nb.p, 0, std::max<size_t>(n_new, 1) * sizeof(T), s));
+    if (n_old && buf.p) RAPID_CUDA(cudaMemcpyAsync(nb.p, buf.p, n_old * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    RAPID_CUDA(cudaStreamSynchronize(s));
+    std::swap(buf.p, nb.p); std::swap(buf.cap, nb.cap);
+    return RAPID_OK;
+}
+
+static int32_t ensure_pre_capacity(CD* cd, Bucketed* b) {
+    const size_t slots = cd->S_cap;
+    if (slots <= b->in_list_slots) return RAPID_OK;
+    const size_t o = b->in_list_slots, nt = (size_t)b->n_tiles;
+    RAPID_CHECK(grow_keep(b->wl_in_tile, o * nt, slots * nt, cd->stream));
+    RAPID_CHECK(grow_keep(b->wl_listed, o, slots, cd->stream));
+    RAPID_CHECK(grow_keep(b->wl_slots, o, slots, cd->stream));
+    RAPID_CHECK(grow_keep(b->wl_so_tab, o * SO_STRIDE, slots * SO_STRIDE, cd->stream));
+    RAPID_CHECK(grow_keep(b->has_so, o, slots, cd->stream));
+    b->in_list_slots = slots;
+    return RAPID_OK;
+}
+
 int32_t bucketed_prep_buffers(CD* cd, int64_t A, PrepOut* po) {
     Bucketed* b = state(cd);
+    b->n_tiles = (int)(cd->Rpad / TILE_R);
+    RAPID_CHECK(ensure_pre_capacity(cd, b));
     const size_t a = (size_t)std::max<int64_t>(A, 1);
     RAPID_CHECK(b->desc.reserve(a)); RAPID_CHECK(b->walk.reserve(a));
     RAPID_CHECK(b->sidx.reserve(a)); RAPID_CHECK(b->s_ring.reserve(a)); RAPID_CHECK(b->s_status.reserve(a));
-    const size_t slots = (size_t)std::min<int64_t>((int64_t)cd->S + A, std::max<int64_t>(cd->ntot_cap, 1));
+    // per-slot scratch: a batch can touch at most S_cap slots (a batch that needs more is rolled back on the device)
+    const size_t slots = std::max<size_t>(cd->S_cap, 1);
     RAPID_CHECK(b->batch_index.reserve(slots));
     RAPID_CHECK(b->seg_pos.reserve(slots));
     if (slots > b->seg_cnt.cap) {
@@ -988,99 +1195,98 @@ int32_t bucketed_prep_buffers(CD* cd, int64_t A, PrepOut* po) {
     }
     po->desc = b->desc.p; po->walk = b->walk.p; po->sidx = b->sidx.p; po->s_ring = b->s_ring.p; po->s_status = b->s_status.p;
     po->batch_index = b->batch_index.p; po->seg_cnt = b->seg_cnt.p; po->seg_pos = b->seg_pos.p;
+    po->wl = worklist(b);
     return RAPID_OK;
 }
 
-int32_t bucketed_pair_count(const CD* cd) {
-    if (!cd->bucketed_state) return 0;
-    const Bucketed* b = static_cast<const Bucketed*>(cd->bucketed_state);
-    int32_t n = 0;
-    if (b->pre_count.p) cudaMemcpy(&n, b->pre_count.p, sizeof(n), cudaMemcpyDeviceToHost);
-    return n;
-}
-
-__global__ void k_clear_pairs(const int2* __restrict__ pairs, int32_t* __restrict__ count, int32_t cap, int32_t* __restrict__ in_list,
-                              int n_tiles) {
-    const int n = min(*count, cap);
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        const int2 pr = pairs[e];
-        in_list[(size_t)pr.y * n_tiles + pr.x] = 0;
+// forget the work list: O(listed subjects x tiles), not O(slots x tiles)
+__global__ void k_clear_worklist(WorkList wl) {
+    const int n = min(*wl.count, wl.cap);
+    const int64_t items = (int64_t)n * wl.n_tiles;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < items; e += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t sl = wl.slots[e / wl.n_tiles];
+        const int tile = (int)(e % wl.n_tiles);
+        wl.in_tile[(size_t)sl * wl.n_tiles + tile] = 0;
+        if (tile == 0) wl.listed[sl] = 0;
     }
 }
-__global__ void k_zero_i32(int32_t* p) { *p = 0; }
+// a new configuration epoch: no slots, per-batch counters armed
+__global__ void k_reset_counts(BatchCounts* bc, BatchCounts* snap, int32_t* pre_count) {
+    BatchCounts c;
+    memset(&c, 0, sizeof(c));
+    c.bad_ring = -1; c.bad_dst = -1;
+    const int32_t sr = bc->sticky_bad_ring, sd = bc->sticky_bad_dst, so = bc->sticky_overflow;
+    c.sticky_bad_ring = sr; c.sticky_bad_dst = sd; c.sticky_overflow = so;       // errors not collected yet survive a clear()
+    *bc = c;
+    *snap = c;
+    *pre_count = 0;
+}
+__global__ void k_clear_sticky(BatchCounts* bc) { bc->sticky_bad_ring = 0; bc->sticky_bad_dst = 0; bc->sticky_overflow = 0; }
+
+int32_t bucketed_clear_sticky(CD* cd) {
+    k_clear_sticky<<<1, 1, 0, cd->stream>>>(cd->counts.p);
+    RAPID_KERNEL_CHECK();
+    return RAPID_OK;
+}
 
 int32_t bucketed_clear(CD* cd) {
     if (!cd->bucketed) return RAPID_OK;
     Bucketed* b = state(cd);
     b->n_tiles = (int)(cd->Rpad / TILE_R);
     cudaStream_t s = cd->stream;
-    if (!b->pre_count.p) {
-        RAPID_CHECK(b->pre_count.reserve(1));
-        RAPID_CUDA(cudaMemsetAsync(b->pre_count.p, 0, sizeof(int32_t), s));
+    if (!b->wl_count.p) {
+        RAPID_CHECK(b->wl_count.reserve(1));
+        RAPID_CUDA(cudaMemsetAsync(b->wl_count.p, 0, sizeof(int32_t), s));
+        RAPID_CHECK(b->mx_changed.reserve(4));
+        RAPID_CUDA(cudaMemsetAsync(b->mx_changed.p, 0, 4 * sizeof(int32_t), s));
     }
-    if (b->in_list.p && b->in_list_slots) {
-        // undo only the (tile, subject) pairs that were noted: O(#pairs), not O(slots x tiles)
-        const int32_t cap = (int32_t)std::min<size_t>(b->in_list_slots * (size_t)b->n_tiles, 0x7fffffff);
-        k_clear_pairs<<<64, 256, 0, s>>>(b->pre_pairs.p, b->pre_count.p, cap, b->in_list.p, b->n_tiles);
-        k_zero_i32<<<1, 1, 0, s>>>(b->pre_count.p);
+    if (b->in_list_slots) {
+        k_clear_worklist<<<128, 256, 0, s>>>(worklist(b));
         RAPID_KERNEL_CHECK();
     }
-    if (!b->k3_res.p) {      // zero once: k_finalize2 leaves them zero after every batch
-        RAPID_CHECK(b->k3_res.reserve(cd->Rpad));
-        RAPID_CHECK(b->k3_h1.reserve(cd->Rpad));
-        RAPID_CHECK(b->k3_h2.reserve(cd->Rpad));
-        RAPID_CUDA(cudaMemsetAsync(b->k3_res.p, 0, cd->Rpad * sizeof(int32_t), s));
-        RAPID_CUDA(cudaMemsetAsync(b->k3_h1.p, 0, cd->Rpad * sizeof(unsigned long long), s));
-        RAPID_CUDA(cudaMemsetAsync(b->k3_h2.p, 0, cd->Rpad * sizeof(unsigned long long), s));
-    }
+    k_reset_counts<<<1, 1, 0, s>>>(cd->counts.p, cd->counts_snap.p, b->wl_count.p);
+    RAPID_KERNEL_CHECK();
     return RAPID_OK;
 }
 
-static int32_t ensure_pre_capacity(CD* cd, Bucketed* b) {
-    const size_t slots = cd->S_cap;
-    if (slots <= b->in_list_slots) return RAPID_OK;
-    const size_t n_old = b->in_list_slots * (size_t)b->n_tiles, n_new = slots * (size_t)b->n_tiles;
-    DevBuf<int32_t> nl;
-    RAPID_CHECK(nl.reserve(n_new));
-    RAPID_CUDA(cudaMemsetAsync(nl.p, 0, n_new * sizeof(int32_t), cd->stream));
-    if (n_old) RAPID_CUDA(cudaMemcpyAsync(nl.p, b->in_list.p, n_old * sizeof(int32_t), cudaMemcpyDeviceToDevice, cd->stream));
-    DevBuf<int2> np;
-    RAPID_CHECK(np.reserve(n_new));
-    if (n_old) RAPID_CUDA(cudaMemcpyAsync(np.p, b->pre_pairs.p, n_old * sizeof(int2), cudaMemcpyDeviceToDevice, cd->stream));
-    RAPID_CUDA(cudaStreamSynchronize(cd->stream));
-    std::swap(b->in_list.p, nl.p); std::swap(b->in_list.cap, nl.cap);
-    std::swap(b->pre_pairs.p, np.p); std::swap(b->pre_pairs.cap, np.cap);
-    b->in_list_slots = slots;
-    return RAPID_OK;
-}
-
-int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCounts& bc) {
+// Everything of one batch after k_prepare, enqueued on the handle's stream with NO host synchronisation: the apply kernel
+// (grid sized from an ESTIMATE of the number of batch subjects — the kernels take the real one from the device counters), the
+// cooperative resolve kernel, and the copy of the counter snapshot to pinned host memory.
+int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl) {
     Bucketed* b = state(cd);
     cudaStream_t s = cd->stream;
-    const int TB = 256;
-    const int Sb = bc.n_batch_subj;
-    const int32_t n_valid = bc.n_valid;
     const bool uniform = !(dl.flags & (RAPID_DELIVERY_BITMAP | RAPID_DELIVERY_PERMUTED));
+    const bool counts_only = (dl.flags & RAPID_DELIVERY_PERMUTED) && !(dl.flags & RAPID_DELIVERY_BITMAP);
+    const bool swar = uniform || counts_only;          // k_apply_uniform<PERM>: 8 receivers per thread
     b->n_tiles = (int)(cd->Rpad / TILE_R);
-    RAPID_CHECK(ensure_pre_capacity(cd, b));
 
-    int n_chunks = 1, chunk = std::max(Sb, 1);
-    if (Sb > 0) {
-        // ---- grid: tiles x subject chunks, a few waves of 148 SMs -----------------------------------------------------
-        const int rblocks = uniform ? b->n_tiles : (int)(cd->Rpad / GEN_THREADS);
+    if (b->slots_uniform == 0) {
+        int dev = 0, sms = 148, per_u = 8, per_g = 4, per_r = 2;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_u, k_apply_uniform<false>, UNI_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_g, k_apply_generic, GEN_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_r, k_mixed_flip, GEN_THREADS, 0);
+        int per_m = 2;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_m, k_marks, GEN_THREADS, 0);
+        per_r = std::min(per_r, per_m);
+        b->slots_uniform = sms * std::max(per_u, 1);
+        b->slots_generic = sms * std::max(per_g, 1);
+        b->resolve_grid = sms * std::max(per_r, 1);
+    }
+    // ---- grid: tiles x subject chunks, a few waves of 148 SMs ---------------------------------------------------------
+    // The number of batch subjects is only known on the device; the previous batch's ratio of subjects to cells (or one
+    // subject per K/2 cells) is a good enough guess — it only shapes the grid, the kernels split the real count.
+    int Sb = (int)std::max<int64_t>(1, std::min<int64_t>(A, cd->est_A > 0 ? (A * (int64_t)std::max(cd->est_Sb, 1) + cd->est_A - 1) / cd->est_A
+                                                                           : (2 * A + cd->K - 1) / cd->K));
+    Sb = (int)std::min<int64_t>(Sb, (int64_t)std::max<size_t>(cd->S_cap, 1));
+    int n_chunks = 1;
+    {
+        const int rblocks = swar ? b->n_tiles : (int)(cd->Rpad / GEN_THREADS);
         // Pick the number of subject chunks so that (tiles x chunks) blocks fill whole waves of resident blocks:
         // a bandwidth-bound grid whose last wave is mostly empty pays almost a full wave for it.  More chunks also
         // mean more per-receiver partials (48 B each), so cap them at ~8 % of the mask traffic.
-        if (b->slots_uniform == 0) {
-            int dev = 0, sms = 148, per_u = 8, per_g = 4;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_u, k_apply_uniform, UNI_THREADS, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_g, k_apply_generic, GEN_THREADS, 0);
-            b->slots_uniform = sms * std::max(per_u, 1);
-            b->slots_generic = sms * std::max(per_g, 1);
-        }
-        const int slots = uniform ? b->slots_uniform : b->slots_generic;
+        const int slots = swar ? b->slots_uniform : b->slots_generic;
         const int cmax = std::max(1, std::min(Sb, std::max(Sb / 300, ceil_div(slots, rblocks))));
         double best = -1.0;
         for (int c = 1; c <= cmax; ++c) {
@@ -1093,20 +1299,16 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
             if (w <= 1.0) eff = 0.85 + 0.15 * w;                                   // one partial wave: a little less occupancy
             else eff = w / (std::floor(w) + (f > 0 ? std::max(f, 0.6) : 0.0));     // tail wave: needs ~60 % of the slots to saturate HBM
             eff -= 0.001 * cc;                                                     // per-chunk prologue (fresh subjects cost no partials)
-            if (eff > best) { best = eff; n_chunks = cc; chunk = ch; }
+            if (eff > best) { best = eff; n_chunks = cc; }
         }
-        if (const char* ov = getenv("RAPID_B200_CHUNKS")) {          // tuning aid: force the number of subject chunks
-            const int c = std::max(1, std::min(Sb, atoi(ov)));
-            chunk = ceil_div(Sb, c);
-            n_chunks = ceil_div(Sb, chunk);
-        }
+        if (const char* ov = getenv("RAPID_B200_CHUNKS")) n_chunks = std::max(1, std::min(Sb, atoi(ov)));   // tuning aid
     }
     const size_t pn = (size_t)n_chunks * cd->Rpad;
     RAPID_CHECK(b->p_cnt.reserve(pn)); RAPID_CHECK(b->p_minTH.reserve(pn)); RAPID_CHECK(b->p_minTLun.reserve(pn));
     RAPID_CHECK(b->p_h1.reserve(pn)); RAPID_CHECK(b->p_h2.reserve(pn));
     RAPID_CHECK(b->mx_fl.reserve(cd->Rpad)); RAPID_CHECK(b->mx_a.reserve(cd->Rpad)); RAPID_CHECK(b->mx_cand.reserve(cd->Rpad));
     RAPID_CHECK(b->mx_emax.reserve(cd->Rpad)); RAPID_CHECK(b->mx_p1.reserve(cd->Rpad)); RAPID_CHECK(b->mx_p2.reserve(cd->Rpad));
-    RAPID_CHECK(b->mx_pc.reserve(cd->Rpad)); RAPID_CHECK(b->estar.reserve(cd->Rpad)); RAPID_CHECK(b->mx_changed.reserve(1));
+    RAPID_CHECK(b->mx_pc.reserve(cd->Rpad)); RAPID_CHECK(b->estar.reserve(cd->Rpad));
     if (!b->mx_e1.p) {
         RAPID_CHECK(b->mx_e1.reserve(cd->Rpad)); RAPID_CHECK(b->mx_e2.reserve(cd->Rpad)); RAPID_CHECK(b->mx_ec.reserve(cd->Rpad));
         RAPID_CUDA(cudaMemsetAsync(b->mx_e1.p, 0, cd->Rpad * sizeof(unsigned long long), s));
@@ -1120,117 +1322,50 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCoun
     ApplyArgs ap;
     ap.masks = cd->masks.p; ap.cur = cd->cur.p; ap.Rpad = cd->Rpad;
     ap.K = cd->K; ap.H = cd->H; ap.L = cd->L; ap.R = cd->R; ap.rbegin = cd->rbegin;
-    ap.rflags = cd->rflags.p; ap.dl = dl; ap.Sb = Sb; ap.chunk = chunk;
+    ap.rflags = cd->rflags.p; ap.dl = dl; ap.bc = cd->counts.p;
     ap.desc = b->desc.p; ap.walk = b->walk.p; ap.slot_subject = cd->slot_subject.p;
     ap.sidx = b->sidx.p; ap.s_ring = b->s_ring.p; ap.s_status = b->s_status.p;
-    ap.part = part; ap.n_tiles = b->n_tiles; ap.in_list = b->in_list.p; ap.pre_pairs = b->pre_pairs.p;
-    ap.S_before = cd->S_before;
-    ap.pre_count = b->pre_count.p; ap.pre_cap = (int32_t)std::min<size_t>(b->in_list_slots * (size_t)b->n_tiles, 0x7fffffff);
+    ap.part = part; ap.n_tiles = b->n_tiles; ap.wl = worklist(b);
 
     RAPID_CUDA(cudaEventRecord(cd->evk0, s));
-    if (Sb > 0) {
-        if (uniform) {
-            dim3 grid((unsigned)b->n_tiles, (unsigned)n_chunks);
-            k_apply_uniform<<<grid, UNI_THREADS, 0, s>>>(ap);
-            cd->last_path = 2;
-        } else {
-            dim3 grid((unsigned)(cd->Rpad / GEN_THREADS), (unsigned)n_chunks);
-            k_apply_generic<<<grid, GEN_THREADS, 0, s>>>(ap);
-            cd->last_path = 3;
-        }
-        RAPID_KERNEL_CHECK();
-        cd->last_launches += 1;
+    if (swar) {
+        dim3 grid((unsigned)b->n_tiles, (unsigned)n_chunks);
+        if (counts_only) k_apply_uniform<true><<<grid, UNI_THREADS, 0, s>>>(ap);
+        else k_apply_uniform<false><<<grid, UNI_THREADS, 0, s>>>(ap);
+        cd->last_path = counts_only ? 4 : 2;
     } else {
-        RAPID_CUDA(cudaMemsetAsync(b->p_flag.p, 0, (size_t)n_chunks * std::max(b->n_tiles, 1) * sizeof(int32_t), s));
-        RAPID_CUDA(cudaMemsetAsync(b->p_chunk.p, 0, (size_t)n_chunks * sizeof(ChunkAcc), s));
-        cd->last_path = uniform ? 2 : 3;
+        dim3 grid((unsigned)(cd->Rpad / GEN_THREADS), (unsigned)n_chunks);
+        k_apply_generic<<<grid, GEN_THREADS, 0, s>>>(ap);
+        cd->last_path = 3;
     }
+    RAPID_KERNEL_CHECK();
     RAPID_CUDA(cudaEventRecord(cd->evk1, s));
 
-    FinArgs fa;
-    fa.R = cd->R; fa.Rpad = cd->Rpad; fa.n_chunks = n_chunks; fa.part = part; fa.dl = dl;
-    fa.any_down_uniform = bc.any_down; fa.uniform = uniform ? 1 : 0;
-    fa.n_pre = cd->n_pre.p; fa.rflags = cd->rflags.p; fa.pend_h1 = cd->pend_h1.p; fa.pend_h2 = cd->pend_h2.p;
-    fa.pend_cnt = cd->pend_cnt.p; fa.out_h1 = cd->out_h1.p; fa.out_h2 = cd->out_h2.p; fa.out_len = cd->out_len.p;
-    fa.mx_fl = b->mx_fl.p; fa.mx_a = b->mx_a.p; fa.mx_cand = b->mx_cand.p; fa.mx_emax = b->mx_emax.p;
-    fa.mx_p1 = b->mx_p1.p; fa.mx_p2 = b->mx_p2.p; fa.mx_pc = b->mx_pc.p; fa.bc = cd->counts.p;
-    const unsigned gr = (unsigned)ceil_div<int64_t>(cd->R, TB);
-    k_finalize1<<<gr, TB, 0, s>>>(fa);
+    ResolveArgs ra;
+    ra.ap = ap; ra.bc = cd->counts.p; ra.snap = cd->counts_snap.p; ra.n_chunks = n_chunks;
+    ra.uniform = uniform ? 1 : 0; ra.counts_only = counts_only ? 1 : 0; ra.cur_w = cd->cur.p;
+    ra.n_pre = cd->n_pre.p; ra.rflags = cd->rflags.p; ra.pend_h1 = cd->pend_h1.p; ra.pend_h2 = cd->pend_h2.p;
+    ra.pend_cnt = cd->pend_cnt.p; ra.out_h1 = cd->out_h1.p; ra.out_h2 = cd->out_h2.p; ra.out_len = cd->out_len.p; ra.out_ann = cd->out_ann.p;
+    ra.mx_fl = b->mx_fl.p; ra.mx_a = b->mx_a.p; ra.mx_cand = b->mx_cand.p; ra.mx_emax = b->mx_emax.p;
+    ra.mx_p1 = b->mx_p1.p; ra.mx_p2 = b->mx_p2.p; ra.mx_pc = b->mx_pc.p; ra.estar = b->estar.p;
+    ra.mx_e1 = b->mx_e1.p; ra.mx_e2 = b->mx_e2.p; ra.mx_ec = b->mx_ec.p; ra.mx_changed = b->mx_changed.p;
+    ra.slot_of = cd->slot_of.p; ra.obs = cd->view->obs.p; ra.touch = cd->touch.p; ra.batch_index = b->batch_index.p;
+    ra.serial = cd->batch_serial;
+    const unsigned rblocks = (unsigned)(cd->Rpad / GEN_THREADS);
+    const int cgrid = std::max(1, std::min(b->resolve_grid, std::max(32, 4 * (int)rblocks)));      // co-resident (cooperative) grids
+    RAPID_CHECK(b->ra_dev.reserve(sizeof(ResolveArgs)));
+    // pageable source, a few hundred bytes: the driver copies it into the command stream before returning
+    RAPID_CUDA(cudaMemcpyAsync(b->ra_dev.p, &ra, sizeof(ResolveArgs), cudaMemcpyHostToDevice, s));
+    const ResolveArgs* ga = (const ResolveArgs*)b->ra_dev.p;
+    void* args[] = {(void*)&ga};
+    k_finalize1<<<rblocks, GEN_THREADS, 0, s>>>(ga);
     RAPID_KERNEL_CHECK();
-    cd->last_launches += 1;
-
-    // ---- receivers needing the exact interval analysis (one small readback tells whether there are any) ----------------
-    RAPID_CUDA(cudaMemcpyAsync(cd->h_counts.p, cd->counts.p, sizeof(BatchCounts), cudaMemcpyDeviceToHost, s));
-    RAPID_CUDA(cudaStreamSynchronize(s));
-    const int n_mixed = cd->h_counts.p->n_mixed;
-    EmitCtx ectx;
-    ectx.ap = ap; ectx.touch = cd->touch.p; ectx.batch_index = b->batch_index.p; ectx.serial = cd->batch_serial;
-    ectx.estar = b->estar.p; ectx.uniform = uniform ? 1 : 0;
-    if (n_mixed > 0 && Sb > 0) {
-        MixArgs ma;
-        ma.ap = ap; ma.mx_fl = b->mx_fl.p; ma.mx_a = b->mx_a.p; ma.mx_cand = b->mx_cand.p; ma.mx_emax = b->mx_emax.p;
-        ma.estar = b->estar.p; ma.mx_e1 = b->mx_e1.p; ma.mx_e2 = b->mx_e2.p; ma.mx_ec = b->mx_ec.p; ma.uniform = uniform ? 1 : 0;
-        const int rblocks = (int)(cd->Rpad / GEN_THREADS);
-        int mchunks = std::max(1, std::min(ceil_div(Sb, STAGE), ceil_div(2 * std::max(b->slots_generic, 148), rblocks)));
-        ma.ap.chunk = ceil_div(Sb, mchunks);
-        mchunks = ceil_div(Sb, ma.ap.chunk);
-        dim3 mgrid((unsigned)rblocks, (unsigned)mchunks);
-        for (int iter = 0; iter <= Sb + 1; ++iter) {
-            RAPID_CUDA(cudaMemsetAsync(b->mx_changed.p, 0, sizeof(int32_t), s));
-            k_mixed_pass<0><<<mgrid, GEN_THREADS, 0, s>>>(ma);
-            k_mixed_update<<<gr, TB, 0, s>>>(cd->R, b->mx_fl.p, b->mx_a.p, b->mx_cand.p, b->mx_emax.p, b->estar.p, b->mx_changed.p);
-            RAPID_KERNEL_CHECK();
-            cd->last_launches += 2;
-            int32_t changed = 0;
-            RAPID_CUDA(cudaMemcpyAsync(&changed, b->mx_changed.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-            RAPID_CUDA(cudaStreamSynchronize(s));
-            if (changed == 0) break;
-        }
-        k_mixed_pass<1><<<mgrid, GEN_THREADS, 0, s>>>(ma);
-        MixCommitArgs mc;
-        mc.R = cd->R; mc.mx_fl = b->mx_fl.p; mc.mx_p1 = b->mx_p1.p; mc.mx_p2 = b->mx_p2.p; mc.mx_pc = b->mx_pc.p;
-        mc.mx_e1 = b->mx_e1.p; mc.mx_e2 = b->mx_e2.p; mc.mx_ec = b->mx_ec.p; mc.rflags = cd->rflags.p;
-        mc.pend_h1 = cd->pend_h1.p; mc.pend_h2 = cd->pend_h2.p; mc.pend_cnt = cd->pend_cnt.p;
-        mc.out_h1 = cd->out_h1.p; mc.out_h2 = cd->out_h2.p; mc.out_len = cd->out_len.p;
-        k_mixed_commit<<<gr, TB, 0, s>>>(mc);
-        RAPID_KERNEL_CHECK();
-        cd->last_launches += 2;
-    }
-    if (Sb > 0) {
-        k_flip<<<(unsigned)ceil_div(Sb, TB), TB, 0, s>>>(Sb, b->desc.p, cd->cur.p);
-        RAPID_KERNEL_CHECK();
-        cd->last_launches += 1;
-        ectx.ap.cur = cd->cur.p;
-    }
-    InvArgs ia;
-    ia.masks = cd->masks.p; ia.cur = cd->cur.p; ia.Rpad = cd->Rpad; ia.K = cd->K; ia.H = cd->H; ia.L = cd->L; ia.R = cd->R;
-    ia.rflags = cd->rflags.p; ia.pre_pairs = b->pre_pairs.p; ia.pre_count = b->pre_count.p; ia.pre_cap = ap.pre_cap;
-    ia.slot_subject = cd->slot_subject.p; ia.slot_of = cd->slot_of.p; ia.obs = cd->view->obs.p;
-    ia.k3_res = b->k3_res.p; ia.k3_h1 = b->k3_h1.p; ia.k3_h2 = b->k3_h2.p;
-    ia.mixed = n_mixed > 0 ? 1 : 0; ia.ec = ectx;
-    k_inval_pairs<<<148 * 16, 256, 0, s>>>(ia);
-    Fin2Args f2;
-    f2.R = cd->R; f2.n_pre = cd->n_pre.p; f2.rflags = cd->rflags.p; f2.pend_h1 = cd->pend_h1.p; f2.pend_h2 = cd->pend_h2.p;
-    f2.pend_cnt = cd->pend_cnt.p; f2.out_h1 = cd->out_h1.p; f2.out_h2 = cd->out_h2.p; f2.out_len = cd->out_len.p;
-    f2.out_ann = cd->out_ann.p; f2.k3_res = b->k3_res.p; f2.k3_h1 = b->k3_h1.p; f2.k3_h2 = b->k3_h2.p; f2.bc = cd->counts.p;
-    k_finalize2<<<gr, TB, 0, s>>>(f2);
+    RAPID_CUDA(cudaLaunchCooperativeKernel((void*)k_mixed_flip, dim3((unsigned)cgrid), dim3(GEN_THREADS), args, 0, s));
+    k_inval_finalize2<<<std::min<unsigned>(rblocks, 148u * 32u), GEN_THREADS, 0, s>>>(ga);
     RAPID_KERNEL_CHECK();
-    cd->last_launches += 2;
-    if (n_mixed > 0) {
-        RAPID_CUDA(cudaMemcpyAsync(cd->h_counts.p, cd->counts.p, sizeof(BatchCounts), cudaMemcpyDeviceToHost, s));
-        RAPID_CUDA(cudaStreamSynchronize(s));
-        if (cd->h_counts.p->n_inval > 0 && cd->S > 0) {
-            // receivers that announce only the explicit part: persist it as bit 15 while the pre-batch rows still exist
-            const int spb = 64;
-            dim3 kgrid((unsigned)(cd->Rpad / GEN_THREADS), (unsigned)ceil_div(cd->S, spb));
-            k_mixed_mark<<<kgrid, GEN_THREADS, 0, s>>>(ectx, cd->S, spb, cd->rflags.p);
-            RAPID_KERNEL_CHECK();
-            cd->last_launches += 1;
-        }
-        k_inval_unmark<<<148 * 4, 256, 0, s>>>(ia);          // only now: the marks above still needed bit 14
-        RAPID_KERNEL_CHECK();
-        cd->last_launches += 1;
-    }
+    RAPID_CUDA(cudaLaunchCooperativeKernel((void*)k_marks, dim3((unsigned)cgrid), dim3(GEN_THREADS), args, 0, s));
+    cd->last_launches += 5;
+    RAPID_CUDA(cudaMemcpyAsync(cd->h_counts.p, cd->counts_snap.p, sizeof(BatchCounts), cudaMemcpyDeviceToHost, s));
     return RAPID_OK;
 }
 

@@ -194,9 +194,11 @@ __global__ void k_dump_masks(RowRef rows, int32_t S, int64_t r, uint32_t RM, con
     out_masks[s] = (uint16_t)(rows.row(s)[r] & RM);
 }
 
-__global__ void k_reset_slots(int32_t S, const int32_t* __restrict__ slot_subject, int32_t* __restrict__ slot_of,
-                              uint8_t* __restrict__ cur) {
+// S < 0: the slot count lives on the device (bucketed handles), the grid covers the handle's capacity
+__global__ void k_reset_slots(int32_t S, const BatchCounts* __restrict__ bc, const int32_t* __restrict__ slot_subject,
+                              int32_t* __restrict__ slot_of, uint8_t* __restrict__ cur) {
     const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (S < 0) S = bc->n_slots;
     if (s < S) { slot_of[slot_subject[s]] = -1; cur[s] = 0; }
 }
 
@@ -259,7 +261,10 @@ static int32_t ensure_slot_capacity(CD* cd, size_t need) {
     return RAPID_OK;
 }
 
-// Filter the batch, give every new subject a slot, write cell_slot[]; one host sync to read the counts.
+// Sweep handles: filter the batch, give every new subject a slot, write cell_slot[]; one host sync to read the counts (the sweep
+// kernel's rows must exist before it runs).  Cells with a ring number >= K or an unknown edgeDst are dropped and reported
+// (RAPID_EINVAL) AFTER the rest of the batch has been applied — the Java trusts ring numbers (only `assert`,
+// MultiNodeCutDetector.java:87) and never loses the valid alerts of a batch.
 static int32_t preprocess(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev, const uint8_t* ring_dev,
                           const uint8_t* status_dev, const int64_t* cfg_dev, BatchCounts* out) {
     cudaStream_t s = cd->stream;
@@ -274,27 +279,59 @@ static int32_t preprocess(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev
     *cd->h_counts.p = init;
     RAPID_CUDA(cudaMemcpyAsync(cd->counts.p, cd->h_counts.p, sizeof(BatchCounts), cudaMemcpyHostToDevice, s));
     if (A > 0) {
-        PrepOut po;
-        const bool regroup = cd->bucketed;
-        if (regroup) RAPID_CHECK(bucketed_prep_buffers(cd, A, &po));
-        RAPID_CHECK(prepare_batch(cd, cfg, A, dst_dev, ring_dev, status_dev, cfg_dev, regroup ? &po : nullptr));
+        RAPID_CHECK(prepare_batch(cd, cfg, A, dst_dev, ring_dev, status_dev, cfg_dev, nullptr));
     } else {
         ++cd->batch_serial;
     }
     RAPID_CUDA(cudaMemcpyAsync(cd->h_counts.p, cd->counts.p, sizeof(BatchCounts), cudaMemcpyDeviceToHost, s));
     RAPID_CUDA(cudaStreamSynchronize(s));
     *out = *cd->h_counts.p;
-    if (out->bad_ring >= 0 || out->bad_dst >= 0) {
-        // undo nothing: slots assigned to valid cells stay (harmless); report the offending cell
-        if (out->bad_ring >= 0) set_error("cell %d: ring number >= K (%d)", out->bad_ring, cd->K);
-        else set_error("cell %d: edgeDst id outside [0, members + registered joiners)", out->bad_dst);
-        cd->S = out->n_slots;
-        RAPID_CHECK(ensure_slot_capacity(cd, (size_t)cd->S));
-        return RAPID_EINVAL;
-    }
     cd->S = out->n_slots;
     RAPID_CHECK(ensure_slot_capacity(cd, (size_t)cd->S));
     return RAPID_OK;
+}
+
+static int32_t bad_cell_status(const CD* cd, const BatchCounts& c) {
+    if (c.bad_ring >= 0) { set_error("cell %d: ring number >= K (%d) (dropped; the rest of the batch was applied)", c.bad_ring, cd->K); return RAPID_EINVAL; }
+    if (c.bad_dst >= 0) { set_error("cell %d: edgeDst id outside [0, members + registered joiners) (dropped; the rest of the batch was applied)", c.bad_dst); return RAPID_EINVAL; }
+    return RAPID_OK;
+}
+
+// ---- bucketed handles: asynchronous batches -----------------------------------------------------------------------------
+// The stream is idle: read the snapshot of the device counters the last enqueued operation left in pinned memory.
+static void collect(CD* cd) {
+    const BatchCounts c = *cd->h_counts.p;
+    cd->last = c;
+    cd->S = c.n_slots;
+    if (c.n_batch_subj > 0 && cd->last_A > 0) { cd->est_Sb = c.n_batch_subj; cd->est_A = cd->last_A; }
+    cudaEventElapsedTime(&cd->last_ms, cd->ev0, cd->ev1);
+    cudaEventElapsedTime(&cd->last_main_ms, cd->evk0, cd->evk1);
+    cudaGetLastError();
+    if (c.sticky_overflow || c.sticky_bad_ring || c.sticky_bad_dst) {
+        if (c.sticky_overflow) {
+            cd->deferred_rc = RAPID_ENOMEM;
+            cd->deferred_msg = "a batch needed more subject slots than the handle holds and was NOT applied (asynchronous batches cannot "
+                               "grow the handle: raise max_subjects, or use the synchronous entry points)";
+        } else if (cd->deferred_rc == RAPID_OK) {
+            cd->deferred_rc = RAPID_EINVAL;
+            cd->deferred_msg = c.sticky_bad_ring ? "a cell with ring number >= K was dropped (the rest of its batch was applied)"
+                                                 : "a cell with edgeDst outside [0, members + registered joiners) was dropped (the rest of its batch was applied)";
+        }
+        bucketed_clear_sticky(cd);
+    }
+    cd->pending = false;
+}
+
+int32_t cd_wait(const CD* ccd, bool take_status) {
+    CD* cd = const_cast<CD*>(ccd);
+    RAPID_CUDA(cudaStreamSynchronize(cd->stream));
+    if (cd->pending) collect(cd);
+    if (!take_status || cd->deferred_rc == RAPID_OK) return RAPID_OK;
+    const int32_t rc = cd->deferred_rc;
+    set_error("%s", cd->deferred_msg.c_str());
+    cd->deferred_rc = RAPID_OK;
+    cd->deferred_msg.clear();
+    return rc;
 }
 
 static int32_t launch_sweep(CD* cd, int64_t A, const uint8_t* ring_dev, const uint8_t* status_dev, const DeliveryDev& dl,
@@ -353,28 +390,59 @@ static int32_t upload_delivery(CD* cd, int64_t A, const rapid_delivery* d, bool 
 
 static int32_t apply_common(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev, const uint8_t* ring_dev,
                             const uint8_t* status_dev, const int64_t* cfg_dev, const DeliveryDev& dl,
-                            const int64_t* batch_off_dev = nullptr, int32_t n_batches = 0, int32_t* out_batch_dev = nullptr) {
+                            const int64_t* batch_off_dev = nullptr, int32_t n_batches = 0, int32_t* out_batch_dev = nullptr,
+                            bool async = false) {
+    cd->cur_ring_dev = ring_dev;
+    cd->cur_status_dev = status_dev;
+    if (cd->bucketed) {
+        if (batch_off_dev) { set_error("a sequence of batches needs the per-cell order of a sweep handle (RAPID_CD_SWEEP)"); return RAPID_EUNSUPPORTED; }
+        // Three launches (prepare, apply, resolve) and the copy of the counter snapshot, no host round trip in between.  The
+        // synchronous entry points wait here and replay the batch if the handle had to grow; the asynchronous one returns.
+        for (int attempt = 0;; ++attempt) {
+            cd->last_launches = 0;
+            cd->last_A = A;
+            RAPID_CUDA(cudaEventRecord(cd->ev0, cd->stream));
+            RAPID_CHECK(ensure_id_capacity(cd));
+            RAPID_CHECK(cd->cell_slot.reserve(std::max<int64_t>(A, 1)));
+            PrepOut po;
+            RAPID_CHECK(bucketed_prep_buffers(cd, A, &po));
+            if (A > 0) RAPID_CHECK(prepare_batch(cd, cfg, A, dst_dev, ring_dev, status_dev, cfg_dev, &po));
+            else ++cd->batch_serial;
+            RAPID_CHECK(bucketed_apply(cd, A, dl));
+            RAPID_CUDA(cudaEventRecord(cd->ev1, cd->stream));
+            RAPID_CUDA(cudaEventRecord(cd->ev_done, cd->stream));
+            cd->pending = true;
+            if (async) return RAPID_OK;
+            RAPID_CUDA(cudaStreamSynchronize(cd->stream));
+            const int32_t carried_rc = cd->deferred_rc;            // errors of EARLIER asynchronous batches stay latched
+            const std::string carried_msg = cd->deferred_msg;
+            collect(cd);
+            if (cd->last.overflow && attempt < 4) {
+                // not an error here: grow the handle and replay (k_prepare rolled its slot assignment back, nothing was applied)
+                cd->deferred_rc = carried_rc; cd->deferred_msg = carried_msg;
+                RAPID_CHECK(ensure_slot_capacity(cd, (size_t)cd->last.need_slots));
+                ++cd->retries;
+                continue;
+            }
+            const int32_t rc = bad_cell_status(cd, cd->last);
+            if (rc != RAPID_OK) { cd->deferred_rc = carried_rc; cd->deferred_msg = carried_msg; return rc; }
+            return RAPID_OK;
+        }
+    }
     cd->last_launches = 0;
     cd->last_A = A;
     RAPID_CUDA(cudaEventRecord(cd->ev0, cd->stream));
     BatchCounts bc;
     RAPID_CHECK(preprocess(cd, cfg, A, dst_dev, ring_dev, status_dev, cfg_dev, &bc));
-    int32_t rc;
-    cd->cur_ring_dev = ring_dev;
-    cd->cur_status_dev = status_dev;
-    if (cd->bucketed) {
-        if (batch_off_dev) { set_error("a sequence of batches needs the per-cell order of a sweep handle (RAPID_CD_SWEEP)"); return RAPID_EUNSUPPORTED; }
-        rc = bucketed_apply(cd, A, dl, bc);
-    } else {
-        if (dl.flags & RAPID_DELIVERY_PERMUTED) { set_error("the sweep kernel applies cells in array order; RAPID_DELIVERY_PERMUTED needs a bucketed handle"); return RAPID_EUNSUPPORTED; }
-        rc = launch_sweep(cd, A, ring_dev, status_dev, dl, true, !cd->raw, batch_off_dev, n_batches, out_batch_dev);
-    }
-    if (rc != RAPID_OK) return rc;
+    if (dl.flags & RAPID_DELIVERY_PERMUTED) { set_error("the sweep kernel applies cells in array order; RAPID_DELIVERY_PERMUTED needs a bucketed handle"); return RAPID_EUNSUPPORTED; }
+    RAPID_CHECK(launch_sweep(cd, A, ring_dev, status_dev, dl, true, !cd->raw, batch_off_dev, n_batches, out_batch_dev));
     RAPID_CUDA(cudaEventRecord(cd->ev1, cd->stream));
+    RAPID_CUDA(cudaEventRecord(cd->ev_done, cd->stream));
     RAPID_CUDA(cudaStreamSynchronize(cd->stream));
     cudaEventElapsedTime(&cd->last_ms, cd->ev0, cd->ev1);
     cudaEventElapsedTime(&cd->last_main_ms, cd->evk0, cd->evk1);
-    return RAPID_OK;
+    cd->last = bc;
+    return bad_cell_status(cd, bc);
 }
 
 }  // namespace rapid
@@ -416,7 +484,8 @@ int32_t rapid_cd_create(rapid_cd** out, const rapid_view* v, int32_t H, int32_t 
     do {
         if (cudaStreamCreateWithFlags(&cd->stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreate(&cd->ev0) != cudaSuccess || cudaEventCreate(&cd->ev1) != cudaSuccess ||
-            cudaEventCreate(&cd->evk0) != cudaSuccess || cudaEventCreate(&cd->evk1) != cudaSuccess) {
+            cudaEventCreate(&cd->evk0) != cudaSuccess || cudaEventCreate(&cd->evk1) != cudaSuccess ||
+            cudaEventCreateWithFlags(&cd->ev_done, cudaEventDisableTiming) != cudaSuccess) {
             rc = cuda_fail(cudaGetLastError(), "stream/event create", __FILE__, __LINE__); break;
         }
         const size_t R = (size_t)cd->Rpad;
@@ -431,7 +500,15 @@ int32_t rapid_cd_create(rapid_cd** out, const rapid_view* v, int32_t H, int32_t 
         if ((rc = cd->out_len.reserve(R))) break;
         if ((rc = cd->out_ann.reserve(R))) break;
         if ((rc = cd->counts.reserve(1))) break;
+        if ((rc = cd->counts_snap.reserve(1))) break;
         if ((rc = cd->h_counts.reserve(1))) break;
+        memset(cd->h_counts.p, 0, sizeof(BatchCounts));
+        // the device counters must be valid BEFORE the first clear(): it resets "the slots in use" and reads their number
+        if (cudaMemsetAsync(cd->counts.p, 0, sizeof(BatchCounts), cd->stream) != cudaSuccess ||
+            cudaMemsetAsync(cd->counts_snap.p, 0, sizeof(BatchCounts), cd->stream) != cudaSuccess) {
+            rc = cuda_fail(cudaGetLastError(), "memset", __FILE__, __LINE__); break;
+        }
+        memset(&cd->last, 0, sizeof(BatchCounts));
         if ((rc = ensure_id_capacity(cd))) break;
         if ((rc = ensure_slot_capacity(cd, (size_t)std::max<int64_t>(max_subjects, 16)))) break;
         rc = rapid_cd_clear(cd);
@@ -450,6 +527,7 @@ int32_t rapid_cd_destroy(rapid_cd* cd) {
     if (cd->ev1) cudaEventDestroy(cd->ev1);
     if (cd->evk0) cudaEventDestroy(cd->evk0);
     if (cd->evk1) cudaEventDestroy(cd->evk1);
+    if (cd->ev_done) cudaEventDestroy(cd->ev_done);
     if (cd->stream) cudaStreamDestroy(cd->stream);
     delete cd;
     return RAPID_OK;
@@ -460,13 +538,19 @@ int32_t rapid_cd_clear(rapid_cd* cd) {
     DeviceGuard g(cd->device);
     cudaStream_t s = cd->stream;
     const size_t R = cd->Rpad;
-    if (cd->S > 0) {
-        k_reset_slots<<<(unsigned)ceil_div<int32_t>(cd->S, 256), 256, 0, s>>>(cd->S, cd->slot_subject.p, cd->slot_of.p, cd->cur.p);
+    if (cd->bucketed) {
+        // Bucketed handles never read the state of a slot before the batch that assigns it has written it (slots >= S_before
+        // are write-only), so clear() is O(#slots): forget the dictionary.  The slot count lives on the device — no host
+        // round trip, the whole reset is asynchronous.
+        if (cd->S_cap > 0) {
+            k_reset_slots<<<(unsigned)ceil_div<size_t>(cd->S_cap, 256), 256, 0, s>>>(-1, cd->counts.p, cd->slot_subject.p, cd->slot_of.p, cd->cur.p);
+            RAPID_KERNEL_CHECK();
+        }
+    } else if (cd->S > 0) {
+        k_reset_slots<<<(unsigned)ceil_div<int32_t>(cd->S, 256), 256, 0, s>>>(cd->S, cd->counts.p, cd->slot_subject.p, cd->slot_of.p, cd->cur.p);
         RAPID_KERNEL_CHECK();
-        // Bucketed handles never read the state of a slot before the batch that assigns it has written it
-        // (ApplyArgs::S_before), so clear() is O(#slots) there; the sweep kernel reads in place and needs zeros.
-        if (!cd->bucketed)
-            RAPID_CUDA(cudaMemsetAsync(cd->masks.p, 0, (size_t)cd->S * cd->nbuf * cd->Rpad * sizeof(uint16_t), s));
+        // the sweep kernel reads in place and needs zeros
+        RAPID_CUDA(cudaMemsetAsync(cd->masks.p, 0, (size_t)cd->S * cd->nbuf * cd->Rpad * sizeof(uint16_t), s));
     }
     cd->S = 0;
     k_clear_receivers<<<(unsigned)ceil_div<size_t>(R, 256), 256, 0, s>>>((int64_t)R, cd->n_pre.p, cd->n_prop.p, cd->rflags.p, cd->pend_h1.p,
@@ -474,15 +558,26 @@ int32_t rapid_cd_clear(rapid_cd* cd) {
                                                                         cd->out_len.p, cd->out_ann.p);
     RAPID_KERNEL_CHECK();
     RAPID_CHECK(bucketed_clear(cd));
-    // no synchronisation: everything that follows runs on the same stream (the tally reads the detector's outputs only
-    // after rapid_cd_apply_batch, which synchronises)
+    if (cd->bucketed) {
+        RAPID_CUDA(cudaMemcpyAsync(cd->h_counts.p, cd->counts_snap.p, sizeof(BatchCounts), cudaMemcpyDeviceToHost, s));
+        cd->last_A = 0;
+        cd->pending = true;
+    }
+    RAPID_CUDA(cudaEventRecord(cd->ev_done, s));
+    // no synchronisation: everything that follows runs on the same stream, and other streams (the tally) wait on ev_done
     return RAPID_OK;
+}
+
+int32_t rapid_cd_sync(rapid_cd* cd) {
+    if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    return cd_wait(cd, true);
 }
 
 int32_t rapid_cd_read_outputs(const rapid_cd* cd, uint64_t* h1, uint64_t* h2, int32_t* len, uint8_t* ann) {
     if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
     DeviceGuard g(cd->device);
-    cudaStreamSynchronize(cd->stream);   // clear() and the apply calls are asynchronous on the handle's stream
+    RAPID_CHECK(cd_wait(cd, false));     // clear() and asynchronous batches are still in flight on the handle's stream
     const size_t R = (size_t)cd->R;
     if (h1) RAPID_CUDA(cudaMemcpyAsync(h1, cd->out_h1.p, R * sizeof(uint64_t), cudaMemcpyDeviceToHost, cd->stream));
     if (h2) RAPID_CUDA(cudaMemcpyAsync(h2, cd->out_h2.p, R * sizeof(uint64_t), cudaMemcpyDeviceToHost, cd->stream));
@@ -502,6 +597,18 @@ int32_t rapid_cd_apply_batch_dev(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, 
     DeliveryDev dl;
     RAPID_CHECK(upload_delivery(cd, n_cells, delivery_dev, true, &dl));
     return apply_common(cd, cfg_id, n_cells, dst_dev, ring_dev, status_dev, cell_cfg_dev, dl);
+}
+
+int32_t rapid_cd_apply_batch_dev_async(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src_dev, const int32_t* dst_dev,
+                                       const uint8_t* ring_dev, const uint8_t* status_dev, const int64_t* cell_cfg_dev,
+                                       const rapid_delivery* delivery_dev) {
+    (void)src_dev;
+    if (!cd || n_cells < 0 || (n_cells && (!dst_dev || !ring_dev || !status_dev))) { set_error("bad arguments"); return RAPID_EINVAL; }
+    if (!cd->bucketed) { set_error("asynchronous batches run on the subject-bucketed kernels (SERVICE / BUCKETED handles)"); return RAPID_EUNSUPPORTED; }
+    DeviceGuard g(cd->device);
+    DeliveryDev dl;
+    RAPID_CHECK(upload_delivery(cd, n_cells, delivery_dev, true, &dl));
+    return apply_common(cd, cfg_id, n_cells, dst_dev, ring_dev, status_dev, cell_cfg_dev, dl, nullptr, 0, nullptr, true);
 }
 
 // Host arrays -> one pinned blob -> ONE host-to-device copy.  Layout: [cfg int64 x n]? [dst int32 x n] [ring u8 x n]
@@ -659,7 +766,7 @@ int32_t rapid_cd_invalidate(rapid_cd* cd, int64_t receiver, int32_t* out_ids, in
 int32_t rapid_cd_get_proposal(const rapid_cd* cd, int64_t receiver, int32_t* out_ids, int32_t cap, int32_t* out_len) {
     if (!cd || !out_len || receiver < 0 || receiver >= cd->R) { set_error("bad arguments"); return RAPID_EINVAL; }
     DeviceGuard g(cd->device);
-    cudaStreamSynchronize(cd->stream);   // clear() and the apply calls are asynchronous on the handle's stream
+    RAPID_CHECK(cd_wait(cd, false));     // clear() and asynchronous batches are still in flight on the handle's stream
     uint32_t flags = 0;
     RAPID_CUDA(cudaMemcpy(&flags, cd->rflags.p + receiver, sizeof(flags), cudaMemcpyDeviceToHost));
     *out_len = 0;
@@ -696,7 +803,7 @@ int32_t rapid_cd_num_proposals(const rapid_cd* cd, int64_t receiver, int32_t* ou
     if (!cd || !out || receiver < 0 || receiver >= cd->R) { set_error("bad arguments"); return RAPID_EINVAL; }
     if (cd->bucketed) { set_error("getNumProposals is exact only on sweep handles (RAPID_CD_SWEEP / RAPID_CD_RAW)"); return RAPID_EUNSUPPORTED; }
     DeviceGuard g(cd->device);
-    cudaStreamSynchronize(cd->stream);   // clear() and the apply calls are asynchronous on the handle's stream
+    RAPID_CHECK(cd_wait(cd, false));     // clear() and asynchronous batches are still in flight on the handle's stream
     RAPID_CUDA(cudaMemcpy(out, cd->n_prop.p + receiver, sizeof(int32_t), cudaMemcpyDeviceToHost));
     return RAPID_OK;
 }
@@ -704,7 +811,7 @@ int32_t rapid_cd_num_proposals(const rapid_cd* cd, int64_t receiver, int32_t* ou
 int32_t rapid_cd_debug_masks(const rapid_cd* cd, int64_t receiver, int32_t* out_subject_ids, uint16_t* out_masks, int32_t cap, int32_t* out_n) {
     if (!cd || !out_n || receiver < 0 || receiver >= cd->R) { set_error("bad arguments"); return RAPID_EINVAL; }
     DeviceGuard g(cd->device);
-    cudaStreamSynchronize(cd->stream);   // clear() and the apply calls are asynchronous on the handle's stream
+    RAPID_CHECK(cd_wait(cd, false));     // clear() and asynchronous batches are still in flight on the handle's stream
     const int32_t S = cd->S;
     *out_n = S;
     if (S == 0) return RAPID_OK;
@@ -724,7 +831,7 @@ int32_t rapid_cd_debug_masks(const rapid_cd* cd, int64_t receiver, int32_t* out_
 int32_t rapid_cd_debug_counters(const rapid_cd* cd, int64_t receiver, int32_t* updates_in_progress, int32_t* seen_link_down) {
     if (!cd || receiver < 0 || receiver >= cd->R) { set_error("bad arguments"); return RAPID_EINVAL; }
     DeviceGuard g(cd->device);
-    cudaStreamSynchronize(cd->stream);   // clear() and the apply calls are asynchronous on the handle's stream
+    RAPID_CHECK(cd_wait(cd, false));     // clear() and asynchronous batches are still in flight on the handle's stream
     if (updates_in_progress) RAPID_CUDA(cudaMemcpy(updates_in_progress, cd->n_pre.p + receiver, sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (seen_link_down) {
         uint32_t f = 0;
@@ -738,18 +845,19 @@ int32_t rapid_cd_debug_stats(const rapid_cd* cd, int32_t* n_mixed, int32_t* n_in
                              int32_t* n_valid_cells) {
     if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
     DeviceGuard g(cd->device);
-    cudaStreamSynchronize(cd->stream);   // clear() and the apply calls are asynchronous on the handle's stream
-    BatchCounts bc;
-    RAPID_CUDA(cudaMemcpy(&bc, cd->counts.p, sizeof(bc), cudaMemcpyDeviceToHost));
+    RAPID_CHECK(cd_wait(cd, false));     // clear() and asynchronous batches are still in flight on the handle's stream
+    const BatchCounts& bc = cd->last;     // snapshot taken by the last kernel of the last batch
     if (n_mixed) *n_mixed = bc.n_mixed;
     if (n_batch_subjects) *n_batch_subjects = bc.n_batch_subj;
     if (n_valid_cells) *n_valid_cells = bc.n_valid;
-    if (n_inval_pairs) *n_inval_pairs = bucketed_pair_count(cd);
+    if (n_inval_pairs) *n_inval_pairs = cd->bucketed ? bc.n_pairs : 0;
     return RAPID_OK;
 }
 
 int32_t rapid_cd_last_path(const rapid_cd* cd, int32_t* path, int32_t* n_kernel_launches) {
     if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    RAPID_CHECK(cd_wait(cd, false));
     if (path) *path = cd->last_path;
     if (n_kernel_launches) *n_kernel_launches = cd->last_launches;
     return RAPID_OK;
@@ -757,6 +865,8 @@ int32_t rapid_cd_last_path(const rapid_cd* cd, int32_t* path, int32_t* n_kernel_
 
 int32_t rapid_cd_last_device_ms(const rapid_cd* cd, float* total_ms, float* main_kernel_ms) {
     if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    RAPID_CHECK(cd_wait(cd, false));
     if (total_ms) *total_ms = cd->last_ms;
     if (main_kernel_ms) *main_kernel_ms = cd->last_main_ms;
     return RAPID_OK;

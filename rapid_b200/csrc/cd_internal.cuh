@@ -1,6 +1,8 @@
 // Internal layout of the cut-detector handle (shared by cd_core.cu and cd_bucketed.cu).
 #pragma once
 
+#include <string>
+
 #include "common.cuh"
 
 namespace rapid {
@@ -20,15 +22,29 @@ namespace rapid {
 #define RF_RULE_GE_H   4u   // announced proposal == { popc >= H } (else == { bit 15 })
 #define RF_ANN_NOW     8u   // announced by the batch in flight (votes in rapid_fp_tally_cd)
 
-struct BatchCounts {       // written by the preprocessing kernels, read back once per batch
-    int32_t n_slots;       // S after slot assignment
+// Device-resident counters of a handle.  Sweep handles: initialised by the host before every batch and read back after the
+// prepare kernel.  Bucketed handles: they never leave the device inside a batch — `n_slots` persists from batch to batch, the
+// per-batch fields are reset by the batch's last kernel right after it copied the whole record to a snapshot the host reads at
+// its next synchronisation point (no host round trip between the kernels of a batch).
+struct BatchCounts {
+    int32_t n_slots;       // S after slot assignment (persists across batches)
     int32_t n_valid;       // cells that passed the filter
     int32_t n_batch_subj;  // distinct subjects with at least one valid cell in this batch
     int32_t any_down;      // some valid cell has status DOWN
-    int32_t bad_ring;      // index of a cell with ring >= K, or -1
-    int32_t bad_dst;       // index of a cell with dst outside [0, n + joiners), or -1
+    int32_t bad_ring;      // index of a cell with ring >= K, or -1 (the cell is dropped, the rest of the batch applies)
+    int32_t bad_dst;       // index of a cell with dst outside [0, n + joiners), or -1 (dropped likewise)
     int32_t n_mixed;       // bucketed: receivers needing exact interval resolution
-    int32_t n_inval;       // bucketed: receivers entering the invalidation pass
+    int32_t n_inval;       // bucketed: receivers that announce only the explicit part (bit-15 marks needed)
+    int32_t S_before;      // n_slots when the batch started: slots >= S_before are "fresh" (known-zero state, never read)
+    int32_t overflow;      // the batch needs more subject slots than the handle holds: NOTHING was applied
+    int32_t need_slots;    // ... and this many would do
+    int32_t n_times;       // PERMUTED delivery: receivers whose classification needed their own crossing moments
+    int32_t mixed_iters;   // fixpoint iterations of the interval analysis
+    int32_t n_pairs;       // (tile, subject) pairs on the invalidation work list
+    int32_t ticket;        // "last block done" counter of the resolve kernel
+    int32_t serial;        // serial of the batch this record describes
+    int32_t sticky_bad_ring, sticky_bad_dst, sticky_overflow;   // latched until the host collects them (asynchronous batches)
+    int32_t pad_;
 };
 
 struct CD {
@@ -42,8 +58,8 @@ struct CD {
     int64_t R = 0, rbegin = 0;
     size_t Rpad = 0;
     int nbuf = 1;                     // 2 = double-buffered rows (bucketed handles)
-    int32_t S = 0;                    // slots in use (host mirror)
-    int32_t S_before = 0;             // S when the batch in flight started
+    int32_t S = 0;                    // slots in use (host mirror; bucketed handles: as of the last synchronisation point)
+    int32_t S_before = 0;             // S when the batch in flight started (sweep handles)
     size_t S_cap = 0;
     int64_t ntot_cap = 0;             // capacity of slot_of / first_idx (node + joiner ids)
 
@@ -77,7 +93,16 @@ struct CD {
     DevBuf<int32_t> scan_tmp;         // [A]
     DevBuf<int32_t> scan_sums;        // tile totals of the prefix sums
     DevBuf<BatchCounts> counts;       // [1]
+    DevBuf<BatchCounts> counts_snap;  // [1] bucketed handles: copy of `counts` taken by the last kernel of a batch
     PinnedBuf<BatchCounts> h_counts;
+    cudaEvent_t ev_done = nullptr;    // recorded after the last enqueued operation (other streams wait on it)
+    bool pending = false;             // an asynchronous batch is in flight: its status has not been collected yet
+    int32_t deferred_rc = 0;          // status of asynchronous batches collected since the last rapid_cd_sync
+    std::string deferred_msg;
+    int32_t est_Sb = 0;               // batch subjects of the previous batch (grid sizing hint only)
+    int64_t est_A = 0;
+    BatchCounts last;                 // counters of the last collected batch
+    int32_t retries = 0;              // batches replayed after growing the subject capacity
     DevBuf<uint8_t> cub_tmp;
     // bucketed scratch lives in cd_bucketed.cu's own struct hung off here
     void* bucketed_state = nullptr;
@@ -125,6 +150,27 @@ struct SubjWalk {                     // first-occurrence ring sequence in arriv
     uint32_t time[16];
 };
 
+// Invalidation work list of a bucketed handle: the subjects that sit in the unstable band of SOME receiver and have an observer
+// that is itself a subject (only those can receive implicit reports, MultiNodeCutDetector.java:147-158), plus, per subject, the
+// 1024-receiver tiles in which that is the case.
+constexpr int SO_STRIDE = 16;
+struct WorkList {
+    uint8_t* has_so;                  // [slot] some observer of the subject has a slot
+    int32_t* so_tab;                  // [slot][SO_STRIDE] slots of the subject's K observers (-1: not a subject)
+    uint8_t* in_tile;                 // [slot][n_tiles] some receiver of the tile left the subject inside the band
+    int32_t* listed;                  // [slot] on the list
+    int32_t* slots;                   // the list
+    int32_t* count;
+    int32_t cap, n_tiles;
+};
+__device__ __forceinline__ void worklist_note(const WorkList& wl, int tile, int32_t slot) {
+    wl.in_tile[(size_t)slot * wl.n_tiles + tile] = 1;
+    if (*(volatile int32_t*)&wl.listed[slot] == 0 && atomicExch(&wl.listed[slot], 1) == 0) {
+        const int32_t at = atomicAdd(wl.count, 1);
+        if (at < wl.cap) wl.slots[at] = slot;
+    }
+}
+
 struct PrepOut {                      // where the prepare kernel writes the regrouped batch
     SubjDesc* desc;
     SubjWalk* walk;
@@ -134,6 +180,7 @@ struct PrepOut {                      // where the prepare kernel writes the reg
     int32_t* batch_index;             // [slot] -> index of the subject in the batch
     int32_t* seg_cnt;                 // [slot] scratch, all zero between batches
     int32_t* seg_pos;                 // [slot] scratch
+    WorkList wl;                      // invalidation work list (bucketed handles; wl.has_so == nullptr otherwise)
 };
 
 // implemented in cd_prepare.cu: filter + slot dictionary (+ regrouping by subject when po != nullptr) in ONE cooperative launch
@@ -142,10 +189,13 @@ int32_t prepare_batch(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev, co
 // implemented in cd_bucketed.cu
 int32_t bucketed_prep_buffers(CD* cd, int64_t A, PrepOut* po);
 
-int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, const BatchCounts& bc);
+int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl);     // enqueue only: no host synchronisation
 void bucketed_destroy(CD* cd);
 int32_t bucketed_clear(CD* cd);
-int32_t bucketed_pair_count(const CD* cd);
+int32_t bucketed_clear_sticky(CD* cd);
+// Wait for everything enqueued on the handle and collect the outcome of asynchronous batches (host mirrors of the slot count,
+// timings, latched errors).  Returns the latched status (and clears it) when take_status is set.
+int32_t cd_wait(const CD* cd, bool take_status);
 
 }  // namespace rapid
 

@@ -35,7 +35,10 @@ struct PrepArgs {
     int64_t cfg;
     int raw, K, L, H;
     int64_t n_members, n_total;
-    int32_t S_old, serial;
+    int32_t S_old, serial;   // S_old < 0: read it from bc->n_slots (bucketed handles keep it on the device)
+    int32_t S_cap;           // slots the handle can hold (bucketed); a batch that needs more is rolled back (bc->overflow)
+    WorkList wl;             // invalidation work list (bucketed): refreshed here whenever a subject gets a slot
+    const int32_t* obs;      // view: [id][K]
     int32_t* slot_of;
     int32_t* first_idx;
     int32_t* slot_subject;
@@ -89,10 +92,12 @@ __device__ __forceinline__ bool cell_is_new(const PrepArgs& a, int64_t i) {
     return a.slot_of[d] < 0 && a.first_idx[d] == (int32_t)i;
 }
 
-__global__ void __launch_bounds__(PREP_THREADS) k_prepare(const PrepArgs a) {
+__global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ int32_t warp_sums[PREP_THREADS / 32];
     const int t = threadIdx.x, G = gridDim.x, bid = blockIdx.x;
+    if (a.S_old < 0) a.S_old = a.bc->n_slots;          // read by every block before anyone can change it (P3 is two barriers away)
+    if (bid == 0 && t == 0) a.bc->S_before = a.S_old;
     // contiguous range of cells owned by this block (multiple of the block size)
     const int64_t per = ((a.A + G - 1) / G + PREP_THREADS - 1) / PREP_THREADS * PREP_THREADS;
     const int64_t c0 = min(a.A, (int64_t)bid * per), c1 = min(a.A, c0 + per);
@@ -142,9 +147,25 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(const PrepArgs a) {
             }
             base += total;
         }
-        if (bid == G - 1 && t == 0) a.bc->n_slots = base;                    // last block ends at S_old + all new subjects
+        if (bid == G - 1 && t == 0) a.bc->need_slots = base;                 // last block ends at S_old + all new subjects
     }
     grid.sync();
+    const int32_t S_new = a.bc->need_slots;
+    if (S_new > a.S_cap) {
+        // More subjects than the handle has rows for: undo the slot assignment of this batch and apply NOTHING (the host
+        // grows the handle and replays the batch; an asynchronous caller gets RAPID_ENOMEM at its next synchronisation).
+        for (int64_t i = c0 + t; i < c1; i += PREP_THREADS) {
+            if (a.cell_slot[i] != -2) continue;
+            const int32_t d = a.dst[i];
+            if (a.first_idx[d] == (int32_t)i) {
+                if (a.slot_of[d] >= a.S_old) a.slot_of[d] = -1;
+                a.first_idx[d] = INT_MAX;
+            }
+        }
+        if (bid == 0 && t == 0) a.bc->overflow = 1;
+        return;
+    }
+    if (bid == 0 && t == 0) a.bc->n_slots = S_new;
     // NOTE: first_idx is reset in P4 (a subject's first cell owner resets it), after every block has used it in P3
     // ---- P4: cell -> slot, cells per slot, distinct subjects ---------------------------------------------------------------------
     {
@@ -165,7 +186,27 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(const PrepArgs a) {
     if (!a.regroup) return;
     grid.sync();
     // ---- P5: prefix over slots (touched?, cells) --------------------------------------------------------------------------------
-    const int32_t S_new = a.bc->n_slots;
+    if (a.wl.has_so && S_new > a.S_old) {
+        // Some subject got a slot: refresh "which observers of this subject are subjects themselves" for every slot.  Only
+        // subjects with such an observer can ever receive an implicit report (MultiNodeCutDetector.java:147-158), so only
+        // they go on the invalidation work list.
+        for (int32_t sl = bid * PREP_THREADS + t; sl < S_new; sl += G * PREP_THREADS) {
+            const int32_t subject = a.slot_subject[sl];
+            bool any = false;
+            for (int k = 0; k < a.K; ++k) {
+                const int32_t o = a.obs[(size_t)subject * a.K + k];
+                const int32_t so = o >= 0 ? a.slot_of[o] : -1;
+                a.wl.so_tab[(size_t)sl * SO_STRIDE + k] = so;
+                if (so >= 0) any = true;
+            }
+            const bool old = sl < a.S_old && a.wl.has_so[sl];
+            a.wl.has_so[sl] = any ? 1 : 0;
+            if (any && !old && sl < a.S_old) {
+                // an observer of an OLDER subject joined the dictionary: the subject may sit in the unstable band of any tile
+                for (int tile = 0; tile < a.wl.n_tiles; ++tile) worklist_note(a.wl, tile, sl);
+            }
+        }
+    }
     const int32_t sper = ((S_new + G - 1) / G + PREP_THREADS - 1) / PREP_THREADS * PREP_THREADS;
     const int32_t q0 = min(S_new, bid * sper), q1 = min(S_new, q0 + sper);
     {
@@ -272,7 +313,11 @@ int32_t prepare_batch(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev, co
     a.A = A; a.dst = dst_dev; a.ring = ring_dev; a.status = status_dev; a.cell_cfg = cfg_dev; a.cfg = cfg;
     a.raw = cd->raw ? 1 : 0; a.K = cd->K; a.L = cd->L; a.H = cd->H;
     a.n_members = cd->view->n; a.n_total = cd->view->n + cd->view->nj;
-    a.S_old = cd->S; a.serial = ++cd->batch_serial;
+    a.S_old = cd->bucketed ? -1 : cd->S; a.serial = ++cd->batch_serial;
+    a.S_cap = cd->bucketed ? (int32_t)std::min<size_t>(cd->S_cap, 0x7fffffff) : INT_MAX;
+    a.obs = cd->view->obs.p;
+    memset(&a.wl, 0, sizeof(a.wl));
+    if (po) a.wl = po->wl;
     a.slot_of = cd->slot_of.p; a.first_idx = cd->first_idx.p; a.slot_subject = cd->slot_subject.p; a.touch = cd->touch.p;
     a.cell_slot = cd->cell_slot.p; a.bc = cd->counts.p;
     a.blk_a = cd->scan_sums.p; a.blk_b = cd->scan_sums.p + cd->prep_grid_max;

@@ -7,13 +7,17 @@
 // "first index" table, counted in an open-addressing table with warp-aggregated atomics, and the exact
 // decision point (the vote at which a count reaches N - floor((N-1)/4)) is recovered with a prefix scan so
 // that votesReceived / count at the moment of decision match the sequential reference.
+#include <cooperative_groups.h>
 #include <dlfcn.h>
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 
 #include "cd_internal.cuh"
 #include "scan.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace rapid {
 
@@ -26,9 +30,16 @@ struct FPState {
     int32_t cand[8];
     int32_t i_star;
     int32_t bad_sender;
+    int32_t n_entries;      // table entries created since the last reset (listed in FP::entries)
+    int32_t n_call;         // entries that received votes in the call in flight (listed in FP::call_list)
+    int32_t ticket;         // "last block done" counter of k_fp_tally_cd
+    int32_t too_many;       // more than 8 proposals reached the quorum in one call
 };
 
-struct FPResult;
+struct FPResult {
+    int32_t decided, len, count, received;
+    uint64_t h1, h2;
+};
 struct FP {
     int device = 0;
     bool decided_host = false;            // host mirror of FPState::decided
@@ -41,6 +52,9 @@ struct FP {
     DevBuf<int32_t> t_state, t_len, t_count, t_call;
     DevBuf<uint64_t> t_h1, t_h2;
     DevBuf<int32_t> ent, scan, scan_sums; // per-vote scratch
+    DevBuf<int32_t> entries, call_list;   // [T] created entries / entries voted for in the call in flight
+    DevBuf<int32_t> blk_cnt;              // [8][grid] per-block vote counts of the quorum candidates (k_fp_tally_cd)
+    int tally_grid = 0;                   // co-resident blocks of the cooperative tally kernel
     DevBuf<FPState> st;
     PinnedBuf<FPState> h_st;
     // staging for host-array votes
@@ -115,7 +129,10 @@ __global__ void k_fp_reset(int64_t sender_cap, int32_t* __restrict__ seen, uint3
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < sender_cap) seen[i] = INT_MAX;
     if (i < (int64_t)T) { t_state[i] = 0; t_count[i] = 0; t_call[i] = 0; }
-    if (i == 0) { st->decided = 0; st->decided_entry = 0; st->votes_received = 0; st->n_valid_call = 0; st->n_cand = 0; st->i_star = INT_MAX; st->bad_sender = -1; }
+    if (i == 0) {
+        st->decided = 0; st->decided_entry = 0; st->votes_received = 0; st->n_valid_call = 0; st->n_cand = 0; st->i_star = INT_MAX; st->bad_sender = -1;
+        st->n_entries = 0; st->n_call = 0; st->ticket = 0; st->too_many = 0;
+    }
 }
 
 // first vote of every sender in this call (votesReceived.contains(sender), :134)
@@ -139,7 +156,7 @@ __global__ void k_fp_insert(int64_t n, const int32_t* __restrict__ sender, const
                             const int32_t* __restrict__ lenv, int32_t* __restrict__ seen, uint32_t T,
                             int32_t* __restrict__ t_state, uint64_t* __restrict__ t_h1, uint64_t* __restrict__ t_h2,
                             int32_t* __restrict__ t_len, int32_t* __restrict__ t_call, int32_t* __restrict__ ent,
-                            FPState* __restrict__ st, int unique_senders, int direct) {
+                            FPState* __restrict__ st, int unique_senders, int direct, int32_t* __restrict__ entries) {
     // direct (sharded tally of a detector's own votes): no arrival-order bookkeeping is needed, so the counts go straight
     // to t_count (the caller passes it as t_call), the senders are marked as having voted and votesReceived grows here
     __shared__ int32_t s_key[16], s_val[16];
@@ -176,6 +193,7 @@ __global__ void k_fp_insert(int64_t n, const int32_t* __restrict__ sender, const
                     t_h1[pos] = h1; t_h2[pos] = h2; t_len[pos] = len;
                     __threadfence();
                     atomicExch(&t_state[pos], 2);
+                    entries[atomicAdd(&st->n_entries, 1)] = (int32_t)pos;
                     e = (int32_t)pos;
                     break;
                 }
@@ -209,6 +227,7 @@ __global__ void k_fp_insert(int64_t n, const int32_t* __restrict__ sender, const
                     t_h1[pos] = h1; t_h2[pos] = h2; t_len[pos] = len;
                     __threadfence();
                     atomicExch(&t_state[pos], 2);
+                    entries[atomicAdd(&st->n_entries, 1)] = (int32_t)pos;
                     break;
                 }
                 while (state == 1) state = atomicAdd(&t_state[pos], 0);
@@ -381,11 +400,6 @@ __global__ void k_fp_begin(FPState* st) {
     st->n_valid_call = 0; st->n_cand = 0; st->i_star = INT_MAX; st->bad_sender = -1;
 }
 
-struct FPResult {
-    int32_t decided, len, count, received;
-    uint64_t h1, h2;
-};
-
 __global__ void k_fp_result(const FPState* __restrict__ st, const uint64_t* __restrict__ t_h1, const uint64_t* __restrict__ t_h2,
                             const int32_t* __restrict__ t_len, const int32_t* __restrict__ t_count, FPResult* __restrict__ out) {
     FPResult r;
@@ -457,10 +471,315 @@ __global__ void k_fp_decide_sum_impl(const unsigned long long* __restrict__ buf,
     }
 }
 
+// one block: initialise the result, then look for the bucket that reached the quorum (k_fp_sum_begin + k_fp_decide_sum_impl fused)
+__global__ void __launch_bounds__(1024) k_fp_decide_sum(const unsigned long long* __restrict__ buf, unsigned long long Q,
+                                                        FPSumResult* __restrict__ out, FPState* __restrict__ st) {
+    if (threadIdx.x == 0) {
+        out->r.decided = 0; out->r.len = 0; out->r.count = 0; out->r.h1 = 0; out->r.h2 = 0;
+        out->r.received = (int32_t)buf[(size_t)SUM_BUCKETS * SUM_WORDS];
+        out->ambiguous = 0; out->pad = 0;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < SUM_BUCKETS; b += blockDim.x) {
+        const unsigned long long* w = buf + (size_t)b * SUM_WORDS;
+        const unsigned long long c = w[0];
+        if (c < Q || c == 0) continue;
+        bool ok = true;
+        for (int q = 1; q < SUM_WORDS; ++q) ok = ok && (w[q] % c == 0);
+        uint64_t h1 = 0, h2 = 0, len = 0;
+        if (ok) {
+            const uint64_t a1 = w[1] / c, a2 = w[2] / c, b1 = w[3] / c, b2 = w[4] / c;
+            len = w[5] / c;
+            ok = a1 <= 0xFFFFFFFFull && a2 <= 0xFFFFFFFFull && b1 <= 0xFFFFFFFFull && b2 <= 0xFFFFFFFFull && len <= 0x7FFFFFFFull;
+            h1 = (a1 << 32) | a2; h2 = (b1 << 32) | b2;
+            if (ok) {
+                const uint64_t m = fp_check_word(h1, h2, len);
+                ok = (w[6] / c == (m >> 32)) && (w[7] / c == (m & 0xFFFFFFFFull)) && ((h1 >> 52) == (uint64_t)b);
+            }
+        }
+        if (ok) {
+            out->r.decided = 1; out->r.h1 = h1; out->r.h2 = h2; out->r.len = (int32_t)len; out->r.count = (int32_t)c;
+            // remember the decision locally so that later votes are ignored (:138)
+            st->decided = 1; st->decided_entry = -1; st->votes_received = (int32_t)buf[(size_t)SUM_BUCKETS * SUM_WORDS];
+        } else {
+            out->ambiguous = 1;
+        }
+    }
+}
+
 __global__ void k_fp_sum_begin(const unsigned long long* __restrict__ buf, FPSumResult* __restrict__ out) {
     out->r.decided = 0; out->r.len = 0; out->r.count = 0; out->r.h1 = 0; out->r.h2 = 0;
     out->r.received = (int32_t)buf[(size_t)SUM_BUCKETS * SUM_WORDS];
     out->ambiguous = 0; out->pad = 0;
+}
+
+// ==================================================================================================================
+// k_fp_tally_cd: the fast-round tally of a detector's own votes in ONE cooperative launch.
+//
+// Every receiver that announced in the last batch votes for its proposal (FastPaxos.propose :94-108), in receiver order
+// (= arrival order on one GPU).  Senders are unique by construction, so "first vote of a sender" is just "has not voted
+// in an earlier call".  Phases (grid barriers in between, every block owns a CONTIGUOUS range of receivers so that
+// arrival order is block order):
+//   A  find-or-insert the proposal of every vote (warp- and block-aggregated counts -> t_call); the add that takes a
+//      proposal over the quorum nominates it as a candidate
+//   C  only if there is a candidate: the exact vote i* at which its running count reaches the quorum (per-block counts,
+//      prefix over blocks, in-block scan) — votes after i* are ignored, as the sequential reference would (:138)
+//   D  apply: votesReceived, counts, seen marks for the votes with index <= i*
+//   tail (last block): decision + result record, per-call scratch re-armed
+// direct != 0 (sharded tally): no arrival order across ranks — counts go straight to t_count and phase S adds this rank's
+// table to the all-reduce buffer.
+// ==================================================================================================================
+constexpr int TALLY_THREADS = 256;
+constexpr int SUM_BUCKETS_ = 4096, SUM_WORDS_ = 8;
+
+struct TallyCdArgs {
+    int64_t R, rbegin;
+    const uint32_t* rflags;
+    const int32_t* ring0;
+    const uint64_t* h1v;
+    const uint64_t* h2v;
+    const int32_t* lenv;
+    int64_t sender_cap;
+    int32_t* seen;
+    uint32_t T;
+    int32_t* t_state;
+    uint64_t* t_h1;
+    uint64_t* t_h2;
+    int32_t* t_len;
+    int32_t* t_count;
+    int32_t* t_call;
+    int32_t* ent;
+    int32_t* entries;
+    int32_t* call_list;
+    int32_t* blk_cnt;
+    FPState* st;
+    int32_t Q;
+    int direct;
+    unsigned long long* sumbuf;
+    FPResult* out;
+};
+
+__device__ __forceinline__ int32_t fp_find_or_insert(const TallyCdArgs& a, uint64_t h1, uint64_t h2, int32_t len) {
+    uint32_t pos = fp_slot_hash(h1, h2, len) & (a.T - 1);
+    for (;;) {
+        int32_t state = *(volatile int32_t*)&a.t_state[pos];              // published entries need no atomic
+        if (state == 0) state = atomicCAS(&a.t_state[pos], 0, 1);
+        if (state == 0) {                                                 // claimed an empty entry: publish the key
+            a.t_h1[pos] = h1; a.t_h2[pos] = h2; a.t_len[pos] = len;
+            __threadfence();
+            atomicExch(&a.t_state[pos], 2);
+            a.entries[atomicAdd(&a.st->n_entries, 1)] = (int32_t)pos;
+            return (int32_t)pos;
+        }
+        while (state == 1) state = atomicAdd(&a.t_state[pos], 0);          // another warp is publishing
+        __threadfence();
+        if (a.t_h1[pos] == h1 && a.t_h2[pos] == h2 && a.t_len[pos] == len) return (int32_t)pos;
+        pos = (pos + 1) & (a.T - 1);
+    }
+}
+
+// add c votes of this call to entry e; nominate it if THIS add takes it over the quorum
+__device__ __forceinline__ void fp_add_call(const TallyCdArgs& a, int32_t e, int32_t c) {
+    if (a.direct) { atomicAdd(&a.t_count[e], c); return; }
+    const int32_t old = atomicAdd(&a.t_call[e], c);
+    if (old == 0) a.call_list[atomicAdd(&a.st->n_call, 1)] = e;
+    const int32_t before = a.t_count[e] + old;
+    if (before < a.Q && before + c >= a.Q) {
+        const int32_t at = atomicAdd(&a.st->n_cand, 1);
+        if (at < 8) a.st->cand[at] = e; else a.st->too_many = 1;
+    }
+}
+
+__device__ __forceinline__ int32_t tally_block_scan(int32_t v, int32_t* warp_sums, int32_t* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += x;
+    }
+    __syncthreads();
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int32_t s = lane < (TALLY_THREADS >> 5) ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t x = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += x;
+        }
+        if (lane < (TALLY_THREADS >> 5)) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    *total = warp_sums[(TALLY_THREADS >> 5) - 1];
+    return (wid ? warp_sums[wid - 1] : 0) + inc - v;
+}
+
+__global__ void __launch_bounds__(TALLY_THREADS) k_fp_tally_cd(const TallyCdArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int32_t s_key[16], s_val[16], s_recv, s_last;
+    __shared__ int32_t warp_sums[TALLY_THREADS / 32];
+    const int t = threadIdx.x, G = gridDim.x, bid = blockIdx.x;
+    const int64_t per = ((a.R + G - 1) / G + TALLY_THREADS - 1) / TALLY_THREADS * TALLY_THREADS;
+    const int64_t c0 = min(a.R, (int64_t)bid * per), c1 = min(a.R, c0 + per);
+    const bool was_decided = a.st->decided != 0;          // :138 — everything after the decision is ignored
+
+    auto block_flush = [&](bool to_count) {               // block-level partial counts -> global
+        __syncthreads();
+        if (t < 16 && s_key[t] >= 0) {
+            if (to_count) atomicAdd(&a.t_count[s_key[t]], s_val[t]);
+            else fp_add_call(a, s_key[t], s_val[t]);
+        }
+        __syncthreads();
+        if (t < 16) { s_key[t] = -1; s_val[t] = 0; }
+        __syncthreads();
+    };
+    auto block_add = [&](int32_t e, int32_t c, bool to_count) {   // called by one lane per (warp, entry)
+        int slot = -1;
+        for (int q = 0; q < 16; ++q) {
+            const int32_t k = atomicCAS(&s_key[q], -1, e);
+            if (k == -1 || k == e) { slot = q; break; }
+        }
+        if (slot >= 0) atomicAdd(&s_val[slot], c);
+        else if (to_count) atomicAdd(&a.t_count[e], c);           // more than 16 distinct proposals in one block
+        else fp_add_call(a, e, c);
+    };
+
+    if (t < 16) { s_key[t] = -1; s_val[t] = 0; }
+    if (t == 0) s_recv = 0;
+    __syncthreads();
+    if (!was_decided) {
+        // ---- A: one table probe per distinct fingerprint per warp ------------------------------------------------------------
+        for (int64_t base = c0; base < c1; base += TALLY_THREADS) {
+            const int64_t i = base + t;
+            bool valid = false;
+            uint64_t h1 = 0, h2 = 0;
+            int32_t len = 0, sender = -1;
+            if (i < c1 && (a.rflags[i] & RF_ANN_NOW)) {
+                sender = a.ring0[a.rbegin + i];
+                if (sender >= 0 && sender < a.sender_cap && a.seen[sender] != -1) {
+                    valid = true;
+                    h1 = a.h1v[i]; h2 = a.h2v[i]; len = a.lenv[i];
+                }
+            }
+            int32_t e = -1;
+            const unsigned active = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const unsigned same = __match_any_sync(active, h1 ^ rotl64(h2, 21) ^ ((uint64_t)(uint32_t)len << 1));
+                const int leader = __ffs(same) - 1;
+                if ((t & 31) == leader) e = fp_find_or_insert(a, h1, h2, len);
+                e = __shfl_sync(same, e, leader);
+                const uint64_t lh1 = __shfl_sync(same, h1, leader), lh2 = __shfl_sync(same, h2, leader);
+                const int32_t llen = __shfl_sync(same, len, leader);
+                const bool mine = lh1 == h1 && lh2 == h2 && llen == len;
+                if (!mine) e = fp_find_or_insert(a, h1, h2, len);           // folded-key collision inside the warp (astronomically rare)
+                const unsigned grp = __match_any_sync(same, e);             // the leader's group minus the collided lanes, per entry
+                if ((t & 31) == __ffs(grp) - 1) block_add(e, __popc(grp), a.direct != 0);
+                if (a.direct) a.seen[sender] = -1;
+            }
+            if (i < c1) a.ent[i] = e;
+            if ((t & 31) == 0 && active) atomicAdd(&s_recv, __popc(active));
+        }
+        block_flush(a.direct != 0);
+        if (t == 0 && s_recv) {
+            if (a.direct) atomicAdd(&a.st->votes_received, s_recv);
+            else atomicAdd(&a.st->n_valid_call, s_recv);
+        }
+    }
+    if (a.direct) {
+        // ---- S: this rank's table -> the all-reduce buffer (count-weighted sums per 12-bit bucket of the fingerprint) ------
+        grid.sync();
+        const int32_t ne = *(volatile int32_t*)&a.st->n_entries;
+        if (bid == 0 && t == 0) a.sumbuf[(size_t)SUM_BUCKETS_ * SUM_WORDS_] = (unsigned long long)*(volatile int32_t*)&a.st->votes_received;
+        for (int32_t q = bid * TALLY_THREADS + t; q < ne; q += G * TALLY_THREADS) {
+            const int32_t e = a.entries[q];
+            const unsigned long long c = (unsigned long long)a.t_count[e];
+            if (c == 0) continue;
+            const uint64_t h1 = a.t_h1[e], h2 = a.t_h2[e], len = (uint64_t)(uint32_t)a.t_len[e], m = fp_check_word(h1, h2, len);
+            unsigned long long* b = a.sumbuf + (size_t)(h1 >> 52) * SUM_WORDS_;
+            atomicAdd(b + 0, c);
+            atomicAdd(b + 1, c * (h1 >> 32)); atomicAdd(b + 2, c * (h1 & 0xFFFFFFFFull));
+            atomicAdd(b + 3, c * (h2 >> 32)); atomicAdd(b + 4, c * (h2 & 0xFFFFFFFFull));
+            atomicAdd(b + 5, c * len);
+            atomicAdd(b + 6, c * (m >> 32)); atomicAdd(b + 7, c * (m & 0xFFFFFFFFull));
+        }
+        return;
+    }
+    grid.sync();
+    const int32_t n_cand = was_decided ? 0 : min(8, *(volatile int32_t*)&a.st->n_cand);
+    int64_t limit = INT64_MAX;
+    if (n_cand > 0) {
+        // ---- C: the vote at which a candidate's running count reaches the quorum ------------------------------------------------
+        for (int c = 0; c < n_cand; ++c) {
+            const int32_t e = ((volatile FPState*)a.st)->cand[c];
+            int32_t mine = 0;
+            for (int64_t i = c0 + t; i < c1; i += TALLY_THREADS) mine += a.ent[i] == e ? 1 : 0;
+            int32_t total;
+            tally_block_scan(mine, warp_sums, &total);
+            if (t == 0) a.blk_cnt[(size_t)c * G + bid] = total;
+        }
+        grid.sync();
+        for (int c = 0; c < n_cand; ++c) {
+            const int32_t e = ((volatile FPState*)a.st)->cand[c];
+            const int32_t need = a.Q - a.t_count[e];                       // >= 1: it was below the quorum before this call
+            int32_t before = 0;
+            for (int q = t; q < bid; q += TALLY_THREADS) before += *(volatile int32_t*)&a.blk_cnt[(size_t)c * G + q];
+            int32_t prefix;
+            tally_block_scan(before, warp_sums, &prefix);
+            const int32_t own = *(volatile int32_t*)&a.blk_cnt[(size_t)c * G + bid];
+            if (!(prefix < need && need <= prefix + own)) continue;       // uniform across the block
+            for (int64_t base = c0; base < c1; base += TALLY_THREADS) {
+                const int64_t i = base + t;
+                const int32_t f = (i < c1 && a.ent[i] == e) ? 1 : 0;
+                int32_t total;
+                const int32_t off = tally_block_scan(f, warp_sums, &total);
+                if (f && prefix + off + 1 == need) atomicMin(&a.st->i_star, (int32_t)i);
+                prefix += total;
+            }
+        }
+        grid.sync();
+        limit = (int64_t)*(volatile int32_t*)&a.st->i_star;
+    }
+    if (!was_decided) {
+        // ---- D: votesReceived.add(sender) :141, count :142-144 for the votes up to the decision ------------------------------
+        if (t == 0) s_recv = 0;
+        __syncthreads();
+        for (int64_t base = c0; base < c1; base += TALLY_THREADS) {
+            const int64_t i = base + t;
+            const int32_t e = i < c1 ? a.ent[i] : -1;
+            const bool counted = e >= 0 && i <= limit;
+            if (counted) a.seen[a.ring0[a.rbegin + i]] = -1;
+            const unsigned m = __ballot_sync(0xffffffffu, counted);
+            if (counted) {
+                const unsigned same = __match_any_sync(m, e);
+                if ((t & 31) == __ffs(same) - 1) block_add(e, __popc(same), true);
+            }
+            if ((t & 31) == 0 && m) atomicAdd(&s_recv, __popc(m));
+        }
+        block_flush(true);
+        if (t == 0 && s_recv) atomicAdd(&a.st->votes_received, s_recv);
+    }
+    // ---- tail: the last block publishes the outcome and re-arms the per-call scratch ---------------------------------------------
+    __syncthreads();
+    if (t == 0) { __threadfence(); s_last = atomicAdd(&a.st->ticket, 1) == G - 1; }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    volatile FPState* st = a.st;
+    const int32_t nc = st->n_call;
+    for (int32_t q = t; q < nc; q += TALLY_THREADS) a.t_call[a.call_list[q]] = 0;
+    if (t == 0) {
+        if (!was_decided && n_cand > 0 && st->i_star < INT_MAX) { st->decided = 1; st->decided_entry = a.ent[st->i_star]; }
+        FPResult r;
+        r.decided = st->decided; r.received = st->votes_received; r.len = 0; r.count = 0; r.h1 = 0; r.h2 = 0;
+        if (r.decided && st->decided_entry >= 0) {
+            const int32_t e = st->decided_entry;
+            r.h1 = a.t_h1[e]; r.h2 = a.t_h2[e]; r.len = a.t_len[e]; r.count = *(volatile int32_t*)&a.t_count[e];
+        }
+        if (st->too_many) r.decided = -1;                  // reported as RAPID_EUNSUPPORTED by the host
+        *a.out = r;
+        st->n_call = 0; st->n_cand = 0; st->n_valid_call = 0; st->i_star = INT_MAX; st->ticket = 0; st->too_many = 0;
+    }
 }
 
 static int32_t fp_reset_call_state(FP* fp) {        // per-call fields only; no host round trip
@@ -487,7 +806,7 @@ static int32_t tally_device(FP* fp, int64_t n, const int32_t* sender, const int6
     const bool direct = !exact_order && unique_senders;
     k_fp_insert<<<g, TB, 0, s>>>(n, sender, vcfg, fp->cfg, fp->sender_cap, h1, h2, len, fp->seen.p, fp->T, fp->t_state.p,
                                  fp->t_h1.p, fp->t_h2.p, fp->t_len.p, direct ? fp->t_count.p : fp->t_call.p, fp->ent.p, fp->st.p,
-                                 unique_senders ? 1 : 0, direct ? 1 : 0);
+                                 unique_senders ? 1 : 0, direct ? 1 : 0, fp->entries.p);
     if (direct) { RAPID_KERNEL_CHECK(); fp->last_launches += 1; return RAPID_OK; }
     const unsigned gt = (unsigned)ceil_div<uint32_t>(fp->T, TB);
     k_fp_candidates<<<gt, TB, 0, s>>>(fp->T, fp->t_count.p, fp->t_call.p, (int32_t)fp->Q, fp->st.p);
@@ -581,6 +900,8 @@ int32_t rapid_fp_create(rapid_fp** out, int64_t cfg_id, int64_t membership_size,
         if ((rc = fp->t_len.reserve(T))) break;
         if ((rc = fp->t_count.reserve(T))) break;
         if ((rc = fp->t_call.reserve(T))) break;
+        if ((rc = fp->entries.reserve(T))) break;
+        if ((rc = fp->call_list.reserve(T))) break;
         if ((rc = fp->t_h1.reserve(T))) break;
         if ((rc = fp->t_h2.reserve(T))) break;
         if ((rc = fp->st.reserve(1))) break;
@@ -596,6 +917,7 @@ int32_t rapid_fp_create(rapid_fp** out, int64_t cfg_id, int64_t membership_size,
         cudaMemsetAsync(fp->t_count.p, 0, T * sizeof(int32_t), fp->stream);
         cudaMemsetAsync(fp->t_call.p, 0, T * sizeof(int32_t), fp->stream);
         cudaMemsetAsync(fp->st.p, 0, sizeof(FPState), fp->stream);
+        k_fp_reset<<<1, 32, 0, fp->stream>>>(0, fp->seen.p, 0, fp->t_state.p, fp->t_count.p, fp->t_call.p, fp->st.p);   // i_star = INT_MAX, bad_sender = -1
         if (cudaStreamSynchronize(fp->stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "init", __FILE__, __LINE__); break; }
     } while (0);
     if (rc) { rapid_fp_destroy(fp); return rc; }
@@ -660,54 +982,79 @@ int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, in
     if (!fp || !cd) { set_error("NULL handle"); return RAPID_EINVAL; }
     if (fp->device != cd->device) { set_error("fp and cd live on different devices"); return RAPID_EINVAL; }
     if (cd->raw) { set_error("RAW detectors do not announce proposals"); return RAPID_EINVAL; }
+    if (comm && comm->device != fp->device) { set_error("comm and fp live on different devices"); return RAPID_EINVAL; }
     DeviceGuard g(fp->device);
     cudaStream_t s = fp->stream;
-    const int TB = 256;
     const int64_t R = cd->R;
-    RAPID_CHECK(fp->v_sender.reserve((size_t)R));
-    RAPID_CUDA(cudaEventRecord(fp->ev0, s));
-    k_fp_votes_from_cd<<<(unsigned)ceil_div<int64_t>(R, TB), TB, 0, s>>>(R, cd->rflags.p, cd->view->ring.p, cd->rbegin, fp->v_sender.p);
-    RAPID_KERNEL_CHECK();
-    // single GPU: exact arrival order = receiver order.  Sharded: counts only (order across ranks is undefined).
-    RAPID_CHECK(tally_device(fp, R, fp->v_sender.p, nullptr, cd->out_h1.p, cd->out_h2.p, cd->out_len.p, 1, comm == nullptr, true));
-    fp->last_launches += 1;
-    if (comm == nullptr) {
-        RAPID_CUDA(cudaEventRecord(fp->ev1, s));
-        RAPID_CHECK(read_result(fp, decided, decided_hash, decided_hash2, decided_len, decided_count, votes_received));
-        cudaEventElapsedTime(&fp->last_ms, fp->ev0, fp->ev1);
-        return RAPID_OK;
+    RAPID_CHECK(fp->ent.reserve((size_t)R));
+    if (fp->tally_grid == 0) {
+        int dev = 0, sms = 148, per = 4;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_fp_tally_cd, TALLY_THREADS, 0);
+        fp->tally_grid = std::max(1, sms * std::max(per, 1));
+        RAPID_CHECK(fp->blk_cnt.reserve((size_t)8 * fp->tally_grid));
     }
-    // ---- sharded: radix histogram of the local table -> ONE all-reduce (sum) -> verify the winning bucket holds a
-    // single fingerprint with a 6-word all-reduce (max); refine digit by digit only if two fingerprints share it.
-    if (comm->device != fp->device) { set_error("comm and fp live on different devices"); return RAPID_EINVAL; }
-    const unsigned gt = (unsigned)ceil_div<uint32_t>(fp->T, TB);
-    {   // the common case: ONE all-reduce, one readback
-        const size_t words = (size_t)(SUM_BUCKETS + 1) * SUM_WORDS;
+    // The detector's outputs are produced on ITS stream (possibly by an asynchronous batch still in flight): order this
+    // tally after them on the device instead of waiting on the host.
+    RAPID_CUDA(cudaStreamWaitEvent(s, cd->ev_done, 0));
+    RAPID_CUDA(cudaEventRecord(fp->ev0, s));
+    const bool direct = comm != nullptr;
+    const size_t words = (size_t)(SUM_BUCKETS + 1) * SUM_WORDS;
+    if (direct) {
         RAPID_CHECK(fp->sumbuf.reserve(words));
         RAPID_CUDA(cudaMemsetAsync(fp->sumbuf.p, 0, words * sizeof(unsigned long long), s));
-        k_fp_hist_sum<<<gt, TB, 0, s>>>(fp->T, fp->t_state.p, fp->t_h1.p, fp->t_h2.p, fp->t_len.p, fp->t_count.p, fp->st.p, fp->sumbuf.p);
-        RAPID_KERNEL_CHECK();
+    }
+    TallyCdArgs ta;
+    ta.R = R; ta.rbegin = cd->rbegin; ta.rflags = cd->rflags.p; ta.ring0 = cd->view->ring.p;
+    ta.h1v = cd->out_h1.p; ta.h2v = cd->out_h2.p; ta.lenv = cd->out_len.p;
+    ta.sender_cap = fp->sender_cap; ta.seen = fp->seen.p; ta.T = fp->T;
+    ta.t_state = fp->t_state.p; ta.t_h1 = fp->t_h1.p; ta.t_h2 = fp->t_h2.p; ta.t_len = fp->t_len.p;
+    ta.t_count = fp->t_count.p; ta.t_call = fp->t_call.p; ta.ent = fp->ent.p;
+    ta.entries = fp->entries.p; ta.call_list = fp->call_list.p; ta.blk_cnt = fp->blk_cnt.p;
+    ta.st = fp->st.p; ta.Q = (int32_t)fp->Q; ta.direct = direct ? 1 : 0; ta.sumbuf = fp->sumbuf.p;
+    ta.out = (FPResult*)fp->d_res_raw.p;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(fp->tally_grid, ceil_div<int64_t>(R, TALLY_THREADS)));
+    void* args[] = {(void*)&ta};
+    RAPID_CUDA(cudaLaunchCooperativeKernel((void*)k_fp_tally_cd, dim3((unsigned)grid), dim3(TALLY_THREADS), args, 0, s));
+    fp->last_launches = 1;
+    if (!direct) {
+        // single GPU: exact arrival order = receiver order; ONE launch, one read-back
+        RAPID_CUDA(cudaMemcpyAsync(fp->h_res_raw.p, fp->d_res_raw.p, sizeof(FPResult), cudaMemcpyDeviceToHost, s));
+        RAPID_CUDA(cudaEventRecord(fp->ev1, s));
+        RAPID_CUDA(cudaStreamSynchronize(s));
+        cudaEventElapsedTime(&fp->last_ms, fp->ev0, fp->ev1);
+        const FPResult r = *(const FPResult*)fp->h_res_raw.p;
+        RAPID_CHECK(cd_wait(cd, true));                  // outcome of the (asynchronous) batch these votes came from
+        if (r.decided < 0) { set_error("more than 8 proposals reached the quorum in one call"); return RAPID_EUNSUPPORTED; }
+        fp->decided_host = r.decided != 0;
+        if (decided) *decided = r.decided;
+        if (votes_received) *votes_received = r.received;
+        if (decided_hash) *decided_hash = r.h1;
+        if (decided_hash2) *decided_hash2 = r.h2;
+        if (decided_len) *decided_len = r.len;
+        if (decided_count) *decided_count = r.count;
+        return RAPID_OK;
+    }
+    // ---- sharded: count-weighted sums of the local table -> ONE all-reduce (sum) -> the winning bucket gives the proposal
+    // back by exact division; refine digit by digit only if two fingerprints share a quorum-sized bucket.
+    const int TB = 256;
+    const unsigned gt = (unsigned)ceil_div<uint32_t>(fp->T, TB);
+    // RAPID_B200_FORCE_REFINE: test hook — take the refinement path even though no bucket is ambiguous
+    if (getenv("RAPID_B200_FORCE_REFINE") == nullptr) {   // the common case: ONE all-reduce, one readback
         RAPID_NCCL(g_nccl.AllReduce(fp->sumbuf.p, fp->sumbuf.p, words, NCCL_UINT64, NCCL_SUM, comm->comm, s));
         FPSumResult* dres = (FPSumResult*)fp->d_res_raw.p;
-        k_fp_sum_begin<<<1, 1, 0, s>>>(fp->sumbuf.p, dres);
-        k_fp_decide_sum_impl<<<SUM_BUCKETS / TB, TB, 0, s>>>(fp->sumbuf.p, (unsigned long long)fp->Q, dres);
+        k_fp_decide_sum<<<1, 1024, 0, s>>>(fp->sumbuf.p, (unsigned long long)fp->Q, dres, fp->st.p);
         RAPID_KERNEL_CHECK();
-        fp->last_launches += 3;
+        fp->last_launches += 1;
         RAPID_CUDA(cudaMemcpyAsync(fp->h_res_raw.p, dres, sizeof(FPSumResult), cudaMemcpyDeviceToHost, s));
         RAPID_CUDA(cudaEventRecord(fp->ev1, s));
         RAPID_CUDA(cudaStreamSynchronize(s));
+        RAPID_CHECK(cd_wait(cd, true));
         const FPSumResult res = *(const FPSumResult*)fp->h_res_raw.p;
         if (!res.ambiguous) {
             cudaEventElapsedTime(&fp->last_ms, fp->ev0, fp->ev1);
-            if (res.r.decided) {      // remember the decision locally so later votes are ignored (:138)
-                FPState stn;
-                memset(&stn, 0, sizeof(stn));
-                stn.decided = 1; stn.decided_entry = -1; stn.votes_received = res.r.received; stn.i_star = INT_MAX; stn.bad_sender = -1;
-                *fp->h_st.p = stn;
-                RAPID_CUDA(cudaMemcpyAsync(fp->st.p, fp->h_st.p, sizeof(FPState), cudaMemcpyHostToDevice, s));
-                RAPID_CUDA(cudaStreamSynchronize(s));
-                fp->decided_host = true;
-            }
+            if (res.r.decided) fp->decided_host = true;
             if (decided) *decided = res.r.decided;
             if (decided_hash) *decided_hash = res.r.h1;
             if (decided_hash2) *decided_hash2 = res.r.h2;
@@ -717,6 +1064,9 @@ int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, in
             return RAPID_OK;
         }
         // two proposals share a quorum-sized bucket: fall through to the digit-by-digit refinement
+    } else {
+        RAPID_CUDA(cudaStreamSynchronize(s));
+        RAPID_CHECK(cd_wait(cd, true));
     }
     Prefix pf;
     pf.n = 0;

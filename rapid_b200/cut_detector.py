@@ -158,6 +158,28 @@ class VirtualCluster:
                                              N.ptr(ln), N.ptr(ann)))
         return AlertBatchResult(h1, h2, ln, ann) if read_outputs else None
 
+    def handleBatchDevice(self, cfg_id, n_cells, dst_dev, ring_dev, status_dev, cell_cfg_dev=0, blocked_dev=0, perm_seed=None,
+                          wait=False):
+        """Cell arrays already resident in device memory (raw device pointers).  wait=False only ENQUEUES the batch
+        (rapid_cd_apply_batch_dev_async): its status is collected by sync() / FastPaxos.tallyCluster."""
+        d = None
+        if blocked_dev or perm_seed is not None:
+            d = N.Delivery()
+            d.flags = 0
+            if blocked_dev:
+                d.flags |= N.DELIVERY_BLOCKED
+                d.blocked = blocked_dev
+            if perm_seed is not None:
+                d.flags |= N.DELIVERY_PERMUTED
+                d.perm_seed = perm_seed & 0xFFFFFFFFFFFFFFFF
+        fn = N.lib().rapid_cd_apply_batch_dev if wait else N.lib().rapid_cd_apply_batch_dev_async
+        N.check(fn(self._h, int(cfg_id), int(n_cells), None, dst_dev, ring_dev, status_dev, cell_cfg_dev or None,
+                   C.byref(d) if d is not None else None))
+
+    def sync(self):
+        """wait for asynchronous batches; raises if one of them failed"""
+        N.check(N.lib().rapid_cd_sync(self._h))
+
     def handleBatches(self, cfg_id, src, dst, ring, status, batch_off, cell_cfg=None, blocked=None, bitmap=None):
         """A sequence of BatchedAlertMessages (batch b = cells batch_off[b]:batch_off[b+1]) delivered in order, with the
         announcedProposal gating between them (MembershipService.java:318-319).  Sweep handles only.

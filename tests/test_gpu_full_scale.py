@@ -108,7 +108,7 @@ def test_c4_hundred_thousand_nodes_flip_flop_stream():
     decided = None
     for b in batches:
         res = cl.handleBatch(cfg, None, b.dst, b.ring, b.status, blocked=blocked, perm_seed=b.meta["perm_seed"])
-        assert cl.lastPath()[0] == 3                                # per-receiver order: the generic kernel
+        assert cl.lastPath()[0] == 4                                # per-receiver order, every cell to everyone: uniform kernel, moments on demand
         ann = res.proposal_len > 0
         # whoever announces in a batch announces a subset of the flapping nodes; once everything is in, the whole set
         assert (res.proposal_len[ann] <= len(batches[-1].expected_cut)).all()
