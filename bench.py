@@ -1,23 +1,29 @@
 #!/usr/bin/env python
 """bench.py — alert cells / second to a converged, quorum-decided cut (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nodes n] [--workload c5|c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c5|c4|c3|c2] [--nodes n]
 
-One "step" = one pass of the hot path over one synthetic alert batch:
-    filter -> per-receiver cut detection (subject-bucketed kernel) -> implicit invalidation -> per-node proposal
+One "step" = one pass of the hot path over one synthetic alert stream, from an empty detector to the decision:
+    [per batch] filter -> per-receiver cut detection (subject-bucketed kernels) -> implicit invalidation -> per-node proposal
     fingerprints -> fast-round vote tally [-> NCCL histogram all-reduce when sharded] -> decision on the host.
-Default workload (N=1): BASELINE config 5 — 1,000,000 virtual nodes, K=10, H=9, L=4, a 1 % churn batch (5,000 crashes
-+ 5,000 joins, ~10^5 alert cells) — on however many GPUs --gpus names; receivers are sharded by ring-0 range, the
-cluster size stays fixed ("scaling": "strong").
+Workloads:
+    c5 (default)  BASELINE config 5: 1,000,000 virtual nodes, K=10 H=9 L=4, ONE 1 % churn batch (5,000 crashes + 5,000 joins,
+                  ~10^5 alert cells), every receiver gets the batch in array order
+    c4            BASELINE config 4: 100,000 nodes, 1 % flip-flop stream over T = 8 batches with 1/4 duplicate re-sends, every
+                  receiver applies each batch in ITS OWN permuted order, detector state carried from batch to batch; the step
+                  ends with the batch in which the cut is decided (duplicates count as applied cells)
+    c3 / c2       BASELINE configs 3 / 2 (10,000-node correlated partition / 2,000-node simultaneous crash), one batch
+Receivers are sharded over the GPUs by ring-0 range; the cluster size stays fixed ("scaling": "strong").
 
-`value`  : device time only, cell arrays resident in HBM when the timed region starts (CUDA events on the library's
-           streams, summed over the calls of a step, max over ranks).  The epoch reset between steps (clear() / new
-           FastPaxos, the reference's decideViewChange) is outside the timed region.
-`e2e`    : the same through the host-facing C ABI: host arrays in, H2D copies, epoch reset, kernels, decision read
-           back — wall clock.
---impl reference : the reference's own CPU path.  The reference is Java and cannot be built or run in this image (no
-           JDK), so this times oracle/'s literal C++ restatement of it (kind "port") on all host cores, on a bounded
-           sample of the same workload, extrapolated linearly (see `sample`).
+`value`  : cells of one step / device time of one step, with the cell arrays resident in HBM when the timed region starts.
+           The timed region is ONE device-side stopwatch over all K steps (a CUDA event on the detector's stream before the
+           first step, one on the tally's stream after the last): kernels, the epoch resets between steps, the one host
+           synchronisation per batch (the decision) and every idle gap in between are inside it.  Max over ranks.
+`e2e`    : the same through the host-facing C ABI: host arrays in, H2D copies, kernels, decision read back — wall clock.
+--impl reference : the reference's own CPU path.  The reference is Java and cannot be built or run in this image (no JDK), so
+           this times oracle/'s literal C++ restatement of it (kind "port") on all host cores on a FIXED sample of the same
+           workload (8 virtual nodes per thread x the full stream, one FastPaxos instance per thread x 4096 votes); `value` is
+           the measured rate of that sample, the whole-cluster extrapolation is a labelled side field.
 """
 import argparse
 import ctypes as C
@@ -37,6 +43,7 @@ if ROOT not in sys.path:
 K, H, L = 10, 9, 4          # Cluster.java:72-74
 METRIC = "alert_cells_per_sec_to_converged_cut"
 UNIT = "cells/s"
+DEFAULT_NODES = {"c5": 1_000_000, "c4": 100_000, "c3": 10_000, "c2": 2_000}
 
 
 def log(*a):
@@ -49,36 +56,61 @@ def parse():
     p.add_argument("--steps", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--nodes", type=int, default=1_000_000)
-    p.add_argument("--workload", default="c5", choices=["c5", "c2", "c3"])
+    p.add_argument("--nodes", type=int, default=0, help="cluster size (default: the BASELINE size of the workload)")
+    p.add_argument("--workload", default="c5", choices=["c5", "c4", "c3", "c2"])
     p.add_argument("--kernel", default="auto", choices=["auto", "bucketed", "sweep"])
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-carried", action="store_true", help="skip the extra carried-state (read-modify-write) measurement of c5")
     p.add_argument("--emulate-shard", type=int, default=0,
                    help="tuning aid: run rank 0's shard of a G-way run on ONE GPU without NCCL (no decision is reached)")
-    p.add_argument("--cpu-seconds", type=float, default=20.0, help="budget for the CPU baseline sample")
-    return p.parse_args()
-
-
-def workload_name(args, A, S):
-    n = args.nodes
-    if args.workload == "c5":
-        return "C5 %d-node K=10 H=9 L=4, 1%% churn batch (%d DOWN + %d UP subjects, %d cells)" % (n, n // 200, n // 200, A)
-    if args.workload == "c2":
-        return "C2 %d-node K=10 H=9 L=4, 1%% simultaneous crash (%d subjects, %d cells)" % (n, S, A)
-    return "C3 %d-node K=10 H=9 L=4, 5%% correlated one-way partition (%d subjects, %d cells)" % (n, S, A)
-
-
-def make_batch(args, W, obs, joiner_obs, ring0):
-    n = args.nodes
-    if args.workload == "c5":
-        return W.c5_churn(obs, joiner_obs, n, n // 200, n // 200)
-    if args.workload == "c2":
-        return W.c2_simultaneous_crash(obs, n, 0.01)
-    return W.c3_correlated_partition(obs, ring0, n, 0.05)
+    a = p.parse_args()
+    if a.nodes <= 0:
+        a.nodes = DEFAULT_NODES[a.workload]
+    return a
 
 
 def n_joiners(args):
     return args.nodes // 200 if args.workload == "c5" else 0
+
+
+class Stream:
+    """The workload: a list of alert batches applied in order to detectors that start empty."""
+
+    def __init__(self, args, W, obs, joiner_obs, ring0):
+        n = args.nodes
+        self.perm = [None]
+        if args.workload == "c5":
+            self.batches = [W.c5_churn(obs, joiner_obs, n, n // 200, n // 200)]
+        elif args.workload == "c2":
+            self.batches = [W.c2_simultaneous_crash(obs, n, 0.01)]
+        elif args.workload == "c3":
+            self.batches = [W.c3_correlated_partition(obs, ring0, n, 0.05)]
+        else:
+            self.batches = W.c4_flip_flop_stream(obs, n, 0.01, T=8)
+            self.perm = [b.meta["perm_seed"] for b in self.batches]
+        self.blocked = self.batches[0].blocked
+        self.expected_cut = self.batches[-1].expected_cut
+        self.cells = [len(b) for b in self.batches]
+        # subjects first seen in batch t ("fresh": their rows are written, never read) / seen before ("carried": 2 B read + 2 B written)
+        seen = np.zeros(n + n_joiners(args) + 1, bool)
+        self.fresh, self.carried = [], []
+        for b in self.batches:
+            u = np.unique(b.dst)
+            self.fresh.append(int((~seen[u]).sum()))
+            self.carried.append(int(seen[u].sum()))
+            seen[u] = True
+        self.subjects = int(seen.sum())
+
+    def name(self, args, upto):
+        n, A = args.nodes, sum(self.cells[: upto + 1])
+        if args.workload == "c5":
+            return "C5 %d-node K=10 H=9 L=4, 1%% churn batch (%d DOWN + %d UP subjects, %d cells)" % (n, n // 200, n // 200, A)
+        if args.workload == "c2":
+            return "C2 %d-node K=10 H=9 L=4, 1%% simultaneous crash (%d subjects, %d cells)" % (n, self.subjects, A)
+        if args.workload == "c3":
+            return "C3 %d-node K=10 H=9 L=4, 5%% correlated one-way partition (%d subjects, %d cells)" % (n, self.subjects, A)
+        return ("C4 %d-node K=10 H=9 L=4, 1%% flip-flop stream: %d subjects, %d batches with 1/4 duplicate re-sends, per-receiver "
+                "permuted order, state carried; decided in batch %d after %d cells" % (n, self.subjects, len(self.batches), upto, A))
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -157,6 +189,9 @@ def measured_hbm_peak():
 class CpuProblem:
     """The workload inside the oracle (built once; construction is outside every timed region)."""
 
+    NODES_PER_THREAD = 8        # sampled virtual nodes per host thread
+    VOTES = 4096                # votes handed to every sampled FastPaxos instance
+
     def __init__(self, args):
         from oracle import oracle_py as orc
         from rapid_b200 import workloads as W
@@ -171,68 +206,62 @@ class CpuProblem:
         self.cfg = self.view.getCurrentConfigurationId()
         obs = lambda ids: self.view.tables(ids)[0]
         joiner_obs = np.asarray([self.view.getExpectedObserversOf(n + j) for j in range(nj)], np.int32).reshape(nj, K)
-        ring0 = np.asarray(self.view.getRing(0), np.int32) if args.workload == "c3" else None
-        self.b = make_batch(args, W, obs, joiner_obs, ring0)
-        self.A = len(self.b)
-        self.cfgs = np.full(self.A, self.cfg, np.int64)
-        self.live = int(n - int(self.b.blocked.sum()))
+        ring0 = np.asarray(self.view.getRing(0), np.int32)
+        self.ring0 = ring0
+        self.st = Stream(args, W, obs, joiner_obs, ring0)
+        self.live = int(n - int(self.st.blocked.sum()))
         self.setup_s = time.time() - t0
-        self.Rs, self.Vs = None, None       # sample sizes, fixed by the first measurement
 
-    def measure(self, threads, budget_s):
-        """Time the literal C++ restatement on a bounded sample; value = cells/s for the WHOLE cluster (extrapolated)."""
-        orc, b, n = self.orc, self.b, self.args.nodes
-        # apply: R_s receivers x the full batch.  First measurement: a probe of 2 receivers per thread sizes the sample so that it
-        # costs ~budget/4 (one more run); later measurements reuse the size.
-        def run_apply(Rs):
-            sim = orc.ClusterSim(self.view, K, H, L, Rs)
-            out = sim.apply_batch(b.src, b.dst, b.ring, b.status, self.cfgs, threads=threads)
-            return out, sim.last_seconds
-        if self.Rs:
-            Rs = self.Rs
-            (o_len, o_ann, o_ids, o_off), t_apply = run_apply(Rs)
-        else:
-            Rs = max(1, min(threads * 2, self.live))
-            (o_len, o_ann, o_ids, o_off), t_apply = run_apply(Rs)
-            want = int(Rs * (budget_s / 4) / max(t_apply, 1e-3)) // threads * threads
-            want = max(Rs, min(want, 64 * threads, max(threads, self.live // threads * threads)))
-            if want >= 2 * Rs:
-                Rs = want
-                (o_len, o_ann, o_ids, o_off), t_apply = run_apply(Rs)
-        self.Rs = Rs
-        assert (o_len == len(b.expected_cut)).all(), "oracle did not converge to the expected cut"
+    def measure(self, threads):
+        """Time the literal C++ restatement on a FIXED sample: `8 x threads` live virtual nodes apply the whole stream (all
+        threads busy), then `threads` FastPaxos instances count 4096 of the votes each.  Everything reported is measured on
+        that sample; the whole-cluster figure is a labelled extrapolation."""
+        orc, st, n = self.orc, self.st, self.args.nodes
+        W = __import__("rapid_b200.workloads", fromlist=["x"])
+        blocked_r = W.blocked_by_receiver(st.blocked, self.ring0, 0, n)
+        live_pos = np.nonzero(blocked_r == 0)[0]
+        Rs = int(min(self.NODES_PER_THREAD * threads, len(live_pos)))
+        # the sampled receivers are the first Rs LIVE ring-0 positions; the oracle simulates positions [0, hi) and we block the rest
+        hi = int(live_pos[Rs - 1]) + 1
+        sim = orc.ClusterSim(self.view, K, H, L, hi)
+        t_apply, cells, decided_batch, prop = 0.0, 0, None, None
+        for bi, b in enumerate(st.batches):
+            out = sim.apply_batch(b.src, b.dst, b.ring, b.status, np.full(len(b), self.cfg, np.int64), blocked=blocked_r[:hi],
+                                  perm_seed=st.perm[bi], threads=threads)
+            t_apply += sim.last_seconds
+            cells += len(b)
+            o_len, o_ann, o_ids, o_off = out
+            if o_len.max() > 0:
+                r = int(np.nonzero(o_len)[0][0])
+                prop = o_ids[o_off[r]: o_off[r + 1]]
+                if len(prop) == len(st.expected_cut) and (np.sort(prop) == st.expected_cut).all():
+                    decided_batch = bi
+                    break
+        assert decided_batch is not None, "oracle did not converge to the expected cut"
+        Vs = int(min(self.VOTES, self.live))
+        senders = np.arange(Vs, dtype=np.int32)
+        t_tally = orc.sim_tally(self.u, self.cfg, n, threads, senders, np.full(Vs, self.cfg, np.int64), np.zeros(Vs, np.int32),
+                                np.array([0, len(prop)], np.int32), prop, threads=threads)[3]
         apply_whole = t_apply * self.live / Rs
-        # tally: `threads` FastPaxos instances x V_s of the `live` identical votes
-        prop = o_ids[o_off[0]: o_off[1]]
-        def run_tally(Vs):
-            senders = np.arange(Vs, dtype=np.int32)
-            return orc.sim_tally(self.u, self.cfg, n, threads, senders, np.full(Vs, self.cfg, np.int64), np.zeros(Vs, np.int32),
-                                 np.array([0, len(prop)], np.int32), prop, threads=threads)[3]
-        if self.Vs:
-            Vs = self.Vs
-            t_tally = run_tally(Vs)
-        else:
-            Vs = min(64, self.live)
-            t_tally = run_tally(Vs)
-            want = max(Vs, min(int(Vs * (budget_s / 4) / max(t_tally, 1e-3)), self.live))
-            if want >= 2 * Vs:
-                Vs = want
-                t_tally = run_tally(Vs)
-        self.Vs = Vs
         tally_whole = t_tally * (self.live / threads) * (self.live / Vs)
-        whole = apply_whole + tally_whole
         return {
-            "value": self.A / whole, "unit": UNIT, "cores": threads, "kind": "port",
-            "apply_only_value": self.A / apply_whole,
+            "value": cells / (t_apply + t_tally), "unit": UNIT, "cores": threads, "kind": "port",
             "sample": ("literal C++ restatement of MultiNodeCutDetector / MembershipService batch handler / FastPaxos tally "
-                       "(oracle/, g++ -O2; the Java reference cannot run here: no JDK).  apply: %d of %d live virtual nodes x "
-                       "the full %d-cell batch on %d threads = %.3f s; tally: %d nodes x %d of %d votes (each vote re-hashes "
-                       "the %d-endpoint proposal list like List.hashCode) = %.3f s; both extrapolated linearly to all %d "
-                       "nodes and votes (whole job %.3g s, of which tally %.3g s)"
-                       % (Rs, self.live, self.A, threads, t_apply, threads, Vs, self.live, len(prop), t_tally, self.live,
-                          whole, tally_whole)),
+                       "(oracle/, g++ -O2; the Java reference cannot run here: no JDK).  MEASURED: %d of the %d live virtual nodes "
+                       "apply the whole %d-cell stream (%d batch(es)) on %d threads in %.3f s, then %d FastPaxos instances count "
+                       "%d votes each (every vote re-hashes the %d-endpoint proposal like List.hashCode) in %.3f s; value = cells "
+                       "/ (%.3f + %.3f s)" % (Rs, self.live, cells, decided_batch + 1, threads, t_apply, threads, Vs, len(prop),
+                                              t_tally, t_apply, t_tally)),
+            "sampled_nodes": Rs, "sampled_votes_per_instance": Vs, "apply_s": t_apply, "tally_s": t_tally,
+            "apply_node_cells_per_s": Rs * cells / t_apply, "tally_votes_per_s": threads * Vs / max(t_tally, 1e-9),
+            "extrapolated_whole_cluster": {
+                "value": cells / (apply_whole + tally_whole), "apply_only_value": cells / apply_whole, "unit": UNIT,
+                "how": "NOT measured: apply time x (%d live nodes / %d sampled) + tally time x (%d nodes / %d instances) x (%d "
+                       "votes / %d) — every one of the reference's N processes runs its own detector AND its own tally of N "
+                       "votes, while the GPU arm runs N detectors and ONE cluster-wide tally" % (
+                           self.live, Rs, self.live, threads, self.live, Vs)},
             "setup_s": round(self.setup_s, 1),
-        }
+        }, cells, decided_batch
 
 
 def run_reference(args):
@@ -243,27 +272,25 @@ def run_reference(args):
     orc.build()
     threads = max(1, orc.hardware_threads())
     prob = CpuProblem(args)
-    log("[reference] setup %.1fs (n=%d, cells=%d), %d threads" % (prob.setup_s, args.nodes, prob.A, threads))
-    n_iter = args.warmup + args.steps
-    per = max(1.0, min(args.cpu_seconds, 150.0 / max(1, n_iter)))      # the whole run stays within a few minutes
+    log("[reference] setup %.1fs (n=%d), %d threads" % (prob.setup_s, args.nodes, threads))
     vals = []
     t_start = time.time()
-    for i in range(n_iter):
-        d = prob.measure(threads, per)
+    for i in range(args.warmup + args.steps):
+        d, cells, upto = prob.measure(threads)
         if i >= args.warmup:
             vals.append(d)
-        if time.time() - t_start > 200 and vals:
+        if time.time() - t_start > 240 and vals:         # the whole run stays within a few minutes
             break
     v = float(np.mean([x["value"] for x in vals]))
     d = dict(vals[-1])
     d["value"] = v
-    A = prob.A
-    S = len(np.unique(prob.b.dst))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
-        "warmup": args.warmup, "ms_per_step": 1e3 * A / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": 1e3 * cells / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u16", "data": "synthetic",
-        "config": {"workload": workload_name(args, A, S), "nodes": args.nodes, "cells": A, "subjects": S, "K": K, "H": H, "L": L},
+        "config": {"workload": prob.st.name(args, upto), "nodes": args.nodes, "cells": cells, "subjects": prob.st.subjects,
+                   "K": K, "H": H, "L": L,
+                   "note": "CPU arm: a bounded sample of the workload (see cpu_baseline.sample); value is the sample's measured rate"},
         "cpu_baseline": d,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -306,17 +333,16 @@ def run_ours(args):
     obs, _ = view.tables()
     ring0 = view.getRing(0)
     joiner_obs = view.joinerTables() if nj else np.zeros((0, K), np.int32)
-    b = make_batch(args, W, obs, joiner_obs, ring0)
-    A = len(b)
-    S = len(np.unique(b.dst))
+    st = Stream(args, W, obs, joiner_obs, ring0)
+    T = len(st.batches)
     hi, lo = W.node_ids(0, n)
     cfg = view.getCurrentConfigurationId(hi, lo)
     Gs = args.emulate_shard if (args.emulate_shard > 1 and G == 1) else G      # sharding arithmetic only
     begin = rank * n // Gs
     R = (rank + 1) * n // Gs - begin
     emulated = Gs != G
-    blocked = W.blocked_by_receiver(b.blocked, ring0, begin, R)
-    cl = rb.VirtualCluster(view, H, L, n_receivers=R, receiver_begin=begin, kernel=args.kernel, max_subjects=S + 64)
+    blocked = W.blocked_by_receiver(st.blocked, ring0, begin, R)
+    cl = rb.VirtualCluster(view, H, L, n_receivers=R, receiver_begin=begin, kernel=args.kernel, max_subjects=st.subjects + 64)
     fp = rb.FastPaxos(cfg, n, sender_capacity=n, device=local)
     comm = None
     if G > 1:
@@ -325,36 +351,56 @@ def run_ours(args):
             uid.copy_(torch.from_numpy(rb.NcclComm.unique_id()))
         dist.broadcast(uid, 0)
         comm = rb.NcclComm(rank, G, uid.cpu().numpy(), local)
-    want = rb.proposal_fingerprint(b.expected_cut)
-    log("[rank %d] setup %.1fs: n=%d receivers=[%d,%d) cells=%d subjects=%d" % (rank, time.time() - t0, n, begin, begin + R, A, S))
+    want = rb.proposal_fingerprint(st.expected_cut)
+    log("[rank %d] setup %.1fs: n=%d receivers=[%d,%d) batches=%d cells=%d subjects=%d" % (
+        rank, time.time() - t0, n, begin, begin + R, T, sum(st.cells), st.subjects))
 
     # device-resident inputs (torch only holds the memory)
-    d_dst = torch.from_numpy(b.dst).cuda()
-    d_ring = torch.from_numpy(b.ring).cuda()
-    d_status = torch.from_numpy(b.status).cuda()
+    dev = [(torch.from_numpy(b.dst).cuda(), torch.from_numpy(b.ring).cuda(), torch.from_numpy(b.status).cuda()) for b in st.batches]
     d_blocked = torch.from_numpy(blocked).cuda()
-    dl = N.Delivery()
-    dl.flags = N.DELIVERY_BLOCKED
-    dl.blocked = d_blocked.data_ptr()
-    lib = N.lib()
+    asynchronous = args.kernel != "sweep"
 
-    phases = [0.0, 0.0, 0.0]     # apply call, its dominant kernel, tally call (device ms, summed)
+    acc = {"apply": 0.0, "main": 0.0, "tally": 0.0, "launches": 0, "main_by_batch": [0.0] * T, "calls": [0] * T}
 
     def step_device():
+        """clear -> every batch of the stream ENQUEUED (batch, then its tally, ordered on the device) -> ONE host synchronisation:
+        the decision and the index of the batch that produced it.  Votes after the decision are ignored on the device."""
         cl.clear()
         fp.reset(cfg)
-        N.check(lib.rapid_cd_apply_batch_dev(cl._h, cfg, A, None, d_dst.data_ptr(), d_ring.data_ptr(),
-                                             d_status.data_ptr(), None, C.byref(dl)))
-        res = fp.tallyCluster(cl, comm)
-        tot, main = cl.lastDeviceMs()
-        phases[0] += tot; phases[1] += main; phases[2] += fp.lastDeviceMs()
-        return res, tot + fp.lastDeviceMs(), main, cl.lastPath()[1] + fp.lastLaunches()
+        for bi in range(T):
+            d_dst, d_ring, d_status = dev[bi]
+            cl.handleBatchDevice(cfg, st.cells[bi], d_dst.data_ptr(), d_ring.data_ptr(), d_status.data_ptr(),
+                                 blocked_dev=d_blocked.data_ptr(), perm_seed=st.perm[bi], wait=not asynchronous)
+            fp.tallyClusterAsync(cl, comm)
+        res = fp.result()
+        return res, (res.decided_in if res.decided_in is not None and res.decided_in >= 0 else None)
+
+    def step_profile():
+        """the same stream with a host synchronisation after every call, to read the per-call device times (NOT the timed loop)"""
+        cl.clear()
+        fp.reset(cfg)
+        res = None
+        for bi in range(T):
+            d_dst, d_ring, d_status = dev[bi]
+            cl.handleBatchDevice(cfg, st.cells[bi], d_dst.data_ptr(), d_ring.data_ptr(), d_status.data_ptr(),
+                                 blocked_dev=d_blocked.data_ptr(), perm_seed=st.perm[bi], wait=True)
+            res = fp.tallyCluster(cl, comm)
+            tot, main = cl.lastDeviceMs()
+            acc["apply"] += tot; acc["main"] += main; acc["tally"] += fp.lastDeviceMs()
+            acc["main_by_batch"][bi] += main; acc["calls"][bi] += 1
+            acc["launches"] += cl.lastPath()[1] + fp.lastLaunches() + (2 if bi == 0 else 0)     # + clear(), reset()
+        return res
 
     def step_host():
         cl.clear()
         fp.reset(cfg)
-        cl.handleBatch(cfg, None, b.dst, b.ring, b.status, blocked=blocked, read_outputs=False)
-        return fp.tallyCluster(cl, comm)
+        res = None
+        for bi, b in enumerate(st.batches):
+            cl.handleBatch(cfg, None, b.dst, b.ring, b.status, blocked=blocked, perm_seed=st.perm[bi], read_outputs=False)
+            res = fp.tallyCluster(cl, comm)
+            if res.decided:
+                break
+        return res
 
     def barrier():
         torch.cuda.synchronize()
@@ -362,32 +408,48 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def check(res):
+        assert emulated or (res.decided and (res.hash, res.hash2, res.length) == (want[0], want[1], len(st.expected_cut))), \
+            "decision differs from the expected cut: %r" % (res,)
+
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()             # polls from here on; samples taken from the start of the timed region are reported
+    upto = T - 1
     for _ in range(max(3, args.warmup)):
-        res, _, _, _ = step_device()
-    assert emulated or (res.decided and (res.hash, res.hash2, res.length) == (want[0], want[1], len(b.expected_cut))), \
-        "decision differs from the expected cut: %r" % (res,)
+        res, upto_w = step_device()
+        check(res)
+        upto = upto_w if upto_w is not None else T - 1
+    cells_step = sum(st.cells[: upto + 1])        # cells delivered up to and including the deciding batch
 
     import gc
     gc.collect()
     gc.disable()                   # no collector pauses inside the timed loops (one late rank stalls the whole all-reduce)
     clocks.mark_begin()
-    barrier()                      # nothing rank-specific between the barrier and the first timed step: a rank that starts late
-    phases[:] = [0.0, 0.0, 0.0]    # makes every other rank wait for it inside the first all-reduce
-    dev_ms, main_ms, launches = 0.0, 0.0, 0
+    barrier()                      # nothing rank-specific between the barrier and the first timed step
     per_step = []
     w0 = time.perf_counter()
+    cl.timerStart()                # device-side stopwatch over ALL the steps: kernels, resets, host syncs, idle gaps
     for _ in range(args.steps):
         t_step = time.perf_counter()
-        res, ms, mk, nl = step_device()
-        dev_ms += ms; main_ms += mk; launches += nl
+        res, _ = step_device()
         per_step.append((time.perf_counter() - t_step) * 1e3)
+    dev_ms = fp.timerStop(cl)
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
-    log("[rank %d] per step: apply %.3f ms (dominant kernel %.3f ms), tally %.3f ms; host wall per step median %.3f max %.3f ms" % (
-        rank, phases[0] / args.steps, phases[1] / args.steps, phases[2] / args.steps, float(np.median(per_step)), max(per_step)))
+    check(res)
+    prof_steps = max(2, min(args.steps, 5))
+    for _ in range(prof_steps):
+        check(step_profile())
+    for k in ("apply", "main", "tally"):
+        acc[k] *= args.steps / prof_steps          # per-call device times are reported per step of the timed loop
+    acc["main_by_batch"] = [x * args.steps / prof_steps for x in acc["main_by_batch"]]
+    acc["calls"] = [c * args.steps // prof_steps for c in acc["calls"]]
+    acc["launches"] = acc["launches"] * args.steps // prof_steps
+    log("[rank %d] per step: device stopwatch %.3f ms (host wall median %.3f max %.3f ms); per-call device times from %d profiled "
+        "steps: apply %.3f ms (dominant kernel %.3f ms), tally %.3f ms" % (
+            rank, dev_ms / args.steps, float(np.median(per_step)), max(per_step), prof_steps, acc["apply"] / args.steps,
+            acc["main"] / args.steps, acc["tally"] / args.steps))
     # end-to-end through the host-facing ABI (host arrays, H2D, reset, kernels, decision back)
     for _ in range(2):
         step_host()
@@ -397,20 +459,43 @@ def run_ours(args):
         res = step_host()
     barrier()
     e2e_ms = (time.perf_counter() - e0) * 1e3 / args.steps
+    check(res)
+
+    # the carried path of C5 (read-modify-write rows): the same batch delivered as two halves, no clear() in between
+    carried = None
+    if args.workload == "c5" and not args.no_carried and asynchronous:
+        b = st.batches[0]
+        A, half = len(b), len(b) // 2
+        u1 = np.unique(b.dst[:half]); u2 = np.unique(b.dst[half:])
+        S_carried = int(np.isin(u2, u1).sum()); S_fresh2 = len(u2) - S_carried
+        d_dst, d_ring, d_status = dev[0]
+        ms2, reps = 0.0, max(3, min(args.steps, 10))
+        for i in range(reps + 1):
+            cl.clear(); fp.reset(cfg)
+            cl.handleBatchDevice(cfg, half, d_dst.data_ptr(), d_ring.data_ptr(), d_status.data_ptr(), blocked_dev=d_blocked.data_ptr())
+            cl.handleBatchDevice(cfg, A - half, d_dst.data_ptr() + 4 * half, d_ring.data_ptr() + half, d_status.data_ptr() + half,
+                                 blocked_dev=d_blocked.data_ptr())
+            res = fp.tallyCluster(cl, comm)
+            if i:
+                ms2 += cl.lastDeviceMs()[1]
+        check(res)
+        alg2 = (4 * S_carried + 2 * S_fresh2) * R + 5 * R
+        carried = {"kernel": "k_apply_uniform (second half of the batch: %d carried subjects read-modify-write 4 B per (subject, "
+                             "receiver), %d fresh ones write 2 B)" % (S_carried, S_fresh2),
+                   "kernel_ms": ms2 / reps, "algorithmic_bytes_per_launch": int(alg2)}
     gc.enable()
     clk = clocks.stop() if rank == 0 else None
-    assert emulated or (res.decided and res.hash == want[0])
 
     # per-rank breakdown (diagnosis of a late rank: every other rank's wait for it shows up in their tally time)
-    mine = torch.tensor([float(np.median(per_step)), max(per_step), phases[0] / args.steps, phases[2] / args.steps],
-                        dtype=torch.float64, device="cuda")
+    mine = torch.tensor([float(np.median(per_step)), max(per_step), acc["apply"] / args.steps, acc["tally"] / args.steps,
+                         acc["main"] / args.steps], dtype=torch.float64, device="cuda")
     if G > 1:
         allr = [torch.zeros_like(mine) for _ in range(G)]
         dist.all_gather(allr, mine)
     else:
         allr = [mine]
     per_rank = [[round(float(x), 4) for x in r.cpu()] for r in allr]
-    t = torch.tensor([dev_ms, main_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, acc["main"], e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
     if G > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, main_ms, e2e_ms, wall_ms = [float(x) for x in t.cpu()]
@@ -420,32 +505,51 @@ def run_ours(args):
     line = None
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
-        fresh = True   # every step starts a new epoch: all subjects are new, their state is written, never read
-        alg = (2 if fresh else 4) * S * R + 5 * R      # mask bytes written + rflags/blocked read (fresh subjects: no per-receiver partials)
+        # algorithmic bytes of the dominant kernel over one step: per batch, 2 B written per (fresh subject, receiver), 4 B (2 read
+        # + 2 written) per (carried subject, receiver), + flags / blocked read once per receiver
+        alg = sum((2 * st.fresh[bi] + 4 * st.carried[bi]) * R + 5 * R for bi in range(upto + 1))
         achieved = alg / (main_per * 1e-3) / 1e9 if main_per > 0 else 0.0
+        path = cl.lastPath()[0]
+        kname = {1: "k_sweep", 2: "k_apply_uniform<false>", 3: "k_apply_generic", 4: "k_apply_uniform<true> (permuted delivery)"}.get(path)
         line = {
-            "metric": METRIC, "value": A / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": G, "steps": args.steps,
+            "metric": METRIC, "value": cells_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": G, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-            "config": {"workload": workload_name(args, A, S), "nodes": n, "cells": A, "alert_messages": b.n_messages(),
-                       "subjects": S, "K": K, "H": H, "L": L, "receivers_per_gpu": R,
-                       "parallelism": "virtual nodes sharded by ring-0 range x%d; one NCCL histogram all-reduce" % G,
-                       "l2": "per-step state %.1f GB per GPU >> 126 MB L2 (inputs larger than L2, no flush)" % (2 * S * R / 1e9),
-                       "timing": "CUDA events on the library streams per call, summed per step, max over ranks; "
-                                 "epoch reset between steps excluded",
-                       "kernel_path": {1: "sweep", 2: "bucketed-uniform", 3: "bucketed-generic"}.get(cl.lastPath()[0])},
-            "wall_ms_per_step_incl_reset": wall_ms / args.steps,
+            "config": {"workload": st.name(args, upto), "nodes": n, "cells": cells_step, "batches": upto + 1,
+                       "alert_messages": sum(b.n_messages() for b in st.batches[: upto + 1]),
+                       "subjects": st.subjects, "K": K, "H": H, "L": L, "receivers_per_gpu": R,
+                       "parallelism": "virtual nodes sharded by ring-0 range x%d; one NCCL histogram all-reduce per batch" % G,
+                       "l2": ("per-step mask state %.2f GB per GPU vs 126 MB L2: %s" % (
+                           2 * st.subjects * R / 1e9, "inputs larger than L2, no flush" if 2 * st.subjects * R > 4 * 126e6 else
+                           "fits in L2 — every step starts from clear() and rewrites it; reported as is")),
+                       "timing": "one device-side stopwatch over all steps (CUDA event on the detector's stream before the first "
+                                 "step, on the tally's stream after the last): kernels, epoch resets, the one host sync per step "
+                                 "(the decision; every batch and its tally are enqueued, all %d batches of the stream are "
+                                 "applied) and idle gaps included; max over ranks.  Per-kernel times come from extra profiled "
+                                 "steps with a host sync per call" % T,
+                       "kernel_path": {1: "sweep", 2: "bucketed-uniform", 3: "bucketed-generic", 4: "bucketed-permuted"}.get(path)},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "device_ms_in_calls_per_step": {"apply": acc["apply"] / args.steps, "tally": acc["tally"] / args.steps},
             "per_rank_ms": {"host_wall_per_step_median": [r[0] for r in per_rank], "host_wall_per_step_max": [r[1] for r in per_rank],
-                            "apply_device": [r[2] for r in per_rank], "tally_device_incl_allreduce_wait": [r[3] for r in per_rank]},
+                            "apply_device": [r[2] for r in per_rank], "tally_device_incl_allreduce_wait": [r[3] for r in per_rank],
+                            "dominant_kernel": [r[4] for r in per_rank]},
             "clocks": clk,
-            "e2e": {"value": A / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(A * 6 + R), "d2h_bytes_per_step": 64 + 36},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_apply_uniform", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "e2e": {"value": cells_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(sum(st.cells[bi] * 6 + R for bi in range(upto + 1))),
+                    "d2h_bytes_per_step": (64 + 36) * (upto + 1)},
+            "gpu_launches": int(acc["launches"]),
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(args, G), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(alg), "kernel_ms": main_per,
-                         "kernel_share_of_step": main_per / ms_per_step if ms_per_step else None},
+                         "algorithmic_bytes_per_launch": int(alg / (upto + 1)), "launches_per_step": upto + 1,
+                         "kernel_ms": main_per / (upto + 1), "kernel_ms_per_step": main_per,
+                         "kernel_share_of_step": main_per / ms_per_step if ms_per_step else None,
+                         "per_batch": [{"fresh_subjects": st.fresh[bi], "carried_subjects": st.carried[bi],
+                                        "kernel_ms": acc["main_by_batch"][bi] / max(1, acc["calls"][bi])} for bi in range(upto + 1)]},
         }
+        if carried is not None:
+            ach2 = carried["algorithmic_bytes_per_launch"] / (carried["kernel_ms"] * 1e-3) / 1e9
+            carried.update({"bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak})
+            line["roofline_carried"] = carried
     if G > 1:
         dist.barrier()
     if rank == 0:
@@ -453,7 +557,7 @@ def run_ours(args):
             try:
                 from oracle import oracle_py as orc
                 orc.build()
-                line["cpu_baseline"] = CpuProblem(args).measure(max(1, orc.hardware_threads()), args.cpu_seconds)
+                line["cpu_baseline"] = CpuProblem(args).measure(max(1, orc.hardware_threads()))[0]
             except Exception as e:       # the baseline is a reported extra; never lose the GPU line over it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
         emit(line)

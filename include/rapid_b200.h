@@ -252,7 +252,20 @@ int32_t rapid_fp_tally(rapid_fp* fp, int64_t n_votes, const int32_t* sender, con
 int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, int32_t* decided,
                           uint64_t* decided_hash, uint64_t* decided_hash2, int32_t* decided_len,
                           int32_t* decided_count, int32_t* votes_received);
+/* The same in two halves: rapid_fp_tally_cd_async only ENQUEUES the tally (ordered on the device after whatever is in flight on
+ * the detector, asynchronous batches included); rapid_fp_result waits for the LAST enqueued tally and reads the outcome.  A
+ * whole stream of batches can thus be applied and tallied with one host synchronisation at the end: once a proposal has reached
+ * the quorum later votes are ignored on the device (:138) and the decision is kept.  *decided_in_call = index (since
+ * rapid_fp_reset) of the tally call that decided, -1 if undecided. */
+int32_t rapid_fp_tally_cd_async(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm);
+int32_t rapid_fp_result(rapid_fp* fp, int32_t* decided, uint64_t* decided_hash, uint64_t* decided_hash2, int32_t* decided_len,
+                        int32_t* decided_count, int32_t* votes_received, int32_t* decided_in_call);
 int32_t rapid_fp_quorum(int64_t membership_size, int64_t* out);   /* N - floor((N-1)/4) */
+/* Device-side stopwatch over a whole sequence of (asynchronous) calls on a detector and its tally: rapid_cd_timer_start records a
+ * CUDA event on the detector's stream, rapid_fp_timer_stop one on the tally's stream after everything enqueued so far on both,
+ * waits for it and returns the milliseconds in between — kernels, copies AND the idle gaps between them. */
+int32_t rapid_cd_timer_start(rapid_cd* cd);
+int32_t rapid_fp_timer_stop(rapid_fp* fp, const rapid_cd* cd, float* out_ms);
 
 /* ------------------------------------------------------------------------------------------------
  * Classic-Paxos fallback  (Paxos.java)

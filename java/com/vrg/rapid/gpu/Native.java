@@ -58,6 +58,9 @@ public final class Native {
     public static native int fpTally(long fp, int[] sender, long[] voteCfg, long[] hash, long[] hash2, int[] len,
                                      long[] out6);
     public static native int fpTallyCd(long fp, long cd, long comm, long[] out6);
+    /** enqueue only (rapid_fp_tally_cd_async) / collect the last enqueued tally: out7 = out6 + {decidedInCall} */
+    public static native int fpTallyCdAsync(long fp, long cd, long comm);
+    public static native int fpResult(long fp, long[] out7);
 
     public static native long[] proposalFingerprint(int[] ids);
 

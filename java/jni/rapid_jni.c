@@ -232,6 +232,19 @@ JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_fpTallyCd(JNIEnv* env, jcla
     return rc;
 }
 
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_fpTallyCdAsync(JNIEnv* env, jclass c, jlong fp, jlong cd, jlong comm) {
+    return rapid_fp_tally_cd_async(H(rapid_fp, fp), H(rapid_cd, cd), H(rapid_comm, comm));
+}
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_fpResult(JNIEnv* env, jclass c, jlong fp, jlongArray out7) {
+    int32_t decided = 0, dlen = 0, dcount = 0, recv = 0, in_call = -1;
+    uint64_t a = 0, b = 0;
+    const int32_t rc = rapid_fp_result(H(rapid_fp, fp), &decided, &a, &b, &dlen, &dcount, &recv, &in_call);
+    put_result(env, out7, decided, a, b, dlen, dcount, recv);
+    const jlong v = in_call;
+    (*env)->SetLongArrayRegion(env, out7, 6, 1, &v);
+    return rc;
+}
+
 JNIEXPORT jlongArray JNICALL Java_com_vrg_rapid_gpu_Native_proposalFingerprint(JNIEnv* env, jclass c, jintArray ids) {
     const jsize n = (*env)->GetArrayLength(env, ids);
     jint* p = (*env)->GetIntArrayElements(env, ids, NULL);

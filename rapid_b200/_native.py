@@ -94,7 +94,11 @@ SIGNATURES = {
     "rapid_fp_reset": [_vp, _i64, _i64],
     "rapid_fp_tally": [_vp, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "rapid_fp_tally_cd": [_vp, _vp, _vp, _p, _p, _p, _p, _p, _p],
+    "rapid_fp_tally_cd_async": [_vp, _vp, _vp],
+    "rapid_fp_result": [_vp, _p, _p, _p, _p, _p, _p, _p],
     "rapid_fp_quorum": [_i64, _p],
+    "rapid_cd_timer_start": [_vp],
+    "rapid_fp_timer_stop": [_vp, _vp, _p],
     "rapid_comm_unique_id": [_p],
     "rapid_comm_init": [_pp, _i32, _i32, _p, _i32],
     "rapid_comm_destroy": [_vp],

@@ -642,6 +642,36 @@ __device__ __forceinline__ int32_t block_sum_i32(int32_t v, int32_t* s_red) {   
 __device__ void phase_finalize1(const ResolveArgs& a, int32_t* s_red) {
     const ApplyArgs& ap = a.ap;
     const int any_down = a.bc->any_down;
+    // What the FRESH subjects of the batch contribute is the same for every active receiver (one ChunkAcc per chunk of the
+    // apply launch): reduce it once per block instead of once per receiver.
+    __shared__ ChunkAcc s_fresh;
+    __shared__ int s_fhave;
+    if (threadIdx.x < 32) {
+        uint32_t nL = 0, nH = 0, nUn = 0, fl = 0, mTH = T32_NONE, mTL = T32_NONE;
+        uint64_t h1 = 0, h2 = 0;
+        for (int c = threadIdx.x; c < a.n_chunks; c += 32) {
+            const ChunkAcc k = ap.part.chunk[c];
+            const uint32_t cH = k.nLH >> 16, cUn = k.tpUn >> 16;
+            nL += k.nLH & 0xFFFFu; nH += cH; nUn += cUn; fl |= k.fl;
+            if (cH) mTH = min(mTH, k.minTH);
+            if (cUn) mTL = min(mTL, k.minTLun);
+            h1 += k.h1; h2 += k.h2;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nL += __shfl_down_sync(0xffffffffu, nL, o); nH += __shfl_down_sync(0xffffffffu, nH, o);
+            nUn += __shfl_down_sync(0xffffffffu, nUn, o); fl |= __shfl_down_sync(0xffffffffu, fl, o);
+            mTH = min(mTH, __shfl_down_sync(0xffffffffu, mTH, o)); mTL = min(mTL, __shfl_down_sync(0xffffffffu, mTL, o));
+            h1 += __shfl_down_sync(0xffffffffu, h1, o); h2 += __shfl_down_sync(0xffffffffu, h2, o);
+        }
+        if (threadIdx.x == 0) {
+            ChunkAcc f;
+            f.nLH = nL | (nH << 16); f.tpUn = nUn << 16; f.fl = fl; f.minTH = mTH; f.minTLun = mTL; f.pad_ = 0; f.h1 = h1; f.h2 = h2;
+            s_fresh = f;
+            s_fhave = (nH ? 1 : 0) | (nUn ? 2 : 0);
+        }
+    }
+    __syncthreads();
     int32_t my_mixed = 0, my_times = 0;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < ap.R; r += (int64_t)gridDim.x * blockDim.x) {
         a.mx_fl[r] = 0;
@@ -650,27 +680,35 @@ __device__ void phase_finalize1(const ResolveArgs& a, int32_t* s_red) {
         const bool active = !(flags & RF_ANNOUNCED) && !((ap.dl.flags & RAPID_DELIVERY_BLOCKED) && ap.dl.blocked[r]);
         if (!active) { a.rflags[r] = flags; a.out_ann[r] = (flags & RF_ANNOUNCED) ? 1 : 0; continue; }
         flags |= RF_ACTIVE;
-        uint32_t nL = 0, nH = 0, tp = 0, nUn = 0, fl = 0;
-        uint64_t minTH = T64_NONE, minTLun = T64_NONE, h1 = 0, h2 = 0;
-        bool haveTH = false, haveTL = false;
+        uint32_t nL = s_fresh.nLH & 0xFFFFu, nH = s_fresh.nLH >> 16, tp = 0, nUn = s_fresh.tpUn >> 16, fl = s_fresh.fl;
+        uint64_t minTH = s_fresh.minTH, minTLun = s_fresh.minTLun, h1 = s_fresh.h1, h2 = s_fresh.h2;
+        bool haveTH = s_fhave & 1, haveTL = (s_fhave & 2) != 0;
         const int tile = (int)(r / TILE_R);
-        for (int c = 0; c < a.n_chunks; ++c) {
-            {   // fresh subjects of the chunk: the same for every active receiver
-                const ChunkAcc k = ap.part.chunk[c];
-                const uint32_t cH = k.nLH >> 16, cUn = k.tpUn >> 16;
-                nL += k.nLH & 0xFFFFu; nH += cH; nUn += cUn; fl |= k.fl;
-                if (cH && (!haveTH || (uint64_t)k.minTH < minTH)) { minTH = k.minTH; haveTH = true; }
-                if (cUn && (!haveTL || (uint64_t)k.minTLun < minTLun)) { minTLun = k.minTLun; haveTL = true; }
-                h1 += k.h1; h2 += k.h2;
+        // per-receiver partials of the chunks that met a carried subject: four chunks' loads in flight at a time
+        for (int c0 = 0; c0 < a.n_chunks; c0 += 4) {
+            int on[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) on[q] = c0 + q < a.n_chunks ? ap.part.flag[(size_t)(c0 + q) * ap.part.n_tiles + tile] : 0;
+            uint4 q4[4];
+            uint64_t th[4], tl[4], a1[4], a2[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (!on[q]) continue;
+                const size_t p = (size_t)(c0 + q) * ap.Rpad + (size_t)r;
+                q4[q] = ap.part.cnt[p]; a1[q] = ap.part.h1[p]; a2[q] = ap.part.h2[p];
+                if (!a.counts_only) { th[q] = ap.part.minTH[p]; tl[q] = ap.part.minTLun[p]; }
             }
-            if (!ap.part.flag[(size_t)c * ap.part.n_tiles + tile]) continue;
-            const size_t p = (size_t)c * ap.Rpad + (size_t)r;
-            const uint4 q = ap.part.cnt[p];
-            const uint32_t cH = q.x >> 16, cUn = q.y >> 16;
-            nL += q.x & 0xFFFFu; nH += cH; tp += q.y & 0xFFFFu; nUn += cUn; fl |= q.z;
-            if (cH) { const uint64_t v = ap.part.minTH[p]; if (!haveTH || v < minTH) { minTH = v; haveTH = true; } }
-            if (cUn) { const uint64_t v = ap.part.minTLun[p]; if (!haveTL || v < minTLun) { minTLun = v; haveTL = true; } }
-            h1 += ap.part.h1[p]; h2 += ap.part.h2[p];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (!on[q]) continue;
+                const uint32_t cH = q4[q].x >> 16, cUn = q4[q].y >> 16;
+                nL += q4[q].x & 0xFFFFu; nH += cH; tp += q4[q].y & 0xFFFFu; nUn += cUn; fl |= q4[q].z;
+                if (!a.counts_only) {
+                    if (cH && (!haveTH || th[q] < minTH)) { minTH = th[q]; haveTH = true; }
+                    if (cUn && (!haveTL || tl[q] < minTLun)) { minTLun = tl[q]; haveTL = true; }
+                }
+                h1 += a1[q]; h2 += a2[q];
+            }
         }
         // every valid cell reaches every active receiver unless there is a per-receiver bitmap
         if ((a.uniform || a.counts_only) ? any_down : (fl & PF_SEEN)) flags |= RF_SEEN_DOWN;
@@ -895,103 +933,176 @@ __device__ __noinline__ bool emitted_in_batch(const ResolveArgs& e, int32_t s, i
 constexpr int INV_STAGE = 32;
 struct InvSmem {
     uint16_t* row[INV_STAGE];
-    const uint16_t* orow[INV_STAGE][MAXK];
-    int32_t slot[INV_STAGE];
-    int32_t so[INV_STAGE][MAXK];
     uint64_t mix1[INV_STAGE], mix2[INV_STAGE];
+    int32_t ebeg[INV_STAGE + 1];                    // edges (observers that are subjects) of staged slot i: [ebeg[i], ebeg[i+1])
+    const uint16_t* e_row[INV_STAGE * MAXK];
+    int32_t e_so[INV_STAGE * MAXK];
+    uint8_t e_k[INV_STAGE * MAXK];
     uint8_t flag[INV_STAGE];
+    uint8_t dense[INV_STAGE];                       // the staged slots that are in the band somewhere in this tile
+    int32_t n_dense;
 };
 
+// A block owns one 1024-receiver tile at a time, a thread 4 consecutive receivers (64-bit row loads, 128-bit flag loads).
+// MX == false: every receiver EXCEPT those that announced through the interval analysis in this batch (RF_MIXED_EMIT) — the
+// common case, no out-of-line call in the loop.  MX == true (k_marks, only when some receiver is MIXED): exactly those receivers;
+// for them an observer that already left in an explicit proposal of this batch is no longer in `proposal` (emitted_in_batch).
+template <bool MX>
 __device__ void phase_inval_finalize2(const ResolveArgs& e, int mixed, InvSmem& sm, int32_t* s_red) {
+    static_assert(TILE_R == 4 * GEN_THREADS, "a thread owns 4 receivers of a tile");
     const ApplyArgs& a = e.ap;
     const uint32_t RM = (1u << a.K) - 1u;
     const int t = threadIdx.x;
     const int n_list = min(*(volatile int32_t*)a.wl.count, a.wl.cap);
-    const int64_t units = (int64_t)(a.Rpad / GEN_THREADS);
     int32_t my_inval = 0;
-    for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-        const int64_t r = u * GEN_THREADS + t;
-        const int tile = (int)(r / TILE_R);
-        uint32_t flags = r < a.R ? e.rflags[r] : 0u;
-        const bool k3 = (flags & RF_ACTIVE) && (flags & RF_K3);
-        int32_t res = 0;
-        uint64_t kh1 = 0, kh2 = 0;
-        if (n_list > 0 && __syncthreads_or(k3 ? 1 : 0)) {
-            const bool mx = mixed && (flags & RF_MIXED_EMIT);
-            const uint64_t rs = mx ? splitmix64(a.dl.perm_seed + (uint64_t)(a.rbegin + r)) : 0ull;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int64_t rb = (int64_t)tile * TILE_R + (int64_t)t * 4;
+        const uint4 rf4 = *reinterpret_cast<const uint4*>(e.rflags + rb);          // rows and flags are padded to whole tiles
+        uint32_t flags[4] = {rf4.x, rf4.y, rf4.z, rf4.w};
+        bool k3[4];
+        bool any_k3 = false;
+        bool mine[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            mine[j] = rb + j < a.R && (((flags[j] & RF_MIXED_EMIT) != 0 && mixed) == MX);
+            k3[j] = mine[j] && (flags[j] & RF_ACTIVE) && (flags[j] & RF_K3);
+            any_k3 |= k3[j];
+        }
+        int32_t res[4] = {0, 0, 0, 0};
+        uint64_t kh1[4] = {0, 0, 0, 0}, kh2[4] = {0, 0, 0, 0};
+        if (n_list > 0 && __syncthreads_or(any_k3 ? 1 : 0)) {
             for (int base = 0; base < n_list; base += INV_STAGE) {
                 const int n = min(INV_STAGE, n_list - base);
                 __syncthreads();
-                if (t < n) {
-                    const int32_t sl = a.wl.slots[base + t];
-                    sm.slot[t] = sl;
-                    sm.flag[t] = a.wl.in_tile[(size_t)sl * a.wl.n_tiles + tile];
-                    sm.row[t] = a.masks + ((size_t)sl * 2 + a.cur[sl]) * a.Rpad;
-                    const int32_t subject = a.slot_subject[sl];
-                    sm.mix1[t] = fp_mix1(subject); sm.mix2[t] = fp_mix2(subject);
-                }
-                for (int q = t; q < n * a.K; q += GEN_THREADS) {
-                    const int i = q / a.K, k = q - i * a.K;
-                    const int32_t s2 = a.wl.so_tab[(size_t)a.wl.slots[base + i] * SO_STRIDE + k];
-                    sm.so[i][k] = s2;
-                    sm.orow[i][k] = s2 < 0 ? nullptr : a.masks + ((size_t)s2 * 2 + a.cur[s2]) * a.Rpad;
+                if (t < 32) {                             // warp 0 stages the slots and their edge lists (INV_STAGE == 32)
+                    int ne = 0;
+                    int32_t sl = -1;
+                    if (t < n) {
+                        sl = a.wl.slots[base + t];
+                        sm.flag[t] = a.wl.in_tile[(size_t)sl * a.wl.n_tiles + tile];
+                        sm.row[t] = a.masks + ((size_t)sl * 2 + a.cur[sl]) * a.Rpad;
+                        const int32_t subject = a.slot_subject[sl];
+                        sm.mix1[t] = fp_mix1(subject); sm.mix2[t] = fp_mix2(subject);
+                        for (int k = 0; k < a.K; ++k) ne += a.wl.so_tab[(size_t)sl * SO_STRIDE + k] >= 0 ? 1 : 0;
+                    }
+                    int inc = ne;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, inc, o); if (t >= o) inc += x; }
+                    int at = inc - ne;
+                    if (t < n) {
+                        sm.ebeg[t] = at;
+                        for (int k = 0; k < a.K; ++k) {
+                            const int32_t s2 = a.wl.so_tab[(size_t)sl * SO_STRIDE + k];
+                            if (s2 < 0) continue;
+                            sm.e_row[at] = a.masks + ((size_t)s2 * 2 + a.cur[s2]) * a.Rpad;
+                            sm.e_so[at] = s2; sm.e_k[at] = (uint8_t)k;
+                            ++at;
+                        }
+                    }
+                    if (t == n - 1) sm.ebeg[n] = at;
+                    const unsigned fm = __ballot_sync(0xffffffffu, t < n && sm.flag[t]);
+                    if (t < n && sm.flag[t]) sm.dense[__popc(fm & ((1u << t) - 1u))] = (uint8_t)t;
+                    if (t == 0) sm.n_dense = __popc(fm);
                 }
                 __syncthreads();
-                if (!k3) continue;
-                for (int i0 = 0; i0 < n; i0 += 4) {
-                    // four independent row loads in flight, then the (rare) observer rows
-                    uint32_t w4[4];
+                if (!any_k3) continue;
+                const int nd = sm.n_dense;
+                for (int g = 0; g < nd; g += 4) {
+                    // four subjects at a time: their rows and the rows of (up to) two observers each in flight together
+                    int idx[4];
+                    uint2 w2v[4], e0v[4], e1v[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) w4[j] = (i0 + j < n && sm.flag[i0 + j]) ? sm.row[i0 + j][r] : 0xFFFFu;
+                    for (int q = 0; q < 4; ++q) {
+                        idx[q] = g + q < nd ? (int)sm.dense[g + q] : -1;
+                        w2v[q] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); e0v[q] = make_uint2(0u, 0u); e1v[q] = make_uint2(0u, 0u);
+                        if (idx[q] < 0) continue;
+                        w2v[q] = *reinterpret_cast<const uint2*>(sm.row[idx[q]] + rb);
+                        const int eb = sm.ebeg[idx[q]], ne = sm.ebeg[idx[q] + 1] - eb;
+                        if (ne > 0) e0v[q] = *reinterpret_cast<const uint2*>(sm.e_row[eb] + rb);
+                        if (ne > 1) e1v[q] = *reinterpret_cast<const uint2*>(sm.e_row[eb + 1] + rb);
+                    }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int i = i0 + j;
-                        if (i >= n || !sm.flag[i]) continue;
-                        const uint32_t w = w4[j];
-                        const int c = __popc(w & RM);
-                        if (c < a.L || c >= a.H) continue;                  // not in this receiver's preProposal
-                        uint32_t implicit = 0;
-                        for (int k = 0; k < a.K; ++k) {
-                            if ((w >> k) & 1u) continue;
-                            const uint16_t* orow = sm.orow[i][k];
-                            if (!orow) continue;
-                            const uint32_t wo = orow[r];
-                            if ((wo & CD_BIT_EMIT) || __popc(wo & RM) < a.L) continue;   // observer not in proposal U preProposal
-                            // a receiver that already announced explicit proposals in this batch: those subjects left `proposal`.
-                            // (bit 14 = raised to >= H by this very pass, i.e. it was in the band at entry, not pending)
-                            if (mx && emitted_in_batch(e, sm.so[i][k], r, wo, rs)) continue;
-                            implicit |= 1u << k;
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = idx[q];
+                        if (i < 0) continue;
+                        const int eb = sm.ebeg[i], ee = sm.ebeg[i + 1];
+                        uint32_t w[4] = {w2v[q].x & 0xFFFFu, w2v[q].x >> 16, w2v[q].y & 0xFFFFu, w2v[q].y >> 16};
+                        uint32_t miss[4];                                   // rings an implicit report could still add, per receiver
+                        uint32_t anymiss = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int c = __popc(w[j] & RM);
+                            miss[j] = (k3[j] && c >= a.L && c < a.H) ? (~w[j] & RM) : 0u;   // in this receiver's preProposal
+                            anymiss |= miss[j];
                         }
-                        if (!implicit) continue;
-                        uint32_t nw = w | implicit;
-                        const bool raised = __popc(nw & RM) >= a.H;
-                        if (raised && mixed) nw |= CD_BIT_CALL;            // transient marker, cleared by the unmark phase
-                        sm.row[i][r] = (uint16_t)nw;
-                        if (raised) { ++res; kh1 += sm.mix1[i]; kh2 += sm.mix2[i]; }   // moved preProposal -> proposal
+                        if (!anymiss) continue;
+                        uint32_t implicit[4] = {0u, 0u, 0u, 0u};
+                        for (int ei = eb; ei < ee; ++ei) {
+                            const int k = sm.e_k[ei];
+                            if (!((anymiss >> k) & 1u)) continue;
+                            const uint2 o2 = ei == eb ? e0v[q] : ei == eb + 1 ? e1v[q] : *reinterpret_cast<const uint2*>(sm.e_row[ei] + rb);
+                            const uint32_t wo[4] = {o2.x & 0xFFFFu, o2.x >> 16, o2.y & 0xFFFFu, o2.y >> 16};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (!((miss[j] >> k) & 1u)) continue;
+                                if ((wo[j] & CD_BIT_EMIT) || __popc(wo[j] & RM) < a.L) continue;   // observer not in proposal U preProposal
+                                // a receiver that already announced explicit proposals in this batch: those subjects left
+                                // `proposal` (bit 14 = raised to >= H by this very pass: in the band at entry, not pending)
+                                if (MX) {
+                                    const int64_t r = rb + j;
+                                    if (emitted_in_batch(e, sm.e_so[ei], r, wo[j], splitmix64(a.dl.perm_seed + (uint64_t)(a.rbegin + r)))) continue;
+                                }
+                                implicit[j] |= 1u << k;
+                            }
+                        }
+                        bool any = false;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (!implicit[j]) continue;
+                            any = true;
+                            uint32_t nw = w[j] | implicit[j];
+                            const bool raised = __popc(nw & RM) >= a.H;
+                            if (raised && mixed) nw |= CD_BIT_CALL;            // transient marker, cleared by the unmark phase
+                            w[j] = nw;
+                            if (raised) { ++res[j]; kh1[j] += sm.mix1[i]; kh2[j] += sm.mix2[i]; }   // moved preProposal -> proposal
+                        }
+                        if (any) *reinterpret_cast<uint2*>(sm.row[i] + rb) = make_uint2(w[0] | (w[1] << 16), w[2] | (w[3] << 16));
                     }
                 }
             }
         }
-        if (r >= a.R || !(flags & RF_ACTIVE)) continue;              // inactive receivers were settled by finalize1
-        if (res > 0) {
-            const int32_t npre = e.n_pre[r] - res;
-            uint64_t ph1 = e.pend_h1[r] + kh1, ph2 = e.pend_h2[r] + kh2;
-            int32_t pc = e.pend_cnt[r] + res;
-            if (npre == 0) {
-                // the last unstable subject resolved inside invalidateFailingEdges: proposal (all of it) is emitted
-                e.out_h1[r] += ph1; e.out_h2[r] += ph2; e.out_len[r] += pc;
-                ph1 = 0; ph2 = 0; pc = 0;
-                flags |= RF_ANNOUNCED | RF_ANN_NOW | RF_RULE_GE_H;
+        // ---- finalize2: emissions of the invalidation pass, announced flags --------------------------------------------------
+        uint32_t ann = 0;
+        bool touched = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t r = rb + j;
+            if (r >= a.R) continue;
+            if (!mine[j] || !(flags[j] & RF_ACTIVE)) { ann |= ((flags[j] & RF_ANNOUNCED) ? 1u : 0u) << (8 * j); continue; }   // not this pass's / settled by finalize1
+            touched = true;
+            if (res[j] > 0) {
+                const int32_t npre = e.n_pre[r] - res[j];
+                uint64_t ph1 = e.pend_h1[r] + kh1[j], ph2 = e.pend_h2[r] + kh2[j];
+                int32_t pc = e.pend_cnt[r] + res[j];
+                if (npre == 0) {
+                    // the last unstable subject resolved inside invalidateFailingEdges: proposal (all of it) is emitted
+                    e.out_h1[r] += ph1; e.out_h2[r] += ph2; e.out_len[r] += pc;
+                    ph1 = 0; ph2 = 0; pc = 0;
+                    flags[j] |= RF_ANNOUNCED | RF_ANN_NOW | RF_RULE_GE_H;
+                }
+                e.n_pre[r] = npre;
+                e.pend_h1[r] = ph1; e.pend_h2[r] = ph2; e.pend_cnt[r] = pc;
             }
-            e.n_pre[r] = npre;
-            e.pend_h1[r] = ph1; e.pend_h2[r] = ph2; e.pend_cnt[r] = pc;
+            flags[j] &= ~RF_K3;
+            if ((flags[j] & RF_MIXED_EMIT) && (flags[j] & RF_ANN_NOW) && !(flags[j] & RF_RULE_GE_H)) ++my_inval;   // needs bit-15 marks
+            ann |= ((flags[j] & RF_ANNOUNCED) ? 1u : 0u) << (8 * j);
         }
-        flags &= ~RF_K3;
-        if ((flags & RF_MIXED_EMIT) && (flags & RF_ANN_NOW) && !(flags & RF_RULE_GE_H)) ++my_inval;   // needs bit-15 marks
-        e.rflags[r] = flags;
-        e.out_ann[r] = (flags & RF_ANNOUNCED) ? 1 : 0;
+        if (touched) {
+            *reinterpret_cast<uint4*>(e.rflags + rb) = make_uint4(flags[0], flags[1], flags[2], flags[3]);
+            *reinterpret_cast<uint32_t*>(e.out_ann + rb) = ann;
+        }
     }
-    if (mixed) {
+    if (MX) {
         const int32_t b = block_sum_i32(my_inval, s_red);
         if (t == 0 && b) atomicAdd(&e.bc->n_inval, b);
     }
@@ -1110,12 +1221,12 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) k_mixed_flip(const ResolveArgs
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < Sb; b += gridDim.x * blockDim.x) a.cur_w[a.ap.desc[b].slot] ^= 1;
 }
 
-__global__ void __launch_bounds__(GEN_THREADS, 3) k_inval_finalize2(const ResolveArgs* __restrict__ ga) {
+__global__ void __launch_bounds__(GEN_THREADS, 2) k_inval_finalize2(const ResolveArgs* __restrict__ ga) {
     const ResolveArgs& a = *ga;
     __shared__ InvSmem sm;
     __shared__ int32_t s_red[GEN_THREADS / 32];
     const int mixed = a.bc->n_mixed > 0 ? 1 : 0;
-    if (!a.bc->overflow) phase_inval_finalize2(a, mixed, sm, s_red);
+    if (!a.bc->overflow) phase_inval_finalize2<false>(a, mixed, sm, s_red);
     if (!mixed) resolve_tail(a, a.serial);                               // else k_marks closes the batch
 }
 
@@ -1123,10 +1234,14 @@ __global__ void __launch_bounds__(GEN_THREADS, 3) k_inval_finalize2(const Resolv
 __global__ void __launch_bounds__(GEN_THREADS, 2) k_marks(const ResolveArgs* __restrict__ ga) {
     const ResolveArgs& a = *ga;
     cg::grid_group grid = cg::this_grid();
+    __shared__ InvSmem sm;
+    __shared__ int32_t s_red[GEN_THREADS / 32];
     if (a.bc->n_mixed <= 0) return;                                      // (k_inval_finalize2 closed the batch)
-    if (a.bc->n_inval > 0) {
+    phase_inval_finalize2<true>(a, 1, sm, s_red);                        // the receivers k_inval_finalize2 left out
+    grid.sync();
+    if (*(volatile int32_t*)&a.bc->n_inval > 0) {
         // receivers that announce only the explicit part: persist it as bit 15 while the pre-batch rows still exist
-        phase_mixed_mark(a, a.bc->n_slots);
+        phase_mixed_mark(a, *(volatile int32_t*)&a.bc->n_slots);
         grid.sync();
     }
     phase_inval_unmark(a);                                              // only now: the marks above still needed bit 14
@@ -1361,7 +1476,7 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl) {
     k_finalize1<<<rblocks, GEN_THREADS, 0, s>>>(ga);
     RAPID_KERNEL_CHECK();
     RAPID_CUDA(cudaLaunchCooperativeKernel((void*)k_mixed_flip, dim3((unsigned)cgrid), dim3(GEN_THREADS), args, 0, s));
-    k_inval_finalize2<<<std::min<unsigned>(rblocks, 148u * 32u), GEN_THREADS, 0, s>>>(ga);
+    k_inval_finalize2<<<(unsigned)std::max(b->n_tiles, 1), GEN_THREADS, 0, s>>>(ga);
     RAPID_KERNEL_CHECK();
     RAPID_CUDA(cudaLaunchCooperativeKernel((void*)k_marks, dim3((unsigned)cgrid), dim3(GEN_THREADS), args, 0, s));
     cd->last_launches += 5;

@@ -485,7 +485,7 @@ int32_t rapid_cd_create(rapid_cd** out, const rapid_view* v, int32_t H, int32_t 
         if (cudaStreamCreateWithFlags(&cd->stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreate(&cd->ev0) != cudaSuccess || cudaEventCreate(&cd->ev1) != cudaSuccess ||
             cudaEventCreate(&cd->evk0) != cudaSuccess || cudaEventCreate(&cd->evk1) != cudaSuccess ||
-            cudaEventCreateWithFlags(&cd->ev_done, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&cd->ev_done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&cd->ev_t0) != cudaSuccess) {
             rc = cuda_fail(cudaGetLastError(), "stream/event create", __FILE__, __LINE__); break;
         }
         const size_t R = (size_t)cd->Rpad;
@@ -528,6 +528,7 @@ int32_t rapid_cd_destroy(rapid_cd* cd) {
     if (cd->evk0) cudaEventDestroy(cd->evk0);
     if (cd->evk1) cudaEventDestroy(cd->evk1);
     if (cd->ev_done) cudaEventDestroy(cd->ev_done);
+    if (cd->ev_t0) cudaEventDestroy(cd->ev_t0);
     if (cd->stream) cudaStreamDestroy(cd->stream);
     delete cd;
     return RAPID_OK;
@@ -565,6 +566,14 @@ int32_t rapid_cd_clear(rapid_cd* cd) {
     }
     RAPID_CUDA(cudaEventRecord(cd->ev_done, s));
     // no synchronisation: everything that follows runs on the same stream, and other streams (the tally) wait on ev_done
+    return RAPID_OK;
+}
+
+int32_t rapid_cd_timer_start(rapid_cd* cd) {
+    if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    RAPID_CUDA(cudaEventRecord(cd->ev_t0, cd->stream));
+    RAPID_CUDA(cudaEventRecord(cd->ev_done, cd->stream));
     return RAPID_OK;
 }
 

@@ -96,6 +96,7 @@ struct CD {
     DevBuf<BatchCounts> counts_snap;  // [1] bucketed handles: copy of `counts` taken by the last kernel of a batch
     PinnedBuf<BatchCounts> h_counts;
     cudaEvent_t ev_done = nullptr;    // recorded after the last enqueued operation (other streams wait on it)
+    cudaEvent_t ev_t0 = nullptr;      // rapid_cd_timer_start
     bool pending = false;             // an asynchronous batch is in flight: its status has not been collected yet
     int32_t deferred_rc = 0;          // status of asynchronous batches collected since the last rapid_cd_sync
     std::string deferred_msg;

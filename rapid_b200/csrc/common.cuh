@@ -56,7 +56,10 @@ struct DevBuf {
         if (n <= cap) return RAPID_OK;
         size_t ncap = cap ? cap : 1;
         while (ncap < n) ncap *= 2;
-        if (!keep) ncap = n;
+        // scratch buffers: the FIRST allocation is exact (the big state arrays are allocated once), a later one grows
+        // geometrically — cudaFree synchronises the device, which an asynchronous stream of batches of slowly growing size
+        // would otherwise pay on every batch
+        if (!keep && cap == 0) ncap = n;
         T* np = nullptr;
         cudaError_t e = cudaMalloc((void**)&np, ncap * sizeof(T));
         if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes) failed: %s", ncap * sizeof(T), cudaGetErrorString(e)); cudaGetLastError(); return RAPID_ENOMEM; }

@@ -34,11 +34,14 @@ struct FPState {
     int32_t n_call;         // entries that received votes in the call in flight (listed in FP::call_list)
     int32_t ticket;         // "last block done" counter of k_fp_tally_cd
     int32_t too_many;       // more than 8 proposals reached the quorum in one call
+    int32_t calls;          // rapid_fp_tally_cd[_async] calls since the last reset
+    int32_t decided_call;   // index of the call that decided (-1: undecided)
 };
 
 struct FPResult {
     int32_t decided, len, count, received;
     uint64_t h1, h2;
+    int32_t decided_call, pad;
 };
 struct FP {
     int device = 0;
@@ -55,6 +58,8 @@ struct FP {
     DevBuf<int32_t> entries, call_list;   // [T] created entries / entries voted for in the call in flight
     DevBuf<int32_t> blk_cnt;              // [8][grid] per-block vote counts of the quorum candidates (k_fp_tally_cd)
     int tally_grid = 0;                   // co-resident blocks of the cooperative tally kernel
+    rapid_comm* pending_comm = nullptr;   // what the last enqueued rapid_fp_tally_cd[_async] was called with
+    const rapid_cd* pending_cd = nullptr;
     DevBuf<FPState> st;
     PinnedBuf<FPState> h_st;
     // staging for host-array votes
@@ -131,7 +136,7 @@ __global__ void k_fp_reset(int64_t sender_cap, int32_t* __restrict__ seen, uint3
     if (i < (int64_t)T) { t_state[i] = 0; t_count[i] = 0; t_call[i] = 0; }
     if (i == 0) {
         st->decided = 0; st->decided_entry = 0; st->votes_received = 0; st->n_valid_call = 0; st->n_cand = 0; st->i_star = INT_MAX; st->bad_sender = -1;
-        st->n_entries = 0; st->n_call = 0; st->ticket = 0; st->too_many = 0;
+        st->n_entries = 0; st->n_call = 0; st->ticket = 0; st->too_many = 0; st->calls = 0; st->decided_call = -1;
     }
 }
 
@@ -404,6 +409,7 @@ __global__ void k_fp_result(const FPState* __restrict__ st, const uint64_t* __re
                             const int32_t* __restrict__ t_len, const int32_t* __restrict__ t_count, FPResult* __restrict__ out) {
     FPResult r;
     r.decided = st->decided; r.received = st->votes_received; r.len = 0; r.count = 0; r.h1 = 0; r.h2 = 0;
+    r.decided_call = st->decided_call; r.pad = 0;
     if (r.decided && st->decided_entry >= 0) {
         const int32_t e = st->decided_entry;
         r.h1 = t_h1[e]; r.h2 = t_h2[e]; r.len = t_len[e]; r.count = t_count[e];
@@ -474,10 +480,14 @@ __global__ void k_fp_decide_sum_impl(const unsigned long long* __restrict__ buf,
 // one block: initialise the result, then look for the bucket that reached the quorum (k_fp_sum_begin + k_fp_decide_sum_impl fused)
 __global__ void __launch_bounds__(1024) k_fp_decide_sum(const unsigned long long* __restrict__ buf, unsigned long long Q,
                                                         FPSumResult* __restrict__ out, FPState* __restrict__ st) {
+    __shared__ int32_t s_call;
     if (threadIdx.x == 0) {
         out->r.decided = 0; out->r.len = 0; out->r.count = 0; out->r.h1 = 0; out->r.h2 = 0;
         out->r.received = (int32_t)buf[(size_t)SUM_BUCKETS * SUM_WORDS];
+        out->r.decided_call = st->decided_call; out->r.pad = 0;
         out->ambiguous = 0; out->pad = 0;
+        s_call = st->calls;
+        st->calls = s_call + 1;
     }
     __syncthreads();
     for (int b = threadIdx.x; b < SUM_BUCKETS; b += blockDim.x) {
@@ -500,7 +510,8 @@ __global__ void __launch_bounds__(1024) k_fp_decide_sum(const unsigned long long
         if (ok) {
             out->r.decided = 1; out->r.h1 = h1; out->r.h2 = h2; out->r.len = (int32_t)len; out->r.count = (int32_t)c;
             // remember the decision locally so that later votes are ignored (:138)
-            st->decided = 1; st->decided_entry = -1; st->votes_received = (int32_t)buf[(size_t)SUM_BUCKETS * SUM_WORDS];
+            if (!st->decided) { st->decided_call = s_call; out->r.decided_call = s_call; }
+            st->decided = 1; st->decided_entry = -1;
         } else {
             out->ambiguous = 1;
         }
@@ -769,9 +780,11 @@ __global__ void __launch_bounds__(TALLY_THREADS) k_fp_tally_cd(const TallyCdArgs
     const int32_t nc = st->n_call;
     for (int32_t q = t; q < nc; q += TALLY_THREADS) a.t_call[a.call_list[q]] = 0;
     if (t == 0) {
-        if (!was_decided && n_cand > 0 && st->i_star < INT_MAX) { st->decided = 1; st->decided_entry = a.ent[st->i_star]; }
+        if (!was_decided && n_cand > 0 && st->i_star < INT_MAX) { st->decided = 1; st->decided_entry = a.ent[st->i_star]; st->decided_call = st->calls; }
         FPResult r;
         r.decided = st->decided; r.received = st->votes_received; r.len = 0; r.count = 0; r.h1 = 0; r.h2 = 0;
+        r.decided_call = st->decided_call; r.pad = 0;
+        st->calls = st->calls + 1;
         if (r.decided && st->decided_entry >= 0) {
             const int32_t e = st->decided_entry;
             r.h1 = a.t_h1[e]; r.h2 = a.t_h2[e]; r.len = a.t_len[e]; r.count = *(volatile int32_t*)&a.t_count[e];
@@ -977,13 +990,12 @@ int32_t rapid_fp_tally(rapid_fp* fp, int64_t n_votes, const int32_t* sender, con
     return RAPID_OK;
 }
 
-int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, int32_t* decided, uint64_t* decided_hash,
-                          uint64_t* decided_hash2, int32_t* decided_len, int32_t* decided_count, int32_t* votes_received) {
+// enqueue the tally of the detector's votes (and, sharded, the all-reduce + decision kernel) on the tally's stream
+static int32_t tally_cd_enqueue(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm) {
     if (!fp || !cd) { set_error("NULL handle"); return RAPID_EINVAL; }
     if (fp->device != cd->device) { set_error("fp and cd live on different devices"); return RAPID_EINVAL; }
     if (cd->raw) { set_error("RAW detectors do not announce proposals"); return RAPID_EINVAL; }
     if (comm && comm->device != fp->device) { set_error("comm and fp live on different devices"); return RAPID_EINVAL; }
-    DeviceGuard g(fp->device);
     cudaStream_t s = fp->stream;
     const int64_t R = cd->R;
     RAPID_CHECK(fp->ent.reserve((size_t)R));
@@ -1018,14 +1030,35 @@ int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, in
     void* args[] = {(void*)&ta};
     RAPID_CUDA(cudaLaunchCooperativeKernel((void*)k_fp_tally_cd, dim3((unsigned)grid), dim3(TALLY_THREADS), args, 0, s));
     fp->last_launches = 1;
-    if (!direct) {
-        // single GPU: exact arrival order = receiver order; ONE launch, one read-back
-        RAPID_CUDA(cudaMemcpyAsync(fp->h_res_raw.p, fp->d_res_raw.p, sizeof(FPResult), cudaMemcpyDeviceToHost, s));
-        RAPID_CUDA(cudaEventRecord(fp->ev1, s));
-        RAPID_CUDA(cudaStreamSynchronize(s));
-        cudaEventElapsedTime(&fp->last_ms, fp->ev0, fp->ev1);
+    fp->pending_comm = comm;
+    fp->pending_cd = cd;
+    if (direct && getenv("RAPID_B200_FORCE_REFINE") == nullptr) {
+        // sharded: count-weighted sums of the local table -> ONE all-reduce (sum) -> the winning bucket gives the proposal back
+        // by exact division (RAPID_B200_FORCE_REFINE: test hook that skips this and takes the digit-by-digit refinement)
+        RAPID_NCCL(g_nccl.AllReduce(fp->sumbuf.p, fp->sumbuf.p, words, NCCL_UINT64, NCCL_SUM, comm->comm, s));
+        k_fp_decide_sum<<<1, 1024, 0, s>>>(fp->sumbuf.p, (unsigned long long)fp->Q, (FPSumResult*)fp->d_res_raw.p, fp->st.p);
+        RAPID_KERNEL_CHECK();
+        fp->last_launches += 1;
+    }
+    RAPID_CUDA(cudaMemcpyAsync(fp->h_res_raw.p, fp->d_res_raw.p, sizeof(FPSumResult), cudaMemcpyDeviceToHost, s));
+    RAPID_CUDA(cudaEventRecord(fp->ev1, s));
+    return RAPID_OK;
+}
+
+static int32_t tally_cd_refine(rapid_fp* fp, rapid_comm* comm, int32_t* decided, uint64_t* decided_hash, uint64_t* decided_hash2,
+                               int32_t* decided_len, int32_t* decided_count, int32_t* votes_received);
+
+// wait for the last enqueued tally and read its outcome (ONE host synchronisation)
+static int32_t tally_cd_collect(rapid_fp* fp, int32_t* decided, uint64_t* decided_hash, uint64_t* decided_hash2, int32_t* decided_len,
+                                int32_t* decided_count, int32_t* votes_received, int32_t* decided_in_call) {
+    cudaStream_t s = fp->stream;
+    RAPID_CUDA(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&fp->last_ms, fp->ev0, fp->ev1);
+    cudaGetLastError();
+    if (fp->pending_cd) RAPID_CHECK(cd_wait(fp->pending_cd, true));      // outcome of the (asynchronous) batches these votes came from
+    rapid_comm* comm = fp->pending_comm;
+    if (comm == nullptr) {
         const FPResult r = *(const FPResult*)fp->h_res_raw.p;
-        RAPID_CHECK(cd_wait(cd, true));                  // outcome of the (asynchronous) batch these votes came from
         if (r.decided < 0) { set_error("more than 8 proposals reached the quorum in one call"); return RAPID_EUNSUPPORTED; }
         fp->decided_host = r.decided != 0;
         if (decided) *decided = r.decided;
@@ -1034,26 +1067,12 @@ int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, in
         if (decided_hash2) *decided_hash2 = r.h2;
         if (decided_len) *decided_len = r.len;
         if (decided_count) *decided_count = r.count;
+        if (decided_in_call) *decided_in_call = r.decided_call;
         return RAPID_OK;
     }
-    // ---- sharded: count-weighted sums of the local table -> ONE all-reduce (sum) -> the winning bucket gives the proposal
-    // back by exact division; refine digit by digit only if two fingerprints share a quorum-sized bucket.
-    const int TB = 256;
-    const unsigned gt = (unsigned)ceil_div<uint32_t>(fp->T, TB);
-    // RAPID_B200_FORCE_REFINE: test hook — take the refinement path even though no bucket is ambiguous
-    if (getenv("RAPID_B200_FORCE_REFINE") == nullptr) {   // the common case: ONE all-reduce, one readback
-        RAPID_NCCL(g_nccl.AllReduce(fp->sumbuf.p, fp->sumbuf.p, words, NCCL_UINT64, NCCL_SUM, comm->comm, s));
-        FPSumResult* dres = (FPSumResult*)fp->d_res_raw.p;
-        k_fp_decide_sum<<<1, 1024, 0, s>>>(fp->sumbuf.p, (unsigned long long)fp->Q, dres, fp->st.p);
-        RAPID_KERNEL_CHECK();
-        fp->last_launches += 1;
-        RAPID_CUDA(cudaMemcpyAsync(fp->h_res_raw.p, dres, sizeof(FPSumResult), cudaMemcpyDeviceToHost, s));
-        RAPID_CUDA(cudaEventRecord(fp->ev1, s));
-        RAPID_CUDA(cudaStreamSynchronize(s));
-        RAPID_CHECK(cd_wait(cd, true));
+    if (getenv("RAPID_B200_FORCE_REFINE") == nullptr) {
         const FPSumResult res = *(const FPSumResult*)fp->h_res_raw.p;
         if (!res.ambiguous) {
-            cudaEventElapsedTime(&fp->last_ms, fp->ev0, fp->ev1);
             if (res.r.decided) fp->decided_host = true;
             if (decided) *decided = res.r.decided;
             if (decided_hash) *decided_hash = res.r.h1;
@@ -1061,13 +1080,46 @@ int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, in
             if (decided_len) *decided_len = res.r.len;
             if (decided_count) *decided_count = res.r.count;
             if (votes_received) *votes_received = res.r.received;
+            if (decided_in_call) *decided_in_call = res.r.decided_call;
             return RAPID_OK;
         }
-        // two proposals share a quorum-sized bucket: fall through to the digit-by-digit refinement
-    } else {
-        RAPID_CUDA(cudaStreamSynchronize(s));
-        RAPID_CHECK(cd_wait(cd, true));
+        // two proposals share a quorum-sized bucket (every rank sees the same flag): digit-by-digit refinement
     }
+    if (decided_in_call) *decided_in_call = -1;
+    return tally_cd_refine(fp, comm, decided, decided_hash, decided_hash2, decided_len, decided_count, votes_received);
+}
+
+int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, int32_t* decided, uint64_t* decided_hash,
+                          uint64_t* decided_hash2, int32_t* decided_len, int32_t* decided_count, int32_t* votes_received) {
+    if (!fp) { set_error("NULL handle"); return RAPID_EINVAL; }
+    DeviceGuard g(fp->device);
+    RAPID_CHECK(tally_cd_enqueue(fp, cd, comm));
+    return tally_cd_collect(fp, decided, decided_hash, decided_hash2, decided_len, decided_count, votes_received, nullptr);
+}
+
+int32_t rapid_fp_tally_cd_async(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm) {
+    if (!fp) { set_error("NULL handle"); return RAPID_EINVAL; }
+    DeviceGuard g(fp->device);
+    return tally_cd_enqueue(fp, cd, comm);
+}
+
+int32_t rapid_fp_result(rapid_fp* fp, int32_t* decided, uint64_t* decided_hash, uint64_t* decided_hash2, int32_t* decided_len,
+                        int32_t* decided_count, int32_t* votes_received, int32_t* decided_in_call) {
+    if (!fp) { set_error("NULL handle"); return RAPID_EINVAL; }
+    if (!fp->pending_cd) { set_error("no rapid_fp_tally_cd_async call to collect"); return RAPID_EINVAL; }
+    DeviceGuard g(fp->device);
+    return tally_cd_collect(fp, decided, decided_hash, decided_hash2, decided_len, decided_count, votes_received, decided_in_call);
+}
+
+// the rare path: a quorum-sized bucket of the sum buffer holds more than one fingerprint
+static int32_t tally_cd_refine(rapid_fp* fp, rapid_comm* comm, int32_t* decided, uint64_t* decided_hash, uint64_t* decided_hash2,
+                               int32_t* decided_len, int32_t* decided_count, int32_t* votes_received) {
+    cudaStream_t s = fp->stream;
+    const int TB = 256;
+    const unsigned gt = (unsigned)ceil_div<uint32_t>(fp->T, TB);
+    RAPID_CUDA(cudaEventRecord(fp->ev0, s));
+    RAPID_CUDA(cudaMemcpyAsync(fp->h_st.p, fp->st.p, sizeof(FPState), cudaMemcpyDeviceToHost, s));
+    RAPID_CUDA(cudaStreamSynchronize(s));
     Prefix pf;
     pf.n = 0;
     int32_t dec = 0, dcount = 0, dlen = 0;
@@ -1124,6 +1176,18 @@ int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, in
     if (decided_len) *decided_len = dlen;
     if (decided_count) *decided_count = dcount;
     if (votes_received) *votes_received = recv;
+    return RAPID_OK;
+}
+
+int32_t rapid_fp_timer_stop(rapid_fp* fp, const rapid_cd* cd, float* out_ms) {
+    if (!fp || !cd || !out_ms) { set_error("NULL argument"); return RAPID_EINVAL; }
+    if (fp->device != cd->device) { set_error("fp and cd live on different devices"); return RAPID_EINVAL; }
+    DeviceGuard g(fp->device);
+    RAPID_CUDA(cudaStreamWaitEvent(fp->stream, cd->ev_done, 0));
+    RAPID_CUDA(cudaEventRecord(fp->ev1, fp->stream));
+    RAPID_CUDA(cudaStreamSynchronize(fp->stream));
+    RAPID_CHECK(cd_wait(cd, false));
+    RAPID_CUDA(cudaEventElapsedTime(out_ms, cd->ev_t0, fp->ev1));
     return RAPID_OK;
 }
 

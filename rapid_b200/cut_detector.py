@@ -176,6 +176,9 @@ class VirtualCluster:
         N.check(fn(self._h, int(cfg_id), int(n_cells), None, dst_dev, ring_dev, status_dev, cell_cfg_dev or None,
                    C.byref(d) if d is not None else None))
 
+    def timerStart(self):
+        N.check(N.lib().rapid_cd_timer_start(self._h))
+
     def sync(self):
         """wait for asynchronous batches; raises if one of them failed"""
         N.check(N.lib().rapid_cd_sync(self._h))

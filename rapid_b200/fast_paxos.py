@@ -15,10 +15,11 @@ def quorum(membership_size):
 
 
 class TallyResult:
-    __slots__ = ("decided", "hash", "hash2", "length", "count", "votes_received")
+    __slots__ = ("decided", "hash", "hash2", "length", "count", "votes_received", "decided_in")
 
-    def __init__(self, decided, h1, h2, ln, count, received):
+    def __init__(self, decided, h1, h2, ln, count, received, decided_in=None):
         self.decided, self.hash, self.hash2, self.length, self.count, self.votes_received = decided, h1, h2, ln, count, received
+        self.decided_in = decided_in          # index of the tally call that decided (asynchronous tallies only)
 
     def __repr__(self):
         return "TallyResult(decided=%s, hash=%#x, len=%d, count=%d, votes_received=%d)" % (
@@ -89,12 +90,28 @@ class FastPaxos:
                                           C.byref(a), C.byref(b), C.byref(l), C.byref(c), C.byref(r)))
         return TallyResult(bool(d.value), a.value, b.value, l.value, c.value, r.value)
 
+    def tallyClusterAsync(self, cluster, comm=None):
+        """enqueue only; result() collects the outcome of the last enqueued tally"""
+        N.check(N.lib().rapid_fp_tally_cd_async(self._h, cluster._h, comm._h if comm is not None else None))
+
+    def result(self):
+        d, a, b, l, c, r = self._outs()
+        k = C.c_int32(-1)
+        N.check(N.lib().rapid_fp_result(self._h, C.byref(d), C.byref(a), C.byref(b), C.byref(l), C.byref(c), C.byref(r), C.byref(k)))
+        return TallyResult(bool(d.value), a.value, b.value, l.value, c.value, r.value, k.value)
+
     def reset(self, configuration_id, membership_size=None):
         """the new FastPaxos instance of the next configuration (MembershipService.java:427-429)"""
         self.cfg = int(configuration_id)
         if membership_size is not None:
             self.N = int(membership_size)
         N.check(N.lib().rapid_fp_reset(self._h, self.cfg, self.N))
+
+    def timerStop(self, cluster):
+        """milliseconds on the device since cluster.timerStart(), after everything enqueued so far on both handles"""
+        a = C.c_float(0)
+        N.check(N.lib().rapid_fp_timer_stop(self._h, cluster._h, C.byref(a)))
+        return a.value
 
     def lastLaunches(self):
         a = C.c_int32(0)

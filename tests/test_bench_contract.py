@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_contract_line(orc):
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--nodes", "3000", "--steps", "2",
-                        "--warmup", "1", "--cpu-seconds", "1"], capture_output=True, text=True, timeout=600)
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, p.stdout
@@ -25,6 +25,18 @@ def test_reference_arm_prints_one_contract_line(orc):
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 0 and d["steps"] == 2
+    # everything in cpu_baseline is measured on the sample; the whole-cluster figure is a labelled extrapolation on the side
+    assert cb["sampled_nodes"] >= 1 and cb["apply_s"] > 0 and cb["tally_s"] > 0
+    assert abs(cb["value"] - d["config"]["cells"] / (cb["apply_s"] + cb["tally_s"])) <= 0.5 * cb["value"]     # mean of 2 steps
+    assert "NOT measured" in cb["extrapolated_whole_cluster"]["how"]
+
+
+def test_reference_arm_runs_the_flip_flop_stream(orc):
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c4", "--nodes", "3000",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads([l for l in p.stdout.splitlines() if l.strip()][0])
+    assert d["config"]["workload"].startswith("C4 3000-node") and d["value"] > 0
 
 
 def test_other_ranks_of_the_reference_arm_do_nothing():
