@@ -70,6 +70,45 @@ final class GpuMembershipView {
         return byId.get(id);
     }
 
+    /** id of a known endpoint (member or registered joiner), -1 otherwise; never registers anything */
+    int tryIdOf(final Endpoint e) {
+        final Integer id = ids.get(e);
+        return id == null ? -1 : id;
+    }
+
+    int getMembershipSize() {                                 // :425-432
+        return members;
+    }
+
+    List<Endpoint> getRing(final int k) {                     // :380-388
+        final int[] out = new int[members];
+        final int rc = Native.viewRing(handle, k, out);
+        return map(out, rc < 0 ? rc : members);
+    }
+
+    List<Integer> getRingNumbers(final Endpoint observer, final Endpoint subject) {   // :397-418
+        final int mask = Native.viewRingNumbers(handle, idOf(observer, false), idOf(subject, false));
+        if (mask < 0) {
+            throw new IllegalStateException(Native.lastError());
+        }
+        final List<Integer> rings = new ArrayList<>();
+        for (int k = 0; k < K; k++) {
+            if (((mask >> k) & 1) != 0) {
+                rings.add(k);
+            }
+        }
+        return rings;
+    }
+
+    /** :360-372, :544-556 — identifiersSeen is kept by the caller (NodeId high / low words, any order: sorted on the device) */
+    long getCurrentConfigurationId(final long[] idHigh, final long[] idLow) {
+        final long[] out = new long[1];
+        if (Native.viewConfigId(handle, idHigh, idLow, out) != 0) {
+            throw new IllegalStateException(Native.lastError());
+        }
+        return out[0];
+    }
+
     List<Endpoint> getObserversOf(final Endpoint node) {      // :210-224
         return row(node, true);
     }

@@ -1,6 +1,6 @@
 """The N > 1 path on CPU: two processes (torch.distributed, gloo, 127.0.0.1) shard the virtual nodes by ring-0 range,
 each computes its own nodes' proposals (with the oracle — this is a test), and the sharded tally protocol
-(histogram sum all-reduce + verification max all-reduce, rapid_b200/sharding.py == csrc/fast_paxos.cu) must reach the
+(histogram sum all-reduce + verification max all-reduce, tests/sharding_model.py == csrc/fast_paxos.cu) must reach the
 decision a single FastPaxos instance reaches over all votes."""
 import os
 import socket
@@ -15,11 +15,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = textwrap.dedent("""
     import os, sys
     sys.path.insert(0, %(root)r)
+    sys.path.insert(0, os.path.join(%(root)r, "tests"))
     import numpy as np
     import torch
     import torch.distributed as dist
     from oracle import oracle_py as orc
-    from rapid_b200 import workloads as W, sharding as S
+    from rapid_b200 import workloads as W
+    import sharding_model as S
     from rapid_b200._native import lib
     import ctypes as C
 
@@ -122,7 +124,7 @@ def test_two_process_sharded_tally(tmp_path, orc):
 
 
 def test_shard_ranges_partition():
-    from rapid_b200 import sharding as S
+    import sharding_model as S
     for n in (1, 7, 1000, 1_000_003):
         for world in (1, 2, 3, 4, 8):
             edges = [S.shard_range(n, r, world) for r in range(world)]
