@@ -11,7 +11,9 @@ Workloads:
                   ~10^5 alert cells), every receiver gets the batch in array order
     c4            BASELINE config 4: 100,000 nodes, 1 % flip-flop stream over T = 8 batches with 1/4 duplicate re-sends, every
                   receiver applies each batch in ITS OWN permuted order, detector state carried from batch to batch; the step
-                  ends with the batch in which the cut is decided (duplicates count as applied cells)
+                  ends with the batch in which the cut is decided (duplicates count as applied cells).  --stream sequence
+                  (default): the 8 batches are handed over in ONE rapid_cd_apply_batches call — handleMessage once per batch
+                  with the announcedProposal gating between them, computed in one pass over the state; --stream batches: 8 calls
     c3 / c2       BASELINE configs 3 / 2 (10,000-node correlated partition / 2,000-node simultaneous crash), one batch
 Receivers are sharded over the GPUs by ring-0 range; the cluster size stays fixed ("scaling": "strong").
 
@@ -61,6 +63,9 @@ def parse():
     p.add_argument("--kernel", default="auto", choices=["auto", "bucketed", "sweep"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-carried", action="store_true", help="skip the extra carried-state (read-modify-write) measurement of c5")
+    p.add_argument("--stream", default="sequence", choices=["sequence", "batches"],
+                   help="c4 only: deliver the 8-batch stream as ONE rapid_cd_apply_batches call (one pass over the detector state, "
+                        "checked on the device, batch-by-batch replay if refused) or as 8 separate calls")
     p.add_argument("--emulate-shard", type=int, default=0,
                    help="tuning aid: run rank 0's shard of a G-way run on ONE GPU without NCCL (no decision is reached)")
     a = p.parse_args()
@@ -359,6 +364,15 @@ def run_ours(args):
     dev = [(torch.from_numpy(b.dst).cuda(), torch.from_numpy(b.ring).cuda(), torch.from_numpy(b.status).cuda()) for b in st.batches]
     d_blocked = torch.from_numpy(blocked).cuda()
     asynchronous = args.kernel != "sweep"
+    sequence = args.workload == "c4" and args.stream == "sequence" and args.kernel != "sweep"
+    if sequence:
+        cat = (torch.from_numpy(np.concatenate([b.dst for b in st.batches])).cuda(),
+               torch.from_numpy(np.concatenate([b.ring for b in st.batches])).cuda(),
+               torch.from_numpy(np.concatenate([b.status for b in st.batches])).cuda())
+        seq_off = np.concatenate([[0], np.cumsum(st.cells)]).astype(np.int64)
+        assert all(st.perm[t] == st.perm[0] + t for t in range(T))        # batch b is permuted with perm_seed + b
+        host_cat = (np.concatenate([b.dst for b in st.batches]), np.concatenate([b.ring for b in st.batches]),
+                    np.concatenate([b.status for b in st.batches]))
 
     acc = {"apply": 0.0, "main": 0.0, "tally": 0.0, "launches": 0, "main_by_batch": [0.0] * T, "calls": [0] * T}
 
@@ -367,6 +381,13 @@ def run_ours(args):
         the decision and the index of the batch that produced it.  Votes after the decision are ignored on the device."""
         cl.clear()
         fp.reset(cfg)
+        if sequence:
+            # the whole stream in one call (one host synchronisation inside it: the outcome of the device-side check), then the tally
+            cl.handleBatchesDevice(cfg, int(seq_off[-1]), cat[0].data_ptr(), cat[1].data_ptr(), cat[2].data_ptr(), seq_off,
+                                   blocked_dev=d_blocked.data_ptr(), perm_seed=st.perm[0])
+            fp.tallyClusterAsync(cl, comm)
+            res = fp.result()
+            return res, (T - 1 if res.decided else None)
         for bi in range(T):
             d_dst, d_ring, d_status = dev[bi]
             cl.handleBatchDevice(cfg, st.cells[bi], d_dst.data_ptr(), d_ring.data_ptr(), d_status.data_ptr(),
@@ -380,6 +401,15 @@ def run_ours(args):
         cl.clear()
         fp.reset(cfg)
         res = None
+        if sequence:
+            cl.handleBatchesDevice(cfg, int(seq_off[-1]), cat[0].data_ptr(), cat[1].data_ptr(), cat[2].data_ptr(), seq_off,
+                                   blocked_dev=d_blocked.data_ptr(), perm_seed=st.perm[0])
+            res = fp.tallyCluster(cl, comm)
+            tot, main = cl.lastDeviceMs()
+            acc["apply"] += tot; acc["main"] += main; acc["tally"] += fp.lastDeviceMs()
+            acc["main_by_batch"][0] += main; acc["calls"][0] += 1
+            acc["launches"] += cl.lastPath()[1] + 3 + fp.lastLaunches() + 2     # + announced_in kernels, clear(), reset()
+            return res
         for bi in range(T):
             d_dst, d_ring, d_status = dev[bi]
             cl.handleBatchDevice(cfg, st.cells[bi], d_dst.data_ptr(), d_ring.data_ptr(), d_status.data_ptr(),
@@ -395,6 +425,10 @@ def run_ours(args):
         cl.clear()
         fp.reset(cfg)
         res = None
+        if sequence:
+            cl.handleBatches(cfg, None, host_cat[0], host_cat[1], host_cat[2], seq_off, blocked=blocked, perm_seed=st.perm[0],
+                             read_outputs=False)
+            return fp.tallyCluster(cl, comm)
         for bi, b in enumerate(st.batches):
             cl.handleBatch(cfg, None, b.dst, b.ring, b.status, blocked=blocked, perm_seed=st.perm[bi], read_outputs=False)
             res = fp.tallyCluster(cl, comm)
@@ -508,9 +542,19 @@ def run_ours(args):
         # algorithmic bytes of the dominant kernel over one step: per batch, 2 B written per (fresh subject, receiver), 4 B (2 read
         # + 2 written) per (carried subject, receiver), + flags / blocked read once per receiver
         alg = sum((2 * st.fresh[bi] + 4 * st.carried[bi]) * R + 5 * R for bi in range(upto + 1))
+        n_kernel_launches = upto + 1
+        seq_stats = None
+        if sequence:
+            # ONE pass over the state for the whole stream: every subject of the stream is first seen in this call (the step starts
+            # from clear()), so its row is written once and never read: 2 B per (subject, receiver)
+            alg = 2 * st.subjects * R + 5 * R
+            n_kernel_launches = 1
+            seq_stats = cl.sequenceStats()
         achieved = alg / (main_per * 1e-3) / 1e9 if main_per > 0 else 0.0
         path = cl.lastPath()[0]
         kname = {1: "k_sweep", 2: "k_apply_uniform<false>", 3: "k_apply_generic", 4: "k_apply_uniform<true> (permuted delivery)"}.get(path)
+        if sequence:
+            kname += " [sequence of batches, one pass]"
         line = {
             "metric": METRIC, "value": cells_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": G, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -540,12 +584,19 @@ def run_ours(args):
             "gpu_launches": int(acc["launches"]),
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(args, G), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(alg / (upto + 1)), "launches_per_step": upto + 1,
-                         "kernel_ms": main_per / (upto + 1), "kernel_ms_per_step": main_per,
+                         "algorithmic_bytes_per_launch": int(alg / n_kernel_launches), "launches_per_step": n_kernel_launches,
+                         "kernel_ms": main_per / n_kernel_launches, "kernel_ms_per_step": main_per,
                          "kernel_share_of_step": main_per / ms_per_step if ms_per_step else None,
                          "per_batch": [{"fresh_subjects": st.fresh[bi], "carried_subjects": st.carried[bi],
                                         "kernel_ms": acc["main_by_batch"][bi] / max(1, acc["calls"][bi])} for bi in range(upto + 1)]},
         }
+        if sequence:
+            line["config"]["stream"] = ("the %d batches handed over in ONE rapid_cd_apply_batches call: handleMessage once per batch with the "
+                                        "announcedProposal gating between them, computed in one pass over the detector state after a "
+                                        "device-side check per receiver (sequences served in one pass / replayed batch by batch so far: "
+                                        "%d / %d)" % (T, seq_stats[0], seq_stats[1]))
+            line["roofline"]["per_batch"] = None
+            line["roofline"]["note"] = "one launch for the whole stream; all %d subjects are first seen in it: 2 B written per (subject, receiver)" % st.subjects
         if carried is not None:
             ach2 = carried["algorithmic_bytes_per_launch"] / (carried["kernel_ms"] * 1e-3) / 1e9
             carried.update({"bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak})

@@ -167,13 +167,28 @@ int32_t rapid_cd_apply_batch(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, cons
  * Every receiver runs handleMessage (:300-354) once per batch, in array order: filter, cells, invalidateFailingEdges, and the
  * announcedProposal gating BETWEEN batches — a receiver that announces in batch b ignores batches b+1.. (:318-319).  Outputs as
  * rapid_cd_apply_batch (the proposal is that of the announcing batch), plus announced_in[receiver] = index of the batch in
- * which it announced during this call (-1: it did not).  RAPID_CD_SWEEP handles only (RAPID_EUNSUPPORTED otherwise);
- * delivery may carry BLOCKED / BITMAP. */
+ * which it announced during this call (-1: it did not).
+ * Sweep handles walk the cells per receiver; delivery may carry BLOCKED / BITMAP.
+ * Subject-bucketed handles (the default) first treat the whole sequence in ONE pass over the detector state — every batch
+ * before the last folded, order-independently, into the state the last batch is applied to — which is exact whenever no
+ * receiver emits a proposal before the last batch and no invalidation pass at the end of an earlier batch adds a report; both
+ * premises are checked per receiver on the device before anything is committed, and if one fails for any receiver the
+ * sequence is replayed batch by batch (always exact; rapid_cd_sequence_stats counts both outcomes).  delivery may carry
+ * BLOCKED, PERMUTED (batch b is delivered to receiver r in the order of perm_seed + b) or BITMAP (always batch by batch). */
 int32_t rapid_cd_apply_batches(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src, const int32_t* dst,
                                const uint8_t* ring, const uint8_t* status, const int64_t* cell_cfg, int64_t n_batches,
                                const int64_t* batch_off, const rapid_delivery* delivery, uint64_t* proposal_hash,
                                uint64_t* proposal_hash2, int32_t* proposal_len, uint8_t* announced, int32_t* announced_in);
-/* Same, with the cell arrays (and delivery arrays) already resident in device memory and no per-receiver
+/* rapid_cd_apply_batches with the cell arrays (and delivery arrays) already resident in device memory; batch_off stays a HOST
+ * array.  Results stay on the device: rapid_fp_tally_cd counts every receiver that announced during the call,
+ * rapid_cd_read_outputs / rapid_cd_read_announced_in copy them out. */
+int32_t rapid_cd_apply_batches_dev(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src_dev, const int32_t* dst_dev,
+                                   const uint8_t* ring_dev, const uint8_t* status_dev, const int64_t* cell_cfg_dev,
+                                   int64_t n_batches, const int64_t* batch_off, const rapid_delivery* delivery_dev);
+int32_t rapid_cd_read_announced_in(const rapid_cd* cd, int32_t* announced_in /* [R] */);
+/* How many sequences this handle served in one pass / had to replay batch by batch (diagnostics). */
+int32_t rapid_cd_sequence_stats(const rapid_cd* cd, int32_t* one_pass, int32_t* replayed);
+/* Same as rapid_cd_apply_batch, with the cell arrays (and delivery arrays) already resident in device memory and no per-receiver
  * readback: results stay on the device for rapid_fp_tally_cd / rapid_cd_read_outputs. */
 int32_t rapid_cd_apply_batch_dev(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src_dev,
                                  const int32_t* dst_dev, const uint8_t* ring_dev, const uint8_t* status_dev,

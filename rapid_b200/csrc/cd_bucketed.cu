@@ -34,6 +34,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <climits>
 #include <cstdlib>
 
 #include "cd_internal.cuh"
@@ -65,14 +66,21 @@ constexpr uint32_t PF_NEGINF = 2u;    // a subject already in the unstable band 
 struct ChunkAcc {                     // what the FRESH subjects of a chunk contribute to EVERY active receiver
     uint32_t nLH, tpUn, fl, minTH, minTLun, pad_;
     uint64_t h1, h2;
+    // sequences of batches: the prefix part (batches before the last one)
+    uint32_t nLHp, tpc, minBHp, minBLlong;
+    uint64_t h1p, h2p;
 };
 
 struct Partials {                     // [n_chunks][Rpad] structure of arrays
-    uint4* cnt;                       // x = nL | nH << 16, y = touched_pre | nUn << 16, z = flags, w = 0
+    uint4* cnt;                       // x = nL | nH << 16, y = touched_pre | nUn << 16, z = flags | tpc << 16, w = nLp | nHp << 16
     uint64_t* minTH;
     uint64_t* minTLun;
     uint64_t* h1;
     uint64_t* h2;
+    uint64_t* h1p;                    // sequences only: fingerprint of the subjects that reached H in the prefix
+    uint64_t* h2p;
+    uint2* seq;                       // sequences only: x = min prefix batch with an H-crossing, y = min L-batch of a subject still in
+                                      // the band when the last batch starts (0 = since before the call)
     int32_t* flag;                    // [n_chunks][n_tiles] 1 = the per-receiver partials of this (chunk, tile) were written
     ChunkAcc* chunk;                  // [n_chunks] used for (chunk, tile) pairs whose flag is 0
     int n_tiles;
@@ -80,14 +88,17 @@ struct Partials {                     // [n_chunks][Rpad] structure of arrays
 
 struct Bucketed {
     DevBuf<int32_t> sidx;                     // cell indices grouped by subject (arrival order inside a subject)
-    DevBuf<int32_t> seg_cnt, seg_pos;         // [slot] scratch of the prepare kernel (seg_cnt all zero between batches)
+    DevBuf<int32_t> seg_cnt, batch_slots;     // [slot] scratch of the prepare kernel (seg_cnt all zero between batches)
+    DevBuf<int32_t> bins, ovf;                // [slot][16] cell bins, [A] overflow list
     DevBuf<SubjDesc> desc;
     DevBuf<SubjWalk> walk;
     DevBuf<uint8_t> s_ring, s_status;         // per sorted cell
     DevBuf<int32_t> p_flag;
     DevBuf<ChunkAcc> p_chunk;
     DevBuf<uint4> p_cnt;
-    DevBuf<uint64_t> p_minTH, p_minTLun, p_h1, p_h2;
+    DevBuf<uint64_t> p_minTH, p_minTLun, p_h1, p_h2, p_h1p, p_h2p;
+    DevBuf<uint2> p_seq;
+    DevBuf<SubjWalk> pwalk;                   // sequences: prefix walks
     DevBuf<unsigned char> ra_dev;             // the ResolveArgs of the batch in flight (the kernels take a pointer: the struct is
                                               // too big to pass by value to the out-of-line rare paths without a per-thread copy)
     DevBuf<uint32_t> mx_fl;                   // [Rpad] MX_* flags
@@ -119,11 +130,13 @@ struct Visit {
     uint32_t tL, tH;
 };
 
+// `ur` is the receiver's state for the subject when the (last) batch starts: its stored word, plus — in a sequence of batches —
+// the rings of the prefix (SubjDesc::pmask)
 __device__ __forceinline__ Visit visit_uniform(uint32_t ur, const SubjDesc& d, const SubjWalk& w, int L, int H) {
     Visit v;
     v.tL = 0; v.tH = 0;
-    if (ur == 0) {                                      // fresh subject: the descriptor already knows the answer
-        v.c0 = 0; v.c1 = d.nr;
+    if (ur == d.pmask) {                                // fresh subject: the descriptor already knows the answer
+        v.c0 = __popc(ur); v.c1 = __popc(ur | d.bmask);
         v.tL = d.tLf; v.tH = d.tHf;
     } else {
         int c = __popc(ur);
@@ -159,6 +172,9 @@ struct Acc {
     uint32_t nL = 0, nH = 0, tp = 0, nUn = 0, flags = 0;
     uint32_t minTH = T32_NONE, minTLun = T32_NONE;
     uint64_t h1 = 0, h2 = 0;
+    // sequences of batches (SEQ kernels only): what the prefix did
+    uint32_t nLp = 0, nHp = 0, tpc = 0, minBHp = T32_NONE, minBLlong = T32_NONE;
+    uint64_t h1p = 0, h2p = 0;
 };
 
 __device__ __forceinline__ bool accumulate(Acc& a, const Visit& v, const SubjDesc& d, int L, int H) {
@@ -171,6 +187,44 @@ __device__ __forceinline__ bool accumulate(Acc& a, const Visit& v, const SubjDes
         return true;
     }
     return false;
+}
+
+// ---- sequences of batches in ONE pass ------------------------------------------------------------------------------------
+// rapid_cd_apply_batches on a bucketed handle: B BatchedAlertMessages, handleMessage (MembershipService.java:300-354) once per
+// batch in order — cells, invalidateFailingEdges, and the announcedProposal gating between batches.  If no receiver emits a
+// proposal before the LAST batch and no invalidation pass at the end of an earlier batch adds a report, then the earlier batches
+// (the "prefix") did nothing but set ring bits and move subjects across L / H — order-independent — and the whole call equals
+// ONE batch (the last) applied to the state `stored word | prefix rings`.  That is what the SEQ kernels compute: one pass over the
+// rows for the whole sequence instead of one per batch.  Both premises are CHECKED per receiver on the device (k_seq_check), with
+// batch-granular sufficient conditions:
+//   A1  no emission in the prefix: no H-crossing in the prefix at all, or a subject that is in the unstable band from a batch
+//       strictly before the first H-crossing until the last batch starts (updatesInProgress never returns to 0 in between)
+//   A2  no implicit report at the end of a prefix batch: for every (subject s, ring k, observer o) with both in the dictionary,
+//       the first batch end at which s is in the band, o is in proposal U preProposal and a DOWN alert has been seen comes
+//       after s reached H or ring k was reported anyway — or is not in the prefix
+// A receiver that fails either test aborts the pass for EVERYONE before anything is committed (rows are double-buffered, the
+// scalars are written by the finalize kernels): the host then replays the sequence batch by batch.
+__device__ __forceinline__ uint32_t visit_prefix(Acc& a, uint32_t ur, const SubjDesc& d, const SubjWalk& pw, int L, int H) {
+    const int c0 = __popc(ur);
+    int c = c0;
+    uint32_t bLp = 0, bHp = 0;
+    if (ur == 0) {                                       // fresh subject: the descriptor knows
+        c = __popc(d.pmask); bLp = d.f_bLp; bHp = d.f_bHp;
+    } else {
+        const int np = __popc(d.pmask);
+        for (int q = 0; q < np; ++q) {
+            const int k = pw.ring[q];
+            const bool isnew = !((ur >> k) & 1u);
+            c += isnew;
+            if (isnew && c == L) bLp = pw.time[q];
+            if (isnew && c == H) bHp = pw.time[q];
+        }
+    }
+    if (c0 >= L && c0 < H) a.tpc++;                      // in the band before the call, touched by the call
+    if (c0 < L && c >= L) a.nLp++;
+    if (c0 < H && c >= H) { a.nHp++; a.h1p += d.mix1; a.h2p += d.mix2; a.minBHp = min(a.minBHp, bHp); }
+    if (c >= L && c < H) a.minBLlong = min(a.minBLlong, c0 >= L ? 0u : bLp);   // in the band when the last batch starts
+    return ur | d.pmask;
 }
 
 struct ApplyArgs {
@@ -186,6 +240,7 @@ struct ApplyArgs {
                                   // overflow flag come from HERE — the host never learns them inside a batch
     const SubjDesc* desc;
     const SubjWalk* walk;
+    const SubjWalk* pwalk;        // sequences of batches: prefix walks
     const int32_t* slot_subject;
     const int32_t* sidx;          // sorted cell indices
     const uint8_t* s_ring;
@@ -203,13 +258,30 @@ __device__ __forceinline__ void note_unresolved(const ApplyArgs& a, int tile, in
 // visit is computed once, merged into the new word with a SWAR mask, and accumulated in registers ("com").  Only
 // when active neighbours disagree (partitions) do we fall back to a per-receiver visit whose accumulators live in
 // the thread's own slice of the global partial arrays.
-__device__ __forceinline__ void part_store(const Partials& p, size_t at, uint32_t nLH, uint32_t tpUn, uint32_t fl,
-                                           uint32_t mTH, uint32_t mTL, uint64_t h1, uint64_t h2) {
-    p.cnt[at] = make_uint4(nLH, tpUn, fl, 0u);
-    p.minTH[at] = mTH == T32_NONE ? T64_NONE : (uint64_t)mTH;
-    p.minTLun[at] = mTL == T32_NONE ? T64_NONE : (uint64_t)mTL;
-    p.h1[at] = h1;
-    p.h2[at] = h2;
+template <bool SEQ>
+__device__ __forceinline__ void part_store(const Partials& p, size_t at, const Acc& a) {
+    p.cnt[at] = make_uint4(a.nL | (a.nH << 16), a.tp | (a.nUn << 16), a.flags | (SEQ ? a.tpc << 16 : 0u), SEQ ? (a.nLp | (a.nHp << 16)) : 0u);
+    p.minTH[at] = a.minTH == T32_NONE ? T64_NONE : (uint64_t)a.minTH;
+    p.minTLun[at] = a.minTLun == T32_NONE ? T64_NONE : (uint64_t)a.minTLun;
+    p.h1[at] = a.h1;
+    p.h2[at] = a.h2;
+    if (SEQ) { p.h1p[at] = a.h1p; p.h2p[at] = a.h2p; p.seq[at] = make_uint2(a.minBHp, a.minBLlong); }
+}
+template <bool SEQ>
+__device__ __forceinline__ void part_merge(const Partials& p, size_t at, const Acc& a) {      // add `a` to what the slot holds
+    uint4 c = p.cnt[at];
+    c.x += a.nL | (a.nH << 16); c.y += a.tp | (a.nUn << 16); c.z |= a.flags;
+    if (SEQ) { c.z += a.tpc << 16; c.w += a.nLp | (a.nHp << 16); }
+    p.cnt[at] = c;
+    if (a.minTH != T32_NONE) { const uint64_t o = p.minTH[at]; if ((uint64_t)a.minTH < o) p.minTH[at] = a.minTH; }
+    if (a.minTLun != T32_NONE) { const uint64_t o = p.minTLun[at]; if ((uint64_t)a.minTLun < o) p.minTLun[at] = a.minTLun; }
+    if (a.nH) { p.h1[at] += a.h1; p.h2[at] += a.h2; }
+    if (SEQ) {
+        if (a.nHp) { p.h1p[at] += a.h1p; p.h2p[at] += a.h2p; }
+        uint2 q = p.seq[at];
+        q.x = min(q.x, a.minBHp); q.y = min(q.y, a.minBLlong);
+        p.seq[at] = q;
+    }
 }
 
 // Subjects whose slot was assigned by this very batch ("fresh") have known-zero state for EVERY receiver: nothing is
@@ -219,15 +291,25 @@ __device__ __forceinline__ void part_store(const Partials& p, size_t at, uint32_
 struct StageAcc {
     uint32_t nLH, tpUn, fl, minTH, minTLun;
     uint64_t h1, h2;
+    uint32_t nLHp, tpc, minBHp, minBLlong;
+    uint64_t h1p, h2p;
 };
 
-template <bool PERM>
+template <bool PERM, bool SEQ>
+__device__ __forceinline__ bool visit_acc(Acc& acc, uint32_t ur, const SubjDesc& d, const SubjWalk* w, const SubjWalk* pw, uint32_t RM, int L, int H) {
+    if (SEQ) ur = visit_prefix(acc, ur, d, *pw, L, H);
+    const Visit v = PERM ? visit_counts(ur & RM, d, RM, L, H) : visit_uniform(ur & RM, d, *w, L, H);
+    return accumulate(acc, v, d, L, H);
+}
+
+template <bool PERM, bool SEQ>
 __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a) {
     __shared__ SubjDesc sd[STAGE];
     __shared__ SubjWalk sw[PERM ? 1 : STAGE];
+    __shared__ SubjWalk spw[SEQ ? STAGE : 1];
     __shared__ const uint16_t* s_src[STAGE];
     __shared__ uint16_t* s_dst[STAGE];
-    __shared__ uint32_t s_nw[STAGE];          // (batch ring mask) replicated in both half-words
+    __shared__ uint32_t s_nw[STAGE];          // (rings reported by the call) replicated in both half-words
     __shared__ int s_unres[STAGE];
     __shared__ StageAcc s_facc;               // fresh-subject accumulators of this block's chunk (same for every receiver)
 
@@ -255,7 +337,10 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
     uint32_t am[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) am[q] = (((act >> (2 * q)) & 1u) ? 0x0000FFFFu : 0u) | (((act >> (2 * q + 1)) & 1u) ? 0xFFFF0000u : 0u);
-    if (t == 0) { s_facc.nLH = 0; s_facc.tpUn = 0; s_facc.fl = 0; s_facc.minTH = T32_NONE; s_facc.minTLun = T32_NONE; s_facc.h1 = 0; s_facc.h2 = 0; }
+    if (t == 0) {
+        s_facc.nLH = 0; s_facc.tpUn = 0; s_facc.fl = 0; s_facc.minTH = T32_NONE; s_facc.minTLun = T32_NONE; s_facc.h1 = 0; s_facc.h2 = 0;
+        s_facc.nLHp = 0; s_facc.tpc = 0; s_facc.minBHp = T32_NONE; s_facc.minBLlong = T32_NONE; s_facc.h1p = 0; s_facc.h2p = 0;
+    }
     const int block_active = __syncthreads_or(act != 0);
     Acc com;                                              // carried subjects: shared by all ACTIVE receivers of this thread
     bool had_exc = false;                                 // the thread's global partial slots hold per-receiver extras
@@ -265,8 +350,7 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
         const int n = min(STAGE, s1 - base);
         __syncthreads();
         if (t < 32) {                                     // warp 0 stages the descriptors (STAGE == 32)
-            uint32_t nLH = 0, tpUn = 0, mTH = T32_NONE, mTL = T32_NONE;
-            uint64_t h1 = 0, h2 = 0;
+            Acc f;                                        // what this lane's FRESH subject contributes to every active receiver
             if (t < n) {
                 const SubjDesc d = a.desc[base + t];
                 sd[t] = d;
@@ -274,15 +358,15 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                 const bool fresh = d.slot >= S_before;
                 s_src[t] = fresh ? nullptr : a.masks + ((size_t)d.slot * 2 + c) * a.Rpad;
                 s_dst[t] = a.masks + ((size_t)d.slot * 2 + (c ^ 1)) * a.Rpad;
-                s_nw[t] = (uint32_t)d.bmask * 0x10001u;
+                s_nw[t] = (uint32_t)(d.bmask | d.pmask) * 0x10001u;
                 int un = 0;
                 if (fresh) {
-                    const int nr = d.nr;
-                    if (nr >= L) nLH += 1u;
-                    if (nr >= H) { nLH += 1u << 16; mTH = d.tHf; h1 = d.mix1; h2 = d.mix2; }
-                    else if (nr >= L) { tpUn += 1u << 16; mTL = d.tLf; un = block_active; }
-                } else if (!PERM) {
-                    sw[t] = a.walk[base + t];
+                    // state 0 for everyone: the descriptor-level answers (visit_prefix / visit_uniform take their shortcuts)
+                    un = (visit_acc<PERM, SEQ>(f, 0u, d, &sw[0], &spw[0], RM, L, H) && block_active) ? 1 : 0;   // (walks not read)
+                    if (PERM) { f.minTH = T32_NONE; f.minTLun = T32_NONE; }
+                } else {
+                    if (!PERM) sw[t] = a.walk[base + t];
+                    if (SEQ) spw[t] = a.pwalk[base + t];
                 }
                 // only subjects with an observer in the dictionary can receive implicit reports: the others never go on
                 // the invalidation work list (has_so is refreshed by k_prepare whenever a subject gets a slot)
@@ -290,18 +374,35 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                 if (!fresh) s_unres[t] = a.wl.has_so[d.slot] ? 0 : -1;       // -1: never list it
             }
             // warp reduction of the fresh subjects' contribution
+            uint32_t nLH = f.nL | (f.nH << 16), tpUn = f.tp | (f.nUn << 16), fl = f.flags, mTH = f.minTH, mTL = f.minTLun;
+            uint64_t h1 = f.h1, h2 = f.h2;
+            uint32_t nLHp = f.nLp | (f.nHp << 16), tpc = f.tpc, mBH = f.minBHp, mBL = f.minBLlong;
+            uint64_t h1p = f.h1p, h2p = f.h2p;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 nLH += __shfl_down_sync(0xffffffffu, nLH, o);
                 tpUn += __shfl_down_sync(0xffffffffu, tpUn, o);
+                fl |= __shfl_down_sync(0xffffffffu, fl, o);
                 mTH = min(mTH, __shfl_down_sync(0xffffffffu, mTH, o));
                 mTL = min(mTL, __shfl_down_sync(0xffffffffu, mTL, o));
                 h1 += __shfl_down_sync(0xffffffffu, h1, o);
                 h2 += __shfl_down_sync(0xffffffffu, h2, o);
+                if (SEQ) {
+                    nLHp += __shfl_down_sync(0xffffffffu, nLHp, o);
+                    tpc += __shfl_down_sync(0xffffffffu, tpc, o);
+                    mBH = min(mBH, __shfl_down_sync(0xffffffffu, mBH, o));
+                    mBL = min(mBL, __shfl_down_sync(0xffffffffu, mBL, o));
+                    h1p += __shfl_down_sync(0xffffffffu, h1p, o);
+                    h2p += __shfl_down_sync(0xffffffffu, h2p, o);
+                }
             }
             if (t == 0) {
-                s_facc.nLH += nLH; s_facc.tpUn += tpUn; s_facc.minTH = min(s_facc.minTH, mTH);
+                s_facc.nLH += nLH; s_facc.tpUn += tpUn; s_facc.fl |= fl; s_facc.minTH = min(s_facc.minTH, mTH);
                 s_facc.minTLun = min(s_facc.minTLun, mTL); s_facc.h1 += h1; s_facc.h2 += h2;
+                if (SEQ) {
+                    s_facc.nLHp += nLHp; s_facc.tpc += tpc; s_facc.minBHp = min(s_facc.minBHp, mBH);
+                    s_facc.minBLlong = min(s_facc.minBLlong, mBL); s_facc.h1p += h1p; s_facc.h2p += h2p;
+                }
             }
         }
         __syncthreads();
@@ -324,8 +425,7 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                 const uint32_t andv = andw & (andw >> 16) & 0xFFFFu, st = (orw | (orw >> 16)) & 0xFFFFu;
                 carried = true;
                 if (andv == st) {
-                    const Visit v = PERM ? visit_counts(st & RM, d, RM, L, H) : visit_uniform(st & RM, d, sw[PERM ? 0 : i], L, H);
-                    unres = accumulate(com, v, d, L, H);
+                    unres = visit_acc<PERM, SEQ>(com, st & RM, d, &sw[PERM ? 0 : i], &spw[SEQ ? i : 0], RM, L, H);
                     const uint32_t nw = st * 0x10001u | nwb;
                     w.x = (w.x & ~am[0]) | (nw & am[0]);
                     w.y = (w.y & ~am[1]) | (nw & am[1]);
@@ -334,25 +434,19 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                 } else {
                     if (!had_exc) {
                         had_exc = true;
+                        const Acc zero;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) part_store(a.part, pbase + j, 0u, 0u, 0u, T32_NONE, T32_NONE, 0ull, 0ull);
+                        for (int j = 0; j < 8; ++j) part_store<SEQ>(a.part, pbase + j, zero);
                     }
                     uint32_t words[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (!((act >> j) & 1u)) continue;
                         const uint32_t sj = (words[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-                        const Visit v = PERM ? visit_counts(sj & RM, d, RM, L, H) : visit_uniform(sj & RM, d, sw[PERM ? 0 : i], L, H);
                         Acc ex;
-                        unres |= accumulate(ex, v, d, L, H);
-                        const size_t at = pbase + j;
-                        uint4 c = a.part.cnt[at];
-                        c.x += ex.nL | (ex.nH << 16); c.y += ex.tp | (ex.nUn << 16); c.z |= ex.flags;
-                        a.part.cnt[at] = c;
-                        if (ex.minTH != T32_NONE) { const uint64_t o = a.part.minTH[at]; if ((uint64_t)ex.minTH < o) a.part.minTH[at] = ex.minTH; }
-                        if (ex.minTLun != T32_NONE) { const uint64_t o = a.part.minTLun[at]; if ((uint64_t)ex.minTLun < o) a.part.minTLun[at] = ex.minTLun; }
-                        if (ex.nH) { a.part.h1[at] += ex.h1; a.part.h2[at] += ex.h2; }
-                        words[j >> 1] |= (uint32_t)d.bmask << ((j & 1) * 16);
+                        unres |= visit_acc<PERM, SEQ>(ex, sj & RM, d, &sw[PERM ? 0 : i], &spw[SEQ ? i : 0], RM, L, H);
+                        part_merge<SEQ>(a.part, pbase + j, ex);
+                        words[j >> 1] |= (nwb & 0xFFFFu) << ((j & 1) * 16);
                     }
                     w = make_uint4(words[0], words[1], words[2], words[3]);
                 }
@@ -372,25 +466,18 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
             const StageAcc f = s_facc;
             ChunkAcc c;
             c.nLH = f.nLH; c.tpUn = f.tpUn; c.fl = f.fl; c.minTH = f.minTH; c.minTLun = f.minTLun; c.pad_ = 0; c.h1 = f.h1; c.h2 = f.h2;
+            c.nLHp = f.nLHp; c.tpc = f.tpc; c.minBHp = f.minBHp; c.minBLlong = f.minBLlong; c.h1p = f.h1p; c.h2p = f.h2p;
             a.part.chunk[chunk] = c;
         }
     }
     if (!need) return;
+    const Acc zero;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const size_t at = pbase + j;
         const bool on = (act >> j) & 1u;
-        if (!had_exc) {
-            if (on) part_store(a.part, at, com.nL | (com.nH << 16), com.tp | (com.nUn << 16), com.flags, com.minTH, com.minTLun, com.h1, com.h2);
-            else part_store(a.part, at, 0u, 0u, 0u, T32_NONE, T32_NONE, 0ull, 0ull);
-        } else if (on) {
-            uint4 c = a.part.cnt[at];
-            c.x += com.nL | (com.nH << 16); c.y += com.tp | (com.nUn << 16); c.z |= com.flags;
-            a.part.cnt[at] = c;
-            if (com.minTH != T32_NONE) { const uint64_t o = a.part.minTH[at]; if ((uint64_t)com.minTH < o) a.part.minTH[at] = com.minTH; }
-            if (com.minTLun != T32_NONE) { const uint64_t o = a.part.minTLun[at]; if ((uint64_t)com.minTLun < o) a.part.minTLun[at] = com.minTLun; }
-            a.part.h1[at] += com.h1; a.part.h2[at] += com.h2;
-        }
+        if (!had_exc) part_store<SEQ>(a.part, at, on ? com : zero);
+        else if (on) part_merge<SEQ>(a.part, at, com);
     }
 }
 
@@ -423,7 +510,7 @@ __device__ __forceinline__ GVisit visit_generic(uint32_t ur, const SubjDesc& d, 
                 if (!has_bitmap || ((dl.bitmap[(size_t)ci * dl.words + (r >> 5)] >> (r & 31)) & 1u)) {
                     ok[j] = true;
                     rk[j] = s_ring[d.seg_begin + j];
-                    tm[j] = permuted ? splitmix64(rs ^ (uint64_t)ci) : (uint64_t)ci + 1ull;
+                    tm[j] = permuted ? splitmix64(rs ^ (uint64_t)(ci - dl.cell_base)) : (uint64_t)ci + 1ull;
                     if (s_status[d.seg_begin + j] == RAPID_EDGE_DOWN) v.seen_down = true;
                     v.have |= 1u << rk[j];
                 }
@@ -465,7 +552,7 @@ __device__ __forceinline__ GVisit visit_generic(uint32_t ur, const SubjDesc& d, 
         if (has_bitmap && !((dl.bitmap[(size_t)ci * dl.words + (r >> 5)] >> (r & 31)) & 1u)) continue;
         if (s_status[j] == RAPID_EDGE_DOWN) v.seen_down = true;
         const int k = s_ring[j];
-        const uint64_t tm = permuted ? splitmix64(rs ^ (uint64_t)ci) : (uint64_t)ci + 1ull;
+        const uint64_t tm = permuted ? splitmix64(rs ^ (uint64_t)(ci - dl.cell_base)) : (uint64_t)ci + 1ull;
         const bool had = (v.have >> k) & 1u;
 #pragma unroll
         for (int kk = 0; kk < MAXK; ++kk)
@@ -596,6 +683,8 @@ struct ResolveArgs {
     int n_chunks;                 // subject chunks of the apply launch (layout of the partials)
     int uniform;                  // moments are cell indices (no PERMUTED / BITMAP)
     int counts_only;              // the apply kernel left the moments out (k_apply_uniform<true>)
+    int seq;                      // a sequence of batches applied in one pass (prefix folded into the state, see visit_prefix)
+    uint8_t* seq_dev;             // [Rpad] scratch of k_seq_check
     uint8_t* cur_w;
     int32_t* n_pre;
     uint32_t* rflags;
@@ -639,39 +728,56 @@ __device__ __forceinline__ int32_t block_sum_i32(int32_t v, int32_t* s_red) {   
 // ------------------------------------------------------------------------------------------------------------------
 // finalize 1: combine the chunk partials of every receiver, classify, keep the scalars
 // ------------------------------------------------------------------------------------------------------------------
-__device__ void phase_finalize1(const ResolveArgs& a, int32_t* s_red) {
+// What the FRESH subjects of the batch contribute is the same for every active receiver (one ChunkAcc per chunk of the apply
+// launch): reduced once per block (warp 0) instead of once per receiver.
+__device__ __forceinline__ void reduce_fresh(const ResolveArgs& a, ChunkAcc* s_fresh, int* s_fhave) {
     const ApplyArgs& ap = a.ap;
-    const int any_down = a.bc->any_down;
-    // What the FRESH subjects of the batch contribute is the same for every active receiver (one ChunkAcc per chunk of the
-    // apply launch): reduce it once per block instead of once per receiver.
-    __shared__ ChunkAcc s_fresh;
-    __shared__ int s_fhave;
     if (threadIdx.x < 32) {
-        uint32_t nL = 0, nH = 0, nUn = 0, fl = 0, mTH = T32_NONE, mTL = T32_NONE;
+        uint32_t nL = 0, nH = 0, tp = 0, nUn = 0, fl = 0, mTH = T32_NONE, mTL = T32_NONE;
         uint64_t h1 = 0, h2 = 0;
+        uint32_t nLp = 0, nHp = 0, tpc = 0, mBH = T32_NONE, mBL = T32_NONE;
+        uint64_t h1p = 0, h2p = 0;
         for (int c = threadIdx.x; c < a.n_chunks; c += 32) {
             const ChunkAcc k = ap.part.chunk[c];
             const uint32_t cH = k.nLH >> 16, cUn = k.tpUn >> 16;
-            nL += k.nLH & 0xFFFFu; nH += cH; nUn += cUn; fl |= k.fl;
+            nL += k.nLH & 0xFFFFu; nH += cH; tp += k.tpUn & 0xFFFFu; nUn += cUn; fl |= k.fl;
             if (cH) mTH = min(mTH, k.minTH);
             if (cUn) mTL = min(mTL, k.minTLun);
             h1 += k.h1; h2 += k.h2;
+            if (a.seq) {
+                nLp += k.nLHp & 0xFFFFu; nHp += k.nLHp >> 16; tpc += k.tpc; mBH = min(mBH, k.minBHp); mBL = min(mBL, k.minBLlong);
+                h1p += k.h1p; h2p += k.h2p;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             nL += __shfl_down_sync(0xffffffffu, nL, o); nH += __shfl_down_sync(0xffffffffu, nH, o);
+            tp += __shfl_down_sync(0xffffffffu, tp, o);
             nUn += __shfl_down_sync(0xffffffffu, nUn, o); fl |= __shfl_down_sync(0xffffffffu, fl, o);
             mTH = min(mTH, __shfl_down_sync(0xffffffffu, mTH, o)); mTL = min(mTL, __shfl_down_sync(0xffffffffu, mTL, o));
             h1 += __shfl_down_sync(0xffffffffu, h1, o); h2 += __shfl_down_sync(0xffffffffu, h2, o);
+            nLp += __shfl_down_sync(0xffffffffu, nLp, o); nHp += __shfl_down_sync(0xffffffffu, nHp, o);
+            tpc += __shfl_down_sync(0xffffffffu, tpc, o);
+            mBH = min(mBH, __shfl_down_sync(0xffffffffu, mBH, o)); mBL = min(mBL, __shfl_down_sync(0xffffffffu, mBL, o));
+            h1p += __shfl_down_sync(0xffffffffu, h1p, o); h2p += __shfl_down_sync(0xffffffffu, h2p, o);
         }
         if (threadIdx.x == 0) {
             ChunkAcc f;
-            f.nLH = nL | (nH << 16); f.tpUn = nUn << 16; f.fl = fl; f.minTH = mTH; f.minTLun = mTL; f.pad_ = 0; f.h1 = h1; f.h2 = h2;
-            s_fresh = f;
-            s_fhave = (nH ? 1 : 0) | (nUn ? 2 : 0);
+            f.nLH = nL | (nH << 16); f.tpUn = tp | (nUn << 16); f.fl = fl; f.minTH = mTH; f.minTLun = mTL; f.pad_ = 0; f.h1 = h1; f.h2 = h2;
+            f.nLHp = nLp | (nHp << 16); f.tpc = tpc; f.minBHp = mBH; f.minBLlong = mBL; f.h1p = h1p; f.h2p = h2p;
+            *s_fresh = f;
+            *s_fhave = (nH ? 1 : 0) | (nUn ? 2 : 0);
         }
     }
     __syncthreads();
+}
+
+__device__ void phase_finalize1(const ResolveArgs& a, int32_t* s_red) {
+    const ApplyArgs& ap = a.ap;
+    const int any_down = a.bc->any_down;
+    __shared__ ChunkAcc s_fresh;
+    __shared__ int s_fhave;
+    reduce_fresh(a, &s_fresh, &s_fhave);
     int32_t my_mixed = 0, my_times = 0;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < ap.R; r += (int64_t)gridDim.x * blockDim.x) {
         a.mx_fl[r] = 0;
@@ -680,8 +786,10 @@ __device__ void phase_finalize1(const ResolveArgs& a, int32_t* s_red) {
         const bool active = !(flags & RF_ANNOUNCED) && !((ap.dl.flags & RAPID_DELIVERY_BLOCKED) && ap.dl.blocked[r]);
         if (!active) { a.rflags[r] = flags; a.out_ann[r] = (flags & RF_ANNOUNCED) ? 1 : 0; continue; }
         flags |= RF_ACTIVE;
-        uint32_t nL = s_fresh.nLH & 0xFFFFu, nH = s_fresh.nLH >> 16, tp = 0, nUn = s_fresh.tpUn >> 16, fl = s_fresh.fl;
+        uint32_t nL = s_fresh.nLH & 0xFFFFu, nH = s_fresh.nLH >> 16, tp = s_fresh.tpUn & 0xFFFFu, nUn = s_fresh.tpUn >> 16, fl = s_fresh.fl;
         uint64_t minTH = s_fresh.minTH, minTLun = s_fresh.minTLun, h1 = s_fresh.h1, h2 = s_fresh.h2;
+        uint32_t nLp = s_fresh.nLHp & 0xFFFFu, nHp = s_fresh.nLHp >> 16;                  // sequences: what the prefix did
+        uint64_t h1p = s_fresh.h1p, h2p = s_fresh.h2p;
         bool haveTH = s_fhave & 1, haveTL = (s_fhave & 2) != 0;
         const int tile = (int)(r / TILE_R);
         // per-receiver partials of the chunks that met a carried subject: four chunks' loads in flight at a time
@@ -690,32 +798,35 @@ __device__ void phase_finalize1(const ResolveArgs& a, int32_t* s_red) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) on[q] = c0 + q < a.n_chunks ? ap.part.flag[(size_t)(c0 + q) * ap.part.n_tiles + tile] : 0;
             uint4 q4[4];
-            uint64_t th[4], tl[4], a1[4], a2[4];
+            uint64_t th[4], tl[4], a1[4], a2[4], b1[4], b2[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (!on[q]) continue;
                 const size_t p = (size_t)(c0 + q) * ap.Rpad + (size_t)r;
                 q4[q] = ap.part.cnt[p]; a1[q] = ap.part.h1[p]; a2[q] = ap.part.h2[p];
                 if (!a.counts_only) { th[q] = ap.part.minTH[p]; tl[q] = ap.part.minTLun[p]; }
+                if (a.seq) { b1[q] = ap.part.h1p[p]; b2[q] = ap.part.h2p[p]; }
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (!on[q]) continue;
                 const uint32_t cH = q4[q].x >> 16, cUn = q4[q].y >> 16;
-                nL += q4[q].x & 0xFFFFu; nH += cH; tp += q4[q].y & 0xFFFFu; nUn += cUn; fl |= q4[q].z;
+                nL += q4[q].x & 0xFFFFu; nH += cH; tp += q4[q].y & 0xFFFFu; nUn += cUn; fl |= q4[q].z & 0xFFFFu;
                 if (!a.counts_only) {
                     if (cH && (!haveTH || th[q] < minTH)) { minTH = th[q]; haveTH = true; }
                     if (cUn && (!haveTL || tl[q] < minTLun)) { minTLun = tl[q]; haveTL = true; }
                 }
                 h1 += a1[q]; h2 += a2[q];
+                if (a.seq) { nLp += q4[q].w & 0xFFFFu; nHp += q4[q].w >> 16; h1p += b1[q]; h2p += b2[q]; }
             }
         }
         // every valid cell reaches every active receiver unless there is a per-receiver bitmap
         if ((a.uniform || a.counts_only) ? any_down : (fl & PF_SEEN)) flags |= RF_SEEN_DOWN;
-        const int32_t npre_old = a.n_pre[r];
+        // a sequence of batches: the prefix moved nLp subjects into the band and nHp on to `proposal` before the last batch started
+        const int32_t npre_old = a.n_pre[r] + (int32_t)nLp - (int32_t)nHp;
         const int32_t npre_new = npre_old + (int32_t)nL - (int32_t)nH;
-        const uint64_t p1_old = a.pend_h1[r], p2_old = a.pend_h2[r];
-        const int32_t pc_old = a.pend_cnt[r];
+        const uint64_t p1_old = a.pend_h1[r] + h1p, p2_old = a.pend_h2[r] + h2p;
+        const int32_t pc_old = a.pend_cnt[r] + (int32_t)nHp;
         uint64_t ph1 = p1_old + h1, ph2 = p2_old + h2;
         int32_t pc = pc_old + (int32_t)nH;
         const int32_t untouched_pre = npre_old - (int32_t)tp;
@@ -827,7 +938,7 @@ __device__ __noinline__ void mixed_pass(const ResolveArgs& m, PassSmem& sm, cons
             if (!on) continue;
             for (int i = 0; i < n; ++i) {
                 const SubjDesc& d = sm.sd[i];
-                const uint32_t st = sm.s_old[i] ? sm.s_old[i][r] : 0u;
+                const uint32_t st = (sm.s_old[i] ? sm.s_old[i][r] : 0u) | d.pmask;   // state when the (last) batch starts
                 const IVisit v = interval_visit(a, m.uniform, st & RM, d, &sm.sw[i], r, rs);
                 if (MODE == 0) {
                     if (!v.crossH) continue;                                  // never closes, or never in the band
@@ -915,8 +1026,8 @@ __device__ __noinline__ bool emitted_in_batch(const ResolveArgs& e, int32_t s, i
     if (e.touch[s] != e.serial) return __popc(w_new & RM) >= a.H && !(w_new & CD_BIT_CALL);
     const int b = e.batch_index[s];
     const SubjDesc d = a.desc[b];
-    const uint32_t old = s >= a.bc->S_before ? 0u : (a.masks + ((size_t)s * 2 + (a.cur[s] ^ 1)) * a.Rpad)[r];
-    if (__popc(old & RM) >= a.H) return true;                              // pending before the batch
+    const uint32_t old = (s >= a.bc->S_before ? 0u : (a.masks + ((size_t)s * 2 + (a.cur[s] ^ 1)) * a.Rpad)[r]) | d.pmask;
+    if (__popc(old & RM) >= a.H) return true;                              // pending before the (last) batch
     SubjWalk wl;
     if (e.uniform) wl = a.walk[b];
     const IVisit v = interval_visit(a, e.uniform, old & RM, d, &wl, r, rs);
@@ -1165,6 +1276,8 @@ __device__ void resolve_tail(const ResolveArgs& a, int32_t serial) {
     c.bad_ring = b->bad_ring; c.bad_dst = b->bad_dst; c.n_mixed = b->n_mixed; c.n_inval = b->n_inval; c.S_before = b->S_before;
     c.overflow = b->overflow; c.need_slots = b->need_slots; c.n_times = b->n_times; c.mixed_iters = b->mixed_iters;
     c.n_pairs = *(volatile int32_t*)a.ap.wl.count; c.ticket = 0; c.serial = serial;
+    c.seq_last = b->seq_last; c.seq_down = b->seq_down; c.seq_abort = b->seq_abort; c.pad_[0] = 0; c.pad_[1] = 0;
+    if (c.seq_abort) { c.n_slots = c.S_before; b->n_slots = c.S_before; }   // the slots this call assigned were given back (seq_rollback)
     // errors stay latched until the host has collected them (an asynchronous caller may have several batches in flight)
     c.sticky_bad_ring = b->sticky_bad_ring | (c.bad_ring >= 0 ? 1 : 0);
     c.sticky_bad_dst = b->sticky_bad_dst | (c.bad_dst >= 0 ? 1 : 0);
@@ -1173,13 +1286,106 @@ __device__ void resolve_tail(const ResolveArgs& a, int32_t serial) {
     *a.snap = c;
     b->n_valid = 0; b->n_batch_subj = 0; b->any_down = 0; b->bad_ring = -1; b->bad_dst = -1; b->n_mixed = 0; b->n_inval = 0;
     b->overflow = 0; b->need_slots = 0; b->n_times = 0; b->mixed_iters = 0; b->ticket = 0;
+    b->seq_last = 0; b->seq_down = INT_MAX; b->seq_abort = 0;
+    b->S_before = c.n_slots;                                            // the next batch starts from here (k_prepare reads it)
+}
+
+// ==================================================================================================================
+// k_seq_check: the two premises of the one-pass treatment of a sequence of batches (see visit_prefix), per receiver.
+// blockIdx.y == 0: A1 from the partial accumulators; blockIdx.y >= 1: A2 over a chunk of the dictionary's slots.  Counts
+// the receivers that fail into bc->seq_abort — every later kernel of the batch returns at once if that is non-zero.
+// ==================================================================================================================
+struct PrefixInfo { uint32_t bL, bH, bK; };      // 1-based prefix batch in which the subject reaches L / H / ring k is first
+                                                  // reported; 0 = already so before the call; T32_NONE = not within the prefix
+__device__ __forceinline__ PrefixInfo prefix_info(uint32_t ur, const SubjDesc* d, const SubjWalk* pw, int k, int L, int H) {
+    PrefixInfo o;
+    int c = __popc(ur);
+    o.bL = c >= L ? 0u : T32_NONE;
+    o.bH = c >= H ? 0u : T32_NONE;
+    o.bK = ((ur >> k) & 1u) ? 0u : T32_NONE;
+    if (d == nullptr || d->pmask == 0) return o;
+    const int np = __popc(d->pmask);
+    for (int q = 0; q < np; ++q) {
+        const int kk = pw->ring[q];
+        if ((ur >> kk) & 1u) continue;
+        ++c;
+        if (c == L) o.bL = pw->time[q];
+        if (c == H) o.bH = pw->time[q];
+        if (kk == k) o.bK = pw->time[q];
+    }
+    return o;
+}
+
+__global__ void __launch_bounds__(GEN_THREADS) k_seq_check(const ResolveArgs* __restrict__ ga) {
+    const ResolveArgs& a = *ga;
+    const ApplyArgs& ap = a.ap;
+    __shared__ int32_t s_red[GEN_THREADS / 32];
+    __shared__ ChunkAcc s_fresh;
+    __shared__ int s_fhave;
+    if (a.bc->overflow) return;
+    const int64_t r = (int64_t)blockIdx.x * GEN_THREADS + threadIdx.x;
+    const uint32_t rf = r < ap.R ? a.rflags[r] : RF_ANNOUNCED;
+    const bool active = r < ap.R && !(rf & RF_ANNOUNCED) && !((ap.dl.flags & RAPID_DELIVERY_BLOCKED) && ap.dl.blocked[r]);
+    int32_t bad = 0;
+    if (blockIdx.y == 0) {
+        // ---- A1: no proposal can have been emitted before the last batch ------------------------------------------------------
+        reduce_fresh(a, &s_fresh, &s_fhave);
+        if (active) {
+            uint32_t tpc = s_fresh.tpc, mBH = s_fresh.minBHp, mBL = s_fresh.minBLlong;
+            const int tile = (int)(r / TILE_R);
+            for (int c = 0; c < a.n_chunks; ++c) {
+                if (!ap.part.flag[(size_t)c * ap.part.n_tiles + tile]) continue;
+                const size_t p = (size_t)c * ap.Rpad + (size_t)r;
+                tpc += ap.part.cnt[p].z >> 16;
+                const uint2 q = ap.part.seq[p];
+                mBH = min(mBH, q.x); mBL = min(mBL, q.y);
+            }
+            // an H-crossing in the prefix needs a subject that sits in the band from an EARLIER batch (or an untouched one
+            // that has been there since before the call) until the last batch starts
+            const bool ok = mBH == T32_NONE || (a.n_pre[r] - (int32_t)tpc) > 0 || mBL < mBH;
+            if (!ok) bad = 1;
+        }
+    } else {
+        // ---- A2: no invalidation pass at the end of a prefix batch adds a report --------------------------------------------------
+        const int32_t S = a.bc->n_slots, S_before = a.bc->S_before;
+        const uint32_t last = (uint32_t)a.bc->seq_last;                   // prefix batches are 1 .. last (1-based)
+        const int nchunks = (int)gridDim.y - 1;
+        const int per = (S + nchunks - 1) / nchunks;
+        const int32_t q0 = min(S, ((int)blockIdx.y - 1) * per), q1 = min(S, q0 + per);
+        const uint32_t RM = (1u << ap.K) - 1u;
+        const uint32_t bDown = (rf & RF_SEEN_DOWN) ? 0u : (a.bc->seq_down == INT_MAX ? T32_NONE : (uint32_t)a.bc->seq_down);
+        for (int32_t sl = q0; sl < q1; ++sl) {
+            if (!ap.wl.has_so[sl]) continue;                               // (uniform across the block)
+            const bool s_touched = a.touch[sl] == a.serial;
+            const int bs_idx = s_touched ? a.batch_index[sl] : 0;
+            const SubjDesc* ds = s_touched ? &ap.desc[bs_idx] : nullptr;
+            const uint32_t us = (active && sl < S_before) ? ((ap.masks + ((size_t)sl * 2 + ap.cur[sl]) * ap.Rpad)[r] & RM) : 0u;
+            for (int k = 0; k < ap.K; ++k) {
+                const int32_t so = ap.wl.so_tab[(size_t)sl * SO_STRIDE + k];
+                if (so < 0) continue;
+                const bool o_touched = a.touch[so] == a.serial;
+                if (!s_touched && !o_touched && bDown == 0u) continue;     // nothing about this edge changes in the call
+                if (!active) continue;
+                const int bo_idx = o_touched ? a.batch_index[so] : 0;
+                const SubjDesc* dobs = o_touched ? &ap.desc[bo_idx] : nullptr;
+                const uint32_t uo = so < S_before ? ((ap.masks + ((size_t)so * 2 + ap.cur[so]) * ap.Rpad)[r] & RM) : 0u;
+                const PrefixInfo ps = prefix_info(us, ds, s_touched ? &ap.pwalk[bs_idx] : nullptr, k, ap.L, ap.H);
+                const PrefixInfo po = prefix_info(uo, dobs, o_touched ? &ap.pwalk[bo_idx] : nullptr, k, ap.L, ap.H);
+                if (ps.bL == T32_NONE || po.bL == T32_NONE || bDown == T32_NONE) continue;
+                const uint32_t at = max(max(ps.bL, po.bL), bDown);         // first batch end with s in the band, o in U, DOWN seen
+                if (at <= last && at < ps.bH && at < ps.bK) bad = 1;       // ... s still below H, ring k still unreported: it WOULD fire
+            }
+        }
+    }
+    const int32_t b = block_sum_i32(bad, s_red);
+    if (threadIdx.x == 0 && b) atomicAdd(&a.bc->seq_abort, b);
 }
 
 // ---- the four launches after the apply kernel (no host round trip between them) ---------------------------------------------
 __global__ void __launch_bounds__(GEN_THREADS) k_finalize1(const ResolveArgs* __restrict__ ga) {
     const ResolveArgs& a = *ga;
     __shared__ int32_t s_red[GEN_THREADS / 32];
-    if (a.bc->overflow) return;                                         // rolled back by k_prepare: nothing to resolve
+    if (a.bc->overflow || a.bc->seq_abort) return;                      // rolled back by k_prepare / the sequence is replayed batch by batch
     phase_finalize1(a, s_red);
 }
 
@@ -1189,7 +1395,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) k_mixed_flip(const ResolveArgs
     cg::grid_group grid = cg::this_grid();
     __shared__ PassSmem sm;
     __shared__ int32_t s_red[GEN_THREADS / 32];
-    if (a.bc->overflow) return;
+    if (a.bc->overflow || a.bc->seq_abort) return;                      // (no flip: the pre-call rows stay current)
     const int Sb = a.bc->n_batch_subj, S_before = a.bc->S_before;
     if (a.counts_only && a.bc->n_times > 0 && Sb > 0) {
         mixed_pass<2>(a, sm, Sb, S_before);
@@ -1226,7 +1432,14 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) k_inval_finalize2(const Resolv
     __shared__ InvSmem sm;
     __shared__ int32_t s_red[GEN_THREADS / 32];
     const int mixed = a.bc->n_mixed > 0 ? 1 : 0;
-    if (!a.bc->overflow) phase_inval_finalize2<false>(a, mixed, sm, s_red);
+    if (!a.bc->overflow && !a.bc->seq_abort) phase_inval_finalize2<false>(a, mixed, sm, s_red);
+    if (a.bc->seq_abort) {
+        // the one-pass treatment of the sequence was refused: give back the slots this call assigned (their rows were written
+        // but never made current), so that the batch-by-batch replay sees the dictionary of before the call
+        const int32_t s0 = a.bc->S_before, s1 = a.bc->n_slots;
+        for (int32_t sl = s0 + blockIdx.x * blockDim.x + threadIdx.x; sl < s1; sl += gridDim.x * blockDim.x)
+            const_cast<int32_t*>(a.slot_of)[a.ap.slot_subject[sl]] = -1;
+    }
     if (!mixed) resolve_tail(a, a.serial);                               // else k_marks closes the batch
 }
 
@@ -1298,18 +1511,21 @@ int32_t bucketed_prep_buffers(CD* cd, int64_t A, PrepOut* po) {
     b->n_tiles = (int)(cd->Rpad / TILE_R);
     RAPID_CHECK(ensure_pre_capacity(cd, b));
     const size_t a = (size_t)std::max<int64_t>(A, 1);
-    RAPID_CHECK(b->desc.reserve(a)); RAPID_CHECK(b->walk.reserve(a));
+    RAPID_CHECK(b->desc.reserve(a)); RAPID_CHECK(b->walk.reserve(a)); RAPID_CHECK(b->pwalk.reserve(a));
     RAPID_CHECK(b->sidx.reserve(a)); RAPID_CHECK(b->s_ring.reserve(a)); RAPID_CHECK(b->s_status.reserve(a));
     // per-slot scratch: a batch can touch at most S_cap slots (a batch that needs more is rolled back on the device)
     const size_t slots = std::max<size_t>(cd->S_cap, 1);
     RAPID_CHECK(b->batch_index.reserve(slots));
-    RAPID_CHECK(b->seg_pos.reserve(slots));
+    RAPID_CHECK(b->batch_slots.reserve(slots));
+    RAPID_CHECK(b->bins.reserve(slots * 16));
+    RAPID_CHECK(b->ovf.reserve(a));
     if (slots > b->seg_cnt.cap) {
         RAPID_CHECK(b->seg_cnt.reserve(slots));
         RAPID_CUDA(cudaMemsetAsync(b->seg_cnt.p, 0, b->seg_cnt.cap * sizeof(int32_t), cd->stream));
     }
     po->desc = b->desc.p; po->walk = b->walk.p; po->sidx = b->sidx.p; po->s_ring = b->s_ring.p; po->s_status = b->s_status.p;
-    po->batch_index = b->batch_index.p; po->seg_cnt = b->seg_cnt.p; po->seg_pos = b->seg_pos.p;
+    po->batch_index = b->batch_index.p; po->seg_cnt = b->seg_cnt.p; po->batch_slots = b->batch_slots.p;
+    po->bins = b->bins.p; po->ovf = b->ovf.p; po->pwalk = b->pwalk.p;
     po->wl = worklist(b);
     return RAPID_OK;
 }
@@ -1329,7 +1545,7 @@ __global__ void k_clear_worklist(WorkList wl) {
 __global__ void k_reset_counts(BatchCounts* bc, BatchCounts* snap, int32_t* pre_count) {
     BatchCounts c;
     memset(&c, 0, sizeof(c));
-    c.bad_ring = -1; c.bad_dst = -1;
+    c.bad_ring = -1; c.bad_dst = -1; c.seq_down = INT_MAX;
     const int32_t sr = bc->sticky_bad_ring, sd = bc->sticky_bad_dst, so = bc->sticky_overflow;
     c.sticky_bad_ring = sr; c.sticky_bad_dst = sd; c.sticky_overflow = so;       // errors not collected yet survive a clear()
     *bc = c;
@@ -1367,7 +1583,7 @@ int32_t bucketed_clear(CD* cd) {
 // Everything of one batch after k_prepare, enqueued on the handle's stream with NO host synchronisation: the apply kernel
 // (grid sized from an ESTIMATE of the number of batch subjects — the kernels take the real one from the device counters), the
 // cooperative resolve kernel, and the copy of the counter snapshot to pinned host memory.
-int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl) {
+int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, bool seq) {
     Bucketed* b = state(cd);
     cudaStream_t s = cd->stream;
     const bool uniform = !(dl.flags & (RAPID_DELIVERY_BITMAP | RAPID_DELIVERY_PERMUTED));
@@ -1379,7 +1595,7 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl) {
         int dev = 0, sms = 148, per_u = 8, per_g = 4, per_r = 2;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_u, k_apply_uniform<false>, UNI_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_u, k_apply_uniform<false, false>, UNI_THREADS, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_g, k_apply_generic, GEN_THREADS, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_r, k_mixed_flip, GEN_THREADS, 0);
         int per_m = 2;
@@ -1421,6 +1637,7 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl) {
     const size_t pn = (size_t)n_chunks * cd->Rpad;
     RAPID_CHECK(b->p_cnt.reserve(pn)); RAPID_CHECK(b->p_minTH.reserve(pn)); RAPID_CHECK(b->p_minTLun.reserve(pn));
     RAPID_CHECK(b->p_h1.reserve(pn)); RAPID_CHECK(b->p_h2.reserve(pn));
+    if (seq) { RAPID_CHECK(b->p_h1p.reserve(pn)); RAPID_CHECK(b->p_h2p.reserve(pn)); RAPID_CHECK(b->p_seq.reserve(pn)); }
     RAPID_CHECK(b->mx_fl.reserve(cd->Rpad)); RAPID_CHECK(b->mx_a.reserve(cd->Rpad)); RAPID_CHECK(b->mx_cand.reserve(cd->Rpad));
     RAPID_CHECK(b->mx_emax.reserve(cd->Rpad)); RAPID_CHECK(b->mx_p1.reserve(cd->Rpad)); RAPID_CHECK(b->mx_p2.reserve(cd->Rpad));
     RAPID_CHECK(b->mx_pc.reserve(cd->Rpad)); RAPID_CHECK(b->estar.reserve(cd->Rpad));
@@ -1432,21 +1649,26 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl) {
     }
     RAPID_CHECK(b->p_flag.reserve((size_t)n_chunks * std::max(b->n_tiles, 1)));
     RAPID_CHECK(b->p_chunk.reserve((size_t)n_chunks));
-    Partials part{b->p_cnt.p, b->p_minTH.p, b->p_minTLun.p, b->p_h1.p, b->p_h2.p, b->p_flag.p, b->p_chunk.p, b->n_tiles};
+    Partials part{b->p_cnt.p, b->p_minTH.p, b->p_minTLun.p, b->p_h1.p, b->p_h2.p, b->p_h1p.p, b->p_h2p.p, b->p_seq.p, b->p_flag.p, b->p_chunk.p, b->n_tiles};
 
     ApplyArgs ap;
     ap.masks = cd->masks.p; ap.cur = cd->cur.p; ap.Rpad = cd->Rpad;
     ap.K = cd->K; ap.H = cd->H; ap.L = cd->L; ap.R = cd->R; ap.rbegin = cd->rbegin;
     ap.rflags = cd->rflags.p; ap.dl = dl; ap.bc = cd->counts.p;
-    ap.desc = b->desc.p; ap.walk = b->walk.p; ap.slot_subject = cd->slot_subject.p;
+    ap.desc = b->desc.p; ap.walk = b->walk.p; ap.pwalk = b->pwalk.p; ap.slot_subject = cd->slot_subject.p;
     ap.sidx = b->sidx.p; ap.s_ring = b->s_ring.p; ap.s_status = b->s_status.p;
     ap.part = part; ap.n_tiles = b->n_tiles; ap.wl = worklist(b);
 
     RAPID_CUDA(cudaEventRecord(cd->evk0, s));
     if (swar) {
         dim3 grid((unsigned)b->n_tiles, (unsigned)n_chunks);
-        if (counts_only) k_apply_uniform<true><<<grid, UNI_THREADS, 0, s>>>(ap);
-        else k_apply_uniform<false><<<grid, UNI_THREADS, 0, s>>>(ap);
+        if (seq) {
+            if (counts_only) k_apply_uniform<true, true><<<grid, UNI_THREADS, 0, s>>>(ap);
+            else k_apply_uniform<false, true><<<grid, UNI_THREADS, 0, s>>>(ap);
+        } else {
+            if (counts_only) k_apply_uniform<true, false><<<grid, UNI_THREADS, 0, s>>>(ap);
+            else k_apply_uniform<false, false><<<grid, UNI_THREADS, 0, s>>>(ap);
+        }
         cd->last_path = counts_only ? 4 : 2;
     } else {
         dim3 grid((unsigned)(cd->Rpad / GEN_THREADS), (unsigned)n_chunks);
@@ -1459,6 +1681,7 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl) {
     ResolveArgs ra;
     ra.ap = ap; ra.bc = cd->counts.p; ra.snap = cd->counts_snap.p; ra.n_chunks = n_chunks;
     ra.uniform = uniform ? 1 : 0; ra.counts_only = counts_only ? 1 : 0; ra.cur_w = cd->cur.p;
+    ra.seq = seq ? 1 : 0; ra.seq_dev = nullptr;
     ra.n_pre = cd->n_pre.p; ra.rflags = cd->rflags.p; ra.pend_h1 = cd->pend_h1.p; ra.pend_h2 = cd->pend_h2.p;
     ra.pend_cnt = cd->pend_cnt.p; ra.out_h1 = cd->out_h1.p; ra.out_h2 = cd->out_h2.p; ra.out_len = cd->out_len.p; ra.out_ann = cd->out_ann.p;
     ra.mx_fl = b->mx_fl.p; ra.mx_a = b->mx_a.p; ra.mx_cand = b->mx_cand.p; ra.mx_emax = b->mx_emax.p;
@@ -1473,6 +1696,13 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl) {
     RAPID_CUDA(cudaMemcpyAsync(b->ra_dev.p, &ra, sizeof(ResolveArgs), cudaMemcpyHostToDevice, s));
     const ResolveArgs* ga = (const ResolveArgs*)b->ra_dev.p;
     void* args[] = {(void*)&ga};
+    if (seq) {
+        // the premises of the one-pass treatment, per receiver, BEFORE anything is committed (y = 0: A1, y >= 1: A2 over slot chunks)
+        const unsigned echunks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, 4736 / std::max(1u, rblocks)));
+        k_seq_check<<<dim3(rblocks, 1 + echunks), GEN_THREADS, 0, s>>>(ga);
+        RAPID_KERNEL_CHECK();
+        cd->last_launches += 1;
+    }
     k_finalize1<<<rblocks, GEN_THREADS, 0, s>>>(ga);
     RAPID_KERNEL_CHECK();
     RAPID_CUDA(cudaLaunchCooperativeKernel((void*)k_mixed_flip, dim3((unsigned)cgrid), dim3(GEN_THREADS), args, 0, s));

@@ -11,6 +11,8 @@
 // kernel) or a SWAR lane of the subject-bucketed kernels (cd_bucketed.cu).
 #include <algorithm>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 
 #include "cd_internal.cuh"
 
@@ -307,6 +309,15 @@ static void collect(CD* cd) {
     cudaEventElapsedTime(&cd->last_ms, cd->ev0, cd->ev1);
     cudaEventElapsedTime(&cd->last_main_ms, cd->evk0, cd->evk1);
     cudaGetLastError();
+    if (cd->prep_stamps.p && getenv("RAPID_B200_PREP_STAMPS")) {           // profiling aid: phase boundaries of the last k_prepare
+        unsigned long long st[16];
+        if (cudaMemcpy(st, cd->prep_stamps.p, sizeof(st), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            fprintf(stderr, "[k_prepare phases, us]");
+            int prev = 0;
+            for (int i = 1; i < 16; ++i) if (st[i]) { fprintf(stderr, " P%d:%.1f", i, (double)(st[i] - st[prev]) / 1e3); prev = i; }
+            fprintf(stderr, " total:%.1f\n", (double)(st[prev] - st[0]) / 1e3);
+        }
+    }
     if (c.sticky_overflow || c.sticky_bad_ring || c.sticky_bad_dst) {
         if (c.sticky_overflow) {
             cd->deferred_rc = RAPID_ENOMEM;
@@ -388,46 +399,162 @@ static int32_t upload_delivery(CD* cd, int64_t A, const rapid_delivery* d, bool 
     return RAPID_OK;
 }
 
+// ---- bucketed handles: one batch (or a whole sequence of batches in one pass: batch_off_dev != nullptr) -----------------------
+// Three-plus launches (prepare, apply, resolve kernels) and the copy of the counter snapshot, no host round trip in between.
+// The synchronous entry points wait here and replay the batch if the handle had to grow; the asynchronous one returns.
+static int32_t bucketed_one(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev, const uint8_t* ring_dev, const uint8_t* status_dev,
+                            const int64_t* cfg_dev, const DeliveryDev& dl, bool async, const int64_t* batch_off_dev = nullptr,
+                            int32_t n_batches = 1, int32_t seq_last = 0) {
+    cd->cur_ring_dev = ring_dev;
+    cd->cur_status_dev = status_dev;
+    const bool seq = batch_off_dev != nullptr && seq_last > 0;
+    for (int attempt = 0;; ++attempt) {
+        cd->last_launches = 0;
+        cd->last_A = A;
+        RAPID_CUDA(cudaEventRecord(cd->ev0, cd->stream));
+        RAPID_CHECK(ensure_id_capacity(cd));
+        RAPID_CHECK(cd->cell_slot.reserve(std::max<int64_t>(A, 1)));
+        PrepOut po;
+        RAPID_CHECK(bucketed_prep_buffers(cd, A, &po));
+        if (A > 0) RAPID_CHECK(prepare_batch(cd, cfg, A, dst_dev, ring_dev, status_dev, cfg_dev, &po, seq ? batch_off_dev : nullptr, n_batches, seq_last));
+        else ++cd->batch_serial;
+        RAPID_CHECK(bucketed_apply(cd, A, dl, seq));
+        RAPID_CUDA(cudaEventRecord(cd->ev1, cd->stream));
+        RAPID_CUDA(cudaEventRecord(cd->ev_done, cd->stream));
+        cd->pending = true;
+        if (async) return RAPID_OK;
+        RAPID_CUDA(cudaStreamSynchronize(cd->stream));
+        const int32_t carried_rc = cd->deferred_rc;            // errors of EARLIER asynchronous batches stay latched
+        const std::string carried_msg = cd->deferred_msg;
+        collect(cd);
+        if (cd->last.overflow && attempt < 4) {
+            // not an error here: grow the handle and replay (k_prepare rolled its slot assignment back, nothing was applied)
+            cd->deferred_rc = carried_rc; cd->deferred_msg = carried_msg;
+            RAPID_CHECK(ensure_slot_capacity(cd, (size_t)cd->last.need_slots));
+            ++cd->retries;
+            continue;
+        }
+        const int32_t rc = bad_cell_status(cd, cd->last);
+        if (rc != RAPID_OK) { cd->deferred_rc = carried_rc; cd->deferred_msg = carried_msg; return rc; }
+        return RAPID_OK;
+    }
+}
+
+// ---- a sequence of BatchedAlertMessages on a bucketed handle --------------------------------------------------------------------
+// announced_in / outputs of a sequence: a receiver that announces in batch b keeps that batch's proposal as its output even though
+// later batches of a batch-by-batch replay reset the per-batch output arrays.
+__global__ void k_seq_begin(int64_t R, int32_t* __restrict__ out_batch) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) out_batch[r] = -1;
+}
+__global__ void k_seq_note(int64_t R, const uint32_t* __restrict__ rflags, int32_t b, int32_t* __restrict__ out_batch,
+                           const uint64_t* __restrict__ out_h1, const uint64_t* __restrict__ out_h2, const int32_t* __restrict__ out_len,
+                           uint64_t* __restrict__ sq_h1, uint64_t* __restrict__ sq_h2, int32_t* __restrict__ sq_len) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R || !(rflags[r] & RF_ANN_NOW)) return;
+    out_batch[r] = b; sq_h1[r] = out_h1[r]; sq_h2[r] = out_h2[r]; sq_len[r] = out_len[r];
+}
+__global__ void k_seq_finish(int64_t R, uint32_t* __restrict__ rflags, const int32_t* __restrict__ out_batch,
+                             uint64_t* __restrict__ out_h1, uint64_t* __restrict__ out_h2, int32_t* __restrict__ out_len,
+                             const uint64_t* __restrict__ sq_h1, const uint64_t* __restrict__ sq_h2, const int32_t* __restrict__ sq_len) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R || out_batch[r] < 0) return;
+    rflags[r] |= RF_ANN_NOW;                     // "announced during this call": what rapid_fp_tally_cd turns into votes
+    out_h1[r] = sq_h1[r]; out_h2[r] = sq_h2[r]; out_len[r] = sq_len[r];
+}
+
+// handleMessage (MembershipService.java:300-354) once per batch, in order, for every receiver.  First the whole sequence in ONE
+// pass over the state (cd_bucketed.cu, "sequences of batches in ONE pass": exact whenever its two premises hold for every
+// receiver, which the device checks before committing anything); if a receiver fails the check, batch by batch.
+static int32_t bucketed_sequence(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev, const uint8_t* ring_dev, const uint8_t* status_dev,
+                                 const int64_t* cfg_dev, const DeliveryDev& dl, const int64_t* off, const int64_t* batch_off_dev,
+                                 int32_t n_batches, int32_t* out_batch_dev) {
+    (void)A;
+    cudaStream_t s = cd->stream;
+    const size_t R = (size_t)cd->R;
+    RAPID_CHECK(cd->sq_h1.reserve(R)); RAPID_CHECK(cd->sq_h2.reserve(R)); RAPID_CHECK(cd->sq_len.reserve(R));
+    const unsigned g = (unsigned)ceil_div<int64_t>(cd->R, 256);
+    k_seq_begin<<<g, 256, 0, s>>>(cd->R, out_batch_dev);
+    RAPID_KERNEL_CHECK();
+    auto note = [&](int32_t b) -> int32_t {
+        k_seq_note<<<g, 256, 0, s>>>(cd->R, cd->rflags.p, b, out_batch_dev, cd->out_h1.p, cd->out_h2.p, cd->out_len.p,
+                                     cd->sq_h1.p, cd->sq_h2.p, cd->sq_len.p);
+        RAPID_KERNEL_CHECK();
+        return RAPID_OK;
+    };
+    auto finish = [&]() -> int32_t {
+        k_seq_finish<<<g, 256, 0, s>>>(cd->R, cd->rflags.p, out_batch_dev, cd->out_h1.p, cd->out_h2.p, cd->out_len.p,
+                                       cd->sq_h1.p, cd->sq_h2.p, cd->sq_len.p);
+        RAPID_KERNEL_CHECK();
+        RAPID_CUDA(cudaEventRecord(cd->ev_done, s));
+        return RAPID_OK;
+    };
+    auto one = [&](int32_t b) -> int32_t {                       // batch b on its own
+        DeliveryDev d = dl;
+        d.perm_seed = dl.perm_seed + (uint64_t)b;
+        if (d.bitmap) d.bitmap = dl.bitmap + (size_t)off[b] * (size_t)dl.words;
+        return bucketed_one(cd, cfg, off[b + 1] - off[b], dst_dev + off[b], ring_dev + off[b], status_dev + off[b],
+                            cfg_dev ? cfg_dev + off[b] : nullptr, d, false);
+    };
+    int32_t first = -1, last = -1;
+    for (int32_t b = 0; b < n_batches; ++b)
+        if (off[b + 1] > off[b]) { if (first < 0) first = b; last = b; }
+    if (last < 0) {                                              // no cells at all: handleMessage still runs invalidateFailingEdges
+        RAPID_CHECK(bucketed_one(cd, cfg, 0, dst_dev, ring_dev, status_dev, cfg_dev, dl, false));
+        RAPID_CHECK(note(0));
+        return finish();
+    }
+    int32_t first_rc = RAPID_OK;
+    std::string first_msg;
+    auto keep = [&](int32_t rc) { if (rc != RAPID_OK && first_rc == RAPID_OK) { first_rc = rc; char buf[512]; rapid_last_error(buf, sizeof(buf)); first_msg = buf; } };
+    if (first == last) {                                         // (batches without cells change nothing: the invalidation pass is idempotent)
+        const int32_t rc = one(last);
+        if (rc != RAPID_OK && rc != RAPID_EINVAL) return rc;
+        keep(rc);
+        RAPID_CHECK(note(last));
+        RAPID_CHECK(finish());
+        if (first_rc != RAPID_OK) { set_error("%s", first_msg.c_str()); return first_rc; }
+        return RAPID_OK;
+    }
+    const bool mergeable = !(dl.flags & RAPID_DELIVERY_BITMAP) && getenv("RAPID_B200_NO_SEQ_MERGE") == nullptr;
+    if (mergeable) {
+        DeliveryDev d = dl;
+        d.perm_seed = dl.perm_seed + (uint64_t)last;             // the moments that matter are those of the last batch
+        d.cell_base = off[last];
+        const int32_t rc = bucketed_one(cd, cfg, off[last + 1], dst_dev, ring_dev, status_dev, cfg_dev, d, false, batch_off_dev, n_batches, last);
+        if (rc != RAPID_OK && rc != RAPID_EINVAL) return rc;
+        if (!cd->last.seq_abort) {
+            keep(rc);
+            ++cd->seq_merged;
+            RAPID_CHECK(note(last));
+            RAPID_CHECK(finish());
+            if (first_rc != RAPID_OK) { set_error("%s", first_msg.c_str()); return first_rc; }
+            return RAPID_OK;
+        }
+        // refused for some receiver: nothing was committed — batch by batch (bad cells are reported by the replay)
+    }
+    ++cd->seq_replayed;
+    for (int32_t b = first; b <= last; ++b) {
+        if (off[b + 1] == off[b]) continue;
+        const int32_t rc = one(b);
+        if (rc != RAPID_OK && rc != RAPID_EINVAL) return rc;
+        keep(rc);
+        RAPID_CHECK(note(b));
+    }
+    RAPID_CHECK(finish());
+    if (first_rc != RAPID_OK) { set_error("%s", first_msg.c_str()); return first_rc; }
+    return RAPID_OK;
+}
+
 static int32_t apply_common(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev, const uint8_t* ring_dev,
                             const uint8_t* status_dev, const int64_t* cfg_dev, const DeliveryDev& dl,
                             const int64_t* batch_off_dev = nullptr, int32_t n_batches = 0, int32_t* out_batch_dev = nullptr,
-                            bool async = false) {
+                            bool async = false, const int64_t* batch_off_host = nullptr) {
     cd->cur_ring_dev = ring_dev;
     cd->cur_status_dev = status_dev;
     if (cd->bucketed) {
-        if (batch_off_dev) { set_error("a sequence of batches needs the per-cell order of a sweep handle (RAPID_CD_SWEEP)"); return RAPID_EUNSUPPORTED; }
-        // Three launches (prepare, apply, resolve) and the copy of the counter snapshot, no host round trip in between.  The
-        // synchronous entry points wait here and replay the batch if the handle had to grow; the asynchronous one returns.
-        for (int attempt = 0;; ++attempt) {
-            cd->last_launches = 0;
-            cd->last_A = A;
-            RAPID_CUDA(cudaEventRecord(cd->ev0, cd->stream));
-            RAPID_CHECK(ensure_id_capacity(cd));
-            RAPID_CHECK(cd->cell_slot.reserve(std::max<int64_t>(A, 1)));
-            PrepOut po;
-            RAPID_CHECK(bucketed_prep_buffers(cd, A, &po));
-            if (A > 0) RAPID_CHECK(prepare_batch(cd, cfg, A, dst_dev, ring_dev, status_dev, cfg_dev, &po));
-            else ++cd->batch_serial;
-            RAPID_CHECK(bucketed_apply(cd, A, dl));
-            RAPID_CUDA(cudaEventRecord(cd->ev1, cd->stream));
-            RAPID_CUDA(cudaEventRecord(cd->ev_done, cd->stream));
-            cd->pending = true;
-            if (async) return RAPID_OK;
-            RAPID_CUDA(cudaStreamSynchronize(cd->stream));
-            const int32_t carried_rc = cd->deferred_rc;            // errors of EARLIER asynchronous batches stay latched
-            const std::string carried_msg = cd->deferred_msg;
-            collect(cd);
-            if (cd->last.overflow && attempt < 4) {
-                // not an error here: grow the handle and replay (k_prepare rolled its slot assignment back, nothing was applied)
-                cd->deferred_rc = carried_rc; cd->deferred_msg = carried_msg;
-                RAPID_CHECK(ensure_slot_capacity(cd, (size_t)cd->last.need_slots));
-                ++cd->retries;
-                continue;
-            }
-            const int32_t rc = bad_cell_status(cd, cd->last);
-            if (rc != RAPID_OK) { cd->deferred_rc = carried_rc; cd->deferred_msg = carried_msg; return rc; }
-            return RAPID_OK;
-        }
+        if (batch_off_dev) return bucketed_sequence(cd, cfg, A, dst_dev, ring_dev, status_dev, cfg_dev, dl, batch_off_host, batch_off_dev, n_batches, out_batch_dev);
+        return bucketed_one(cd, cfg, A, dst_dev, ring_dev, status_dev, cfg_dev, dl, async);
     }
     cd->last_launches = 0;
     cd->last_A = A;
@@ -675,7 +802,6 @@ int32_t rapid_cd_apply_batches(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, co
     (void)src;
     if (!cd || n_cells < 0 || (n_cells && (!dst || !ring || !status)) || n_batches < 0 || n_batches > 0x7ffffff0LL || !batch_off) { set_error("bad arguments"); return RAPID_EINVAL; }
     if (cd->raw) { set_error("RAW handles take rapid_cd_aggregate / rapid_cd_invalidate"); return RAPID_EINVAL; }
-    if (cd->bucketed) { set_error("a sequence of batches needs the per-cell order of a sweep handle (RAPID_CD_SWEEP)"); return RAPID_EUNSUPPORTED; }
     if (batch_off[0] != 0 || batch_off[n_batches] != n_cells) { set_error("batch_off must run from 0 to n_cells"); return RAPID_EINVAL; }
     for (int64_t b = 0; b < n_batches; ++b)
         if (batch_off[b + 1] < batch_off[b]) { set_error("batch_off must be non-decreasing"); return RAPID_EINVAL; }
@@ -690,10 +816,54 @@ int32_t rapid_cd_apply_batches(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, co
     RAPID_CHECK(cd->batch_off.reserve((size_t)n_batches + 1));
     RAPID_CHECK(cd->out_batch.reserve((size_t)cd->Rpad));
     RAPID_CUDA(cudaMemcpyAsync(cd->batch_off.p, batch_off, (size_t)(n_batches + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, cd->stream));
-    RAPID_CHECK(apply_common(cd, cfg_id, n_cells, st.dst, st.ring, st.status, st.cfg, dl, cd->batch_off.p, (int32_t)n_batches, cd->out_batch.p));
+    if (!cd->bucketed && (dl.flags & RAPID_DELIVERY_PERMUTED)) { set_error("the sweep kernel applies cells in array order; RAPID_DELIVERY_PERMUTED needs a bucketed handle"); return RAPID_EUNSUPPORTED; }
+    const int32_t rc = apply_common(cd, cfg_id, n_cells, st.dst, st.ring, st.status, st.cfg, dl, cd->batch_off.p, (int32_t)n_batches, cd->out_batch.p, false, batch_off);
+    if (rc != RAPID_OK && rc != RAPID_EINVAL) return rc;         // RAPID_EINVAL: bad cells were dropped, the rest was applied
+    char msg[512];
+    if (rc != RAPID_OK) rapid_last_error(msg, sizeof(msg));
+    RAPID_CHECK(cd_wait(cd, false));
     if (announced_in) RAPID_CUDA(cudaMemcpy(announced_in, cd->out_batch.p, (size_t)cd->R * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (proposal_hash || proposal_hash2 || proposal_len || announced)
-        return rapid_cd_read_outputs(cd, proposal_hash, proposal_hash2, proposal_len, announced);
+        RAPID_CHECK(rapid_cd_read_outputs(cd, proposal_hash, proposal_hash2, proposal_len, announced));
+    if (rc != RAPID_OK) set_error("%s", msg);
+    return rc;
+}
+
+// The same with the cell arrays already in device memory (batch_off stays a HOST array: the host walks the batches when the
+// one-pass treatment is refused).  Outputs: rapid_cd_read_outputs / rapid_cd_read_announced_in, or straight into rapid_fp_tally_cd.
+int32_t rapid_cd_apply_batches_dev(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src_dev, const int32_t* dst_dev,
+                                   const uint8_t* ring_dev, const uint8_t* status_dev, const int64_t* cell_cfg_dev, int64_t n_batches,
+                                   const int64_t* batch_off, const rapid_delivery* delivery_dev) {
+    (void)src_dev;
+    if (!cd || n_cells < 0 || (n_cells && (!dst_dev || !ring_dev || !status_dev)) || n_batches < 0 || n_batches > 0x7ffffff0LL || !batch_off) { set_error("bad arguments"); return RAPID_EINVAL; }
+    if (cd->raw) { set_error("RAW handles take rapid_cd_aggregate / rapid_cd_invalidate"); return RAPID_EINVAL; }
+    if (batch_off[0] != 0 || batch_off[n_batches] != n_cells) { set_error("batch_off must run from 0 to n_cells"); return RAPID_EINVAL; }
+    for (int64_t b = 0; b < n_batches; ++b)
+        if (batch_off[b + 1] < batch_off[b]) { set_error("batch_off must be non-decreasing"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    DeliveryDev dl;
+    RAPID_CHECK(upload_delivery(cd, n_cells, delivery_dev, true, &dl));
+    if (!cd->bucketed && (dl.flags & RAPID_DELIVERY_PERMUTED)) { set_error("the sweep kernel applies cells in array order; RAPID_DELIVERY_PERMUTED needs a bucketed handle"); return RAPID_EUNSUPPORTED; }
+    RAPID_CHECK(cd->batch_off.reserve((size_t)n_batches + 1));
+    RAPID_CHECK(cd->out_batch.reserve((size_t)cd->Rpad));
+    RAPID_CUDA(cudaMemcpyAsync(cd->batch_off.p, batch_off, (size_t)(n_batches + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, cd->stream));
+    return apply_common(cd, cfg_id, n_cells, dst_dev, ring_dev, status_dev, cell_cfg_dev, dl, cd->batch_off.p, (int32_t)n_batches, cd->out_batch.p, false, batch_off);
+}
+
+int32_t rapid_cd_read_announced_in(const rapid_cd* cd, int32_t* announced_in) {
+    if (!cd || !announced_in) { set_error("NULL argument"); return RAPID_EINVAL; }
+    if (!cd->out_batch.p) { set_error("no rapid_cd_apply_batches call yet"); return RAPID_EINVAL; }
+    DeviceGuard g(cd->device);
+    RAPID_CHECK(cd_wait(cd, false));
+    RAPID_CUDA(cudaMemcpy(announced_in, cd->out_batch.p, (size_t)cd->R * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return RAPID_OK;
+}
+
+// diagnostics: sequences served in one pass / replayed batch by batch since the handle was created
+int32_t rapid_cd_sequence_stats(const rapid_cd* cd, int32_t* one_pass, int32_t* replayed) {
+    if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
+    if (one_pass) *one_pass = cd->seq_merged;
+    if (replayed) *replayed = cd->seq_replayed;
     return RAPID_OK;
 }
 

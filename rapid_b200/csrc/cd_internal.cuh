@@ -35,7 +35,8 @@ struct BatchCounts {
     int32_t bad_dst;       // index of a cell with dst outside [0, n + joiners), or -1 (dropped likewise)
     int32_t n_mixed;       // bucketed: receivers needing exact interval resolution
     int32_t n_inval;       // bucketed: receivers that announce only the explicit part (bit-15 marks needed)
-    int32_t S_before;      // n_slots when the batch started: slots >= S_before are "fresh" (known-zero state, never read)
+    int32_t S_before;      // n_slots when the batch started: slots >= S_before are "fresh" (known-zero state, never read);
+                           // between batches S_before == n_slots (the prepare kernel takes the slot count from here)
     int32_t overflow;      // the batch needs more subject slots than the handle holds: NOTHING was applied
     int32_t need_slots;    // ... and this many would do
     int32_t n_times;       // PERMUTED delivery: receivers whose classification needed their own crossing moments
@@ -44,7 +45,11 @@ struct BatchCounts {
     int32_t ticket;        // "last block done" counter of the resolve kernel
     int32_t serial;        // serial of the batch this record describes
     int32_t sticky_bad_ring, sticky_bad_dst, sticky_overflow;   // latched until the host collects them (asynchronous batches)
-    int32_t pad_;
+    // ---- a sequence of batches applied in one pass (see cd_bucketed.cu "sequences")
+    int32_t seq_last;      // index of the last non-empty batch of the call in flight (0 for a single batch)
+    int32_t seq_down;      // 1-based index of the first batch with a valid DOWN cell, INT_MAX if none
+    int32_t seq_abort;     // receivers for which the one-pass treatment is not provably exact: NOTHING was committed
+    int32_t pad_[2];
 };
 
 struct CD {
@@ -80,6 +85,9 @@ struct CD {
     DevBuf<uint64_t> out_h1, out_h2;  // [R] outputs of the last batch
     DevBuf<int64_t> batch_off;        // rapid_cd_apply_batches: batch boundaries
     DevBuf<int32_t> out_batch;        // [R] ... and the batch in which each receiver announced
+    DevBuf<uint64_t> sq_h1, sq_h2;    // [R] outputs of the announcing batch while a sequence is replayed batch by batch
+    DevBuf<int32_t> sq_len;
+    int32_t seq_merged = 0, seq_replayed = 0;   // sequences served in one pass / replayed batch by batch (diagnostics)
     DevBuf<int32_t> out_len;          // [R]
     DevBuf<uint8_t> out_ann;          // [R]
 
@@ -105,6 +113,7 @@ struct CD {
     BatchCounts last;                 // counters of the last collected batch
     int32_t retries = 0;              // batches replayed after growing the subject capacity
     DevBuf<uint8_t> cub_tmp;
+    DevBuf<unsigned long long> prep_stamps;   // RAPID_B200_PREP_STAMPS profiling aid
     // bucketed scratch lives in cd_bucketed.cu's own struct hung off here
     void* bucketed_state = nullptr;
 
@@ -133,22 +142,30 @@ struct DeliveryDev {
     const uint32_t* bitmap = nullptr;
     int64_t words = 0;
     uint64_t perm_seed = 0;
+    int64_t cell_base = 0;            // PERMUTED: a receiver's order key of cell i is a function of i - cell_base (the index inside its batch)
 };
 
 // ---- the batch regrouped by subject (built by cd_prepare.cu, consumed by cd_bucketed.cu) -------------------------
-struct SubjDesc {                     // 48 bytes, one per subject of the batch
+struct SubjDesc {                     // 64 bytes, one per subject of the batch
     int32_t slot;
-    uint16_t bmask;                   // rings reported in this batch
-    uint8_t nr;                       // number of distinct rings
+    uint16_t bmask;                   // rings reported in this batch (of a sequence of batches: in its LAST batch)
+    uint8_t nr;                       // number of distinct rings in bmask
     uint8_t any_down;
-    uint32_t tLf, tHf;                // for a fresh subject (no earlier reports): moment of the L-th / H-th distinct ring, 0 if none
-    uint32_t seg_begin, seg_len;      // its cells in the slot-sorted arrays
+    uint32_t tLf, tHf;                // for a fresh subject (state == pmask): moment of the cell that makes the L-th / H-th distinct ring, 0 if none
+    uint32_t seg_begin, seg_len;      // its cells (of the last batch) in the slot-sorted arrays
     uint64_t mix1, mix2;              // fp_mix1 / fp_mix2 of the subject id
-    uint64_t pad_;
+    // ---- a sequence of batches in one call (rapid_cd_apply_batches on bucketed handles): everything before the last batch
+    uint16_t pmask;                   // rings reported in the PREFIX (batches before the last one); 0 for a single batch
+    uint8_t pdown;                    // a DOWN cell in the prefix
+    uint8_t pad0_;
+    uint32_t f_bLp, f_bHp;            // fresh subject: 1-based prefix batch in which it reaches L / H distinct rings, 0 if it does not
+    uint32_t pseg_len;                // prefix cells: they sit right before seg_begin in the sorted arrays
+    uint64_t pad1_;
 };
+static_assert(sizeof(SubjDesc) == 64, "SubjDesc is staged in shared memory as 64-byte records");
 struct SubjWalk {                     // first-occurrence ring sequence in arrival order (uniform delivery)
     uint8_t ring[16];
-    uint32_t time[16];
+    uint32_t time[16];                // 1-based cell index; in a PREFIX walk (PrepOut::pwalk): 1-based batch index
 };
 
 // Invalidation work list of a bucketed handle: the subjects that sit in the unstable band of SOME receiver and have an observer
@@ -179,18 +196,25 @@ struct PrepOut {                      // where the prepare kernel writes the reg
     uint8_t* s_ring;
     uint8_t* s_status;
     int32_t* batch_index;             // [slot] -> index of the subject in the batch
-    int32_t* seg_cnt;                 // [slot] scratch, all zero between batches
-    int32_t* seg_pos;                 // [slot] scratch
+    int32_t* seg_cnt;                 // [slot] cells of the subject in this batch (scratch, all zero between batches)
+    int32_t* batch_slots;             // [batch index] -> slot
+    int32_t* bins;                    // [slot][16] indices of the subject's first 16 cells of this batch (any order)
+    int32_t* ovf;                     // [A] cells beyond a subject's bin
+    SubjWalk* pwalk;                  // sequences of batches: first-occurrence ring sequence of the prefix, time = batch index + 1
     WorkList wl;                      // invalidation work list (bucketed handles; wl.has_so == nullptr otherwise)
 };
 
 // implemented in cd_prepare.cu: filter + slot dictionary (+ regrouping by subject when po != nullptr) in ONE cooperative launch
+// batch_off_dev != nullptr: the cells are a SEQUENCE of n_batches batches (cells [batch_off[b], batch_off[b+1]) = batch b) whose
+// last non-empty one is `seq_last`; the descriptors then split every subject's cells into prefix and last batch.
 int32_t prepare_batch(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev, const uint8_t* ring_dev, const uint8_t* status_dev,
-                      const int64_t* cfg_dev, const PrepOut* po);
+                      const int64_t* cfg_dev, const PrepOut* po, const int64_t* batch_off_dev = nullptr, int32_t n_batches = 1,
+                      int32_t seq_last = 0);
 // implemented in cd_bucketed.cu
 int32_t bucketed_prep_buffers(CD* cd, int64_t A, PrepOut* po);
 
-int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl);     // enqueue only: no host synchronisation
+// enqueue only: no host synchronisation.  seq: the cells are a sequence of batches prepared with batch offsets (one pass, checked)
+int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, bool seq = false);
 void bucketed_destroy(CD* cd);
 int32_t bucketed_clear(CD* cd);
 int32_t bucketed_clear_sticky(CD* cd);

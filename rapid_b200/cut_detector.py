@@ -183,9 +183,11 @@ class VirtualCluster:
         """wait for asynchronous batches; raises if one of them failed"""
         N.check(N.lib().rapid_cd_sync(self._h))
 
-    def handleBatches(self, cfg_id, src, dst, ring, status, batch_off, cell_cfg=None, blocked=None, bitmap=None):
+    def handleBatches(self, cfg_id, src, dst, ring, status, batch_off, cell_cfg=None, blocked=None, bitmap=None, perm_seed=None,
+                      read_outputs=True):
         """A sequence of BatchedAlertMessages (batch b = cells batch_off[b]:batch_off[b+1]) delivered in order, with the
-        announcedProposal gating between them (MembershipService.java:318-319).  Sweep handles only.
+        announcedProposal gating between them (MembershipService.java:318-319).  perm_seed: batch b reaches every receiver in
+        its own order, seeded perm_seed + b (bucketed handles).
         -> (AlertBatchResult, announced_in): announced_in[r] = index of the batch in which receiver r announced, -1 if none."""
         dst = N.as_i32(dst)
         A = len(dst)
@@ -193,13 +195,45 @@ class VirtualCluster:
         ring, status = N.as_u8(ring), N.as_u8(status)
         off = N.as_i64(batch_off)
         cc = None if cell_cfg is None else N.as_i64(cell_cfg)
-        d = self._delivery(blocked, bitmap, None)
+        d = self._delivery(blocked, bitmap, perm_seed)
+        if not read_outputs:
+            N.check(N.lib().rapid_cd_apply_batches(self._h, int(cfg_id), A, N.ptr(src), N.ptr(dst), N.ptr(ring), N.ptr(status), N.ptr(cc),
+                                                   len(off) - 1, N.ptr(off), C.byref(d) if d is not None else None, None, None, None,
+                                                   None, None))
+            return None, None
         h1, h2 = np.zeros(self.R, np.uint64), np.zeros(self.R, np.uint64)
         ln, ann, ain = np.zeros(self.R, np.int32), np.zeros(self.R, np.uint8), np.zeros(self.R, np.int32)
         N.check(N.lib().rapid_cd_apply_batches(self._h, int(cfg_id), A, N.ptr(src), N.ptr(dst), N.ptr(ring), N.ptr(status), N.ptr(cc),
                                                len(off) - 1, N.ptr(off), C.byref(d) if d is not None else None, N.ptr(h1), N.ptr(h2),
                                                N.ptr(ln), N.ptr(ann), N.ptr(ain)))
         return AlertBatchResult(h1, h2, ln, ann), ain
+
+    def handleBatchesDevice(self, cfg_id, n_cells, dst_dev, ring_dev, status_dev, batch_off, cell_cfg_dev=0, blocked_dev=0, perm_seed=None):
+        """handleBatches with the cell arrays resident in device memory (raw device pointers; batch_off on the host)."""
+        d = None
+        if blocked_dev or perm_seed is not None:
+            d = N.Delivery()
+            d.flags = 0
+            if blocked_dev:
+                d.flags |= N.DELIVERY_BLOCKED
+                d.blocked = blocked_dev
+            if perm_seed is not None:
+                d.flags |= N.DELIVERY_PERMUTED
+                d.perm_seed = perm_seed & 0xFFFFFFFFFFFFFFFF
+        off = N.as_i64(batch_off)
+        N.check(N.lib().rapid_cd_apply_batches_dev(self._h, int(cfg_id), int(n_cells), None, dst_dev, ring_dev, status_dev,
+                                                   cell_cfg_dev or None, len(off) - 1, N.ptr(off), C.byref(d) if d is not None else None))
+
+    def readAnnouncedIn(self):
+        out = np.zeros(self.R, np.int32)
+        N.check(N.lib().rapid_cd_read_announced_in(self._h, N.ptr(out)))
+        return out
+
+    def sequenceStats(self):
+        """(sequences served in one pass, sequences replayed batch by batch)"""
+        a, b = C.c_int32(0), C.c_int32(0)
+        N.check(N.lib().rapid_cd_sequence_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def readOutputs(self):
         h1 = np.zeros(self.R, np.uint64)

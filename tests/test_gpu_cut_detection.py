@@ -541,36 +541,53 @@ def _per_sender(src, dst, ring, status):
     return src[idx], dst[idx], ring[idx], status[idx], off
 
 
+def _oracle_sequence(sim, cfg, src, dst, ring, status, off, n, blocked=None, perm_seed=None):
+    """the oracle handling the batches one by one -> (announced_in, length, ids per announcer, announced flags)"""
+    want_len, want_in, want_ids, o_ann = np.zeros(n, np.int32), np.full(n, -1, np.int32), {}, None
+    for b in range(len(off) - 1):
+        sl = slice(int(off[b]), int(off[b + 1]))
+        o_len, o_ann, o_ids, o_off = sim.apply_batch(src[sl], dst[sl], ring[sl], status[sl], np.full(sl.stop - sl.start, cfg, np.int64),
+                                                     blocked=blocked, perm_seed=None if perm_seed is None else perm_seed + b, threads=2)
+        for r in np.nonzero(o_len)[0]:
+            assert want_in[r] == -1                                   # a receiver announces once per configuration
+            want_in[r], want_len[r] = b, o_len[r]
+            want_ids[int(r)] = o_ids[o_off[r]: o_off[r + 1]].tolist()
+    return want_in, want_len, want_ids, o_ann
+
+
+def _check_sequence(rb, cl, sim, res, ain, want_in, want_len, want_ids, o_ann, check_masks=True):
+    np.testing.assert_array_equal(ain, want_in)
+    np.testing.assert_array_equal(res.proposal_len, want_len)
+    np.testing.assert_array_equal(res.announced, o_ann)
+    for r, ids in want_ids.items():
+        assert rb.proposal_fingerprint(ids) == (int(res.proposal_hash[r]), int(res.proposal_hash2[r])), "receiver %d" % r
+    for r, ids in list(want_ids.items())[:6]:
+        assert cl.getProposal(r) == ids
+    if check_masks:
+        live = np.nonzero(o_ann == 0)[0]
+        for r in live[:: max(1, len(live) // 8)][:8]:
+            for subj, m in cl.debugMasks(int(r)).items():
+                assert sim.reportMask(int(r), int(subj)) == m, "mask of subject %d at receiver %d" % (subj, r)
+            assert cl.debugCounters(int(r))[0] == sim.updatesInProgress(int(r))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("seed", range(8))
-def test_sequence_of_per_sender_batches_matches_sequential_handling(orc, rb, seed):
+def test_sequence_of_per_sender_batches_matches_sequential_handling(orc, rb, seed, kernel):
     """the reference's AlertBatcher sends one BatchedAlertMessage per observer; a receiver handles them one by one and stops
     at the first that yields a proposal.  One rapid_cd_apply_batches call == the oracle handling the batches one by one."""
     rng = np.random.default_rng(12000 + seed)
     n, nj = int(rng.integers(30, 400)), int(rng.integers(0, 5))
     Hh, Ll = (9, 4) if seed % 2 else (8, 3)
-    w, v, sim, cl = _worlds(orc, rb, n, n_joiners=nj, Hh=Hh, Ll=Ll, kernel="sweep")
+    w, v, sim, cl = _worlds(orc, rb, n, n_joiners=nj, Hh=Hh, Ll=Ll, kernel=kernel)
     cfg = w.view.getCurrentConfigurationId()
     for call in range(3):
         src, dst, ring, status = random_batch(rng, n + nj, K, int(rng.integers(1, 6)), int(rng.integers(5, 120)), n)
         src, dst, ring, status, off = _per_sender(src, dst, ring, status)
         blocked = (rng.random(n) < 0.1).astype(np.uint8) if call == 1 else None
-        want_len, want_in = np.zeros(n, np.int32), np.full(n, -1, np.int32)
-        want_ids = {}
-        for b in range(len(off) - 1):
-            sl = slice(int(off[b]), int(off[b + 1]))
-            o_len, o_ann, o_ids, o_off = sim.apply_batch(src[sl], dst[sl], ring[sl], status[sl], np.full(sl.stop - sl.start, cfg, np.int64),
-                                                         blocked=blocked, threads=2)
-            for r in np.nonzero(o_len)[0]:
-                assert want_in[r] == -1                                   # a receiver announces once per configuration
-                want_in[r], want_len[r] = b, o_len[r]
-                want_ids[int(r)] = o_ids[o_off[r]: o_off[r + 1]].tolist()
+        want = _oracle_sequence(sim, cfg, src, dst, ring, status, off, n, blocked=blocked)
         res, ain = cl.handleBatches(cfg, src, dst, ring, status, off, blocked=blocked)
-        np.testing.assert_array_equal(ain, want_in)
-        np.testing.assert_array_equal(res.proposal_len, want_len)
-        np.testing.assert_array_equal(res.announced, o_ann)
-        for r, ids in list(want_ids.items())[:6]:
-            assert rb.proposal_fingerprint(ids) == (int(res.proposal_hash[r]), int(res.proposal_hash2[r]))
-            assert cl.getProposal(r) == ids
+        _check_sequence(rb, cl, sim, res, ain, *want)
 
 
 def test_per_sender_batches_can_differ_from_one_merged_batch(orc, rb):
@@ -586,6 +603,72 @@ def test_per_sender_batches_can_differ_from_one_merged_batch(orc, rb):
     assert set(res.proposal_len.tolist()) == {1} and set(ain.tolist()) == {8}        # the 9th report (H = 9) of node 5, alone
     merged = rb.VirtualCluster(v, 9, 4, kernel="sweep").handleBatch(cfg, src, dst, ring, status)
     assert set(merged.proposal_len.tolist()) == {2}
+    # the subject-bucketed kernels: the one-pass treatment must be REFUSED here (node 5's cut is emitted before the last batch) and
+    # the batch-by-batch replay gives the sequential answer
     bk = rb.VirtualCluster(v, 9, 4, kernel="bucketed")
-    with pytest.raises(rb.RapidError):
-        bk.handleBatches(cfg, src, dst, ring, status, off)
+    res2, ain2 = bk.handleBatches(cfg, src, dst, ring, status, off)
+    assert set(res2.proposal_len.tolist()) == {1} and set(ain2.tolist()) == {8}
+    assert bk.sequenceStats() == (0, 1)
+
+
+@pytest.mark.parametrize("mode", ["uniform", "permuted"])
+@pytest.mark.parametrize("seed", range(10))
+def test_sequences_on_the_bucketed_path_fuzz(orc, rb, seed, mode):
+    """rapid_cd_apply_batches on bucketed handles: random streams cut into random batches (a few long ones, many tiny ones,
+    empty ones), uniform or per-receiver permuted delivery, blocked receivers, state carried from call to call — against the
+    oracle handling every batch on its own.  Both outcomes of the one-pass attempt occur (served in one pass / refused and
+    replayed) and must be indistinguishable."""
+    rng = np.random.default_rng(77000 + seed)
+    n, nj = int(rng.integers(60, 1500)), int(rng.integers(0, 6))
+    Hh, Ll = (9, 4) if seed % 3 else (8, 2)
+    w, v, sim, cl = _worlds(orc, rb, n, n_joiners=nj, Hh=Hh, Ll=Ll, kernel="bucketed")
+    cfg = w.view.getCurrentConfigurationId()
+    obs = w.tables()[0]
+    for call in range(4):
+        if call % 2 == 0:
+            # crash-shaped: every observer of a few subjects reports, spread over the batches (long unstable intervals: the
+            # one-pass premises usually hold)
+            subj = rng.choice(n, size=int(rng.integers(2, 12)), replace=False)
+            cells = [(int(obs[s][r]), int(s), r, 1) for s in subj for r in range(K) if rng.random() < 0.95]
+            order = rng.permutation(len(cells))
+            src, dst, ring, status = (np.array(x) for x in zip(*[cells[i] for i in order]))
+            src, dst = src.astype(np.int32), dst.astype(np.int32)
+            ring, status = ring.astype(np.uint8), status.astype(np.uint8)
+        else:
+            src, dst, ring, status = random_batch(rng, n + nj, K, int(rng.integers(1, 8)), int(rng.integers(5, 150)), n)
+        A = len(dst)
+        nb = int(rng.integers(2, 12))
+        cuts = np.sort(rng.integers(0, A + 1, size=nb - 1))
+        off = np.concatenate([[0], cuts, [A]]).astype(np.int64)        # empty batches happen
+        blocked = (rng.random(n) < 0.1).astype(np.uint8) if call % 3 == 1 else None
+        perm = int(rng.integers(1, 2**60)) if mode == "permuted" else None
+        want = _oracle_sequence(sim, cfg, src, dst, ring, status, off, n, blocked=blocked, perm_seed=perm)
+        res, ain = cl.handleBatches(cfg, src, dst, ring, status, off, blocked=blocked, perm_seed=perm)
+        _check_sequence(rb, cl, sim, res, ain, *want)
+    one_pass, replayed = cl.sequenceStats()
+    assert one_pass + replayed >= 1
+
+
+def test_sequence_stream_c4_in_one_pass(orc, rb):
+    """BASELINE config 4's shape (flip-flop stream, 8 batches, duplicates, per-receiver permuted order) as ONE sequence call: served
+    in one pass over the state, same announcements as eight separate batches."""
+    n = 3000
+    w, v, sim, cl = _worlds(orc, rb, n, kernel="bucketed")
+    cfg = w.view.getCurrentConfigurationId()
+    obs = w.tables()[0]
+    batches = W.c4_flip_flop_stream(obs, n, 0.01, T=8)
+    blocked = W.blocked_by_receiver(batches[0].blocked, v.getRing(0), 0, n)
+    src = np.concatenate([b.src for b in batches]); dst = np.concatenate([b.dst for b in batches])
+    ring = np.concatenate([b.ring for b in batches]); status = np.concatenate([b.status for b in batches])
+    off = np.concatenate([[0], np.cumsum([len(b) for b in batches])]).astype(np.int64)
+    perm = batches[0].meta["perm_seed"]
+    assert [b.meta["perm_seed"] for b in batches] == [perm + t for t in range(8)]
+    want = _oracle_sequence(sim, cfg, src, dst, ring, status, off, n, blocked=blocked, perm_seed=perm)
+    res, ain = cl.handleBatches(cfg, src, dst, ring, status, off, blocked=blocked, perm_seed=perm)
+    _check_sequence(rb, cl, sim, res, ain, *want)
+    live = blocked == 0
+    assert (ain[live] == 7).all() and (res.proposal_len[live] == len(batches[-1].expected_cut)).all()
+    assert cl.sequenceStats() == (1, 0)
+    fp = rb.FastPaxos(cfg, n)
+    t = fp.tallyCluster(cl)
+    assert t.decided and t.length == len(batches[-1].expected_cut) and t.count == rb.quorum(n)
