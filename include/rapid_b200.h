@@ -186,8 +186,10 @@ int32_t rapid_cd_apply_batches_dev(rapid_cd* cd, int64_t cfg_id, int64_t n_cells
                                    const uint8_t* ring_dev, const uint8_t* status_dev, const int64_t* cell_cfg_dev,
                                    int64_t n_batches, const int64_t* batch_off, const rapid_delivery* delivery_dev);
 int32_t rapid_cd_read_announced_in(const rapid_cd* cd, int32_t* announced_in /* [R] */);
-/* How many sequences this handle served in one pass / had to replay batch by batch (diagnostics). */
-int32_t rapid_cd_sequence_stats(const rapid_cd* cd, int32_t* one_pass, int32_t* replayed);
+/* How many sequences this handle served in one pass / had to replay batch by batch, and — for the last refused attempt — how many
+ * receivers failed either premise (a proposal could have been emitted before the last batch / an implicit report would have been
+ * added at the end of an earlier batch).  Diagnostics; any pointer may be NULL. */
+int32_t rapid_cd_sequence_stats(const rapid_cd* cd, int32_t* one_pass, int32_t* replayed, int32_t* refused_a1, int32_t* refused_a2);
 /* Same as rapid_cd_apply_batch, with the cell arrays (and delivery arrays) already resident in device memory and no per-receiver
  * readback: results stay on the device for rapid_fp_tally_cd / rapid_cd_read_outputs. */
 int32_t rapid_cd_apply_batch_dev(rapid_cd* cd, int64_t cfg_id, int64_t n_cells, const int32_t* src_dev,

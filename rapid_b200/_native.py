@@ -81,7 +81,7 @@ SIGNATURES = {
     "rapid_cd_apply_batches": [_vp, _i64, _i64, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p],
     "rapid_cd_apply_batches_dev": [_vp, _i64, _i64, _p, _p, _p, _p, _p, _i64, _p, _p],
     "rapid_cd_read_announced_in": [_vp, _p],
-    "rapid_cd_sequence_stats": [_vp, _p, _p],
+    "rapid_cd_sequence_stats": [_vp, _p, _p, _p, _p],
     "rapid_cd_read_outputs": [_vp, _p, _p, _p, _p],
     "rapid_cd_get_proposal": [_vp, _i64, _p, _i32, _p],
     "rapid_cd_num_proposals": [_vp, _i64, _p],

@@ -204,27 +204,71 @@ __device__ __forceinline__ bool accumulate(Acc& a, const Visit& v, const SubjDes
 //       after s reached H or ring k was reported anyway — or is not in the prefix
 // A receiver that fails either test aborts the pass for EVERYONE before anything is committed (rows are double-buffered, the
 // scalars are written by the finalize kernels): the host then replays the sequence batch by batch.
-__device__ __forceinline__ uint32_t visit_prefix(Acc& a, uint32_t ur, const SubjDesc& d, const SubjWalk& pw, int L, int H) {
+// One (subject, receiver) through the prefix.  `u[k]` (for the rings in `umask`) is the first prefix batch END (1-based) at which the
+// subject's ring-k observer is in proposal U preProposal and a DOWN alert has been seen — from then on an invalidation pass reports
+// ring k implicitly while the subject sits in the unstable band (MultiNodeCutDetector.java:147-158).  The walk merges the explicit
+// first reports (during batch t) with those passes (at the END of batch e; a pass applies ALL its eligible rings, :151-157, even
+// past H) in batch order.  Returns the state when the last batch starts; acc (may be null) receives the prefix's crossings.
+__device__ __forceinline__ uint32_t prefix_core(Acc* acc, uint32_t ur, const SubjDesc& d, const SubjWalk& pw, const uint32_t* u,
+                                                uint32_t umask, int L, int H, uint32_t last) {
     const int c0 = __popc(ur);
     int c = c0;
-    uint32_t bLp = 0, bHp = 0;
-    if (ur == 0) {                                       // fresh subject: the descriptor knows
-        c = __popc(d.pmask); bLp = d.f_bLp; bHp = d.f_bHp;
+    uint32_t word = ur, bLp = 0, bHp = 0;
+    if (ur == 0 && umask == 0) {                         // fresh subject without dictionary observers: the descriptor knows
+        c = __popc(d.pmask); bLp = d.f_bLp; bHp = d.f_bHp; word = d.pmask;
     } else {
         const int np = __popc(d.pmask);
-        for (int q = 0; q < np; ++q) {
-            const int k = pw.ring[q];
-            const bool isnew = !((ur >> k) & 1u);
-            c += isnew;
-            if (isnew && c == L) bLp = pw.time[q];
-            if (isnew && c == H) bHp = pw.time[q];
+        uint32_t imp = umask & ~ur;                      // implicit candidates still open
+        uint32_t bL = c >= L ? 0u : T32_NONE;
+        int q = 0;
+        for (;;) {
+            while (q < np && ((word >> pw.ring[q]) & 1u)) ++q;                     // explicit entries already reported
+            const uint32_t te = q < np ? pw.time[q] : T32_NONE;
+            uint32_t ti = T32_NONE;
+            if (imp && c >= L && c < H) {
+                for (uint32_t m = imp; m; m &= m - 1) { const int k = __ffs(m) - 1; if (u[k] != T32_NONE) ti = min(ti, max(u[k], bL)); }
+                if (ti > last) ti = T32_NONE;
+            }
+            if (ti != T32_NONE && ti < te) {             // the invalidation pass at the end of batch ti comes first
+                for (uint32_t m = imp; m; m &= m - 1) {
+                    const int k = __ffs(m) - 1;
+                    if (u[k] == T32_NONE || u[k] > ti) continue;
+                    word |= 1u << k; imp &= ~(1u << k);
+                    ++c;
+                    if (c == H) bHp = ti;
+                }
+                if (c >= H) imp = 0;                     // out of preProposal: no later pass touches it
+            } else if (te != T32_NONE) {
+                const int k = pw.ring[q];
+                word |= 1u << k; imp &= ~(1u << k);
+                ++c; ++q;
+                if (c == L) { bL = te; bLp = te; }
+                if (c == H) bHp = te;
+            } else {
+                break;
+            }
         }
     }
-    if (c0 >= L && c0 < H) a.tpc++;                      // in the band before the call, touched by the call
-    if (c0 < L && c >= L) a.nLp++;
-    if (c0 < H && c >= H) { a.nHp++; a.h1p += d.mix1; a.h2p += d.mix2; a.minBHp = min(a.minBHp, bHp); }
-    if (c >= L && c < H) a.minBLlong = min(a.minBLlong, c0 >= L ? 0u : bLp);   // in the band when the last batch starts
-    return ur | d.pmask;
+    if (acc) {
+        if (c0 >= L && c0 < H) acc->tpc++;               // in the band before the call, touched by the call
+        if (c0 < L && c >= L) acc->nLp++;
+        if (c0 < H && c >= H) { acc->nHp++; acc->h1p += d.mix1; acc->h2p += d.mix2; acc->minBHp = min(acc->minBHp, bHp); }
+        if (c >= L && c < H) acc->minBLlong = min(acc->minBLlong, c0 >= L ? 0u : bLp);   // in the band when the last batch starts
+    }
+    return word;
+}
+
+// first prefix batch (1-based) in which an observer with stored word `uo` has >= L reports: 0 = it already has, T32_NONE = not in the prefix
+__device__ __forceinline__ uint32_t observer_L_batch(uint32_t uo, const SubjDesc* dobs, const SubjWalk* pwo, int L) {
+    int c = __popc(uo);
+    if (c >= L) return 0u;
+    if (dobs == nullptr || dobs->pmask == 0) return T32_NONE;
+    const int np = __popc(dobs->pmask);
+    for (int q = 0; q < np; ++q) {
+        if ((uo >> pwo->ring[q]) & 1u) continue;
+        if (++c == L) return pwo->time[q];
+    }
+    return T32_NONE;
 }
 
 struct ApplyArgs {
@@ -241,6 +285,10 @@ struct ApplyArgs {
     const SubjDesc* desc;
     const SubjWalk* walk;
     const SubjWalk* pwalk;        // sequences of batches: prefix walks
+    const int32_t* touch;         // [slot] serial of the last batch with a valid cell for the slot
+    const int32_t* batch_index;   // [slot] -> index in the batch in flight (valid if touch[slot] == serial)
+    int32_t serial;
+    int seq;                      // a sequence of batches in one pass (SEQ kernels)
     const int32_t* slot_subject;
     const int32_t* sidx;          // sorted cell indices
     const uint8_t* s_ring;
@@ -295,11 +343,55 @@ struct StageAcc {
     uint64_t h1p, h2p;
 };
 
+// One (subject, receiver) visit: [the prefix of a sequence,] then the (last) batch.  *word_out = the state when the last batch starts.
 template <bool PERM, bool SEQ>
-__device__ __forceinline__ bool visit_acc(Acc& acc, uint32_t ur, const SubjDesc& d, const SubjWalk* w, const SubjWalk* pw, uint32_t RM, int L, int H) {
-    if (SEQ) ur = visit_prefix(acc, ur, d, *pw, L, H);
+__device__ __forceinline__ bool visit_acc(Acc& acc, uint32_t ur, const SubjDesc& d, const SubjWalk* w, const SubjWalk* pw, uint32_t RM, int L, int H,
+                                          const uint32_t* u = nullptr, uint32_t umask = 0, uint32_t last = 0, uint32_t* word_out = nullptr) {
+    if (SEQ) ur = prefix_core(&acc, ur, d, *pw, u, umask, L, H, last);
+    if (word_out) *word_out = ur;
     const Visit v = PERM ? visit_counts(ur & RM, d, RM, L, H) : visit_uniform(ur & RM, d, *w, L, H);
     return accumulate(acc, v, d, L, H);
+}
+
+// ---- dictionary observers of a subject ("edges"): when do they make the invalidation pass report a ring? ---------------------------
+// RF_PRE_DOWN: finalize1 keeps the receiver's seenLinkDownEvents of BEFORE the call there (the passes after it recompute visits)
+constexpr uint32_t RF_PRE_DOWN = 128u;
+__device__ __forceinline__ uint32_t receiver_down_batch(const ApplyArgs& a, uint32_t rflag, bool after_finalize1) {
+    if (rflag & (after_finalize1 ? RF_PRE_DOWN : RF_SEEN_DOWN)) return 0u;
+    const int32_t sd = a.bc->seq_down;
+    return sd == INT_MAX ? T32_NONE : (uint32_t)sd;
+}
+// pre-call row of a slot: before the flip it is the current one; after the flip the other one — for the slots the call touched
+__device__ __forceinline__ const uint16_t* precall_row(const ApplyArgs& a, int32_t slot, bool post_flip) {
+    const int flipped = post_flip && a.touch[slot] == a.serial ? 1 : 0;
+    return a.masks + ((size_t)slot * 2 + (a.cur[slot] ^ flipped)) * a.Rpad;
+}
+// generic (one receiver, scalar loads): u[k] for every ring of `slot` whose observer is a subject itself; returns the ring mask
+__device__ __noinline__ uint32_t edge_times(const ApplyArgs& a, int32_t slot, int64_t r, bool post_flip, uint32_t bDown, uint32_t* u) {
+    if (!a.wl.has_so[slot]) return 0u;
+    const uint32_t RM = (1u << a.K) - 1u;
+    const int32_t S_before = a.bc->S_before;
+    uint32_t umask = 0;
+    for (int k = 0; k < a.K; ++k) {
+        const int32_t so = a.wl.so_tab[(size_t)slot * SO_STRIDE + k];
+        if (so < 0) continue;
+        const bool ot = a.touch[so] == a.serial;
+        const int bo = ot ? a.batch_index[so] : 0;
+        const uint32_t uo = so >= S_before ? 0u : (precall_row(a, so, post_flip)[r] & RM);
+        const uint32_t bLo = observer_L_batch(uo, ot ? &a.desc[bo] : nullptr, ot ? &a.pwalk[bo] : nullptr, a.L);
+        u[k] = (bLo == T32_NONE || bDown == T32_NONE) ? T32_NONE : max(bLo, bDown);
+        umask |= 1u << k;
+    }
+    return umask;
+}
+// state of (batch subject d, receiver r) when the last batch of the call starts, from its PRE-call word (passes that recompute visits)
+__device__ __forceinline__ uint32_t seq_state(const ApplyArgs& a, const SubjDesc& d, int b_index, int64_t r, uint32_t old, bool post_flip,
+                                              bool after_finalize1) {
+    if (!a.seq) return old;
+    uint32_t u[MAXK];
+    const uint32_t umask = edge_times(a, d.slot, r, post_flip, receiver_down_batch(a, a.rflags[r], after_finalize1), u);
+    if (umask == 0 && d.pmask == 0) return old;
+    return prefix_core(nullptr, old, d, a.pwalk[b_index], u, umask, a.L, a.H, (uint32_t)a.bc->seq_last);
 }
 
 template <bool PERM, bool SEQ>
@@ -312,6 +404,11 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
     __shared__ uint32_t s_nw[STAGE];          // (rings reported by the call) replicated in both half-words
     __shared__ int s_unres[STAGE];
     __shared__ StageAcc s_facc;               // fresh-subject accumulators of this block's chunk (same for every receiver)
+    // SEQ: the dictionary observers ("edges") of the staged subjects — their pre-call rows (nullptr: fresh, state 0) and batch index
+    __shared__ uint8_t s_ne[SEQ ? STAGE : 1];
+    __shared__ uint8_t s_ek[SEQ ? STAGE : 1][MAXK];
+    __shared__ const uint16_t* s_erow[SEQ ? STAGE : 1][MAXK];
+    __shared__ int32_t s_eob[SEQ ? STAGE : 1][MAXK];
 
     if (a.bc->overflow) return;               // the batch was rolled back by k_prepare
     // the number of batch subjects / the first fresh slot are only known on the device
@@ -323,14 +420,17 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
     const size_t pbase = (size_t)chunk * a.Rpad + (size_t)r0;
     const uint32_t RM = (1u << a.K) - 1u;
     const int L = a.L, H = a.H;
+    const uint32_t seq_last = SEQ ? (uint32_t)a.bc->seq_last : 0u;
 
-    uint32_t act = 0;
+    uint32_t act = 0, seen = 0;               // seen: receivers whose seenLinkDownEvents is already set (SEQ)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int64_t r = r0 + j;
         if (r < a.R) {
-            const bool on = !(a.rflags[r] & RF_ANNOUNCED) && !((a.dl.flags & RAPID_DELIVERY_BLOCKED) && a.dl.blocked[r]);
+            const uint32_t rf = a.rflags[r];
+            const bool on = !(rf & RF_ANNOUNCED) && !((a.dl.flags & RAPID_DELIVERY_BLOCKED) && a.dl.blocked[r]);
             act |= (on ? 1u : 0u) << j;
+            if (SEQ && (rf & RF_SEEN_DOWN)) seen |= 1u << j;
         }
     }
     // SWAR masks: 0xFFFF per active half-word
@@ -360,18 +460,34 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                 s_dst[t] = a.masks + ((size_t)d.slot * 2 + (c ^ 1)) * a.Rpad;
                 s_nw[t] = (uint32_t)(d.bmask | d.pmask) * 0x10001u;
                 int un = 0;
-                if (fresh) {
-                    // state 0 for everyone: the descriptor-level answers (visit_prefix / visit_uniform take their shortcuts)
+                const bool edges = SEQ && a.wl.has_so[d.slot];   // implicit reports inside the prefix: per-receiver state matters
+                if (SEQ) {
+                    int ne = 0;
+                    if (edges) {
+                        for (int k = 0; k < a.K; ++k) {
+                            const int32_t so = a.wl.so_tab[(size_t)d.slot * SO_STRIDE + k];
+                            if (so < 0) continue;
+                            s_ek[t][ne] = (uint8_t)k;
+                            s_erow[t][ne] = so >= S_before ? nullptr : a.masks + ((size_t)so * 2 + a.cur[so]) * a.Rpad;
+                            s_eob[t][ne] = a.touch[so] == a.serial ? a.batch_index[so] : -1;
+                            ++ne;
+                        }
+                    }
+                    s_ne[t] = (uint8_t)ne;
+                }
+                if (fresh && !edges) {
+                    // state 0 for everyone: the descriptor-level answers (prefix_core / visit_uniform take their shortcuts)
                     un = (visit_acc<PERM, SEQ>(f, 0u, d, &sw[0], &spw[0], RM, L, H) && block_active) ? 1 : 0;   // (walks not read)
                     if (PERM) { f.minTH = T32_NONE; f.minTLun = T32_NONE; }
                 } else {
                     if (!PERM) sw[t] = a.walk[base + t];
                     if (SEQ) spw[t] = a.pwalk[base + t];
+                    if (fresh) s_src[t] = nullptr;
                 }
                 // only subjects with an observer in the dictionary can receive implicit reports: the others never go on
                 // the invalidation work list (has_so is refreshed by k_prepare whenever a subject gets a slot)
                 s_unres[t] = (un && a.wl.has_so[d.slot]) ? 1 : 0;
-                if (!fresh) s_unres[t] = a.wl.has_so[d.slot] ? 0 : -1;       // -1: never list it
+                if (!fresh || edges) s_unres[t] = a.wl.has_so[d.slot] ? 0 : -1;       // -1: never list it
             }
             // warp reduction of the fresh subjects' contribution
             uint32_t nLH = f.nL | (f.nH << 16), tpUn = f.tp | (f.nUn << 16), fl = f.flags, mTH = f.minTH, mTL = f.minTLun;
@@ -411,11 +527,12 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
             const uint16_t* src = s_src[i];
             uint16_t* dst = s_dst[i];
             const uint32_t nwb = s_nw[i];
-            if (src == nullptr) {                          // fresh subject: write-only
+            const int ne = SEQ ? (int)s_ne[i] : 0;
+            if (src == nullptr && ne == 0) {               // fresh subject: write-only
                 *reinterpret_cast<uint4*>(dst + r0) = make_uint4(nwb & am[0], nwb & am[1], nwb & am[2], nwb & am[3]);
                 continue;
             }
-            uint4 w = *reinterpret_cast<const uint4*>(src + r0);
+            uint4 w = src ? *reinterpret_cast<const uint4*>(src + r0) : make_uint4(0u, 0u, 0u, 0u);
             bool unres = false;
             if (act) {
                 const SubjDesc& d = sd[i];
@@ -424,9 +541,34 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                 const uint32_t orw = (w.x & am[0]) | (w.y & am[1]) | (w.z & am[2]) | (w.w & am[3]);
                 const uint32_t andv = andw & (andw >> 16) & 0xFFFFu, st = (orw | (orw >> 16)) & 0xFFFFu;
                 carried = true;
-                if (andv == st) {
-                    unres = visit_acc<PERM, SEQ>(com, st & RM, d, &sw[PERM ? 0 : i], &spw[SEQ ? i : 0], RM, L, H);
-                    const uint32_t nw = st * 0x10001u | nwb;
+                bool same = andv == st;
+                // SEQ, subject with dictionary observers: their state (and seenLinkDownEvents) must be the same across the thread's
+                // active receivers too, or every receiver is visited on its own
+                uint32_t u[MAXK];
+                uint32_t umask = 0;
+                if (SEQ && ne) {
+                    const uint32_t sact = seen & act;
+                    same = same && (sact == 0 || sact == act);
+                    const uint32_t bDown = sact ? 0u : (a.bc->seq_down == INT_MAX ? T32_NONE : (uint32_t)a.bc->seq_down);
+                    for (int e = 0; e < ne && same; ++e) {
+                        uint32_t so_st = 0;
+                        if (s_erow[i][e]) {
+                            const uint4 wo = *reinterpret_cast<const uint4*>(s_erow[i][e] + r0);
+                            const uint32_t aw = (wo.x | ~am[0]) & (wo.y | ~am[1]) & (wo.z | ~am[2]) & (wo.w | ~am[3]);
+                            const uint32_t ow = (wo.x & am[0]) | (wo.y & am[1]) | (wo.z & am[2]) | (wo.w & am[3]);
+                            so_st = (ow | (ow >> 16)) & 0xFFFFu;
+                            same = (aw & (aw >> 16) & 0xFFFFu) == so_st;
+                        }
+                        const int ob = s_eob[i][e], k = s_ek[i][e];
+                        const uint32_t bLo = observer_L_batch(so_st & RM, ob >= 0 ? &a.desc[ob] : nullptr, ob >= 0 ? &a.pwalk[ob] : nullptr, L);
+                        u[k] = (bLo == T32_NONE || bDown == T32_NONE) ? T32_NONE : max(bLo, bDown);
+                        umask |= 1u << k;
+                    }
+                }
+                if (same) {
+                    uint32_t at_last = st;
+                    unres = visit_acc<PERM, SEQ>(com, st & RM, d, &sw[PERM ? 0 : i], &spw[SEQ ? i : 0], RM, L, H, u, umask, seq_last, &at_last);
+                    const uint32_t nw = (SEQ ? (at_last | (st & ~RM)) : st) * 0x10001u | nwb;
                     w.x = (w.x & ~am[0]) | (nw & am[0]);
                     w.y = (w.y & ~am[1]) | (nw & am[1]);
                     w.z = (w.z & ~am[2]) | (nw & am[2]);
@@ -444,9 +586,11 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                         if (!((act >> j) & 1u)) continue;
                         const uint32_t sj = (words[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
                         Acc ex;
-                        unres |= visit_acc<PERM, SEQ>(ex, sj & RM, d, &sw[PERM ? 0 : i], &spw[SEQ ? i : 0], RM, L, H);
+                        uint32_t at_last = sj;
+                        if (SEQ && ne) umask = edge_times(a, d.slot, r0 + j, false, receiver_down_batch(a, ((seen >> j) & 1u) ? RF_SEEN_DOWN : 0u, false), u);
+                        unres |= visit_acc<PERM, SEQ>(ex, sj & RM, d, &sw[PERM ? 0 : i], &spw[SEQ ? i : 0], RM, L, H, u, umask, seq_last, &at_last);
                         part_merge<SEQ>(a.part, pbase + j, ex);
-                        words[j >> 1] |= (nwb & 0xFFFFu) << ((j & 1) * 16);
+                        words[j >> 1] |= ((SEQ ? (at_last & RM) : 0u) | (nwb & 0xFFFFu)) << ((j & 1) * 16);
                     }
                     w = make_uint4(words[0], words[1], words[2], words[3]);
                 }
@@ -781,7 +925,8 @@ __device__ void phase_finalize1(const ResolveArgs& a, int32_t* s_red) {
     int32_t my_mixed = 0, my_times = 0;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < ap.R; r += (int64_t)gridDim.x * blockDim.x) {
         a.mx_fl[r] = 0;
-        uint32_t flags = a.rflags[r] & ~(RF_ANN_NOW | RF_K3 | RF_ACTIVE);
+        uint32_t flags = a.rflags[r] & ~(RF_ANN_NOW | RF_K3 | RF_ACTIVE | RF_PRE_DOWN);
+        if (flags & RF_SEEN_DOWN) flags |= RF_PRE_DOWN;                 // seenLinkDownEvents as it was before this call
         a.out_h1[r] = 0; a.out_h2[r] = 0; a.out_len[r] = 0;
         const bool active = !(flags & RF_ANNOUNCED) && !((ap.dl.flags & RAPID_DELIVERY_BLOCKED) && ap.dl.blocked[r]);
         if (!active) { a.rflags[r] = flags; a.out_ann[r] = (flags & RF_ANNOUNCED) ? 1 : 0; continue; }
@@ -938,7 +1083,7 @@ __device__ __noinline__ void mixed_pass(const ResolveArgs& m, PassSmem& sm, cons
             if (!on) continue;
             for (int i = 0; i < n; ++i) {
                 const SubjDesc& d = sm.sd[i];
-                const uint32_t st = (sm.s_old[i] ? sm.s_old[i][r] : 0u) | d.pmask;   // state when the (last) batch starts
+                const uint32_t st = seq_state(a, d, base + i, r, (sm.s_old[i] ? sm.s_old[i][r] : 0u) & RM, false, true);   // when the (last) batch starts
                 const IVisit v = interval_visit(a, m.uniform, st & RM, d, &sm.sw[i], r, rs);
                 if (MODE == 0) {
                     if (!v.crossH) continue;                                  // never closes, or never in the band
@@ -1026,7 +1171,7 @@ __device__ __noinline__ bool emitted_in_batch(const ResolveArgs& e, int32_t s, i
     if (e.touch[s] != e.serial) return __popc(w_new & RM) >= a.H && !(w_new & CD_BIT_CALL);
     const int b = e.batch_index[s];
     const SubjDesc d = a.desc[b];
-    const uint32_t old = (s >= a.bc->S_before ? 0u : (a.masks + ((size_t)s * 2 + (a.cur[s] ^ 1)) * a.Rpad)[r]) | d.pmask;
+    const uint32_t old = seq_state(a, d, b, r, (s >= a.bc->S_before ? 0u : (a.masks + ((size_t)s * 2 + (a.cur[s] ^ 1)) * a.Rpad)[r]) & RM, true, true);
     if (__popc(old & RM) >= a.H) return true;                              // pending before the (last) batch
     SubjWalk wl;
     if (e.uniform) wl = a.walk[b];
@@ -1276,7 +1421,7 @@ __device__ void resolve_tail(const ResolveArgs& a, int32_t serial) {
     c.bad_ring = b->bad_ring; c.bad_dst = b->bad_dst; c.n_mixed = b->n_mixed; c.n_inval = b->n_inval; c.S_before = b->S_before;
     c.overflow = b->overflow; c.need_slots = b->need_slots; c.n_times = b->n_times; c.mixed_iters = b->mixed_iters;
     c.n_pairs = *(volatile int32_t*)a.ap.wl.count; c.ticket = 0; c.serial = serial;
-    c.seq_last = b->seq_last; c.seq_down = b->seq_down; c.seq_abort = b->seq_abort; c.pad_[0] = 0; c.pad_[1] = 0;
+    c.seq_last = b->seq_last; c.seq_down = b->seq_down; c.seq_abort = b->seq_abort; c.seq_a1 = b->seq_a1; c.seq_a2 = b->seq_a2;
     if (c.seq_abort) { c.n_slots = c.S_before; b->n_slots = c.S_before; }   // the slots this call assigned were given back (seq_rollback)
     // errors stay latched until the host has collected them (an asynchronous caller may have several batches in flight)
     c.sticky_bad_ring = b->sticky_bad_ring | (c.bad_ring >= 0 ? 1 : 0);
@@ -1286,7 +1431,7 @@ __device__ void resolve_tail(const ResolveArgs& a, int32_t serial) {
     *a.snap = c;
     b->n_valid = 0; b->n_batch_subj = 0; b->any_down = 0; b->bad_ring = -1; b->bad_dst = -1; b->n_mixed = 0; b->n_inval = 0;
     b->overflow = 0; b->need_slots = 0; b->n_times = 0; b->mixed_iters = 0; b->ticket = 0;
-    b->seq_last = 0; b->seq_down = INT_MAX; b->seq_abort = 0;
+    b->seq_last = 0; b->seq_down = INT_MAX; b->seq_abort = 0; b->seq_a1 = 0; b->seq_a2 = 0;
     b->S_before = c.n_slots;                                            // the next batch starts from here (k_prepare reads it)
 }
 
@@ -1295,27 +1440,6 @@ __device__ void resolve_tail(const ResolveArgs& a, int32_t serial) {
 // blockIdx.y == 0: A1 from the partial accumulators; blockIdx.y >= 1: A2 over a chunk of the dictionary's slots.  Counts
 // the receivers that fail into bc->seq_abort — every later kernel of the batch returns at once if that is non-zero.
 // ==================================================================================================================
-struct PrefixInfo { uint32_t bL, bH, bK; };      // 1-based prefix batch in which the subject reaches L / H / ring k is first
-                                                  // reported; 0 = already so before the call; T32_NONE = not within the prefix
-__device__ __forceinline__ PrefixInfo prefix_info(uint32_t ur, const SubjDesc* d, const SubjWalk* pw, int k, int L, int H) {
-    PrefixInfo o;
-    int c = __popc(ur);
-    o.bL = c >= L ? 0u : T32_NONE;
-    o.bH = c >= H ? 0u : T32_NONE;
-    o.bK = ((ur >> k) & 1u) ? 0u : T32_NONE;
-    if (d == nullptr || d->pmask == 0) return o;
-    const int np = __popc(d->pmask);
-    for (int q = 0; q < np; ++q) {
-        const int kk = pw->ring[q];
-        if ((ur >> kk) & 1u) continue;
-        ++c;
-        if (c == L) o.bL = pw->time[q];
-        if (c == H) o.bH = pw->time[q];
-        if (kk == k) o.bK = pw->time[q];
-    }
-    return o;
-}
-
 __global__ void __launch_bounds__(GEN_THREADS) k_seq_check(const ResolveArgs* __restrict__ ga) {
     const ResolveArgs& a = *ga;
     const ApplyArgs& ap = a.ap;
@@ -1346,39 +1470,34 @@ __global__ void __launch_bounds__(GEN_THREADS) k_seq_check(const ResolveArgs* __
             if (!ok) bad = 1;
         }
     } else {
-        // ---- A2: no invalidation pass at the end of a prefix batch adds a report --------------------------------------------------
+        // ---- A2: no invalidation pass at the end of a prefix batch reports a ring of a subject the call does NOT touch ------------
+        // (the subjects the call touches carry their implicit reports through the visit: prefix_core)
         const int32_t S = a.bc->n_slots, S_before = a.bc->S_before;
         const uint32_t last = (uint32_t)a.bc->seq_last;                   // prefix batches are 1 .. last (1-based)
         const int nchunks = (int)gridDim.y - 1;
         const int per = (S + nchunks - 1) / nchunks;
         const int32_t q0 = min(S, ((int)blockIdx.y - 1) * per), q1 = min(S, q0 + per);
         const uint32_t RM = (1u << ap.K) - 1u;
-        const uint32_t bDown = (rf & RF_SEEN_DOWN) ? 0u : (a.bc->seq_down == INT_MAX ? T32_NONE : (uint32_t)a.bc->seq_down);
+        const uint32_t bDown = receiver_down_batch(ap, rf, false);
         for (int32_t sl = q0; sl < q1; ++sl) {
-            if (!ap.wl.has_so[sl]) continue;                               // (uniform across the block)
-            const bool s_touched = a.touch[sl] == a.serial;
-            const int bs_idx = s_touched ? a.batch_index[sl] : 0;
-            const SubjDesc* ds = s_touched ? &ap.desc[bs_idx] : nullptr;
-            const uint32_t us = (active && sl < S_before) ? ((ap.masks + ((size_t)sl * 2 + ap.cur[sl]) * ap.Rpad)[r] & RM) : 0u;
+            if (sl >= S_before || !ap.wl.has_so[sl] || a.touch[sl] == a.serial) continue;      // (uniform across the block)
+            if (!active || bDown == T32_NONE) continue;
+            const uint32_t us = (ap.masks + ((size_t)sl * 2 + ap.cur[sl]) * ap.Rpad)[r] & RM;
+            const int cs = __popc(us);
+            if (cs < ap.L || cs >= ap.H) continue;                         // not in this receiver's preProposal
             for (int k = 0; k < ap.K; ++k) {
                 const int32_t so = ap.wl.so_tab[(size_t)sl * SO_STRIDE + k];
-                if (so < 0) continue;
+                if (so < 0 || ((us >> k) & 1u)) continue;
                 const bool o_touched = a.touch[so] == a.serial;
-                if (!s_touched && !o_touched && bDown == 0u) continue;     // nothing about this edge changes in the call
-                if (!active) continue;
                 const int bo_idx = o_touched ? a.batch_index[so] : 0;
-                const SubjDesc* dobs = o_touched ? &ap.desc[bo_idx] : nullptr;
                 const uint32_t uo = so < S_before ? ((ap.masks + ((size_t)so * 2 + ap.cur[so]) * ap.Rpad)[r] & RM) : 0u;
-                const PrefixInfo ps = prefix_info(us, ds, s_touched ? &ap.pwalk[bs_idx] : nullptr, k, ap.L, ap.H);
-                const PrefixInfo po = prefix_info(uo, dobs, o_touched ? &ap.pwalk[bo_idx] : nullptr, k, ap.L, ap.H);
-                if (ps.bL == T32_NONE || po.bL == T32_NONE || bDown == T32_NONE) continue;
-                const uint32_t at = max(max(ps.bL, po.bL), bDown);         // first batch end with s in the band, o in U, DOWN seen
-                if (at <= last && at < ps.bH && at < ps.bK) bad = 1;       // ... s still below H, ring k still unreported: it WOULD fire
+                const uint32_t bLo = observer_L_batch(uo, o_touched ? &ap.desc[bo_idx] : nullptr, o_touched ? &ap.pwalk[bo_idx] : nullptr, ap.L);
+                if (bLo != T32_NONE && max(bLo, bDown) <= last) bad = 1;  // an invalidation pass inside the prefix would report ring k
             }
         }
     }
     const int32_t b = block_sum_i32(bad, s_red);
-    if (threadIdx.x == 0 && b) atomicAdd(&a.bc->seq_abort, b);
+    if (threadIdx.x == 0 && b) { atomicAdd(&a.bc->seq_abort, b); atomicAdd(blockIdx.y == 0 ? &a.bc->seq_a1 : &a.bc->seq_a2, b); }
 }
 
 // ---- the four launches after the apply kernel (no host round trip between them) ---------------------------------------------
@@ -1656,6 +1775,7 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, bool seq) {
     ap.K = cd->K; ap.H = cd->H; ap.L = cd->L; ap.R = cd->R; ap.rbegin = cd->rbegin;
     ap.rflags = cd->rflags.p; ap.dl = dl; ap.bc = cd->counts.p;
     ap.desc = b->desc.p; ap.walk = b->walk.p; ap.pwalk = b->pwalk.p; ap.slot_subject = cd->slot_subject.p;
+    ap.touch = cd->touch.p; ap.batch_index = b->batch_index.p; ap.serial = cd->batch_serial; ap.seq = seq ? 1 : 0;
     ap.sidx = b->sidx.p; ap.s_ring = b->s_ring.p; ap.s_status = b->s_status.p;
     ap.part = part; ap.n_tiles = b->n_tiles; ap.wl = worklist(b);
 

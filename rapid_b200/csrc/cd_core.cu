@@ -532,6 +532,7 @@ static int32_t bucketed_sequence(CD* cd, int64_t cfg, int64_t A, const int32_t* 
             return RAPID_OK;
         }
         // refused for some receiver: nothing was committed — batch by batch (bad cells are reported by the replay)
+        cd->seq_refused_a1 = cd->last.seq_a1; cd->seq_refused_a2 = cd->last.seq_a2;
     }
     ++cd->seq_replayed;
     for (int32_t b = first; b <= last; ++b) {
@@ -860,10 +861,12 @@ int32_t rapid_cd_read_announced_in(const rapid_cd* cd, int32_t* announced_in) {
 }
 
 // diagnostics: sequences served in one pass / replayed batch by batch since the handle was created
-int32_t rapid_cd_sequence_stats(const rapid_cd* cd, int32_t* one_pass, int32_t* replayed) {
+int32_t rapid_cd_sequence_stats(const rapid_cd* cd, int32_t* one_pass, int32_t* replayed, int32_t* refused_a1, int32_t* refused_a2) {
     if (!cd) { set_error("NULL handle"); return RAPID_EINVAL; }
     if (one_pass) *one_pass = cd->seq_merged;
     if (replayed) *replayed = cd->seq_replayed;
+    if (refused_a1) *refused_a1 = cd->seq_refused_a1;
+    if (refused_a2) *refused_a2 = cd->seq_refused_a2;
     return RAPID_OK;
 }
 

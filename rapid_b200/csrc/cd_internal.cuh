@@ -49,7 +49,7 @@ struct BatchCounts {
     int32_t seq_last;      // index of the last non-empty batch of the call in flight (0 for a single batch)
     int32_t seq_down;      // 1-based index of the first batch with a valid DOWN cell, INT_MAX if none
     int32_t seq_abort;     // receivers for which the one-pass treatment is not provably exact: NOTHING was committed
-    int32_t pad_[2];
+    int32_t seq_a1, seq_a2; // ... of which: could have emitted before the last batch / an implicit report would fire inside the prefix
 };
 
 struct CD {
@@ -88,6 +88,7 @@ struct CD {
     DevBuf<uint64_t> sq_h1, sq_h2;    // [R] outputs of the announcing batch while a sequence is replayed batch by batch
     DevBuf<int32_t> sq_len;
     int32_t seq_merged = 0, seq_replayed = 0;   // sequences served in one pass / replayed batch by batch (diagnostics)
+    int32_t seq_refused_a1 = 0, seq_refused_a2 = 0;   // receivers that failed either premise in the last refused attempt
     DevBuf<int32_t> out_len;          // [R]
     DevBuf<uint8_t> out_ann;          // [R]
 

@@ -232,7 +232,13 @@ class VirtualCluster:
     def sequenceStats(self):
         """(sequences served in one pass, sequences replayed batch by batch)"""
         a, b = C.c_int32(0), C.c_int32(0)
-        N.check(N.lib().rapid_cd_sequence_stats(self._h, C.byref(a), C.byref(b)))
+        N.check(N.lib().rapid_cd_sequence_stats(self._h, C.byref(a), C.byref(b), None, None))
+        return a.value, b.value
+
+    def sequenceRefusal(self):
+        """receivers that failed premise A1 / A2 in the last refused one-pass attempt"""
+        a, b = C.c_int32(0), C.c_int32(0)
+        N.check(N.lib().rapid_cd_sequence_stats(self._h, None, None, C.byref(a), C.byref(b)))
         return a.value, b.value
 
     def readOutputs(self):

@@ -668,7 +668,7 @@ def test_sequence_stream_c4_in_one_pass(orc, rb):
     _check_sequence(rb, cl, sim, res, ain, *want)
     live = blocked == 0
     assert (ain[live] == 7).all() and (res.proposal_len[live] == len(batches[-1].expected_cut)).all()
-    assert cl.sequenceStats() == (1, 0)
+    assert cl.sequenceStats() == (1, 0), cl.sequenceRefusal()
     fp = rb.FastPaxos(cfg, n)
     t = fp.tallyCluster(cl)
     assert t.decided and t.length == len(batches[-1].expected_cut) and t.count == rb.quorum(n)
