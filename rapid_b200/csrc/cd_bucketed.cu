@@ -89,7 +89,7 @@ struct Partials {                     // [n_chunks][Rpad] structure of arrays
 struct Bucketed {
     DevBuf<int32_t> sidx;                     // cell indices grouped by subject (arrival order inside a subject)
     DevBuf<int32_t> seg_cnt, batch_slots;     // [slot] scratch of the prepare kernel (seg_cnt all zero between batches)
-    DevBuf<int32_t> bins, ovf;                // [slot][16] cell bins, [A] overflow list
+    DevBuf<int32_t> bins, ovf;                // [slot][64] cell bins (PREP_BIN), [A] overflow list
     DevBuf<SubjDesc> desc;
     DevBuf<SubjWalk> walk;
     DevBuf<uint8_t> s_ring, s_status;         // per sorted cell
@@ -1636,7 +1636,7 @@ int32_t bucketed_prep_buffers(CD* cd, int64_t A, PrepOut* po) {
     const size_t slots = std::max<size_t>(cd->S_cap, 1);
     RAPID_CHECK(b->batch_index.reserve(slots));
     RAPID_CHECK(b->batch_slots.reserve(slots));
-    RAPID_CHECK(b->bins.reserve(slots * 16));
+    RAPID_CHECK(b->bins.reserve(slots * 64));
     RAPID_CHECK(b->ovf.reserve(a));
     if (slots > b->seg_cnt.cap) {
         RAPID_CHECK(b->seg_cnt.reserve(slots));

@@ -199,7 +199,7 @@ struct PrepOut {                      // where the prepare kernel writes the reg
     int32_t* batch_index;             // [slot] -> index of the subject in the batch
     int32_t* seg_cnt;                 // [slot] cells of the subject in this batch (scratch, all zero between batches)
     int32_t* batch_slots;             // [batch index] -> slot
-    int32_t* bins;                    // [slot][16] indices of the subject's first 16 cells of this batch (any order)
+    int32_t* bins;                    // [slot][64] indices of the subject's first 64 cells of this batch (any order)
     int32_t* ovf;                     // [A] cells beyond a subject's bin
     SubjWalk* pwalk;                  // sequences of batches: first-occurrence ring sequence of the prefix, time = batch index + 1
     WorkList wl;                      // invalidation work list (bucketed handles; wl.has_so == nullptr otherwise)

@@ -6,7 +6,7 @@
 //       (no consumer depends on their order), so no prefix sum over "new subjects per block" is needed
 //                                                                                           ── grid.sync
 //   P2  cell -> slot; the cell's position among its subject's cells (atomic counter) drops its index into the subject's
-//       16-entry BIN (cells beyond 16 of one subject in one batch go to a shared overflow list); the first cell to touch a
+//       64-entry BIN (cells beyond 64 of one subject in one call go to a shared overflow list); the first cell to touch a
 //       subject in this batch gives it its index in the batch.  Also: which observers of a subject are subjects themselves
 //       (refreshed when the dictionary grew) — the invalidation work list's edge table
 //                                                                                           ── grid.sync
@@ -100,7 +100,8 @@ __device__ __forceinline__ int32_t batch_of_cell(const int64_t* __restrict__ off
     return lo;
 }
 
-constexpr int PREP_BIN = 16;          // cells of one subject kept in its bin; the rest of a (duplicate-heavy) subject overflow
+constexpr int PREP_BIN = 64;          // cells of one subject kept in its bin; the rest of a (duplicate-heavy) subject overflow
+constexpr int PREP_REG = 16;          // ... of which this many are sorted in registers (the usual case: ~K cells per subject)
 
 __device__ __forceinline__ void prep_stamp(const PrepArgs& a, int i) {
     if (a.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -289,13 +290,13 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepArgs a) {
                 }
             }
         };
-        if (len <= PREP_BIN) {
-            int32_t c[PREP_BIN];
+        if (len <= PREP_REG) {
+            int32_t c[PREP_REG];
 #pragma unroll
-            for (int q = 0; q < PREP_BIN; ++q) c[q] = q < len ? a.po.bins[(size_t)slot * PREP_BIN + q] : INT_MAX;
+            for (int q = 0; q < PREP_REG; ++q) c[q] = q < len ? a.po.bins[(size_t)slot * PREP_BIN + q] : INT_MAX;
             // insertion sort by compare-exchange on registers (fully unrolled: no local memory)
 #pragma unroll
-            for (int i = 1; i < PREP_BIN; ++i) {
+            for (int i = 1; i < PREP_REG; ++i) {
 #pragma unroll
                 for (int j = i; j > 0; --j) {
                     const int32_t lo = min(c[j - 1], c[j]), hi = max(c[j - 1], c[j]);
@@ -303,14 +304,18 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepArgs a) {
                 }
             }
 #pragma unroll
-            for (int q = 0; q < PREP_BIN; ++q) if (q < len) take(q, c[q]);
+            for (int q = 0; q < PREP_REG; ++q) if (q < len) take(q, c[q]);
         } else {
-            // duplicate-heavy subject: bin + its cells on the overflow list, sorted in place (correct for any length)
-            for (int q = 0; q < PREP_BIN; ++q) seg[q] = a.po.bins[(size_t)slot * PREP_BIN + q];
-            int32_t at = PREP_BIN;
-            for (int32_t q = 0; q < n_ovf; ++q) {
-                const int32_t ci = a.po.ovf[q];
-                if (a.cell_slot[ci] == slot) seg[at++] = ci;
+            // more cells than the register path holds (streams with re-sent duplicates; sequences of batches): the bin — and, past
+            // its capacity, the subject's cells on the shared overflow list — sorted in place (correct for any length)
+            const int32_t nb = min(len, PREP_BIN);
+            for (int q = 0; q < nb; ++q) seg[q] = a.po.bins[(size_t)slot * PREP_BIN + q];
+            if (len > PREP_BIN) {
+                int32_t at = PREP_BIN;
+                for (int32_t q = 0; q < n_ovf; ++q) {
+                    const int32_t ci = a.po.ovf[q];
+                    if (a.cell_slot[ci] == slot) seg[at++] = ci;
+                }
             }
             for (int32_t gap = len >> 1; gap > 0; gap >>= 1)
                 for (int32_t i = gap; i < len; ++i) {
