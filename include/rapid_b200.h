@@ -103,11 +103,22 @@ int32_t rapid_view_register_joiners(rapid_view* v, int64_t n_add, const uint8_t*
                                     const int32_t* host_off, const int32_t* port, int32_t* out_first_id);
 int32_t rapid_view_num_joiners(const rapid_view* v, int64_t* out);
 /* decideViewChange (MembershipService.java:385-444) on the view: every cut id that is a member is removed (ringDelete
- * :167-201), every other one must be a registered joiner and is added (ringAdd :123-160); the K rings are rebuilt on the
- * device.  Ids are renumbered densely (surviving members in order, then the admitted joiners; joiners not in the cut are
- * dropped); out_old_to_new[n + joiners] receives the mapping (-1 = gone) and may be NULL.  Detector handles created on
- * the old view must be destroyed and recreated. */
+ * :167-201), every other one must be a registered joiner and is added (ringAdd :123-160).  The K rings are UPDATED on the
+ * device — order-preserving compaction of every ring + a sorted merge of the joiners, no re-hash or re-sort of the members;
+ * the endpoint table, per-id keys and NodeIds are compacted alongside; only the cut ids (in) and status words (out) cross the
+ * bus.  Ids are renumbered densely (surviving members in order, then the admitted joiners; joiners not in the cut are
+ * dropped); out_old_to_new[n + joiners] receives the mapping (-1 = gone) and may be NULL.  With NodeIds set
+ * (rapid_view_set_node_ids) an admitted joiner whose NodeId is already in identifiersSeen -> RAPID_EUUID_SEEN
+ * (UUIDAlreadySeenException, MembershipView.java:126-128) and NOTHING changes.  Detector handles created on the old view must be
+ * destroyed and recreated (their receivers are ring-0 positions of that view). */
 int32_t rapid_view_apply_cut(rapid_view* v, const int32_t* cut_ids, int64_t n_cut, int32_t* out_old_to_new);
+/* identifiersSeen on the device (MembershipView.java:58-60): NodeIds of the current members (index = node id) seed it —
+ * RAPID_EUUID_SEEN if two members share one; the NodeIds of registered joiners [first_joiner_id, +count) come from their UP
+ * alerts (MembershipService.java:677-685) and join the set when a cut admits them; ids of removed nodes stay (:167-201).
+ * rapid_view_current_config_id = getCurrentConfigurationId (:360-372, :544-556) from that set and ring 0: 8 bytes leave the device. */
+int32_t rapid_view_set_node_ids(rapid_view* v, const int64_t* id_high, const int64_t* id_low);
+int32_t rapid_view_set_joiner_ids(rapid_view* v, int32_t first_joiner_id, int64_t count, const int64_t* id_high, const int64_t* id_low);
+int32_t rapid_view_current_config_id(const rapid_view* v, int64_t* out);
 /* expected observers of every registered joiner: out[j*K+k] for joiner id n + j. */
 int32_t rapid_view_joiner_tables(const rapid_view* v, int32_t* out);
 

@@ -71,6 +71,9 @@ SIGNATURES = {
     "rapid_view_num_joiners": [_vp, _p],
     "rapid_view_joiner_tables": [_vp, _p],
     "rapid_view_apply_cut": [_vp, _p, _i64, _p],
+    "rapid_view_set_node_ids": [_vp, _p, _p],
+    "rapid_view_set_joiner_ids": [_vp, _i32, _i64, _p, _p],
+    "rapid_view_current_config_id": [_vp, _p],
     "rapid_cd_debug_stats": [_vp, _p, _p, _p, _p],
     "rapid_cd_create": [_pp, _vp, _i32, _i32, _i64, _i64, _u32, _i64],
     "rapid_cd_destroy": [_vp],

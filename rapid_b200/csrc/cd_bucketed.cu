@@ -1649,34 +1649,63 @@ int32_t bucketed_prep_buffers(CD* cd, int64_t A, PrepOut* po) {
     return RAPID_OK;
 }
 
-// forget the work list: O(listed subjects x tiles), not O(slots x tiles)
-__global__ void k_clear_worklist(WorkList wl) {
-    const int n = min(*wl.count, wl.cap);
-    const int64_t items = (int64_t)n * wl.n_tiles;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < items; e += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t sl = wl.slots[e / wl.n_tiles];
-        const int tile = (int)(e % wl.n_tiles);
-        wl.in_tile[(size_t)sl * wl.n_tiles + tile] = 0;
-        if (tile == 0) wl.listed[sl] = 0;
-    }
-}
-// a new configuration epoch: no slots, per-batch counters armed
-__global__ void k_reset_counts(BatchCounts* bc, BatchCounts* snap, int32_t* pre_count) {
-    BatchCounts c;
-    memset(&c, 0, sizeof(c));
-    c.bad_ring = -1; c.bad_dst = -1; c.seq_down = INT_MAX;
-    const int32_t sr = bc->sticky_bad_ring, sd = bc->sticky_bad_dst, so = bc->sticky_overflow;
-    c.sticky_bad_ring = sr; c.sticky_bad_dst = sd; c.sticky_overflow = so;       // errors not collected yet survive a clear()
-    *bc = c;
-    *snap = c;
-    *pre_count = 0;
-}
 __global__ void k_clear_sticky(BatchCounts* bc) { bc->sticky_bad_ring = 0; bc->sticky_bad_dst = 0; bc->sticky_overflow = 0; }
 
 int32_t bucketed_clear_sticky(CD* cd) {
     k_clear_sticky<<<1, 1, 0, cd->stream>>>(cd->counts.p);
     RAPID_KERNEL_CHECK();
     return RAPID_OK;
+}
+
+// clear() of a bucketed handle in ONE launch: every receiver's detector scalars (MultiNodeCutDetector.java:169-178 +
+// announcedProposal = false), the subject dictionary (O(#slots in use)), the invalidation work list, and — by the last block to
+// finish, because the loops above read the slot count and the list length — the device counters for a new configuration epoch.
+struct ClearArgs {
+    int64_t Rpad;
+    int32_t* n_pre; int32_t* n_prop; uint32_t* rflags;
+    uint64_t* pend_h1; uint64_t* pend_h2; int32_t* pend_cnt;
+    uint64_t* out_h1; uint64_t* out_h2; int32_t* out_len; uint8_t* out_ann;
+    BatchCounts* bc; BatchCounts* snap;
+    const int32_t* slot_subject; int32_t* slot_of; uint8_t* cur;
+    WorkList wl;
+    int has_wl;
+};
+__global__ void __launch_bounds__(256) k_clear_bucketed(const ClearArgs a) {
+    __shared__ int s_last;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = gtid; r < a.Rpad; r += gthreads) {
+        a.n_pre[r] = 0; a.n_prop[r] = 0; a.rflags[r] = 0u;
+        a.pend_h1[r] = 0; a.pend_h2[r] = 0; a.pend_cnt[r] = 0;
+        a.out_h1[r] = 0; a.out_h2[r] = 0; a.out_len[r] = 0; a.out_ann[r] = 0;
+    }
+    const int32_t S = a.bc->n_slots;
+    for (int64_t sl = gtid; sl < S; sl += gthreads) { a.slot_of[a.slot_subject[sl]] = -1; a.cur[sl] = 0; }
+    if (a.has_wl) {
+        const int n = min(*a.wl.count, a.wl.cap);
+        const int64_t items = (int64_t)n * a.wl.n_tiles;
+        for (int64_t e = gtid; e < items; e += gthreads) {
+            const int32_t sl = a.wl.slots[e / a.wl.n_tiles];
+            const int tile = (int)(e % a.wl.n_tiles);
+            a.wl.in_tile[(size_t)sl * a.wl.n_tiles + tile] = 0;
+            if (tile == 0) a.wl.listed[sl] = 0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&a.bc->ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    BatchCounts c;
+    memset(&c, 0, sizeof(c));
+    c.bad_ring = -1; c.bad_dst = -1; c.seq_down = INT_MAX;
+    volatile BatchCounts* b = a.bc;
+    c.sticky_bad_ring = b->sticky_bad_ring; c.sticky_bad_dst = b->sticky_bad_dst; c.sticky_overflow = b->sticky_overflow;   // errors not collected yet survive a clear()
+    *a.bc = c;
+    *a.snap = c;
+    *a.wl.count = 0;
 }
 
 int32_t bucketed_clear(CD* cd) {
@@ -1690,11 +1719,16 @@ int32_t bucketed_clear(CD* cd) {
         RAPID_CHECK(b->mx_changed.reserve(4));
         RAPID_CUDA(cudaMemsetAsync(b->mx_changed.p, 0, 4 * sizeof(int32_t), s));
     }
-    if (b->in_list_slots) {
-        k_clear_worklist<<<128, 256, 0, s>>>(worklist(b));
-        RAPID_KERNEL_CHECK();
-    }
-    k_reset_counts<<<1, 1, 0, s>>>(cd->counts.p, cd->counts_snap.p, b->wl_count.p);
+    ClearArgs a;
+    a.Rpad = (int64_t)cd->Rpad;
+    a.n_pre = cd->n_pre.p; a.n_prop = cd->n_prop.p; a.rflags = cd->rflags.p;
+    a.pend_h1 = cd->pend_h1.p; a.pend_h2 = cd->pend_h2.p; a.pend_cnt = cd->pend_cnt.p;
+    a.out_h1 = cd->out_h1.p; a.out_h2 = cd->out_h2.p; a.out_len = cd->out_len.p; a.out_ann = cd->out_ann.p;
+    a.bc = cd->counts.p; a.snap = cd->counts_snap.p;
+    a.slot_subject = cd->slot_subject.p; a.slot_of = cd->slot_of.p; a.cur = cd->cur.p;
+    a.wl = worklist(b); a.has_wl = b->in_list_slots ? 1 : 0;
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(ceil_div<size_t>(cd->Rpad, 256), 148 * 8));
+    k_clear_bucketed<<<grid, 256, 0, s>>>(a);
     RAPID_KERNEL_CHECK();
     return RAPID_OK;
 }

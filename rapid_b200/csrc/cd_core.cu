@@ -669,24 +669,23 @@ int32_t rapid_cd_clear(rapid_cd* cd) {
     const size_t R = cd->Rpad;
     if (cd->bucketed) {
         // Bucketed handles never read the state of a slot before the batch that assigns it has written it (slots >= S_before
-        // are write-only), so clear() is O(#slots): forget the dictionary.  The slot count lives on the device — no host
-        // round trip, the whole reset is asynchronous.
-        if (cd->S_cap > 0) {
-            k_reset_slots<<<(unsigned)ceil_div<size_t>(cd->S_cap, 256), 256, 0, s>>>(-1, cd->counts.p, cd->slot_subject.p, cd->slot_of.p, cd->cur.p);
+        // are write-only), so clear() is O(#slots + #receivers): forget the dictionary, reset the receivers' scalars, the work
+        // list and the device counters — ONE launch, no host round trip (the slot count lives on the device).
+        cd->S = 0;
+        RAPID_CHECK(bucketed_clear(cd));
+    } else {
+        if (cd->S > 0) {
+            k_reset_slots<<<(unsigned)ceil_div<int32_t>(cd->S, 256), 256, 0, s>>>(cd->S, cd->counts.p, cd->slot_subject.p, cd->slot_of.p, cd->cur.p);
             RAPID_KERNEL_CHECK();
+            // the sweep kernel reads in place and needs zeros
+            RAPID_CUDA(cudaMemsetAsync(cd->masks.p, 0, (size_t)cd->S * cd->nbuf * cd->Rpad * sizeof(uint16_t), s));
         }
-    } else if (cd->S > 0) {
-        k_reset_slots<<<(unsigned)ceil_div<int32_t>(cd->S, 256), 256, 0, s>>>(cd->S, cd->counts.p, cd->slot_subject.p, cd->slot_of.p, cd->cur.p);
+        cd->S = 0;
+        k_clear_receivers<<<(unsigned)ceil_div<size_t>(R, 256), 256, 0, s>>>((int64_t)R, cd->n_pre.p, cd->n_prop.p, cd->rflags.p, cd->pend_h1.p,
+                                                                            cd->pend_h2.p, cd->pend_cnt.p, cd->out_h1.p, cd->out_h2.p,
+                                                                            cd->out_len.p, cd->out_ann.p);
         RAPID_KERNEL_CHECK();
-        // the sweep kernel reads in place and needs zeros
-        RAPID_CUDA(cudaMemsetAsync(cd->masks.p, 0, (size_t)cd->S * cd->nbuf * cd->Rpad * sizeof(uint16_t), s));
     }
-    cd->S = 0;
-    k_clear_receivers<<<(unsigned)ceil_div<size_t>(R, 256), 256, 0, s>>>((int64_t)R, cd->n_pre.p, cd->n_prop.p, cd->rflags.p, cd->pend_h1.p,
-                                                                        cd->pend_h2.p, cd->pend_cnt.p, cd->out_h1.p, cd->out_h2.p,
-                                                                        cd->out_len.p, cd->out_ann.p);
-    RAPID_KERNEL_CHECK();
-    RAPID_CHECK(bucketed_clear(cd));
     if (cd->bucketed) {
         RAPID_CUDA(cudaMemcpyAsync(cd->h_counts.p, cd->counts_snap.p, sizeof(BatchCounts), cudaMemcpyDeviceToHost, s));
         cd->last_A = 0;

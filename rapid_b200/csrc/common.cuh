@@ -174,12 +174,18 @@ struct View {
     int64_t n = 0;          // members
     int64_t nj = 0;         // registered joiners (ids n .. n+nj-1)
     uint64_t epoch = 1;     // bumped whenever the endpoint -> id dictionary changes (joiners registered, cut applied)
+    uint64_t member_epoch = 1;   // bumped only when the MEMBERS change (a cut was applied): what per-member state hangs off
     cudaStream_t stream = nullptr;
     // endpoints (members then joiners)
     DevBuf<uint8_t> host_bytes;   size_t host_bytes_len = 0;
     DevBuf<int32_t> host_off;     // [n+nj+1]
     DevBuf<int32_t> port;         // [n+nj]
-    std::vector<uint8_t> h_host_bytes;  std::vector<int32_t> h_host_off, h_port;   // host copies (joiner dedupe)
+    // NodeIds (MembershipView.java:58-60 identifiersSeen, :126-128 UUIDAlreadySeenException) — optional (rapid_view_set_node_ids)
+    bool has_node_ids = false;
+    DevBuf<int64_t> node_hi, node_lo;     // [n+nj] NodeId of every endpoint id
+    DevBuf<int64_t> seen_hi, seen_lo;     // [n_seen] identifiersSeen, sorted by signed (high, low); only ever grows
+    int64_t n_seen = 0;
+    void* scratch = nullptr;              // view.cu's sort / scan scratch
     // rings
     DevBuf<int64_t> key;          // [K][ntot_cap]  key of node id on ring k (members + joiners)
     size_t key_stride = 0;        // ntot capacity (row stride of key)

@@ -113,7 +113,7 @@ static inline unsigned grid_for(int64_t n) { return (unsigned)ceil_div<int64_t>(
 
 static int32_t fd_alloc(FD* fd) {
     const View* v = fd->view;
-    fd->n = v->n; fd->K = v->K; fd->view_epoch = v->epoch;
+    fd->n = v->n; fd->K = v->K; fd->view_epoch = v->member_epoch;
     const size_t D = (size_t)std::max<int64_t>(fd->n * fd->K, 1);
     if (fd->n * fd->K > 0x7ffffff0LL) { set_error("more than 2^31 detectors"); return RAPID_EINVAL; }
     RAPID_CHECK(fd->st.reserve(D)); RAPID_CHECK(fd->fired.reserve(D));      // at most every detector fires in one interval
@@ -214,7 +214,7 @@ int32_t rapid_fdet_reset(rapid_fdet* h) {
 int32_t rapid_fdet_tick(rapid_fdet* h, const uint8_t* node_flags, const uint8_t* edge_fail, int64_t cfg_id, int64_t* n_alerts, int64_t* n_cells) {
     rapid_fdet* fd = h;
     if (!fd || (fd->n && !node_flags)) { set_error("bad arguments"); return RAPID_EINVAL; }
-    if (fd->view_epoch != fd->view->epoch || fd->n != fd->view->n) { set_error("the view changed: call rapid_fdet_reset (detectors are re-created per configuration)"); return RAPID_EINVAL; }
+    if (fd->view_epoch != fd->view->member_epoch || fd->n != fd->view->n) { set_error("the view changed: call rapid_fdet_reset (detectors are re-created per configuration)"); return RAPID_EINVAL; }
     DeviceGuard g(fd->device);
     cudaStream_t s = fd->stream;
     RAPID_CUDA(cudaEventRecord(fd->ev0, s));
@@ -229,7 +229,7 @@ int32_t rapid_fdet_tick_dev(rapid_fdet* h, const uint8_t* node_flags_dev, const 
                             int64_t* n_cells) {
     rapid_fdet* fd = h;
     if (!fd || (fd->n && !node_flags_dev)) { set_error("bad arguments"); return RAPID_EINVAL; }
-    if (fd->view_epoch != fd->view->epoch || fd->n != fd->view->n) { set_error("the view changed: call rapid_fdet_reset"); return RAPID_EINVAL; }
+    if (fd->view_epoch != fd->view->member_epoch || fd->n != fd->view->n) { set_error("the view changed: call rapid_fdet_reset"); return RAPID_EINVAL; }
     DeviceGuard g(fd->device);
     cudaStream_t s = fd->stream;
     RAPID_CUDA(cudaEventRecord(fd->ev0, s));

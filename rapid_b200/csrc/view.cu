@@ -5,15 +5,15 @@
 //   observers = ring successors (:234-257), subjects / expected observers = predecessors (:308-322)
 //   configuration id = 37-ary polynomial hash over identifiersSeen then ring-0 order       (:544-556)
 // Not a port: the Java keeps K red-black trees of Endpoint objects with a memoised comparator; here every
-// (ring, node) key is hashed in one kernel, each ring is one radix sort, and the observer/subject relations
+// (ring, node) key is hashed in one kernel, each ring is one radix sort (radix.cuh), and the observer/subject relations
 // become two dense int32 tables that the cut-detection kernels index directly.
-#include <cub/cub.cuh>
-
 #include <algorithm>
 #include <string>
-#include <unordered_map>
+#include <vector>
 
 #include "common.cuh"
+#include "radix.cuh"
+#include "scan.cuh"
 
 namespace rapid {
 
@@ -119,7 +119,7 @@ __global__ void k_config_id(const int64_t* __restrict__ id_high, const int64_t* 
         for (int64_t i = s; i < e; ++i) {
             uint64_t x;
             if (i < 2 * n_ids) {
-                const int32_t j = id_order[i >> 1];
+                const int32_t j = id_order ? id_order[i >> 1] : (int32_t)(i >> 1);
                 x = xxh64_long((i & 1) ? id_low[j] : id_high[j], 0);
             } else {
                 const int64_t q = i - 2 * n_ids;
@@ -157,13 +157,18 @@ __global__ void k_id_sort_keys(const int64_t* __restrict__ v, int64_t n, uint64_
 }
 
 // ------------------------------------------------------------------ host helpers
-static int32_t sort_pairs(DevBuf<uint8_t>& tmp, const uint64_t* kin, uint64_t* kout, const int32_t* vin, int32_t* vout,
-                          int64_t n, cudaStream_t s) {
-    size_t bytes = 0;
-    RAPID_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, 64, s));
-    RAPID_CHECK(tmp.reserve(bytes ? bytes : 1));
-    RAPID_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, 64, s));
-    return RAPID_OK;
+struct ViewScratch {
+    RadixScratch rs;
+    DevBuf<int32_t> scan_sums;
+};
+static ViewScratch* scratch(View* v) {
+    if (!v->scratch) v->scratch = new ViewScratch();
+    return static_cast<ViewScratch*>(v->scratch);
+}
+
+// (keys_in, vals_in) are scratch for the caller: the sort may use them as its ping-pong buffers
+static int32_t sort_pairs(View* v, uint64_t* kin, uint64_t* kout, int32_t* vin, int32_t* vout, int64_t n, cudaStream_t s) {
+    return radix_sort_pairs(scratch(v)->rs, kin, vin, kout, vout, n, 0, 64, s);
 }
 
 static int32_t ensure_total_capacity(View* v, int64_t ntot) {
@@ -185,39 +190,46 @@ static int32_t ensure_total_capacity(View* v, int64_t ntot) {
     return RAPID_OK;
 }
 
-static int32_t upload_endpoints(View* v, int64_t count, const uint8_t* hb, const int32_t* off, const int32_t* port) {
-    // append to host mirrors, then to device
+// Append `count` endpoints after the ones the view holds (members then joiners).  The endpoint table lives on the device only:
+// hostname bytes, offsets and ports are appended in place (no host mirror).  *added_bytes lets a failed caller undo it.
+static int32_t upload_endpoints(View* v, int64_t count, const uint8_t* hb, const int32_t* off, const int32_t* port, size_t* added_bytes = nullptr) {
     const int64_t base = v->n + v->nj;      // v->n must already be set for members (0 during create)
-    const size_t old_bytes = v->h_host_bytes.size();
+    const size_t old_bytes = v->host_bytes_len;
     const size_t add_bytes = count ? (size_t)(off[count] - off[0]) : 0;
-    if (v->h_host_off.empty()) v->h_host_off.push_back(0);
-    v->h_host_bytes.insert(v->h_host_bytes.end(), hb + (count ? off[0] : 0), hb + (count ? off[0] : 0) + add_bytes);
+    std::vector<int32_t> rebased((size_t)count + 1);
+    rebased[0] = (int32_t)old_bytes;
     for (int64_t i = 0; i < count; ++i) {
         const int32_t len = off[i + 1] - off[i];
         if (len < 0) { set_error("host_off must be non-decreasing"); return RAPID_EINVAL; }
-        v->h_host_off.push_back(v->h_host_off.back() + len);
-        v->h_port.push_back(port[i]);
+        rebased[(size_t)i + 1] = rebased[(size_t)i] + len;
     }
-    if (v->h_host_bytes.size() > 0x7fffffffULL) { set_error("hostname bytes exceed 2 GiB"); return RAPID_EINVAL; }
-    RAPID_CHECK(v->host_bytes.reserve(std::max<size_t>(1, v->h_host_bytes.size()), true, v->stream));
+    if (old_bytes + add_bytes > 0x7fffffffULL) { set_error("hostname bytes exceed 2 GiB"); return RAPID_EINVAL; }
+    RAPID_CHECK(v->host_bytes.reserve(std::max<size_t>(1, old_bytes + add_bytes), true, v->stream));
     RAPID_CHECK(v->host_off.reserve((size_t)(base + count + 1), true, v->stream));
     RAPID_CHECK(v->port.reserve(std::max<size_t>(1, (size_t)(base + count)), true, v->stream));
     if (add_bytes)
-        RAPID_CUDA(cudaMemcpyAsync(v->host_bytes.p + old_bytes, v->h_host_bytes.data() + old_bytes, add_bytes,
-                                   cudaMemcpyHostToDevice, v->stream));
-    RAPID_CUDA(cudaMemcpyAsync(v->host_off.p + base, v->h_host_off.data() + base, (size_t)(count + 1) * sizeof(int32_t),
-                               cudaMemcpyHostToDevice, v->stream));
+        RAPID_CUDA(cudaMemcpyAsync(v->host_bytes.p + old_bytes, hb + off[0], add_bytes, cudaMemcpyHostToDevice, v->stream));
+    RAPID_CUDA(cudaMemcpyAsync(v->host_off.p + base, rebased.data(), (size_t)(count + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, v->stream));
     if (count)
-        RAPID_CUDA(cudaMemcpyAsync(v->port.p + base, v->h_port.data() + base, (size_t)count * sizeof(int32_t),
-                                   cudaMemcpyHostToDevice, v->stream));
+        RAPID_CUDA(cudaMemcpyAsync(v->port.p + base, port, (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice, v->stream));
     RAPID_CUDA(cudaStreamSynchronize(v->stream));
+    v->host_bytes_len = old_bytes + add_bytes;
+    if (added_bytes) *added_bytes = add_bytes;
     return RAPID_OK;
 }
 
+// error reporting only: are the endpoints with ids a and b the same (hostname, port)?  Fetched from the device.
 static bool same_endpoint(const View* v, int64_t a, int64_t b) {
-    const int32_t la = v->h_host_off[a + 1] - v->h_host_off[a], lb = v->h_host_off[b + 1] - v->h_host_off[b];
-    return la == lb && v->h_port[a] == v->h_port[b] &&
-           memcmp(v->h_host_bytes.data() + v->h_host_off[a], v->h_host_bytes.data() + v->h_host_off[b], (size_t)la) == 0;
+    int32_t oa[2], ob[2], pa = 0, pb = 0;
+    if (cudaMemcpy(oa, v->host_off.p + a, sizeof(oa), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    if (cudaMemcpy(ob, v->host_off.p + b, sizeof(ob), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    cudaMemcpy(&pa, v->port.p + a, sizeof(pa), cudaMemcpyDeviceToHost);
+    cudaMemcpy(&pb, v->port.p + b, sizeof(pb), cudaMemcpyDeviceToHost);
+    const int32_t la = oa[1] - oa[0], lb = ob[1] - ob[0];
+    if (la != lb || pa != pb) return false;
+    std::vector<uint8_t> ba((size_t)std::max(la, 1)), bb((size_t)std::max(lb, 1));
+    if (la) { cudaMemcpy(ba.data(), v->host_bytes.p + oa[0], (size_t)la, cudaMemcpyDeviceToHost); cudaMemcpy(bb.data(), v->host_bytes.p + ob[0], (size_t)lb, cudaMemcpyDeviceToHost); }
+    return memcmp(ba.data(), bb.data(), (size_t)la) == 0;
 }
 
 static int32_t build_rings(View* v) {
@@ -236,7 +248,6 @@ static int32_t build_rings(View* v) {
     RAPID_KERNEL_CHECK();
     DevBuf<uint64_t> uk_in, uk_out;
     DevBuf<int32_t> id_in, collision;
-    DevBuf<uint8_t> tmp;
     RAPID_CHECK(uk_in.reserve((size_t)n));
     RAPID_CHECK(uk_out.reserve((size_t)n));
     RAPID_CHECK(id_in.reserve((size_t)n));
@@ -245,7 +256,7 @@ static int32_t build_rings(View* v) {
     for (int k = 0; k < K; ++k) {
         k_flip_keys<<<(unsigned)ceil_div<int64_t>(n, TB), TB, 0, s>>>(v->key.p, v->key_stride, k, n, uk_in.p, id_in.p);
         RAPID_KERNEL_CHECK();
-        RAPID_CHECK(sort_pairs(tmp, uk_in.p, uk_out.p, id_in.p, v->ring.p + (size_t)k * n, n, s));
+        RAPID_CHECK(sort_pairs(v, uk_in.p, uk_out.p, id_in.p, v->ring.p + (size_t)k * n, n, s));
         k_unflip_and_check<<<(unsigned)ceil_div<int64_t>(n, TB), TB, 0, s>>>(uk_out.p, n, v->sorted_key.p + (size_t)k * n,
                                                                              collision.p, k);
         RAPID_KERNEL_CHECK();
@@ -311,6 +322,7 @@ int32_t rapid_view_destroy(rapid_view* v) {
     if (!v) return RAPID_OK;
     DeviceGuard g(v->device);
     if (v->stream) cudaStreamDestroy(v->stream);
+    if (v->scratch) { delete static_cast<ViewScratch*>(v->scratch); v->scratch = nullptr; }
     delete v;
     return RAPID_OK;
 }
@@ -406,10 +418,7 @@ static int32_t joiner_rows(rapid_view* v, int64_t first, int64_t count, std::vec
     return RAPID_OK;
 }
 
-static void pop_endpoints(rapid_view* v, int64_t count) {
-    for (int64_t i = 0; i < count; ++i) { v->h_host_off.pop_back(); v->h_port.pop_back(); }
-    v->h_host_bytes.resize((size_t)v->h_host_off.back());
-}
+static void pop_endpoints(rapid_view* v, size_t bytes) { v->host_bytes_len -= bytes; }     // the entries past n + nj are simply forgotten
 
 int32_t rapid_view_register_joiners(rapid_view* v, int64_t n_add, const uint8_t* host_bytes, const int32_t* host_off,
                                     const int32_t* port, int32_t* out_first_id) {
@@ -420,61 +429,376 @@ int32_t rapid_view_register_joiners(rapid_view* v, int64_t n_add, const uint8_t*
     if (n_add == 0) return RAPID_OK;
     if (first + n_add > 0x7ffffff0LL) { set_error("too many endpoints"); return RAPID_EINVAL; }
     RAPID_CHECK(ensure_total_capacity(v, first + n_add));
-    RAPID_CHECK(upload_endpoints(v, n_add, host_bytes, host_off, port));
+    size_t added = 0;
+    RAPID_CHECK(upload_endpoints(v, n_add, host_bytes, host_off, port, &added));
     std::vector<int32_t> flags;
     int32_t rc = joiner_rows(v, first, n_add, flags);
     if (rc == RAPID_OK) {
         for (int64_t j = 0; j < n_add; ++j)
             if (flags[(size_t)j]) { set_error("joiner %lld is already a member", (long long)j); rc = RAPID_EALREADY_IN_RING; break; }
     }
-    if (rc != RAPID_OK) { pop_endpoints(v, n_add); return rc; }
+    if (rc != RAPID_OK) { pop_endpoints(v, added); return rc; }
+    if (v->has_node_ids) {                                   // NodeIds of the new joiners are unknown until rapid_view_set_joiner_ids
+        RAPID_CHECK(v->node_hi.reserve((size_t)(first + n_add), true, v->stream));
+        RAPID_CHECK(v->node_lo.reserve((size_t)(first + n_add), true, v->stream));
+        RAPID_CUDA(cudaMemsetAsync(v->node_hi.p + first, 0, (size_t)n_add * sizeof(int64_t), v->stream));
+        RAPID_CUDA(cudaMemsetAsync(v->node_lo.p + first, 0, (size_t)n_add * sizeof(int64_t), v->stream));
+    }
     v->nj += n_add;
     ++v->epoch;
     return RAPID_OK;
 }
 
+}  // extern "C"
+
+namespace rapid {
+
+// ==================================================================================================================
+// decideViewChange on the device (MembershipService.java:385-444): ringDelete (:167-201) of the members in the cut,
+// ringAdd (:123-160) of the joiners in it, on all K rings — as one order-preserving compaction of every ring plus one
+// sorted merge of the (few) joiners into it; the endpoint table, the per-id keys and the NodeIds are compacted alongside.
+// Nothing visits the host except the cut's ids (in) and two status words (out).
+// ==================================================================================================================
+__global__ void k_cut_mark(const int32_t* __restrict__ cut, int64_t n_cut, int64_t n, int64_t tot, int32_t* __restrict__ incut,
+                           int32_t* __restrict__ err /* [0] = code (1 range, 2 twice), [1] = id */) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cut) return;
+    const int32_t id = cut[i];
+    if (id < 0 || id >= tot) { if (atomicCAS(&err[0], 0, 1) == 0) err[1] = id; return; }
+    if (atomicExch(&incut[id], 1) != 0) { if (atomicCAS(&err[0], 0, 2) == 0) err[1] = id; }
+    (void)n;
+}
+// members stay unless they are in the cut, joiners come in only if they are
+__global__ void k_cut_keep(int64_t n, int64_t tot, const int32_t* __restrict__ incut, const int32_t* __restrict__ off,
+                           int32_t* __restrict__ keep, int32_t* __restrict__ len) {
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= tot) return;
+    const int k = id < n ? (incut[id] ? 0 : 1) : (incut[id] ? 1 : 0);
+    keep[id] = k;
+    len[id] = k ? off[id + 1] - off[id] : 0;
+}
+__global__ void k_cut_endpoints(int64_t tot, const int32_t* __restrict__ keep, const int32_t* __restrict__ newid,
+                                const int32_t* __restrict__ newoff, const int32_t* __restrict__ off, const uint8_t* __restrict__ hb,
+                                const int32_t* __restrict__ port, uint8_t* __restrict__ hb2, int32_t* __restrict__ off2,
+                                int32_t* __restrict__ port2, const int64_t* __restrict__ nhi, const int64_t* __restrict__ nlo,
+                                int64_t* __restrict__ nhi2, int64_t* __restrict__ nlo2, int32_t* __restrict__ map, int32_t total_bytes, int32_t n2) {
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id == 0) off2[n2] = total_bytes;
+    if (id >= tot) return;
+    if (!keep[id]) { map[id] = -1; return; }
+    const int32_t q = newid[id], o = off[id], o2 = newoff[id], l = off[id + 1] - o;
+    map[id] = q;
+    off2[q] = o2;
+    port2[q] = port[id];
+    for (int32_t c = 0; c < l; ++c) hb2[o2 + c] = hb[o + c];
+    if (nhi) { nhi2[q] = nhi[id]; nlo2[q] = nlo[id]; }
+}
+__global__ void k_cut_keys(int K, int64_t tot, size_t stride, size_t stride2, const int32_t* __restrict__ keep,
+                           const int32_t* __restrict__ newid, const int64_t* __restrict__ key, int64_t* __restrict__ key2) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)K * tot) return;
+    const int k = (int)(t / tot);
+    const int64_t id = t % tot;
+    if (keep[id]) key2[(size_t)k * stride2 + newid[id]] = key[(size_t)k * stride + id];
+}
+__global__ void k_cut_ring_flags(int K, int64_t n, const int32_t* __restrict__ ring, const int32_t* __restrict__ keep, int32_t* __restrict__ flag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (int64_t)K * n) flag[t] = keep[ring[t]];
+}
+// the admitted joiners of ring k as (sortable key, new id) pairs
+__global__ void k_cut_joiner_keys(int k, int64_t n, int64_t tot, size_t stride, const int32_t* __restrict__ keep, const int32_t* __restrict__ newid,
+                                  int32_t n_surv, const int64_t* __restrict__ key, uint64_t* __restrict__ jk, int32_t* __restrict__ jv) {
+    const int64_t id = n + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= tot || !keep[id]) return;
+    const int32_t j = newid[id] - n_surv;
+    jk[j] = (uint64_t)key[(size_t)k * stride + id] ^ 0x8000000000000000ULL;
+    jv[j] = newid[id];
+}
+// merge of ring k: survivors keep their order, every joiner slots in by its key (TreeSet order of the new membership)
+__global__ void k_cut_merge(int k, int64_t n, int32_t n_surv, int32_t m, const int32_t* __restrict__ ring, const int64_t* __restrict__ sorted_key,
+                            const int32_t* __restrict__ flag, const int32_t* __restrict__ pos /* exclusive scan of flag over [K][n] */,
+                            const int32_t* __restrict__ newid, const uint64_t* __restrict__ jk, const int32_t* __restrict__ jv,
+                            int32_t* __restrict__ ring2, int64_t* __restrict__ sorted_key2, int32_t* __restrict__ collision) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t* fl = flag + (size_t)k * n;
+    const int32_t* ps = pos + (size_t)k * n;
+    const int64_t* sk = sorted_key + (size_t)k * n;
+    const int32_t base = n ? ps[0] : 0;
+    const int32_t n2 = n_surv + m;
+    if (t < n) {
+        if (!fl[t]) return;
+        const uint64_t u = (uint64_t)sk[t] ^ 0x8000000000000000ULL;
+        int32_t lo = 0, hi = m;                               // joiners with a smaller key
+        while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (jk[mid] < u) lo = mid + 1; else hi = mid; }
+        if (lo < m && jk[lo] == u) atomicCAS(&collision[0], -1, k);
+        const int32_t out = (ps[t] - base) + lo;
+        ring2[(size_t)k * n2 + out] = newid[ring[(size_t)k * n + t]];
+        sorted_key2[(size_t)k * n2 + out] = sk[t];
+    } else if (t < n + m) {
+        const int32_t i = (int32_t)(t - n);
+        const int64_t key = (int64_t)(jk[i] ^ 0x8000000000000000ULL);
+        int64_t lo = 0, hi = n;                               // first old position whose key is >= the joiner's
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sk[mid] < key) lo = mid + 1; else hi = mid; }
+        const int32_t before = n == 0 ? 0 : (lo < n ? ps[lo] - base : ps[n - 1] + fl[n - 1] - base);
+        if (lo < n && sk[lo] == key && fl[lo]) atomicCAS(&collision[0], -1, k);
+        if (i + 1 < m && jk[i + 1] == jk[i]) atomicCAS(&collision[0], -1, k);
+        const int32_t out = before + i;
+        ring2[(size_t)k * n2 + out] = jv[i];
+        sorted_key2[(size_t)k * n2 + out] = key;
+    }
+}
+
+// ---- identifiersSeen (MembershipView.java:58-60, :126-128, :474-500) ---------------------------------------------------------
+__global__ void k_u64_flip(const int64_t* __restrict__ v, const int32_t* __restrict__ order, int64_t n, uint64_t* __restrict__ out, int32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t j = order ? order[i] : (int32_t)i;
+    out[i] = (uint64_t)v[j] ^ 0x8000000000000000ULL;
+    idx[i] = j;
+}
+__global__ void k_gather_ids(const int64_t* __restrict__ hi, const int64_t* __restrict__ lo, const int32_t* __restrict__ order, int64_t n,
+                             int64_t* __restrict__ hi2, int64_t* __restrict__ lo2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { hi2[i] = hi[order[i]]; lo2[i] = lo[order[i]]; }
+}
+__global__ void k_ids_adjacent_equal(const int64_t* __restrict__ hi, const int64_t* __restrict__ lo, int64_t n, int32_t* __restrict__ found) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 < n && hi[i] == hi[i + 1] && lo[i] == lo[i + 1]) atomicCAS(found, -1, (int32_t)i);
+}
+
+// sorts n (hi, lo) pairs by signed (hi, lo) into (hi2, lo2): LSD — stable sort by low, then by high
+static int32_t sort_node_ids(View* v, const int64_t* hi, const int64_t* lo, int64_t n, int64_t* hi2, int64_t* lo2) {
+    if (n <= 0) return RAPID_OK;
+    cudaStream_t s = v->stream;
+    const int TB = 256;
+    const unsigned gb = (unsigned)ceil_div<int64_t>(n, TB);
+    DevBuf<uint64_t> k_in, k_out;
+    DevBuf<int32_t> i_in, i_mid, order;
+    RAPID_CHECK(k_in.reserve((size_t)n)); RAPID_CHECK(k_out.reserve((size_t)n));
+    RAPID_CHECK(i_in.reserve((size_t)n)); RAPID_CHECK(i_mid.reserve((size_t)n)); RAPID_CHECK(order.reserve((size_t)n));
+    k_u64_flip<<<gb, TB, 0, s>>>(lo, nullptr, n, k_in.p, i_in.p);
+    RAPID_KERNEL_CHECK();
+    RAPID_CHECK(sort_pairs(v, k_in.p, k_out.p, i_in.p, i_mid.p, n, s));
+    k_u64_flip<<<gb, TB, 0, s>>>(hi, i_mid.p, n, k_in.p, i_in.p);
+    RAPID_KERNEL_CHECK();
+    RAPID_CHECK(sort_pairs(v, k_in.p, k_out.p, i_in.p, order.p, n, s));
+    k_gather_ids<<<gb, TB, 0, s>>>(hi, lo, order.p, n, hi2, lo2);
+    RAPID_KERNEL_CHECK();
+    RAPID_CUDA(cudaStreamSynchronize(s));                    // the scratch buffers go out of scope
+    return RAPID_OK;
+}
+
+// identifiersSeen := sorted(identifiersSeen ++ add);  RAPID_EUUID_SEEN (nothing changed) if that contains a NodeId twice
+static int32_t seen_add(View* v, const int64_t* add_hi_dev, const int64_t* add_lo_dev, int64_t n_add) {
+    if (n_add <= 0) return RAPID_OK;
+    cudaStream_t s = v->stream;
+    const int64_t tot = v->n_seen + n_add;
+    DevBuf<int64_t> ch, cl, sh, sl;
+    DevBuf<int32_t> found;
+    RAPID_CHECK(ch.reserve((size_t)tot)); RAPID_CHECK(cl.reserve((size_t)tot)); RAPID_CHECK(sh.reserve((size_t)tot)); RAPID_CHECK(sl.reserve((size_t)tot));
+    RAPID_CHECK(found.reserve(1));
+    if (v->n_seen) {
+        RAPID_CUDA(cudaMemcpyAsync(ch.p, v->seen_hi.p, (size_t)v->n_seen * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+        RAPID_CUDA(cudaMemcpyAsync(cl.p, v->seen_lo.p, (size_t)v->n_seen * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    }
+    RAPID_CUDA(cudaMemcpyAsync(ch.p + v->n_seen, add_hi_dev, (size_t)n_add * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    RAPID_CUDA(cudaMemcpyAsync(cl.p + v->n_seen, add_lo_dev, (size_t)n_add * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    RAPID_CHECK(sort_node_ids(v, ch.p, cl.p, tot, sh.p, sl.p));
+    RAPID_CUDA(cudaMemsetAsync(found.p, 0xff, sizeof(int32_t), s));
+    k_ids_adjacent_equal<<<(unsigned)ceil_div<int64_t>(tot, 256), 256, 0, s>>>(sh.p, sl.p, tot, found.p);
+    RAPID_KERNEL_CHECK();
+    int32_t f = -1;
+    RAPID_CUDA(cudaMemcpyAsync(&f, found.p, sizeof(f), cudaMemcpyDeviceToHost, s));
+    RAPID_CUDA(cudaStreamSynchronize(s));
+    if (f >= 0) { set_error("a NodeId was seen before (UUIDAlreadySeenException)"); return RAPID_EUUID_SEEN; }
+    std::swap(v->seen_hi.p, sh.p); std::swap(v->seen_hi.cap, sh.cap);
+    std::swap(v->seen_lo.p, sl.p); std::swap(v->seen_lo.cap, sl.cap);
+    v->n_seen = tot;
+    return RAPID_OK;
+}
+
+template <typename T>
+static void swap_buf(DevBuf<T>& a, DevBuf<T>& b) { std::swap(a.p, b.p); std::swap(a.cap, b.cap); }
+
+static int32_t apply_cut_device(View* v, const int32_t* cut_ids, int64_t n_cut, int32_t* out_old_to_new) {
+    cudaStream_t s = v->stream;
+    const int K = v->K, TB = 256;
+    const int64_t n = v->n, tot = v->n + v->nj;
+    ViewScratch* sc = scratch(v);
+    DevBuf<int32_t> d_cut, incut, keep, len, err, map, flag, jv, jv2, collision, totals;
+    DevBuf<uint64_t> jk, jk2;
+    const size_t t1 = (size_t)std::max<int64_t>(tot, 1);
+    RAPID_CHECK(d_cut.reserve((size_t)std::max<int64_t>(n_cut, 1))); RAPID_CHECK(incut.reserve(t1)); RAPID_CHECK(keep.reserve(t1 + 1));
+    RAPID_CHECK(len.reserve(t1 + 1)); RAPID_CHECK(err.reserve(2)); RAPID_CHECK(map.reserve(t1)); RAPID_CHECK(totals.reserve(2));
+    RAPID_CHECK(collision.reserve(1));
+    RAPID_CUDA(cudaMemsetAsync(incut.p, 0, t1 * sizeof(int32_t), s));
+    RAPID_CUDA(cudaMemsetAsync(err.p, 0, 2 * sizeof(int32_t), s));
+    if (n_cut) {
+        RAPID_CUDA(cudaMemcpyAsync(d_cut.p, cut_ids, (size_t)n_cut * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        k_cut_mark<<<(unsigned)ceil_div<int64_t>(n_cut, TB), TB, 0, s>>>(d_cut.p, n_cut, n, tot, incut.p, err.p);
+        RAPID_KERNEL_CHECK();
+    }
+    if (tot) {
+        k_cut_keep<<<(unsigned)ceil_div<int64_t>(tot, TB), TB, 0, s>>>(n, tot, incut.p, v->host_off.p, keep.p, len.p);
+        RAPID_KERNEL_CHECK();
+    }
+    // keep -> new ids, len -> new byte offsets (exclusive scans in place; totals on the device)
+    RAPID_CHECK(exclusive_scan_i32(keep.p, tot, sc->scan_sums, totals.p, s, nullptr));
+    RAPID_CHECK(exclusive_scan_i32(len.p, tot, sc->scan_sums, totals.p + 1, s, nullptr));
+    int32_t h_err[2] = {0, 0}, h_tot[2] = {0, 0}, n_surv = 0;
+    RAPID_CUDA(cudaMemcpyAsync(h_err, err.p, sizeof(h_err), cudaMemcpyDeviceToHost, s));
+    RAPID_CUDA(cudaMemcpyAsync(h_tot, totals.p, sizeof(h_tot), cudaMemcpyDeviceToHost, s));
+    if (n < tot) RAPID_CUDA(cudaMemcpyAsync(&n_surv, keep.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, s));   // members that stay = new id of the first joiner
+    RAPID_CUDA(cudaStreamSynchronize(s));
+    if (h_err[0] == 1) { set_error("cut id %d outside [0, members + joiners)", h_err[1]); return RAPID_EINVAL; }
+    if (h_err[0] == 2) {
+        set_error("cut names node %d twice", h_err[1]);
+        return h_err[1] < n ? RAPID_ENOT_IN_RING : RAPID_EALREADY_IN_RING;      // second ringDelete / ringAdd would throw
+    }
+    const int32_t n2 = h_tot[0], bytes2 = h_tot[1];
+    if (n == tot) n_surv = n2;
+    const int32_t m = n2 - n_surv;                                              // joiners admitted
+    // `keep` now holds the new ids; the kept flags are recovered from incut (k_cut_keep's rule) where needed: recompute
+    DevBuf<int32_t> kept;
+    RAPID_CHECK(kept.reserve(t1));
+    if (tot) { k_cut_keep<<<(unsigned)ceil_div<int64_t>(tot, TB), TB, 0, s>>>(n, tot, incut.p, v->host_off.p, kept.p, map.p /*scratch*/); RAPID_KERNEL_CHECK(); }
+    // ---- UUID rule for the joiners that come in (:126-128), before anything is modified ---------------------------------------
+    DevBuf<int64_t> nhi2, nlo2;
+    // ---- new endpoint table, keys, NodeIds -------------------------------------------------------------------------------------
+    DevBuf<uint8_t> hb2;
+    DevBuf<int32_t> off2, port2, ring2;
+    DevBuf<int64_t> key2, sk2;
+    const size_t n2s = (size_t)std::max(n2, 1);
+    size_t stride2 = 1;
+    while (stride2 < n2s) stride2 *= 2;
+    RAPID_CHECK(hb2.reserve((size_t)std::max(bytes2, 1))); RAPID_CHECK(off2.reserve(n2s + 1)); RAPID_CHECK(port2.reserve(n2s));
+    RAPID_CHECK(key2.reserve(stride2 * (size_t)K)); RAPID_CHECK(ring2.reserve(n2s * (size_t)K)); RAPID_CHECK(sk2.reserve(n2s * (size_t)K));
+    if (v->has_node_ids) { RAPID_CHECK(nhi2.reserve(n2s)); RAPID_CHECK(nlo2.reserve(n2s)); }
+    k_cut_endpoints<<<(unsigned)ceil_div<int64_t>(std::max<int64_t>(tot, 1), TB), TB, 0, s>>>(
+        tot, kept.p, keep.p, len.p, v->host_off.p, v->host_bytes.p, v->port.p, hb2.p, off2.p, port2.p,
+        v->has_node_ids ? v->node_hi.p : nullptr, v->has_node_ids ? v->node_lo.p : nullptr, nhi2.p, nlo2.p, map.p, bytes2, n2);
+    RAPID_KERNEL_CHECK();
+    if (tot) {
+        k_cut_keys<<<(unsigned)ceil_div<int64_t>((int64_t)K * tot, TB), TB, 0, s>>>(K, tot, v->key_stride, stride2, kept.p, keep.p, v->key.p, key2.p);
+        RAPID_KERNEL_CHECK();
+    }
+    if (v->has_node_ids && m > 0) {
+        // the joiners' NodeIds are the last m entries of the new NodeId arrays (joiners follow the surviving members)
+        const int32_t rc = seen_add(v, nhi2.p + n_surv, nlo2.p + n_surv, m);
+        if (rc != RAPID_OK) return rc;                                           // UUIDAlreadySeenException: the view is unchanged
+    }
+    // ---- rings -----------------------------------------------------------------------------------------------------------------
+    RAPID_CUDA(cudaMemsetAsync(collision.p, 0xff, sizeof(int32_t), s));
+    if (n > 0) {
+        RAPID_CHECK(flag.reserve((size_t)K * n));
+        DevBuf<int32_t> pos;
+        RAPID_CHECK(pos.reserve((size_t)K * n));
+        k_cut_ring_flags<<<(unsigned)ceil_div<int64_t>((int64_t)K * n, TB), TB, 0, s>>>(K, n, v->ring.p, kept.p, flag.p);
+        RAPID_KERNEL_CHECK();
+        RAPID_CUDA(cudaMemcpyAsync(pos.p, flag.p, (size_t)K * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        RAPID_CHECK(exclusive_scan_i32(pos.p, (int64_t)K * n, sc->scan_sums, nullptr, s, nullptr));
+        RAPID_CHECK(jk.reserve((size_t)std::max(m, 1))); RAPID_CHECK(jk2.reserve((size_t)std::max(m, 1)));
+        RAPID_CHECK(jv.reserve((size_t)std::max(m, 1))); RAPID_CHECK(jv2.reserve((size_t)std::max(m, 1)));
+        for (int k = 0; k < K; ++k) {
+            if (m > 0) {
+                k_cut_joiner_keys<<<(unsigned)ceil_div<int64_t>(tot - n, TB), TB, 0, s>>>(k, n, tot, v->key_stride, kept.p, keep.p, n_surv, v->key.p, jk.p, jv.p);
+                RAPID_KERNEL_CHECK();
+                RAPID_CHECK(sort_pairs(v, jk.p, jk2.p, jv.p, jv2.p, m, s));
+            }
+            k_cut_merge<<<(unsigned)ceil_div<int64_t>(n + m, TB), TB, 0, s>>>(k, n, n_surv, m, v->ring.p, v->sorted_key.p, flag.p, pos.p, keep.p,
+                                                                             jk2.p, jv2.p, ring2.p, sk2.p, collision.p);
+            RAPID_KERNEL_CHECK();
+        }
+        int32_t coll = -1;
+        RAPID_CUDA(cudaMemcpyAsync(&coll, collision.p, sizeof(coll), cudaMemcpyDeviceToHost, s));
+        RAPID_CUDA(cudaStreamSynchronize(s));
+        if (coll >= 0) { set_error("ring-%d key collision while adding joiners (TreeSet would silently drop one)", coll); return RAPID_EHASH_COLLISION; }
+    } else if (m > 0) {
+        // no members before: the rings are just the sorted joiners
+        RAPID_CHECK(jk.reserve((size_t)m)); RAPID_CHECK(jk2.reserve((size_t)m)); RAPID_CHECK(jv.reserve((size_t)m)); RAPID_CHECK(jv2.reserve((size_t)m));
+        DevBuf<int32_t> noflag, nopos;
+        RAPID_CHECK(noflag.reserve(1)); RAPID_CHECK(nopos.reserve(1));
+        for (int k = 0; k < K; ++k) {
+            k_cut_joiner_keys<<<(unsigned)ceil_div<int64_t>(tot - n, TB), TB, 0, s>>>(k, n, tot, v->key_stride, kept.p, keep.p, n_surv, v->key.p, jk.p, jv.p);
+            RAPID_CHECK(sort_pairs(v, jk.p, jk2.p, jv.p, jv2.p, m, s));
+            k_cut_merge<<<(unsigned)ceil_div<int64_t>(m, TB), TB, 0, s>>>(k, 0, 0, m, v->ring.p, v->sorted_key.p, noflag.p, nopos.p, keep.p, jk2.p, jv2.p,
+                                                                         ring2.p, sk2.p, collision.p);
+            RAPID_KERNEL_CHECK();
+        }
+        int32_t coll = -1;
+        RAPID_CUDA(cudaMemcpyAsync(&coll, collision.p, sizeof(coll), cudaMemcpyDeviceToHost, s));
+        RAPID_CUDA(cudaStreamSynchronize(s));
+        if (coll >= 0) { set_error("ring-%d key collision among the joiners", coll); return RAPID_EHASH_COLLISION; }
+    }
+    if (out_old_to_new && tot) RAPID_CUDA(cudaMemcpyAsync(out_old_to_new, map.p, (size_t)tot * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    // ---- swap in ------------------------------------------------------------------------------------------------------------------
+    RAPID_CUDA(cudaStreamSynchronize(s));
+    swap_buf(v->host_bytes, hb2); swap_buf(v->host_off, off2); swap_buf(v->port, port2);
+    swap_buf(v->key, key2); swap_buf(v->ring, ring2); swap_buf(v->sorted_key, sk2);
+    if (v->has_node_ids) { swap_buf(v->node_hi, nhi2); swap_buf(v->node_lo, nlo2); }
+    v->key_stride = stride2;
+    v->host_bytes_len = (size_t)bytes2;
+    v->n = n2; v->nj = 0;
+    ++v->epoch; ++v->member_epoch;
+    RAPID_CHECK(v->obs.reserve(stride2 * (size_t)K));
+    RAPID_CHECK(v->subj.reserve(n2s * (size_t)K));
+    RAPID_CHECK(v->pos0.reserve(n2s));
+    if (n2 > 0) {
+        k_tables<<<(unsigned)ceil_div<int64_t>((int64_t)n2 * K, TB), TB, 0, s>>>(v->ring.p, n2, K, v->obs.p, v->subj.p, v->pos0.p);
+        RAPID_KERNEL_CHECK();
+    }
+    RAPID_CUDA(cudaStreamSynchronize(s));
+    return RAPID_OK;
+}
+
+}  // namespace rapid
+
+extern "C" {
+
 // decideViewChange (MembershipService.java:385-444): every node of the decided cut that is a member leaves (ringDelete,
 // MembershipView.java:167-201), every other one — a registered joiner — is added (ringAdd, :123-160).  The K rings are
-// rebuilt on the device from the surviving endpoints (hash + radix sort + tables); ids are renumbered densely: surviving
-// members keep their relative order, the admitted joiners follow in id order, joiners not in the cut are dropped.
+// UPDATED on the device (order-preserving compaction + sorted merge of the joiners, no re-hash, no re-sort of the members);
+// ids are renumbered densely: surviving members keep their relative order, the admitted joiners follow in id order, joiners
+// not in the cut are dropped.  With NodeIds set (rapid_view_set_node_ids) a joiner whose NodeId is already in
+// identifiersSeen is refused (UUIDAlreadySeenException :126-128) and nothing changes.
 int32_t rapid_view_apply_cut(rapid_view* v, const int32_t* cut_ids, int64_t n_cut, int32_t* out_old_to_new) {
     if (!v || n_cut < 0 || (n_cut && !cut_ids)) { set_error("bad arguments"); return RAPID_EINVAL; }
     DeviceGuard g(v->device);
+    return apply_cut_device(v, cut_ids, n_cut, out_old_to_new);
+}
+
+// NodeIds of the current members (index = node id): seeds identifiersSeen.  RAPID_EUUID_SEEN if two members share one.
+int32_t rapid_view_set_node_ids(rapid_view* v, const int64_t* id_high, const int64_t* id_low) {
+    if (!v || (v->n && (!id_high || !id_low))) { set_error("bad arguments"); return RAPID_EINVAL; }
+    DeviceGuard g(v->device);
     const int64_t tot = v->n + v->nj;
-    std::vector<uint8_t> in_cut((size_t)tot, 0);
-    for (int64_t i = 0; i < n_cut; ++i) {
-        const int32_t id = cut_ids[i];
-        if (id < 0 || id >= tot) { set_error("cut id %d outside [0, members + joiners)", id); return RAPID_EINVAL; }
-        if (in_cut[(size_t)id]) {
-            set_error("cut names node %d twice", id);
-            return id < v->n ? RAPID_ENOT_IN_RING : RAPID_EALREADY_IN_RING;      // second ringDelete / ringAdd would throw
-        }
-        in_cut[(size_t)id] = 1;
+    RAPID_CHECK(v->node_hi.reserve((size_t)std::max<int64_t>(tot, 1))); RAPID_CHECK(v->node_lo.reserve((size_t)std::max<int64_t>(tot, 1)));
+    RAPID_CUDA(cudaMemsetAsync(v->node_hi.p, 0, (size_t)std::max<int64_t>(tot, 1) * sizeof(int64_t), v->stream));
+    RAPID_CUDA(cudaMemsetAsync(v->node_lo.p, 0, (size_t)std::max<int64_t>(tot, 1) * sizeof(int64_t), v->stream));
+    if (v->n) {
+        RAPID_CUDA(cudaMemcpyAsync(v->node_hi.p, id_high, (size_t)v->n * sizeof(int64_t), cudaMemcpyHostToDevice, v->stream));
+        RAPID_CUDA(cudaMemcpyAsync(v->node_lo.p, id_low, (size_t)v->n * sizeof(int64_t), cudaMemcpyHostToDevice, v->stream));
     }
-    std::vector<uint8_t> hb;
-    std::vector<int32_t> off(1, 0), port;
-    std::vector<int32_t> map((size_t)tot, -1);
-    hb.reserve(v->h_host_bytes.size());
-    int32_t next = 0;
-    for (int64_t id = 0; id < tot; ++id) {
-        const bool keep = id < v->n ? !in_cut[(size_t)id] : in_cut[(size_t)id];
-        if (!keep) continue;
-        const int32_t o = v->h_host_off[(size_t)id], len = v->h_host_off[(size_t)id + 1] - o;
-        hb.insert(hb.end(), v->h_host_bytes.begin() + o, v->h_host_bytes.begin() + o + len);
-        off.push_back(off.back() + len);
-        port.push_back(v->h_port[(size_t)id]);
-        map[(size_t)id] = next++;
+    RAPID_CUDA(cudaStreamSynchronize(v->stream));
+    v->n_seen = 0;
+    const int32_t rc = seen_add(v, v->node_hi.p, v->node_lo.p, v->n);
+    if (rc != RAPID_OK) return rc;
+    v->has_node_ids = true;
+    return RAPID_OK;
+}
+
+// NodeIds of registered joiners [first_joiner_id, first_joiner_id + count) (AlertMessage.nodeId of their UP alerts,
+// MembershipService.java:677-685); checked against identifiersSeen when a cut admits them.
+int32_t rapid_view_set_joiner_ids(rapid_view* v, int32_t first_joiner_id, int64_t count, const int64_t* id_high, const int64_t* id_low) {
+    if (!v || count < 0 || (count && (!id_high || !id_low))) { set_error("bad arguments"); return RAPID_EINVAL; }
+    if (!v->has_node_ids) { set_error("rapid_view_set_node_ids first"); return RAPID_EINVAL; }
+    if (first_joiner_id < v->n || (int64_t)first_joiner_id + count > v->n + v->nj) { set_error("not registered joiners"); return RAPID_EINVAL; }
+    DeviceGuard g(v->device);
+    if (count) {
+        RAPID_CUDA(cudaMemcpyAsync(v->node_hi.p + first_joiner_id, id_high, (size_t)count * sizeof(int64_t), cudaMemcpyHostToDevice, v->stream));
+        RAPID_CUDA(cudaMemcpyAsync(v->node_lo.p + first_joiner_id, id_low, (size_t)count * sizeof(int64_t), cudaMemcpyHostToDevice, v->stream));
+        RAPID_CUDA(cudaStreamSynchronize(v->stream));
     }
-    // swap in the new endpoint list and rebuild
-    v->h_host_bytes.clear(); v->h_host_off.clear(); v->h_port.clear();
-    v->n = 0; v->nj = 0;
-    static const uint8_t dummy = 0;
-    static const int32_t zero_off[1] = {0};
-    RAPID_CHECK(upload_endpoints(v, next, next ? hb.data() : &dummy, next ? off.data() : zero_off, port.data()));
-    v->n = next;
-    ++v->epoch;
-    RAPID_CHECK(build_rings(v));
-    if (out_old_to_new) memcpy(out_old_to_new, map.data(), (size_t)tot * sizeof(int32_t));
     return RAPID_OK;
 }
 
@@ -488,49 +812,28 @@ int32_t rapid_view_expected_observers(const rapid_view* cv, const uint8_t* host,
     RAPID_CHECK(ensure_total_capacity(v, first + 1));
     const int32_t off[2] = {0, len};
     static const uint8_t dummy = 0;
-    RAPID_CHECK(upload_endpoints(v, 1, len ? host : &dummy, off, &port));
+    size_t added = 0;
+    RAPID_CHECK(upload_endpoints(v, 1, len ? host : &dummy, off, &port, &added));
     std::vector<int32_t> flags;
     int32_t rc = joiner_rows(v, first, 1, flags);
     if (rc == RAPID_OK) {
         cudaError_t e = cudaMemcpy(out, v->obs.p + (size_t)first * v->K, (size_t)v->K * sizeof(int32_t), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = cuda_fail(e, "copy", __FILE__, __LINE__);
     }
-    pop_endpoints(v, 1);
+    pop_endpoints(v, added);
     if (rc == RAPID_OK) *out_count = v->K;
     return rc;
 }
 
-int32_t rapid_view_config_id(const rapid_view* v, const int64_t* id_high, const int64_t* id_low, int64_t n_ids, int64_t* out) {
-    if (!v || !out || n_ids < 0 || (n_ids && (!id_high || !id_low))) { set_error("bad arguments"); return RAPID_EINVAL; }
-    DeviceGuard g(v->device);
+static int32_t config_id_from(rapid_view* v, const int64_t* hi_sorted_dev, const int64_t* lo_sorted_dev, int64_t n_ids, int64_t* out) {
     cudaStream_t s = v->stream;
     const int TB = 256;
-    DevBuf<int64_t> dh, dl;
-    DevBuf<uint64_t> k_in, k_out;
-    DevBuf<int32_t> i_in, i_mid, order;
-    DevBuf<uint8_t> tmp;
     DevBuf<unsigned long long> acc;
-    const size_t m = std::max<int64_t>(1, n_ids);
-    RAPID_CHECK(dh.reserve(m)); RAPID_CHECK(dl.reserve(m));
-    RAPID_CHECK(k_in.reserve(m)); RAPID_CHECK(k_out.reserve(m));
-    RAPID_CHECK(i_in.reserve(m)); RAPID_CHECK(i_mid.reserve(m)); RAPID_CHECK(order.reserve(m));
     RAPID_CHECK(acc.reserve(1));
-    if (n_ids) {
-        RAPID_CUDA(cudaMemcpyAsync(dh.p, id_high, (size_t)n_ids * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-        RAPID_CUDA(cudaMemcpyAsync(dl.p, id_low, (size_t)n_ids * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-        // NodeIdComparator (:474-500): signed (high, low).  LSD: stable sort by low, then by high.
-        const unsigned gb = (unsigned)ceil_div<int64_t>(n_ids, TB);
-        k_id_sort_keys<<<gb, TB, 0, s>>>(dl.p, n_ids, k_in.p, i_in.p, nullptr);
-        RAPID_KERNEL_CHECK();
-        RAPID_CHECK(sort_pairs(tmp, k_in.p, k_out.p, i_in.p, i_mid.p, n_ids, s));
-        k_id_sort_keys<<<gb, TB, 0, s>>>(dh.p, n_ids, k_in.p, i_in.p, i_mid.p);
-        RAPID_KERNEL_CHECK();
-        RAPID_CHECK(sort_pairs(tmp, k_in.p, k_out.p, i_in.p, order.p, n_ids, s));
-    }
     RAPID_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(unsigned long long), s));
     const int64_t M = 2 * n_ids + 2 * v->n;
     const int64_t threads = std::max<int64_t>(1, ceil_div<int64_t>(M, 32));
-    k_config_id<<<(unsigned)ceil_div<int64_t>(threads, TB), TB, 0, s>>>(dh.p, dl.p, order.p, n_ids, v->host_bytes.p, v->host_off.p,
+    k_config_id<<<(unsigned)ceil_div<int64_t>(threads, TB), TB, 0, s>>>(hi_sorted_dev, lo_sorted_dev, nullptr, n_ids, v->host_bytes.p, v->host_off.p,
                                                                         v->port.p, v->ring.p, v->n, acc.p);
     RAPID_KERNEL_CHECK();
     unsigned long long h = 0;
@@ -538,6 +841,33 @@ int32_t rapid_view_config_id(const rapid_view* v, const int64_t* id_high, const 
     RAPID_CUDA(cudaStreamSynchronize(s));
     *out = (int64_t)h;
     return RAPID_OK;
+}
+
+// Configuration.getConfigurationId (:544-556) over caller-supplied identifiers (any order: sorted here by signed (high, low))
+int32_t rapid_view_config_id(const rapid_view* cv, const int64_t* id_high, const int64_t* id_low, int64_t n_ids, int64_t* out) {
+    rapid_view* v = const_cast<rapid_view*>(cv);
+    if (!v || !out || n_ids < 0 || (n_ids && (!id_high || !id_low))) { set_error("bad arguments"); return RAPID_EINVAL; }
+    DeviceGuard g(v->device);
+    cudaStream_t s = v->stream;
+    DevBuf<int64_t> dh, dl, sh, sl;
+    const size_t m = (size_t)std::max<int64_t>(1, n_ids);
+    RAPID_CHECK(dh.reserve(m)); RAPID_CHECK(dl.reserve(m)); RAPID_CHECK(sh.reserve(m)); RAPID_CHECK(sl.reserve(m));
+    if (n_ids) {
+        RAPID_CUDA(cudaMemcpyAsync(dh.p, id_high, (size_t)n_ids * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        RAPID_CUDA(cudaMemcpyAsync(dl.p, id_low, (size_t)n_ids * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        RAPID_CHECK(sort_node_ids(v, dh.p, dl.p, n_ids, sh.p, sl.p));       // NodeIdComparator (:474-500): signed (high, low)
+    }
+    return config_id_from(v, sh.p, sl.p, n_ids, out);
+}
+
+// getCurrentConfigurationId (:360-372) from the view's OWN identifiersSeen (rapid_view_set_node_ids; grows with every admitted
+// joiner, never shrinks — ids of removed nodes stay, :167-201) and its ring 0: nothing but the 8-byte result leaves the device.
+int32_t rapid_view_current_config_id(const rapid_view* cv, int64_t* out) {
+    rapid_view* v = const_cast<rapid_view*>(cv);
+    if (!v || !out) { set_error("bad arguments"); return RAPID_EINVAL; }
+    if (!v->has_node_ids) { set_error("rapid_view_set_node_ids first"); return RAPID_EINVAL; }
+    DeviceGuard g(v->device);
+    return config_id_from(v, v->seen_hi.p, v->seen_lo.p, v->n_seen, out);
 }
 
 }  // extern "C"

@@ -104,6 +104,21 @@ class MembershipView:
         N.check(N.lib().rapid_view_config_id(self._h, N.ptr(hi), N.ptr(lo), len(hi), C.byref(out)))
         return out.value
 
+    def setNodeIds(self, id_high, id_low):
+        """NodeIds of the current members (index = node id): identifiersSeen on the device (MembershipView.java:58-60)."""
+        hi, lo = N.as_i64(id_high), N.as_i64(id_low)
+        assert len(hi) == self.n and len(lo) == self.n
+        N.check(N.lib().rapid_view_set_node_ids(self._h, N.ptr(hi), N.ptr(lo)))
+
+    def setJoinerIds(self, first_joiner_id, id_high, id_low):
+        hi, lo = N.as_i64(id_high), N.as_i64(id_low)
+        N.check(N.lib().rapid_view_set_joiner_ids(self._h, int(first_joiner_id), len(hi), N.ptr(hi), N.ptr(lo)))
+
+    def currentConfigurationId(self):                              # :360-372 from the device-resident identifiersSeen
+        out = C.c_int64(0)
+        N.check(N.lib().rapid_view_current_config_id(self._h, C.byref(out)))
+        return out.value
+
     def registerJoiners(self, hostnames, ports):
         """ids for endpoints that UP alerts will name (the edgeDst of a join)."""
         hb, off = N.pack_hostnames(hostnames)
@@ -114,7 +129,8 @@ class MembershipView:
 
     def applyCut(self, cut_ids):
         """decideViewChange (MembershipService.java:385-444): members in the cut leave, registered joiners in it are added;
-        rings rebuilt on the device.  Returns old id -> new id (-1 = gone); detector handles on the old view are stale."""
+        the K rings are updated on the device (compaction + sorted merge).  Returns old id -> new id (-1 = gone); detector handles
+        on the old view are stale.  Raises UUIDAlreadySeenException (view unchanged) if NodeIds are set and a joiner's was seen."""
         ids = N.as_i32(cut_ids)
         tot = self.n + self.numJoiners()
         mapping = np.empty(max(tot, 1), np.int32)

@@ -148,3 +148,104 @@ def test_apply_cut_matches_ring_delete_and_add(orc, rb):
     b = W.c2_simultaneous_crash(obs, v.n, 0.01)
     res = cl.handleBatch(5, b.src, b.dst, b.ring, b.status)
     assert set(res.proposal_len.tolist()) == {len(b.expected_cut)}
+
+
+def test_apply_cut_with_node_ids_uuid_rule_and_device_config_id(orc, rb):
+    """identifiersSeen lives on the device: an admitted joiner's NodeId joins it, the ids of the departed stay
+    (MembershipView.java:167-201), a NodeId seen before is refused (UUIDAlreadySeenException, :126-128) and leaves the view
+    untouched; getCurrentConfigurationId comes from that set without the caller handing identifiers in."""
+    n, nj = 700, 40
+    w = OracleWorld(orc, n, K, n_joiners=nj)
+    v = rb.MembershipView.from_packed(K, *w.member_packed())
+    v.setNodeIds(w.id_high, w.id_low)
+    assert v.currentConfigurationId() == w.view.getCurrentConfigurationId()
+    first = v.registerJoiners(*w.joiner_endpoints())[0]
+    hi, lo = W.node_ids(n, nj)
+    v.setJoinerIds(first, hi, lo)
+    rng = np.random.default_rng(21)
+    ever = set()                                          # joiners admitted at some point: their NodeIds are used up
+    for round_ in range(3):
+        members = v.getMembershipSize()
+        tot = members + v.numJoiners()
+        # ids are renumbered after every cut: keep the oracle's tags alongside
+        if round_ == 0:
+            tag_of = list(range(n + nj))                    # device id -> oracle tag
+        leave = sorted(rng.choice(members, size=11, replace=False).tolist())
+        joiners = list(range(members, tot))
+        join = sorted(rng.choice(joiners, size=min(6, len(joiners)), replace=False).tolist()) if joiners else []
+        mapping = v.applyCut(leave + join)
+        for x in leave:
+            w.view.ringDelete(tag_of[x])
+        for x in join:
+            t = tag_of[x]
+            w.view.ringAdd(t, (int(hi[t - n]), int(lo[t - n])))
+            ever.add(t)
+        new_tag = [None] * v.getMembershipSize()
+        for old, new in enumerate(mapping.tolist()):
+            if new >= 0:
+                new_tag[new] = tag_of[old]
+        tag_of = new_tag
+        assert v.getMembershipSize() == w.view.getMembershipSize()
+        for k in range(K):
+            assert [tag_of[i] for i in v.getRing(k).tolist()] == w.view.getRing(k)
+        assert v.currentConfigurationId() == w.view.getCurrentConfigurationId()
+        # joiners that were not admitted are dropped: register the rest again for the next round
+        rest = [t for t in range(n, n + nj) if t not in tag_of and t not in ever]
+        if rest and round_ < 2:
+            hosts, ports = W.endpoints(n, nj)
+            sel = [t - n for t in rest]
+            first = v.registerJoiners([hosts[i] for i in sel], [ports[i] for i in sel])[0]
+            v.setJoinerIds(first, hi[sel], lo[sel])
+            tag_of = tag_of + rest
+    # UUIDAlreadySeenException: a new endpoint that re-uses the NodeId of a node that LEFT (its id is still in identifiersSeen)
+    before = (v.getMembershipSize(), v.getRing(0).tolist(), v.currentConfigurationId())
+    hosts, ports = W.endpoints(n + nj, 1)
+    jid = v.registerJoiners(hosts, ports)[0]
+    v.setJoinerIds(jid, [int(w.id_high[5])], [int(w.id_low[5])])
+    with pytest.raises(rb.UUIDAlreadySeenException):
+        v.applyCut([jid])
+    assert (v.getMembershipSize(), v.getRing(0).tolist(), v.currentConfigurationId()) == before
+    # two members with the same NodeId are refused up front
+    v2 = rb.MembershipView.from_packed(K, *w.member_packed())
+    bad_hi = w.id_high.copy(); bad_lo = w.id_low.copy()
+    bad_hi[3], bad_lo[3] = bad_hi[9], bad_lo[9]
+    with pytest.raises(rb.UUIDAlreadySeenException):
+        v2.setNodeIds(bad_hi, bad_lo)
+
+
+@pytest.mark.parametrize("n", [1, 2, 4095, 4096, 4097, 20_000])
+def test_rings_from_the_hand_written_radix_sort(orc, rb, n):
+    """ring order = signed 64-bit key order, sizes around the sort's 4096-pair tile and several tiles (decoupled look-back)"""
+    w = OracleWorld(orc, n, K)
+    v = rb.MembershipView.from_packed(K, *w.member_packed())
+    for k in (0, K - 1):
+        ring = v.getRing(k)
+        keys = v.keys(k)[ring]
+        assert (np.diff(keys) > 0).all() and sorted(ring.tolist()) == list(range(n))
+        assert ring.tolist() == w.view.getRing(k)
+
+
+def test_apply_cut_at_scale_stays_on_the_device(rb):
+    """1 % churn of a 200,000-node view: 1,000 leave, 1,000 join; rings stay sorted, ids stay dense, tables consistent"""
+    n, nj = 200_000, 1000
+    hb, off, ports = W.packed_endpoints(0, n + nj)
+    v = rb.MembershipView.from_packed(K, hb[: off[n]], off[: n + 1], ports[:n])
+    hosts, jports = W.endpoints(n, nj)
+    v.registerJoiners(hosts, jports)
+    keys_before = {k: v.keys(k).copy() for k in (0, 3)}
+    rng = np.random.default_rng(5)
+    leave = np.sort(rng.choice(n, size=1000, replace=False))
+    mapping = v.applyCut(np.concatenate([leave, np.arange(n, n + nj)]).astype(np.int32))
+    assert v.getMembershipSize() == n and v.numJoiners() == 0
+    assert (mapping[leave] == -1).all() and (np.sort(mapping[mapping >= 0]) == np.arange(n)).all()
+    inv = np.empty(n, np.int64); old = np.nonzero(mapping >= 0)[0]; inv[mapping[old]] = old
+    for k in (0, 3):
+        ring = v.getRing(k)
+        kk = v.keys(k)
+        assert (np.diff(kk[ring]) > 0).all()
+        # every surviving node kept its key under its new id
+        assert (kk == keys_before[k][inv]).all()
+    obs, subj = v.tables()
+    r0 = v.getRing(0)
+    assert (obs[r0[:-1], 0] == r0[1:]).all() and obs[r0[-1], 0] == r0[0]
+    assert (subj[r0[1:], 0] == r0[:-1]).all()
