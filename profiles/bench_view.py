@@ -42,13 +42,36 @@ def main():
     t0 = time.perf_counter()
     v.registerJoiners(jh, jp)
     reg_ms = (time.perf_counter() - t0) * 1e3
+    v.setNodeIds(hi, lo)
+    jhi, jlo = W.node_ids(n, nj)
+    v.setJoinerIds(n, jhi, jlo)
+    t0 = time.perf_counter()
+    cfg_dev = v.currentConfigurationId()
+    cfg_dev_ms = (time.perf_counter() - t0) * 1e3
+    assert cfg_dev == cfg
     cut = np.concatenate([W.pick_smallest(n, n // 100, 7), np.arange(n, n + nj)]).astype(np.int32)
     t0 = time.perf_counter()
-    v.applyCut(cut)
+    v.applyCut(cut, want_map=False)
     cut_ms = (time.perf_counter() - t0) * 1e3
     assert v.getMembershipSize() == n - n // 100 + nj
+    t0 = time.perf_counter()
+    cfg_after = v.currentConfigurationId()
+    cfg_after_ms = (time.perf_counter() - t0) * 1e3
+    # a second cut of the same size on the updated view (buffers warm)
+    nj2 = n // 200
+    jh2, jp2 = W.endpoints(n + nj, nj2)
+    first2 = v.registerJoiners(jh2, jp2)[0]
+    h2, l2 = W.node_ids(n + nj, nj2)
+    v.setJoinerIds(first2, h2, l2)
+    m_now = v.getMembershipSize()
+    cut2 = np.concatenate([W.pick_smallest(m_now, n // 100, 11), np.arange(first2, first2 + nj2)]).astype(np.int32)
+    t0 = time.perf_counter()
+    v.applyCut(cut2, want_map=False)
+    cut2_ms = (time.perf_counter() - t0) * 1e3
     res = {"nodes": n, "K": K, "gpu_build_ms": min(build), "gpu_build_first_ms": build[0], "gpu_configuration_id_ms": cfg_ms,
-           "gpu_register_joiners_ms": reg_ms, "joiners": nj, "gpu_apply_cut_ms": cut_ms, "cut_size": int(len(cut)),
+           "gpu_register_joiners_ms": reg_ms, "joiners": nj, "gpu_apply_cut_ms": cut_ms, "gpu_apply_cut_second_ms": cut2_ms,
+           "cut_size": int(len(cut)), "gpu_configuration_id_device_resident_ms": cfg_dev_ms,
+           "gpu_configuration_id_after_cut_ms": cfg_after_ms, "configuration_id_after_cut": int(cfg_after),
            "configuration_id": int(cfg),
            "note": "wall time of the C-ABI calls with host arrays (endpoint bytes copied in, tables stay on the device)"}
     from oracle import oracle_py as orc

@@ -9,10 +9,11 @@
 // then the element at offset k of each key's run.  Everything is exact; nothing depends on thread scheduling.
 #include <limits.h>
 
-#include <cub/cub.cuh>
 
 #include "cd_internal.cuh"
 #include "common.cuh"
+#include "radix.cuh"
+#include "scan.cuh"
 
 namespace rapid {
 
@@ -380,8 +381,8 @@ struct PX {
     uint32_t RT = 0;                       // rule table (cleared per evaluation)
     DevBuf<PxEntry> rtbl;
     DevBuf<uint32_t> key, skey;
-    DevBuf<int32_t> idx, sidx, keep, pos, app_src, slot;
-    DevBuf<uint8_t> cub_tmp;
+    DevBuf<int32_t> idx, sidx, keep, pos, app_src, slot, scan_sums;
+    RadixScratch rs;
     DevBuf<PxScal> sc;
     PinnedBuf<PxScal> h_sc;
     // staging of host message arrays
@@ -409,7 +410,7 @@ struct PXA {
     DevBuf<int32_t> reply, pos, o_sender, o_len, total;
     DevBuf<int64_t> o_vr;
     DevBuf<uint64_t> o_h1, o_h2;
-    DevBuf<uint8_t> cub_tmp;
+    DevBuf<int32_t> scan_sums;
     PinnedBuf<int32_t> h_total;
     DevBuf<int32_t> bad;
     DevBuf<int64_t> s_acc;
@@ -428,12 +429,9 @@ static int32_t px_scratch(PX* px, int64_t n) {
     return RAPID_OK;
 }
 
+// stable sort of (key, idx) by the low `bits` bits of the key (radix.cuh, hand-written; inputs only read)
 static int32_t px_sort_pairs(PX* px, int64_t m, int bits) {
-    size_t bytes = 0;
-    RAPID_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, px->key.p, px->skey.p, px->idx.p, px->sidx.p, (int)m, 0, bits, px->stream));
-    RAPID_CHECK(px->cub_tmp.reserve(bytes));
-    RAPID_CUDA(cub::DeviceRadixSort::SortPairs(px->cub_tmp.p, bytes, px->key.p, px->skey.p, px->idx.p, px->sidx.p, (int)m, 0, bits, px->stream));
-    return RAPID_OK;
+    return radix_sort_pairs<uint32_t>(px->rs, px->key.p, px->idx.p, px->skey.p, px->sidx.p, m, 0, bits, px->stream, false);
 }
 static int bits_for(uint32_t T) { int b = 1; while ((1ull << b) <= (uint64_t)T) ++b; return b; }   // keys in [0, T]
 
@@ -484,10 +482,7 @@ static int32_t px_phase1b_device(PX* px, int64_t n, const int64_t* mcfg, const i
         k_px1b_begin<<<1, 1, 0, s>>>(px->sc.p);
         k_px1b_keep<<<grid_for(n), TB, 0, s>>>(n, mcfg, px->cfg, rnd, rnd_const, px->crnd, px->keep.p);
         RAPID_KERNEL_CHECK();
-        size_t bytes = 0;
-        RAPID_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, px->keep.p, px->pos.p, (int)n, s));
-        RAPID_CHECK(px->cub_tmp.reserve(bytes));
-        RAPID_CUDA(cub::DeviceScan::ExclusiveSum(px->cub_tmp.p, bytes, px->keep.p, px->pos.p, (int)n, s));
+        RAPID_CHECK(exclusive_scan_i32_to(px->keep.p, px->pos.p, n, px->scan_sums, s));
         k_px1b_append<<<grid_for(n), TB, 0, s>>>(n, px->keep.p, px->pos.p, px->n_msgs, vr, h1, h2, len, px->L_vr.p, px->L_h1.p,
                                                   px->L_h2.p, px->L_len.p, px->app_src.p, px->sc.p);
         RAPID_KERNEL_CHECK();
@@ -583,10 +578,7 @@ static int32_t px_arrival_order(PX* px, const PXA* a, uint64_t perm_seed, const 
     RAPID_CHECK(px->idx.reserve((size_t)n)); RAPID_CHECK(px->sidx.reserve((size_t)n));
     k_px_perm_keys<<<grid_for(n), TB, 0, s>>>(n, a->o_sender.p, perm_seed, px->pkey.p, px->idx.p);
     RAPID_KERNEL_CHECK();
-    size_t bytes = 0;
-    RAPID_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, px->pkey.p, px->spkey.p, px->idx.p, px->sidx.p, (int)n, 0, 64, s));
-    RAPID_CHECK(px->cub_tmp.reserve(bytes));
-    RAPID_CUDA(cub::DeviceRadixSort::SortPairs(px->cub_tmp.p, bytes, px->pkey.p, px->spkey.p, px->idx.p, px->sidx.p, (int)n, 0, 64, s));
+    RAPID_CHECK(radix_sort_pairs<uint64_t>(px->rs, px->pkey.p, px->idx.p, px->spkey.p, px->sidx.p, n, 0, 64, s, false));
     RAPID_CHECK(px->g_sender.reserve((size_t)n));
     k_px_gather<int32_t><<<grid_for(n), TB, 0, s>>>(n, px->sidx.p, a->o_sender.p, px->g_sender.p);
     RAPID_KERNEL_CHECK();
@@ -829,10 +821,7 @@ int32_t rapid_pxa_register_fast_round_votes_cd(rapid_pxa* a, const rapid_cd* cd)
 
 static int32_t pxa_compact(rapid_pxa* a, bool with_values) {
     cudaStream_t s = a->stream;
-    size_t bytes = 0;
-    RAPID_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, a->reply.p, a->pos.p, (int)a->R, s));
-    RAPID_CHECK(a->cub_tmp.reserve(bytes));
-    RAPID_CUDA(cub::DeviceScan::ExclusiveSum(a->cub_tmp.p, bytes, a->reply.p, a->pos.p, (int)a->R, s));
+    RAPID_CHECK(exclusive_scan_i32_to(a->reply.p, a->pos.p, a->R, a->scan_sums, s));
     k_pxa_gather1b<<<grid_for(a->R), TB, 0, s>>>(a->R, a->reply.p, a->pos.p, a->begin, a->vrnd.p, a->h1.p, a->h2.p, a->len.p, a->o_sender.p,
                                                  with_values ? a->o_vr.p : nullptr, a->o_h1.p, a->o_h2.p, a->o_len.p);
     k_pxa_total<<<1, 1, 0, s>>>(a->R, a->reply.p, a->pos.p, a->total.p);

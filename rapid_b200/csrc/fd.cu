@@ -6,9 +6,10 @@
 // appended to a list, sorted back into detector order, and expanded into alerts and cells.
 #include <limits.h>
 
-#include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "radix.cuh"
+#include "scan.cuh"
 
 namespace rapid {
 
@@ -98,7 +99,9 @@ struct FD {
     uint64_t view_epoch = 0;
     DevBuf<uint32_t> st, fired, fired_sorted;
     DevBuf<int32_t> cnt, pos;
-    DevBuf<uint8_t> flags, edge, cub_tmp;
+    DevBuf<uint8_t> flags, edge;
+    DevBuf<int32_t> scan_sums;
+    RadixScratch rs;
     DevBuf<FdScal> sc;
     PinnedBuf<FdScal> h_sc;
     int64_t n_alerts = 0, n_cells = 0;
@@ -146,14 +149,11 @@ static int32_t fd_tick_device(FD* fd, const uint8_t* d_flags, const uint8_t* d_e
             RAPID_CHECK(fd->a_obs.reserve(F)); RAPID_CHECK(fd->a_subj.reserve(F)); RAPID_CHECK(fd->a_mask.reserve(F));
             RAPID_CHECK(fd->c_src.reserve(C)); RAPID_CHECK(fd->c_dst.reserve(C)); RAPID_CHECK(fd->c_ring.reserve(C));
             RAPID_CHECK(fd->c_status.reserve(C)); RAPID_CHECK(fd->c_cfg.reserve(C));
-            size_t b1 = 0, b2 = 0;
-            RAPID_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, b1, fd->fired.p, fd->fired_sorted.p, nf, 0, 32, s));
-            RAPID_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b2, fd->cnt.p, fd->pos.p, nf, s));
-            RAPID_CHECK(fd->cub_tmp.reserve(std::max(b1, b2)));
-            RAPID_CUDA(cub::DeviceRadixSort::SortKeys(fd->cub_tmp.p, b1, fd->fired.p, fd->fired_sorted.p, nf, 0, 32, s));
+            // the notifying detectors back into (node, detector) order: hand-written radix sort (radix.cuh), keys only
+            RAPID_CHECK(radix_sort_pairs<uint32_t>(fd->rs, fd->fired.p, nullptr, fd->fired_sorted.p, nullptr, nf, 0, 32, s, false));
             k_fd_count<<<grid_for(nf), TB, 0, s>>>(nf, (uint32_t)fd->K, fd->fired_sorted.p, fd->view->subj.p, fd->cnt.p);
             RAPID_KERNEL_CHECK();
-            RAPID_CUDA(cub::DeviceScan::ExclusiveSum(fd->cub_tmp.p, b2, fd->cnt.p, fd->pos.p, nf, s));
+            RAPID_CHECK(exclusive_scan_i32_to(fd->cnt.p, fd->pos.p, nf, fd->scan_sums, s));
             k_fd_emit<<<grid_for(nf), TB, 0, s>>>(nf, (uint32_t)fd->K, fd->fired_sorted.p, fd->view->subj.p, fd->cnt.p, fd->pos.p, cfg, fd->a_obs.p,
                                                  fd->a_subj.p, fd->a_mask.p, fd->c_src.p, fd->c_dst.p, fd->c_ring.p, fd->c_status.p, fd->c_cfg.p, fd->sc.p);
             RAPID_KERNEL_CHECK();

@@ -37,12 +37,12 @@ __device__ __forceinline__ int32_t scan_block_exclusive(int32_t v, int32_t* warp
     return warp_off + inc - v;
 }
 
-static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(int32_t* __restrict__ data, int64_t n, int32_t* __restrict__ sums) {
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const int32_t* src, int32_t* data, int64_t n, int32_t* __restrict__ sums) {
     __shared__ int32_t warp_sums[SCAN_THREADS / 32];
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     int32_t v[SCAN_ITEMS], tsum = 0;
 #pragma unroll
-    for (int q = 0; q < SCAN_ITEMS; ++q) { v[q] = base + q < n ? data[base + q] : 0; tsum += v[q]; }
+    for (int q = 0; q < SCAN_ITEMS; ++q) { v[q] = base + q < n ? src[base + q] : 0; tsum += v[q]; }
     int32_t total;
     int32_t run = scan_block_exclusive(tsum, warp_sums, &total);
 #pragma unroll
@@ -79,19 +79,26 @@ static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(int32_t* __res
 }
 
 // data[n] -> exclusive prefix sums in place; *total_dev (optional, device) = sum.  `sums` must hold ceil(n / 2048) ints.
-static inline int32_t exclusive_scan_i32(int32_t* data, int64_t n, DevBuf<int32_t>& sums, int32_t* total_dev, cudaStream_t s, int* launches) {
+static inline int32_t exclusive_scan_i32(int32_t* data, int64_t n, DevBuf<int32_t>& sums, int32_t* total_dev, cudaStream_t s, int* launches,
+                                         const int32_t* src = nullptr) {
     if (n <= 0) {
         if (total_dev) RAPID_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(int32_t), s));
         return RAPID_OK;
     }
     const int32_t tiles = (int32_t)ceil_div<int64_t>(n, SCAN_TILE);
     RAPID_CHECK(sums.reserve((size_t)tiles));
-    k_scan_tiles<<<tiles, SCAN_THREADS, 0, s>>>(data, n, sums.p);
+    k_scan_tiles<<<tiles, SCAN_THREADS, 0, s>>>(src ? src : data, data, n, sums.p);
     k_scan_sums<<<1, SCAN_THREADS, 0, s>>>(sums.p, tiles, total_dev);
     if (tiles > 1) k_scan_add<<<tiles, SCAN_THREADS, 0, s>>>(data, n, sums.p);
     RAPID_KERNEL_CHECK();
     if (launches) *launches += tiles > 1 ? 3 : 2;
     return RAPID_OK;
+}
+
+// dst[n] = exclusive prefix sums of src[n] (src untouched)
+static inline int32_t exclusive_scan_i32_to(const int32_t* src, int32_t* dst, int64_t n, DevBuf<int32_t>& sums, cudaStream_t s, int* launches = nullptr) {
+    if (n <= 0) return RAPID_OK;
+    return exclusive_scan_i32(dst, n, sums, nullptr, s, launches, src);
 }
 
 }  // namespace rapid

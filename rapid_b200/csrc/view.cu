@@ -157,9 +157,22 @@ __global__ void k_id_sort_keys(const int64_t* __restrict__ v, int64_t n, uint64_
 }
 
 // ------------------------------------------------------------------ host helpers
+struct CutScratch {                                      // rapid_view_apply_cut: everything it builds beside the live arrays
+    DevBuf<int32_t> d_cut, incut, newid, kept, len, err, map, flag, pos, jv, jv2, collision, off2, port2, ring2;
+    DevBuf<uint64_t> jk, jk2;
+    DevBuf<uint8_t> hb2;
+    DevBuf<int64_t> key2, sk2, nhi2, nlo2;
+};
+struct IdScratch {                                       // NodeId sorting / merging
+    DevBuf<uint64_t> k_in, k_out;
+    DevBuf<int32_t> i_in, i_mid, order, dup;
+    DevBuf<int64_t> bh, bl, oh, ol;
+};
 struct ViewScratch {
     RadixScratch rs;
     DevBuf<int32_t> scan_sums;
+    CutScratch cut;
+    IdScratch ids;
 };
 static ViewScratch* scratch(View* v) {
     if (!v->scratch) v->scratch = new ViewScratch();
@@ -168,7 +181,7 @@ static ViewScratch* scratch(View* v) {
 
 // (keys_in, vals_in) are scratch for the caller: the sort may use them as its ping-pong buffers
 static int32_t sort_pairs(View* v, uint64_t* kin, uint64_t* kout, int32_t* vin, int32_t* vout, int64_t n, cudaStream_t s) {
-    return radix_sort_pairs(scratch(v)->rs, kin, vin, kout, vout, n, 0, 64, s);
+    return radix_sort_pairs<uint64_t>(scratch(v)->rs, kin, vin, kout, vout, n, 0, 64, s);
 }
 
 static int32_t ensure_total_capacity(View* v, int64_t ntot) {
@@ -505,24 +518,51 @@ __global__ void k_cut_ring_flags(int K, int64_t n, const int32_t* __restrict__ r
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < (int64_t)K * n) flag[t] = keep[ring[t]];
 }
-// the admitted joiners of ring k as (sortable key, new id) pairs
-__global__ void k_cut_joiner_keys(int k, int64_t n, int64_t tot, size_t stride, const int32_t* __restrict__ keep, const int32_t* __restrict__ newid,
-                                  int32_t n_surv, const int64_t* __restrict__ key, uint64_t* __restrict__ jk, int32_t* __restrict__ jv) {
+// the admitted joiners of every ring as (sortable key, new id) pairs: jk[k][j], jv[k][j]
+__global__ void k_cut_joiner_keys(int K, int64_t n, int64_t tot, size_t stride, const int32_t* __restrict__ keep, const int32_t* __restrict__ newid,
+                                  int32_t n_surv, int32_t m, const int64_t* __restrict__ key, uint64_t* __restrict__ jk, int32_t* __restrict__ jv) {
     const int64_t id = n + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= tot || !keep[id]) return;
+    const int k = blockIdx.y;
+    if (k >= K || id >= tot || !keep[id]) return;
     const int32_t j = newid[id] - n_surv;
-    jk[j] = (uint64_t)key[(size_t)k * stride + id] ^ 0x8000000000000000ULL;
-    jv[j] = newid[id];
+    jk[(size_t)k * m + j] = (uint64_t)key[(size_t)k * stride + id] ^ 0x8000000000000000ULL;
+    jv[(size_t)k * m + j] = newid[id];
 }
-// merge of ring k: survivors keep their order, every joiner slots in by its key (TreeSet order of the new membership)
-__global__ void k_cut_merge(int k, int64_t n, int32_t n_surv, int32_t m, const int32_t* __restrict__ ring, const int64_t* __restrict__ sorted_key,
+// the (few) joiners of every ring sorted by key: rank = number of joiners with a smaller key, all pairs through shared memory;
+// two joiners with the same key on a ring -> collision (TreeSet.add would silently drop one)
+__global__ void __launch_bounds__(256) k_cut_joiner_rank(int32_t m, const uint64_t* __restrict__ jk, const int32_t* __restrict__ jv,
+                                                         uint64_t* __restrict__ jk2, int32_t* __restrict__ jv2, int32_t* __restrict__ collision) {
+    __shared__ uint64_t s_k[256];
+    const int k = blockIdx.y;
+    const uint64_t* mk = jk + (size_t)k * m;
+    const int32_t i = blockIdx.x * 256 + threadIdx.x;
+    const uint64_t key = i < m ? mk[i] : 0ull;
+    int32_t rank = 0;
+    for (int32_t b = 0; b < m; b += 256) {
+        __syncthreads();
+        s_k[threadIdx.x] = b + (int32_t)threadIdx.x < m ? mk[b + threadIdx.x] : ~0ull;
+        __syncthreads();
+        const int32_t lim = min(256, m - b);
+        for (int32_t j = 0; j < lim; ++j) {
+            const uint64_t o = s_k[j];
+            rank += o < key ? 1 : 0;
+            if (o == key && b + j != i && i < m) atomicCAS(&collision[0], -1, k);
+        }
+    }
+    if (i < m) { jk2[(size_t)k * m + rank] = key; jv2[(size_t)k * m + rank] = jv[(size_t)k * m + i]; }
+}
+// merge of every ring (blockIdx.y): survivors keep their order, every joiner slots in by its key (TreeSet order of the new membership)
+__global__ void k_cut_merge(int64_t n, int32_t n_surv, int32_t m, const int32_t* __restrict__ ring, const int64_t* __restrict__ sorted_key,
                             const int32_t* __restrict__ flag, const int32_t* __restrict__ pos /* exclusive scan of flag over [K][n] */,
-                            const int32_t* __restrict__ newid, const uint64_t* __restrict__ jk, const int32_t* __restrict__ jv,
+                            const int32_t* __restrict__ newid, const uint64_t* __restrict__ jk_all, const int32_t* __restrict__ jv_all,
                             int32_t* __restrict__ ring2, int64_t* __restrict__ sorted_key2, int32_t* __restrict__ collision) {
+    const int k = blockIdx.y;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int32_t* fl = flag + (size_t)k * n;
     const int32_t* ps = pos + (size_t)k * n;
     const int64_t* sk = sorted_key + (size_t)k * n;
+    const uint64_t* jk = jk_all + (size_t)k * m;
+    const int32_t* jv = jv_all + (size_t)k * m;
     const int32_t base = n ? ps[0] : 0;
     const int32_t n2 = n_surv + m;
     if (t < n) {
@@ -541,7 +581,6 @@ __global__ void k_cut_merge(int k, int64_t n, int32_t n_surv, int32_t m, const i
         while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sk[mid] < key) lo = mid + 1; else hi = mid; }
         const int32_t before = n == 0 ? 0 : (lo < n ? ps[lo] - base : ps[n - 1] + fl[n - 1] - base);
         if (lo < n && sk[lo] == key && fl[lo]) atomicCAS(&collision[0], -1, k);
-        if (i + 1 < m && jk[i + 1] == jk[i]) atomicCAS(&collision[0], -1, k);
         const int32_t out = before + i;
         ring2[(size_t)k * n2 + out] = jv[i];
         sorted_key2[(size_t)k * n2 + out] = key;
@@ -561,19 +600,15 @@ __global__ void k_gather_ids(const int64_t* __restrict__ hi, const int64_t* __re
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { hi2[i] = hi[order[i]]; lo2[i] = lo[order[i]]; }
 }
-__global__ void k_ids_adjacent_equal(const int64_t* __restrict__ hi, const int64_t* __restrict__ lo, int64_t n, int32_t* __restrict__ found) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i + 1 < n && hi[i] == hi[i + 1] && lo[i] == lo[i + 1]) atomicCAS(found, -1, (int32_t)i);
-}
-
 // sorts n (hi, lo) pairs by signed (hi, lo) into (hi2, lo2): LSD — stable sort by low, then by high
 static int32_t sort_node_ids(View* v, const int64_t* hi, const int64_t* lo, int64_t n, int64_t* hi2, int64_t* lo2) {
     if (n <= 0) return RAPID_OK;
     cudaStream_t s = v->stream;
     const int TB = 256;
     const unsigned gb = (unsigned)ceil_div<int64_t>(n, TB);
-    DevBuf<uint64_t> k_in, k_out;
-    DevBuf<int32_t> i_in, i_mid, order;
+    IdScratch& c = scratch(v)->ids;
+    DevBuf<uint64_t>& k_in = c.k_in; DevBuf<uint64_t>& k_out = c.k_out;
+    DevBuf<int32_t>& i_in = c.i_in; DevBuf<int32_t>& i_mid = c.i_mid; DevBuf<int32_t>& order = c.order;
     RAPID_CHECK(k_in.reserve((size_t)n)); RAPID_CHECK(k_out.reserve((size_t)n));
     RAPID_CHECK(i_in.reserve((size_t)n)); RAPID_CHECK(i_mid.reserve((size_t)n)); RAPID_CHECK(order.reserve((size_t)n));
     k_u64_flip<<<gb, TB, 0, s>>>(lo, nullptr, n, k_in.p, i_in.p);
@@ -584,35 +619,50 @@ static int32_t sort_node_ids(View* v, const int64_t* hi, const int64_t* lo, int6
     RAPID_CHECK(sort_pairs(v, k_in.p, k_out.p, i_in.p, order.p, n, s));
     k_gather_ids<<<gb, TB, 0, s>>>(hi, lo, order.p, n, hi2, lo2);
     RAPID_KERNEL_CHECK();
-    RAPID_CUDA(cudaStreamSynchronize(s));                    // the scratch buffers go out of scope
     return RAPID_OK;
 }
 
-// identifiersSeen := sorted(identifiersSeen ++ add);  RAPID_EUUID_SEEN (nothing changed) if that contains a NodeId twice
+// signed (hi, lo) order of NodeIdComparator (:474-500)
+__device__ __forceinline__ bool id_less(int64_t ah, int64_t al, int64_t bh, int64_t bl) { return ah < bh || (ah == bh && al < bl); }
+// merge of two sorted NodeId lists (a: identifiersSeen, b: the new ones, both strictly increasing): thread i < na places a[i],
+// thread na + j places b[j]; an id present in both (or twice in b) sets *dup
+__global__ void k_ids_merge(const int64_t* __restrict__ ah, const int64_t* __restrict__ al, int64_t na, const int64_t* __restrict__ bh,
+                            const int64_t* __restrict__ bl, int64_t nb, int64_t* __restrict__ oh, int64_t* __restrict__ ol, int32_t* __restrict__ dup) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < na) {
+        const int64_t h = ah[t], l = al[t];
+        int64_t lo = 0, hi = nb;                             // new ids smaller than a[t]
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (id_less(bh[mid], bl[mid], h, l)) lo = mid + 1; else hi = mid; }
+        if (lo < nb && bh[lo] == h && bl[lo] == l) atomicCAS(dup, -1, (int32_t)lo);
+        oh[t + lo] = h; ol[t + lo] = l;
+    } else if (t < na + nb) {
+        const int64_t j = t - na;
+        const int64_t h = bh[j], l = bl[j];
+        int64_t lo = 0, hi = na;                             // seen ids smaller than b[j]
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (id_less(ah[mid], al[mid], h, l)) lo = mid + 1; else hi = mid; }
+        if (j + 1 < nb && bh[j + 1] == h && bl[j + 1] == l) atomicCAS(dup, -1, (int32_t)j);
+        oh[lo + j] = h; ol[lo + j] = l;
+    }
+}
+
+// identifiersSeen := merge(identifiersSeen, sorted(add));  RAPID_EUUID_SEEN (nothing changed) if a NodeId would be there twice
 static int32_t seen_add(View* v, const int64_t* add_hi_dev, const int64_t* add_lo_dev, int64_t n_add) {
     if (n_add <= 0) return RAPID_OK;
     cudaStream_t s = v->stream;
+    IdScratch& c = scratch(v)->ids;
     const int64_t tot = v->n_seen + n_add;
-    DevBuf<int64_t> ch, cl, sh, sl;
-    DevBuf<int32_t> found;
-    RAPID_CHECK(ch.reserve((size_t)tot)); RAPID_CHECK(cl.reserve((size_t)tot)); RAPID_CHECK(sh.reserve((size_t)tot)); RAPID_CHECK(sl.reserve((size_t)tot));
-    RAPID_CHECK(found.reserve(1));
-    if (v->n_seen) {
-        RAPID_CUDA(cudaMemcpyAsync(ch.p, v->seen_hi.p, (size_t)v->n_seen * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
-        RAPID_CUDA(cudaMemcpyAsync(cl.p, v->seen_lo.p, (size_t)v->n_seen * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
-    }
-    RAPID_CUDA(cudaMemcpyAsync(ch.p + v->n_seen, add_hi_dev, (size_t)n_add * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
-    RAPID_CUDA(cudaMemcpyAsync(cl.p + v->n_seen, add_lo_dev, (size_t)n_add * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
-    RAPID_CHECK(sort_node_ids(v, ch.p, cl.p, tot, sh.p, sl.p));
-    RAPID_CUDA(cudaMemsetAsync(found.p, 0xff, sizeof(int32_t), s));
-    k_ids_adjacent_equal<<<(unsigned)ceil_div<int64_t>(tot, 256), 256, 0, s>>>(sh.p, sl.p, tot, found.p);
+    RAPID_CHECK(c.bh.reserve((size_t)n_add)); RAPID_CHECK(c.bl.reserve((size_t)n_add));
+    RAPID_CHECK(c.oh.reserve((size_t)tot)); RAPID_CHECK(c.ol.reserve((size_t)tot)); RAPID_CHECK(c.dup.reserve(1));
+    RAPID_CHECK(sort_node_ids(v, add_hi_dev, add_lo_dev, n_add, c.bh.p, c.bl.p));
+    RAPID_CUDA(cudaMemsetAsync(c.dup.p, 0xff, sizeof(int32_t), s));
+    k_ids_merge<<<(unsigned)ceil_div<int64_t>(tot, 256), 256, 0, s>>>(v->seen_hi.p, v->seen_lo.p, v->n_seen, c.bh.p, c.bl.p, n_add, c.oh.p, c.ol.p, c.dup.p);
     RAPID_KERNEL_CHECK();
     int32_t f = -1;
-    RAPID_CUDA(cudaMemcpyAsync(&f, found.p, sizeof(f), cudaMemcpyDeviceToHost, s));
+    RAPID_CUDA(cudaMemcpyAsync(&f, c.dup.p, sizeof(f), cudaMemcpyDeviceToHost, s));
     RAPID_CUDA(cudaStreamSynchronize(s));
     if (f >= 0) { set_error("a NodeId was seen before (UUIDAlreadySeenException)"); return RAPID_EUUID_SEEN; }
-    std::swap(v->seen_hi.p, sh.p); std::swap(v->seen_hi.cap, sh.cap);
-    std::swap(v->seen_lo.p, sl.p); std::swap(v->seen_lo.cap, sl.cap);
+    std::swap(v->seen_hi.p, c.oh.p); std::swap(v->seen_hi.cap, c.oh.cap);
+    std::swap(v->seen_lo.p, c.ol.p); std::swap(v->seen_lo.cap, c.ol.cap);
     v->n_seen = tot;
     return RAPID_OK;
 }
@@ -625,117 +675,95 @@ static int32_t apply_cut_device(View* v, const int32_t* cut_ids, int64_t n_cut, 
     const int K = v->K, TB = 256;
     const int64_t n = v->n, tot = v->n + v->nj;
     ViewScratch* sc = scratch(v);
-    DevBuf<int32_t> d_cut, incut, keep, len, err, map, flag, jv, jv2, collision, totals;
-    DevBuf<uint64_t> jk, jk2;
+    CutScratch& c = sc->cut;                                  // persistent: no cudaMalloc / cudaFree per view change
     const size_t t1 = (size_t)std::max<int64_t>(tot, 1);
-    RAPID_CHECK(d_cut.reserve((size_t)std::max<int64_t>(n_cut, 1))); RAPID_CHECK(incut.reserve(t1)); RAPID_CHECK(keep.reserve(t1 + 1));
-    RAPID_CHECK(len.reserve(t1 + 1)); RAPID_CHECK(err.reserve(2)); RAPID_CHECK(map.reserve(t1)); RAPID_CHECK(totals.reserve(2));
-    RAPID_CHECK(collision.reserve(1));
-    RAPID_CUDA(cudaMemsetAsync(incut.p, 0, t1 * sizeof(int32_t), s));
-    RAPID_CUDA(cudaMemsetAsync(err.p, 0, 2 * sizeof(int32_t), s));
+    RAPID_CHECK(c.d_cut.reserve((size_t)std::max<int64_t>(n_cut, 1))); RAPID_CHECK(c.incut.reserve(t1)); RAPID_CHECK(c.newid.reserve(t1 + 1));
+    RAPID_CHECK(c.kept.reserve(t1)); RAPID_CHECK(c.len.reserve(t1 + 1)); RAPID_CHECK(c.err.reserve(4)); RAPID_CHECK(c.map.reserve(t1));
+    RAPID_CUDA(cudaMemsetAsync(c.incut.p, 0, t1 * sizeof(int32_t), s));
+    RAPID_CUDA(cudaMemsetAsync(c.err.p, 0, 4 * sizeof(int32_t), s));       // [0..1] error, [2..3] totals
     if (n_cut) {
-        RAPID_CUDA(cudaMemcpyAsync(d_cut.p, cut_ids, (size_t)n_cut * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-        k_cut_mark<<<(unsigned)ceil_div<int64_t>(n_cut, TB), TB, 0, s>>>(d_cut.p, n_cut, n, tot, incut.p, err.p);
+        RAPID_CUDA(cudaMemcpyAsync(c.d_cut.p, cut_ids, (size_t)n_cut * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        k_cut_mark<<<(unsigned)ceil_div<int64_t>(n_cut, TB), TB, 0, s>>>(c.d_cut.p, n_cut, n, tot, c.incut.p, c.err.p);
         RAPID_KERNEL_CHECK();
     }
     if (tot) {
-        k_cut_keep<<<(unsigned)ceil_div<int64_t>(tot, TB), TB, 0, s>>>(n, tot, incut.p, v->host_off.p, keep.p, len.p);
+        k_cut_keep<<<(unsigned)ceil_div<int64_t>(tot, TB), TB, 0, s>>>(n, tot, c.incut.p, v->host_off.p, c.kept.p, c.len.p);
         RAPID_KERNEL_CHECK();
+        RAPID_CUDA(cudaMemcpyAsync(c.newid.p, c.kept.p, (size_t)tot * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
     }
-    // keep -> new ids, len -> new byte offsets (exclusive scans in place; totals on the device)
-    RAPID_CHECK(exclusive_scan_i32(keep.p, tot, sc->scan_sums, totals.p, s, nullptr));
-    RAPID_CHECK(exclusive_scan_i32(len.p, tot, sc->scan_sums, totals.p + 1, s, nullptr));
-    int32_t h_err[2] = {0, 0}, h_tot[2] = {0, 0}, n_surv = 0;
-    RAPID_CUDA(cudaMemcpyAsync(h_err, err.p, sizeof(h_err), cudaMemcpyDeviceToHost, s));
-    RAPID_CUDA(cudaMemcpyAsync(h_tot, totals.p, sizeof(h_tot), cudaMemcpyDeviceToHost, s));
-    if (n < tot) RAPID_CUDA(cudaMemcpyAsync(&n_surv, keep.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, s));   // members that stay = new id of the first joiner
+    // kept -> new ids, len -> new byte offsets (exclusive scans; totals on the device)
+    RAPID_CHECK(exclusive_scan_i32(c.newid.p, tot, sc->scan_sums, c.err.p + 2, s, nullptr));
+    RAPID_CHECK(exclusive_scan_i32(c.len.p, tot, sc->scan_sums, c.err.p + 3, s, nullptr));
+    int32_t h[4] = {0, 0, 0, 0}, n_surv = 0;
+    RAPID_CUDA(cudaMemcpyAsync(h, c.err.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    if (n < tot) RAPID_CUDA(cudaMemcpyAsync(&n_surv, c.newid.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, s));   // members that stay = new id of the first joiner
     RAPID_CUDA(cudaStreamSynchronize(s));
-    if (h_err[0] == 1) { set_error("cut id %d outside [0, members + joiners)", h_err[1]); return RAPID_EINVAL; }
-    if (h_err[0] == 2) {
-        set_error("cut names node %d twice", h_err[1]);
-        return h_err[1] < n ? RAPID_ENOT_IN_RING : RAPID_EALREADY_IN_RING;      // second ringDelete / ringAdd would throw
+    if (h[0] == 1) { set_error("cut id %d outside [0, members + joiners)", h[1]); return RAPID_EINVAL; }
+    if (h[0] == 2) {
+        set_error("cut names node %d twice", h[1]);
+        return h[1] < n ? RAPID_ENOT_IN_RING : RAPID_EALREADY_IN_RING;      // second ringDelete / ringAdd would throw
     }
-    const int32_t n2 = h_tot[0], bytes2 = h_tot[1];
+    const int32_t n2 = h[2], bytes2 = h[3];
     if (n == tot) n_surv = n2;
-    const int32_t m = n2 - n_surv;                                              // joiners admitted
-    // `keep` now holds the new ids; the kept flags are recovered from incut (k_cut_keep's rule) where needed: recompute
-    DevBuf<int32_t> kept;
-    RAPID_CHECK(kept.reserve(t1));
-    if (tot) { k_cut_keep<<<(unsigned)ceil_div<int64_t>(tot, TB), TB, 0, s>>>(n, tot, incut.p, v->host_off.p, kept.p, map.p /*scratch*/); RAPID_KERNEL_CHECK(); }
-    // ---- UUID rule for the joiners that come in (:126-128), before anything is modified ---------------------------------------
-    DevBuf<int64_t> nhi2, nlo2;
-    // ---- new endpoint table, keys, NodeIds -------------------------------------------------------------------------------------
-    DevBuf<uint8_t> hb2;
-    DevBuf<int32_t> off2, port2, ring2;
-    DevBuf<int64_t> key2, sk2;
+    const int32_t m = n2 - n_surv;                                          // joiners admitted
+    // ---- new endpoint table, keys, NodeIds (built beside the current ones, swapped in at the end) ----------------------------
     const size_t n2s = (size_t)std::max(n2, 1);
     size_t stride2 = 1;
     while (stride2 < n2s) stride2 *= 2;
-    RAPID_CHECK(hb2.reserve((size_t)std::max(bytes2, 1))); RAPID_CHECK(off2.reserve(n2s + 1)); RAPID_CHECK(port2.reserve(n2s));
-    RAPID_CHECK(key2.reserve(stride2 * (size_t)K)); RAPID_CHECK(ring2.reserve(n2s * (size_t)K)); RAPID_CHECK(sk2.reserve(n2s * (size_t)K));
-    if (v->has_node_ids) { RAPID_CHECK(nhi2.reserve(n2s)); RAPID_CHECK(nlo2.reserve(n2s)); }
+    RAPID_CHECK(c.hb2.reserve((size_t)std::max(bytes2, 1))); RAPID_CHECK(c.off2.reserve(n2s + 1)); RAPID_CHECK(c.port2.reserve(n2s));
+    RAPID_CHECK(c.key2.reserve(stride2 * (size_t)K)); RAPID_CHECK(c.ring2.reserve(n2s * (size_t)K)); RAPID_CHECK(c.sk2.reserve(n2s * (size_t)K));
+    if (v->has_node_ids) { RAPID_CHECK(c.nhi2.reserve(n2s)); RAPID_CHECK(c.nlo2.reserve(n2s)); }
     k_cut_endpoints<<<(unsigned)ceil_div<int64_t>(std::max<int64_t>(tot, 1), TB), TB, 0, s>>>(
-        tot, kept.p, keep.p, len.p, v->host_off.p, v->host_bytes.p, v->port.p, hb2.p, off2.p, port2.p,
-        v->has_node_ids ? v->node_hi.p : nullptr, v->has_node_ids ? v->node_lo.p : nullptr, nhi2.p, nlo2.p, map.p, bytes2, n2);
+        tot, c.kept.p, c.newid.p, c.len.p, v->host_off.p, v->host_bytes.p, v->port.p, c.hb2.p, c.off2.p, c.port2.p,
+        v->has_node_ids ? v->node_hi.p : nullptr, v->has_node_ids ? v->node_lo.p : nullptr, c.nhi2.p, c.nlo2.p, c.map.p, bytes2, n2);
     RAPID_KERNEL_CHECK();
     if (tot) {
-        k_cut_keys<<<(unsigned)ceil_div<int64_t>((int64_t)K * tot, TB), TB, 0, s>>>(K, tot, v->key_stride, stride2, kept.p, keep.p, v->key.p, key2.p);
+        k_cut_keys<<<(unsigned)ceil_div<int64_t>((int64_t)K * tot, TB), TB, 0, s>>>(K, tot, v->key_stride, stride2, c.kept.p, c.newid.p, v->key.p, c.key2.p);
         RAPID_KERNEL_CHECK();
     }
+    // ---- UUID rule for the joiners that come in (:126-128), before anything is swapped in ---------------------------------------
     if (v->has_node_ids && m > 0) {
         // the joiners' NodeIds are the last m entries of the new NodeId arrays (joiners follow the surviving members)
-        const int32_t rc = seen_add(v, nhi2.p + n_surv, nlo2.p + n_surv, m);
-        if (rc != RAPID_OK) return rc;                                           // UUIDAlreadySeenException: the view is unchanged
+        const int32_t rc = seen_add(v, c.nhi2.p + n_surv, c.nlo2.p + n_surv, m);
+        if (rc != RAPID_OK) return rc;                                       // UUIDAlreadySeenException: the view is unchanged
     }
-    // ---- rings -----------------------------------------------------------------------------------------------------------------
-    RAPID_CUDA(cudaMemsetAsync(collision.p, 0xff, sizeof(int32_t), s));
+    // ---- rings: all K at once ------------------------------------------------------------------------------------------------------
+    RAPID_CHECK(c.collision.reserve(1));
+    RAPID_CUDA(cudaMemsetAsync(c.collision.p, 0xff, sizeof(int32_t), s));
+    const size_t kn = (size_t)K * (size_t)std::max<int64_t>(n, 1), km = (size_t)K * (size_t)std::max(m, 1);
+    RAPID_CHECK(c.flag.reserve(kn)); RAPID_CHECK(c.pos.reserve(kn));
+    RAPID_CHECK(c.jk.reserve(km)); RAPID_CHECK(c.jk2.reserve(km)); RAPID_CHECK(c.jv.reserve(km)); RAPID_CHECK(c.jv2.reserve(km));
     if (n > 0) {
-        RAPID_CHECK(flag.reserve((size_t)K * n));
-        DevBuf<int32_t> pos;
-        RAPID_CHECK(pos.reserve((size_t)K * n));
-        k_cut_ring_flags<<<(unsigned)ceil_div<int64_t>((int64_t)K * n, TB), TB, 0, s>>>(K, n, v->ring.p, kept.p, flag.p);
+        k_cut_ring_flags<<<(unsigned)ceil_div<int64_t>((int64_t)K * n, TB), TB, 0, s>>>(K, n, v->ring.p, c.kept.p, c.flag.p);
         RAPID_KERNEL_CHECK();
-        RAPID_CUDA(cudaMemcpyAsync(pos.p, flag.p, (size_t)K * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
-        RAPID_CHECK(exclusive_scan_i32(pos.p, (int64_t)K * n, sc->scan_sums, nullptr, s, nullptr));
-        RAPID_CHECK(jk.reserve((size_t)std::max(m, 1))); RAPID_CHECK(jk2.reserve((size_t)std::max(m, 1)));
-        RAPID_CHECK(jv.reserve((size_t)std::max(m, 1))); RAPID_CHECK(jv2.reserve((size_t)std::max(m, 1)));
-        for (int k = 0; k < K; ++k) {
-            if (m > 0) {
-                k_cut_joiner_keys<<<(unsigned)ceil_div<int64_t>(tot - n, TB), TB, 0, s>>>(k, n, tot, v->key_stride, kept.p, keep.p, n_surv, v->key.p, jk.p, jv.p);
-                RAPID_KERNEL_CHECK();
-                RAPID_CHECK(sort_pairs(v, jk.p, jk2.p, jv.p, jv2.p, m, s));
-            }
-            k_cut_merge<<<(unsigned)ceil_div<int64_t>(n + m, TB), TB, 0, s>>>(k, n, n_surv, m, v->ring.p, v->sorted_key.p, flag.p, pos.p, keep.p,
-                                                                             jk2.p, jv2.p, ring2.p, sk2.p, collision.p);
-            RAPID_KERNEL_CHECK();
-        }
-        int32_t coll = -1;
-        RAPID_CUDA(cudaMemcpyAsync(&coll, collision.p, sizeof(coll), cudaMemcpyDeviceToHost, s));
-        RAPID_CUDA(cudaStreamSynchronize(s));
-        if (coll >= 0) { set_error("ring-%d key collision while adding joiners (TreeSet would silently drop one)", coll); return RAPID_EHASH_COLLISION; }
-    } else if (m > 0) {
-        // no members before: the rings are just the sorted joiners
-        RAPID_CHECK(jk.reserve((size_t)m)); RAPID_CHECK(jk2.reserve((size_t)m)); RAPID_CHECK(jv.reserve((size_t)m)); RAPID_CHECK(jv2.reserve((size_t)m));
-        DevBuf<int32_t> noflag, nopos;
-        RAPID_CHECK(noflag.reserve(1)); RAPID_CHECK(nopos.reserve(1));
-        for (int k = 0; k < K; ++k) {
-            k_cut_joiner_keys<<<(unsigned)ceil_div<int64_t>(tot - n, TB), TB, 0, s>>>(k, n, tot, v->key_stride, kept.p, keep.p, n_surv, v->key.p, jk.p, jv.p);
-            RAPID_CHECK(sort_pairs(v, jk.p, jk2.p, jv.p, jv2.p, m, s));
-            k_cut_merge<<<(unsigned)ceil_div<int64_t>(m, TB), TB, 0, s>>>(k, 0, 0, m, v->ring.p, v->sorted_key.p, noflag.p, nopos.p, keep.p, jk2.p, jv2.p,
-                                                                         ring2.p, sk2.p, collision.p);
-            RAPID_KERNEL_CHECK();
-        }
-        int32_t coll = -1;
-        RAPID_CUDA(cudaMemcpyAsync(&coll, collision.p, sizeof(coll), cudaMemcpyDeviceToHost, s));
-        RAPID_CUDA(cudaStreamSynchronize(s));
-        if (coll >= 0) { set_error("ring-%d key collision among the joiners", coll); return RAPID_EHASH_COLLISION; }
+        RAPID_CHECK(exclusive_scan_i32_to(c.flag.p, c.pos.p, (int64_t)K * n, sc->scan_sums, s));
     }
-    if (out_old_to_new && tot) RAPID_CUDA(cudaMemcpyAsync(out_old_to_new, map.p, (size_t)tot * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    // ---- swap in ------------------------------------------------------------------------------------------------------------------
+    if (m > 0) {
+        k_cut_joiner_keys<<<dim3((unsigned)ceil_div<int64_t>(tot - n, TB), (unsigned)K), TB, 0, s>>>(K, n, tot, v->key_stride, c.kept.p, c.newid.p, n_surv, m,
+                                                                                                    v->key.p, c.jk.p, c.jv.p);
+        RAPID_KERNEL_CHECK();
+        if (m <= 32768) {
+            k_cut_joiner_rank<<<dim3((unsigned)ceil_div<int32_t>(m, 256), (unsigned)K), 256, 0, s>>>(m, c.jk.p, c.jv.p, c.jk2.p, c.jv2.p, c.collision.p);
+            RAPID_KERNEL_CHECK();
+        } else {
+            for (int k = 0; k < K; ++k)
+                RAPID_CHECK(sort_pairs(v, c.jk.p + (size_t)k * m, c.jk2.p + (size_t)k * m, c.jv.p + (size_t)k * m, c.jv2.p + (size_t)k * m, m, s));
+        }
+    }
+    if (n + m > 0) {
+        k_cut_merge<<<dim3((unsigned)ceil_div<int64_t>(n + m, TB), (unsigned)K), TB, 0, s>>>(n, n_surv, m, v->ring.p, v->sorted_key.p, c.flag.p, c.pos.p, c.newid.p,
+                                                                                            c.jk2.p, c.jv2.p, c.ring2.p, c.sk2.p, c.collision.p);
+        RAPID_KERNEL_CHECK();
+    }
+    int32_t coll = -1;
+    RAPID_CUDA(cudaMemcpyAsync(&coll, c.collision.p, sizeof(coll), cudaMemcpyDeviceToHost, s));
+    if (out_old_to_new && tot) RAPID_CUDA(cudaMemcpyAsync(out_old_to_new, c.map.p, (size_t)tot * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     RAPID_CUDA(cudaStreamSynchronize(s));
-    swap_buf(v->host_bytes, hb2); swap_buf(v->host_off, off2); swap_buf(v->port, port2);
-    swap_buf(v->key, key2); swap_buf(v->ring, ring2); swap_buf(v->sorted_key, sk2);
-    if (v->has_node_ids) { swap_buf(v->node_hi, nhi2); swap_buf(v->node_lo, nlo2); }
+    if (coll >= 0) { set_error("ring-%d key collision while adding joiners (TreeSet would silently drop one)", coll); return RAPID_EHASH_COLLISION; }
+    // ---- swap in ------------------------------------------------------------------------------------------------------------------
+    swap_buf(v->host_bytes, c.hb2); swap_buf(v->host_off, c.off2); swap_buf(v->port, c.port2);
+    swap_buf(v->key, c.key2); swap_buf(v->ring, c.ring2); swap_buf(v->sorted_key, c.sk2);
+    if (v->has_node_ids) { swap_buf(v->node_hi, c.nhi2); swap_buf(v->node_lo, c.nlo2); }
     v->key_stride = stride2;
     v->host_bytes_len = (size_t)bytes2;
     v->n = n2; v->nj = 0;

@@ -13,9 +13,9 @@
 #include <utility>
 #include <vector>
 
-#include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace rapid {
 
@@ -311,9 +311,9 @@ struct Wire {
     uint64_t table_epoch = 0;
     uint32_t T = 0;
     DevBuf<int32_t> table;
-    DevBuf<uint8_t> buf, cub_tmp;
+    DevBuf<uint8_t> buf;
     DevBuf<int64_t> moff;
-    DevBuf<int32_t> mlen, need, cnt, pos;
+    DevBuf<int32_t> mlen, need, cnt, pos, scan_sums;
     DevBuf<MsgRec> rec;
     DevBuf<WireScal> sc;
     PinnedBuf<WireScal> h_sc;
@@ -485,10 +485,7 @@ int32_t rapid_wire_decode_alerts(rapid_wire* w, const uint8_t* bytes, int64_t le
         }
         k_wire_counts<<<grid_for(M), TB, 0, s>>>(M, w->rec.p, w->cnt.p, w->sc.p);
         RAPID_KERNEL_CHECK();
-        size_t tb = 0;
-        RAPID_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, w->cnt.p, w->pos.p, (int)M, s));
-        RAPID_CHECK(w->cub_tmp.reserve(tb));
-        RAPID_CUDA(cub::DeviceScan::ExclusiveSum(w->cub_tmp.p, tb, w->cnt.p, w->pos.p, (int)M, s));
+        RAPID_CHECK(exclusive_scan_i32_to(w->cnt.p, w->pos.p, M, w->scan_sums, s));
         // every ring number is at least one byte on the wire: len bounds the number of cells
         const size_t cap = (size_t)std::max<int64_t>(len, 1);
         RAPID_CHECK(w->o_src.reserve(cap)); RAPID_CHECK(w->o_dst.reserve(cap)); RAPID_CHECK(w->o_ring.reserve(cap));

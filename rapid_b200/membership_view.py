@@ -127,16 +127,16 @@ class MembershipView:
         N.check(N.lib().rapid_view_register_joiners(self._h, len(port), N.ptr(hb), N.ptr(off), N.ptr(port), C.byref(first)))
         return list(range(first.value, first.value + len(port)))
 
-    def applyCut(self, cut_ids):
+    def applyCut(self, cut_ids, want_map=True):
         """decideViewChange (MembershipService.java:385-444): members in the cut leave, registered joiners in it are added;
         the K rings are updated on the device (compaction + sorted merge).  Returns old id -> new id (-1 = gone); detector handles
         on the old view are stale.  Raises UUIDAlreadySeenException (view unchanged) if NodeIds are set and a joiner's was seen."""
         ids = N.as_i32(cut_ids)
         tot = self.n + self.numJoiners()
-        mapping = np.empty(max(tot, 1), np.int32)
+        mapping = np.empty(max(tot, 1), np.int32) if want_map else None
         N.check(N.lib().rapid_view_apply_cut(self._h, N.ptr(ids), len(ids), N.ptr(mapping)))
         self.n = self.getMembershipSize()
-        return mapping[:tot]
+        return mapping[:tot] if want_map else None
 
     def joinerTables(self):
         """expected observers [n_joiners][K] of the registered joiners"""
