@@ -136,6 +136,8 @@ int32_t rapid_view_joiner_tables(const rapid_view* v, int32_t* out);
 #define RAPID_CD_RAW       1u   /* bare MultiNodeCutDetector semantics (aggregate / invalidate calls)             */
 #define RAPID_CD_SWEEP     2u   /* force the per-cell sweep kernel (exact counters; the simple path)               */
 #define RAPID_CD_BUCKETED  4u   /* force the subject-bucketed kernels (the fast path; SERVICE mode only)            */
+#define RAPID_CD_LOG       8u   /* bucketed handles: keep the epoch's filtered cells (6 B per cell + the blocked flags) so
+                                 * that rapid_cd_num_proposals can replay one receiver exactly; cleared by rapid_cd_clear  */
 
 /* delivery description: which receiver gets which cells, in which order */
 #define RAPID_DELIVERY_BLOCKED  1u   /* blocked[r] != 0: receiver r receives nothing this batch             */
@@ -223,7 +225,10 @@ int32_t rapid_cd_read_outputs(const rapid_cd* cd, uint64_t* proposal_hash, uint6
 /* The proposal receiver r announced, in canonical order = sorted by the ring-0 comparator
  * (MembershipService.java:346-348). */
 int32_t rapid_cd_get_proposal(const rapid_cd* cd, int64_t receiver, int32_t* out_ids, int32_t cap, int32_t* out_len);
-/* getNumProposals :62-66.  Exact on sweep handles; RAPID_EUNSUPPORTED on bucketed handles. */
+/* getNumProposals :62-66 (the reference's tests are its only caller).  Sweep handles count while they walk the cells.
+ * Subject-bucketed handles never see a receiver's cells in order, so they answer by REPLAYING that one receiver through the
+ * literal per-cell rule over the epoch's cell log — exact; needs RAPID_CD_LOG at creation (RAPID_EUNSUPPORTED otherwise, or once
+ * the epoch held a per-receiver BITMAP delivery or more than 2^24 cells). */
 int32_t rapid_cd_num_proposals(const rapid_cd* cd, int64_t receiver, int32_t* out);
 /* clear() :169-178 + announcedProposal = false (MembershipService.java:425-426) for every receiver. */
 int32_t rapid_cd_clear(rapid_cd* cd);
@@ -377,6 +382,10 @@ int32_t rapid_pxa_read(const rapid_pxa* a, int64_t acceptor, int32_t* ranks, uin
 /* A decoder owns the Endpoint{hostname, port} -> int32 id table of `v` (rebuilt when the view changes). */
 int32_t rapid_wire_create(rapid_wire** out, rapid_view* v);
 int32_t rapid_wire_destroy(rapid_wire* w);
+/* The configuration the receiver is in: from now on only UP alerts carrying this configurationId register their edgeDst as a
+ * joiner (a stale alert is dropped by filterAlertMessages, MembershipService.java:653, before it can introduce anything).
+ * Without it every UP alert about an unknown endpoint registers one. */
+int32_t rapid_wire_set_configuration(rapid_wire* w, int64_t cfg_id);
 /* One serialized BatchedAlertMessage (rapid.proto:95-99): every AlertMessage (:101-110) becomes one cell per ring
  * number (MultiNodeCutDetector.java:79-80), in message order then ring order.  Endpoints map to ids; the edgeDst of
  * an UP alert that is not in the dictionary yet is REGISTERED as a joiner (rapid_view_register_joiners) in order of
@@ -399,8 +408,12 @@ int32_t rapid_wire_read_cells(const rapid_wire* w, int32_t* src, int32_t* dst, u
 int32_t rapid_wire_read_messages(const rapid_wire* w, int32_t* dst, uint8_t* status, int32_t* n_rings, int64_t* node_high,
                                  int64_t* node_low, uint8_t* has_node_id, int64_t* meta_off, int32_t* meta_len);
 /* n serialized FastRoundPhase2bMessages (rapid.proto:105-110), message i = bytes[off[i] .. off[i+1]):
- * sender id (-1 if unknown), configurationId, and the proposal as rapid_proposal_fingerprint + size.  A proposal
- * naming an endpoint that is not in the dictionary cannot be identified: RAPID_ENOT_IN_RING. */
+ * sender id (-1 if unknown), configurationId, and the proposal as rapid_proposal_fingerprint + size.  An endpoint that is
+ * not in the dictionary (typical of a delayed vote of an earlier configuration, which FastPaxos.java:126-132 drops by its
+ * configurationId) enters the fingerprint through its ring-0 key instead of an id: identical lists keep identical
+ * fingerprints, nothing is refused, and rapid_fp_tally's configuration filter decides.  Proposal identity is
+ * ORDER-INSENSITIVE (the Java compares List<Endpoint> in order; every proposer sorts by the ring-0 comparator first,
+ * MembershipService.java:346-348, so well-formed votes never differ in order only). */
 int32_t rapid_wire_decode_votes(rapid_wire* w, const uint8_t* bytes, const int64_t* off, int64_t n, uint32_t flags,
                                 int32_t* sender, int64_t* vote_cfg, uint64_t* proposal_hash, uint64_t* proposal_hash2,
                                 int32_t* proposal_len);
@@ -433,6 +446,10 @@ int32_t rapid_fdet_tick_dev(rapid_fdet* fd, const uint8_t* node_flags_dev, const
 /* Cells of the last tick on the device (for rapid_cd_apply_batch_dev) / on the host; alerts as (observer, subject, ring bitmask). */
 int32_t rapid_fdet_cells_dev(const rapid_fdet* fd, const int32_t** src, const int32_t** dst, const uint8_t** ring,
                              const uint8_t** status, const int64_t** cfg);
+/* The last interval's cells grouped as the reference ships them — AlertBatcher sends ONE BatchedAlertMessage per sender and
+ * window (MembershipService.java:613-637): batch b = the cells raised by one observer.  batch_off[0 .. *n_batches] feeds
+ * rapid_cd_apply_batches_dev together with rapid_fdet_cells_dev; RAPID_ENOMEM (with *n_batches set) if cap is too small. */
+int32_t rapid_fdet_sender_batches(const rapid_fdet* fd, int64_t* batch_off, int64_t cap, int64_t* n_batches);
 int32_t rapid_fdet_read_cells(const rapid_fdet* fd, int32_t* src, int32_t* dst, uint8_t* ring, uint8_t* status, int64_t* cfg);
 int32_t rapid_fdet_read_alerts(const rapid_fdet* fd, int32_t* observer, int32_t* subject, uint16_t* ring_mask);
 /* failureCount / notified of node's k-th detector */

@@ -14,7 +14,7 @@ from . import _build
 OK = 0
 EINVAL, ENOT_IN_RING, EALREADY_IN_RING, EUUID_SEEN, EHASH_COLLISION, ECUDA, ENCCL, ENOMEM, EUNSUPPORTED = range(-1, -10, -1)
 
-CD_SERVICE, CD_RAW, CD_SWEEP, CD_BUCKETED = 0, 1, 2, 4
+CD_SERVICE, CD_RAW, CD_SWEEP, CD_BUCKETED, CD_LOG = 0, 1, 2, 4, 8
 DELIVERY_BLOCKED, DELIVERY_BITMAP, DELIVERY_PERMUTED = 1, 2, 4
 WIRE_REQUEST = 1
 EDGE_UP, EDGE_DOWN = 0, 1
@@ -117,6 +117,7 @@ SIGNATURES = {
     "rapid_pxa_reset": [_vp, _i64],
     "rapid_wire_create": [_pp, _vp],
     "rapid_wire_destroy": [_vp],
+    "rapid_wire_set_configuration": [_vp, _i64],
     "rapid_wire_decode_alerts": [_vp, _p, _i64, _u32, _p, _p, _p, _p, _p],
     "rapid_wire_cells_dev": [_vp, _p, _p, _p, _p, _p],
     "rapid_wire_read_cells": [_vp, _p, _p, _p, _p, _p],
@@ -129,6 +130,7 @@ SIGNATURES = {
     "rapid_fdet_tick": [_vp, _p, _p, _i64, _p, _p],
     "rapid_fdet_tick_dev": [_vp, _p, _p, _i64, _p, _p],
     "rapid_fdet_cells_dev": [_vp, _p, _p, _p, _p, _p],
+    "rapid_fdet_sender_batches": [_vp, _p, _i64, _p],
     "rapid_fdet_read_cells": [_vp, _p, _p, _p, _p, _p],
     "rapid_fdet_read_alerts": [_vp, _p, _p, _p],
     "rapid_fdet_state": [_vp, _i64, _i32, _p, _p],

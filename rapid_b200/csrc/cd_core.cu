@@ -15,6 +15,7 @@
 #include <cstdlib>
 
 #include "cd_internal.cuh"
+#include "radix.cuh"
 
 namespace rapid {
 
@@ -320,6 +321,7 @@ static void collect(CD* cd) {
     }
     if (c.sticky_overflow || c.sticky_bad_ring || c.sticky_bad_dst) {
         if (c.sticky_overflow) {
+            cd->log_complete = false;                       // a logged batch was not applied after all
             cd->deferred_rc = RAPID_ENOMEM;
             cd->deferred_msg = "a batch needed more subject slots than the handle holds and was NOT applied (asynchronous batches cannot "
                                "grow the handle: raise max_subjects, or use the synchronous entry points)";
@@ -399,12 +401,133 @@ static int32_t upload_delivery(CD* cd, int64_t A, const rapid_delivery* d, bool 
     return RAPID_OK;
 }
 
+// ---- RAPID_CD_LOG: the epoch's cells, and the exact replay of one receiver ---------------------------------------------------------
+constexpr size_t LOG_MAX_CELLS = (size_t)1 << 24;
+
+// after a batch (or a whole sequence) has been prepared: keep its filtered cells (slot per cell), ring numbers, status and the
+// delivery parameters; enqueued on the handle's stream (cell_slot is overwritten by the next prepare)
+static int32_t log_append(CD* cd, int64_t A, const uint8_t* ring_dev, const uint8_t* status_dev, const DeliveryDev& dl, uint64_t perm_seed_base,
+                          const int64_t* batch_off_host, int32_t n_batches) {
+    if (!cd->log_on || !cd->log_complete) return RAPID_OK;
+    if ((dl.flags & RAPID_DELIVERY_BITMAP) || cd->log_cells + (size_t)A > LOG_MAX_CELLS) { cd->log_complete = false; return RAPID_OK; }
+    cudaStream_t s = cd->stream;
+    const size_t c0 = cd->log_cells, n = (size_t)A;
+    if (n) {
+        RAPID_CHECK(cd->log_slot.reserve(c0 + n, true, s)); RAPID_CHECK(cd->log_ring.reserve(c0 + n, true, s)); RAPID_CHECK(cd->log_status.reserve(c0 + n, true, s));
+        RAPID_CUDA(cudaMemcpyAsync(cd->log_slot.p + c0, cd->cell_slot.p, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        RAPID_CUDA(cudaMemcpyAsync(cd->log_ring.p + c0, ring_dev, n, cudaMemcpyDeviceToDevice, s));
+        RAPID_CUDA(cudaMemcpyAsync(cd->log_status.p + c0, status_dev, n, cudaMemcpyDeviceToDevice, s));
+    }
+    int64_t boff = -1;
+    if (dl.flags & RAPID_DELIVERY_BLOCKED) {
+        boff = (int64_t)cd->log_blocked_bytes;
+        RAPID_CHECK(cd->log_blocked.reserve(cd->log_blocked_bytes + (size_t)cd->R, true, s));
+        RAPID_CUDA(cudaMemcpyAsync(cd->log_blocked.p + boff, dl.blocked, (size_t)cd->R, cudaMemcpyDeviceToDevice, s));
+        cd->log_blocked_bytes += (size_t)cd->R;
+    }
+    if (batch_off_host) {
+        for (int32_t b = 0; b < n_batches; ++b) {
+            if (batch_off_host[b] >= A) break;
+            const int64_t e = std::min<int64_t>(batch_off_host[b + 1], A);
+            if (e == batch_off_host[b]) continue;
+            cd->log_batches.push_back(CD::LogRec{(int64_t)c0 + batch_off_host[b], (int64_t)c0 + e, dl.flags, perm_seed_base + (uint64_t)b, boff});
+        }
+    } else {
+        cd->log_batches.push_back(CD::LogRec{(int64_t)c0, (int64_t)(c0 + n), dl.flags, perm_seed_base, boff});
+    }
+    cd->log_cells += n;
+    return RAPID_OK;
+}
+
+struct ReplayBatch { int64_t c0, c1; int32_t permuted, blocked; uint64_t rs; };
+// ONE receiver, the literal rule (MultiNodeCutDetector.java:84-128, :137-164, MembershipService.java:300-354) over the logged
+// batches in order.  Thread 0 walks the cells; the invalidation pass (order-independent) runs across the block.
+__global__ void __launch_bounds__(256) k_replay_receiver(int n_batches, const ReplayBatch* __restrict__ rb, const int32_t* __restrict__ cslot,
+                                                         const uint8_t* __restrict__ cring, const uint8_t* __restrict__ cstatus,
+                                                         const int32_t* __restrict__ order /* permuted batches: cell order of this receiver */,
+                                                         int32_t S, int K, int H, int L, const int32_t* __restrict__ slot_subject,
+                                                         const int32_t* __restrict__ slot_of, const int32_t* __restrict__ obs,
+                                                         uint16_t* __restrict__ m /* [S] zeroed */, uint16_t* __restrict__ tmp /* [S] */,
+                                                         int32_t* __restrict__ out /* [0] numProposals, [1] announced in batch (-1) */) {
+    __shared__ int s_npre, s_seen, s_nprop, s_emitted, s_raised;
+    const uint32_t RM = (1u << K) - 1u;
+    const int t = threadIdx.x;
+    if (t == 0) { s_npre = 0; s_seen = 0; s_nprop = 0; s_emitted = 0; out[1] = -1; }
+    __syncthreads();
+    for (int b = 0; b < n_batches; ++b) {
+        if (rb[b].blocked) continue;                       // nothing delivered to this receiver
+        if (t == 0) {
+            auto emit = [&]() {
+                for (int32_t s = 0; s < S; ++s) { const uint32_t w = m[s]; if (!(w & CD_BIT_EMIT) && __popc(w & RM) >= H) m[s] = (uint16_t)(w | CD_BIT_EMIT); }
+                ++s_nprop; s_emitted = 1;
+            };
+            for (int64_t q = rb[b].c0; q < rb[b].c1; ++q) {
+                const int64_t i = rb[b].permuted ? (int64_t)order[q] : q;
+                const int32_t slot = cslot[i];
+                if (slot < 0) continue;
+                if (cstatus[i] == RAPID_EDGE_DOWN) s_seen = 1;
+                uint32_t w = m[slot];
+                const uint32_t bit = 1u << cring[i];
+                if (w & bit) continue;
+                w |= bit; m[slot] = (uint16_t)w;
+                const int c = __popc(w & RM);
+                if (c == L) ++s_npre;
+                if (c == H) { --s_npre; if (s_npre == 0) emit(); }
+            }
+        }
+        __syncthreads();
+        if (s_seen && s_npre > 0) {                         // invalidateFailingEdges: implicit reports from observers in proposal U preProposal
+            if (t == 0) s_raised = 0;
+            __syncthreads();
+            for (int32_t s = t; s < S; s += 256) {
+                const uint32_t w0 = m[s];
+                uint32_t w = w0;
+                const int c0 = __popc(w0 & RM);
+                if (c0 >= L && c0 < H) {
+                    const int32_t subject = slot_subject[s];
+                    for (int k = 0; k < K; ++k) {
+                        const int32_t o = obs[(size_t)subject * K + k];
+                        const int32_t so = o >= 0 ? slot_of[o] : -1;
+                        if (so < 0 || so >= S) continue;
+                        const uint32_t wo = m[so];
+                        if ((wo & CD_BIT_EMIT) || __popc(wo & RM) < L) continue;
+                        w |= 1u << k;
+                    }
+                    if (__popc(w & RM) >= H) atomicAdd(&s_raised, 1);
+                }
+                tmp[s] = (uint16_t)w;
+            }
+            __syncthreads();
+            for (int32_t s = t; s < S; s += 256) m[s] = tmp[s];
+            __syncthreads();
+            if (t == 0 && s_raised > 0) {
+                s_npre -= s_raised;
+                if (s_npre == 0) {
+                    for (int32_t s = 0; s < S; ++s) { const uint32_t w = m[s]; if (!(w & CD_BIT_EMIT) && __popc(w & RM) >= H) m[s] = (uint16_t)(w | CD_BIT_EMIT); }
+                    ++s_nprop; s_emitted = 1;
+                }
+            }
+            __syncthreads();
+        }
+        if (s_emitted) { if (t == 0) out[1] = b; break; }   // announcedProposal: every later batch is ignored (:318-319)
+    }
+    __syncthreads();
+    if (t == 0) out[0] = s_nprop;
+}
+
+__global__ void k_replay_keys(int64_t c0, int64_t c1, uint64_t rs, uint64_t* __restrict__ key, int32_t* __restrict__ idx) {
+    const int64_t i = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c1) return;
+    key[i - c0] = splitmix64(rs ^ (uint64_t)(i - c0));
+    idx[i - c0] = (int32_t)i;
+}
+
 // ---- bucketed handles: one batch (or a whole sequence of batches in one pass: batch_off_dev != nullptr) -----------------------
 // Three-plus launches (prepare, apply, resolve kernels) and the copy of the counter snapshot, no host round trip in between.
 // The synchronous entry points wait here and replay the batch if the handle had to grow; the asynchronous one returns.
 static int32_t bucketed_one(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_dev, const uint8_t* ring_dev, const uint8_t* status_dev,
                             const int64_t* cfg_dev, const DeliveryDev& dl, bool async, const int64_t* batch_off_dev = nullptr,
-                            int32_t n_batches = 1, int32_t seq_last = 0) {
+                            int32_t n_batches = 1, int32_t seq_last = 0, bool do_log = true) {
     cd->cur_ring_dev = ring_dev;
     cd->cur_status_dev = status_dev;
     const bool seq = batch_off_dev != nullptr && seq_last > 0;
@@ -422,7 +545,10 @@ static int32_t bucketed_one(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_d
         RAPID_CUDA(cudaEventRecord(cd->ev1, cd->stream));
         RAPID_CUDA(cudaEventRecord(cd->ev_done, cd->stream));
         cd->pending = true;
-        if (async) return RAPID_OK;
+        if (async) {
+            if (do_log) RAPID_CHECK(log_append(cd, A, ring_dev, status_dev, dl, dl.perm_seed, nullptr, 1));   // (an overflow found later voids the log)
+            return RAPID_OK;
+        }
         RAPID_CUDA(cudaStreamSynchronize(cd->stream));
         const int32_t carried_rc = cd->deferred_rc;            // errors of EARLIER asynchronous batches stay latched
         const std::string carried_msg = cd->deferred_msg;
@@ -434,6 +560,7 @@ static int32_t bucketed_one(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_d
             ++cd->retries;
             continue;
         }
+        if (do_log && !cd->last.overflow) RAPID_CHECK(log_append(cd, A, ring_dev, status_dev, dl, dl.perm_seed, nullptr, 1));
         const int32_t rc = bad_cell_status(cd, cd->last);
         if (rc != RAPID_OK) { cd->deferred_rc = carried_rc; cd->deferred_msg = carried_msg; return rc; }
         return RAPID_OK;
@@ -521,10 +648,11 @@ static int32_t bucketed_sequence(CD* cd, int64_t cfg, int64_t A, const int32_t* 
         DeliveryDev d = dl;
         d.perm_seed = dl.perm_seed + (uint64_t)last;             // the moments that matter are those of the last batch
         d.cell_base = off[last];
-        const int32_t rc = bucketed_one(cd, cfg, off[last + 1], dst_dev, ring_dev, status_dev, cfg_dev, d, false, batch_off_dev, n_batches, last);
+        const int32_t rc = bucketed_one(cd, cfg, off[last + 1], dst_dev, ring_dev, status_dev, cfg_dev, d, false, batch_off_dev, n_batches, last, false);
         if (rc != RAPID_OK && rc != RAPID_EINVAL) return rc;
         if (!cd->last.seq_abort) {
             keep(rc);
+            if (!cd->last.overflow) RAPID_CHECK(log_append(cd, off[last + 1], ring_dev, status_dev, dl, dl.perm_seed, off, n_batches));
             ++cd->seq_merged;
             RAPID_CHECK(note(last));
             RAPID_CHECK(finish());
@@ -573,6 +701,54 @@ static int32_t apply_common(CD* cd, int64_t cfg, int64_t A, const int32_t* dst_d
     return bad_cell_status(cd, bc);
 }
 
+// getNumProposals of ONE receiver of a bucketed handle: replay its epoch through the literal per-cell rule (the bucketed kernels
+// never see a receiver's cells in order, so they cannot count emissions; the log can)
+static int32_t replay_num_proposals(CD* cd, int64_t receiver, int32_t* out) {
+    if (!cd->log_on) { set_error("getNumProposals on the subject-bucketed kernels replays the epoch's cell log: create the handle with RAPID_CD_LOG (or use a RAPID_CD_SWEEP handle)"); return RAPID_EUNSUPPORTED; }
+    if (!cd->log_complete) { set_error("the epoch's cell log is incomplete (a per-receiver BITMAP delivery, more than 2^24 cells, or a batch that was not applied)"); return RAPID_EUNSUPPORTED; }
+    cudaStream_t s = cd->stream;
+    const size_t nb = cd->log_batches.size();
+    const int32_t S = cd->S;
+    if (nb == 0 || S == 0) { *out = 0; return RAPID_OK; }
+    std::vector<ReplayBatch> rb(nb);
+    std::vector<uint8_t> blk(1);
+    DevBuf<int32_t> order, idx, d_out;
+    DevBuf<uint64_t> key, skey;
+    DevBuf<uint16_t> m, tmp;
+    DevBuf<ReplayBatch> d_rb;
+    RadixScratch rs;
+    RAPID_CHECK(order.reserve(std::max<size_t>(cd->log_cells, 1))); RAPID_CHECK(d_out.reserve(2)); RAPID_CHECK(d_rb.reserve(nb));
+    RAPID_CHECK(m.reserve((size_t)S)); RAPID_CHECK(tmp.reserve((size_t)S));
+    RAPID_CUDA(cudaMemsetAsync(m.p, 0, (size_t)S * sizeof(uint16_t), s));
+    for (size_t b = 0; b < nb; ++b) {
+        const CD::LogRec& r = cd->log_batches[b];
+        rb[b].c0 = r.c0; rb[b].c1 = r.c1; rb[b].permuted = (r.flags & RAPID_DELIVERY_PERMUTED) ? 1 : 0; rb[b].blocked = 0;
+        rb[b].rs = splitmix64(r.perm_seed + (uint64_t)(cd->rbegin + receiver));
+        if (r.blocked_off >= 0) {
+            RAPID_CUDA(cudaMemcpyAsync(blk.data(), cd->log_blocked.p + r.blocked_off + receiver, 1, cudaMemcpyDeviceToHost, s));
+            RAPID_CUDA(cudaStreamSynchronize(s));
+            rb[b].blocked = blk[0] ? 1 : 0;
+        }
+        if (rb[b].permuted && !rb[b].blocked && r.c1 > r.c0) {
+            // this receiver's own order of the batch: ascending splitmix64(rs ^ index inside the batch)
+            const int64_t n = r.c1 - r.c0;
+            RAPID_CHECK(key.reserve((size_t)n)); RAPID_CHECK(skey.reserve((size_t)n)); RAPID_CHECK(idx.reserve((size_t)n));
+            k_replay_keys<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, s>>>(r.c0, r.c1, rb[b].rs, key.p, idx.p);
+            RAPID_KERNEL_CHECK();
+            RAPID_CHECK(radix_sort_pairs<uint64_t>(rs, key.p, idx.p, skey.p, order.p + r.c0, n, 0, 64, s));
+        }
+    }
+    RAPID_CUDA(cudaMemcpyAsync(d_rb.p, rb.data(), nb * sizeof(ReplayBatch), cudaMemcpyHostToDevice, s));
+    k_replay_receiver<<<1, 256, 0, s>>>((int)nb, d_rb.p, cd->log_slot.p, cd->log_ring.p, cd->log_status.p, order.p, S, cd->K, cd->H, cd->L,
+                                        cd->slot_subject.p, cd->slot_of.p, cd->view->obs.p, m.p, tmp.p, d_out.p);
+    RAPID_KERNEL_CHECK();
+    int32_t h[2] = {0, -1};
+    RAPID_CUDA(cudaMemcpyAsync(h, d_out.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    RAPID_CUDA(cudaStreamSynchronize(s));
+    *out = h[0];
+    return RAPID_OK;
+}
+
 }  // namespace rapid
 
 using namespace rapid;
@@ -602,6 +778,7 @@ int32_t rapid_cd_create(rapid_cd** out, const rapid_view* v, int32_t H, int32_t 
     cd->mode = mode_flags;
     cd->raw = raw;
     cd->bucketed = !raw && !(mode_flags & RAPID_CD_SWEEP);
+    cd->log_on = cd->bucketed && (mode_flags & RAPID_CD_LOG);
     cd->nbuf = cd->bucketed ? 2 : 1;
     cd->R = n_receivers;
     cd->rbegin = receiver_begin;
@@ -673,6 +850,7 @@ int32_t rapid_cd_clear(rapid_cd* cd) {
         // list and the device counters — ONE launch, no host round trip (the slot count lives on the device).
         cd->S = 0;
         RAPID_CHECK(bucketed_clear(cd));
+        cd->log_cells = 0; cd->log_blocked_bytes = 0; cd->log_batches.clear(); cd->log_complete = true;
     } else {
         if (cd->S > 0) {
             k_reset_slots<<<(unsigned)ceil_div<int32_t>(cd->S, 256), 256, 0, s>>>(cd->S, cd->counts.p, cd->slot_subject.p, cd->slot_of.p, cd->cur.p);
@@ -982,9 +1160,9 @@ int32_t rapid_cd_get_proposal(const rapid_cd* cd, int64_t receiver, int32_t* out
 
 int32_t rapid_cd_num_proposals(const rapid_cd* cd, int64_t receiver, int32_t* out) {
     if (!cd || !out || receiver < 0 || receiver >= cd->R) { set_error("bad arguments"); return RAPID_EINVAL; }
-    if (cd->bucketed) { set_error("getNumProposals is exact only on sweep handles (RAPID_CD_SWEEP / RAPID_CD_RAW)"); return RAPID_EUNSUPPORTED; }
     DeviceGuard g(cd->device);
     RAPID_CHECK(cd_wait(cd, false));     // clear() and asynchronous batches are still in flight on the handle's stream
+    if (cd->bucketed) return replay_num_proposals(const_cast<rapid_cd*>(cd), receiver, out);
     RAPID_CUDA(cudaMemcpy(out, cd->n_prop.p + receiver, sizeof(int32_t), cudaMemcpyDeviceToHost));
     return RAPID_OK;
 }

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -87,6 +88,13 @@ struct CD {
     DevBuf<int32_t> out_batch;        // [R] ... and the batch in which each receiver announced
     DevBuf<uint64_t> sq_h1, sq_h2;    // [R] outputs of the announcing batch while a sequence is replayed batch by batch
     DevBuf<int32_t> sq_len;
+    // ---- RAPID_CD_LOG: the epoch's filtered cells, for the exact replay of ONE receiver (rapid_cd_num_proposals) -------------
+    struct LogRec { int64_t c0, c1; uint32_t flags; uint64_t perm_seed; int64_t blocked_off; };
+    bool log_on = false, log_complete = true;
+    DevBuf<int32_t> log_slot;         // per logged cell: subject slot, -1 = filtered out
+    DevBuf<uint8_t> log_ring, log_status, log_blocked;
+    size_t log_cells = 0, log_blocked_bytes = 0;
+    std::vector<LogRec> log_batches;
     int32_t seq_merged = 0, seq_replayed = 0;   // sequences served in one pass / replayed batch by batch (diagnostics)
     int32_t seq_refused_a1 = 0, seq_refused_a2 = 0;   // receivers that failed either premise in the last refused attempt
     DevBuf<int32_t> out_len;          // [R]

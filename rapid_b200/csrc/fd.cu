@@ -7,6 +7,8 @@
 #include <limits.h>
 
 
+#include <vector>
+
 #include "common.cuh"
 #include "radix.cuh"
 #include "scan.cuh"
@@ -247,6 +249,29 @@ int32_t rapid_fdet_cells_dev(const rapid_fdet* h, const int32_t** src, const int
     if (ring) *ring = fd->c_ring.p;
     if (status) *status = fd->c_status.p;
     if (cfg) *cfg = fd->c_cfg.p;
+    return RAPID_OK;
+}
+
+// The interval's cells grouped the way the reference ships them: AlertBatcher (MembershipService.java:613-637) sends ONE
+// BatchedAlertMessage per sender and window, so batch b = the cells raised by one observer (cells are ordered by node already).
+// batch_off[0 .. *n_batches] for rapid_cd_apply_batches[_dev]; RAPID_ENOMEM if cap (entries) is too small (*n_batches is set).
+int32_t rapid_fdet_sender_batches(const rapid_fdet* h, int64_t* batch_off, int64_t cap, int64_t* n_batches) {
+    const rapid_fdet* fd = h;
+    if (!fd || !n_batches || (cap > 0 && !batch_off)) { set_error("bad arguments"); return RAPID_EINVAL; }
+    DeviceGuard g(fd->device);
+    const size_t n = (size_t)fd->n_cells;
+    std::vector<int32_t> src(n);
+    if (n) {
+        RAPID_CUDA(cudaMemcpyAsync(src.data(), fd->c_src.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, fd->stream));
+        RAPID_CUDA(cudaStreamSynchronize(fd->stream));
+    }
+    int64_t nb = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (i == 0 || src[i] != src[i - 1]) { if (nb < cap) batch_off[nb] = (int64_t)i; ++nb; }
+    }
+    *n_batches = nb;
+    if (nb + 1 > cap) { set_error("batch_off holds %lld entries, %lld needed", (long long)cap, (long long)nb + 1); return RAPID_ENOMEM; }
+    batch_off[nb] = (int64_t)n;
     return RAPID_OK;
 }
 

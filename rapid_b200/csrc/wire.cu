@@ -132,7 +132,7 @@ struct WireScal {
 // pass 1: parse every AlertMessage, resolve its endpoints, count its ring numbers
 __global__ void k_wire_parse_alerts(int64_t M, const uint8_t* __restrict__ buf, const int64_t* __restrict__ moff,
                                     const int32_t* __restrict__ mlen, Dict d, MsgRec* __restrict__ rec, int32_t* __restrict__ need,
-                                    WireScal* __restrict__ sc) {
+                                    WireScal* __restrict__ sc, int have_cfg, int64_t cur_cfg) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     MsgRec r;
@@ -177,7 +177,9 @@ __global__ void k_wire_parse_alerts(int64_t M, const uint8_t* __restrict__ buf, 
     r.dst_id = r.dst.present ? ep_lookup(buf, r.dst, d.T, d.table, d.key0, d.hb, d.hoff, d.hport) : -1;
     // a default-valued edgeDst (field absent) is the endpoint {"" , 0}: resolvable like any other
     if (!r.dst.present) { EpRef e{0, 0, 0, 1}; r.dst = e; r.dst_id = ep_lookup(buf, e, d.T, d.table, d.key0, d.hb, d.hoff, d.hport); }
-    const bool nd = r.dst_id < 0 && r.status == 0;                                        // UP about an unknown endpoint
+    // UP about an unknown endpoint: a joiner — but only an alert of the CURRENT configuration may introduce one (a stale one is
+    // dropped by filterAlertMessages, MembershipService.java:653, before extractJoinerUuidAndMetadata ever sees it)
+    const bool nd = r.dst_id < 0 && r.status == 0 && (!have_cfg || r.cfg == cur_cfg);
     need[m] = nd ? 1 : 0;
     if (nd) atomicAdd(&sc->n_need, 1);
     rec[m] = r;
@@ -286,7 +288,15 @@ __global__ void k_wire_votes(int64_t n, const uint8_t* __restrict__ buf, const i
                     EpRef e{0, 0, 0, 0};
                     parse_endpoint(buf, q, ql, &e, &ok);
                     const int32_t id = ep_lookup(buf, e, d.T, d.table, d.key0, d.hb, d.hoff, d.hport);
-                    if (id < 0) unknown = true; else { a += fp_mix1(id); b += fp_mix2(id); }
+                    if (id >= 0) { a += fp_mix1(id); b += fp_mix2(id); }
+                    else {
+                        // an endpoint outside the dictionary (a vote of another configuration, say — FastPaxos.java:126-132 drops
+                        // those by their configurationId, not by their content): it still gets an identity — its ring-0 key — so that
+                        // identical lists keep identical fingerprints and the tally's own filters decide what the vote is worth
+                        const uint64_t kk = (uint64_t)ring_key(buf + e.off, e.len, e.port, 0);
+                        a += splitmix64(kk ^ 0x554E4B4E4F574E31ULL); b += splitmix64((kk * 0xD6E8FEB86659FD93ULL) ^ 0x554E4B4E4F574E32ULL);
+                        unknown = true;
+                    }
                     ++cnt;
                 }
             }
@@ -296,7 +306,7 @@ __global__ void k_wire_votes(int64_t n, const uint8_t* __restrict__ buf, const i
         if (!r.ok) ok = false;
     }
     if (!ok) { atomicMin(&sc->bad_msg, (int32_t)i); sender[i] = -1; cfg[i] = 0; h1[i] = 0; h2[i] = 0; len[i] = 0; return; }
-    if (unknown) atomicMin(&sc->bad_vote, (int32_t)i);
+    if (unknown) atomicMin(&sc->bad_vote, (int32_t)i);       // reported as a count-free diagnostic only (first such vote)
     sender[i] = ep_lookup(buf, s, d.T, d.table, d.key0, d.hb, d.hoff, d.hport);
     cfg[i] = c; h1[i] = a; h2[i] = b; len[i] = cnt;
 }
@@ -309,6 +319,8 @@ struct Wire {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
     uint64_t table_epoch = 0;
+    bool have_cfg = false;            // rapid_wire_set_configuration: only alerts of this configuration register joiners
+    int64_t cur_cfg = 0;
     uint32_t T = 0;
     DevBuf<int32_t> table;
     DevBuf<uint8_t> buf;
@@ -394,6 +406,12 @@ int32_t rapid_wire_create(rapid_wire** out, rapid_view* v) {
     return RAPID_OK;
 }
 
+int32_t rapid_wire_set_configuration(rapid_wire* w, int64_t cfg_id) {
+    if (!w) { set_error("NULL handle"); return RAPID_EINVAL; }
+    w->have_cfg = true; w->cur_cfg = cfg_id;
+    return RAPID_OK;
+}
+
 int32_t rapid_wire_destroy(rapid_wire* w) {
     if (!w) return RAPID_OK;
     DeviceGuard g(w->device);
@@ -450,7 +468,7 @@ int32_t rapid_wire_decode_alerts(rapid_wire* w, const uint8_t* bytes, int64_t le
         RAPID_CHECK(w->cnt.reserve((size_t)M)); RAPID_CHECK(w->pos.reserve((size_t)M)); RAPID_CHECK(w->rec.reserve((size_t)M));
         RAPID_CUDA(cudaMemcpyAsync(w->moff.p, moff.data(), (size_t)M * sizeof(int64_t), cudaMemcpyHostToDevice, s));
         RAPID_CUDA(cudaMemcpyAsync(w->mlen.p, mlen.data(), (size_t)M * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-        k_wire_parse_alerts<<<grid_for(M), TB, 0, s>>>(M, w->buf.p, w->moff.p, w->mlen.p, d, w->rec.p, w->need.p, w->sc.p);
+        k_wire_parse_alerts<<<grid_for(M), TB, 0, s>>>(M, w->buf.p, w->moff.p, w->mlen.p, d, w->rec.p, w->need.p, w->sc.p, w->have_cfg ? 1 : 0, w->cur_cfg);
         RAPID_KERNEL_CHECK();
         RAPID_CHECK(wire_read_scal(w));
         if (w->h_sc.p->bad_msg != INT_MAX) { set_error("malformed AlertMessage at index %d", w->h_sc.p->bad_msg); return RAPID_EINVAL; }
@@ -585,7 +603,7 @@ int32_t rapid_wire_decode_votes(rapid_wire* w, const uint8_t* bytes, const int64
     RAPID_CHECK(wire_read_scal(w));
     cudaEventElapsedTime(&w->last_ms, w->ev0, w->ev1);
     if (w->h_sc.p->bad_msg != INT_MAX) { set_error("malformed FastRoundPhase2bMessage at index %d", w->h_sc.p->bad_msg); return RAPID_EINVAL; }
-    if (w->h_sc.p->bad_vote != INT_MAX) { set_error("vote %d names an endpoint that is not in the dictionary", w->h_sc.p->bad_vote); return RAPID_ENOT_IN_RING; }
+    // (a vote naming an endpoint outside the dictionary is NOT an error: see k_wire_votes)
     const size_t m = (size_t)n;
     if (sender) RAPID_CUDA(cudaMemcpyAsync(sender, w->v_sender.p, m * 4, cudaMemcpyDeviceToHost, s));
     if (vote_cfg) RAPID_CUDA(cudaMemcpyAsync(vote_cfg, w->v_cfg.p, m * 8, cudaMemcpyDeviceToHost, s));

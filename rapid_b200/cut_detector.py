@@ -89,11 +89,13 @@ class VirtualCluster:
     Receiver r is the node at ring-0 position receiver_begin + r.
     """
 
-    def __init__(self, view: MembershipView, H, L, n_receivers=None, receiver_begin=0, kernel="auto", max_subjects=0):
+    def __init__(self, view: MembershipView, H, L, n_receivers=None, receiver_begin=0, kernel="auto", max_subjects=0, log=False):
         self.view = view
         self.R = int(view.n if n_receivers is None else n_receivers)
         self.receiver_begin = int(receiver_begin)
         flags = {"auto": N.CD_SERVICE, "sweep": N.CD_SWEEP, "bucketed": N.CD_BUCKETED}[kernel]
+        if log:
+            flags |= N.CD_LOG              # keep the epoch's cells: getNumProposals on the bucketed kernels
         self._h = C.c_void_p()
         rc = N.lib().rapid_cd_create(C.byref(self._h), view._h, int(H), int(L), self.R, self.receiver_begin, flags,
                                      int(max_subjects))

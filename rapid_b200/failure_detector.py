@@ -57,6 +57,15 @@ class EdgeFailureDetectors:
         N.check(N.lib().rapid_fdet_read_cells(self._h, N.ptr(src), N.ptr(dst), N.ptr(ring), N.ptr(status), N.ptr(cfg)))
         return src, dst, ring, status, cfg
 
+    def senderBatches(self):
+        """batch offsets of the last tick's cells grouped per sender, the way AlertBatcher ships them (one BatchedAlertMessage
+        per observer and window, MembershipService.java:613-637): feed VirtualCluster.handleBatchesDevice"""
+        cap = self.n_cells + 2
+        off = np.zeros(cap, np.int64)
+        nb = C.c_int64(0)
+        N.check(N.lib().rapid_fdet_sender_batches(self._h, N.ptr(off), cap, C.byref(nb)))
+        return off[: nb.value + 1]
+
     def cellsDevice(self):
         p = [C.c_void_p() for _ in range(5)]
         N.check(N.lib().rapid_fdet_cells_dev(self._h, *[C.byref(x) for x in p]))

@@ -39,6 +39,10 @@ class WireDecoder:
         except Exception:
             pass
 
+    def setConfiguration(self, cfg_id):
+        """only UP alerts of this configuration may register joiners from now on (MembershipService.java:653)"""
+        N.check(N.lib().rapid_wire_set_configuration(self._h, int(cfg_id)))
+
     def decodeBatchedAlertMessage(self, data, is_request=False):
         """bytes of a BatchedAlertMessage (or of the RapidRequest carrying it) -> DecodedAlerts; the cells stay on the device"""
         buf = np.frombuffer(bytes(data), dtype=np.uint8) if len(data) else np.zeros(1, np.uint8)

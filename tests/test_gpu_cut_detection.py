@@ -273,6 +273,46 @@ def test_num_proposals_sweep(orc, rb):
         assert cl.getNumProposals(r) == sim.numProposals(r)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_num_proposals_on_the_bucketed_kernels_by_replay(orc, rb, seed):
+    """getNumProposals (MultiNodeCutDetector.java:62-66) on a bucketed handle created with RAPID_CD_LOG: the receiver asked about is
+    replayed through the per-cell rule over the epoch's cell log — several batches, blocked receivers, permuted delivery, a
+    sequence call, several emissions inside one batch (small H / L); after clear() the count starts over."""
+    rng = np.random.default_rng(4100 + seed)
+    n = int(rng.integers(40, 600))
+    Hh, Ll = [(8, 2), (9, 4), (3, 1)][seed % 3]
+    w = OracleWorld(orc, n, K)
+    v = rb.MembershipView.from_packed(K, *w.member_packed())
+    sim = orc.ClusterSim(w.view, K, Hh, Ll, n)
+    cl = rb.VirtualCluster(v, Hh, Ll, kernel="bucketed", log=True)
+    cfg = w.view.getCurrentConfigurationId()
+    for epoch in range(2):
+        for call in range(3):
+            src, dst, ring, status = random_batch(rng, n, K, int(rng.integers(1, 7)), int(rng.integers(10, 90)), n)
+            blocked = (rng.random(n) < 0.15).astype(np.uint8) if call == 1 else None
+            perm = int(rng.integers(1, 2**60)) if (seed + call) % 2 else None
+            if call == 2:
+                A = len(dst)
+                off = np.concatenate([[0], np.sort(rng.integers(0, A + 1, size=3)), [A]]).astype(np.int64)
+                for b in range(len(off) - 1):
+                    sl = slice(int(off[b]), int(off[b + 1]))
+                    sim.apply_batch(src[sl], dst[sl], ring[sl], status[sl], np.full(sl.stop - sl.start, cfg, np.int64), blocked=blocked,
+                                    perm_seed=None if perm is None else perm + b, threads=2)
+                cl.handleBatches(cfg, src, dst, ring, status, off, blocked=blocked, perm_seed=perm)
+            else:
+                compare_batch(rb, w, sim, cl, None, (src, dst, ring, status), blocked=blocked, perm_seed=perm)
+            for r in rng.choice(n, size=6, replace=False).tolist():
+                assert cl.getNumProposals(r) == sim.numProposals(r), "receiver %d after call %d" % (r, call)
+        if (Hh, Ll) == (3, 1):
+            assert max(sim.numProposals(r) for r in range(n)) >= 1      # (with H = 3 the random batches do emit)
+        cl.clear(); sim.reset()
+        assert cl.getNumProposals(0) == 0
+    # without the log the bucketed kernels cannot answer
+    plain = rb.VirtualCluster(v, Hh, Ll, kernel="bucketed")
+    with pytest.raises(rb.RapidError):
+        plain.getNumProposals(0)
+
+
 @pytest.mark.parametrize("permuted", [False, True])
 def test_mixed_receivers_take_the_interval_analysis(orc, rb, permuted):
     """a proposal is emitted early in the batch, then another subject enters the unstable band and stays there:

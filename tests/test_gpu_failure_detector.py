@@ -94,6 +94,49 @@ def test_detectors_to_decision_without_leaving_the_device(orc, rb):
     assert fd.tick(flags, 5) == (0, 0)                        # notified once
 
 
+def test_detectors_to_per_sender_batches_on_the_device(orc, rb):
+    """the same scenario shipped the way the reference ships it: ONE BatchedAlertMessage per sender (AlertBatcher,
+    MembershipService.java:613-637), handled one by one with the announcedProposal gating — as a single rapid_cd_apply_batches_dev
+    call on the cells in the detectors' buffers.  Checked against the oracle handling every sender's batch on its own."""
+    import torch
+    n, K = 4_000, 10
+    w = OracleWorld(orc, n, K)
+    v = rb.MembershipView.from_packed(K, *w.member_packed())
+    obs, _ = v.tables()
+    b = W.c2_simultaneous_crash(obs, n)
+    flags = np.zeros(n, np.uint8)
+    flags[np.asarray(b.expected_cut)] = 1
+    fd = rb.EdgeFailureDetectors(v)
+    cfg = w.view.getCurrentConfigurationId()
+    for t in range(10):
+        assert fd.tick(flags, cfg) == (0, 0)
+    na, nc = fd.tick(flags, cfg)
+    off = fd.senderBatches()
+    src, dst, ring, status, ccfg = fd.cells()
+    assert off[0] == 0 and off[-1] == nc and len(off) - 1 == len(np.unique(src))
+    assert all(len(set(src[off[i]: off[i + 1]].tolist())) == 1 for i in range(len(off) - 1))
+    ring0 = np.asarray(v.getRing(0))
+    blocked = np.ascontiguousarray(flags[ring0])
+    d_blocked = torch.from_numpy(blocked).cuda()
+    cl = rb.VirtualCluster(v, 9, 4, kernel="bucketed")
+    p = fd.cellsDevice()
+    cl.handleBatchesDevice(cfg, nc, p[1], p[2], p[3], off, cell_cfg_dev=p[4], blocked_dev=d_blocked.data_ptr())
+    res, ain = cl.readOutputs(), cl.readAnnouncedIn()
+    # the oracle: every sender's batch on its own, in order
+    sim = orc.ClusterSim(w.view, K, 9, 4, n)
+    want_in, want_len = np.full(n, -1, np.int32), np.zeros(n, np.int32)
+    for i in range(len(off) - 1):
+        sl = slice(int(off[i]), int(off[i + 1]))
+        o_len, o_ann, o_ids, o_off = sim.apply_batch(src[sl], dst[sl], ring[sl], status[sl], ccfg[sl], blocked=blocked, threads=4)
+        for r in np.nonzero(o_len)[0]:
+            want_in[r], want_len[r] = i, o_len[r]
+    np.testing.assert_array_equal(ain, want_in)
+    np.testing.assert_array_equal(res.proposal_len, want_len)
+    np.testing.assert_array_equal(res.announced, o_ann)
+    live = blocked == 0
+    assert (want_len[live] > 0).all()
+
+
 def test_view_change_requires_reset(orc, rb):
     n, K = 50, 10
     w = OracleWorld(orc, n, K)

@@ -228,10 +228,22 @@ def test_votes_decode_to_sender_cfg_and_fingerprint(rb, pb, as_request):
     # the decoded votes go straight into the tally
     fp = rb.FastPaxos(3, n, sender_capacity=n + 16)
     fp.handleFastRoundProposals(np.where(s >= 0, s, n + 5), h1, h2, ln, vote_cfg=c)
-    stranger = pb.FastRoundPhase2bMessage()
-    stranger.endpoints.add().hostname = b"nobody"
-    with pytest.raises(rb.RapidError):
-        dec.decodeFastRoundPhase2bMessages([stranger.SerializeToString()])
+    # A vote naming an endpoint the dictionary does not hold — a delayed vote of an EARLIER configuration about a node that has
+    # since left, say — is not an error and does not take the rest of the burst down with it (FastPaxos.java:126-132 drops it by
+    # its configurationId): it decodes, identical stranger lists get identical fingerprints, and the tally's filter does the rest.
+    def stranger(cfg_id, port):
+        m = pb.FastRoundPhase2bMessage()
+        m.sender.CopyFrom(ep(pb, 7))
+        m.configurationId = cfg_id
+        m.endpoints.add().CopyFrom(ep(pb, 1))
+        e = m.endpoints.add(); e.hostname = b"nobody"; e.port = port
+        return pb.RapidRequest(fastRoundPhase2bMessage=m).SerializeToString() if as_request else m.SerializeToString()
+    good = msgs[:5]
+    s2, c2, g1, g2, l2 = dec.decodeFastRoundPhase2bMessages([stranger(99, 1), stranger(99, 1), stranger(99, 2)] + good, is_request=as_request)
+    assert list(zip(s2[3:].tolist(), c2[3:].tolist(), g1[3:].tolist(), g2[3:].tolist(), l2[3:].tolist())) == want[:5]
+    assert l2[:3].tolist() == [2, 2, 2] and c2[:3].tolist() == [99, 99, 99]
+    assert (g1[0], g2[0]) == (g1[1], g2[1]) and (g1[0], g2[0]) != (g1[2], g2[2])
+    assert (int(g1[0]), int(g2[0])) != rb.proposal_fingerprint([1])
     with pytest.raises(rb.RapidError):
         dec.decodeFastRoundPhase2bMessages([msgs[0][:-1]], is_request=as_request)
 
@@ -262,3 +274,26 @@ def test_one_hundred_thousand_alert_messages(rb, pb):
     assert status.min() == 1 and (cfg == 42).all()
     assert pb.BatchedAlertMessage.FromString(data).messages[77].edgeDst.port == int(ports[subj[77]])
     print("decode of %d bytes: %.3f ms on the device" % (len(data), dec.lastDeviceMs()))
+
+
+def test_only_alerts_of_the_current_configuration_register_joiners(rb, pb):
+    """filterAlertMessages (MembershipService.java:653) drops a stale alert before extractJoinerUuidAndMetadata sees it: with the
+    receiver's configuration set on the decoder, an UP alert of another configuration about an unknown endpoint registers nothing
+    (and so does not disturb state that hangs off the endpoint dictionary), while one of the current configuration does."""
+    n = 300
+    view = make_view(rb, n)
+    dec = rb.WireDecoder(view)
+    dec.setConfiguration(42)
+
+    def up(j, cfg):
+        a = pb.AlertMessage()
+        a.edgeSrc.CopyFrom(ep(pb, 3)); a.edgeDst.CopyFrom(ep(pb, j)); a.edgeStatus = 0; a.configurationId = cfg
+        a.ringNumber.extend([0, 1])
+        return a
+    b = pb.BatchedAlertMessage()
+    b.sender.CopyFrom(ep(pb, 3))
+    b.messages.extend([up(n + 1, 41), up(n + 2, 42), up(n + 1, 41)])
+    r = dec.decodeBatchedAlertMessage(b.SerializeToString())
+    assert view.numJoiners() == 1                           # only the endpoint named by the configuration-42 alert
+    src, dst, ring, status, cfg = dec.cells()
+    assert dst.tolist() == [n, n] and cfg.tolist() == [42, 42] and r.n_dropped == 2
