@@ -19,7 +19,7 @@ final class GpuMembershipView {
     private final long handle;
     private final List<Endpoint> byId = new ArrayList<>();
     private final Map<Endpoint, Integer> ids = new HashMap<>();
-    private final int members;
+    private int members;
 
     GpuMembershipView(final int K, final List<Endpoint> endpoints, final int device) {
         this.K = K;
@@ -68,6 +68,63 @@ final class GpuMembershipView {
 
     Endpoint endpointOf(final int id) {
         return byId.get(id);
+    }
+
+
+    /**
+     * decideViewChange (MembershipService.java:385-444) on the device: the members named by the decision leave (ringDelete
+     * :167-201), the joiners named by it — registered when their UP alerts arrived — are added (ringAdd :123-160).  The K rings
+     * are updated in HBM (compaction + sorted merge); only the cut's ids go down and the id mapping comes back.
+     */
+    void applyViewChange(final List<Endpoint> decidedCut) {
+        final int[] cut = new int[decidedCut.size()];
+        for (int i = 0; i < cut.length; i++) {
+            cut[i] = idOf(decidedCut.get(i), false);
+        }
+        final int[] oldToNew = new int[byId.size()];
+        final int rc = Native.viewApplyCut(handle, cut, oldToNew);
+        if (rc == -4) {                                       // RAPID_EUUID_SEEN
+            throw new MembershipView.UUIDAlreadySeenException(decidedCut.get(0), null);
+        }
+        if (rc != 0) {
+            throw new IllegalStateException(Native.lastError());
+        }
+        final List<Endpoint> old = new ArrayList<>(byId);
+        byId.clear();
+        ids.clear();
+        int n = 0;
+        for (int oldId = 0; oldId < old.size(); oldId++) {
+            if (oldToNew[oldId] >= 0) {
+                n = Math.max(n, oldToNew[oldId] + 1);
+            }
+        }
+        for (int i = 0; i < n; i++) {
+            byId.add(null);
+        }
+        for (int oldId = 0; oldId < old.size(); oldId++) {
+            final int q = oldToNew[oldId];
+            if (q >= 0) {
+                byId.set(q, old.get(oldId));
+                ids.put(old.get(oldId), q);
+            }
+        }
+        members = n;                                          // joiners that were not admitted are dropped
+    }
+
+    /** identifiersSeen on the device (MembershipView.java:58-60): NodeIds of the members, index = node id */
+    void setNodeIds(final long[] idHigh, final long[] idLow) {
+        if (Native.viewSetNodeIds(handle, idHigh, idLow) != 0) {
+            throw new IllegalStateException(Native.lastError());
+        }
+    }
+
+    /** getCurrentConfigurationId (:360-372) from the device-resident identifiersSeen and ring 0 */
+    long getCurrentConfigurationId() {
+        final long[] out = new long[1];
+        if (Native.viewCurrentConfigId(handle, out) != 0) {
+            throw new IllegalStateException(Native.lastError());
+        }
+        return out[0];
     }
 
     /** id of a known endpoint (member or registered joiner), -1 otherwise; never registers anything */

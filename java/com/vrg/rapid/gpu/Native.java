@@ -28,6 +28,14 @@ public final class Native {
     public static native int viewRingNumbers(long view, int observer, int subject);   // bitmask or <0
     public static native int viewConfigId(long view, long[] idHigh, long[] idLow, long[] out1);
     public static native int viewRegisterJoiners(long view, byte[] hostBytes, int[] hostOff, int[] port);  // first id
+    /** decideViewChange on the device (rapid_view_apply_cut): members in the cut leave, registered joiners in it are added;
+     *  outOldToNew may be null.  RAPID_EUUID_SEEN (-4) = UUIDAlreadySeenException, nothing changed. */
+    public static native int viewApplyCut(long view, int[] cutIds, int[] outOldToNew);
+    /** identifiersSeen on the device: NodeIds of the members (index = node id) / of registered joiners */
+    public static native int viewSetNodeIds(long view, long[] idHigh, long[] idLow);
+    public static native int viewSetJoinerIds(long view, int firstJoinerId, long[] idHigh, long[] idLow);
+    /** getCurrentConfigurationId from the device-resident identifiersSeen + ring 0 */
+    public static native int viewCurrentConfigId(long view, long[] out1);
 
     // ---- MultiNodeCutDetector / alert-batch handler ----
     public static native long cdCreate(long view, int h, int l, long receivers, long receiverBegin, int modeFlags,
@@ -43,6 +51,8 @@ public final class Native {
     public static native int cdInvalidate(long cd, long receiver, int[] outIds);
     public static native int cdNumProposals(long cd, long receiver);
     public static native int cdClear(long cd);
+    /** out4 = {sequences served in one pass, replayed batch by batch, receivers failing premise A1 / A2 in the last refusal} */
+    public static native int cdSequenceStats(long cd, int[] out4);
     /** wait for asynchronous batches (wireApplyToDetector / fdetApplyToDetector with async = true); returns their latched status */
     public static native int cdSync(long cd);
     /** several BatchedAlertMessages in one call: batch b = cells [batchOff[b], batchOff[b+1]); announcedIn[r] = batch index or -1 */
@@ -87,6 +97,8 @@ public final class Native {
 
     // ---- wire-format ingest (rapid.proto bytes -> cells on the device) ----
     public static native long wireCreate(long view);
+    /** only UP alerts of this configuration register joiners from now on */
+    public static native int wireSetConfiguration(long wire, long cfgId);
     public static native int wireDestroy(long wire);
     /** bytes = BatchedAlertMessage.toByteArray() (or the RapidRequest, asRequest); out5 = {nMessages, nCells, nDropped, nNewJoiners, senderId} */
     public static native int wireDecodeAlerts(long wire, ByteBuffer bytes, int len, boolean asRequest, long[] out5);

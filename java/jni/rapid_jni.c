@@ -112,6 +112,44 @@ JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_viewRegisterJoiners(JNIEnv*
     return rc == RAPID_OK ? first : rc;
 }
 
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_viewApplyCut(JNIEnv* env, jclass c, jlong view, jintArray cutIds, jintArray outOldToNew) {
+    const jsize n = (*env)->GetArrayLength(env, cutIds);
+    jint* ids = (*env)->GetIntArrayElements(env, cutIds, NULL);
+    jint* map = outOldToNew ? (*env)->GetIntArrayElements(env, outOldToNew, NULL) : NULL;
+    const int32_t rc = rapid_view_apply_cut(H(rapid_view, view), (const int32_t*)ids, n, (int32_t*)map);
+    (*env)->ReleaseIntArrayElements(env, cutIds, ids, JNI_ABORT);
+    if (map) (*env)->ReleaseIntArrayElements(env, outOldToNew, map, 0);
+    return rc;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_viewSetNodeIds(JNIEnv* env, jclass c, jlong view, jlongArray idHigh, jlongArray idLow) {
+    jlong* hi = (*env)->GetLongArrayElements(env, idHigh, NULL);
+    jlong* lo = (*env)->GetLongArrayElements(env, idLow, NULL);
+    const int32_t rc = rapid_view_set_node_ids(H(rapid_view, view), (const int64_t*)hi, (const int64_t*)lo);
+    (*env)->ReleaseLongArrayElements(env, idHigh, hi, JNI_ABORT);
+    (*env)->ReleaseLongArrayElements(env, idLow, lo, JNI_ABORT);
+    return rc;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_viewSetJoinerIds(JNIEnv* env, jclass c, jlong view, jint firstJoinerId, jlongArray idHigh,
+                                                                      jlongArray idLow) {
+    const jsize n = (*env)->GetArrayLength(env, idHigh);
+    jlong* hi = (*env)->GetLongArrayElements(env, idHigh, NULL);
+    jlong* lo = (*env)->GetLongArrayElements(env, idLow, NULL);
+    const int32_t rc = rapid_view_set_joiner_ids(H(rapid_view, view), firstJoinerId, n, (const int64_t*)hi, (const int64_t*)lo);
+    (*env)->ReleaseLongArrayElements(env, idHigh, hi, JNI_ABORT);
+    (*env)->ReleaseLongArrayElements(env, idLow, lo, JNI_ABORT);
+    return rc;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_viewCurrentConfigId(JNIEnv* env, jclass c, jlong view, jlongArray out1) {
+    int64_t v = 0;
+    const int32_t rc = rapid_view_current_config_id(H(rapid_view, view), &v);
+    const jlong j = (jlong)v;
+    (*env)->SetLongArrayRegion(env, out1, 0, 1, &j);
+    return rc;
+}
+
 /* ---------------------------------------------------------------- cut detector */
 JNIEXPORT jlong JNICALL Java_com_vrg_rapid_gpu_Native_cdCreate(JNIEnv* env, jclass c, jlong view, jint h, jint l, jlong receivers,
                                                                jlong begin, jint flags, jlong maxSubjects) {
@@ -181,6 +219,15 @@ JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_cdNumProposals(JNIEnv* env,
 
 JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_cdClear(JNIEnv* env, jclass c, jlong cd) {
     return rapid_cd_clear(H(rapid_cd, cd));
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_cdSequenceStats(JNIEnv* env, jclass c, jlong cd, jintArray out4) {
+    int32_t v[4] = {0, 0, 0, 0};
+    const int32_t rc = rapid_cd_sequence_stats(H(rapid_cd, cd), &v[0], &v[1], &v[2], &v[3]);
+    jint* o = (*env)->GetIntArrayElements(env, out4, NULL);
+    for (int i = 0; i < 4; ++i) o[i] = v[i];
+    (*env)->ReleaseIntArrayElements(env, out4, o, 0);
+    return rc;
 }
 
 /* ---------------------------------------------------------------- FastPaxos fast round */
@@ -396,6 +443,10 @@ JNIEXPORT jlong JNICALL Java_com_vrg_rapid_gpu_Native_wireCreate(JNIEnv* env, jc
     rapid_wire* w = NULL;
     const int32_t rc = rapid_wire_create(&w, H(rapid_view, view));
     return rc == RAPID_OK ? (jlong)(intptr_t)w : 0;
+}
+
+JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_wireSetConfiguration(JNIEnv* env, jclass c, jlong wire, jlong cfgId) {
+    return rapid_wire_set_configuration(H(rapid_wire, wire), cfgId);
 }
 JNIEXPORT jint JNICALL Java_com_vrg_rapid_gpu_Native_wireDestroy(JNIEnv* env, jclass c, jlong w) { return rapid_wire_destroy(H(rapid_wire, w)); }
 
