@@ -31,6 +31,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import signal
 import subprocess
 import sys
 import threading
@@ -150,9 +151,35 @@ class Clocks:
     def mark_begin(self):
         self.t_begin = time.perf_counter()
 
+    def pause(self):
+        """One poll stalls the GPU it queries for ~1 ms (measured: 1 step in 50 of a 2-GPU run takes +0.85 ms with the poller,
+        none without) — more than a whole 8-GPU step.  The poller is therefore stopped across the K device-timed steps (a sample
+        is taken right before) and resumed right after: its samples bracket that loop within one period and run through the
+        end-to-end timed loop, which executes the same kernels."""
+        if self.proc is None:
+            return
+        n = len(self.rows)
+        t0 = time.perf_counter()
+        while len(self.rows) == n and time.perf_counter() - t0 < 0.3:      # a fresh sample under the warm-up load
+            time.sleep(0.005)
+        try:
+            self.proc.send_signal(signal.SIGSTOP)
+            self.paused = True
+        except OSError:
+            pass
+
+    def resume(self):
+        if self.proc is not None and getattr(self, "paused", False):
+            try:
+                self.proc.send_signal(signal.SIGCONT)
+            except OSError:
+                pass
+            self.paused = False
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.resume()
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
@@ -167,7 +194,10 @@ class Clocks:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "poll": "nvidia-smi -lms 100 from before the timed region to the end of the run (through the end-to-end timed loop); "
+                        "stopped across the K device-timed steps, with a sample right before and after them, because one poll stalls "
+                        "the polled GPU for ~1 ms (more than an 8-GPU step)"}
 
 
 def ncu_traffic(args, gpus):
@@ -447,7 +477,7 @@ def run_ours(args):
             "decision differs from the expected cut: %r" % (res,)
 
     clocks = Clocks(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("RAPID_B200_NO_CLOCKS"):
         clocks.start()             # polls from here on; samples taken from the start of the timed region are reported
     upto = T - 1
     for _ in range(max(3, args.warmup)):
@@ -460,6 +490,8 @@ def run_ours(args):
     gc.collect()
     gc.disable()                   # no collector pauses inside the timed loops (one late rank stalls the whole all-reduce)
     clocks.mark_begin()
+    if rank == 0:
+        clocks.pause()
     barrier()                      # nothing rank-specific between the barrier and the first timed step
     per_step = []
     w0 = time.perf_counter()
@@ -469,8 +501,12 @@ def run_ours(args):
         res, _ = step_device()
         per_step.append((time.perf_counter() - t_step) * 1e3)
     dev_ms = fp.timerStop(cl)
+    if rank == 0:
+        clocks.resume()
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
+    if os.environ.get("RAPID_B200_STEP_TIMES"):
+        log("[rank %d] per-step host wall ms: %s" % (rank, " ".join("%.3f" % x for x in per_step)))
     check(res)
     prof_steps = max(2, min(args.steps, 5))
     for _ in range(prof_steps):
