@@ -409,6 +409,13 @@ def run_ours(args):
     def step_device():
         """clear -> every batch of the stream ENQUEUED (batch, then its tally, ordered on the device) -> ONE host synchronisation:
         the decision and the index of the batch that produced it.  Votes after the decision are ignored on the device."""
+        if T == 1 and asynchronous:
+            # the whole epoch (resets, the batch, its tally) enqueued by one C call; the decision is the step's one host synchronisation
+            d_dst, d_ring, d_status = dev[0]
+            fp.epochAsync(cl, cfg, st.cells[0], d_dst.data_ptr(), d_ring.data_ptr(), d_status.data_ptr(), comm=comm,
+                          blocked_dev=d_blocked.data_ptr(), perm_seed=st.perm[0])
+            res = fp.result()
+            return res, (res.decided_in if res.decided_in is not None and res.decided_in >= 0 else None)
         cl.clear()
         fp.reset(cfg)
         if sequence:

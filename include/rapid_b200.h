@@ -291,6 +291,11 @@ int32_t rapid_fp_tally_cd(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm, in
  * the quorum later votes are ignored on the device (:138) and the decision is kept.  *decided_in_call = index (since
  * rapid_fp_reset) of the tally call that decided, -1 if undecided. */
 int32_t rapid_fp_tally_cd_async(rapid_fp* fp, const rapid_cd* cd, rapid_comm* comm);
+/* One configuration epoch of a virtual cluster enqueued in ONE call: rapid_cd_clear + rapid_fp_reset (decideViewChange's resets,
+ * MembershipService.java:425-429) + rapid_cd_apply_batch_dev_async + rapid_fp_tally_cd_async.  Collect with rapid_fp_result. */
+int32_t rapid_fp_epoch_async(rapid_fp* fp, rapid_cd* cd, rapid_comm* comm, int64_t cfg_id, int64_t membership_size, int64_t n_cells,
+                             const int32_t* dst_dev, const uint8_t* ring_dev, const uint8_t* status_dev, const int64_t* cell_cfg_dev,
+                             const rapid_delivery* delivery_dev);
 int32_t rapid_fp_result(rapid_fp* fp, int32_t* decided, uint64_t* decided_hash, uint64_t* decided_hash2, int32_t* decided_len,
                         int32_t* decided_count, int32_t* votes_received, int32_t* decided_in_call);
 int32_t rapid_fp_quorum(int64_t membership_size, int64_t* out);   /* N - floor((N-1)/4) */

@@ -100,6 +100,7 @@ SIGNATURES = {
     "rapid_fp_reset": [_vp, _i64, _i64],
     "rapid_fp_tally": [_vp, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "rapid_fp_tally_cd": [_vp, _vp, _vp, _p, _p, _p, _p, _p, _p],
+    "rapid_fp_epoch_async": [_vp, _vp, _vp, _i64, _i64, _i64, _p, _p, _p, _p, _p],
     "rapid_fp_tally_cd_async": [_vp, _vp, _vp],
     "rapid_fp_result": [_vp, _p, _p, _p, _p, _p, _p, _p],
     "rapid_fp_quorum": [_i64, _p],

@@ -1186,11 +1186,11 @@ __device__ __noinline__ bool emitted_in_batch(const ResolveArgs& e, int32_t s, i
 // reports from observers that are themselves in proposal U preProposal, and — since everything a receiver needs is now in
 // the thread's registers — finishes the receiver right away: emissions of the pass, announced flags, outputs.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int INV_STAGE = 32;
+constexpr int INV_STAGE = 128;            // work-list subjects staged at a time: one thread each (GEN_THREADS >= INV_STAGE)
 struct InvSmem {
     uint16_t* row[INV_STAGE];
     uint64_t mix1[INV_STAGE], mix2[INV_STAGE];
-    int32_t ebeg[INV_STAGE + 1];                    // edges (observers that are subjects) of staged slot i: [ebeg[i], ebeg[i+1])
+    uint8_t ne[INV_STAGE];                          // edges (observers that are subjects) of staged slot i: entries [i * MAXK, i * MAXK + ne[i])
     const uint16_t* e_row[INV_STAGE * MAXK];
     int32_t e_so[INV_STAGE * MAXK];
     uint8_t e_k[INV_STAGE * MAXK];
@@ -1230,35 +1230,25 @@ __device__ void phase_inval_finalize2(const ResolveArgs& e, int mixed, InvSmem& 
             for (int base = 0; base < n_list; base += INV_STAGE) {
                 const int n = min(INV_STAGE, n_list - base);
                 __syncthreads();
-                if (t < 32) {                             // warp 0 stages the slots and their edge lists (INV_STAGE == 32)
+                if (t == 0) sm.n_dense = 0;
+                __syncthreads();
+                if (t < n) {                              // one thread per staged slot: its row, its edge list, is it in the band in this tile?
+                    const int32_t sl = a.wl.slots[base + t];
+                    const uint8_t fl = a.wl.in_tile[(size_t)sl * a.wl.n_tiles + tile];
+                    sm.flag[t] = fl;
+                    sm.row[t] = a.masks + ((size_t)sl * 2 + a.cur[sl]) * a.Rpad;
+                    const int32_t subject = a.slot_subject[sl];
+                    sm.mix1[t] = fp_mix1(subject); sm.mix2[t] = fp_mix2(subject);
                     int ne = 0;
-                    int32_t sl = -1;
-                    if (t < n) {
-                        sl = a.wl.slots[base + t];
-                        sm.flag[t] = a.wl.in_tile[(size_t)sl * a.wl.n_tiles + tile];
-                        sm.row[t] = a.masks + ((size_t)sl * 2 + a.cur[sl]) * a.Rpad;
-                        const int32_t subject = a.slot_subject[sl];
-                        sm.mix1[t] = fp_mix1(subject); sm.mix2[t] = fp_mix2(subject);
-                        for (int k = 0; k < a.K; ++k) ne += a.wl.so_tab[(size_t)sl * SO_STRIDE + k] >= 0 ? 1 : 0;
+                    for (int k = 0; k < a.K; ++k) {
+                        const int32_t s2 = a.wl.so_tab[(size_t)sl * SO_STRIDE + k];
+                        if (s2 < 0) continue;
+                        sm.e_row[t * MAXK + ne] = a.masks + ((size_t)s2 * 2 + a.cur[s2]) * a.Rpad;
+                        sm.e_so[t * MAXK + ne] = s2; sm.e_k[t * MAXK + ne] = (uint8_t)k;
+                        ++ne;
                     }
-                    int inc = ne;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, inc, o); if (t >= o) inc += x; }
-                    int at = inc - ne;
-                    if (t < n) {
-                        sm.ebeg[t] = at;
-                        for (int k = 0; k < a.K; ++k) {
-                            const int32_t s2 = a.wl.so_tab[(size_t)sl * SO_STRIDE + k];
-                            if (s2 < 0) continue;
-                            sm.e_row[at] = a.masks + ((size_t)s2 * 2 + a.cur[s2]) * a.Rpad;
-                            sm.e_so[at] = s2; sm.e_k[at] = (uint8_t)k;
-                            ++at;
-                        }
-                    }
-                    if (t == n - 1) sm.ebeg[n] = at;
-                    const unsigned fm = __ballot_sync(0xffffffffu, t < n && sm.flag[t]);
-                    if (t < n && sm.flag[t]) sm.dense[__popc(fm & ((1u << t) - 1u))] = (uint8_t)t;
-                    if (t == 0) sm.n_dense = __popc(fm);
+                    sm.ne[t] = (uint8_t)ne;
+                    if (fl) sm.dense[atomicAdd(&sm.n_dense, 1)] = (uint8_t)t;      // (the pass does not depend on the order)
                 }
                 __syncthreads();
                 if (!any_k3) continue;
@@ -1273,7 +1263,7 @@ __device__ void phase_inval_finalize2(const ResolveArgs& e, int mixed, InvSmem& 
                         w2v[q] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); e0v[q] = make_uint2(0u, 0u); e1v[q] = make_uint2(0u, 0u);
                         if (idx[q] < 0) continue;
                         w2v[q] = *reinterpret_cast<const uint2*>(sm.row[idx[q]] + rb);
-                        const int eb = sm.ebeg[idx[q]], ne = sm.ebeg[idx[q] + 1] - eb;
+                        const int eb = idx[q] * MAXK, ne = sm.ne[idx[q]];
                         if (ne > 0) e0v[q] = *reinterpret_cast<const uint2*>(sm.e_row[eb] + rb);
                         if (ne > 1) e1v[q] = *reinterpret_cast<const uint2*>(sm.e_row[eb + 1] + rb);
                     }
@@ -1281,7 +1271,7 @@ __device__ void phase_inval_finalize2(const ResolveArgs& e, int mixed, InvSmem& 
                     for (int q = 0; q < 4; ++q) {
                         const int i = idx[q];
                         if (i < 0) continue;
-                        const int eb = sm.ebeg[i], ee = sm.ebeg[i + 1];
+                        const int eb = i * MAXK, ee = eb + sm.ne[i];
                         uint32_t w[4] = {w2v[q].x & 0xFFFFu, w2v[q].x >> 16, w2v[q].y & 0xFFFFu, w2v[q].y >> 16};
                         uint32_t miss[4];                                   // rings an implicit report could still add, per receiver
                         uint32_t anymiss = 0;

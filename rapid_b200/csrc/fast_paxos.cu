@@ -1103,6 +1103,18 @@ int32_t rapid_fp_tally_cd_async(rapid_fp* fp, const rapid_cd* cd, rapid_comm* co
     return tally_cd_enqueue(fp, cd, comm);
 }
 
+// One configuration epoch of a virtual cluster, enqueued in ONE call: clear() of the detectors + a new FastPaxos instance
+// (decideViewChange's resets, MembershipService.java:425-429), one alert batch resident on the device, and the fast-round tally of
+// the proposals it produces — nothing waits on the host; rapid_fp_result collects the decision.
+int32_t rapid_fp_epoch_async(rapid_fp* fp, rapid_cd* cd, rapid_comm* comm, int64_t cfg_id, int64_t membership_size, int64_t n_cells,
+                             const int32_t* dst_dev, const uint8_t* ring_dev, const uint8_t* status_dev, const int64_t* cell_cfg_dev,
+                             const rapid_delivery* delivery_dev) {
+    RAPID_CHECK(rapid_cd_clear(cd));
+    RAPID_CHECK(rapid_fp_reset(fp, cfg_id, membership_size));
+    RAPID_CHECK(rapid_cd_apply_batch_dev_async(cd, cfg_id, n_cells, nullptr, dst_dev, ring_dev, status_dev, cell_cfg_dev, delivery_dev));
+    return rapid_fp_tally_cd_async(fp, cd, comm);
+}
+
 int32_t rapid_fp_result(rapid_fp* fp, int32_t* decided, uint64_t* decided_hash, uint64_t* decided_hash2, int32_t* decided_len,
                         int32_t* decided_count, int32_t* votes_received, int32_t* decided_in_call) {
     if (!fp) { set_error("NULL handle"); return RAPID_EINVAL; }

@@ -94,6 +94,23 @@ class FastPaxos:
         """enqueue only; result() collects the outcome of the last enqueued tally"""
         N.check(N.lib().rapid_fp_tally_cd_async(self._h, cluster._h, comm._h if comm is not None else None))
 
+    def epochAsync(self, cluster, configuration_id, n_cells, dst_dev, ring_dev, status_dev, comm=None, blocked_dev=0, perm_seed=None):
+        """clear() + a new FastPaxos instance + one device-resident alert batch + its tally, enqueued in one call"""
+        from . import _native as Nn
+        d = None
+        if blocked_dev or perm_seed is not None:
+            d = Nn.Delivery()
+            d.flags = 0
+            if blocked_dev:
+                d.flags |= Nn.DELIVERY_BLOCKED
+                d.blocked = blocked_dev
+            if perm_seed is not None:
+                d.flags |= Nn.DELIVERY_PERMUTED
+                d.perm_seed = perm_seed & 0xFFFFFFFFFFFFFFFF
+        self.cfg = int(configuration_id)
+        N.check(N.lib().rapid_fp_epoch_async(self._h, cluster._h, comm._h if comm is not None else None, self.cfg, self.N, int(n_cells),
+                                             dst_dev, ring_dev, status_dev, None, C.byref(d) if d is not None else None))
+
     def result(self):
         d, a, b, l, c, r = self._outs()
         k = C.c_int32(-1)
