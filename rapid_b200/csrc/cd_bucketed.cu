@@ -43,6 +43,14 @@ namespace cg = cooperative_groups;
 
 namespace rapid {
 
+// tuning switches (A/B builds: profiles/ab_build.sh)
+#ifndef RAPID_UNI_MINBLOCKS
+#define RAPID_UNI_MINBLOCKS 8
+#endif
+#ifndef RAPID_SPLIT_LOOP
+#define RAPID_SPLIT_LOOP 0
+#endif
+
 constexpr int TILE_R = 1024;          // receivers per tile (uniform kernel: 128 threads x 8 receivers)
 constexpr int UNI_THREADS = 128;
 constexpr int GEN_THREADS = 256;
@@ -395,7 +403,7 @@ __device__ __forceinline__ uint32_t seq_state(const ApplyArgs& a, const SubjDesc
 }
 
 template <bool PERM, bool SEQ>
-__global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a) {
+__global__ void __launch_bounds__(UNI_THREADS, RAPID_UNI_MINBLOCKS) k_apply_uniform(const ApplyArgs a) {
     __shared__ SubjDesc sd[STAGE];
     __shared__ SubjWalk sw[PERM ? 1 : STAGE];
     __shared__ SubjWalk spw[SEQ ? STAGE : 1];
@@ -404,6 +412,7 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
     __shared__ uint32_t s_nw[STAGE];          // (rings reported by the call) replicated in both half-words
     __shared__ int s_unres[STAGE];
     __shared__ StageAcc s_facc;               // fresh-subject accumulators of this block's chunk (same for every receiver)
+    __shared__ int s_heavy;                   // staged subjects that are NOT plain fresh ones (carried, or with dictionary observers)
     // SEQ: the dictionary observers ("edges") of the staged subjects — their pre-call rows (nullptr: fresh, state 0) and batch index
     __shared__ uint8_t s_ne[SEQ ? STAGE : 1];
     __shared__ uint8_t s_ek[SEQ ? STAGE : 1][MAXK];
@@ -451,6 +460,7 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
         __syncthreads();
         if (t < 32) {                                     // warp 0 stages the descriptors (STAGE == 32)
             Acc f;                                        // what this lane's FRESH subject contributes to every active receiver
+            bool heavy = false;
             if (t < n) {
                 const SubjDesc d = a.desc[base + t];
                 sd[t] = d;
@@ -488,6 +498,11 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                 // the invalidation work list (has_so is refreshed by k_prepare whenever a subject gets a slot)
                 s_unres[t] = (un && a.wl.has_so[d.slot]) ? 1 : 0;
                 if (!fresh || edges) s_unres[t] = a.wl.has_so[d.slot] ? 0 : -1;       // -1: never list it
+                heavy = !fresh || edges;
+            }
+            {
+                const unsigned hm = __ballot_sync(0xffffffffu, heavy);
+                if (t == 0) s_heavy = __popc(hm);
             }
             // warp reduction of the fresh subjects' contribution
             uint32_t nLH = f.nL | (f.nH << 16), tpUn = f.tp | (f.nUn << 16), fl = f.flags, mTH = f.minTH, mTL = f.minTLun;
@@ -522,6 +537,22 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
             }
         }
         __syncthreads();
+#if RAPID_SPLIT_LOOP
+        // fresh subjects of the stage first: write-only, in a loop of their own
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            const uint32_t nwb = s_nw[i];
+            if (s_src[i] == nullptr && (!SEQ || s_ne[i] == 0))
+                *reinterpret_cast<uint4*>(s_dst[i] + r0) = make_uint4(nwb & am[0], nwb & am[1], nwb & am[2], nwb & am[3]);
+        }
+        const int n_heavy = s_heavy ? n : 0;               // (uniform) nothing but plain fresh subjects in this stage: skip the visit loop
+        for (int i = 0; i < n_heavy; ++i) {
+            const uint16_t* src = s_src[i];
+            uint16_t* dst = s_dst[i];
+            const uint32_t nwb = s_nw[i];
+            const int ne = SEQ ? (int)s_ne[i] : 0;
+            if (src == nullptr && ne == 0) continue;       // (done above)
+#else
 #pragma unroll 4
         for (int i = 0; i < n; ++i) {
             const uint16_t* src = s_src[i];
@@ -532,6 +563,7 @@ __global__ void __launch_bounds__(UNI_THREADS) k_apply_uniform(const ApplyArgs a
                 *reinterpret_cast<uint4*>(dst + r0) = make_uint4(nwb & am[0], nwb & am[1], nwb & am[2], nwb & am[3]);
                 continue;
             }
+#endif
             uint4 w = src ? *reinterpret_cast<const uint4*>(src + r0) : make_uint4(0u, 0u, 0u, 0u);
             bool unres = false;
             if (act) {

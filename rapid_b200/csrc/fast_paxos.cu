@@ -344,6 +344,18 @@ __global__ void k_fp_apply(int64_t n, const int32_t* __restrict__ sender, const 
     if (threadIdx.x == 0 && s_recv) atomicAdd(&st->votes_received, s_recv);
 }
 
+// A call that fails after k_fp_first / k_fp_insert (bad sender id, too many candidates) must leave no trace: the first-index marks
+// of this call's senders go back to "has not voted" (a mark left behind would make every later vote of that sender look like a
+// duplicate), and the per-call counts are zeroed by k_fp_zero_call.
+__global__ void k_fp_rollback(int64_t n, const int32_t* __restrict__ sender, int64_t sender_cap, int32_t* __restrict__ seen) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t s = sender[i];
+    if (s < 0 || s >= sender_cap) return;
+    const int32_t v = seen[s];
+    if (v >= 0 && v != INT_MAX) seen[s] = INT_MAX;          // (-1 = voted in an EARLIER call: stays)
+}
+
 __global__ void k_fp_zero_call(uint32_t T, int32_t* __restrict__ t_call) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < T) t_call[e] = 0;
@@ -835,14 +847,19 @@ static int32_t tally_device(FP* fp, int64_t n, const int32_t* sender, const int6
     RAPID_CUDA(cudaMemcpyAsync(fp->h_st.p, fp->st.p, sizeof(FPState), cudaMemcpyDeviceToHost, s));
     RAPID_CUDA(cudaStreamSynchronize(s));
     const FPState st = *fp->h_st.p;
+    auto rollback = [&]() {
+        k_fp_rollback<<<g, TB, 0, s>>>(n, sender, fp->sender_cap, fp->seen.p);
+        k_fp_zero_call<<<gt, TB, 0, s>>>(fp->T, fp->t_call.p);
+        cudaStreamSynchronize(s);
+    };
     if (st.bad_sender >= 0) {
-        // roll the first-index marks back before failing
+        rollback();                                          // nothing of this call stays behind
         set_error("vote %d: sender id outside [0, sender_capacity)", st.bad_sender);
         return RAPID_EINVAL;
     }
     int use_istar = 0;
     if (st.n_cand > 0 && exact_order) {
-        if (st.n_cand > 8) { set_error("more than 8 proposals reached the quorum in one call"); return RAPID_EUNSUPPORTED; }
+        if (st.n_cand > 8) { rollback(); set_error("more than 8 proposals reached the quorum in one call"); return RAPID_EUNSUPPORTED; }
         RAPID_CHECK(fp->scan.reserve((size_t)n));
         for (int c = 0; c < st.n_cand; ++c) {
             const int32_t e = st.cand[c];

@@ -91,6 +91,18 @@ def test_bad_sender_rejected(rb):
         fp.handleFastRoundProposals([10], [1], [1], [1])
 
 
+def test_a_refused_call_leaves_no_trace(rb):
+    """a call that is refused (a sender id outside the table) must not poison the tally: the senders it named can still vote"""
+    N = 40
+    fp = rb.FastPaxos(7, N, sender_capacity=N)
+    good = np.arange(10, dtype=np.int32)
+    with pytest.raises(rb.RapidError):
+        fp.handleFastRoundProposals(np.concatenate([good, [N + 5]]).astype(np.int32), np.full(11, 99, np.uint64))
+    q = rb.quorum(N)
+    t = fp.handleFastRoundProposals(np.arange(q, dtype=np.int32), np.full(q, 99, np.uint64))
+    assert t.decided and t.count == q and t.votes_received == q          # senders 0..9 were NOT burnt by the refused call
+
+
 def test_tally_from_cluster(orc, rb):
     """C2 end to end on one GPU: alert batch -> per-node proposals -> votes -> decision == the crashed set"""
     from helpers import OracleWorld
