@@ -65,6 +65,7 @@ constexpr uint32_t RF_MIXED_EMIT = 64u;   // announced a proposal found by the i
 
 // per-receiver state of the interval analysis (MIXED receivers)
 constexpr uint32_t MX_ON = 1u, MX_NEG = 2u, MX_HAS_E = 4u, MX_DONE = 8u;
+constexpr uint32_t MX_REF = 32u;      // resolved through the reference receiver (its sums are already in mx_e1 / mx_e2 / mx_ec)
 constexpr uint32_t MX_TIME = 16u;     // PERMUTED delivery: the classification needs this receiver's own min t_H / min t_L
 
 // partial-accumulator flags
@@ -97,7 +98,7 @@ struct Partials {                     // [n_chunks][Rpad] structure of arrays
 struct Bucketed {
     DevBuf<int32_t> sidx;                     // cell indices grouped by subject (arrival order inside a subject)
     DevBuf<int32_t> seg_cnt, batch_slots;     // [slot] scratch of the prepare kernel (seg_cnt all zero between batches)
-    DevBuf<int32_t> bins, ovf;                // [slot][64] cell bins (PREP_BIN), [A] overflow list
+    DevBuf<int32_t> bins, ovf, cell_batch;    // [slot][64] cell bins (PREP_BIN), [A] overflow list, [A] batch of every cell (sequences)
     DevBuf<SubjDesc> desc;
     DevBuf<SubjWalk> walk;
     DevBuf<uint8_t> s_ring, s_status;         // per sorted cell
@@ -117,6 +118,7 @@ struct Bucketed {
     DevBuf<int32_t> mx_ec;
     DevBuf<uint64_t> estar;                   // [Rpad] last explicit emission moment of RF_MIXED_EMIT receivers
     DevBuf<int32_t> mx_changed;               // [4] rotating "the component grew" counters of the fixpoint loop
+    DevBuf<uint32_t> mx_dev;                  // [Rpad / 32]
     DevBuf<int32_t> batch_index;              // [slot] -> index of the subject in the batch in flight
     // invalidation work list (WorkList)
     DevBuf<int32_t> wl_slots, wl_count, wl_listed, wl_so_tab;
@@ -883,6 +885,7 @@ struct ResolveArgs {
     unsigned long long* mx_e2;
     int32_t* mx_ec;
     int32_t* mx_changed;          // [4]
+    uint32_t* mx_dev;             // [Rpad / 32] scratch of the reference-receiver shortcut (all zero between batches)
     const int32_t* slot_of;
     const int32_t* obs;
     const int32_t* touch;
@@ -1025,6 +1028,7 @@ __device__ void phase_finalize1(const ResolveArgs& a, int32_t* s_red) {
             } else if (!(haveTL && minTLun < minTH)) {
                 // MIXED: some proposals may have been emitted before the unresolved subjects entered the band
                 ++my_mixed;
+                atomicMin(&a.bc->mx_first, (int32_t)r);              // candidate reference receiver of the interval analysis
                 a.mx_fl[r] = MX_ON;
                 a.mx_a[r] = minTLun; a.mx_cand[r] = T64_NONE; a.mx_emax[r] = 0;
                 a.mx_p1[r] = p1_old; a.mx_p2[r] = p2_old; a.mx_pc[r] = pc_old;
@@ -1079,7 +1083,7 @@ struct PassSmem {
 // MODE 0: FIX pass (next candidate for `a`, e* candidate)   1: SUM pass (fingerprint of {t_H <= e*})
 // MODE 2: MOMENT pass (min t_H over H-crossers -> mx_cand, min t_L over subjects left in the band -> mx_a)
 template <int MODE>
-__device__ __noinline__ void mixed_pass(const ResolveArgs& m, PassSmem& sm, const int Sb, const int S_before) {
+__device__ __noinline__ void mixed_pass(const ResolveArgs& m, PassSmem& sm, const int Sb, const int S_before, const int64_t only_r = -1) {
     const ApplyArgs& a = m.ap;
     const int t = threadIdx.x;
     const uint32_t RM = (1u << a.K) - 1u;
@@ -1093,7 +1097,8 @@ __device__ __noinline__ void mixed_pass(const ResolveArgs& m, PassSmem& sm, cons
         const int rb = (int)(wi % rblocks), chunk = (int)(wi / rblocks);
         const int64_t r = (int64_t)rb * GEN_THREADS + t;
         const uint32_t fl = r < a.R ? m.mx_fl[r] : 0u;
-        const bool on = MODE == 0 ? ((fl & MX_ON) && !(fl & MX_DONE)) : MODE == 1 ? ((fl & MX_DONE) && (fl & MX_HAS_E)) : ((fl & MX_TIME) != 0);
+        const bool on = (only_r < 0 || r == only_r) &&
+                        (MODE == 0 ? ((fl & MX_ON) && !(fl & MX_DONE)) : MODE == 1 ? ((fl & MX_DONE) && (fl & MX_HAS_E) && !(fl & MX_REF)) : ((fl & MX_TIME) != 0));
         if (!__syncthreads_or(on ? 1 : 0)) continue;
         const uint64_t ref = on ? (MODE == 0 ? m.mx_a[r] : MODE == 1 ? m.estar[r] : 0ull) : 0ull;
         const uint64_t rs = splitmix64(a.dl.perm_seed + (uint64_t)(a.rbegin + r));
@@ -1158,9 +1163,10 @@ __device__ void phase_classify_moments(const ResolveArgs& a, int32_t* s_red) {
     if (threadIdx.x == 0 && bm) atomicAdd(&a.bc->n_mixed, bm);
 }
 
-__device__ void phase_mixed_update(const ResolveArgs& a, int32_t* changed, int32_t* s_red) {
+__device__ void phase_mixed_update(const ResolveArgs& a, int32_t* changed, int32_t* s_red, const int64_t only_r = -1) {
     int32_t my = 0;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.ap.R; r += (int64_t)gridDim.x * blockDim.x) {
+        if (only_r >= 0 && r != only_r) continue;
         const uint32_t fl = a.mx_fl[r];
         if (!(fl & MX_ON) || (fl & MX_DONE)) continue;
         if (fl & MX_NEG) { a.mx_fl[r] = 0; continue; }           // covered since before the batch: nothing was emitted
@@ -1444,6 +1450,7 @@ __device__ void resolve_tail(const ResolveArgs& a, int32_t serial) {
     c.overflow = b->overflow; c.need_slots = b->need_slots; c.n_times = b->n_times; c.mixed_iters = b->mixed_iters;
     c.n_pairs = *(volatile int32_t*)a.ap.wl.count; c.ticket = 0; c.serial = serial;
     c.seq_last = b->seq_last; c.seq_down = b->seq_down; c.seq_abort = b->seq_abort; c.seq_a1 = b->seq_a1; c.seq_a2 = b->seq_a2;
+    c.mx_first = b->mx_first; c.mx_left = b->mx_left;
     if (c.seq_abort) { c.n_slots = c.S_before; b->n_slots = c.S_before; }   // the slots this call assigned were given back (seq_rollback)
     // errors stay latched until the host has collected them (an asynchronous caller may have several batches in flight)
     c.sticky_bad_ring = b->sticky_bad_ring | (c.bad_ring >= 0 ? 1 : 0);
@@ -1453,8 +1460,66 @@ __device__ void resolve_tail(const ResolveArgs& a, int32_t serial) {
     *a.snap = c;
     b->n_valid = 0; b->n_batch_subj = 0; b->any_down = 0; b->bad_ring = -1; b->bad_dst = -1; b->n_mixed = 0; b->n_inval = 0;
     b->overflow = 0; b->need_slots = 0; b->n_times = 0; b->mixed_iters = 0; b->ticket = 0;
-    b->seq_last = 0; b->seq_down = INT_MAX; b->seq_abort = 0; b->seq_a1 = 0; b->seq_a2 = 0;
+    b->seq_last = 0; b->seq_down = INT_MAX; b->seq_abort = 0; b->seq_a1 = 0; b->seq_a2 = 0; b->mx_first = INT_MAX; b->mx_left = 0;
     b->S_before = c.n_slots;                                            // the next batch starts from here (k_prepare reads it)
+}
+
+// ---- the reference-receiver shortcut of the interval analysis (uniform delivery) ------------------------------------------------------
+// mx_dev: one bit per receiver, set if it differs from receiver r0 in the pre-batch word of SOME batch subject
+__device__ void phase_ref_compare(const ResolveArgs& e, const int64_t r0, const int Sb, const int S_before) {
+    static_assert(TILE_R == 4 * GEN_THREADS, "a thread owns 4 receivers of a tile");
+    const ApplyArgs& a = e.ap;
+    const uint32_t RM2 = ((1u << a.K) - 1u) * 0x10001u;
+    const int t = threadIdx.x;
+    // work items: (tile, chunk of subjects); a block-wide OR-reduction is not needed — each thread owns its 4 receivers' bits
+    constexpr int CH = 64;
+    __shared__ const uint16_t* s_row[CH];
+    __shared__ uint32_t s_ref[CH];
+    const int nch = (Sb + CH - 1) / CH;
+    const int64_t items = (int64_t)a.n_tiles * nch;
+    for (int64_t wi = blockIdx.x; wi < items; wi += gridDim.x) {
+        const int tile = (int)(wi % a.n_tiles), ch = (int)(wi / a.n_tiles);
+        const int64_t rb = (int64_t)tile * TILE_R + (int64_t)t * 4;
+        const int b0 = ch * CH, nb = min(Sb, b0 + CH) - b0;
+        __syncthreads();
+        if (t < nb) {
+            const int32_t slot = a.desc[b0 + t].slot;
+            const uint16_t* row = slot >= S_before ? nullptr : a.masks + ((size_t)slot * 2 + a.cur[slot]) * a.Rpad;   // pre-batch row (not flipped yet); fresh: state 0 for everyone
+            s_row[t] = row;
+            s_ref[t] = row ? (uint32_t)row[r0] * 0x10001u : 0u;
+        }
+        __syncthreads();
+        uint32_t dx = 0, dy = 0;
+#pragma unroll 8
+        for (int i = 0; i < nb; ++i) {
+            const uint16_t* row = s_row[i];
+            if (row == nullptr) continue;
+            const uint2 w = *reinterpret_cast<const uint2*>(row + rb);
+            dx |= (w.x ^ s_ref[i]) & RM2; dy |= (w.y ^ s_ref[i]) & RM2;
+        }
+        const uint32_t bits = ((dx & 0xFFFFu) ? 1u : 0u) | ((dx >> 16) ? 2u : 0u) | ((dy & 0xFFFFu) ? 4u : 0u) | ((dy >> 16) ? 8u : 0u);
+        if (bits) atomicOr(&e.mx_dev[rb >> 5], bits << (rb & 31));
+    }
+}
+// the flagged receivers that agree with r0 take its outcome; the others are counted (bc->mx_left) and go through the general passes
+__device__ void phase_ref_adopt(const ResolveArgs& a, const int64_t r0, int32_t* s_red) {
+    const uint32_t f0 = a.mx_fl[r0];
+    int32_t my = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.ap.R; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t fl = a.mx_fl[r];
+        const bool dev = (a.mx_dev[r >> 5] >> (r & 31)) & 1u;
+        if (r != r0 && (fl & MX_ON) && !(fl & MX_DONE)) {
+            if (!dev) {
+                a.mx_fl[r] = f0 ? (f0 | MX_REF) : 0u;                           // 0: nothing was emitted explicitly
+                if ((f0 & MX_DONE) && (f0 & MX_HAS_E)) { a.estar[r] = a.estar[r0]; a.mx_e1[r] = a.mx_e1[r0]; a.mx_e2[r] = a.mx_e2[r0]; a.mx_ec[r] = a.mx_ec[r0]; }
+            } else {
+                ++my;
+            }
+        }
+    }
+    const int32_t b = block_sum_i32(my, s_red);
+    if (threadIdx.x == 0 && b) atomicAdd(&a.bc->mx_left, b);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && f0) a.mx_fl[r0] = f0 | MX_REF;
 }
 
 // ==================================================================================================================
@@ -1546,21 +1611,40 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) k_mixed_flip(const ResolveArgs
     }
     const int mixed = *(volatile int32_t*)&a.bc->n_mixed > 0 ? 1 : 0;
     if (mixed && Sb > 0) {
-        int it = 0;
-        for (;; ++it) {
-            mixed_pass<0>(a, sm, Sb, S_before);
+        auto analyse = [&](const int64_t only_r) -> int {       // the fixpoint loop + the sum pass, for everyone flagged or for one receiver
+            int it = 0;
+            for (;; ++it) {
+                mixed_pass<0>(a, sm, Sb, S_before, only_r);
+                grid.sync();
+                if (blockIdx.x == 0 && threadIdx.x == 0) a.mx_changed[(it + 2) & 3] = 0;
+                phase_mixed_update(a, &a.mx_changed[it & 3], s_red, only_r);
+                grid.sync();
+                if (*(volatile int32_t*)&a.mx_changed[it & 3] == 0 || it > Sb + 1) break;
+            }
+            mixed_pass<1>(a, sm, Sb, S_before, only_r);
             grid.sync();
-            if (blockIdx.x == 0 && threadIdx.x == 0) a.mx_changed[(it + 2) & 3] = 0;
-            phase_mixed_update(a, &a.mx_changed[it & 3], s_red);
+            if (blockIdx.x == 0 && threadIdx.x == 0) { a.mx_changed[0] = 0; a.mx_changed[1] = 0; a.mx_changed[2] = 0; a.mx_changed[3] = 0; }
             grid.sync();
-            if (*(volatile int32_t*)&a.mx_changed[it & 3] == 0 || it > Sb + 1) break;
+            return it + 1;
+        };
+        int iters = 0;
+        int left = 1;
+        if (a.uniform && !a.ap.seq) {
+            // Uniform delivery: receivers that hold the same words for the batch's subjects get the same intervals, hence the same
+            // answer.  Analyse ONE flagged receiver, find the flagged receivers that agree with it on every batch subject (one
+            // read-only pass over the pre-batch rows) and hand them its result; only the others take the passes below.
+            const int64_t r0 = (int64_t)*(volatile int32_t*)&a.bc->mx_first;
+            iters = analyse(r0);
+            phase_ref_compare(a, r0, Sb, S_before);
+            grid.sync();
+            phase_ref_adopt(a, r0, s_red);
+            grid.sync();
+            left = *(volatile int32_t*)&a.bc->mx_left;
+            // (every block is past the adoption: the difference bits go back to all-zero for the next batch)
+            for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < (int64_t)(a.ap.Rpad >> 5); q += (int64_t)gridDim.x * blockDim.x) a.mx_dev[q] = 0;
         }
-        mixed_pass<1>(a, sm, Sb, S_before);
-        grid.sync();
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            a.mx_changed[0] = 0; a.mx_changed[1] = 0; a.mx_changed[2] = 0; a.mx_changed[3] = 0;
-            a.bc->mixed_iters = it + 1;
-        }
+        if (left > 0) iters += analyse(-1);
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.bc->mixed_iters = iters;
         phase_mixed_commit(a);
         grid.sync();
     }
@@ -1659,14 +1743,14 @@ int32_t bucketed_prep_buffers(CD* cd, int64_t A, PrepOut* po) {
     RAPID_CHECK(b->batch_index.reserve(slots));
     RAPID_CHECK(b->batch_slots.reserve(slots));
     RAPID_CHECK(b->bins.reserve(slots * 64));
-    RAPID_CHECK(b->ovf.reserve(a));
+    RAPID_CHECK(b->ovf.reserve(a)); RAPID_CHECK(b->cell_batch.reserve(a));
     if (slots > b->seg_cnt.cap) {
         RAPID_CHECK(b->seg_cnt.reserve(slots));
         RAPID_CUDA(cudaMemsetAsync(b->seg_cnt.p, 0, b->seg_cnt.cap * sizeof(int32_t), cd->stream));
     }
     po->desc = b->desc.p; po->walk = b->walk.p; po->sidx = b->sidx.p; po->s_ring = b->s_ring.p; po->s_status = b->s_status.p;
     po->batch_index = b->batch_index.p; po->seg_cnt = b->seg_cnt.p; po->batch_slots = b->batch_slots.p;
-    po->bins = b->bins.p; po->ovf = b->ovf.p; po->pwalk = b->pwalk.p;
+    po->bins = b->bins.p; po->ovf = b->ovf.p; po->pwalk = b->pwalk.p; po->cell_batch = b->cell_batch.p;
     po->wl = worklist(b);
     return RAPID_OK;
 }
@@ -1722,7 +1806,7 @@ __global__ void __launch_bounds__(256) k_clear_bucketed(const ClearArgs a) {
     __threadfence();
     BatchCounts c;
     memset(&c, 0, sizeof(c));
-    c.bad_ring = -1; c.bad_dst = -1; c.seq_down = INT_MAX;
+    c.bad_ring = -1; c.bad_dst = -1; c.seq_down = INT_MAX; c.mx_first = INT_MAX;
     volatile BatchCounts* b = a.bc;
     c.sticky_bad_ring = b->sticky_bad_ring; c.sticky_bad_dst = b->sticky_bad_dst; c.sticky_overflow = b->sticky_overflow;   // errors not collected yet survive a clear()
     *a.bc = c;
@@ -1816,6 +1900,10 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, bool seq) {
     RAPID_CHECK(b->mx_fl.reserve(cd->Rpad)); RAPID_CHECK(b->mx_a.reserve(cd->Rpad)); RAPID_CHECK(b->mx_cand.reserve(cd->Rpad));
     RAPID_CHECK(b->mx_emax.reserve(cd->Rpad)); RAPID_CHECK(b->mx_p1.reserve(cd->Rpad)); RAPID_CHECK(b->mx_p2.reserve(cd->Rpad));
     RAPID_CHECK(b->mx_pc.reserve(cd->Rpad)); RAPID_CHECK(b->estar.reserve(cd->Rpad));
+    if (!b->mx_dev.p || b->mx_dev.cap < (cd->Rpad >> 5)) {
+        RAPID_CHECK(b->mx_dev.reserve(std::max<size_t>(cd->Rpad >> 5, 1)));
+        RAPID_CUDA(cudaMemsetAsync(b->mx_dev.p, 0, std::max<size_t>(cd->Rpad >> 5, 1) * sizeof(uint32_t), s));
+    }
     if (!b->mx_e1.p) {
         RAPID_CHECK(b->mx_e1.reserve(cd->Rpad)); RAPID_CHECK(b->mx_e2.reserve(cd->Rpad)); RAPID_CHECK(b->mx_ec.reserve(cd->Rpad));
         RAPID_CUDA(cudaMemsetAsync(b->mx_e1.p, 0, cd->Rpad * sizeof(unsigned long long), s));
@@ -1862,7 +1950,7 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, bool seq) {
     ra.pend_cnt = cd->pend_cnt.p; ra.out_h1 = cd->out_h1.p; ra.out_h2 = cd->out_h2.p; ra.out_len = cd->out_len.p; ra.out_ann = cd->out_ann.p;
     ra.mx_fl = b->mx_fl.p; ra.mx_a = b->mx_a.p; ra.mx_cand = b->mx_cand.p; ra.mx_emax = b->mx_emax.p;
     ra.mx_p1 = b->mx_p1.p; ra.mx_p2 = b->mx_p2.p; ra.mx_pc = b->mx_pc.p; ra.estar = b->estar.p;
-    ra.mx_e1 = b->mx_e1.p; ra.mx_e2 = b->mx_e2.p; ra.mx_ec = b->mx_ec.p; ra.mx_changed = b->mx_changed.p;
+    ra.mx_e1 = b->mx_e1.p; ra.mx_e2 = b->mx_e2.p; ra.mx_ec = b->mx_ec.p; ra.mx_changed = b->mx_changed.p; ra.mx_dev = b->mx_dev.p;
     ra.slot_of = cd->slot_of.p; ra.obs = cd->view->obs.p; ra.touch = cd->touch.p; ra.batch_index = b->batch_index.p;
     ra.serial = cd->batch_serial;
     const unsigned rblocks = (unsigned)(cd->Rpad / GEN_THREADS);

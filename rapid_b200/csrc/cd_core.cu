@@ -314,8 +314,10 @@ static void collect(CD* cd) {
         unsigned long long st[16];
         if (cudaMemcpy(st, cd->prep_stamps.p, sizeof(st), cudaMemcpyDeviceToHost) == cudaSuccess) {
             fprintf(stderr, "[k_prepare phases, us]");
+            // stamps 1, 2, 15: after the grid barriers / at the end; 8-11: block 0's progress inside phases 2 and 3
+            static const int order[] = {1, 8, 9, 2, 10, 11, 15};
             int prev = 0;
-            for (int i = 1; i < 16; ++i) if (st[i]) { fprintf(stderr, " P%d:%.1f", i, (double)(st[i] - st[prev]) / 1e3); prev = i; }
+            for (int q = 0; q < 7; ++q) { const int i = order[q]; if (st[i]) { fprintf(stderr, " S%d:+%.1f", i, (double)(st[i] - st[prev]) / 1e3); prev = i; } }
             fprintf(stderr, " total:%.1f\n", (double)(st[prev] - st[0]) / 1e3);
         }
     }

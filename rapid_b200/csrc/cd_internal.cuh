@@ -50,6 +50,8 @@ struct BatchCounts {
     int32_t seq_last;      // index of the last non-empty batch of the call in flight (0 for a single batch)
     int32_t seq_down;      // 1-based index of the first batch with a valid DOWN cell, INT_MAX if none
     int32_t seq_abort;     // receivers for which the one-pass treatment is not provably exact: NOTHING was committed
+    int32_t mx_first;      // interval analysis: lowest flagged receiver (the reference of the uniform-delivery shortcut), INT_MAX if none
+    int32_t mx_left;       // ... flagged receivers that differ from it and take the general passes
     int32_t seq_a1, seq_a2; // ... of which: could have emitted before the last batch / an implicit report would fire inside the prefix
 };
 
@@ -209,6 +211,7 @@ struct PrepOut {                      // where the prepare kernel writes the reg
     int32_t* bins;                    // [slot][64] indices of the subject's first 64 cells of this batch (any order)
     int32_t* ovf;                     // [A] cells beyond a subject's bin
     SubjWalk* pwalk;                  // sequences of batches: first-occurrence ring sequence of the prefix, time = batch index + 1
+    int32_t* cell_batch;              // sequences of batches: [A] index of the batch of every valid cell
     WorkList wl;                      // invalidation work list (bucketed handles; wl.has_so == nullptr otherwise)
 };
 

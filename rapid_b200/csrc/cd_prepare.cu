@@ -101,7 +101,8 @@ __device__ __forceinline__ int32_t batch_of_cell(const int64_t* __restrict__ off
 }
 
 constexpr int PREP_BIN = 64;          // cells of one subject kept in its bin; the rest of a (duplicate-heavy) subject overflow
-constexpr int PREP_REG = 16;          // ... of which this many are sorted in registers (the usual case: ~K cells per subject)
+constexpr int PREP_REG = 32;          // ... of which this many are sorted in registers (~K cells per subject and batch; a few more with
+                                     // re-sent duplicates or when a whole sequence of batches is prepared at once)
 
 __device__ __forceinline__ void prep_stamp(const PrepArgs& a, int i) {
     if (a.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -145,9 +146,11 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepArgs a) {
             }
             a.cell_slot[i] = v;
             if (v == -2) {
+                const int32_t bt = a.batch_off ? batch_of_cell(a.batch_off, a.n_batches, i) : 0;
+                if (a.batch_off) a.po.cell_batch[i] = bt;             // (P3 walks a subject's cells one after the other: no searches there)
                 if (a.status[i] == RAPID_EDGE_DOWN) {
                     a.bc->any_down = 1;
-                    if (a.batch_off) atomicMin(&a.bc->seq_down, batch_of_cell(a.batch_off, a.n_batches, i) + 1);
+                    if (a.batch_off) atomicMin(&a.bc->seq_down, bt + 1);
                 }
                 // this cell names the subject's slot if it wins the claim
                 claimed = *(volatile int32_t*)&a.slot_of[d] == -1 && atomicCAS(&a.slot_of[d], -1, -2) == -1;
@@ -208,6 +211,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepArgs a) {
         if (t == 0 && total) atomicAdd(&a.bc->n_valid, total);
     }
     if (!a.regroup) return;
+    prep_stamp(a, 8);                                   // (sub-stamps: block 0's own progress inside a phase)
     if (a.wl.has_so && S_new > a.S_old) {
         // Some subject got a slot: refresh "which observers of this subject are subjects themselves" for every slot.  Only
         // subjects with such an observer can ever receive an implicit report (MultiNodeCutDetector.java:147-158), so only
@@ -215,11 +219,18 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepArgs a) {
         for (int64_t sl = gtid; sl < S_new; sl += gthreads) {
             const int32_t subject = a.slot_subject[sl];
             bool any = false;
-            for (int k = 0; k < a.K; ++k) {
-                const int32_t o = a.obs[(size_t)subject * a.K + k];
-                const int32_t so = o >= 0 ? a.slot_of[o] : -1;
-                a.wl.so_tab[(size_t)sl * SO_STRIDE + k] = so;
-                if (so >= 0) any = true;
+            // all K observer ids, then all K slot lookups, in flight together (one loop of load -> load -> store per ring serialises
+            // 2K dependent round trips: the stores may alias the tables as far as the compiler knows)
+            int32_t o[RAPID_MAX_K], so[RAPID_MAX_K];
+#pragma unroll
+            for (int k = 0; k < RAPID_MAX_K; ++k) o[k] = k < a.K ? a.obs[(size_t)subject * a.K + k] : -1;
+#pragma unroll
+            for (int k = 0; k < RAPID_MAX_K; ++k) so[k] = o[k] >= 0 ? a.slot_of[o[k]] : -1;
+#pragma unroll
+            for (int k = 0; k < RAPID_MAX_K; ++k) {
+                if (k >= a.K) break;
+                a.wl.so_tab[(size_t)sl * SO_STRIDE + k] = so[k];
+                if (so[k] >= 0) any = true;
             }
             const bool old = sl < a.S_old && a.wl.has_so[sl];
             a.wl.has_so[sl] = any ? 1 : 0;
@@ -229,6 +240,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepArgs a) {
             }
         }
     }
+    prep_stamp(a, 9);
     grid.sync();
     prep_stamp(a, 2);
     // ---- P3: per subject: arrival order, segment, descriptor -------------------------------------------------------------------
@@ -249,20 +261,18 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepArgs a) {
         __syncthreads();
         if (!on) continue;
         const int32_t seg_begin = s_base + off;
+        prep_stamp(a, 10);
         int32_t* seg = a.po.sidx + seg_begin;
         SubjDesc d;
         d.slot = slot; d.bmask = 0; d.nr = 0; d.any_down = 0; d.tLf = 0; d.tHf = 0;
         d.pmask = 0; d.pdown = 0; d.pad0_ = 0; d.f_bLp = 0; d.f_bHp = 0; d.pseg_len = 0; d.pad1_ = 0;
         SubjWalk w, pw;
         int pn = 0, cf = 0;                                                // distinct rings of the prefix / of prefix + last batch
-        auto take = [&](int32_t e, int32_t c) {                            // the subject's e-th cell in arrival order
-            const int k = a.ring[c];
-            const uint8_t st = a.status[c];
+        auto take = [&](int32_t e, int32_t c, int k, uint8_t st, int32_t bt) {   // the subject's e-th cell in arrival order: ring, status, batch
             seg[e] = c;
             a.po.s_ring[seg_begin + e] = (uint8_t)k;
             a.po.s_status[seg_begin + e] = st;
             if (a.batch_off) {
-                const int32_t bt = batch_of_cell(a.batch_off, a.n_batches, c);
                 if (bt < a.seq_last) {                                     // a cell of the prefix (batches before the last one)
                     ++d.pseg_len;
                     if (st == RAPID_EDGE_DOWN) d.pdown = 1;
@@ -303,19 +313,44 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepArgs a) {
                     c[j - 1] = lo; c[j] = hi;
                 }
             }
+            // ring / status / batch of the cells in flight together, 16 at a time (the stores inside take() would serialise one load
+            // per cell; more than 16 at once costs too many registers)
 #pragma unroll
-            for (int q = 0; q < PREP_REG; ++q) if (q < len) take(q, c[q]);
-        } else {
-            // more cells than the register path holds (streams with re-sent duplicates; sequences of batches): the bin — and, past
-            // its capacity, the subject's cells on the shared overflow list — sorted in place (correct for any length)
-            const int32_t nb = min(len, PREP_BIN);
-            for (int q = 0; q < nb; ++q) seg[q] = a.po.bins[(size_t)slot * PREP_BIN + q];
-            if (len > PREP_BIN) {
-                int32_t at = PREP_BIN;
-                for (int32_t q = 0; q < n_ovf; ++q) {
-                    const int32_t ci = a.po.ovf[q];
-                    if (a.cell_slot[ci] == slot) seg[at++] = ci;
+            for (int h = 0; h < PREP_REG; h += 16) {
+                if (h >= len) break;
+                int rk[16];
+                uint8_t rs[16];
+                int32_t rb[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    rk[q] = h + q < len ? a.ring[c[h + q]] : 0; rs[q] = h + q < len ? a.status[c[h + q]] : 0;
+                    rb[q] = (a.batch_off && h + q < len) ? a.po.cell_batch[c[h + q]] : 0;
                 }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) if (h + q < len) take(h + q, c[h + q], rk[q], rs[q], rb[q]);
+            }
+        } else if (len <= PREP_BIN) {
+            // more cells than the register path holds (streams with re-sent duplicates; sequences of batches): sorted in the
+            // thread's local memory (L1) — sorting in place in global memory cost ~0.5 us per dependent access
+            int32_t c[PREP_BIN];
+            for (int q = 0; q < len; ++q) c[q] = a.po.bins[(size_t)slot * PREP_BIN + q];
+            for (int i = 1; i < len; ++i) {
+                const int32_t v = c[i];
+                int j = i;
+                for (; j > 0 && c[j - 1] > v; --j) c[j] = c[j - 1];
+                c[j] = v;
+            }
+            uint8_t rk[PREP_BIN], rs[PREP_BIN];
+            int32_t rb[PREP_BIN];
+            for (int q = 0; q < len; ++q) { rk[q] = a.ring[c[q]]; rs[q] = a.status[c[q]]; rb[q] = a.batch_off ? a.po.cell_batch[c[q]] : 0; }
+            for (int q = 0; q < len; ++q) take(q, c[q], rk[q], rs[q], rb[q]);
+        } else {
+            // a duplicate-heavy subject: the bin and the subject's cells on the shared overflow list, sorted in place (any length)
+            for (int q = 0; q < PREP_BIN; ++q) seg[q] = a.po.bins[(size_t)slot * PREP_BIN + q];
+            int32_t at = PREP_BIN;
+            for (int32_t q = 0; q < n_ovf; ++q) {
+                const int32_t ci = a.po.ovf[q];
+                if (a.cell_slot[ci] == slot) seg[at++] = ci;
             }
             for (int32_t gap = len >> 1; gap > 0; gap >>= 1)
                 for (int32_t i = gap; i < len; ++i) {
@@ -324,8 +359,9 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepArgs a) {
                     for (; j >= gap && seg[j - gap] > v; j -= gap) seg[j] = seg[j - gap];
                     seg[j] = v;
                 }
-            for (int32_t e = 0; e < len; ++e) take(e, seg[e]);
+            for (int32_t e = 0; e < len; ++e) { const int32_t ci = seg[e]; take(e, ci, a.ring[ci], a.status[ci], a.batch_off ? a.po.cell_batch[ci] : 0); }
         }
+        prep_stamp(a, 11);
         for (int q = d.nr; q < 16; ++q) { w.ring[q] = 0; w.time[q] = 0; }
         const int32_t id = a.slot_subject[slot];
         d.mix1 = fp_mix1(id);
