@@ -1,8 +1,20 @@
 #!/bin/bash
-# same box, same run: every variant twice, interleaved
+# same box, same run: every variant twice, interleaved (run through gpurun from the repo root after profiles/ab_build.sh)
+mkdir -p gpurun_out
 for rep in 1 2; do
-for v in mixed_b1 mixed_b8 split_b1 split_b8; do
-  RAPID_B200_LIB=$PWD/rapid_b200/variants/lib_$v.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-carried 2>&1 >/dev/null | grep "per step" | sed "s/^/c5 $v: /" | cut -c1-200
-  RAPID_B200_LIB=$PWD/rapid_b200/variants/lib_$v.so python bench.py --workload c4 --steps 10 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep "per step" | sed "s/^/c4 $v: /" | cut -c1-200
+for v in memo0 memo1; do
+  RAPID_B200_LIB=$PWD/rapid_b200/ab/lib_$v.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_c5_${v}_$rep.json 2> gpurun_out/ab_c5_${v}_$rep.err
+  RAPID_B200_LIB=$PWD/rapid_b200/ab/lib_$v.so python bench.py --workload c4 --stream batches --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_c4b_${v}_$rep.json 2> gpurun_out/ab_c4b_${v}_$rep.err
+  python - <<P
+import json
+for w in ("c5", "c4b"):
+    try:
+        d = json.loads(open("gpurun_out/ab_%s_${v}_$rep.json" % w).read().strip().splitlines()[-1])
+        rc = d.get("roofline_carried") or {}
+        print("%s ${v} rep$rep: ms/step %.3f  dominant %.3f ms frac %.3f  carried %s ms frac %s" % (
+            w, d["ms_per_step"], d["roofline"]["kernel_ms"], d["roofline"]["frac"], rc.get("kernel_ms"), rc.get("frac")))
+    except Exception as e:
+        print(w, "${v}", "failed", e)
+P
 done
 done

@@ -1,42 +1,51 @@
-"""profiles/r01_bench_results.md from the bench lines a gpurun call left in gpurun_out/bench_<G>gpu.json."""
+"""profiles/r02_bench_results.md from the bench lines kept under profiles/r02/ (copies of what gpurun calls left in gpurun_out/)."""
+import glob
 import json
 import os
-import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+D = os.path.join(ROOT, "profiles", "r02")
+
+
+def line(p):
+    with open(p) as f:
+        txt = [l for l in f.read().strip().splitlines() if l.startswith("{")]
+    return json.loads(txt[-1])
+
+
 rows = []
-for g in (1, 2, 4, 8):
-    p = os.path.join(ROOT, "gpurun_out", "bench_%dgpu.json" % g)
-    if os.path.exists(p):
-        with open(p) as f:
-            txt = f.read().strip().splitlines()
-        if txt:
-            rows.append(json.loads(txt[-1]))
-if not rows:
-    sys.exit("no bench lines")
-base = next((r for r in rows if r["n_gpus"] == 1), None)
-out = ["# Round 1 — measured on B200 (gpurun), BASELINE config 5: 1,000,000 virtual nodes, K=10 H=9 L=4, 1 % churn batch",
-       "# (%d alert cells, %d subjects); `python bench.py --gpus G --steps %d --warmup 3` (torchrun for G > 1)" % (
-           rows[0]["config"]["cells"], rows[0]["config"]["subjects"], rows[0]["steps"]),
-       "# value = cells / device time of (apply + tally), max over ranks; e2e = host arrays -> C ABI -> decision, wall clock", "",
-       "| GPUs | value (cells/s) | ms/step | e2e (cells/s) | dominant kernel ms | roofline frac (of measured %.0f GB/s) | SM MHz (median, reasons) | scaling eff. vs 1 GPU |" % rows[0]["roofline"]["peak"],
-       "|---|---|---|---|---|---|---|---|"]
-for r in rows:
-    eff = "%.2f" % (r["value"] / (base["value"] * r["n_gpus"])) if base else "-"
+for p in sorted(glob.glob(os.path.join(D, "bench_*.json"))):
+    name = os.path.basename(p)[6:-5]
+    if name == "ref":
+        continue
+    rows.append((name, line(p)))
+order = {"c5": 0, "c4": 1, "c3": 2, "c2": 3}
+rows.sort(key=lambda r: (order.get(r[0].split("_")[0], 9), r[1]["n_gpus"], r[0]))
+out = ["# Round 2 — bench.py lines measured on B200 through gpurun (the JSON lines themselves: profiles/r02/bench_*.json)",
+       "",
+       "`value` = cells / device time per step (one device-side stopwatch over all K steps: kernels, epoch resets, the one host",
+       "sync per step, idle gaps; max over ranks); `e2e` = host arrays -> C ABI -> decision on the host, wall clock.",
+       "",
+       "| file | workload | GPUs | cells | value (cells/s) | ms/step | e2e (cells/s) | dominant kernel | ms | frac of measured HBM peak | launches/step | SM MHz |",
+       "|---|---|---|---|---|---|---|---|---|---|---|---|"]
+for name, r in rows:
+    rf = r["roofline"]
     clk = r.get("clocks") or {}
-    out.append("| %d | %.2e | %.3f | %.2e | %.3f | %.3f | %s %s | %s |" % (
-        r["n_gpus"], r["value"], r["ms_per_step"], r["e2e"]["value"], r["roofline"]["kernel_ms"], r["roofline"]["frac"],
-        clk.get("sm_mhz"), clk.get("reasons"), eff))
-out += ["", "The driver's own scaling run at round end is authoritative; these are the lines this repository's last gpurun calls produced",
-        "(the 1- and 2-GPU lines after, the 4- and 8-GPU lines before `bench.py` stopped doing rank-specific work between the barrier and the",
-        "first timed step).", "",
-        "Notes on the 8-GPU line.  All eight ranks spend the same 0.57 ms in `apply` (dominant kernel 0.41 ms); seven of them then wait ~0.34 ms",
-        "(averaged over the 20 steps) inside the tally's all-reduce for ONE rank (its own tally takes 0.09 ms: it never waits).  A 2-GPU run with",
-        "per-step host timings showed the mechanism: a single step in which one rank entered ~3 ms late (work done after the barrier on that",
-        "rank only), every other step aligned to 0.1 ms — a start skew, charged to the waiting ranks' device time, not a per-step cost.  `bench.py`",
-        "now keeps the region between the barrier and the first timed step empty and reports `per_rank_ms` (host wall median / max per step,",
-        "apply and tally device time per rank) in its JSON line.  An earlier run of this round on another 8-GPU box measured",
-        "**1.38e8 cells/s at 0.72 ms/step** (efficiency 0.62) with the same kernels; the `e2e` loop of the 0.995e8 run itself ran at 0.86 ms/step."]
-with open(os.path.join(ROOT, "profiles", "r01_bench_results.md"), "w") as f:
+    out.append("| %s | %s | %d | %d | %.3e | %.3f | %.3e | %s | %.3f | %.3f | %d | %s %s |" % (
+        name, r["config"]["workload"].split(",")[0], r["n_gpus"], r["config"]["cells"], r["value"], r["ms_per_step"],
+        r["e2e"]["value"], rf["kernel"].split(" [")[0], rf["kernel_ms"], rf["frac"],
+        r["gpu_launches"] // max(1, r["steps"]), clk.get("sm_mhz"), clk.get("reasons")))
+    rc = r.get("roofline_carried")
+    if rc:
+        out.append("| | carried path (the same batch as two halves, no clear(): every row read-modify-written) | %d | | | | | %s | %.3f | %.3f | | |" % (
+            r["n_gpus"], rc["kernel"].split(" [")[0], rc["kernel_ms"], rc["frac"]))
+ref = os.path.join(D, "bench_ref.json")
+if os.path.exists(ref):
+    r = line(ref)
+    cb = r["cpu_baseline"]
+    out += ["", "CPU arm (`bench.py --impl reference`, the oracle's literal restatement, %d threads): **%.3e cells/s** on its fixed sample "
+            "(apply %.2f s + tally %.2f s); the whole-cluster extrapolation is a side field, never the value." % (
+                cb["cores"], r["value"], cb["apply_s"], cb["tally_s"])]
+with open(os.path.join(ROOT, "profiles", "r02_bench_results.md"), "w") as f:
     f.write("\n".join(out) + "\n")
 print("\n".join(out))
