@@ -50,6 +50,20 @@ namespace rapid {
 #ifndef RAPID_SPLIT_LOOP
 #define RAPID_SPLIT_LOOP 0
 #endif
+#ifndef RAPID_PF
+#define RAPID_PF 2                    // carried subjects: L2 prefetch distance (in staged subjects) of the row loads, 0 = off (A/B on one box: profiles/r02_ab_carried.md)
+#endif
+#ifndef RAPID_PF_L1
+#define RAPID_PF_L1 0                 // 1: prefetch into L1 instead of L2
+#endif
+#if RAPID_PF_L1
+#define RAPID_PF_ASM "prefetch.global.L1 [%0];"
+#else
+#define RAPID_PF_ASM "prefetch.global.L2 [%0];"
+#endif
+#ifndef RAPID_MEMO
+#define RAPID_MEMO 1                  // carried subjects: the visit of the tile's sample state is computed once per block (see k_apply_uniform)
+#endif
 
 constexpr int TILE_R = 1024;          // receivers per tile (uniform kernel: 128 threads x 8 receivers)
 constexpr int UNI_THREADS = 128;
@@ -353,6 +367,49 @@ struct StageAcc {
     uint64_t h1p, h2p;
 };
 
+template <bool SEQ>
+__device__ __forceinline__ StageAcc stage_pack(const Acc& f) {
+    StageAcc s;
+    s.nLH = f.nL | (f.nH << 16); s.tpUn = f.tp | (f.nUn << 16); s.fl = f.flags; s.minTH = f.minTH; s.minTLun = f.minTLun;
+    s.h1 = f.h1; s.h2 = f.h2;
+    s.nLHp = SEQ ? f.nLp | (f.nHp << 16) : 0u; s.tpc = SEQ ? f.tpc : 0u; s.minBHp = SEQ ? f.minBHp : T32_NONE;
+    s.minBLlong = SEQ ? f.minBLlong : T32_NONE; s.h1p = SEQ ? f.h1p : 0ull; s.h2p = SEQ ? f.h2p : 0ull;
+    return s;
+}
+// reduction of one record per lane over the warp (the result is valid in lane 0)
+template <bool SEQ>
+__device__ __forceinline__ StageAcc stage_reduce(StageAcc s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s.nLH += __shfl_down_sync(0xffffffffu, s.nLH, o);
+        s.tpUn += __shfl_down_sync(0xffffffffu, s.tpUn, o);
+        s.fl |= __shfl_down_sync(0xffffffffu, s.fl, o);
+        s.minTH = min(s.minTH, __shfl_down_sync(0xffffffffu, s.minTH, o));
+        s.minTLun = min(s.minTLun, __shfl_down_sync(0xffffffffu, s.minTLun, o));
+        s.h1 += __shfl_down_sync(0xffffffffu, s.h1, o);
+        s.h2 += __shfl_down_sync(0xffffffffu, s.h2, o);
+        if (SEQ) {
+            s.nLHp += __shfl_down_sync(0xffffffffu, s.nLHp, o);
+            s.tpc += __shfl_down_sync(0xffffffffu, s.tpc, o);
+            s.minBHp = min(s.minBHp, __shfl_down_sync(0xffffffffu, s.minBHp, o));
+            s.minBLlong = min(s.minBLlong, __shfl_down_sync(0xffffffffu, s.minBLlong, o));
+            s.h1p += __shfl_down_sync(0xffffffffu, s.h1p, o);
+            s.h2p += __shfl_down_sync(0xffffffffu, s.h2p, o);
+        }
+    }
+    return s;
+}
+// a += the packed contribution of one subject (or of a whole stage)
+template <bool SEQ>
+__device__ __forceinline__ void acc_add(Acc& a, const StageAcc& m) {
+    a.nL += m.nLH & 0xFFFFu; a.nH += m.nLH >> 16; a.tp += m.tpUn & 0xFFFFu; a.nUn += m.tpUn >> 16; a.flags |= m.fl;
+    a.minTH = min(a.minTH, m.minTH); a.minTLun = min(a.minTLun, m.minTLun); a.h1 += m.h1; a.h2 += m.h2;
+    if (SEQ) {
+        a.nLp += m.nLHp & 0xFFFFu; a.nHp += m.nLHp >> 16; a.tpc += m.tpc; a.minBHp = min(a.minBHp, m.minBHp);
+        a.minBLlong = min(a.minBLlong, m.minBLlong); a.h1p += m.h1p; a.h2p += m.h2p;
+    }
+}
+
 // One (subject, receiver) visit: [the prefix of a sequence,] then the (last) batch.  *word_out = the state when the last batch starts.
 template <bool PERM, bool SEQ>
 __device__ __forceinline__ bool visit_acc(Acc& acc, uint32_t ur, const SubjDesc& d, const SubjWalk* w, const SubjWalk* pw, uint32_t RM, int L, int H,
@@ -420,7 +477,19 @@ __global__ void __launch_bounds__(UNI_THREADS, RAPID_UNI_MINBLOCKS) k_apply_unif
     __shared__ uint8_t s_ek[SEQ ? STAGE : 1][MAXK];
     __shared__ const uint16_t* s_erow[SEQ ? STAGE : 1][MAXK];
     __shared__ int32_t s_eob[SEQ ? STAGE : 1][MAXK];
+    // Memo of the carried subjects (RAPID_MEMO): receivers of a tile have almost always seen the same history, so warp 0 computes
+    // the visit ONCE per (block, subject) for the state the tile's first active receiver holds; a thread whose active receivers
+    // all hold exactly that state only merges the precomputed new word, and takes the stage's summed contribution at the end of the
+    // stage.  (The visit itself — the walk over the first-occurrence rings — was what kept the read-modify-write path issue-bound.)
+    __shared__ uint32_t s_mst[STAGE];         // the sample state (0xFFFFFFFF: no memo for this subject)
+    __shared__ uint32_t s_mnw[STAGE];         // the new word for that state, replicated in both half-words
+    __shared__ uint8_t s_mun[STAGE];          // the subject stays in the unstable band for that state
+    __shared__ StageAcc s_macc[STAGE];        // what one such (subject, receiver) visit contributes
+    __shared__ StageAcc s_msum;               // ... summed over the stage's memo subjects
+    __shared__ uint32_t s_mall;               // which staged subjects have a memo
+    __shared__ int s_wfirst[UNI_THREADS / 32];
 
+    constexpr bool MEMO = RAPID_MEMO && !SEQ; // (the sequence kernels keep the plain path: their visit depends on the observers' rows too)
     if (a.bc->overflow) return;               // the batch was rolled back by k_prepare
     // the number of batch subjects / the first fresh slot are only known on the device
     const int Sb = a.bc->n_batch_subj, S_before = a.bc->S_before;
@@ -452,7 +521,20 @@ __global__ void __launch_bounds__(UNI_THREADS, RAPID_UNI_MINBLOCKS) k_apply_unif
         s_facc.nLH = 0; s_facc.tpUn = 0; s_facc.fl = 0; s_facc.minTH = T32_NONE; s_facc.minTLun = T32_NONE; s_facc.h1 = 0; s_facc.h2 = 0;
         s_facc.nLHp = 0; s_facc.tpc = 0; s_facc.minBHp = T32_NONE; s_facc.minBLlong = T32_NONE; s_facc.h1p = 0; s_facc.h2p = 0;
     }
+    if (MEMO) {                                     // the tile's first active receiver
+        const int mine = act ? t * 8 + __ffs(act) - 1 : INT_MAX;
+        const int wmin = __reduce_min_sync(0xffffffffu, mine);
+        if ((t & 31) == 0) s_wfirst[t >> 5] = wmin;
+    }
     const int block_active = __syncthreads_or(act != 0);
+    int sample_r = 0;
+    if (MEMO && t < 32) {
+        int f = INT_MAX;
+#pragma unroll
+        for (int q = 0; q < UNI_THREADS / 32; ++q) f = min(f, s_wfirst[q]);
+        sample_r = f == INT_MAX ? 0 : f;
+    }
+    const size_t sample_at = (size_t)tile * TILE_R + (size_t)sample_r;
     Acc com;                                              // carried subjects: shared by all ACTIVE receivers of this thread
     bool had_exc = false;                                 // the thread's global partial slots hold per-receiver extras
     bool carried = false;                                 // this thread visited a carried subject (com is not just zeros)
@@ -462,7 +544,8 @@ __global__ void __launch_bounds__(UNI_THREADS, RAPID_UNI_MINBLOCKS) k_apply_unif
         __syncthreads();
         if (t < 32) {                                     // warp 0 stages the descriptors (STAGE == 32)
             Acc f;                                        // what this lane's FRESH subject contributes to every active receiver
-            bool heavy = false;
+            Acc m;                                        // memo: what this lane's CARRIED subject contributes for the sample state
+            bool heavy = false, memo = false;
             if (t < n) {
                 const SubjDesc d = a.desc[base + t];
                 sd[t] = d;
@@ -495,7 +578,17 @@ __global__ void __launch_bounds__(UNI_THREADS, RAPID_UNI_MINBLOCKS) k_apply_unif
                     if (!PERM) sw[t] = a.walk[base + t];
                     if (SEQ) spw[t] = a.pwalk[base + t];
                     if (fresh) s_src[t] = nullptr;
+                    if (MEMO && !fresh && !edges && block_active) {
+                        const uint32_t sst = s_src[t][sample_at];
+                        uint32_t at_last = sst;
+                        const bool mun = visit_acc<PERM, SEQ>(m, sst & RM, d, &sw[PERM ? 0 : t], &spw[SEQ ? t : 0], RM, L, H, nullptr, 0u, seq_last, &at_last);
+                        s_mst[t] = sst;
+                        s_mnw[t] = (SEQ ? (at_last | (sst & ~RM)) : sst) * 0x10001u | s_nw[t];
+                        s_mun[t] = mun ? 1 : 0;
+                        memo = true;
+                    }
                 }
+                if (MEMO) { if (!memo) s_mst[t] = 0xFFFFFFFFu; else s_macc[t] = stage_pack<SEQ>(m); }
                 // only subjects with an observer in the dictionary can receive implicit reports: the others never go on
                 // the invalidation work list (has_so is refreshed by k_prepare whenever a subject gets a slot)
                 s_unres[t] = (un && a.wl.has_so[d.slot]) ? 1 : 0;
@@ -507,38 +600,37 @@ __global__ void __launch_bounds__(UNI_THREADS, RAPID_UNI_MINBLOCKS) k_apply_unif
                 if (t == 0) s_heavy = __popc(hm);
             }
             // warp reduction of the fresh subjects' contribution
-            uint32_t nLH = f.nL | (f.nH << 16), tpUn = f.tp | (f.nUn << 16), fl = f.flags, mTH = f.minTH, mTL = f.minTLun;
-            uint64_t h1 = f.h1, h2 = f.h2;
-            uint32_t nLHp = f.nLp | (f.nHp << 16), tpc = f.tpc, mBH = f.minBHp, mBL = f.minBLlong;
-            uint64_t h1p = f.h1p, h2p = f.h2p;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                nLH += __shfl_down_sync(0xffffffffu, nLH, o);
-                tpUn += __shfl_down_sync(0xffffffffu, tpUn, o);
-                fl |= __shfl_down_sync(0xffffffffu, fl, o);
-                mTH = min(mTH, __shfl_down_sync(0xffffffffu, mTH, o));
-                mTL = min(mTL, __shfl_down_sync(0xffffffffu, mTL, o));
-                h1 += __shfl_down_sync(0xffffffffu, h1, o);
-                h2 += __shfl_down_sync(0xffffffffu, h2, o);
+            const StageAcc fr = stage_reduce<SEQ>(stage_pack<SEQ>(f));
+            if (t == 0) {
+                s_facc.nLH += fr.nLH; s_facc.tpUn += fr.tpUn; s_facc.fl |= fr.fl; s_facc.minTH = min(s_facc.minTH, fr.minTH);
+                s_facc.minTLun = min(s_facc.minTLun, fr.minTLun); s_facc.h1 += fr.h1; s_facc.h2 += fr.h2;
                 if (SEQ) {
-                    nLHp += __shfl_down_sync(0xffffffffu, nLHp, o);
-                    tpc += __shfl_down_sync(0xffffffffu, tpc, o);
-                    mBH = min(mBH, __shfl_down_sync(0xffffffffu, mBH, o));
-                    mBL = min(mBL, __shfl_down_sync(0xffffffffu, mBL, o));
-                    h1p += __shfl_down_sync(0xffffffffu, h1p, o);
-                    h2p += __shfl_down_sync(0xffffffffu, h2p, o);
+                    s_facc.nLHp += fr.nLHp; s_facc.tpc += fr.tpc; s_facc.minBHp = min(s_facc.minBHp, fr.minBHp);
+                    s_facc.minBLlong = min(s_facc.minBLlong, fr.minBLlong); s_facc.h1p += fr.h1p; s_facc.h2p += fr.h2p;
                 }
             }
-            if (t == 0) {
-                s_facc.nLH += nLH; s_facc.tpUn += tpUn; s_facc.fl |= fl; s_facc.minTH = min(s_facc.minTH, mTH);
-                s_facc.minTLun = min(s_facc.minTLun, mTL); s_facc.h1 += h1; s_facc.h2 += h2;
-                if (SEQ) {
-                    s_facc.nLHp += nLHp; s_facc.tpc += tpc; s_facc.minBHp = min(s_facc.minBHp, mBH);
-                    s_facc.minBLlong = min(s_facc.minBLlong, mBL); s_facc.h1p += h1p; s_facc.h2p += h2p;
+            if (MEMO) {
+                const unsigned mm = __ballot_sync(0xffffffffu, memo);
+                if (mm) {                                 // (warp-uniform)
+                    const StageAcc mr = stage_reduce<SEQ>(stage_pack<SEQ>(m));
+                    if (t == 0) s_msum = mr;
                 }
+                if (t == 0) s_mall = mm;
             }
         }
         __syncthreads();
+        uint32_t hit = 0;                                  // staged subjects for which this thread took the memo
+#if RAPID_PF > 0
+        // The read-modify-write path has ONE 128-bit load in flight per thread (the loop body branches on the loaded word), i.e.
+        // 16 KB per SM at 8 blocks x 128 threads — about half of what the HBM latency-bandwidth product needs.  The rows of the
+        // next RAPID_PF staged subjects are therefore pulled into L2 ahead of their loads.
+        const bool pf_on = s_heavy != 0;
+        if (pf_on) {
+#pragma unroll
+            for (int j = 0; j < RAPID_PF; ++j)
+                if (j < n && s_src[j]) asm volatile(RAPID_PF_ASM ::"l"(s_src[j] + r0));
+        }
+#endif
 #if RAPID_SPLIT_LOOP
         // fresh subjects of the stage first: write-only, in a loop of their own
 #pragma unroll 4
@@ -561,6 +653,12 @@ __global__ void __launch_bounds__(UNI_THREADS, RAPID_UNI_MINBLOCKS) k_apply_unif
             uint16_t* dst = s_dst[i];
             const uint32_t nwb = s_nw[i];
             const int ne = SEQ ? (int)s_ne[i] : 0;
+#if RAPID_PF > 0
+            if (pf_on && i + RAPID_PF < n) {
+                const uint16_t* nx = s_src[i + RAPID_PF];
+                if (nx) asm volatile(RAPID_PF_ASM ::"l"(nx + r0));
+            }
+#endif
             if (src == nullptr && ne == 0) {               // fresh subject: write-only
                 *reinterpret_cast<uint4*>(dst + r0) = make_uint4(nwb & am[0], nwb & am[1], nwb & am[2], nwb & am[3]);
                 continue;
@@ -576,11 +674,12 @@ __global__ void __launch_bounds__(UNI_THREADS, RAPID_UNI_MINBLOCKS) k_apply_unif
                 const uint32_t andv = andw & (andw >> 16) & 0xFFFFu, st = (orw | (orw >> 16)) & 0xFFFFu;
                 carried = true;
                 bool same = andv == st;
+                const bool mhit = MEMO && same && st == s_mst[i];   // (subjects with edges have no memo)
                 // SEQ, subject with dictionary observers: their state (and seenLinkDownEvents) must be the same across the thread's
                 // active receivers too, or every receiver is visited on its own
                 uint32_t u[MAXK];
                 uint32_t umask = 0;
-                if (SEQ && ne) {
+                if (SEQ && ne && !mhit) {
                     const uint32_t sact = seen & act;
                     same = same && (sact == 0 || sact == act);
                     const uint32_t bDown = sact ? 0u : (a.bc->seq_down == INT_MAX ? T32_NONE : (uint32_t)a.bc->seq_down);
@@ -599,7 +698,15 @@ __global__ void __launch_bounds__(UNI_THREADS, RAPID_UNI_MINBLOCKS) k_apply_unif
                         umask |= 1u << k;
                     }
                 }
-                if (same) {
+                if (mhit) {                                // the tile's common state: everything is precomputed
+                    hit |= 1u << i;
+                    unres = s_mun[i] != 0;
+                    const uint32_t nw = s_mnw[i];
+                    w.x = (w.x & ~am[0]) | (nw & am[0]);
+                    w.y = (w.y & ~am[1]) | (nw & am[1]);
+                    w.z = (w.z & ~am[2]) | (nw & am[2]);
+                    w.w = (w.w & ~am[3]) | (nw & am[3]);
+                } else if (same) {
                     uint32_t at_last = st;
                     unres = visit_acc<PERM, SEQ>(com, st & RM, d, &sw[PERM ? 0 : i], &spw[SEQ ? i : 0], RM, L, H, u, umask, seq_last, &at_last);
                     const uint32_t nw = (SEQ ? (at_last | (st & ~RM)) : st) * 0x10001u | nwb;
@@ -631,6 +738,10 @@ __global__ void __launch_bounds__(UNI_THREADS, RAPID_UNI_MINBLOCKS) k_apply_unif
             }
             *reinterpret_cast<uint4*>(dst + r0) = w;       // the non-current row becomes the new state
             if (__any_sync(0xffffffffu, unres) && (t & 31) == 0 && s_unres[i] == 0) s_unres[i] = 1;
+        }
+        if (MEMO && hit) {                           // the memo subjects this thread met: usually all of the stage's
+            if (hit == s_mall) acc_add<SEQ>(com, s_msum);
+            else for (uint32_t mh = hit; mh; mh &= mh - 1) acc_add<SEQ>(com, s_macc[__ffs(mh) - 1]);
         }
         __syncthreads();
         if (t < n && s_unres[t] > 0) note_unresolved(a, tile, sd[t].slot);
