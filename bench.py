@@ -200,12 +200,12 @@ class Clocks:
                         "the polled GPU for ~1 ms (more than an 8-GPU step)"}
 
 
-def ncu_traffic(args, gpus):
+def ncu_traffic(args, gpus, suffix=""):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu --set full
     capture of this very configuration (profiles/traffic.json); None if that configuration was not captured."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get("%s:%d:%d" % (args.workload, args.nodes, gpus))
+            return json.load(f).get("%s:%d:%d%s" % (args.workload, args.nodes, gpus, suffix))
     except Exception:
         return None
 
@@ -642,7 +642,8 @@ def run_ours(args):
             line["roofline"]["note"] = "one launch for the whole stream; all %d subjects are first seen in it: 2 B written per (subject, receiver)" % st.subjects
         if carried is not None:
             ach2 = carried["algorithmic_bytes_per_launch"] / (carried["kernel_ms"] * 1e-3) / 1e9
-            carried.update({"bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak})
+            carried.update({"bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak,
+                            "traffic": ncu_traffic(args, G, ":carried")})
             line["roofline_carried"] = carried
     if G > 1:
         dist.barrier()

@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(UNI_THREADS, RAPID_UNI_MINBLOCKS) k_apply_unif
         // The read-modify-write path has ONE 128-bit load in flight per thread (the loop body branches on the loaded word), i.e.
         // 16 KB per SM at 8 blocks x 128 threads — about half of what the HBM latency-bandwidth product needs.  The rows of the
         // next RAPID_PF staged subjects are therefore pulled into L2 ahead of their loads.
-        const bool pf_on = s_heavy != 0;
+        const bool pf_on = !SEQ && s_heavy != 0;          // (the sequence kernels keep their measured code: no memo, no prefetch)
         if (pf_on) {
 #pragma unroll
             for (int j = 0; j < RAPID_PF; ++j)
