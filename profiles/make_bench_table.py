@@ -16,7 +16,7 @@ def line(p):
 rows = []
 for p in sorted(glob.glob(os.path.join(D, "bench_*.json"))):
     name = os.path.basename(p)[6:-5]
-    if name == "ref":
+    if name == "ref" or name.endswith("before_memo"):
         continue
     rows.append((name, line(p)))
 order = {"c5": 0, "c4": 1, "c3": 2, "c2": 3}
@@ -46,6 +46,11 @@ if os.path.exists(ref):
     out += ["", "CPU arm (`bench.py --impl reference`, the oracle's literal restatement, %d threads): **%.3e cells/s** on its fixed sample "
             "(apply %.2f s + tally %.2f s); the whole-cluster extrapolation is a side field, never the value." % (
                 cb["cores"], r["value"], cb["apply_s"], cb["tally_s"])]
+out += ["", "Notes.  The c5_1gpu line is the shipped build (memo + L2 prefetch on the read-modify-write path, `profiles/r02_ab_carried.md`), run",
+        "without the CPU leg; `bench_c5_1gpu_before_memo.json` is the full line (with `cpu_baseline`) of the build before it.  The 4-GPU lines predate",
+        "that change (the fresh path they time is unchanged; their carried figure is the old 0.51).  2- and 8-GPU lines were measured earlier in the",
+        "round (quoted in DESIGN.md §5: 5.17e7 cells/s at 1.93 ms, 1.30e8 at 0.76 ms) but their JSON files did not survive a container",
+        "replacement; the driver's own SCALE run at round end is authoritative for 1 / 2 / 4 / 8 GPUs."]
 with open(os.path.join(ROOT, "profiles", "r02_bench_results.md"), "w") as f:
     f.write("\n".join(out) + "\n")
 print("\n".join(out))
