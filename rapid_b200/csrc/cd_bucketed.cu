@@ -21,16 +21,20 @@
 // "Moments" are cell indices for uniform delivery and the receiver's own permutation keys for PERMUTED delivery,
 // so a per-receiver order needs no per-receiver sort.
 //
-// A batch is THREE launches with no host round trip between them (cd_prepare.cu's k_prepare, then the two below); the
+// A batch is a fixed chain of launches with no host round trip between them (cd_prepare.cu's k_prepare, then the kernels below); the
 // host learns the outcome from a snapshot of the device counters at its next synchronisation point:
-//   k_apply_uniform<PERM>  SWAR, 8 receivers per thread, 128-bit loads/stores, write-only fresh-subject path.  PERM = every
-//                          receiver gets every cell but in its OWN order (RAPID_DELIVERY_PERMUTED): the new state and all the
-//                          crossing COUNTS do not depend on the order, so the kernel is the uniform one minus the moments;
-//                          the (rare) receivers whose classification needs their own t_L / t_H get them from a second,
-//                          per-receiver pass over the pre-batch rows inside k_resolve.
+//   k_apply_uniform<PERM, SEQ>  SWAR, 8 receivers per thread, 128-bit loads/stores, write-only fresh-subject path, per-block memo +
+//                          L2 prefetch on the read-modify-write path.  PERM = every receiver gets every cell but in its OWN order
+//                          (RAPID_DELIVERY_PERMUTED): the new state and all the crossing COUNTS do not depend on the order, so the
+//                          kernel is the uniform one minus the moments; the (rare) receivers whose classification needs their own
+//                          t_L / t_H get them from a per-receiver pass over the pre-batch rows inside k_mixed_flip.  SEQ = a sequence
+//                          of batches in one pass (rapid_cd_apply_batches), checked per receiver by k_seq_check.
 //   k_apply_generic        one receiver per thread: per-receiver delivery bitmaps (with or without a permuted order)
-//   k_resolve              cooperative: finalize1 -> [moments on demand] -> [interval analysis to its fixpoint] -> row flip ->
-//                          invalidateFailingEdges over the work list -> finalize2 -> [bit-15 marks] -> counter snapshot.
+//   k_finalize1            classification per receiver (EMIT_ALL / NOEMIT / MIXED) from the partial accumulators
+//   k_mixed_flip           cooperative, always launched: [moments on demand] -> [interval analysis to its fixpoint] -> row flip
+//   k_inval_finalize2      invalidateFailingEdges over the work list + the receivers' closing bookkeeping
+//   k_marks                cooperative, returns at once unless some receiver went through the interval analysis: bit-15 marks,
+//                          counter snapshot
 #include <cooperative_groups.h>
 
 #include <algorithm>
