@@ -44,8 +44,9 @@ class ScenarioCluster:
                 out[o] = msgs
         return out
 
-    def detection_round(self, blacklist, dead, ticks=2):
-        """-> the decided cut (list of tags) or None if nobody proposed"""
+    def detection_round(self, blacklist, dead, ticks=2, source=None):
+        """-> the decided cut (list of tags) or None if nobody proposed.  `source(cfg)` -> {sender: [AlertMessage]} of one batching
+        window; default: the static detector over `blacklist`."""
         orc, view = self.orc, self.w.view
         cfg = view.getCurrentConfigurationId()
         N = view.getMembershipSize()
@@ -53,7 +54,7 @@ class ScenarioCluster:
         handlers = {m: orc.AlertBatchHandler(view, K, H, L) for m in live}
         proposals = {}
         for _ in range(ticks):
-            batches = self.sender_batches(blacklist, dead, cfg)
+            batches = source(cfg) if source else self.sender_batches(blacklist, dead, cfg)
             for r in live:
                 order = list(batches)
                 self.rng.shuffle(order)                            # UnicastToAllBroadcaster shuffles; arrival order is per receiver
@@ -191,6 +192,35 @@ def test_fail_ten_random_nodes_that_stay_alive(orc, seed):                      
     members = c.run(blacklist=failing, dead=[])
     assert members == [m for m in range(n) if m not in failing]
     assert c.w.view.getMembershipSize() == n - f
+
+
+def test_inject_asymmetric_drops(orc):                                           # :342-360
+    """Ten nodes drop the first probes they receive (ingress only: their own probes and alerts still flow), the REAL detector
+    (PingPongFailureDetector.java:38-121) does the rest: ten failed probes per edge, the notification on the eleventh run — by
+    then the subjects answer again, which no longer matters (:71-79) — one AlertMessage per detector, and the cut removes nodes
+    that are alive and voting."""
+    n, f = 50, 10
+    failing = random_hosts(n, f, seed=12, lo=1)
+    c = ScenarioCluster(orc, n, seed=12)
+    fd = orc.FdSim(c.w.view, K, np.arange(n))
+    cfg0 = c.w.view.getCurrentConfigurationId()
+    flags = np.zeros(n, np.uint8)
+    flags[failing] = orc.FD_INGRESS_BLOCKED
+    for _ in range(10):
+        assert fd.tick(flags, cfg0) == []                                       # failures are counted, nobody is notified yet
+    flags[:] = 0                                                                 # the interceptor has used up its drops
+
+    def window(cfg):
+        out = {}
+        for o, s_, rings in fd.tick(flags, cfg):
+            out.setdefault(o, []).append((o, s_, DOWN, cfg, rings))
+        return out
+
+    cut = c.detection_round(set(failing), set(), ticks=2, source=window)        # second window: every detector has notified, no alerts
+    assert sorted(cut) == failing
+    c.apply_cut(cut)
+    assert c.w.view.getMembershipSize() == n - f and c.members == [m for m in range(n) if m not in failing]
+    assert c.fast_decisions == 1                                                 # all 50 processes are alive and vote
 
 
 def test_the_cut_of_a_round_is_what_a_single_detector_computes(orc):
