@@ -57,6 +57,9 @@ namespace rapid {
 #ifndef RAPID_PF
 #define RAPID_PF 2                    // carried subjects: L2 prefetch distance (in staged subjects) of the row loads, 0 = off (A/B on one box: profiles/r02_ab_carried.md)
 #endif
+#ifndef RAPID_INVAL_SPLIT
+#define RAPID_INVAL_SPLIT 0           // 1: k_inval_finalize2 splits the work list of a tile over several blocks (small clusters)
+#endif
 #ifndef RAPID_PF_L1
 #define RAPID_PF_L1 0                 // 1: prefetch into L1 instead of L2
 #endif
@@ -138,6 +141,10 @@ struct Bucketed {
     DevBuf<int32_t> mx_changed;               // [4] rotating "the component grew" counters of the fixpoint loop
     DevBuf<uint32_t> mx_dev;                  // [Rpad / 32]
     DevBuf<int32_t> batch_index;              // [slot] -> index of the subject in the batch in flight
+#if RAPID_INVAL_SPLIT
+    DevBuf<int32_t> inv_res, inv_ticket;      // [Rpad] / [n_tiles] hand-over of k_inval_finalize2's blocks (all zero between launches)
+    DevBuf<unsigned long long> inv_h1, inv_h2;
+#endif
     // invalidation work list (WorkList)
     DevBuf<int32_t> wl_slots, wl_count, wl_listed, wl_so_tab;
     DevBuf<uint8_t> wl_in_tile;               // [slot][n_tiles]
@@ -1006,6 +1013,13 @@ struct ResolveArgs {
     const int32_t* touch;
     const int32_t* batch_index;
     int32_t serial;
+#if RAPID_INVAL_SPLIT
+    int inv_split;                // blocks per 1024-receiver tile in k_inval_finalize2 (1: a block walks the whole work list)
+    int32_t* inv_res;             // [Rpad] subjects raised to >= H by the pass, summed over the blocks of a tile
+    unsigned long long* inv_h1;   // [Rpad] their fingerprint sums
+    unsigned long long* inv_h2;
+    int32_t* inv_ticket;          // [n_tiles] blocks of the tile that have handed their part over
+#endif
 };
 
 __device__ __forceinline__ int32_t block_sum_i32(int32_t v, int32_t* s_red) {      // every thread gets the block total
@@ -1364,7 +1378,23 @@ __device__ void phase_inval_finalize2(const ResolveArgs& e, int mixed, InvSmem& 
     const int t = threadIdx.x;
     const int n_list = min(*(volatile int32_t*)a.wl.count, a.wl.cap);
     int32_t my_inval = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+#if RAPID_INVAL_SPLIT
+    // Small clusters have few tiles and one block per tile would walk the whole list alone (C3: 10 blocks x ~125 dependent
+    // iterations = 350 us).  The pass is independent per subject — an observer's membership in proposal U preProposal does not
+    // change while it runs (implicit reports only move subjects from the band to >= H) — so P blocks share a tile: each takes a
+    // contiguous part of the list, adds what it raised to per-receiver accumulators, and the last one to finish closes the receivers.
+    const int P = MX ? 1 : max(1, e.inv_split);
+    __shared__ int s_fin;
+#else
+    constexpr int P = 1;
+#endif
+    for (int tb = blockIdx.x; tb < a.n_tiles * P; tb += gridDim.x) {
+        const int tile = P > 1 ? tb % a.n_tiles : tb;
+        int lo = 0, hi = n_list;
+        if (P > 1) {
+            const int per = max(8, (n_list + P - 1) / P);
+            lo = min(n_list, (tb / a.n_tiles) * per); hi = min(n_list, lo + per);
+        }
         const int64_t rb = (int64_t)tile * TILE_R + (int64_t)t * 4;
         const uint4 rf4 = *reinterpret_cast<const uint4*>(e.rflags + rb);          // rows and flags are padded to whole tiles
         uint32_t flags[4] = {rf4.x, rf4.y, rf4.z, rf4.w};
@@ -1380,8 +1410,8 @@ __device__ void phase_inval_finalize2(const ResolveArgs& e, int mixed, InvSmem& 
         int32_t res[4] = {0, 0, 0, 0};
         uint64_t kh1[4] = {0, 0, 0, 0}, kh2[4] = {0, 0, 0, 0};
         if (n_list > 0 && __syncthreads_or(any_k3 ? 1 : 0)) {
-            for (int base = 0; base < n_list; base += INV_STAGE) {
-                const int n = min(INV_STAGE, n_list - base);
+            for (int base = lo; base < hi; base += INV_STAGE) {
+                const int n = min(INV_STAGE, hi - base);
                 __syncthreads();
                 if (t == 0) sm.n_dense = 0;
                 __syncthreads();
@@ -1470,6 +1500,26 @@ __device__ void phase_inval_finalize2(const ResolveArgs& e, int mixed, InvSmem& 
                 }
             }
         }
+#if RAPID_INVAL_SPLIT
+        if (P > 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (res[j] > 0) { atomicAdd(&e.inv_res[rb + j], res[j]); atomicAdd(&e.inv_h1[rb + j], (unsigned long long)kh1[j]); atomicAdd(&e.inv_h2[rb + j], (unsigned long long)kh2[j]); }
+            __threadfence();
+            __syncthreads();
+            if (t == 0) s_fin = atomicAdd(&e.inv_ticket[tile], 1) == P - 1 ? 1 : 0;
+            __syncthreads();
+            if (!s_fin) continue;                             // a later block of the tile closes its receivers
+            __threadfence();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                res[j] = atomicExch(&e.inv_res[rb + j], 0);   // (and the accumulators are all zero again)
+                kh1[j] = 0; kh2[j] = 0;
+                if (res[j] > 0) { kh1[j] = atomicExch(&e.inv_h1[rb + j], 0ull); kh2[j] = atomicExch(&e.inv_h2[rb + j], 0ull); }
+            }
+            if (t == 0) e.inv_ticket[tile] = 0;
+        }
+#endif
         // ---- finalize2: emissions of the invalidation pass, announced flags --------------------------------------------------
         uint32_t ann = 0;
         bool touched = false;
@@ -2068,6 +2118,19 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, bool seq) {
     ra.mx_e1 = b->mx_e1.p; ra.mx_e2 = b->mx_e2.p; ra.mx_ec = b->mx_ec.p; ra.mx_changed = b->mx_changed.p; ra.mx_dev = b->mx_dev.p;
     ra.slot_of = cd->slot_of.p; ra.obs = cd->view->obs.p; ra.touch = cd->touch.p; ra.batch_index = b->batch_index.p;
     ra.serial = cd->batch_serial;
+#if RAPID_INVAL_SPLIT
+    // blocks per tile of the invalidation pass: enough to fill the device twice over when the tiles alone do not
+    const int inv_split = b->n_tiles >= 148 ? 1 : std::min(32, (296 + std::max(b->n_tiles, 1) - 1) / std::max(b->n_tiles, 1));
+    if (inv_split > 1 && !b->inv_res.p) {
+        RAPID_CHECK(b->inv_res.reserve(cd->Rpad)); RAPID_CHECK(b->inv_h1.reserve(cd->Rpad)); RAPID_CHECK(b->inv_h2.reserve(cd->Rpad));
+        RAPID_CHECK(b->inv_ticket.reserve((size_t)std::max(b->n_tiles, 1)));
+        RAPID_CUDA(cudaMemsetAsync(b->inv_res.p, 0, cd->Rpad * sizeof(int32_t), s));
+        RAPID_CUDA(cudaMemsetAsync(b->inv_h1.p, 0, cd->Rpad * sizeof(unsigned long long), s));
+        RAPID_CUDA(cudaMemsetAsync(b->inv_h2.p, 0, cd->Rpad * sizeof(unsigned long long), s));
+        RAPID_CUDA(cudaMemsetAsync(b->inv_ticket.p, 0, (size_t)std::max(b->n_tiles, 1) * sizeof(int32_t), s));
+    }
+    ra.inv_split = inv_split; ra.inv_res = b->inv_res.p; ra.inv_h1 = b->inv_h1.p; ra.inv_h2 = b->inv_h2.p; ra.inv_ticket = b->inv_ticket.p;
+#endif
     const unsigned rblocks = (unsigned)(cd->Rpad / GEN_THREADS);
     const int cgrid = std::max(1, std::min(b->resolve_grid, std::max(32, 4 * (int)rblocks)));      // co-resident (cooperative) grids
     RAPID_CHECK(b->ra_dev.reserve(sizeof(ResolveArgs)));
@@ -2085,7 +2148,11 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, bool seq) {
     k_finalize1<<<rblocks, GEN_THREADS, 0, s>>>(ga);
     RAPID_KERNEL_CHECK();
     RAPID_CUDA(cudaLaunchCooperativeKernel((void*)k_mixed_flip, dim3((unsigned)cgrid), dim3(GEN_THREADS), args, 0, s));
+#if RAPID_INVAL_SPLIT
+    k_inval_finalize2<<<(unsigned)(std::max(b->n_tiles, 1) * inv_split), GEN_THREADS, 0, s>>>(ga);
+#else
     k_inval_finalize2<<<(unsigned)std::max(b->n_tiles, 1), GEN_THREADS, 0, s>>>(ga);
+#endif
     RAPID_KERNEL_CHECK();
     RAPID_CUDA(cudaLaunchCooperativeKernel((void*)k_marks, dim3((unsigned)cgrid), dim3(GEN_THREADS), args, 0, s));
     cd->last_launches += 5;
