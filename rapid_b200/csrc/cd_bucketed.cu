@@ -58,7 +58,7 @@ namespace rapid {
 #define RAPID_PF 2                    // carried subjects: L2 prefetch distance (in staged subjects) of the row loads, 0 = off (A/B on one box: profiles/r02_ab_carried.md)
 #endif
 #ifndef RAPID_INVAL_SPLIT
-#define RAPID_INVAL_SPLIT 0           // 1: k_inval_finalize2 splits the work list of a tile over several blocks (small clusters)
+#define RAPID_INVAL_SPLIT 1           // k_inval_finalize2 splits the work list of a tile over several blocks (small clusters); 0 = one block per tile
 #endif
 #ifndef RAPID_PF_L1
 #define RAPID_PF_L1 0                 // 1: prefetch into L1 instead of L2
@@ -2119,8 +2119,10 @@ int32_t bucketed_apply(CD* cd, int64_t A, const DeliveryDev& dl, bool seq) {
     ra.slot_of = cd->slot_of.p; ra.obs = cd->view->obs.p; ra.touch = cd->touch.p; ra.batch_index = b->batch_index.p;
     ra.serial = cd->batch_serial;
 #if RAPID_INVAL_SPLIT
-    // blocks per tile of the invalidation pass: enough to fill the device twice over when the tiles alone do not
-    const int inv_split = b->n_tiles >= 148 ? 1 : std::min(32, (296 + std::max(b->n_tiles, 1) - 1) / std::max(b->n_tiles, 1));
+    // blocks per tile of the invalidation pass: enough to fill the device twice over when the tiles alone are far from it.
+    // Measured on one B200 (profiles/r02_ab_inval_split.md): C3, 10 tiles x 30 blocks, step 0.484 -> 0.209 ms; at 122 tiles (the
+    // C5 shard of an 8-GPU run) 3 blocks per tile cost 5 us more than one, hence the threshold.
+    const int inv_split = b->n_tiles >= 64 ? 1 : std::min(32, (296 + std::max(b->n_tiles, 1) - 1) / std::max(b->n_tiles, 1));
     if (inv_split > 1 && !b->inv_res.p) {
         RAPID_CHECK(b->inv_res.reserve(cd->Rpad)); RAPID_CHECK(b->inv_h1.reserve(cd->Rpad)); RAPID_CHECK(b->inv_h2.reserve(cd->Rpad));
         RAPID_CHECK(b->inv_ticket.reserve((size_t)std::max(b->n_tiles, 1)));
