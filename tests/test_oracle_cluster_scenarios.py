@@ -17,16 +17,18 @@ import numpy as np
 import pytest
 
 from helpers import OracleWorld
+from rapid_b200 import workloads as W
 
 K, H, L = 10, 9, 4                                                 # Cluster.java:72-74
-DOWN = 1
+UP, DOWN = 0, 1
 
 
 class ScenarioCluster:
-    def __init__(self, orc, n, seed):
+    def __init__(self, orc, n, seed, n_joiners=0):
         self.orc, self.n, self.rng = orc, n, random.Random(seed)
-        self.w = OracleWorld(orc, n, K)
+        self.w = OracleWorld(orc, n, K, n_joiners=n_joiners)
         self.members = list(range(n))
+        self.joiner_ids = W.node_ids(n, n_joiners)
         self.rounds, self.fast_decisions, self.classic_decisions = 0, 0, 0
 
     # one failure-detector interval: every live member's K edge detectors (one per entry of getSubjectsOf, :697-707) fire for the
@@ -42,6 +44,17 @@ class ScenarioCluster:
                     msgs.append((o, s, DOWN, cfg, self.w.view.getRingNumbers(o, s)))
             if msgs:
                 out[o] = msgs
+        return out
+
+    # join phase 2 (MembershipService.java:240-281): the joiner asked its K expected observers of THIS configuration; each live one
+    # enqueues an UP alert with the ring numbers the joiner named for it
+    def join_alerts(self, joiners, dead, cfg, out):
+        for j in joiners:
+            exp = self.w.view.getExpectedObserversOf(j)
+            for o in sorted(set(exp)):
+                if o in dead:
+                    continue
+                out.setdefault(o, []).append((o, j, UP, cfg, [k for k in range(K) if exp[k] == o]))
         return out
 
     def detection_round(self, blacklist, dead, ticks=2, source=None):
@@ -131,9 +144,13 @@ class ScenarioCluster:
 
     def apply_cut(self, cut):                                      # decideViewChange :385-444
         for t in cut:
-            assert self.w.view.isHostPresent(t)
-            self.w.view.ringDelete(t)
-            self.members.remove(t)
+            if self.w.view.isHostPresent(t):
+                self.w.view.ringDelete(t)
+                self.members.remove(t)
+            else:                                                  # a joiner: ringAdd with the NodeId its UP alerts carried
+                j = t - self.n
+                self.w.view.ringAdd(t, (int(self.joiner_ids[0][j]), int(self.joiner_ids[1][j])))
+                self.members.append(t)
 
     def run(self, blacklist, dead, max_rounds=12):
         blacklist, dead = set(blacklist), set(dead)
@@ -192,6 +209,40 @@ def test_fail_ten_random_nodes_that_stay_alive(orc, seed):                      
     members = c.run(blacklist=failing, dead=[])
     assert members == [m for m in range(n) if m not in failing]
     assert c.w.view.getMembershipSize() == n - f
+
+
+@pytest.mark.parametrize("seed", [13, 14, 15])
+def test_concurrent_node_joins_and_fails(orc, seed):                             # :228-243
+    """30 nodes, 5 of them fail while 10 others join: DOWN alerts from the live observers of the failed nodes and UP alerts from
+    the joiners' live expected observers travel in the same windows.  A joiner that is not admitted by a view change asks again in
+    the next configuration (new expected observers), exactly like a failed node keeps being reported — until the membership is
+    the 35 nodes ClusterTest waits for."""
+    n, f, nj = 30, 5, 10
+    failing = list(range(2, 2 + f))                                              # basePort + 2 .. (the seed node stays)
+    joiners = list(range(n, n + nj))
+    c = ScenarioCluster(orc, n, seed, n_joiners=nj)
+    dead, blacklist = set(failing), set(failing)
+    while (blacklist & set(c.members)) or (set(joiners) - set(c.members)):
+        assert c.rounds < 12, "no convergence"
+        pending = [j for j in joiners if j not in c.members]
+
+        def window(cfg, first=[True]):
+            out = c.sender_batches(blacklist, dead, cfg)
+            if first[0]:                                                         # a join attempt is one message per observer, not a tick
+                c.join_alerts(pending, dead, cfg, out)
+                first[0] = False
+            return out
+
+        cut = c.detection_round(blacklist, dead, ticks=2, source=window)
+        c.rounds += 1
+        assert cut and set(cut) <= blacklist | set(joiners)
+        c.apply_cut(cut)
+    assert sorted(c.members) == sorted([m for m in range(n) if m not in failing] + joiners)
+    assert c.w.view.getMembershipSize() == n - f + nj
+    for j in joiners:                                                            # identifiersSeen: the same NodeId can never join again
+        with pytest.raises(orc.UUIDAlreadySeenException):
+            c.w.view.ringDelete(j) or c.w.view.ringAdd(j, (int(c.joiner_ids[0][j - n]), int(c.joiner_ids[1][j - n])))
+        c.w.view.ringAdd(j, (int(c.joiner_ids[0][j - n]) ^ 1, int(c.joiner_ids[1][j - n])))
 
 
 def test_inject_asymmetric_drops(orc):                                           # :342-360
