@@ -144,3 +144,141 @@ class PyFastPaxos:
             self.decided, self.decision = True, list(endpoints)
             return True
         return False
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# MembershipView.java restated a second time: python-xxhash (an XXH64 implementation that shares no code with oracle/xxh64.h),
+# sorted Python lists for the TreeSets.  Same READING of zero-allocation-hashing as the oracle (hashInt / hashLong = XXH64 of the
+# little-endian 4 / 8 bytes, hashBytes = XXH64 of the hostname bytes) — that reading stays unpinned; what this
+# catches is an implementation slip on either side.
+# ----------------------------------------------------------------------------------------------------------------------------
+import bisect
+import struct
+
+M64 = (1 << 64) - 1
+
+
+def _s64(x):
+    x &= M64
+    return x - (1 << 64) if x >> 63 else x
+
+
+class PyMembershipView:
+    def __init__(self, K, endpoints=(), node_ids=()):
+        """endpoints: list of (tag, hostname bytes, port); node_ids: list of (high, low) signed 64-bit"""
+        import xxhash
+        self._xx = xxhash.xxh64_intdigest
+        self.K = K
+        self.ep = {}                                               # tag -> (hostname, port)
+        self.rings = [[] for _ in range(K)]                        # sorted [(signed key, tag)]
+        self.keys = {}                                             # (k, tag) -> key   (AddressComparator.hashCache)
+        self.allNodes = set()
+        self.identifiersSeen = set()
+        self.cachedObservers = {}                                  # :52 — restated WITH its invalidation rule (see ringAdd)
+        for tag, host, port in endpoints:
+            self.ep[tag] = (host, port)
+            self.allNodes.add(tag)
+            for k in range(K):
+                bisect.insort(self.rings[k], (self._key(k, tag), tag))
+        self.identifiersSeen.update(node_ids)
+
+    def know(self, tag, host, port):
+        self.ep[tag] = (host, port)
+
+    def _key(self, k, tag):                                        # AddressComparator.computeHash :577-582, seed = ring index
+        if (k, tag) not in self.keys:
+            host, port = self.ep[tag]
+            h = self._xx(host, seed=k) * 31 + self._xx(struct.pack("<i", port), seed=k)
+            self.keys[(k, tag)] = _s64(h)
+        return self.keys[(k, tag)]
+
+    def ringAdd(self, tag, node_id):                               # :123-160
+        if node_id in self.identifiersSeen:
+            raise KeyError("UUIDAlreadySeen")
+        if tag in self.allNodes:
+            raise ValueError("NodeAlreadyInRing")
+        affected = set()
+        for k in range(self.K):
+            bisect.insort(self.rings[k], (self._key(k, tag), tag))
+            low = self._lower_no_wrap(k, tag)                      # endpoints.lower(node): null at the front of the ring — the LAST
+            if low is not None:                                    # node, whose successor wraps around to the new node, keeps its
+                affected.add(low)                                  # cached list (the reference's behaviour, restated as it is)
+        self.allNodes.add(tag)
+        for t in affected:
+            self.cachedObservers.pop(t, None)
+        self.identifiersSeen.add(node_id)
+
+    def ringDelete(self, tag):                                     # :167-201
+        if tag not in self.allNodes:
+            raise LookupError("NodeNotInRing")
+        affected = set()
+        for k in range(self.K):
+            low = self._lower_no_wrap(k, tag)
+            if low is not None:
+                affected.add(low)
+            self.rings[k].remove((self._key(k, tag), tag))
+            self.cachedObservers.pop(tag, None)
+        self.allNodes.discard(tag)
+        for t in affected:
+            self.cachedObservers.pop(t, None)
+
+    def _lower_no_wrap(self, k, tag):
+        ring = self.rings[k]
+        i = bisect.bisect_left(ring, (self._key(k, tag), tag))
+        return ring[i - 1][1] if i > 0 else None
+
+    def _neighbour(self, k, tag, step):
+        ring = self.rings[k]
+        key = (self._key(k, tag), tag)
+        if step > 0:                                               # higher(node), else first()
+            i = bisect.bisect_right(ring, key)
+            return ring[i][1] if i < len(ring) else ring[0][1]
+        i = bisect.bisect_left(ring, key)                          # lower(node), else last()
+        return ring[i - 1][1] if i > 0 else ring[-1][1]
+
+    def getObserversOf(self, tag):                                 # :210-257
+        if tag not in self.allNodes:
+            raise LookupError("NodeNotInRing")
+        if tag not in self.cachedObservers:
+            self.cachedObservers[tag] = self.computeObserversOf(tag)
+        return self.cachedObservers[tag]
+
+    def computeObserversOf(self, tag):                             # :234-257
+        if len(self.rings[0]) <= 1:
+            return []
+        return [self._neighbour(k, tag, +1) for k in range(self.K)]
+
+    def getSubjectsOf(self, tag):                                  # :267-282
+        if tag not in self.allNodes:
+            raise LookupError("NodeNotInRing")
+        if len(self.rings[0]) <= 1:
+            return []
+        return [self._neighbour(k, tag, -1) for k in range(self.K)]
+
+    def getExpectedObserversOf(self, tag):                         # :292-303 (predecessors — also for a node that is not a member)
+        if not self.rings[0]:
+            return []
+        return [self._neighbour(k, tag, -1) for k in range(self.K)]
+
+    def getRingNumbers(self, observer, subject):                   # :397-418
+        return [r for r, s in enumerate(self.getSubjectsOf(observer)) if s == subject]
+
+    def getRing(self, k):
+        return [t for _, t in self.rings[k]]
+
+    def getMembershipSize(self):
+        return len(self.rings[0])
+
+    def isHostPresent(self, tag):
+        return tag in self.allNodes
+
+    def getCurrentConfigurationId(self):                           # Configuration.getConfigurationId :544-556
+        h = 1
+        for high, low in sorted(self.identifiersSeen):             # NodeIdComparator :474-500: signed (high, low)
+            h = (h * 37 + self._xx(struct.pack("<q", high), seed=0)) & M64
+            h = (h * 37 + self._xx(struct.pack("<q", low), seed=0)) & M64
+        for _, tag in self.rings[0]:
+            host, port = self.ep[tag]
+            h = (h * 37 + self._xx(host, seed=0)) & M64
+            h = (h * 37 + self._xx(struct.pack("<i", port), seed=0)) & M64
+        return _s64(h)
