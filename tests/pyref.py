@@ -282,3 +282,85 @@ class PyMembershipView:
             h = (h * 37 + self._xx(host, seed=0)) & M64
             h = (h * 37 + self._xx(struct.pack("<i", port), seed=0)) & M64
         return _s64(h)
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# Paxos.selectProposalUsingCoordinatorRule (Paxos.java:271-328), restated a second time.  msgs: [{'vrnd': (round, nodeIndex),
+# 'vval': [tags]}] in arrival order.
+# ----------------------------------------------------------------------------------------------------------------------------
+def coordinator_rule(N, msgs):
+    if not msgs:
+        raise ValueError("phase1bMessages was empty")
+    maxVrnd = max(m["vrnd"] for m in msgs)                         # compareRanks :333-339: (round, nodeIndex) lexicographic
+    collected = [tuple(m["vval"]) for m in msgs if m["vrnd"] == maxVrnd and len(m["vval"]) > 0]
+    chosen = None
+    if len(set(collected)) == 1:
+        chosen = collected[0]
+    elif len(collected) > 1:
+        counters = {}
+        for value in collected:
+            count = counters.get(value, 0)
+            if count + 1 > N // 4:
+                chosen = value
+                break
+            counters[value] = count + 1
+    if chosen is None:
+        chosen = next((tuple(m["vval"]) for m in msgs if len(m["vval"]) > 0), ())
+    return list(chosen)
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# PingPongFailureDetector.java:38-121 + one process's detectors (MembershipService.java:697-707) + the AlertMessage of a
+# notification (:472-495), restated a second time.  A probe's outcome comes from the scenario: 'ok' | 'fail' | 'bootstrapping'.
+# ----------------------------------------------------------------------------------------------------------------------------
+FAILURE_THRESHOLD, BOOTSTRAP_COUNT_THRESHOLD = 10, 30
+
+
+class PyPingPong:
+    def __init__(self):
+        self.failureCount = 0
+        self.bootstrapResponseCount = 0
+        self.notified = False
+
+    def run(self, probe):
+        """-> True iff the notifier ran in this interval; `probe()` is only called when a probe is sent"""
+        if self.failureCount >= FAILURE_THRESHOLD and not self.notified:
+            self.notified = True
+            return True
+        outcome = probe()
+        if outcome == "fail":
+            self.failureCount += 1
+        elif outcome == "bootstrapping":
+            self.bootstrapResponseCount += 1
+            if self.bootstrapResponseCount > BOOTSTRAP_COUNT_THRESHOLD:
+                self.failureCount += 1
+        return False
+
+
+class PyFdCluster:
+    """every member's detectors, one per entry of getSubjectsOf(member) (duplicates included), ticked in member order"""
+    CRASHED, INGRESS_BLOCKED, EGRESS_BLOCKED, BOOTSTRAPPING = 1, 2, 4, 8
+
+    def __init__(self, view, members):
+        self.view, self.members = view, list(members)
+        self.subjects = {m: view.getSubjectsOf(m) for m in self.members}
+        self.fds = {m: [PyPingPong() for _ in self.subjects[m]] for m in self.members}
+
+    def tick(self, flags, edge_fail=None):
+        """flags[tag]: scenario bits; edge_fail[(member, detector index)]: that probe fails.  -> [(observer, subject, [rings])]"""
+        alerts = []
+        for m in self.members:
+            if flags[m] & self.CRASHED:
+                continue                                           # a crashed process runs nothing
+            for j, (fd, s) in enumerate(zip(self.fds[m], self.subjects[m])):
+                def probe():
+                    if edge_fail and edge_fail.get((m, j)):
+                        return "fail"
+                    if (flags[m] & self.EGRESS_BLOCKED) or (flags[s] & (self.CRASHED | self.INGRESS_BLOCKED)):
+                        return "fail"
+                    if flags[s] & self.BOOTSTRAPPING:
+                        return "bootstrapping"
+                    return "ok"
+                if fd.run(probe):
+                    alerts.append((m, s, self.view.getRingNumbers(m, s)))
+        return alerts
