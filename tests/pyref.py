@@ -364,3 +364,73 @@ class PyFdCluster:
                 if fd.run(probe):
                     alerts.append((m, s, self.view.getRingNumbers(m, s)))
         return alerts
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# Paxos.java:73-257 restated a second time (one object per node; handlers RETURN the message the Java hands to its broadcaster /
+# client, like the oracle's binding).  Ranks are (round, nodeIndex) tuples; my_hash stands in for myAddr.hashCode() (:102).
+# ----------------------------------------------------------------------------------------------------------------------------
+class PyPaxos:
+    def __init__(self, my_tag, my_hash, configurationId, N):
+        self.me, self.my_hash, self.cfg, self.N = my_tag, my_hash, configurationId, N
+        self.rnd = self.vrnd = self.crnd = (0, 0)
+        self.vval, self.cval = [], []
+        self.phase1bMessages = []
+        self.acceptResponses = {}
+        self.decided, self.decision = False, None
+
+    def startPhase1a(self, round_):                                # :98-113
+        if self.crnd[0] > round_:
+            return None
+        self.crnd = (round_, self.my_hash)
+        return {"sender": self.me, "cfg": self.cfg, "rank": self.crnd}
+
+    def handlePhase1aMessage(self, m):                             # :120-151
+        if m["cfg"] != self.cfg:
+            return None
+        if self.rnd < tuple(m["rank"]):
+            self.rnd = tuple(m["rank"])
+        else:
+            return None
+        return {"sender": self.me, "cfg": self.cfg, "rnd": self.rnd, "vrnd": self.vrnd, "vval": list(self.vval)}
+
+    def handlePhase1bMessage(self, m):                             # :159-191
+        if m["cfg"] != self.cfg:
+            return None
+        if self.crnd != tuple(m["rnd"]):
+            return None
+        self.phase1bMessages.append({"vrnd": tuple(m["vrnd"]), "vval": list(m["vval"])})
+        if len(self.phase1bMessages) > self.N // 2:
+            chosen = coordinator_rule(self.N, self.phase1bMessages)
+            if self.crnd == tuple(m["rnd"]) and not self.cval and chosen:
+                self.cval = chosen
+                return {"sender": self.me, "cfg": self.cfg, "rnd": self.crnd, "vval": list(chosen)}
+        return None
+
+    def handlePhase2aMessage(self, m):                             # :198-216
+        if m["cfg"] != self.cfg:
+            return None
+        r = tuple(m["rnd"])
+        if self.rnd <= r and self.vrnd != r:
+            self.rnd = self.vrnd = r
+            self.vval = list(m["vval"])
+            return {"sender": self.me, "cfg": self.cfg, "rnd": r, "endpoints": list(self.vval)}
+        return None
+
+    def handlePhase2bMessage(self, m):                             # :223-236; True iff this message made the node decide
+        if m["cfg"] != self.cfg:
+            return False
+        in_rnd = self.acceptResponses.setdefault(tuple(m["rnd"]), {})
+        in_rnd[m["sender"]] = m
+        if len(in_rnd) > self.N // 2 and not self.decided:
+            self.decision = list(m["endpoints"])
+            self.decided = True
+            return True
+        return False
+
+    def registerFastRoundVote(self, vote):                         # :244-257
+        if self.rnd[0] > 1:
+            return
+        self.rnd = (1, 1)
+        self.vrnd = self.rnd
+        self.vval = list(vote)
