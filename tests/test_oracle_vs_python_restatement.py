@@ -13,6 +13,15 @@ K = 10
 HL = [(9, 4), (8, 2), (8, 3), (9, 3), (10, 1), (3, 3)]
 
 
+def same_reports(ma, mb, H):
+    """Report masks must agree — except BEYOND the high watermark.  invalidateFailingEdges walks a copy of preProposal in HashSet
+    order (MultiNodeCutDetector.java:146-147) and keeps adding implicit reports to a node after it has reached H; when the pass
+    emits in the middle (proposal.clear(), :118-119), the nodes still to be visited find nobody in proposal U preProposal any more.
+    Which of an emitted node's rings beyond the H-th were recorded therefore depends on an iteration order the reference does not
+    define — and nothing can observe it: a count above H never equals L or H again."""
+    return ma == mb or (bin(ma).count("1") >= H and bin(mb).count("1") >= H)
+
+
 def random_stream(rng, w, n, nj, cfg, n_msgs, focus):
     """alerts biased towards `focus` subjects reported by their true observers (so that watermarks are crossed), plus noise"""
     msgs = []
@@ -64,7 +73,7 @@ def test_batch_handler_streams(orc, seed):
             emitted += 1
         assert a.announced() == b.announcedProposal
         for t in range(n + nj):
-            assert a.reportMask(t) == b.cd.reportMask(t), (seed, batch, t)
+            assert same_reports(a.reportMask(t), b.cd.reportMask(t), H), (seed, batch, t)
     assert emitted >= 0
 
 
