@@ -201,6 +201,43 @@ def test_fail_random_third_of_nodes(orc, seed):                                 
     assert c.classic_decisions >= 1                                              # 34 voters < 38: the first view change needs the fallback
 
 
+def test_a_third_of_the_nodes_can_block_the_cut(orc):
+    """The same scenario with another draw (found by sweeping seeds): the detector is ALLOWED to stall.  A failed node Y whose
+    observers on two rings are failed nodes that themselves collect fewer than L reports (most of THEIR observers are dead too)
+    stops at H - 1 reports: its two silent observers are neither in proposal nor in preProposal, so invalidateFailingEdges
+    (MultiNodeCutDetector.java:147-158) has nothing to add, updatesInProgress never returns to 0 and no live node ever proposes —
+    for this configuration.  The reference behaves the same way (its test draws the failed set at random and can time out); what
+    must hold is that every live node is stuck on the SAME subject with the SAME reports."""
+    n, f, seed = 50, 16, 131
+    failing = random_hosts(n, f, seed)
+    c = ScenarioCluster(orc, n, seed)
+    view = c.w.view
+    cfg = view.getCurrentConfigurationId()
+    live = [m for m in range(n) if m not in failing]
+    handlers = {m: orc.AlertBatchHandler(view, K, H, L) for m in live}
+    for tick in range(3):                                          # the static detector keeps firing: nothing changes
+        batches = c.sender_batches(set(failing), set(failing), cfg)
+        for r in live:
+            order = list(batches)
+            c.rng.shuffle(order)
+            for o in order:
+                assert handlers[r].handleBatch(batches[o]) == []
+    def seen(r):                                                   # report counts, up to the watermark (beyond it they depend on arrival order)
+        return {s: min(H, bin(handlers[r].reportMask(s)).count("1")) for s in failing}
+    counts = seen(live[0])
+    stuck = [s for s in failing if L <= counts[s] < H]
+    dark = [s for s in failing if counts[s] < L]
+    assert stuck and dark
+    for r in live:                                                 # everyone holds the same reports
+        assert seen(r) == counts
+    for y in stuck:                                                # every missing ring of a stuck node is observed by a dark node
+        obs = view.getObserversOf(y)
+        missing = [k for k in range(K) if not (handlers[live[0]].reportMask(y) >> k) & 1]
+        assert missing and all(obs[k] in dark for k in missing)
+    with pytest.raises(AssertionError, match="nobody proposes"):
+        ScenarioCluster(orc, n, seed).run(failing, failing)
+
+
 @pytest.mark.parametrize("seed", [9, 10])
 def test_fail_ten_random_nodes_that_stay_alive(orc, seed):                       # :322-336 (the static detector only: nobody shuts down)
     n, f = 50, 10
